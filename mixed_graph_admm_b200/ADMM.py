@@ -1,0 +1,570 @@
+"""Drop-in for the reference's ``ADMM.py``: same class, method names, arguments and side effects,
+with the inner loop running in hand-written sm_100a CUDA behind the C ABI of ``include/mga.h``.
+
+What stays on the host (Python): argument checking, graph construction (once per instance),
+the bookkeeping lists the reference fills (``ADMM.py:66-92``).  What moved: every operator
+application, the three CG solves, the prox / dual updates and the diagnostics of
+``combined_loop`` (``ADMM.py:511-648``).  There is no CPU path: without ``libmga.so`` and a
+CUDA device every compute method raises.
+
+Inputs may live on the CPU (as every caller of the reference passes them) or on the GPU;
+results come back on the device of the input.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _cabi
+from .utils import *  # noqa: F401,F403  (the reference does `from utils import *`)
+from .utils import (connect_list, directed_graph_from_distance, expand_time_dimension, get_data_difference,
+                    k_nearest_neighbors, undirected_graph_from_distance)
+
+__all__ = ["ADMM_algorithm", "initial_guess", "initial_interpolation"]
+
+
+def _device_of(arg):
+    if arg is not None:
+        return torch.device(arg)
+    if not torch.cuda.is_available():
+        raise RuntimeError("mixed_graph_admm_b200 needs a CUDA device (B200); there is no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _regression_consts(t_in):
+    """mean(t) and var(t) exactly as the reference forms them: float32 (ADMM.py:772-774)."""
+    t = torch.arange(0, t_in, 1).to(torch.float)
+    return float(t.mean()), float((t ** 2).mean() - t.mean() ** 2)
+
+
+class _Plan:
+    """Owns one ``mga_plan`` (device copies of the graph tables)."""
+
+    def __init__(self, desc_kwargs, device):
+        L = _cabi.lib()
+        self.keep = []          # host tensors the descriptor points to
+        d = _cabi.GraphDesc()
+        for name, val in desc_kwargs.items():
+            if isinstance(val, torch.Tensor):
+                val = val.contiguous()
+                self.keep.append(val)
+                setattr(d, name, val.data_ptr())
+            else:
+                setattr(d, name, val)
+        h = C.c_void_p()
+        _cabi.check(L.mga_plan_create(C.byref(d), device.index or 0, C.byref(h)))
+        self.handle = h
+        self.device = device
+
+    def __del__(self):
+        try:
+            if getattr(self, "handle", None):
+                _cabi.lib().mga_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+class ADMM_algorithm():
+    '''
+    only with 1 head (reference ADMM.py:11-14)
+
+    Extra keyword-only arguments (not in the reference): ``device`` (default: current CUDA
+    device), ``mode`` ('auto' | 'streaming' | 'resident'), ``verbose`` (print the sigma lines
+    the reference prints from graph construction).
+    '''
+
+    def __init__(self, graph_info, ADMM_info, use_kNN=False, k=4, u_sigma=None, d_sigma=None, expand_time_dim=True,
+                 ablation='None', t_in=12, T=24, use_line_graph=False, skip_connection=1, *, device=None,
+                 mode='auto', verbose=False):
+        self.t_in = t_in
+        self.T = T
+        self.use_line_graph = use_line_graph
+        self.skip_connection = skip_connection
+        self.n_nodes = graph_info['n_nodes']
+        self.u_edges = graph_info['u_edges']
+        self.u_dists = graph_info['u_dist']
+        self.use_kNN = use_kNN
+        if use_kNN:
+            self.connect_list, self.dist_list = k_nearest_neighbors(self.n_nodes, self.u_edges, self.u_dists, k)
+            self.connect_list = self.connect_list.to(torch.int64)
+        else:
+            self.connect_list, self.dist_list = connect_list(self.n_nodes, self.u_edges, self.u_dists)
+
+        self.ablation = ablation
+        assert ablation in ['None', 'DGTV', 'DGLR', 'UT'], "ablation should be in ['None', 'DGTV', 'DGLR', 'UT']"
+        self.u_ew = undirected_graph_from_distance(self.connect_list, self.dist_list, u_sigma=u_sigma,
+                                                   regularized=True, verbose=verbose)
+        if expand_time_dim:
+            self.u_ew = expand_time_dimension(self.u_ew, T)
+        if not self.use_line_graph:
+            self.d_ew = directed_graph_from_distance(self.connect_list, self.dist_list, d_sigma=d_sigma,
+                                                     regularized=True, verbose=verbose)
+            if expand_time_dim:
+                self.d_ew = expand_time_dimension(self.d_ew, T - 1)
+        else:
+            # banded temporal weights (T, skip, N) and source-time table (T, skip), ADMM.py:41-52
+            w = torch.ones((self.n_nodes, self.T, self.skip_connection))
+            w.tril_(diagonal=-1)
+            w[:, 0, 0].fill_(1)
+            w = w / w.sum(-1, keepdim=True)
+            w[:, 0, 0].fill_(0)
+            self.d_ew = w.permute(1, 2, 0)
+            self.time_list = torch.arange(0, self.T).unsqueeze(1) - torch.arange(1, self.skip_connection + 1)
+
+        self.rho = ADMM_info['rho']
+        self.rho_u = ADMM_info['rho_u']
+        self.rho_d = ADMM_info['rho_d']
+        self.mu_u = ADMM_info['mu_u']
+        self.mu_d1 = ADMM_info['mu_d1']
+        self.mu_d2 = ADMM_info['mu_d2']
+
+        self.max_CG_iter = 100
+        self.max_inner_iter = 100
+        self.CG_tol = 1e-8
+        self.ADMM_tol = 1e-6
+        self.max_ADMM_iter = 150
+
+        self._reset_lists(all_lists=True)
+
+        # ---- not in the reference
+        self.device = _device_of(device)
+        self.mode = mode
+        self.strict_quirks = False      # True: reproduce the B>1 converged-return ValueError (quirk Q2)
+        self.keep_iterates = False      # True: combined_loop leaves z_u, z_d, phi, duals in last_iterates
+        self.last_iterates = None
+        self.last_mode = None
+        self._plan_key = None
+        self._plan_obj = None
+
+    # ------------------------------------------------------------------ bookkeeping
+    def _reset_lists(self, all_lists):
+        self.alpha_x = []
+        self.beta_x = []
+        self.alpha_zu = []
+        self.beta_zu = []
+        self.alpha_zd = []
+        self.beta_zd = []
+        self.CG_iter_x = []
+        self.CG_iter_zu = []
+        self.CG_iter_zd = []
+        self.p_res_list = []
+        self.d_res_list = []
+        self.x_shift_list = []
+        self.delta_x_per_step = []
+        self.DGTV_list = []
+        self.DGLR_list = []
+        self.GLR_list = []
+        if all_lists:
+            self.recover_list = []      # init_iterations does not clear it (ADMM.py:100-132)
+        self.res_name = ['zu']
+        if self.ablation in ['None', 'DGLR']:
+            self.res_name.append('phi')
+        if self.ablation != 'DGLR':
+            self.res_name.append('zd')
+
+    def init_iterations(self, ablation, use_line_graph=False):
+        """ADMM.py:100-132, including quirk Q8 (d_ew reset to default sigma, not time-expanded)."""
+        if use_line_graph:
+            self.use_line_graph = True
+            self.d_ew = torch.ones((self.n_nodes, 1))
+        else:
+            self.use_line_graph = False
+            self.d_ew = directed_graph_from_distance(self.connect_list, self.dist_list, d_sigma=None,
+                                                     regularized=True)
+        self.ablation = ablation
+        self._reset_lists(all_lists=False)
+
+    # ------------------------------------------------------------------ plan / params
+    def _plan(self):
+        cl, uw, dw = self.connect_list, self.u_ew, self.d_ew
+        key = (cl.data_ptr(), cl._version, tuple(cl.shape), uw.data_ptr(), uw._version, tuple(uw.shape),
+               dw.data_ptr(), dw._version, tuple(dw.shape), self.t_in, self.T, self.use_line_graph,
+               self.skip_connection, self.use_kNN, str(self.device))
+        if key == self._plan_key:
+            return self._plan_obj
+        N, T = self.n_nodes, self.T
+        cl64 = cl.detach().to('cpu', torch.int64)
+        uw32 = uw.detach().to('cpu', torch.float32)
+        dw32 = dw.detach().to('cpu', torch.float32)
+        nbr_u = cl64[:, 1:].contiguous()
+        if uw32.dim() == 2:
+            u_T = 1
+        elif uw32.dim() == 3 and uw32.shape[0] == T:
+            u_T = T
+        else:
+            raise ValueError(f"u_ew must be (N,k) or (T,N,k), got {tuple(uw32.shape)}")
+        if tuple(uw32.shape[-2:]) != (N, nbr_u.shape[1]):
+            raise ValueError(f"u_ew shape {tuple(uw32.shape)} does not match connect_list {tuple(cl.shape)}")
+        desc = dict(n_nodes=N, T=T, t_in=self.t_in, ku=nbr_u.shape[1], nbr_u=nbr_u, u_w=uw32, u_w_T=u_T,
+                    ldrt_mode=_cabi.LDRT_SCATTER if self.use_kNN else _cabi.LDRT_GATHER)
+        if not self.use_line_graph:
+            if dw32.dim() == 2:
+                d_T = 1
+            elif dw32.dim() == 3 and dw32.shape[0] == T - 1:
+                d_T = T - 1
+            else:
+                raise ValueError(f"d_ew must be (N,K) or (T-1,N,K), got {tuple(dw32.shape)}")
+            if tuple(dw32.shape[-2:]) != tuple(cl64.shape):
+                raise ValueError(f"d_ew shape {tuple(dw32.shape)} does not match connect_list {tuple(cl.shape)}")
+            desc.update(kd=cl64.shape[1], nbr_d=cl64.contiguous(), d_w=dw32, d_w_T=d_T,
+                        temporal=_cabi.TEMPORAL_GRAPH)
+        elif self.skip_connection == 1:
+            desc.update(kd=1, nbr_d=None, d_w=None, d_w_T=1, temporal=_cabi.TEMPORAL_LINE)
+        else:
+            if tuple(dw32.shape) != (T, self.skip_connection, N):
+                raise ValueError("line graph with skip_connection > 1 needs d_ew of shape (T, skip, N)")
+            desc.update(kd=self.skip_connection, nbr_d=None, d_w=dw32, d_w_T=1, temporal=_cabi.TEMPORAL_BAND)
+        desc = {k: (0 if v is None else v) for k, v in desc.items()}
+        self._plan_obj = _Plan(desc, self.device)
+        self._plan_key = key
+        return self._plan_obj
+
+    def _params(self):
+        p = _cabi.Params()
+        p.rho, p.rho_u, p.rho_d = float(self.rho), float(self.rho_u), float(self.rho_d)
+        p.mu_u, p.mu_d1, p.mu_d2 = float(self.mu_u), float(self.mu_d1), float(self.mu_d2)
+        p.ablation = _cabi.ABLATION[self.ablation]
+        return p
+
+    def _in(self, x):
+        """(B,T,N,1) signal -> contiguous tensor on the plan's device."""
+        if x.dim() != 4:
+            raise ValueError(f"signals are (B, T, N, C); got {tuple(x.shape)}")
+        if x.size(-1) != 1:
+            raise NotImplementedError("the B200 path is single-channel (C = 1), like every use in the reference")
+        if x.size(2) != self.n_nodes:
+            raise ValueError(f"signal has {x.size(2)} nodes, graph has {self.n_nodes}")
+        _cabi.dtype_id(x.dtype)
+        return x.detach().to(self.device).contiguous()
+
+    def _apply(self, op, x, mask=None):
+        if x.size(1) != self.T:
+            raise ValueError(f"operator input must have T={self.T} time steps, got {x.size(1)}")
+        xd = self._in(x)
+        md = self._in(mask.to(x.dtype)) if mask is not None else None
+        y = torch.empty_like(xd)
+        plan, prm = self._plan(), self._params()
+        with torch.cuda.device(self.device):
+            _cabi.check(_cabi.lib().mga_apply(plan.handle, _cabi.OP[op], C.byref(prm), _cabi.ptr(xd), _cabi.ptr(y),
+                                              _cabi.ptr(md), xd.size(0), _cabi.dtype_id(xd.dtype),
+                                              _cabi.stream_ptr(self.device)))
+        return y.to(x.device)
+
+    # ------------------------------------------------------------------ operators (ADMM.py:138-228)
+    def apply_op_Lu(self, x):
+        '''signal shape: (B, T, N, n_channels)'''
+        return self._apply("Lu", x)
+
+    def apply_op_Ldr(self, x):
+        return self._apply("Ldr", x)
+
+    def apply_op_Ldr_T(self, x: torch.Tensor):
+        return self._apply("Ldr_T", x)
+
+    def apply_op_cLdr(self, x):
+        return self._apply("cLdr", x)
+
+    def apply_op_Ln(self, x):
+        raise NotImplementedError("apply_op_Ln is unreachable in the reference (LHS_zd tests != 'DGLR' before "
+                                  "== 'UT', ADMM.py:393-396) and is outside the hot path")
+
+    def DGLR(self, x):
+        '''x in (B, T, N, C); mean over the batch of ||L_d x||^2 (ADMM.py:230-235)'''
+        return (self.apply_op_Ldr(x) ** 2).sum((1, 2, 3)).mean()
+
+    def DGTV(self, x):
+        '''mean over the batch of ||L_d x||_1 (ADMM.py:238-243)'''
+        return self.apply_op_Ldr(x).norm(dim=[1, 2, 3], p=1).mean()
+
+    def GLR(self, x):
+        return (x * self.apply_op_Lu(x)).sum((1, 2, 3)).mean()
+
+    # ------------------------------------------------------------------ systems (ADMM.py:371-408)
+    def LHS_x(self, x, mask=None):
+        return self._apply("LHS_x", x, mask)
+
+    def LHS_zu(self, zu):
+        return self._apply("LHS_zu", zu)
+
+    def LHS_zd(self, zd):
+        if self.ablation != 'DGLR':
+            return self._apply("LHS_zd", zd)
+        print('Error: LHS_zd')
+        return None
+
+    def phi_direct(self, x, gamma):
+        '''phi = soft_(mu_d1 / rho) (L^d_r x - gamma / rho)   (ADMM.py:401-408)'''
+        xd, gd = self._in(x), self._in(gamma)
+        out = torch.empty_like(xd)
+        plan, prm = self._plan(), self._params()
+        with torch.cuda.device(self.device):
+            _cabi.check(_cabi.lib().mga_phi_direct(plan.handle, C.byref(prm), _cabi.ptr(xd), _cabi.ptr(gd),
+                                                   _cabi.ptr(out), xd.size(0), _cabi.dtype_id(xd.dtype),
+                                                   _cabi.stream_ptr(self.device)))
+        return out.to(x.device)
+
+    # ------------------------------------------------------------------ CG (ADMM.py:329-368)
+    def _system_of(self, fn):
+        owner = getattr(fn, "__self__", None)
+        func = getattr(fn, "__func__", None)
+        if owner is self:
+            for name in ("x", "zu", "zd"):
+                if func is getattr(type(self), "LHS_" + name):
+                    return name
+        return None
+
+    def CG_solver(self, LHS_func, RHS, x0=None, **kwargs):
+        '''
+        Solving linear systems LHS_func(x) = RHS, B samples at the same time.
+        ``LHS_func`` must be one of this instance's ``LHS_x`` / ``LHS_zu`` / ``LHS_zd`` for the fused
+        CUDA path; any other callable runs the same recurrence with torch ops on the device.
+        Returns ``(x, iters, alphas, betas)`` like the reference: on convergence ``iters = k+1`` and
+        tensors, otherwise ``-1`` and python lists of ``(B,)`` tensors.
+        '''
+        system = self._system_of(LHS_func)
+        if system is None:
+            return self._cg_foreign(LHS_func, RHS, x0, **kwargs)
+        if system == "zd" and self.ablation == 'DGLR':
+            raise TypeError("LHS_zd returns None under ablation 'DGLR' (ADMM.py:397-399)")
+        rhs = self._in(RHS)
+        x = torch.zeros_like(rhs) if x0 is None else self._in(x0).clone()
+        mask = kwargs.get("mask", None)
+        md = self._in(mask.to(RHS.dtype)) if mask is not None else None
+        B = rhs.size(0)
+        n_it = int(self.max_CG_iter)
+        alpha = torch.empty((max(n_it, 1), B), dtype=rhs.dtype, device=self.device)
+        beta = torch.empty_like(alpha)
+        iters = C.c_int32(-1)
+        plan, prm = self._plan(), self._params()
+        with torch.cuda.device(self.device):
+            _cabi.check(_cabi.lib().mga_cg_solve(plan.handle, _cabi.SYS[system], C.byref(prm), _cabi.ptr(rhs),
+                                                 _cabi.ptr(x), _cabi.ptr(md), B, _cabi.dtype_id(rhs.dtype), n_it,
+                                                 float(self.CG_tol), C.byref(iters), _cabi.ptr(alpha),
+                                                 _cabi.ptr(beta), _cabi.stream_ptr(self.device)))
+        al, be = self._coef_lists(alpha, beta, iters.value, n_it, RHS.device)
+        return x.to(RHS.device), iters.value, al, be
+
+    def _coef_lists(self, alpha, beta, iters, n_it, device):
+        """Types of quirk Q11: converged -> Tensor, else python list of (B,) tensors."""
+        B = alpha.size(1)
+        if iters > 0:
+            if B > 1 and self.strict_quirks:
+                raise ValueError("only one element tensors can be converted to Python scalars")   # ADMM.py:362
+            a, b = alpha[:iters].to(device), beta[:iters].to(device)
+            if B == 1:
+                return a.reshape(-1).to(torch.float32), b.reshape(-1).to(torch.float32)   # torch.Tensor(list)
+            return a, b
+        a, b = alpha[:n_it].to(device), beta[:n_it].to(device)
+        return list(a.unbind(0)), list(b.unbind(0))
+
+    def _cg_foreign(self, LHS_func, RHS, x0=None, **kwargs):
+        """The reference recurrence for a caller-supplied operator (not the fused path)."""
+        alpha_list, beta_list = [], []
+        x = torch.zeros_like(RHS) if x0 is None else x0.clone()
+        r = RHS - LHS_func(x, **kwargs)
+        p = r.clone()
+        rr = (r * r).sum((1, 2, 3))
+        for k in range(self.max_CG_iter):
+            Ap = LHS_func(p)
+            alpha = rr / (p * Ap).sum((1, 2, 3))
+            alpha_list.append(alpha)
+            x = x + alpha[:, None, None, None] * p
+            r = r - alpha[:, None, None, None] * Ap
+            rr_new = (r * r).sum((1, 2, 3))
+            beta = rr_new / rr
+            beta_list.append(beta)
+            rr = rr_new
+            if torch.sqrt(rr).max() < self.CG_tol:
+                if rr.numel() > 1 and self.strict_quirks:
+                    raise ValueError("only one element tensors can be converted to Python scalars")
+                return x, k + 1, torch.stack(alpha_list).squeeze(-1), torch.stack(beta_list).squeeze(-1)
+            p = r + beta[:, None, None, None] * p
+        return x, -1, alpha_list, beta_list
+
+    # ------------------------------------------------------------------ the loop (ADMM.py:511-648)
+    def two_loops(self, y, mask=None, differential=False):
+        raise NotImplementedError("two_loops is unfinished upstream (it returns nothing and no script calls it, "
+                                  "ADMM.py:410-508); use combined_loop")
+
+    def combined_loop(self, y, mask=None, differential=False, print_info=True):
+        '''
+        Input:  y in (B, t_in, N, C)   [mask mode: y and mask in (B, T, N, C)]
+        Output: x in (B, T, N, C)
+        '''
+        if differential:
+            assert mask is None, 'differential mode does not support mask'
+            # the reference computes a differential first guess here and then discards it (ADMM.py:521-529)
+        assert not torch.isnan(self.d_ew).any(), 'Directed graph weights d_ew has NaN value'
+        assert not torch.isnan(self.u_ew).any(), 'Undirected graph weights u_ew has NaN value'
+        out_device = y.device
+        B = y.size(0)
+        T, N = self.T, self.n_nodes
+        y_rows = y.size(1)
+        if mask is None and y_rows != self.t_in:
+            raise ValueError(f"y must have t_in={self.t_in} time steps, got {y_rows}")
+        if mask is not None and (y_rows != T or tuple(mask.shape) != tuple(y.shape)):
+            raise ValueError("mask mode needs y and mask of shape (B, T, N, C)")
+        dt = _cabi.dtype_id(y.dtype)
+        n_outer, n_cg = int(self.max_ADMM_iter), int(self.max_CG_iter)
+        cg_tol, admm_tol = float(self.CG_tol), float(self.ADMM_tol)
+        fixed = cg_tol <= 0 and admm_tol <= 0
+        plan, prm = self._plan(), self._params()
+        L = _cabi.lib()
+        t_mean, t_var = _regression_consts(self.t_in)
+        want_iter = bool(self.keep_iterates)
+        dev = self.device
+
+        host_path = (y.device.type == 'cpu' and mask is None and fixed and not want_iter
+                     and self.ablation == 'None')
+        diag_h = np.zeros((n_outer, _cabi.DIAG_COLS), dtype=np.float64)
+        dx_h = np.zeros((n_outer, T, N), dtype=np.float64)
+        cg_iters = np.full((max(n_outer, 1), 3), -1, dtype=np.int32)
+        outer_done = C.c_int32(n_outer)
+        alpha = beta = None
+        with torch.cuda.device(dev):
+            if host_path:
+                # end-to-end call with host buffers: chunked copies overlap the solve
+                yc = y.detach().contiguous()
+                x = torch.empty((B, T, N, 1), dtype=y.dtype, pin_memory=yc.is_pinned())
+                _cabi.check(L.mga_admm_solve_host(plan.handle, C.byref(prm), _cabi.ptr(yc), y_rows, _cabi.ptr(x), B,
+                                                  dt, n_outer, n_cg, t_mean, t_var, 1,
+                                                  diag_h.ctypes.data_as(C.c_void_p),
+                                                  dx_h.ctypes.data_as(C.c_void_p), _cabi.MODE[self.mode], 0))
+                self.last_mode = 'host'
+                self.last_iterates = None
+            else:
+                yd = self._in(y)
+                md = self._in(mask.to(y.dtype)) if mask is not None else None
+                x = torch.empty((B, T, N, 1), dtype=y.dtype, device=dev)
+                outs = _cabi.AdmmOutputs()
+                its = {}
+                if want_iter:
+                    for name in ("zu", "zd", "phi", "gamma", "gamma_u", "gamma_d"):
+                        its[name] = torch.zeros_like(x)
+                        setattr(outs, name, its[name].data_ptr())
+                diag_d = torch.zeros((max(n_outer, 1), _cabi.DIAG_COLS), dtype=torch.float64, device=dev)
+                dx_d = torch.zeros((max(n_outer, 1), T, N), dtype=torch.float64, device=dev)
+                alpha = torch.zeros((max(n_outer, 1), 3, max(n_cg, 1), B), dtype=y.dtype, device=dev)
+                beta = torch.zeros_like(alpha)
+                outs.diag, outs.dx_sum = diag_d.data_ptr(), dx_d.data_ptr()
+                outs.alpha, outs.beta = alpha.data_ptr(), beta.data_ptr()
+                outs.cg_iters = cg_iters.ctypes.data
+                outs.outer_done = C.addressof(outer_done)
+                _cabi.check(L.mga_admm_solve(plan.handle, C.byref(prm), _cabi.ptr(yd), y_rows, _cabi.ptr(md),
+                                             _cabi.ptr(x), B, dt, n_outer, n_cg, cg_tol, admm_tol, t_mean, t_var, 1,
+                                             C.byref(outs), _cabi.MODE[self.mode], _cabi.stream_ptr(dev)))
+                torch.cuda.current_stream(dev).synchronize()
+                diag_h = diag_d.cpu().numpy()
+                dx_h = dx_d.cpu().numpy()
+                self.last_iterates = {k: v.to(out_device) for k, v in its.items()} if want_iter else None
+                self.last_mode = 'device'
+        self._fill_lists(diag_h, dx_h, cg_iters, int(outer_done.value), alpha, beta, B, y.dtype, out_device,
+                         print_info)
+        return x.to(out_device)
+
+    def _fill_lists(self, diag, dx_sum, cg_iters, n_done, alpha, beta, B, dtype, device, print_info):
+        """Append one entry per executed outer iteration to the reference's result lists
+        (ADMM.py:572-643), with the element types of quirk Q11."""
+        with_phi = self.ablation in ['None', 'DGLR']
+        with_zd = self.ablation != 'DGLR'
+
+        def rnd(v):      # value rounded to the signal dtype, as a python float
+            return torch.tensor(v, dtype=torch.float64).to(dtype).item()
+
+        for i in range(n_done):
+            d = diag[i]
+            if d[_cabi.DIAG_NONFINITE] > 0:
+                raise AssertionError(f'x / z / phi / gamma has NaN or inf value in loop {i}')   # ADMM.py:575-606
+            its = [int(v) for v in cg_iters[i]]
+            names = ["x", "zu"] + (["zd"] if with_zd else [])
+            for s, name in enumerate(names):
+                getattr(self, "CG_iter_" + name).append(its[s])
+                if alpha is not None:
+                    n_it = its[s] if its[s] > 0 else int(self.max_CG_iter)
+                    a, b = self._coef_lists(alpha[i, s], beta[i, s], its[s], n_it, device)
+                else:
+                    a, b = [], []          # host path does not bring the CG coefficients back
+                getattr(self, "alpha_" + name).append(a)
+                getattr(self, "beta_" + name).append(b)
+            pri, dual = [], []
+            self.x_shift_list.append(rnd(math.sqrt(d[_cabi.DIAG_DX2])))
+            mean_dx = torch.from_numpy(dx_sum[i] / B)
+            self.delta_x_per_step.append(mean_dx.pow(2).sum(1).sqrt().to(dtype).to(device))
+            pri.append(rnd(math.sqrt(d[_cabi.DIAG_X_ZU2])))
+            dual.append(rnd(math.sqrt(d[_cabi.DIAG_DZU2])))
+            self.GLR_list.append(torch.tensor(d[_cabi.DIAG_GLR] / B, dtype=torch.float64).to(dtype).to(device))
+            self.recover_list.append(rnd(math.sqrt(d[_cabi.DIAG_RECOVER2])))
+            if with_phi:
+                pri.append(rnd(math.sqrt(d[_cabi.DIAG_PHI_LDX2])))
+                dual.append(rnd(math.sqrt(d[_cabi.DIAG_DPHI2])))
+                self.DGTV_list.append(torch.tensor(d[_cabi.DIAG_DGTV] / B, dtype=torch.float64).to(dtype).to(device))
+            if with_zd:
+                pri.append(rnd(math.sqrt(d[_cabi.DIAG_X_ZD2])))
+                dual.append(rnd(math.sqrt(d[_cabi.DIAG_DZD2])))
+                self.DGLR_list.append(torch.tensor(d[_cabi.DIAG_DGLR] / B, dtype=torch.float64).to(dtype).to(device))
+            if print_info:
+                zd_it = its[2] if with_zd else None
+                print(f'ADMM iters {i}: x_CG_iters {its[0]}, zu_CG_iters {its[1]}, zd_CG_iters {zd_it}, '
+                      f'pri_err = [{", ".join([f"{err:.4g}" for err in pri])}], '
+                      f'dual_err = [{", ".join([f"{err:.4g}" for err in dual])}]')
+            self.p_res_list.append(pri)
+            self.d_res_list.append(dual)
+
+    # plots (ADMM.py:650-761) read the lists above; matplotlib is not a dependency of the hot path
+    def _no_plot(self, *a, **k):
+        raise NotImplementedError("plotting is outside the hot path; the lists it reads (p_res_list, d_res_list, "
+                                  "x_shift_list, delta_x_per_step, GLR/DGLR/DGTV_list, alpha_*/beta_*) are filled")
+
+    plot_residual = plot_x_per_step = plot_CG_params = plot_regularization_terms = _no_plot
+
+
+def initial_guess(y, t_in, T):
+    '''
+    y in (B, t_in, N, C) -> x in (B, T, N, C): per (window, node) least-squares line through the
+    observations, extrapolated (ADMM.py:766-781).  Runs the CUDA kernel ``mga_initial_guess``.
+    '''
+    if y.size(1) != t_in:
+        raise ValueError("y must have t_in time steps")
+    if y.size(-1) != 1:
+        raise NotImplementedError("single-channel only")
+    dev = y.device if y.is_cuda else _device_of(None)
+    B, N = y.size(0), y.size(2)
+    # a graph-free plan: initial_guess only needs the shape
+    desc = dict(n_nodes=N, T=T, t_in=t_in, ku=0, nbr_u=0, u_w=0, u_w_T=1, kd=1, nbr_d=0, d_w=0, d_w_T=1,
+                ldrt_mode=0, temporal=_cabi.TEMPORAL_LINE)
+    plan = _Plan(desc, dev)
+    yd = y.detach().to(dev).contiguous()
+    x = torch.empty((B, T, N, 1), dtype=y.dtype, device=dev)
+    t_mean, t_var = _regression_consts(t_in)
+    with torch.cuda.device(dev):
+        _cabi.check(_cabi.lib().mga_initial_guess(plan.handle, _cabi.ptr(yd), _cabi.ptr(x), B,
+                                                  _cabi.dtype_id(y.dtype), t_mean, t_var, _cabi.stream_ptr(dev)))
+        torch.cuda.current_stream(dev).synchronize()
+    return x.to(y.device)
+
+
+def initial_interpolation(y, mask):
+    '''
+    y, mask in (B, T, N, C), y = x * mask: per-node regression through the observed entries, used to
+    fill the missing ones (ADMM.py:783-811).  Host-side torch ops on the device of ``y``; inside
+    combined_loop the same step runs in the CUDA prologue kernel.  Unlike the reference (whose
+    ``w * t`` broadcast only lines up for B == 1, ADMM.py:802) this works for any B.
+    '''
+    B, T, N, Cn = y.size()
+    t = torch.arange(0, T, 1, device=y.device).to(torch.float).view(1, T, 1, 1).expand(B, T, N, Cn)
+    n_data = mask.sum(1, keepdim=True)
+    t_mean = (t * mask).sum(1, keepdim=True) / n_data
+    y_mean = (y * mask).sum(1, keepdim=True) / n_data
+    ty_mean = (t * y * mask).sum(1, keepdim=True) / n_data
+    t2_mean = (t ** 2 * mask).sum(1, keepdim=True) / n_data
+    w = (ty_mean - t_mean * y_mean) / (t2_mean - t_mean ** 2)
+    b = y_mean - w * t_mean
+    assert not torch.isnan(w).any(), 'Initial interpolation w has NaN value'
+    assert not torch.isnan(b).any(), 'Initial interpolation b has NaN value'
+    x = (w * t + b) * (1 - mask) + y
+    assert not torch.isnan(x).any(), 'Initial interpolation x has NaN value'
+    return x

@@ -1,0 +1,132 @@
+// Shared declarations of libmga: plan layout, error plumbing, block reductions.
+// Everything here is internal; the public surface is include/mga.h.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <string>
+#include <vector>
+
+#include "mga.h"
+
+namespace mga {
+
+// ---------------------------------------------------------------------------------------------
+// Device-side view of the graph tables (all pointers are device memory owned by the plan).
+//
+//  ELL tables (one row per node, -1 = no neighbour; quirk Q6: such a slot contributes exactly 0):
+//    nbr_u (N, ku)  u_w (u_wT, N, ku)   — spatial Laplacian L_u        (ADMM.py:138-148)
+//    nbr_d (N, kd)  d_w (d_wT, N, kd)   — temporal operator L_d        (ADMM.py:166-177)
+//  CSR "in-list" for L_d^T: row c lists (src, slot) pairs with f[t,c] = sum d_w[t][slot] * v[t+1,src]
+//    SCATTER (kNN) mode: all (i, i*kd+j) with nbr_d[i,j] == c, ascending slot = the order in which
+//                        the reference's scatter_add visits them (ADMM.py:203-208)
+//    GATHER mode:        row i's own forward list (ADMM.py:211-215)
+//    csr_w (nnz) holds d_w[0][slot] and is used when d_wT == 1.
+// ---------------------------------------------------------------------------------------------
+struct GraphDev {
+  int N, T, t_in;
+  int ku, kd;
+  int u_wT, d_wT;        // 1 = time-invariant
+  int q1;                // 1: row t=0 of Ldr_T keeps the identity term (quirk Q1)
+  int temporal;          // mga_temporal_kind
+  int skip;              // BAND only
+  int nnz, max_in_deg;
+  const int* nbr_u;
+  const float* u_w;
+  const int* nbr_d;
+  const float* d_w;
+  const int* csr_ptr;
+  const int* csr_src;
+  const int* csr_slot;
+  const float* csr_w;
+  const float* band_w;   // (T, skip, N) BAND only
+};
+
+struct Workspace {
+  void* base = nullptr;
+  size_t bytes = 0;
+};
+
+}  // namespace mga
+
+struct mga_plan {
+  int device = 0;
+  int sm_count = 0;
+  int max_smem_optin = 0;
+  mga::GraphDev g{};
+  std::vector<void*> owned;          // device allocations of the tables
+  mga::Workspace ws;                 // grown on demand, reused between calls
+  mga::Workspace ws_host_io;         // device staging of the *_host entry point
+  void* pinned = nullptr;            // small pinned host block (flags, diag read-back)
+  size_t pinned_bytes = 0;
+  cudaStream_t io_streams[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t io_events[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  // host copies for the resident-kernel set-up
+  std::vector<int> h_nbr_u, h_nbr_d, h_csr_ptr, h_csr_src;
+  std::vector<float> h_u_w, h_d_w, h_csr_w;
+};
+
+namespace mga {
+
+void set_error(const std::string& msg);
+int cuda_fail(cudaError_t e, const char* what);
+extern std::atomic<int64_t> g_launches;
+
+#define MGA_CUDA(expr)                                         \
+  do {                                                         \
+    cudaError_t _e = (expr);                                   \
+    if (_e != cudaSuccess) return ::mga::cuda_fail(_e, #expr); \
+  } while (0)
+
+#define MGA_LAUNCH_CHECK(name)                                  \
+  do {                                                          \
+    ::mga::g_launches.fetch_add(1, std::memory_order_relaxed);  \
+    cudaError_t _e = cudaGetLastError();                        \
+    if (_e != cudaSuccess) return ::mga::cuda_fail(_e, name);   \
+  } while (0)
+
+int ensure_workspace(mga_plan* plan, Workspace& ws, size_t bytes);
+
+template <typename S> struct DType;
+template <> struct DType<float> { static constexpr int id = MGA_F32; };
+template <> struct DType<double> { static constexpr int id = MGA_F64; };
+
+// ---- reductions -------------------------------------------------------------------------------
+template <typename S>
+__device__ __forceinline__ S warp_sum(S v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Sum over the block; result valid in every thread.  `red` must hold >= 32 S; callers alternate
+// between two buffers (or sync) so that back-to-back reductions do not race.
+template <typename S>
+__device__ __forceinline__ S block_sum(S v, S* red) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  S t = 0;
+  for (int k = 0; k < nw; ++k) t += red[k];   // fixed order: every thread gets the same bits
+  return t;
+}
+
+// streaming-mode entry points implemented in mga_stream.cu
+int stream_apply(mga_plan*, int op, const mga_params*, const void* x, void* y, const void* mask, int64_t B,
+                 int dtype, cudaStream_t st);
+int stream_cg(mga_plan*, int system, const mga_params*, const void* rhs, void* x, const void* mask_first,
+              int64_t B, int dtype, int max_iter, double tol, int32_t* iters_out, void* alpha, void* beta,
+              cudaStream_t st);
+int stream_admm(mga_plan*, const mga_params*, const void* y, int y_rows, const void* mask, void* x_out, int64_t B,
+                int dtype, int n_outer, int max_cg, double cg_tol, double admm_tol, double t_mean, double t_var,
+                int want_diag, const mga_admm_outputs* outs, cudaStream_t st);
+// resident mode (mga_resident.cu)
+bool resident_eligible(const mga_plan*, int dtype);
+int resident_smem_bytes(const mga_plan*, int* threads);
+int resident_admm(mga_plan*, const mga_params*, const void* y, void* x_out, int64_t B, int n_outer, int n_cg,
+                  double t_mean, double t_var, int want_diag, const mga_admm_outputs* outs, cudaStream_t st);
+
+}  // namespace mga

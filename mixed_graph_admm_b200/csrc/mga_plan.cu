@@ -1,0 +1,378 @@
+// Plan construction (host) and the C-ABI dispatch layer of libmga.
+//
+// The plan replaces the graph state ADMM_algorithm.__init__ leaves behind (ADMM.py:15-98):
+// it validates the neighbour indices once (the reference re-validates on every Ldr_T call,
+// ADMM.py:204-206), narrows them to int32, detects time-invariant weight tables (the
+// reference stores T identical copies, utils.py:294-295), and builds the in-list (transposed
+// CSR) that turns the reference's scatter_add into an atomics-free gather.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include "mga_common.cuh"
+
+namespace mga {
+
+static thread_local std::string t_error;
+std::atomic<int64_t> g_launches{0};
+
+void set_error(const std::string& msg) { t_error = msg; }
+
+int cuda_fail(cudaError_t e, const char* what) {
+  t_error = std::string("CUDA error: ") + cudaGetErrorString(e) + " at " + what;
+  return MGA_ERR_CUDA;
+}
+
+int ensure_workspace(mga_plan* plan, Workspace& ws, size_t bytes) {
+  if (ws.bytes >= bytes) return MGA_OK;
+  if (ws.base) {
+    MGA_CUDA(cudaDeviceSynchronize());
+    MGA_CUDA(cudaFree(ws.base));
+    ws.base = nullptr;
+    ws.bytes = 0;
+  }
+  size_t want = bytes + bytes / 8;
+  cudaError_t e = cudaMalloc(&ws.base, want);
+  if (e != cudaSuccess) {
+    want = bytes;
+    e = cudaMalloc(&ws.base, want);
+  }
+  if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc(workspace)");
+  ws.bytes = want;
+  (void)plan;
+  return MGA_OK;
+}
+
+template <typename T>
+static int upload(mga_plan* p, const std::vector<T>& h, const T** out) {
+  void* d = nullptr;
+  size_t bytes = std::max<size_t>(h.size(), 1) * sizeof(T);
+  MGA_CUDA(cudaMalloc(&d, bytes));
+  p->owned.push_back(d);
+  if (!h.empty()) MGA_CUDA(cudaMemcpy(d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+  *out = static_cast<const T*>(d);
+  return MGA_OK;
+}
+
+// A weight table stored as nT identical slices collapses to one (quirk Q8 / utils.py:294-295).
+static int collapse_time(const float* w, int nT, size_t slice, std::vector<float>& out) {
+  bool same = true;
+  for (int t = 1; t < nT && same; ++t) same = std::memcmp(w, w + (size_t)t * slice, slice * sizeof(float)) == 0;
+  int keep = same ? 1 : nT;
+  out.assign(w, w + (size_t)keep * slice);
+  return keep;
+}
+
+}  // namespace mga
+
+using namespace mga;
+
+extern "C" {
+
+int mga_version(void) { return MGA_VERSION; }
+const char* mga_last_error(void) { return t_error.c_str(); }
+int64_t mga_launch_count(void) { return g_launches.load(); }
+
+int mga_plan_create(const mga_graph_desc* d, int device, mga_plan** out) {
+  if (!d || !out) { set_error("mga_plan_create: NULL argument"); return MGA_ERR_INVALID; }
+  *out = nullptr;
+  const int N = d->n_nodes, T = d->T;
+  if (N <= 0 || T < 2 || d->t_in < 1 || d->t_in > T || d->ku < 0 || !d->nbr_u && d->ku > 0) {
+    set_error("mga_plan_create: bad shape (need N>0, T>=2, 1<=t_in<=T)");
+    return MGA_ERR_INVALID;
+  }
+  if (d->temporal < MGA_TEMPORAL_GRAPH || d->temporal > MGA_TEMPORAL_BAND) {
+    set_error("mga_plan_create: bad temporal kind");
+    return MGA_ERR_INVALID;
+  }
+  if (d->temporal == MGA_TEMPORAL_GRAPH && (d->kd <= 0 || !d->nbr_d || !d->d_w)) {
+    set_error("mga_plan_create: temporal graph needs nbr_d / d_w");
+    return MGA_ERR_INVALID;
+  }
+  if (d->ku > 0 && (!d->u_w || (d->u_w_T != 1 && d->u_w_T != T))) {
+    set_error("mga_plan_create: u_w must be (N,ku) or (T,N,ku)");
+    return MGA_ERR_INVALID;
+  }
+  int ndev = 0;
+  MGA_CUDA(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) { set_error("mga_plan_create: no such CUDA device"); return MGA_ERR_CUDA; }
+  MGA_CUDA(cudaSetDevice(device));
+
+  mga_plan* p = new mga_plan();
+  p->device = device;
+  cudaDeviceProp prop;
+  cudaError_t e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) { delete p; return cuda_fail(e, "cudaGetDeviceProperties"); }
+  p->sm_count = prop.multiProcessorCount;
+  p->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+
+  GraphDev& g = p->g;
+  g.N = N; g.T = T; g.t_in = d->t_in; g.ku = d->ku;
+  g.temporal = d->temporal; g.skip = 0;
+  int rc = MGA_OK;
+  auto fail = [&](int code) { mga_plan_destroy(p); return code; };
+
+  // ---- spatial table
+  p->h_nbr_u.resize((size_t)N * d->ku);
+  for (size_t k = 0; k < p->h_nbr_u.size(); ++k) {
+    int64_t v = d->nbr_u[k];
+    if (v < -1 || v >= N) { set_error("Index out of bounds"); return fail(MGA_ERR_INDEX); }
+    p->h_nbr_u[k] = (int)v;
+  }
+  g.u_wT = d->ku > 0 ? collapse_time(d->u_w, d->u_w_T, (size_t)N * d->ku, p->h_u_w) : 1;
+
+  // ---- temporal table + in-list
+  std::vector<int> slot;
+  if (d->temporal == MGA_TEMPORAL_GRAPH) {
+    if (d->d_w_T != 1 && d->d_w_T != T - 1) {
+      set_error("mga_plan_create: d_w must be (N,kd) or (T-1,N,kd)");
+      return fail(MGA_ERR_INVALID);
+    }
+    g.kd = d->kd;
+    g.q1 = 1;  // ADMM.py:220-222
+    p->h_nbr_d.resize((size_t)N * g.kd);
+    for (size_t k = 0; k < p->h_nbr_d.size(); ++k) {
+      int64_t v = d->nbr_d[k];
+      if (v < -1 || v >= N) { set_error("Index out of bounds"); return fail(MGA_ERR_INDEX); }
+      p->h_nbr_d[k] = (int)v;
+    }
+    g.d_wT = collapse_time(d->d_w, d->d_w_T, (size_t)N * g.kd, p->h_d_w);
+    p->h_csr_ptr.assign(N + 1, 0);
+    if (d->ldrt_mode == MGA_LDRT_SCATTER) {
+      for (size_t k = 0; k < p->h_nbr_d.size(); ++k)
+        if (p->h_nbr_d[k] >= 0) p->h_csr_ptr[p->h_nbr_d[k] + 1]++;
+      for (int c = 0; c < N; ++c) p->h_csr_ptr[c + 1] += p->h_csr_ptr[c];
+      std::vector<int> fill(p->h_csr_ptr.begin(), p->h_csr_ptr.end() - 1);
+      p->h_csr_src.resize(p->h_csr_ptr[N]);
+      slot.resize(p->h_csr_ptr[N]);
+      for (int i = 0; i < N; ++i)        // ascending (i, j) == ascending slot: scatter_add order
+        for (int j = 0; j < g.kd; ++j) {
+          int c = p->h_nbr_d[(size_t)i * g.kd + j];
+          if (c < 0) continue;
+          int pos = fill[c]++;
+          p->h_csr_src[pos] = i;
+          slot[pos] = i * g.kd + j;
+        }
+    } else if (d->ldrt_mode == MGA_LDRT_GATHER) {
+      for (int i = 0; i < N; ++i) {
+        int cnt = 0;
+        for (int j = 0; j < g.kd; ++j) cnt += p->h_nbr_d[(size_t)i * g.kd + j] >= 0;
+        p->h_csr_ptr[i + 1] = p->h_csr_ptr[i] + cnt;
+      }
+      p->h_csr_src.resize(p->h_csr_ptr[N]);
+      slot.resize(p->h_csr_ptr[N]);
+      int pos = 0;
+      for (int i = 0; i < N; ++i)
+        for (int j = 0; j < g.kd; ++j) {
+          int c = p->h_nbr_d[(size_t)i * g.kd + j];
+          if (c < 0) continue;
+          p->h_csr_src[pos] = c;
+          slot[pos] = i * g.kd + j;
+          ++pos;
+        }
+    } else {
+      set_error("mga_plan_create: bad ldrt_mode");
+      return fail(MGA_ERR_INVALID);
+    }
+  } else if (d->temporal == MGA_TEMPORAL_LINE) {
+    // first difference in time (ADMM.py:153-157, 182-186): self link with unit weight, no Q1 term
+    g.kd = 1;
+    g.q1 = 0;
+    g.d_wT = 1;
+    p->h_nbr_d.resize(N);
+    p->h_d_w.assign(N, 1.0f);
+    p->h_csr_ptr.resize(N + 1);
+    p->h_csr_src.resize(N);
+    slot.resize(N);
+    for (int i = 0; i < N; ++i) { p->h_nbr_d[i] = i; p->h_csr_ptr[i] = i; p->h_csr_src[i] = i; slot[i] = i; }
+    p->h_csr_ptr[N] = N;
+  } else {
+    // banded temporal stencil (ADMM.py:41-52, 158-164, 187-194): weights (T, skip, N)
+    if (d->kd < 1 || !d->d_w) { set_error("mga_plan_create: BAND needs d_w (T,skip,N), kd=skip"); return fail(MGA_ERR_INVALID); }
+    g.kd = 0;
+    g.q1 = 0;
+    g.d_wT = 1;
+    g.skip = d->kd;
+    p->h_csr_ptr.assign(N + 1, 0);
+  }
+  g.nnz = (int)p->h_csr_src.size();
+  g.max_in_deg = 0;
+  for (int c = 0; c < N; ++c) g.max_in_deg = std::max(g.max_in_deg, p->h_csr_ptr[c + 1] - p->h_csr_ptr[c]);
+  p->h_csr_w.resize(g.nnz);
+  for (int k = 0; k < g.nnz; ++k) p->h_csr_w[k] = p->h_d_w[slot[k]];
+
+  if ((rc = upload(p, p->h_nbr_u, &g.nbr_u))) return fail(rc);
+  if ((rc = upload(p, p->h_u_w, &g.u_w))) return fail(rc);
+  if ((rc = upload(p, p->h_nbr_d, &g.nbr_d))) return fail(rc);
+  if ((rc = upload(p, p->h_d_w, &g.d_w))) return fail(rc);
+  if ((rc = upload(p, p->h_csr_ptr, &g.csr_ptr))) return fail(rc);
+  if ((rc = upload(p, p->h_csr_src, &g.csr_src))) return fail(rc);
+  if ((rc = upload(p, slot, &g.csr_slot))) return fail(rc);
+  if ((rc = upload(p, p->h_csr_w, &g.csr_w))) return fail(rc);
+  g.band_w = nullptr;
+  if (d->temporal == MGA_TEMPORAL_BAND) {
+    std::vector<float> bw(d->d_w, d->d_w + (size_t)T * g.skip * N);
+    if ((rc = upload(p, bw, &g.band_w))) return fail(rc);
+  }
+  p->pinned_bytes = 1 << 16;
+  e = cudaMallocHost(&p->pinned, p->pinned_bytes);
+  if (e != cudaSuccess) { int c = cuda_fail(e, "cudaMallocHost"); return fail(c); }
+  *out = p;
+  return MGA_OK;
+}
+
+void mga_plan_destroy(mga_plan* p) {
+  if (!p) return;
+  cudaSetDevice(p->device);
+  cudaDeviceSynchronize();
+  for (void* d : p->owned) cudaFree(d);
+  if (p->ws.base) cudaFree(p->ws.base);
+  if (p->ws_host_io.base) cudaFree(p->ws_host_io.base);
+  if (p->pinned) cudaFreeHost(p->pinned);
+  for (auto& s : p->io_streams) if (s) cudaStreamDestroy(s);
+  for (auto& ev : p->io_events) if (ev) cudaEventDestroy(ev);
+  delete p;
+}
+
+int mga_plan_resident_eligible(const mga_plan* p, int dtype) { return p && resident_eligible(p, dtype) ? 1 : 0; }
+
+int mga_plan_info(const mga_plan* p, int32_t* sm_count, int32_t* smem, int32_t* threads, int32_t* max_in) {
+  if (!p) { set_error("mga_plan_info: NULL plan"); return MGA_ERR_INVALID; }
+  if (sm_count) *sm_count = p->sm_count;
+  int th = 0;
+  int sb = resident_eligible(p, MGA_F32) ? resident_smem_bytes(p, &th) : 0;
+  if (smem) *smem = sb;
+  if (threads) *threads = th;
+  if (max_in) *max_in = p->g.max_in_deg;
+  return MGA_OK;
+}
+
+static int check_common(const mga_plan* p, const mga_params* prm, int64_t B, int dtype, const char* who) {
+  if (!p) { set_error(std::string(who) + ": NULL plan"); return MGA_ERR_INVALID; }
+  if (B <= 0) { set_error(std::string(who) + ": batch must be positive"); return MGA_ERR_INVALID; }
+  if (dtype != MGA_F32 && dtype != MGA_F64) { set_error(std::string(who) + ": dtype must be MGA_F32 or MGA_F64"); return MGA_ERR_INVALID; }
+  if (prm && (prm->ablation < MGA_ABL_NONE || prm->ablation > MGA_ABL_UT)) { set_error(std::string(who) + ": bad ablation"); return MGA_ERR_INVALID; }
+  cudaError_t e = cudaSetDevice(p->device);
+  if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+  return MGA_OK;
+}
+
+int mga_apply(mga_plan* p, int op, const mga_params* prm, const void* x, void* y, const void* mask, int64_t B,
+              int dtype, void* stream) {
+  int rc = check_common(p, prm, B, dtype, "mga_apply");
+  if (rc) return rc;
+  if (!x || !y || x == y) { set_error("mga_apply: x and y must be distinct non-NULL device pointers"); return MGA_ERR_INVALID; }
+  if (op < MGA_OP_LU || op > MGA_OP_LHS_ZD) { set_error("mga_apply: bad op"); return MGA_ERR_INVALID; }
+  if (op >= MGA_OP_LHS_X && !prm) { set_error("mga_apply: LHS operators need params"); return MGA_ERR_INVALID; }
+  return stream_apply(p, op, prm, x, y, mask, B, dtype, (cudaStream_t)stream);
+}
+
+int mga_cg_solve(mga_plan* p, int system, const mga_params* prm, const void* rhs, void* x, const void* mask_first,
+                 int64_t B, int dtype, int max_iter, double tol, int32_t* iters_out, void* alpha, void* beta,
+                 void* stream) {
+  int rc = check_common(p, prm, B, dtype, "mga_cg_solve");
+  if (rc) return rc;
+  if (!prm || !rhs || !x || max_iter < 0 || system < MGA_SYS_X || system > MGA_SYS_ZD) {
+    set_error("mga_cg_solve: bad argument");
+    return MGA_ERR_INVALID;
+  }
+  return stream_cg(p, system, prm, rhs, x, mask_first, B, dtype, max_iter, tol, iters_out, alpha, beta,
+                   (cudaStream_t)stream);
+}
+
+int mga_admm_solve(mga_plan* p, const mga_params* prm, const void* y, int y_rows, const void* mask, void* x_out,
+                   int64_t B, int dtype, int n_outer, int max_cg, double cg_tol, double admm_tol, double t_mean,
+                   double t_var, int want_diag, const mga_admm_outputs* outs, int mode, void* stream) {
+  int rc = check_common(p, prm, B, dtype, "mga_admm_solve");
+  if (rc) return rc;
+  if (!prm || !y || !x_out || n_outer < 0 || max_cg < 0) { set_error("mga_admm_solve: bad argument"); return MGA_ERR_INVALID; }
+  const bool forecast = (mask == nullptr);
+  if (forecast && y_rows != p->g.t_in) { set_error("mga_admm_solve: y must have t_in rows"); return MGA_ERR_INVALID; }
+  if (!forecast && y_rows != p->g.T) { set_error("mga_admm_solve: mask mode needs y with T rows"); return MGA_ERR_INVALID; }
+  mga_admm_outputs none{};
+  if (!outs) outs = &none;
+  const bool fixed = cg_tol <= 0 && admm_tol <= 0;
+  const bool can_res = forecast && fixed && prm->ablation == MGA_ABL_NONE && resident_eligible(p, dtype);
+  if (mode == MGA_MODE_RESIDENT && !can_res) {
+    set_error("mga_admm_solve: resident mode needs fp32, fixed iteration counts, ablation None, time-invariant "
+              "weights, N <= 512, T <= 24, kd <= 9");
+    return MGA_ERR_UNSUPPORTED;
+  }
+  if (mode != MGA_MODE_STREAMING && can_res)
+    return resident_admm(p, prm, y, x_out, B, n_outer, max_cg, t_mean, t_var, want_diag, outs, (cudaStream_t)stream);
+  return stream_admm(p, prm, y, y_rows, mask, x_out, B, dtype, n_outer, max_cg, cg_tol, admm_tol, t_mean, t_var,
+                     want_diag, outs, (cudaStream_t)stream);
+}
+
+// End-to-end entry point with host buffers: the batch is cut into chunks; chunk c+1 is uploaded
+// and chunk c-1 downloaded while chunk c computes (three streams, events for ordering).
+int mga_admm_solve_host(mga_plan* p, const mga_params* prm, const void* y_host, int y_rows, void* x_host, int64_t B,
+                        int dtype, int n_outer, int max_cg, double t_mean, double t_var, int want_diag,
+                        double* diag_host, double* dx_sum_host, int mode, int64_t chunk) {
+  int rc = check_common(p, prm, B, dtype, "mga_admm_solve_host");
+  if (rc) return rc;
+  if (!prm || !y_host || !x_host) { set_error("mga_admm_solve_host: NULL buffer"); return MGA_ERR_INVALID; }
+  if (y_rows != p->g.t_in) { set_error("mga_admm_solve_host: y must have t_in rows"); return MGA_ERR_INVALID; }
+  const GraphDev& g = p->g;
+  const size_t es = dtype == MGA_F32 ? 4 : 8;
+  if (chunk <= 0) chunk = std::max<int64_t>(1, std::min<int64_t>(B, (B + 3) / 4));
+  chunk = std::min(chunk, B);
+  const int64_t nchunk = (B + chunk - 1) / chunk;
+  const size_t y_win = (size_t)y_rows * g.N * es, x_win = (size_t)g.T * g.N * es;
+  const size_t diag_n = (size_t)n_outer * MGA_DIAG_COLS, dx_n = (size_t)n_outer * g.T * g.N;
+  // device staging: 2 y-slots, 2 x-slots, diag + dx_sum accumulators
+  size_t off_y = 0, off_x = 2 * (size_t)chunk * y_win, off_d = off_x + 2 * (size_t)chunk * x_win;
+  off_d = (off_d + 255) & ~(size_t)255;
+  size_t total = off_d + (diag_n + dx_n) * sizeof(double);
+  rc = ensure_workspace(p, p->ws_host_io, total);
+  if (rc) return rc;
+  char* base = static_cast<char*>(p->ws_host_io.base);
+  for (auto& s : p->io_streams) if (!s) MGA_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  for (auto& ev : p->io_events) if (!ev) MGA_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  cudaStream_t s_up = p->io_streams[0], s_run = p->io_streams[1], s_dn = p->io_streams[2];
+  cudaEvent_t* up_done = &p->io_events[0];    // [2] y slot filled
+  cudaEvent_t* run_done = &p->io_events[2];   // [2] x slot filled
+  cudaEvent_t* y_free = &p->io_events[4];     // [2] y slot consumed
+  cudaEvent_t* x_free = &p->io_events[6];     // [2] x slot drained
+  double* d_diag = reinterpret_cast<double*>(base + off_d);
+  double* d_dx = d_diag + diag_n;
+  mga_admm_outputs outs{};
+  if (want_diag) {
+    outs.diag = d_diag;
+    outs.dx_sum = d_dx;
+    MGA_CUDA(cudaMemsetAsync(d_diag, 0, (diag_n + dx_n) * sizeof(double), s_run));
+  }
+  for (int64_t c = 0; c < nchunk; ++c) {
+    const int slot = (int)(c & 1);
+    const int64_t b0 = c * chunk, nb = std::min(chunk, B - b0);
+    char* dy = base + off_y + (size_t)slot * chunk * y_win;
+    char* dx = base + off_x + (size_t)slot * chunk * x_win;
+    if (c >= 2) MGA_CUDA(cudaStreamWaitEvent(s_up, y_free[slot], 0));
+    MGA_CUDA(cudaMemcpyAsync(dy, static_cast<const char*>(y_host) + (size_t)b0 * y_win, (size_t)nb * y_win,
+                             cudaMemcpyHostToDevice, s_up));
+    MGA_CUDA(cudaEventRecord(up_done[slot], s_up));
+    MGA_CUDA(cudaStreamWaitEvent(s_run, up_done[slot], 0));
+    if (c >= 2) MGA_CUDA(cudaStreamWaitEvent(s_run, x_free[slot], 0));
+    // diagnostics accumulate across chunks (the kernels add into diag / dx_sum)
+    rc = mga_admm_solve(p, prm, dy, y_rows, nullptr, dx, nb, dtype, n_outer, max_cg, -1.0, -1.0, t_mean, t_var,
+                        want_diag | 2, &outs, mode, s_run);
+    if (rc) { cudaDeviceSynchronize(); return rc; }
+    MGA_CUDA(cudaEventRecord(run_done[slot], s_run));
+    MGA_CUDA(cudaEventRecord(y_free[slot], s_run));
+    MGA_CUDA(cudaStreamWaitEvent(s_dn, run_done[slot], 0));
+    MGA_CUDA(cudaMemcpyAsync(static_cast<char*>(x_host) + (size_t)b0 * x_win, dx, (size_t)nb * x_win,
+                             cudaMemcpyDeviceToHost, s_dn));
+    MGA_CUDA(cudaEventRecord(x_free[slot], s_dn));
+  }
+  if (want_diag) {
+    MGA_CUDA(cudaStreamSynchronize(s_run));
+    if (diag_host) MGA_CUDA(cudaMemcpy(diag_host, d_diag, diag_n * sizeof(double), cudaMemcpyDeviceToHost));
+    if (dx_sum_host) MGA_CUDA(cudaMemcpy(dx_sum_host, d_dx, dx_n * sizeof(double), cudaMemcpyDeviceToHost));
+  }
+  MGA_CUDA(cudaStreamSynchronize(s_dn));
+  MGA_CUDA(cudaStreamSynchronize(s_run));
+  return MGA_OK;
+}
+
+}  // extern "C"
