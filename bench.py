@@ -1,0 +1,379 @@
+#!/usr/bin/env python
+"""Benchmark of the Mixed-Graph-ADMM solver hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--batch B]
+
+One "step" = one pass of the hot path (the whole of ``combined_loop``: 5 outer ADMM iterations x
+3 CG solves x 10 iterations, diagnostics on) over one batch of synthetic PEMS04-shaped windows
+(307 nodes, kNN k=6, T=12, t_in=6, fp32) — BASELINE.json configs[1].  Windows are independent, so
+N GPUs each take their own batch of ``--batch`` windows (weak scaling, no data-path collective).
+
+Prints ONE JSON line (rank 0):
+  value      windows/s, whole job, inputs resident in HBM, C-ABI call ``mga_admm_solve``
+  e2e        windows/s through the public API ``ADMM_algorithm.combined_loop`` with HOST (pinned)
+             buffers: host->device copy of y, solve, device->host copy of x inside the timed region
+  roofline   the dominant kernel against the measured HBM peak (algorithmic bytes: see DESIGN.md §5)
+  cpu_baseline   the oracle port of the reference's torch-CPU path on the host cores (bounded sample)
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+N_NODES, K_NN, T_LEN, T_IN = 307, 6, 12, 6
+N_OUTER, N_CG = 5, 10
+WORKLOAD = "PEMS04-shaped synthetic: 307 nodes, kNN k=6, T=12, t_in=6, full mixed graph (GLR+DGTV+DGLR), " \
+           "5 outer x 3 CG x 10 iters, fp32"
+
+
+def algorithmic_bytes_per_point(n_outer=N_OUTER, n_cg=N_CG, t_in=T_IN, T=T_LEN):
+    """Bytes a streaming implementation must move per lattice point for the whole schedule
+    (DESIGN.md §5): 48 B per CG iteration for the 2-hop systems, 40 B for z_u."""
+    hy = 4.0 * t_in / T
+    per_outer = (
+        (6 * 4 + hy + 4)                 # RHS_x: gamma, phi, zu, zd, gu, gd, y -> rhs
+        + (20 + 12) + 48 * n_cg          # x solve: A x0 (q write+read), r = rhs - A x0; iterations
+        + 12 + (8 + 12) + 40 * n_cg      # RHS_zu; z_u solve
+        + 12 + (20 + 12) + 48 * n_cg     # RHS_zd; z_d solve
+        + 16 + 16 + 16                   # dual ascents, phi prox + gamma
+        + (8 * 4 + hy)                   # diagnostics: x, x_old, zu, zu_old, zd, zd_old, phi, phi_old, y
+    )
+    init = hy + 6 * 4                    # y -> x, zu, zd, phi, (constant duals are not traffic)
+    return n_outer * per_outer + init
+
+
+def cg_iter_bytes_per_point(system="x"):
+    return 40.0 if system == "zu" else 48.0
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            if len(r) >= 9:
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def build_problem(batch, seed, device=None, mode="auto"):
+    from mixed_graph_admm_b200 import synth
+    from mixed_graph_admm_b200.ADMM import ADMM_algorithm
+    gi = synth.road_graph(N_NODES, 1.1, seed=4)
+    blk = ADMM_algorithm(gi, synth.admm_info(N_NODES), use_kNN=True, k=K_NN, u_sigma=50, d_sigma=50, t_in=T_IN,
+                         T=T_LEN, device=device, mode=mode)
+    blk.max_ADMM_iter, blk.max_CG_iter, blk.CG_tol, blk.ADMM_tol = N_OUTER, N_CG, -1.0, -1.0
+    y = synth.signals(batch, T_IN, N_NODES, seed=seed)
+    return blk, y
+
+
+def oracle_problem(blk):
+    from mixed_graph_admm_b200 import synth
+    from oracle import admm_oracle as O
+    og = O.OracleGraph(nbr=blk.connect_list, u_w=blk.u_ew, d_w=blk.d_ew)
+    prm = O.OracleParams(**synth.admm_info(N_NODES), t_in=T_IN, T=T_LEN)
+    return O, og, prm
+
+
+def time_oracle(blk, y, repeats):
+    """windows/s of the CPU oracle port (all host threads) on the sample y; best of `repeats`."""
+    O, og, prm = oracle_problem(blk)
+    torch.set_num_threads(os.cpu_count() or 1)
+    best = float("inf")
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        O.admm_combined(og, prm, y, max_admm_iter=N_OUTER, max_cg_iter=N_CG, cg_tol=-1.0, admm_tol=-1.0)
+        best = min(best, time.perf_counter() - t0)
+    return y.size(0) / best, best
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path (its oracle port —
+    the Python reference cannot travel to the GPU box) on the host cores; rank 0 only."""
+    if rank != 0:
+        return
+    from mixed_graph_admm_b200 import synth
+    from mixed_graph_admm_b200.ADMM import ADMM_algorithm  # noqa: F401  (graph construction only)
+    sample = 32
+    blk, y = build_problem_cpu(sample)
+    for _ in range(min(args.warmup, 1)):
+        time_oracle(blk, y, 1)
+    times = []
+    for _ in range(args.steps):
+        _, dt = time_oracle(blk, y, 1)
+        times.append(dt)
+    tot = sum(times)
+    val = sample * len(times) / tot
+    cores = torch.get_num_threads()
+    line = {"impl": "reference", "metric": "ADMM windows/sec (PEMS04 shape)", "value": val, "unit": "windows/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch_per_step": sample},
+            "cpu_baseline": {"value": val, "unit": "windows/s", "cores": cores, "kind": "port",
+                             "sample": f"{sample} windows of the workload per step, torch-CPU oracle port "
+                                       f"(bit-identical to the reference), {cores} threads"},
+            "e2e": {"value": val, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def build_problem_cpu(batch):
+    """Graph tables without touching CUDA (for the reference arm)."""
+    from mixed_graph_admm_b200 import synth
+    from mixed_graph_admm_b200 import utils as U
+
+    class Tables:
+        pass
+
+    gi = synth.road_graph(N_NODES, 1.1, seed=4)
+    t = Tables()
+    nodes, dists = U.k_nearest_neighbors(N_NODES, gi["u_edges"], gi["u_dist"], K_NN)
+    t.connect_list = nodes.to(torch.int64)
+    t.u_ew = U.expand_time_dimension(U.undirected_graph_from_distance(t.connect_list, dists, u_sigma=50), T_LEN)
+    t.d_ew = U.expand_time_dimension(U.directed_graph_from_distance(t.connect_list, dists, d_sigma=50), T_LEN - 1)
+    return t, synth.signals(batch, T_IN, N_NODES, seed=0)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=1024, help="windows per GPU per step")
+    ap.add_argument("--mode", default="auto", choices=["auto", "resident", "streaming"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cg-batch", type=int, default=16384, help="batch of the streaming CG-iteration probe")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the solver has no CPU fallback")
+    import ctypes as C
+
+    import torch.distributed as dist
+    from mixed_graph_admm_b200 import _cabi
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    warm = max(args.warmup, 3)
+    B = args.batch
+    blk, y_host = build_problem(B, seed=rank, device=dev, mode=args.mode)
+    L = _cabi.lib()
+    plan, prm = blk._plan(), blk._params()
+    y_dev = y_host.to(dev)
+    y_pin = y_host.pin_memory()
+    x_dev = torch.empty((B, T_LEN, N_NODES, 1), dtype=torch.float32, device=dev)
+    diag = torch.zeros((N_OUTER, _cabi.DIAG_COLS), dtype=torch.float64, device=dev)
+    dxs = torch.zeros((N_OUTER, T_LEN, N_NODES), dtype=torch.float64, device=dev)
+    outs = _cabi.AdmmOutputs()
+    outs.diag, outs.dx_sum = diag.data_ptr(), dxs.data_ptr()
+    from mixed_graph_admm_b200.ADMM import _regression_consts
+    t_mean, t_var = _regression_consts(T_IN)
+    stream = torch.cuda.current_stream(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
+
+    def step_device():
+        _cabi.check(L.mga_admm_solve(plan.handle, C.byref(prm), _cabi.ptr(y_dev), T_IN, None, _cabi.ptr(x_dev), B,
+                                     _cabi.MGA_F32, N_OUTER, N_CG, -1.0, -1.0, t_mean, t_var, 1, C.byref(outs),
+                                     _cabi.MODE[args.mode], stream.cuda_stream))
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- device-resident throughput ("value")
+    for _ in range(warm):
+        step_device()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    l0 = L.mga_launch_count()
+    barrier()
+    t_wall0 = time.perf_counter()
+    for s in range(args.steps):
+        flush.fill_(s & 0xff)                 # L2 flush between timed iterations (outside the events)
+        ev[s][0].record(stream)
+        step_device()
+        ev[s][1].record(stream)
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = L.mga_launch_count() - l0
+    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
+    clocks = sampler.stop() if rank == 0 else None
+    tmax = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    dev_ms = float(tmax.item())
+    ms_per_step = dev_ms / args.steps
+    value = world * B * args.steps / (dev_ms * 1e-3)
+    kernel_mode = "resident" if (args.mode != "streaming" and L.mga_plan_resident_eligible(plan.handle, 0)) \
+        else "streaming"
+
+    # ---- end to end through the public API with host buffers ("e2e")
+    blk.mode = args.mode
+    for _ in range(2):
+        blk.combined_loop(y_pin, print_info=False)
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(e2e_steps):
+        x_host = blk.combined_loop(y_pin, print_info=False)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_val = world * B * e2e_steps / float(te.item())
+    assert x_host.shape == (B, T_LEN, N_NODES, 1) and not x_host.is_cuda and blk.last_mode == "host"
+
+    line = None
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        npts = T_LEN * N_NODES
+        alg_bytes = algorithmic_bytes_per_point() * npts * B
+        achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
+        hbm_io = (B * T_IN * N_NODES * 4 + B * npts * 4) / (ms_per_step * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": "k_admm_resident" if kernel_mode == "resident" else "streaming kernels",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src,
+                "note": ("algorithmic bytes = what a streaming implementation must move (DESIGN.md §5); the "
+                         "resident kernel keeps them in registers/SMEM, its real HBM I/O is y in + x out = "
+                         f"{hbm_io:.1f} GB/s") if kernel_mode == "resident" else "streaming mode"}
+        line = {"metric": "ADMM windows/sec (PEMS04 shape)", "value": value, "unit": "windows/s", "n_gpus": world,
+                "steps": args.steps, "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world,
+                           "parallelism": f"windows sharded over {world} GPU(s), no collective",
+                           "kernel_mode": kernel_mode, "diagnostics": "on", "l2": "flushed between timed steps"},
+                "e2e": {"value": e2e_val, "unit": "windows/s", "h2d_bytes_per_step": int(y_pin.numel() * 4),
+                        "d2h_bytes_per_step": int(B * npts * 4 + N_OUTER * (_cabi.DIAG_COLS + npts) * 8),
+                        "steps": e2e_steps, "api": "ADMM_algorithm.combined_loop(y_pinned_cpu) -> mga_admm_solve_host"},
+                "gpu_launches": int(launches), "wall_s_timed_region": t_wall, "clocks": clocks, "roofline": roof}
+
+    # ---- the fused CG iteration in streaming mode vs the HBM roofline (vectors larger than L2)
+    if rank == 0:
+        try:
+            Bc = args.cg_batch
+            n = Bc * T_LEN * N_NODES
+            g = torch.Generator(device="cpu").manual_seed(1)
+            rhs = torch.rand(Bc, T_LEN, N_NODES, 1, generator=g).to(dev)
+            xw = torch.zeros_like(rhs)
+            res = {}
+            for sysname in ("x", "zu"):
+                def solve():
+                    _cabi.check(L.mga_cg_solve(plan.handle, _cabi.SYS[sysname], C.byref(prm), _cabi.ptr(rhs),
+                                               _cabi.ptr(xw), None, Bc, _cabi.MGA_F32, N_CG, -1.0, None, None, None,
+                                               stream.cuda_stream))
+                for _ in range(3):
+                    xw.zero_()
+                    solve()
+                torch.cuda.synchronize(dev)
+                reps, tot = 5, 0.0
+                for _ in range(reps):
+                    xw.zero_()
+                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    a.record(stream)
+                    solve()
+                    b.record(stream)
+                    torch.cuda.synchronize(dev)
+                    tot += a.elapsed_time(b)
+                ms = tot / reps
+                per_it = cg_iter_bytes_per_point(sysname)
+                init_b = 32.0 if sysname == "x" else 20.0
+                gbs = (per_it * N_CG + init_b) * n / (ms * 1e-3) / 1e9
+                res[sysname] = {"ms_per_solve": ms, "ms_per_iter": ms / (N_CG + 1), "achieved": gbs,
+                                "frac": gbs / peak, "bytes_per_point_per_iter": per_it}
+            line["cg_iter_streaming"] = {"batch": Bc, "unit": "GB/s", "peak": peak, "vector_mb": n * 4 / 1e6,
+                                         "systems": res,
+                                         "note": "mga_cg_solve, 10 fixed iterations, vectors exceed L2"}
+            del rhs, xw
+        except Exception as e:  # the headline line must still be printed
+            line["cg_iter_streaming"] = {"error": str(e)[:200]}
+
+    # ---- CPU baseline on the host cores (rank 0, N = 1 only; bounded sample)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sample = 32
+        ys = y_host[:sample].contiguous()
+        val, dt = time_oracle(blk, ys, 3)
+        cores = torch.get_num_threads()
+        # and parity of the timed kernel on that very sample
+        from oracle import admm_oracle as O
+        _, og, pr = oracle_problem(blk)
+        tr = O.admm_combined(og, pr, ys, max_admm_iter=N_OUTER, max_cg_iter=N_CG, cg_tol=-1.0, admm_tol=-1.0)
+        err = ((x_host[:sample].double() - tr.x.double()).norm() / tr.x.double().norm()).item()
+        line["cpu_baseline"] = {"value": val, "unit": "windows/s", "cores": cores, "kind": "port",
+                                "sample": f"first {sample} of the {B} windows, best of 3, torch-CPU oracle port "
+                                          f"(bit-identical to the reference), {cores} threads, {dt:.2f} s"}
+        line["parity_vs_oracle_rel_l2"] = err
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

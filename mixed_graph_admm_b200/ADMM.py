@@ -131,14 +131,26 @@ class ADMM_algorithm():
         self._reset_lists(all_lists=True)
 
         # ---- not in the reference
-        self.device = _device_of(device)
+        self._device_arg = device       # resolved on first use: construction itself needs no GPU
+        self._device = None
         self.mode = mode
+        self.diag_reduce = None         # multi-GPU hook: (diag, dx_sum, B) -> global (diag, dx_sum, B)
         self.strict_quirks = False      # True: reproduce the B>1 converged-return ValueError (quirk Q2)
         self.keep_iterates = False      # True: combined_loop leaves z_u, z_d, phi, duals in last_iterates
         self.last_iterates = None
         self.last_mode = None
         self._plan_key = None
         self._plan_obj = None
+
+    @property
+    def device(self):
+        if self._device is None:
+            self._device = _device_of(self._device_arg)
+        return self._device
+
+    @device.setter
+    def device(self, value):
+        self._device_arg, self._device = value, None
 
     # ------------------------------------------------------------------ bookkeeping
     def _reset_lists(self, all_lists):
@@ -462,6 +474,9 @@ class ADMM_algorithm():
                 dx_h = dx_d.cpu().numpy()
                 self.last_iterates = {k: v.to(out_device) for k, v in its.items()} if want_iter else None
                 self.last_mode = 'device'
+        if self.diag_reduce is not None:      # shards of one batch: sum the partial sums over the ranks
+            diag_h, dx_h, B = self.diag_reduce(diag_h, dx_h, B)
+            alpha = beta = None               # per-window CG coefficients stay with their shard
         self._fill_lists(diag_h, dx_h, cg_iters, int(outer_done.value), alpha, beta, B, y.dtype, out_device,
                          print_info)
         return x.to(out_device)

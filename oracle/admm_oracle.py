@@ -267,6 +267,7 @@ class OracleTrace:
     dglr: list = field(default_factory=list)
     dgtv: list = field(default_factory=list)
     recover: list = field(default_factory=list)
+    dx_mean: list = field(default_factory=list)      # (x - x_old).mean(0), the tensor behind delta_x_per_step
     outer_iters: int = 0
 
 
@@ -324,6 +325,7 @@ def admm_combined(g: OracleGraph, prm: OracleParams, y, mask=None, max_admm_iter
         # diagnostics, ADMM.py:609-643
         pri, dual = [], []
         tr.x_shift.append(torch.norm(x - x_old).item())
+        tr.dx_mean.append((x - x_old).mean(0))
         tr.delta_x_per_step.append((x - x_old).mean(0).norm(dim=[1, 2]))
         pri.append(torch.norm(x - zu).item())
         dual.append(torch.norm(zu - zu_old).item())

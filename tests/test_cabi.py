@@ -1,0 +1,96 @@
+"""The C-ABI library: it builds for sm_100a without a GPU, loads, and exports every symbol
+include/mga.h declares.  No compute calls here (CPU only)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "mga.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mga_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_header_declares_the_documented_entry_points():
+    names = _declared()
+    for must in ["mga_plan_create", "mga_plan_destroy", "mga_apply", "mga_cg_solve", "mga_admm_solve",
+                 "mga_admm_solve_host", "mga_prox_phi_dual", "mga_dual_ascent", "mga_rhs_x", "mga_initial_guess",
+                 "mga_knn_build", "mga_last_error"]:
+        assert must in names
+
+
+def test_library_exports_every_declared_symbol(libmga):
+    from mixed_graph_admm_b200 import _cabi
+    for name in _declared():
+        assert hasattr(libmga, name), f"{name} declared in mga.h but not exported"
+    assert sorted(_cabi.EXPORTS) == _declared()
+    assert libmga.mga_version() == 100
+
+
+def test_library_is_sm100a_with_lineinfo(libmga):
+    from mixed_graph_admm_b200 import _cabi
+    out = subprocess.run(["cuobjdump", "-lelf", _cabi.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out, out[:500]
+    assert "k_admm_resident" in subprocess.run(["cuobjdump", "-res-usage", _cabi.LIB_PATH], capture_output=True,
+                                               text=True).stdout
+
+
+def test_struct_layouts_match_header(libmga):
+    """ctypes mirrors of the header structs (sizes as a C compiler lays them out)."""
+    from mixed_graph_admm_b200 import _cabi
+    code = r'''
+    #include <stdio.h>
+    #include "mga.h"
+    int main(void){ printf("%zu %zu %zu %d\n", sizeof(mga_graph_desc), sizeof(mga_params), sizeof(mga_admm_outputs), MGA_DIAG_COLS); return 0; }
+    '''
+    import tempfile
+    with tempfile.TemporaryDirectory() as td:
+        src = os.path.join(td, "s.c")
+        open(src, "w").write(code)
+        exe = os.path.join(td, "s")
+        subprocess.run(["gcc", "-I", os.path.join(ROOT, "include"), src, "-o", exe], check=True)
+        a, b, c, cols = map(int, subprocess.run([exe], capture_output=True, text=True).stdout.split())
+    assert C.sizeof(_cabi.GraphDesc) == a
+    assert C.sizeof(_cabi.Params) == b
+    assert C.sizeof(_cabi.AdmmOutputs) == c
+    assert _cabi.DIAG_COLS == cols
+
+
+def test_bad_arguments_return_status_not_crash(libmga):
+    from mixed_graph_admm_b200 import _cabi
+    h = C.c_void_p()
+    assert libmga.mga_plan_create(None, 0, C.byref(h)) == _cabi.ERR_INVALID
+    assert b"NULL" in libmga.mga_last_error()
+    d = _cabi.GraphDesc()
+    d.n_nodes, d.T, d.t_in = 0, 1, 1
+    assert libmga.mga_plan_create(C.byref(d), 0, C.byref(h)) == _cabi.ERR_INVALID
+    libmga.mga_plan_destroy(None)        # no-op
+    assert libmga.mga_apply(None, 0, None, None, None, None, 1, 0, None) == _cabi.ERR_INVALID
+
+
+def test_no_cuda_device_fails_loudly(libmga):
+    """There is no CPU fallback: without a usable device plan creation returns MGA_ERR_CUDA."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from mixed_graph_admm_b200 import _cabi
+    nbr = torch.zeros((4, 1), dtype=torch.int64)
+    w = torch.ones((4, 1), dtype=torch.float32)
+    d = _cabi.GraphDesc(n_nodes=4, T=3, t_in=2, ku=0, nbr_u=None, u_w=None, u_w_T=1, kd=1, nbr_d=nbr.data_ptr(),
+                        d_w=w.data_ptr(), d_w_T=1, ldrt_mode=0, temporal=0)
+    h = C.c_void_p()
+    assert libmga.mga_plan_create(C.byref(d), 0, C.byref(h)) == _cabi.ERR_CUDA
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "mixed_graph_admm_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                txt = open(os.path.join(dp, f)).read()
+                assert "oracle" not in txt.replace("the oracle port", ""), f"{f} mentions the oracle"

@@ -1,0 +1,286 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the golden fixtures.
+
+Tolerances (BASELINE.json north_star): relative 1e-5 in fp32 on x, z_u, z_d, phi (we hold the duals
+to the same bar), 1e-11 in fp64; CG iteration counts equal in tolerance mode.  The oracle is
+bit-identical to the reference (tests/test_oracle.py), so "vs golden" is "vs the reference"."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from _cases import FIXED_CASES, ITERATES, TOL_CASES, Golden, max_rel, oracle_from_golden, rel_err, solver_from_golden
+
+pytestmark = pytest.mark.gpu
+
+TOL = {torch.float32: 1e-5, torch.float64: 1e-11}
+OP_TOL = {torch.float32: 2e-6, torch.float64: 1e-13}
+
+
+def _resident_ok(g):
+    return (g.dtype == torch.float32 and g.mask is None and g.ctor.get("ablation", "None") == "None"
+            and int(g.ctor.get("skip_connection", 1)) == 1)
+
+
+def _check_iterates(blk, x, g, tol):
+    got = dict(blk.last_iterates, x=x)
+    for k in ITERATES:
+        if not g.has(k):
+            continue
+        ref = g.t(k)
+        assert got[k].shape == ref.shape
+        e = rel_err(got[k], ref)
+        assert e <= tol, f"{g.name}: {k} rel-L2 error {e:.3e} > {tol}"
+        assert max_rel(got[k], ref) <= 20 * tol, f"{g.name}: {k} pointwise error {max_rel(got[k], ref):.3e}"
+
+
+def _check_lists(blk, g, rtol):
+    np.testing.assert_allclose(np.array(blk.x_shift_list), g.z["x_shift"], rtol=rtol)
+    np.testing.assert_allclose(np.array(blk.p_res_list), g.z["p_res"], rtol=rtol, atol=1e-7)
+    np.testing.assert_allclose(np.array(blk.d_res_list), g.z["d_res"], rtol=rtol, atol=1e-7)
+    np.testing.assert_allclose(np.array(blk.recover_list), g.z["recover"], rtol=rtol, atol=1e-7)
+    np.testing.assert_allclose([v.item() for v in blk.GLR_list], g.z["glr"], rtol=rtol)
+    np.testing.assert_allclose([v.item() for v in blk.DGTV_list], g.z["dgtv"], rtol=rtol)
+    np.testing.assert_allclose([v.item() for v in blk.DGLR_list], g.z["dglr"], rtol=rtol)
+    np.testing.assert_allclose(torch.stack([v.cpu() for v in blk.delta_x_per_step]).numpy(),
+                               g.z["delta_x_per_step"], rtol=10 * rtol, atol=1e-7)
+    assert isinstance(blk.GLR_list[0], torch.Tensor) and blk.GLR_list[0].dim() == 0      # quirk Q11
+    assert isinstance(blk.x_shift_list[0], float)
+
+
+@pytest.mark.parametrize("name", [c for c in FIXED_CASES if c != "tiny_mask"])
+def test_operators_match_reference(name):
+    g = Golden(name)
+    blk = solver_from_golden(g)
+    x, gam = g.t("probe_x"), g.t("probe_gamma")
+    tol = OP_TOL[g.dtype]
+    for op, fn in [("op_Lu", blk.apply_op_Lu), ("op_Ldr", blk.apply_op_Ldr), ("op_Ldr_T", blk.apply_op_Ldr_T),
+                   ("op_cLdr", blk.apply_op_cLdr), ("op_LHS_x", blk.LHS_x), ("op_LHS_zu", blk.LHS_zu),
+                   ("op_LHS_zd", blk.LHS_zd)]:
+        if not g.has(op):
+            continue
+        out = fn(x)
+        assert out.device == x.device and out.dtype == x.dtype
+        assert max_rel(out, g.t(op)) <= tol, f"{name}: {op} {max_rel(out, g.t(op)):.3e}"
+    assert max_rel(blk.phi_direct(x, gam), g.t("op_phi_direct")) <= tol
+
+
+def test_ldr_t_quirk_q1_row0():
+    g = Golden("anchor5")
+    blk = solver_from_golden(g)
+    x = (torch.arange(15, dtype=torch.float32) / 10).reshape(1, 3, 5, 1)
+    lt = blk.apply_op_Ldr_T(x)[0, :, :, 0]
+    np.testing.assert_allclose(lt[0], [-.537754, -.462246, -.524351, -.534284, -.441365], atol=2e-6)
+    np.testing.assert_allclose(lt[2], [1, 1.1, 1.2, 1.3, 1.4], atol=1e-6)
+
+
+@pytest.mark.parametrize("name", FIXED_CASES)
+def test_combined_loop_streaming_matches_reference(name):
+    g = Golden(name)
+    blk = solver_from_golden(g, mode="streaming")
+    blk.keep_iterates = True
+    x = blk.combined_loop(g.y.cuda(), mask=None if g.mask is None else g.mask.cuda(), print_info=False)
+    assert x.is_cuda
+    x = x.cpu()
+    blk.last_iterates = {k: v.cpu() for k, v in blk.last_iterates.items()}
+    _check_iterates(blk, x, g, TOL[g.dtype])
+    _check_lists(blk, g, 2e-5 if g.dtype == torch.float32 else 1e-10)
+    assert blk.CG_iter_x == g.z["cg_iter_x"].tolist()
+    # first CG coefficients of the first outer iteration (later ones are ratios of rounding noise)
+    a0 = torch.stack(list(blk.alpha_x[0])).cpu()[:3].double().numpy()
+    np.testing.assert_allclose(a0, g.z["alpha_x"][0, :3], rtol=1e-4 if g.dtype == torch.float32 else 1e-9)
+    assert isinstance(blk.alpha_x[0], list) and blk.alpha_x[0][0].shape == (g.y.size(0),)     # quirk Q11
+
+
+@pytest.mark.parametrize("name", [c for c in FIXED_CASES if _resident_ok(Golden(c))])
+def test_combined_loop_resident_matches_reference(name):
+    g = Golden(name)
+    blk = solver_from_golden(g, mode="resident")
+    blk.keep_iterates = True
+    x = blk.combined_loop(g.y, print_info=False)          # CPU in -> CPU out, like the reference's callers
+    assert not x.is_cuda
+    _check_iterates(blk, x, g, TOL[g.dtype])
+    _check_lists(blk, g, 2e-5)
+    a0 = torch.stack(list(blk.alpha_x[0]))[:3].double().numpy()
+    np.testing.assert_allclose(a0, g.z["alpha_x"][0, :3], rtol=1e-4)
+
+
+@pytest.mark.parametrize("name", TOL_CASES)
+def test_tolerance_mode_cg_counts_equal(name):
+    g = Golden(name)
+    blk = solver_from_golden(g)
+    blk.keep_iterates = True
+    x = blk.combined_loop(g.y, print_info=False)
+    assert blk.CG_iter_x == g.z["cg_iter_x"].tolist()
+    assert blk.CG_iter_zu == g.z["cg_iter_zu"].tolist()
+    assert blk.CG_iter_zd == g.z["cg_iter_zd"].tolist()
+    _check_iterates(blk, x, g, TOL[g.dtype])
+    assert isinstance(blk.alpha_x[0], torch.Tensor) and blk.alpha_x[0].shape == (blk.CG_iter_x[0],)   # Q11
+    k = min(3, blk.CG_iter_x[0])
+    np.testing.assert_allclose(blk.alpha_x[0][:k].double().numpy(), g.z["alpha_x"][0, :k, 0], rtol=1e-4)
+
+
+def test_cg_solver_api_against_oracle():
+    from oracle import admm_oracle as O
+    g = Golden("tiny_f64")
+    blk = solver_from_golden(g)
+    og, prm = oracle_from_golden(g)
+    gen = torch.Generator().manual_seed(5)
+    rhs = torch.randn(3, g.ctor["T"], g.meta["n_nodes"], 1, generator=gen, dtype=torch.float64)
+    x0 = torch.randn(3, g.ctor["T"], g.meta["n_nodes"], 1, generator=gen, dtype=torch.float64)
+    for fn, ofn in [(blk.LHS_x, lambda v: O.lhs_x(og, prm, v)), (blk.LHS_zu, lambda v: O.lhs_zu(og, prm, v)),
+                    (blk.LHS_zd, lambda v: O.lhs_zd(og, prm, v))]:
+        blk.max_CG_iter, blk.CG_tol = 6, -1.0
+        x, it, al, be = blk.CG_solver(fn, rhs, x0)
+        xo, ito, alo, beo = O.cg(ofn, rhs, x0, max_iter=6, tol=-1.0)
+        assert it == ito == -1 and isinstance(al, list) and len(al) == 6
+        assert rel_err(x, xo) < 1e-12
+        np.testing.assert_allclose(torch.stack(al).numpy(), torch.stack(alo).numpy(), rtol=1e-9)
+        np.testing.assert_allclose(torch.stack(be).numpy(), torch.stack(beo).numpy(), rtol=1e-9)
+        blk.max_CG_iter, blk.CG_tol = 100, 1e-8
+        x, it, al, be = blk.CG_solver(fn, rhs, None)
+        xo, ito, alo, beo = O.cg(ofn, rhs, None, max_iter=100, tol=1e-8)
+        assert it == ito and it > 0
+        assert rel_err(x, xo) < 1e-11
+        assert al.shape == (it, 3)            # B > 1 converged: (iters, B) instead of the reference's crash (Q2)
+
+
+def test_cg_known_answer_foreign_operator():
+    """CG_script.py:49-50 through CG_solver with a caller-supplied operator."""
+    g = Golden("anchor5")
+    blk = solver_from_golden(g)
+    A = torch.tensor([[4., 1.], [1., 3.]], dtype=torch.float64, device="cuda")
+    b = torch.tensor([1., 2.], dtype=torch.float64, device="cuda").reshape(1, 1, 2, 1)
+    blk.max_CG_iter, blk.CG_tol = 1000, 1e-10
+    x, it, _, _ = blk.CG_solver(lambda v: torch.einsum('ij,btjc->btic', A, v), b)
+    assert it == 2
+    np.testing.assert_allclose(x.flatten().cpu(), [1 / 11, 7 / 11], atol=1e-12)
+
+
+def test_initial_guess_kernel():
+    from mixed_graph_admm_b200.ADMM import initial_guess
+    from oracle import admm_oracle as O
+    for dt, tol in [(torch.float32, 2e-6), (torch.float64, 1e-13)]:
+        y = torch.rand(5, 6, 33, 1, generator=torch.Generator().manual_seed(1), dtype=dt)
+        assert max_rel(initial_guess(y, 6, 12), O.first_guess(y, 6, 12)) <= tol
+
+
+def test_index_out_of_bounds_raises_value_error():
+    g = Golden("tiny_f32")
+    blk = solver_from_golden(g)
+    blk.connect_list = blk.connect_list.clone()
+    blk.connect_list[0, 1] = g.meta["n_nodes"] + 3
+    with pytest.raises(ValueError, match="Index out of bounds"):
+        blk.apply_op_Ldr_T(g.t("probe_x"))
+
+
+def test_attribute_mutation_is_seen():
+    """Users mutate rho / d_ew / limits after construction: every call re-reads them."""
+    from oracle import admm_oracle as O
+    g = Golden("tiny_f32")
+    blk = solver_from_golden(g)
+    og, prm = oracle_from_golden(g)
+    x = g.t("probe_x")
+    blk.rho, prm.rho = 7.5, 7.5
+    assert max_rel(blk.LHS_x(x), O.lhs_x(og, prm, x)) < 2e-6
+    blk.d_ew = blk.d_ew * 0.5
+    og.d_w = og.d_w * 0.5
+    assert max_rel(blk.apply_op_cLdr(x), O.op_cldr(og, x)) < 2e-6
+
+
+def _pems04(B, seed=0):
+    from mixed_graph_admm_b200 import synth
+    from mixed_graph_admm_b200.ADMM import ADMM_algorithm
+    N, k, T, t_in = 307, 6, 12, 6
+    gi = synth.road_graph(N, 1.1, seed=4)
+    blk = ADMM_algorithm(gi, synth.admm_info(N), use_kNN=True, k=k, u_sigma=50, d_sigma=50, t_in=t_in, T=T)
+    blk.max_ADMM_iter, blk.max_CG_iter, blk.CG_tol, blk.ADMM_tol = 5, 10, -1.0, -1.0
+    return blk, synth.signals(B, t_in, N, seed=seed)
+
+
+def test_full_size_pems04_b1024_properties():
+    """BASELINE.json configs[1] at full size: resident == streaming, windows independent, the
+    host-buffer (end-to-end) entry equals the device entry, a seeded sample equals the oracle."""
+    from oracle import admm_oracle as O
+    blk, y = _pems04(1024)
+    g = Golden("pems04_f32")
+    assert torch.equal(blk.connect_list, g.t("connect_list")) and torch.equal(blk.d_ew, g.t("d_ew"))
+    blk.mode = "resident"
+    xr = blk.combined_loop(y.cuda(), print_info=False).cpu()
+    glr_res = [v.item() for v in blk.GLR_list]
+    blk.init_iterations('None')
+    blk.d_ew = g.t("d_ew")                       # init_iterations resets d_ew (quirk Q8); restore
+    blk.mode = "streaming"
+    xs = blk.combined_loop(y.cuda(), print_info=False).cpu()
+    assert rel_err(xr, xs) <= 1e-5
+    np.testing.assert_allclose(glr_res, [v.item() for v in blk.GLR_list][-5:], rtol=1e-5)
+    # the fixture holds the reference's result for windows 0..1 of this very batch
+    assert rel_err(xr[:2], g.t("x")) <= 1e-5 and rel_err(xs[:2], g.t("x")) <= 1e-5
+    # window independence / sharding: any slice solved alone gives the same windows
+    blk.mode = "resident"
+    sub = blk.combined_loop(y[500:700].cuda(), print_info=False).cpu()
+    assert torch.equal(sub, xr[500:700])
+    # end-to-end host entry (chunked copies) == device entry
+    xh = blk.combined_loop(y, print_info=False)
+    assert blk.last_mode == 'host' and torch.equal(xh, xr)
+    # a seeded sample against the oracle computed here
+    idx = torch.tensor([3, 257, 511, 1023])
+    og = O.OracleGraph(nbr=blk.connect_list, u_w=blk.u_ew, d_w=blk.d_ew)
+    prm = O.OracleParams(rho=blk.rho, rho_u=blk.rho_u, rho_d=blk.rho_d, mu_u=blk.mu_u, mu_d1=blk.mu_d1,
+                         mu_d2=blk.mu_d2, t_in=6, T=12)
+    tr = O.admm_combined(og, prm, y[idx], max_admm_iter=5, max_cg_iter=10, cg_tol=-1.0, admm_tol=-1.0)
+    assert rel_err(xr[idx], tr.x) <= 1e-5
+    nz = (tr.phi != 0).float().mean().item()
+    assert 0.05 < nz < 0.95, "the DGTV prox must be exercised (SURVEY.md §8d)"
+
+
+def test_long_horizon_t288_streaming():
+    """BASELINE.json configs[3] shape (T = 288), small batch, against the oracle."""
+    from mixed_graph_admm_b200 import synth
+    from mixed_graph_admm_b200.ADMM import ADMM_algorithm
+    from oracle import admm_oracle as O
+    N, k, T, t_in, B = 307, 6, 288, 144, 2
+    gi = synth.road_graph(N, 1.1, seed=4)
+    blk = ADMM_algorithm(gi, synth.admm_info(N), use_kNN=True, k=k, u_sigma=50, d_sigma=50, t_in=t_in, T=T)
+    blk.max_ADMM_iter, blk.max_CG_iter, blk.CG_tol, blk.ADMM_tol = 3, 10, -1.0, -1.0
+    y = synth.signals(B, t_in, N, seed=1)
+    x = blk.combined_loop(y, print_info=False)
+    og = O.OracleGraph(nbr=blk.connect_list, u_w=blk.u_ew, d_w=blk.d_ew)
+    prm = O.OracleParams(**synth.admm_info(N), t_in=t_in, T=T)
+    tr = O.admm_combined(og, prm, y, max_admm_iter=3, max_cg_iter=10, cg_tol=-1.0, admm_tol=-1.0)
+    assert rel_err(x, tr.x) <= 1e-5
+
+
+def test_large_graph_streaming():
+    """BASELINE.json configs[4] family (k = 8, T = 24) at N = 3000: exceeds the resident limits."""
+    from mixed_graph_admm_b200 import synth
+    from mixed_graph_admm_b200.ADMM import ADMM_algorithm
+    from oracle import admm_oracle as O
+    N, k, T, t_in, B = 3000, 8, 24, 12, 2
+    gi = synth.road_graph(N, 1.1, seed=9)
+    blk = ADMM_algorithm(gi, synth.admm_info(N), use_kNN=True, k=k, u_sigma=50, d_sigma=50, t_in=t_in, T=T)
+    blk.max_ADMM_iter, blk.max_CG_iter, blk.CG_tol, blk.ADMM_tol = 2, 10, -1.0, -1.0
+    y = synth.signals(B, t_in, N, seed=2)
+    x = blk.combined_loop(y, print_info=False)
+    og = O.OracleGraph(nbr=blk.connect_list, u_w=blk.u_ew, d_w=blk.d_ew)
+    prm = O.OracleParams(**synth.admm_info(N), t_in=t_in, T=T)
+    tr = O.admm_combined(og, prm, y, max_admm_iter=2, max_cg_iter=10, cg_tol=-1.0, admm_tol=-1.0)
+    assert rel_err(x, tr.x) <= 1e-5
+
+
+def test_t24_resident_reference_default_shape():
+    """The reference's own default window (T = 24, t_in = 12): resident kernel, TT = 24 instantiation."""
+    from mixed_graph_admm_b200 import synth
+    from mixed_graph_admm_b200.ADMM import ADMM_algorithm
+    from oracle import admm_oracle as O
+    N, k, T, t_in, B = 170, 4, 24, 12, 3
+    gi = synth.road_graph(N, 1.7, seed=8, isolate_pair=True)
+    blk = ADMM_algorithm(gi, synth.admm_info(N), use_kNN=True, k=k, u_sigma=50, d_sigma=50, t_in=t_in, T=T,
+                         mode="resident")
+    blk.max_ADMM_iter, blk.max_CG_iter, blk.CG_tol, blk.ADMM_tol = 3, 10, -1.0, -1.0
+    y = synth.signals(B, t_in, N, seed=3)
+    x = blk.combined_loop(y.cuda(), print_info=False).cpu()
+    og = O.OracleGraph(nbr=blk.connect_list, u_w=blk.u_ew, d_w=blk.d_ew)
+    prm = O.OracleParams(**synth.admm_info(N), t_in=t_in, T=T)
+    tr = O.admm_combined(og, prm, y, max_admm_iter=3, max_cg_iter=10, cg_tol=-1.0, admm_tol=-1.0)
+    assert rel_err(x, tr.x) <= 1e-5
