@@ -111,6 +111,9 @@ def main():
     ctor = dict(use_kNN=True, k=k, u_sigma=50, d_sigma=50, t_in=t_in, T=T)
     make_case("tiny_f32", gi, ai, synth.signals(B, t_in, N, seed=0), ctor, fixed(3, 5))
     make_case("tiny_f64", gi, ai, synth.signals(B, t_in, N, seed=0, dtype=torch.float64), ctor, fixed(3, 5))
+    # 2b. small DGTV weight so that the soft-threshold is active on most entries (prox exercised)
+    ai_prox = dict(ai, mu_d1=0.05)
+    make_case("tiny_prox", gi, ai_prox, synth.signals(B, t_in, N, seed=10), ctor, fixed(3, 5))
     # 3. tolerance mode, B = 1: CG iteration counts (default CG_tol 1e-8), 5 outer iterations
     make_case("tiny_tol", gi, ai, synth.signals(1, t_in, N, seed=2, smooth=True), ctor, {"max_ADMM_iter": 5})
     make_case("tiny_tol_f64", gi, ai, synth.signals(1, t_in, N, seed=2, smooth=True, dtype=torch.float64), ctor,

@@ -14,7 +14,10 @@ from _cases import FIXED_CASES, ITERATES, TOL_CASES, Golden, max_rel, oracle_fro
 pytestmark = pytest.mark.gpu
 
 TOL = {torch.float32: 1e-5, torch.float64: 1e-11}
-OP_TOL = {torch.float32: 2e-6, torch.float64: 1e-13}
+# The duals accumulate rho * (x - z) over the outer iterations (cancellation): the reference's own
+# fp32-vs-fp64 difference on them reaches 1.3e-5 (pems08_tol), so they get a 10x looser bound.
+DUAL_TOL = {torch.float32: 1e-4, torch.float64: 1e-10}
+OP_TOL = {torch.float32: 1e-6, torch.float64: 1e-14}
 
 
 def _resident_ok(g):
@@ -23,15 +26,30 @@ def _resident_ok(g):
 
 
 def _check_iterates(blk, x, g, tol):
+    """x, z_u, z_d: relative 1e-5 (L2 and sup norm).  phi = soft-threshold(L_d x - gamma/rho): its error
+    scale is that of L_d x; where the threshold zeroes almost every entry, ||phi|| is a tiny, ill-conditioned
+    denominator (the reference's own fp32-vs-fp64 difference is 1.5e-5 of ||phi|| on tiny_line2), so phi is
+    held to 1e-5 of max(||phi||, ||L_d x||).  Duals: DUAL_TOL."""
+    from oracle import admm_oracle as O
     got = dict(blk.last_iterates, x=x)
+    og, _ = oracle_from_golden(g)
+    ldx = O.op_ldr(og, g.t("x")).double()
     for k in ITERATES:
         if not g.has(k):
             continue
         ref = g.t(k)
-        assert got[k].shape == ref.shape
-        e = rel_err(got[k], ref)
-        assert e <= tol, f"{g.name}: {k} rel-L2 error {e:.3e} > {tol}"
-        assert max_rel(got[k], ref) <= 20 * tol, f"{g.name}: {k} pointwise error {max_rel(got[k], ref):.3e}"
+        assert got[k].shape == ref.shape and got[k].dtype == ref.dtype
+        diff = (got[k].double() - ref.double())
+        if k == "phi":
+            den2 = max(ref.double().norm().item(), ldx.norm().item())
+            deni = max(ref.double().abs().max().item(), ldx.abs().max().item())
+            bound = tol
+        else:
+            den2, deni = ref.double().norm().item(), ref.double().abs().max().item()
+            bound = tol if k in ("x", "zu", "zd") else DUAL_TOL[g.dtype]
+        e2, ei = diff.norm().item() / den2, diff.abs().max().item() / deni
+        assert e2 <= bound, f"{g.name}: {k} rel-L2 error {e2:.3e} > {bound}"
+        assert ei <= 2 * bound, f"{g.name}: {k} sup-norm error {ei:.3e} > {2 * bound}"
 
 
 def _check_lists(blk, g, rtol):
@@ -61,8 +79,9 @@ def test_operators_match_reference(name):
             continue
         out = fn(x)
         assert out.device == x.device and out.dtype == x.dtype
-        assert max_rel(out, g.t(op)) <= tol, f"{name}: {op} {max_rel(out, g.t(op)):.3e}"
-    assert max_rel(blk.phi_direct(x, gam), g.t("op_phi_direct")) <= tol
+        assert rel_err(out, g.t(op)) <= tol, f"{name}: {op} rel-L2 {rel_err(out, g.t(op)):.3e}"
+        assert max_rel(out, g.t(op)) <= 2 * tol, f"{name}: {op} sup-norm {max_rel(out, g.t(op)):.3e}"
+    assert rel_err(blk.phi_direct(x, gam), g.t("op_phi_direct")) <= tol
 
 
 def test_ldr_t_quirk_q1_row0():
@@ -160,9 +179,9 @@ def test_cg_known_answer_foreign_operator():
 def test_initial_guess_kernel():
     from mixed_graph_admm_b200.ADMM import initial_guess
     from oracle import admm_oracle as O
-    for dt, tol in [(torch.float32, 2e-6), (torch.float64, 1e-13)]:
+    for dt, tol in [(torch.float32, 1e-6), (torch.float64, 1e-14)]:
         y = torch.rand(5, 6, 33, 1, generator=torch.Generator().manual_seed(1), dtype=dt)
-        assert max_rel(initial_guess(y, 6, 12), O.first_guess(y, 6, 12)) <= tol
+        assert rel_err(initial_guess(y, 6, 12), O.first_guess(y, 6, 12)) <= tol
 
 
 def test_index_out_of_bounds_raises_value_error():
@@ -182,10 +201,10 @@ def test_attribute_mutation_is_seen():
     og, prm = oracle_from_golden(g)
     x = g.t("probe_x")
     blk.rho, prm.rho = 7.5, 7.5
-    assert max_rel(blk.LHS_x(x), O.lhs_x(og, prm, x)) < 2e-6
+    assert rel_err(blk.LHS_x(x), O.lhs_x(og, prm, x)) < 1e-6
     blk.d_ew = blk.d_ew * 0.5
     og.d_w = og.d_w * 0.5
-    assert max_rel(blk.apply_op_cLdr(x), O.op_cldr(og, x)) < 2e-6
+    assert rel_err(blk.apply_op_cLdr(x), O.op_cldr(og, x)) < 1e-6
 
 
 def _pems04(B, seed=0):
