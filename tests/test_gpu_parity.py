@@ -105,9 +105,10 @@ def test_combined_loop_streaming_matches_reference(name):
     _check_iterates(blk, x, g, TOL[g.dtype])
     _check_lists(blk, g, 2e-5 if g.dtype == torch.float32 else 1e-10)
     assert blk.CG_iter_x == g.z["cg_iter_x"].tolist()
-    # first CG coefficients of the first outer iteration (later ones are ratios of rounding noise)
-    a0 = torch.stack(list(blk.alpha_x[0])).cpu()[:3].double().numpy()
-    np.testing.assert_allclose(a0, g.z["alpha_x"][0, :3], rtol=1e-4 if g.dtype == torch.float32 else 1e-9)
+    # first CG coefficients of the first outer iteration (later ones are ratios of rounding noise; the
+    # diagonal x-system of ablation 'DGTV' has two distinct eigenvalues and is solved after 2 iterations)
+    a0 = torch.stack(list(blk.alpha_x[0])).cpu()[:2].double().numpy()
+    np.testing.assert_allclose(a0, g.z["alpha_x"][0, :2], rtol=1e-4 if g.dtype == torch.float32 else 1e-9)
     assert isinstance(blk.alpha_x[0], list) and blk.alpha_x[0][0].shape == (g.y.size(0),)     # quirk Q11
 
 
