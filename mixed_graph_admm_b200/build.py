@@ -14,7 +14,7 @@ OUT_DIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(OUT_DIR, "libmga.so")
 SOURCES = ["mga_plan.cu", "mga_stream.cu", "mga_resident.cu", "mga_knn.cpp"]
 # the resident kernel is instantiated once per (T bound, K bound), one translation unit each
-RESIDENT_VARIANTS = [(12, 5), (12, 7), (12, 9), (24, 5), (24, 7), (24, 9)]
+RESIDENT_VARIANTS = [(ch, k) for ch in (1, 2, 3) for k in (5, 7, 9)]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-O3", "-I", os.path.join(ROOT, "include"), "-I", CSRC]
 
@@ -55,11 +55,11 @@ def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) 
 
     inst = os.path.join(CSRC, "mga_resident_inst.cu")
     for tt, k in RESIDENT_VARIANTS:
-        obj = os.path.join(OUT_DIR, f"mga_resident_{tt}_{k}.o")
+        obj = os.path.join(OUT_DIR, f"mga_resident_ch{tt}_k{k}.o")
         objs.append(obj)
         if force or _stale(obj, [inst] + headers):
             jobs.append([nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if ptxas_info else []) +
-                        [f"-DMGA_TT={tt}", f"-DMGA_K={k}", "-c", inst, "-o", obj])
+                        [f"-DMGA_CH={tt}", f"-DMGA_K={k}", "-c", inst, "-o", obj])
 
     def run(cmd):
         if verbose:

@@ -6,38 +6,47 @@
 
 namespace mga {
 
-#define MGA_DECL(TT, K) int resident_launch_##TT##_##K(mga_plan*, ResArgs&, int, cudaStream_t);
-MGA_DECL(12, 5) MGA_DECL(12, 7) MGA_DECL(12, 9) MGA_DECL(24, 5) MGA_DECL(24, 7) MGA_DECL(24, 9)
+#define MGA_DECL(CH, K) int resident_launch_##CH##_##K(mga_plan*, ResArgs&, const ResGeom&, cudaStream_t);
+MGA_DECL(1, 5) MGA_DECL(1, 7) MGA_DECL(1, 9) MGA_DECL(2, 5) MGA_DECL(2, 7) MGA_DECL(2, 9)
+MGA_DECL(3, 5) MGA_DECL(3, 7) MGA_DECL(3, 9)
 #undef MGA_DECL
 
-constexpr int kResMaxN = 512;
 constexpr int kResMaxT = 24;
 constexpr int kResMaxK = 9;
+
+static bool geometry(const mga_plan* p, ResGeom* geo) {
+  const GraphDev& g = p->g;
+  if (!res_geometry(g, res_forced_ch(), geo) && !res_geometry(g, 0, geo)) return false;
+  return geo->core_bytes <= (size_t)p->max_smem_optin;
+}
 
 bool resident_eligible(const mga_plan* p, int dtype) {
   const GraphDev& g = p->g;
   if (dtype != MGA_F32) return false;
   if (g.temporal == MGA_TEMPORAL_BAND) return false;
-  if (g.N > kResMaxN || g.T > kResMaxT) return false;
+  if (g.T > kResMaxT) return false;
   if (g.u_wT != 1 || g.d_wT != 1) return false;
   if (std::max(g.kd, g.ku + 1) > kResMaxK) return false;
-  int th = 0;
-  return resident_smem_bytes(p, &th) <= p->max_smem_optin;
+  ResGeom geo;
+  return geometry(p, &geo);
 }
 
 int resident_smem_bytes(const mga_plan* p, int* threads) {
-  const GraphDev& g = p->g;
-  const int NP = ((g.N + 1 + 31) / 32) * 32;
-  if (threads) *threads = ((g.N + 31) / 32) * 32;
-  return (int)res_core_bytes(g, NP);
+  ResGeom geo;
+  if (!geometry(p, &geo)) { if (threads) *threads = 0; return 0; }
+  if (threads) *threads = geo.threads;
+  return (int)geo.core_bytes;
 }
 
-static int pick(mga_plan* p, ResArgs& a, int threads, cudaStream_t st) {
+static int pick(mga_plan* p, ResArgs& a, const ResGeom& geo, cudaStream_t st) {
   const int k = std::max(p->g.kd, p->g.ku + 1);
-  const bool small_t = p->g.T <= 12;
-  if (k <= 5) return small_t ? resident_launch_12_5(p, a, threads, st) : resident_launch_24_5(p, a, threads, st);
-  if (k <= 7) return small_t ? resident_launch_12_7(p, a, threads, st) : resident_launch_24_7(p, a, threads, st);
-  return small_t ? resident_launch_12_9(p, a, threads, st) : resident_launch_24_9(p, a, threads, st);
+  const int kk = k <= 5 ? 5 : (k <= 7 ? 7 : 9);
+#define MGA_CASE(C_, K_) if (geo.CH == C_ && kk == K_) return resident_launch_##C_##_##K_(p, a, geo, st);
+  MGA_CASE(1, 5) MGA_CASE(1, 7) MGA_CASE(1, 9) MGA_CASE(2, 5) MGA_CASE(2, 7) MGA_CASE(2, 9)
+  MGA_CASE(3, 5) MGA_CASE(3, 7) MGA_CASE(3, 9)
+#undef MGA_CASE
+  set_error("resident: no instantiation for this (CH, K)");
+  return MGA_ERR_UNSUPPORTED;
 }
 
 int resident_admm(mga_plan* p, const mga_params* m, const void* y, void* x_out, int64_t B, int n_outer, int n_cg,
@@ -45,7 +54,9 @@ int resident_admm(mga_plan* p, const mga_params* m, const void* y, void* x_out, 
   const GraphDev& g = p->g;
   ResArgs a{};
   a.N = g.N; a.T = g.T; a.t_in = g.t_in; a.n_outer = n_outer; a.n_cg = n_cg; a.q1 = g.q1; a.nnz = g.nnz;
-  a.NP = ((g.N + 1 + 31) / 32) * 32;
+  ResGeom geo;
+  if (!geometry(p, &geo)) { set_error("resident: shape does not fit"); return MGA_ERR_UNSUPPORTED; }
+  a.NT = geo.NT; a.S = geo.S; a.TP = geo.TP;
   a.B = B; a.kd = g.kd; a.ku = g.ku;
   a.nbr_d = g.nbr_d; a.d_w = g.d_w; a.nbr_u = g.nbr_u; a.u_w = g.u_w;
   a.csr_ptr = g.csr_ptr; a.csr_src = g.csr_src; a.csr_w = g.csr_w;
@@ -73,10 +84,9 @@ int resident_admm(mga_plan* p, const mga_params* m, const void* y, void* x_out, 
     if (a.diag) MGA_CUDA(cudaMemsetAsync(a.diag, 0, (size_t)n_outer * MGA_DIAG_COLS * sizeof(double), st));
     if (a.dx_sum) MGA_CUDA(cudaMemsetAsync(a.dx_sum, 0, (size_t)n_outer * g.T * g.N * sizeof(double), st));
   }
-  const int threads = ((g.N + 31) / 32) * 32;
   if (outs->cg_iters) for (int k = 0; k < n_outer * 3; ++k) outs->cg_iters[k] = -1;
   if (outs->outer_done) *outs->outer_done = n_outer;
-  return pick(p, a, threads, st);
+  return pick(p, a, geo, st);
 }
 
 }  // namespace mga

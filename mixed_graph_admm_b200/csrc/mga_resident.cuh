@@ -1,20 +1,35 @@
 // Resident mode: the whole of combined_loop (ADMM.py:528-648) for one window inside one CTA.
 //
-// Mapping: thread i owns node i for ALL time steps.  The four CG vectors (x, r, p, Ap) of the
-// thread's T lattice points live in registers; only the two vectors other threads gather from
-// (p and q = L_d p) are staged in shared memory, row-major (t, node) with one extra zero slot
-// per row that absorbs the "-1 = no neighbour" entries (quirk Q6).  The thread's own rows of the
-// ELL tables (neighbour offsets + weights) are time-invariant and sit in registers; the in-list
-// (transposed CSR) that turns the reference's scatter_add into a gather sits in shared memory.
-// The seven ADMM state vectors are parked between solves either in shared memory (when they
-// fit) or in a per-CTA L2-resident scratch.  HBM traffic per window is y in, x out.
+// Work mapping.  The T time steps of a node are cut into chunks of 4; a thread owns CH
+// consecutive chunks of ONE node (thread = (node i, slab s), slab-major so a warp is uniform in
+// s).  The four CG vectors (x, r, p, Ap) of the thread's 4*CH lattice points live in registers.
 //
-// A persistent grid (<= CTAs that fit on the chip) strides over the batch; there is no
-// inter-CTA communication, so windows shard over CTAs — and over GPUs — with no collective.
+// Shared-memory layout.  Only the vectors other threads gather from are staged: pbuf (p) and
+// qbuf (a shifted copy of q = L_d p), NODE-major: buf[node * TP + t], TP = 4 * odd.  A
+// neighbour's whole time series is then contiguous, so every gather is an aligned 128-bit load
+// (4 time steps per LDS.128), and `TP/4 odd` makes node -> 16-byte bank group a bijection mod 8,
+// which keeps the 8 lanes of a quarter-warp on distinct groups when their nodes differ mod 8.
+// Row N is a zero row that absorbs the "-1 = no neighbour" entries (quirk Q6).
+//
+// The shift.  L_d reads p at t-1 and L_d^T reads q at t+1 (ADMM.py:171, 200-208), which would
+// misalign the 4-step chunks.  Instead each thread computes qs[k] = q[k+1] for the k it owns
+// (neighbour chunks of p at the SAME k, aligned) and qbuf holds qs; the in-list gather of
+// L_d^T then needs qs at the thread's own k (aligned again).  Only the thread's own node is
+// touched off-chunk: p[k+1] and qs[k-1] across the slab edge, one scalar load each.
+//
+// The thread's rows of the ELL tables (neighbour row offsets + weights, time-invariant) sit in
+// registers; the in-list (transposed CSR) that replaces the reference's scatter_add sits in
+// shared memory as (row offset, weight) pairs.  The seven ADMM state vectors are parked between
+// solves in shared memory when they fit, else in a per-CTA L2-resident scratch.  HBM traffic
+// per window is y in, x out (+ optional iterates / diagnostics).
+//
+// A persistent grid strides over the batch; CTAs never communicate, so windows shard over
+// CTAs — and over GPUs — with no collective.
+#pragma once
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 
-#pragma once
 #include "mga_common.cuh"
 
 namespace mga {
@@ -22,7 +37,10 @@ namespace mga {
 enum { ST_X = 0, ST_ZU, ST_ZD, ST_GU, ST_GD, ST_GAM, ST_PHI, ST_COUNT };
 
 struct ResArgs {
-  int N, T, t_in, n_outer, n_cg, NP, q1, want_diag, state_in_smem, nnz;
+  int N, T, t_in, n_outer, n_cg, q1, want_diag, state_in_smem, nnz;
+  int NT;      // threads per slab (N rounded up to 32)
+  int S;       // slabs (threads per node)
+  int TP;      // row stride of the node-major buffers, floats (4 * odd, >= S * 4 * CH)
   int64_t B;
   int kd, ku;
   const int* nbr_d; const float* d_w; const int* nbr_u; const float* u_w;
@@ -37,142 +55,163 @@ struct ResArgs {
   float t_mean, t_var;
 };
 
-template <int TT, int K>
+template <int CH, int K>
 struct Ctx {
-  // per-thread constants
-  int i, T, t_in, NP;
+  static constexpr int TS = 4 * CH;
+  int i, t0, T, t_in, TP;
   bool active;
-  int nd[K];      // smem column of the j-th temporal neighbour (N = zero slot)
+  bool has_next, has_prev;   // another slab of this node owns t0+TS / t0-1
+  int own;                   // i * TP + t0
+  int nd[K];                 // neighbour row offset + t0 (zero row for -1)
   float wd[K];
-  int nu[K - 1];  // spatial neighbours
+  int nu[K - 1];
   float wu[K - 1];
   int e0, e1;
   float* pbuf;
   float* qbuf;
-  const int2* ent;  // (src column, weight bits)
-  float* red;       // 2 x 32
+  const int2* ent;           // (src * TP, weight bits)
+  float* red;                // 2 x 32
   int red_sel;
 
   __device__ __forceinline__ float bsum(float v) {
     float* r = red + 32 * red_sel;
     red_sel ^= 1;
-    return block_sum<float>(v, r);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum<float>(v);
+    if (lane == 0) r[w] = v;
+    __syncthreads();
+    return warp_sum<float>(lane < nw ? r[lane] : 0.f);   // every warp reduces the <= 32 partials itself
   }
 
-  __device__ __forceinline__ void put(float* buf, const float (&v)[TT]) {
+  __device__ __forceinline__ void put(float* buf, const float (&v)[TS]) const {
 #pragma unroll
-    for (int t = 0; t < TT; ++t)
-      if (t < T) buf[t * NP + i] = v[t];
+    for (int c = 0; c < CH; ++c)
+      *reinterpret_cast<float4*>(buf + own + 4 * c) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
   }
 
-  // q = L_d v, reading v from pbuf (ADMM.py:166-177)
-  __device__ __forceinline__ void ldr_from_pbuf(const float (&v)[TT], float (&q)[TT]) {
-    q[0] = 0.f;
+  // acc[k] += w * buf[off + k], k = 0..TS-1, as CH aligned 128-bit loads
+  __device__ __forceinline__ void gather_acc(const float* buf, int off, float w, float (&acc)[TS]) const {
 #pragma unroll
-    for (int t = 1; t < TT; ++t) {
-      float acc = 0.f;
-      if (t < T) {
-        const float* row = pbuf + (t - 1) * NP;
-#pragma unroll
-        for (int j = 0; j < K; ++j) acc += wd[j] * row[nd[j]];
-      }
-      q[t] = v[t] - acc;
+    for (int c = 0; c < CH; ++c) {
+      const float4 g = *reinterpret_cast<const float4*>(buf + off + 4 * c);
+      acc[4 * c] += w * g.x;
+      acc[4 * c + 1] += w * g.y;
+      acc[4 * c + 2] += w * g.z;
+      acc[4 * c + 3] += w * g.w;
     }
   }
 
-  // f[t] = sum over the in-list of w * buf[t+1][src]   (ADMM.py:200-209 as a gather)
-  __device__ __forceinline__ void father_sum(const float* buf, float (&f)[TT]) {
+  // qs[k] = q[t0+k+1] where q = L_d v (ADMM.py:166-177), v already in pbuf (synced).
+  // With first_row_zero the caller wants plain "v shifted by one" (used for Ldr_T of a vector).
+  __device__ __forceinline__ void shifted_ldr(const float (&v)[TS], float (&qs)[TS]) const {
+    float acc[TS];
 #pragma unroll
-    for (int t = 0; t < TT; ++t) f[t] = 0.f;
-    for (int e = e0; e < e1; ++e) {
-      const int2 en = ent[e];
-      const float w = __int_as_float(en.y);
-      const float* col = buf + en.x;
+    for (int k = 0; k < TS; ++k) acc[k] = 0.f;
 #pragma unroll
-      for (int t = 0; t < TT - 1; ++t)
-        if (t + 1 < T) f[t] += w * col[(t + 1) * NP];
+    for (int j = 0; j < K; ++j) gather_acc(pbuf, nd[j], wd[j], acc);
+    const float vnext = has_next ? pbuf[own + TS] : 0.f;
+#pragma unroll
+    for (int k = 0; k < TS; ++k) {
+      const float up = (k < TS - 1) ? v[k + 1] : vnext;
+      qs[k] = (t0 + k + 1 < T) ? up - acc[k] : 0.f;
+    }
+  }
+
+  // f[k] = sum over the in-list of w * buf[src][t0+k]   (ADMM.py:200-209 as a gather; buf holds the
+  // vector shifted by one time step, so this is the "father" sum at t0+k)
+  __device__ __forceinline__ void father_sum(const float* buf, float (&f)[TS]) const {
+#pragma unroll
+    for (int k = 0; k < TS; ++k) f[k] = 0.f;
+    int e = e0;
+    for (; e + 1 < e1; e += 2) {          // two entries per trip: more loads in flight
+      const int2 a = ent[e], b = ent[e + 1];
+      gather_acc(buf, a.x + t0, __int_as_float(a.y), f);
+      gather_acc(buf, b.x + t0, __int_as_float(b.y), f);
+    }
+    if (e < e1) {
+      const int2 a = ent[e];
+      gather_acc(buf, a.x + t0, __int_as_float(a.y), f);
     }
   }
 
   // out = A v for the x / z_d systems: diag(v) + c * L_d^T L_d v  (ADMM.py:371-387, 392-394)
   template <bool XSYS>
-  __device__ __forceinline__ void apply_cldr(const float (&v)[TT], float (&out)[TT], float a, float c) {
+  __device__ __forceinline__ void apply_cldr(const float (&v)[TS], float (&out)[TS], float a, float c) {
     put(pbuf, v);
     __syncthreads();
-    float q[TT];
-    ldr_from_pbuf(v, q);
-    put(qbuf, q);
+    float qs[TS];
+    shifted_ldr(v, qs);
+    put(qbuf, qs);
     __syncthreads();
-    float f[TT];
+    float f[TS];
     father_sum(qbuf, f);
+    const float qprev = has_prev ? qbuf[own - 1] : 0.f;      // q[t0]; q[0] = 0 (ADMM.py:176)
 #pragma unroll
-    for (int t = 0; t < TT; ++t) {
-      const float l = (t == T - 1) ? q[t] : q[t] - f[t];     // q[0] == 0, so Q1 is moot here
-      if (XSYS) out[t] = ((t < t_in ? v[t] : 0.f) + a * v[t]) + c * l;
-      else out[t] = c * l + a * v[t];
+    for (int k = 0; k < TS; ++k) {
+      const float q = (k == 0) ? qprev : qs[k - 1];
+      const float l = q - f[k];      // row T-1: f = 0 because qs[T-1] = 0; Q1 is moot as q[0] = 0
+      if (XSYS) out[k] = ((t0 + k < t_in ? v[k] : 0.f) + a * v[k]) + c * l;
+      else out[k] = c * l + a * v[k];
     }
   }
 
   // out = mu_u L_u v + (rho_u/2) v  (ADMM.py:389-390)
-  __device__ __forceinline__ void apply_lu(const float (&v)[TT], float (&out)[TT], float a, float c) {
+  __device__ __forceinline__ void apply_lu(const float (&v)[TS], float (&out)[TS], float a, float c) {
     put(pbuf, v);
     __syncthreads();
+    float acc[TS];
 #pragma unroll
-    for (int t = 0; t < TT; ++t) {
-      float acc = 0.f;
-      if (t < T) {
-        const float* row = pbuf + t * NP;
+    for (int k = 0; k < TS; ++k) acc[k] = 0.f;
 #pragma unroll
-        for (int j = 0; j < K - 1; ++j) acc += wu[j] * row[nu[j]];
-      }
-      out[t] = c * (v[t] - acc) + a * v[t];
-    }
+    for (int j = 0; j < K - 1; ++j) gather_acc(pbuf, nu[j], wu[j], acc);
+#pragma unroll
+    for (int k = 0; k < TS; ++k) out[k] = c * (v[k] - acc[k]) + a * v[k];
   }
 
   template <int SYS>
-  __device__ __forceinline__ void apply(const float (&v)[TT], float (&out)[TT], float a, float c) {
+  __device__ __forceinline__ void apply(const float (&v)[TS], float (&out)[TS], float a, float c) {
     if (SYS == MGA_SYS_ZU) apply_lu(v, out, a, c);
     else if (SYS == MGA_SYS_X) apply_cldr<true>(v, out, a, c);
     else apply_cldr<false>(v, out, a, c);
   }
 
-  // CG_solver, fixed iteration count (ADMM.py:329-368 with an unreachable tolerance).
-  // On entry r holds the right-hand side and x the warm start.
+  // CG_solver, fixed iteration count (ADMM.py:329-368 with an unreachable tolerance; the
+  // arithmetic is unguarded like the reference's, quirk Q10).  r holds the right-hand side on entry.
   template <int SYS>
-  __device__ __forceinline__ void cg(float (&x)[TT], float (&r)[TT], float a, float c, int n_cg, float* alpha_out,
+  __device__ __forceinline__ void cg(float (&x)[TS], float (&r)[TS], float a, float c, int n_cg, float* alpha_out,
                                      float* beta_out, int64_t B) {
-    float p[TT], ap[TT];
+    float p[TS], ap[TS];
     apply<SYS>(x, ap, a, c);
     float loc = 0.f;
 #pragma unroll
-    for (int t = 0; t < TT; ++t) {
-      r[t] = r[t] - ap[t];
-      p[t] = r[t];
-      loc += r[t] * r[t];
+    for (int k = 0; k < TS; ++k) {
+      r[k] = r[k] - ap[k];
+      p[k] = r[k];
+      loc += r[k] * r[k];
     }
     float rr = bsum(loc);
-    for (int k = 0; k < n_cg; ++k) {
+    for (int it = 0; it < n_cg; ++it) {
       apply<SYS>(p, ap, a, c);
       loc = 0.f;
 #pragma unroll
-      for (int t = 0; t < TT; ++t) loc += p[t] * ap[t];
+      for (int k = 0; k < TS; ++k) loc += p[k] * ap[k];
       const float alpha = rr / bsum(loc);
       loc = 0.f;
 #pragma unroll
-      for (int t = 0; t < TT; ++t) {
-        x[t] = x[t] + alpha * p[t];
-        r[t] = r[t] - alpha * ap[t];
-        loc += r[t] * r[t];
+      for (int k = 0; k < TS; ++k) {
+        x[k] = x[k] + alpha * p[k];
+        r[k] = r[k] - alpha * ap[k];
+        loc += r[k] * r[k];
       }
       const float rrn = bsum(loc);
       const float beta = rrn / rr;
       rr = rrn;
       if (alpha_out && threadIdx.x == 0) {
-        alpha_out[(size_t)k * B] = alpha;
-        beta_out[(size_t)k * B] = beta;
+        alpha_out[(size_t)it * B] = alpha;
+        beta_out[(size_t)it * B] = beta;
       }
 #pragma unroll
-      for (int t = 0; t < TT; ++t) p[t] = r[t] + beta * p[t];
+      for (int k = 0; k < TS; ++k) p[k] = r[k] + beta * p[k];
     }
   }
 };
@@ -183,28 +222,35 @@ __device__ __forceinline__ float soft_thr(float s, float d) {
   return sg * u * (float)(u > 0.f);   // ADMM.py:407-408
 }
 
-template <int TT, int K, int MAXT>
+template <int CH, int K, int MAXT>
 __global__ void __launch_bounds__(MAXT, 1) k_admm_resident(const ResArgs a) {
+  constexpr int TS = 4 * CH;
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int N = a.N, T = a.T, NP = a.NP, t_in = a.t_in;
+  const int N = a.N, T = a.T, TP = a.TP, t_in = a.t_in;
+  const int rows = (N + 1) * TP;
   float* pbuf = reinterpret_cast<float*>(smem_raw);
-  float* qbuf = pbuf + T * NP;
-  float* red = qbuf + T * NP;                       // 64 floats
+  float* qbuf = pbuf + rows;
+  float* red = qbuf + rows;                         // 64 floats
   float* dred = red + 64;                           // MGA_DIAG_COLS x 32 floats
   int2* ent = reinterpret_cast<int2*>(dred + MGA_DIAG_COLS * 32);
   float* st_smem = reinterpret_cast<float*>(ent + ((a.nnz + 1) & ~1));
-  const int i = threadIdx.x;
+  const int s = threadIdx.x / a.NT;
+  const int i = threadIdx.x - s * a.NT;
   const bool active = i < N;
+  const int t0 = s * TS;
 
-  Ctx<TT, K> c;
-  c.i = i; c.T = T; c.t_in = t_in; c.NP = NP; c.active = active;
+  Ctx<CH, K> c;
+  c.i = i; c.t0 = t0; c.T = T; c.t_in = t_in; c.TP = TP; c.active = active;
+  c.has_next = (s + 1 < a.S);
+  c.has_prev = (s > 0);
+  c.own = (active ? i : N) * TP + t0;     // inactive lanes park on the zero row (they only ever write zeros)
   c.pbuf = pbuf; c.qbuf = qbuf; c.ent = ent; c.red = red; c.red_sel = 0;
 #pragma unroll
   for (int j = 0; j < K; ++j) {
     int nb = -1;
     float w = 0.f;
     if (active && j < a.kd) { nb = a.nbr_d[i * a.kd + j]; w = a.d_w[i * a.kd + j]; }
-    c.nd[j] = nb >= 0 ? nb : N;
+    c.nd[j] = (nb >= 0 ? nb : N) * TP + t0;
     c.wd[j] = nb >= 0 ? w : 0.f;
   }
 #pragma unroll
@@ -212,24 +258,49 @@ __global__ void __launch_bounds__(MAXT, 1) k_admm_resident(const ResArgs a) {
     int nb = -1;
     float w = 0.f;
     if (active && j < a.ku) { nb = a.nbr_u[i * a.ku + j]; w = a.u_w[i * a.ku + j]; }
-    c.nu[j] = nb >= 0 ? nb : N;
+    c.nu[j] = (nb >= 0 ? nb : N) * TP + t0;
     c.wu[j] = nb >= 0 ? w : 0.f;
   }
   c.e0 = active ? a.csr_ptr[i] : 0;
   c.e1 = active ? a.csr_ptr[i + 1] : 0;
-  for (int e = i; e < a.nnz; e += blockDim.x) ent[e] = make_int2(a.csr_src[e], __float_as_int(a.csr_w[e]));
-  for (int k = i; k < 2 * T * NP; k += blockDim.x) pbuf[k] = 0.f;
+  for (int e = threadIdx.x; e < a.nnz; e += blockDim.x)
+    ent[e] = make_int2(a.csr_src[e] * TP, __float_as_int(a.csr_w[e]));
+  for (int k = threadIdx.x; k < 2 * rows; k += blockDim.x) pbuf[k] = 0.f;
   __syncthreads();
 
-  const int NS = a.state_in_smem ? NP : N;
-  float* state = a.state_in_smem ? st_smem : a.scratch + (size_t)blockIdx.x * ST_COUNT * T * N;
-  const int col = active ? i : 0;
-#define LD(V, t) (state[((V) * T + (t)) * NS + col])
-#define ST(V, t, val) do { if (active) state[((V) * T + (t)) * NS + col] = (val); } while (0)
+  // ---- parked ADMM state: smem [v][node*TP + t] (128-bit) or global scratch [v][t][node] (coalesced)
+  float* gstate = a.state_in_smem ? nullptr : a.scratch + (size_t)blockIdx.x * ST_COUNT * T * N;
+  auto ld_state = [&](int v, float (&o)[TS]) {
+    if (a.state_in_smem) {
+      const float* base = st_smem + (size_t)v * N * TP + i * TP + t0;
+#pragma unroll
+      for (int cc = 0; cc < CH; ++cc) {
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (active) g = *reinterpret_cast<const float4*>(base + 4 * cc);
+        o[4 * cc] = g.x; o[4 * cc + 1] = g.y; o[4 * cc + 2] = g.z; o[4 * cc + 3] = g.w;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < TS; ++k) o[k] = (active && t0 + k < T) ? gstate[((size_t)v * T + t0 + k) * N + i] : 0.f;
+    }
+  };
+  auto st_state = [&](int v, const float (&o)[TS]) {
+    if (!active) return;
+    if (a.state_in_smem) {
+      float* base = st_smem + (size_t)v * N * TP + i * TP + t0;
+#pragma unroll
+      for (int cc = 0; cc < CH; ++cc)
+        *reinterpret_cast<float4*>(base + 4 * cc) = make_float4(o[4 * cc], o[4 * cc + 1], o[4 * cc + 2], o[4 * cc + 3]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < TS; ++k)
+        if (t0 + k < T) gstate[((size_t)v * T + t0 + k) * N + i] = o[k];
+    }
+  };
 
   for (int64_t b = blockIdx.x; b < a.B; b += gridDim.x) {
-    const float* yw = a.y + (size_t)b * t_in * N + col;
-    float x[TT];
+    const float* yw = a.y + (size_t)b * t_in * N + (active ? i : 0);
+    float x[TS];
     // ---- initial_guess (ADMM.py:766-781) and initial state (ADMM.py:537-544)
     {
       float sy = 0.f, sty = 0.f;
@@ -241,23 +312,28 @@ __global__ void __launch_bounds__(MAXT, 1) k_admm_resident(const ResArgs a) {
       const float my = sy / (float)t_in, mty = sty / (float)t_in;
       const float w = (mty - a.t_mean * my) / a.t_var;
       const float cc = my - w * a.t_mean;
+      float tenth[TS];
 #pragma unroll
-      for (int t = 0; t < TT; ++t) {
+      for (int k = 0; k < TS; ++k) {
+        const int t = t0 + k;
         float v = 0.f;
         if (active && t < T) v = t < t_in ? yw[(size_t)t * N] : w * (float)t + cc;
-        x[t] = v;
-        if (t < T) {
-          ST(ST_X, t, v); ST(ST_ZU, t, v); ST(ST_ZD, t, v);
-          ST(ST_GU, t, 0.1f); ST(ST_GD, t, 0.1f); ST(ST_GAM, t, 0.1f);
-        }
+        x[k] = v;
+        tenth[k] = (active && t < T) ? 0.1f : 0.f;
       }
+      st_state(ST_X, x); st_state(ST_ZU, x); st_state(ST_ZD, x);
+      st_state(ST_GU, tenth); st_state(ST_GD, tenth); st_state(ST_GAM, tenth);
+      // phi = L_d x  (ADMM.py:541)
       c.put(pbuf, x);
       __syncthreads();
-      float q[TT];
-      c.ldr_from_pbuf(x, q);
+      float qs[TS], q[TS];
+      c.shifted_ldr(x, qs);
+      c.put(qbuf, qs);
+      __syncthreads();
+      const float qprev = c.has_prev ? qbuf[c.own - 1] : 0.f;
 #pragma unroll
-      for (int t = 0; t < TT; ++t)
-        if (t < T) ST(ST_PHI, t, q[t]);
+      for (int k = 0; k < TS; ++k) q[k] = (k == 0) ? qprev : qs[k - 1];
+      st_state(ST_PHI, q);
       __syncthreads();
     }
 
@@ -268,139 +344,150 @@ __global__ void __launch_bounds__(MAXT, 1) k_admm_resident(const ResArgs a) {
       float* al = a.alpha ? a.alpha + ((size_t)it * 3) * a.n_cg * a.B + b : nullptr;
       float* be = a.beta ? a.beta + ((size_t)it * 3) * a.n_cg * a.B + b : nullptr;
       const size_t sys_stride = (size_t)a.n_cg * a.B;
-      float r[TT];
+      float r[TS];
       // ---- RHS_x (ADMM.py:552-559): Ldr_T(gamma + rho phi)/2 + (rho_u zu + rho_d zd)/2 - (gu+gd)/2 + H^T y
       {
-        float v[TT], f[TT];
+        float v[TS], vs[TS], f[TS], tmp[TS];
+        ld_state(ST_GAM, v);
+        ld_state(ST_PHI, tmp);
 #pragma unroll
-        for (int t = 0; t < TT; ++t) v[t] = (active && t < T) ? LD(ST_GAM, t) + a.rho * LD(ST_PHI, t) : 0.f;
-        c.put(qbuf, v);
+        for (int k = 0; k < TS; ++k) v[k] = v[k] + a.rho * tmp[k];
+        c.put(pbuf, v);
+        __syncthreads();
+        const float vnext = c.has_next ? pbuf[c.own + TS] : 0.f;
+#pragma unroll
+        for (int k = 0; k < TS; ++k) vs[k] = (t0 + k + 1 < T) ? ((k < TS - 1) ? v[k + 1] : vnext) : 0.f;
+        c.put(qbuf, vs);
         __syncthreads();
         c.father_sum(qbuf, f);
+        float zu[TS], zd[TS], gu[TS], gd[TS];
+        ld_state(ST_ZU, zu); ld_state(ST_ZD, zd); ld_state(ST_GU, gu); ld_state(ST_GD, gd);
 #pragma unroll
-        for (int t = 0; t < TT; ++t) {
-          float l = (t == T - 1) ? v[t] : ((t == 0 && !a.q1) ? -f[t] : v[t] - f[t]);
+        for (int k = 0; k < TS; ++k) {
+          const int t = t0 + k;
+          // rows of apply_op_Ldr_T: t = T-1 keeps v; t = 0 keeps the identity term only under Q1
+          const float l = (t == T - 1) ? v[k] : ((t == 0 && !a.q1) ? -f[k] : v[k] - f[k]);
           float o = 0.f;
           if (active && t < T) {
             const float hty = t < t_in ? yw[(size_t)t * N] : 0.f;
-            o = l / 2.f + (a.rho_u * LD(ST_ZU, t) + a.rho_d * LD(ST_ZD, t)) / 2.f - (LD(ST_GU, t) + LD(ST_GD, t)) / 2.f + hty;
+            o = l / 2.f + (a.rho_u * zu[k] + a.rho_d * zd[k]) / 2.f - (gu[k] + gd[k]) / 2.f + hty;
           }
-          r[t] = o;
+          r[k] = o;
         }
       }
       // ---- x solve (ADMM.py:571); x registers hold x_old
       c.template cg<MGA_SYS_X>(x, r, a.ax, a.cx, a.n_cg, al, be, a.B);
+      {
+        float xo[TS];
+        ld_state(ST_X, xo);
+        if (a.want_diag) {
 #pragma unroll
-      for (int t = 0; t < TT; ++t) {
-        if (active && t < T) {
-          if (a.want_diag) {
-            const float dx = x[t] - LD(ST_X, t);
-            dg[MGA_DIAG_DX2] += dx * dx;
-            if (a.dx_sum) atomicAdd(a.dx_sum + ((size_t)it * T + t) * N + i, (double)dx);
+          for (int k = 0; k < TS; ++k) {
+            if (active && t0 + k < T) {
+              const float dx = x[k] - xo[k];
+              dg[MGA_DIAG_DX2] += dx * dx;
+              if (a.dx_sum) atomicAdd(a.dx_sum + ((size_t)it * T + t0 + k) * N + i, (double)dx);
+            }
           }
-          ST(ST_X, t, x[t]);
         }
+        st_state(ST_X, x);
       }
       // ---- z_u solve (ADMM.py:579-580) + its dual ascent (ADMM.py:595)
       {
-        float z[TT];
+        float z[TS], zo[TS], g[TS];
+        ld_state(ST_ZU, z);
+        ld_state(ST_GU, g);
 #pragma unroll
-        for (int t = 0; t < TT; ++t) {
-          const bool on = active && t < T;
-          z[t] = on ? LD(ST_ZU, t) : 0.f;
-          r[t] = on ? LD(ST_GU, t) / 2.f + a.azu * LD(ST_X, t) : 0.f;
-        }
+        for (int k = 0; k < TS; ++k) { zo[k] = z[k]; r[k] = g[k] / 2.f + a.azu * x[k]; }
         c.template cg<MGA_SYS_ZU>(z, r, a.azu, a.czu, a.n_cg, al ? al + sys_stride : nullptr,
                                   be ? be + sys_stride : nullptr, a.B);
 #pragma unroll
-        for (int t = 0; t < TT; ++t) {
-          if (active && t < T) {
-            const float d0 = LD(ST_X, t) - z[t];
-            if (a.want_diag) {
-              const float d1 = z[t] - LD(ST_ZU, t);
-              dg[MGA_DIAG_X_ZU2] += d0 * d0;
-              dg[MGA_DIAG_DZU2] += d1 * d1;
-            }
-            ST(ST_GU, t, LD(ST_GU, t) + a.rho_u * d0);
-            ST(ST_ZU, t, z[t]);
-          }
+        for (int k = 0; k < TS; ++k) {
+          const float d0 = x[k] - z[k], d1 = z[k] - zo[k];
+          dg[MGA_DIAG_X_ZU2] += d0 * d0;
+          dg[MGA_DIAG_DZU2] += d1 * d1;
+          g[k] = g[k] + a.rho_u * d0;
         }
+        st_state(ST_GU, g);
+        st_state(ST_ZU, z);
       }
       // ---- z_d solve (ADMM.py:587-588) + its dual ascent (ADMM.py:597)
       {
-        float z[TT];
+        float z[TS], zo[TS], g[TS];
+        ld_state(ST_ZD, z);
+        ld_state(ST_GD, g);
 #pragma unroll
-        for (int t = 0; t < TT; ++t) {
-          const bool on = active && t < T;
-          z[t] = on ? LD(ST_ZD, t) : 0.f;
-          r[t] = on ? LD(ST_GD, t) / 2.f + a.azd * LD(ST_X, t) : 0.f;
-        }
+        for (int k = 0; k < TS; ++k) { zo[k] = z[k]; r[k] = g[k] / 2.f + a.azd * x[k]; }
         c.template cg<MGA_SYS_ZD>(z, r, a.azd, a.czd, a.n_cg, al ? al + 2 * sys_stride : nullptr,
                                   be ? be + 2 * sys_stride : nullptr, a.B);
 #pragma unroll
-        for (int t = 0; t < TT; ++t) {
-          if (active && t < T) {
-            const float d0 = LD(ST_X, t) - z[t];
-            if (a.want_diag) {
-              const float d1 = z[t] - LD(ST_ZD, t);
-              dg[MGA_DIAG_X_ZD2] += d0 * d0;
-              dg[MGA_DIAG_DZD2] += d1 * d1;
-            }
-            ST(ST_GD, t, LD(ST_GD, t) + a.rho_d * d0);
-            ST(ST_ZD, t, z[t]);
-          }
+        for (int k = 0; k < TS; ++k) {
+          const float d0 = x[k] - z[k], d1 = z[k] - zo[k];
+          dg[MGA_DIAG_X_ZD2] += d0 * d0;
+          dg[MGA_DIAG_DZD2] += d1 * d1;
+          g[k] = g[k] + a.rho_d * d0;
         }
+        st_state(ST_GD, g);
+        st_state(ST_ZD, z);
       }
       // ---- phi prox + gamma ascent (ADMM.py:600-605) and the remaining diagnostics (ADMM.py:612-637)
       {
-        // x was parked in the state block during the z solves (keeps it out of the CG register budget)
-#pragma unroll
-        for (int t = 0; t < TT; ++t) x[t] = (active && t < T) ? LD(ST_X, t) : 0.f;
         c.put(pbuf, x);
         __syncthreads();
-        float q[TT];
-        c.ldr_from_pbuf(x, q);
+        float qs[TS];
+        c.shifted_ldr(x, qs);
+        c.put(qbuf, qs);
+        __syncthreads();
+        const float qprev = c.has_prev ? qbuf[c.own - 1] : 0.f;
+        float gam[TS], phi[TS], lux[TS];
+        ld_state(ST_GAM, gam);
+        ld_state(ST_PHI, phi);
+        if (a.want_diag) {
+#pragma unroll
+          for (int k = 0; k < TS; ++k) lux[k] = 0.f;
+#pragma unroll
+          for (int j = 0; j < K - 1; ++j) c.gather_acc(pbuf, c.nu[j], c.wu[j], lux);
+        }
         int bad = 0;
 #pragma unroll
-        for (int t = 0; t < TT; ++t) {
+        for (int k = 0; k < TS; ++k) {
+          const int t = t0 + k;
+          const float q = (k == 0) ? qprev : qs[k - 1];           // (L_d x)[t]
+          const float ph = soft_thr(q - gam[k] / a.rho, a.thr);
+          const float gn = gam[k] + a.rho * (ph - q);
           if (active && t < T) {
-            const float gv = LD(ST_GAM, t), po = LD(ST_PHI, t);
-            const float ph = soft_thr(q[t] - gv / a.rho, a.thr);
-            const float gn = gv + a.rho * (ph - q[t]);
-            ST(ST_PHI, t, ph);
-            ST(ST_GAM, t, gn);
-            bad |= !isfinite(x[t]) || !isfinite(ph) || !isfinite(gn);
+            bad |= !isfinite(x[k]) || !isfinite(ph) || !isfinite(gn);
             if (a.want_diag) {
-              const float e = ph - q[t], f = ph - po;
+              const float e = ph - q, f = ph - phi[k];
               dg[MGA_DIAG_PHI_LDX2] += e * e;
               dg[MGA_DIAG_DPHI2] += f * f;
-              dg[MGA_DIAG_DGTV] += fabsf(q[t]);
-              dg[MGA_DIAG_DGLR] += q[t] * q[t];
+              dg[MGA_DIAG_DGTV] += fabsf(q);
+              dg[MGA_DIAG_DGLR] += q * q;
               if (t < t_in) {
-                const float h = x[t] - yw[(size_t)t * N];
+                const float h = x[k] - yw[(size_t)t * N];
                 dg[MGA_DIAG_RECOVER2] += h * h;
               }
-              float acc = 0.f;
-              const float* row = pbuf + t * NP;
-#pragma unroll
-              for (int j = 0; j < K - 1; ++j) acc += c.wu[j] * row[c.nu[j]];
-              dg[MGA_DIAG_GLR] += x[t] * (x[t] - acc);
+              dg[MGA_DIAG_GLR] += x[k] * (x[k] - lux[k]);
             }
+            phi[k] = ph;
+            gam[k] = gn;
           }
         }
+        st_state(ST_PHI, phi);
+        st_state(ST_GAM, gam);
         dg[MGA_DIAG_NONFINITE] = (float)bad;
         // one-sync multi-column block reduction
-        const int lane = i & 31, wp = i >> 5, nw = (blockDim.x + 31) >> 5;
+        const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
 #pragma unroll
         for (int k = 0; k < MGA_DIAG_COLS; ++k) {
           const float v = warp_sum<float>(dg[k]);
           if (lane == 0) dred[k * 32 + wp] = v;
         }
         __syncthreads();
-        if (i < MGA_DIAG_COLS && a.diag) {
+        if (threadIdx.x < MGA_DIAG_COLS && a.diag) {
           float tot = 0.f;
-          for (int k = 0; k < nw; ++k) tot += dred[i * 32 + k];
-          if (tot != 0.f) atomicAdd(a.diag + (size_t)it * MGA_DIAG_COLS + i, (double)tot);
+          for (int k = 0; k < nw; ++k) tot += dred[threadIdx.x * 32 + k];
+          if (tot != 0.f) atomicAdd(a.diag + (size_t)it * MGA_DIAG_COLS + threadIdx.x, (double)tot);
         }
         __syncthreads();
       }
@@ -408,35 +495,74 @@ __global__ void __launch_bounds__(MAXT, 1) k_admm_resident(const ResArgs a) {
     // ---- results
     if (active) {
 #pragma unroll
-      for (int t = 0; t < TT; ++t)
-        if (t < T) a.x_out[((size_t)b * T + t) * N + i] = x[t];
-      for (int v = ST_ZU; v < ST_COUNT; ++v)
-        if (a.out[v])
-          for (int t = 0; t < T; ++t) a.out[v][((size_t)b * T + t) * N + i] = LD(v, t);
+      for (int k = 0; k < TS; ++k)
+        if (t0 + k < T) a.x_out[((size_t)b * T + t0 + k) * N + i] = x[k];
+    }
+    for (int v = ST_ZU; v < ST_COUNT; ++v) {
+      if (a.out[v]) {
+        float o[TS];
+        ld_state(v, o);
+        if (active) {
+#pragma unroll
+          for (int k = 0; k < TS; ++k)
+            if (t0 + k < T) a.out[v][((size_t)b * T + t0 + k) * N + i] = o[k];
+        }
+      }
     }
     __syncthreads();
   }
-#undef LD
-#undef ST
 }
 
-inline size_t res_core_bytes(const GraphDev& g, int NP) {
-  return (size_t)2 * g.T * NP * 4 + 64 * 4 + MGA_DIAG_COLS * 32 * 4 + (size_t)((g.nnz + 1) & ~1) * 8;
+// ---- launch geometry --------------------------------------------------------------------------
+struct ResGeom {
+  int CH, S, NT, TP, threads;
+  size_t core_bytes, state_bytes;
+};
+
+inline int res_tp(int min_len) {          // smallest 4 * odd >= min_len
+  int chunks = (min_len + 3) / 4;
+  if ((chunks & 1) == 0) ++chunks;
+  return 4 * chunks;
 }
 
+// CH = chunks of 4 time steps per thread.  Default: the largest CH <= 3 (a node's table rows and
+// in-list entries are then read once per 12 time steps; measured 252k vs 210k windows/s against
+// CH = 1 at PEMS04 shape on B200); MGA_RES_CH overrides for experiments.
+inline bool res_geometry(const GraphDev& g, int force_ch, ResGeom* out) {
+  const int NT = ((g.N + 31) / 32) * 32;
+  const int chunks = (g.T + 3) / 4;
+  for (int ch = std::min(3, chunks); ch >= 1; --ch) {
+    if (force_ch > 0 && ch != force_ch) continue;
+    const int S = (chunks + ch - 1) / ch;
+    if ((int64_t)S * NT > 1024) continue;
+    ResGeom r;
+    r.CH = ch; r.S = S; r.NT = NT; r.threads = S * NT;
+    r.TP = res_tp(S * 4 * ch);
+    r.core_bytes = (size_t)2 * (g.N + 1) * r.TP * 4 + 64 * 4 + MGA_DIAG_COLS * 32 * 4 + (size_t)((g.nnz + 1) & ~1) * 8;
+    r.state_bytes = (size_t)ST_COUNT * g.N * r.TP * 4;
+    *out = r;
+    return true;
+  }
+  return false;
+}
 
-template <int TT, int K, int MAXT>
-inline int launch_res(mga_plan* p, ResArgs& a, int threads, cudaStream_t st) {
+inline int res_forced_ch() {
+  const char* e = std::getenv("MGA_RES_CH");
+  return e ? std::atoi(e) : 0;
+}
+
+template <int CH, int K, int MAXT>
+inline int launch_res(mga_plan* p, ResArgs& a, const ResGeom& geo, cudaStream_t st) {
   const GraphDev& g = p->g;
-  auto kern = k_admm_resident<TT, K, MAXT>;
-  const size_t core = res_core_bytes(g, a.NP);
-  const size_t with_state = core + (size_t)ST_COUNT * g.T * a.NP * 4;
+  auto kern = k_admm_resident<CH, K, MAXT>;
+  const size_t core = geo.core_bytes;
+  const size_t with_state = core + geo.state_bytes;
   // State in shared memory only if it does not cost residency: compare CTAs/SM both ways.
   int occ_core = 0, occ_state = 0;
   MGA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, p->max_smem_optin));
-  MGA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_core, kern, threads, core));
+  MGA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_core, kern, geo.threads, core));
   if (with_state <= (size_t)p->max_smem_optin)
-    MGA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_state, kern, threads, with_state));
+    MGA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_state, kern, geo.threads, with_state));
   if (occ_core < 1) { set_error("resident kernel does not fit on an SM"); return MGA_ERR_UNSUPPORTED; }
   a.state_in_smem = (occ_state >= occ_core) ? 1 : 0;
   const int occ = a.state_in_smem ? occ_state : occ_core;
@@ -448,17 +574,15 @@ inline int launch_res(mga_plan* p, ResArgs& a, int threads, cudaStream_t st) {
     if (rc) return rc;
     a.scratch = static_cast<float*>(p->ws.base);
   }
-  kern<<<(unsigned)grid, threads, smem, st>>>(a);
+  kern<<<(unsigned)grid, geo.threads, smem, st>>>(a);
   MGA_LAUNCH_CHECK("k_admm_resident");
   return MGA_OK;
 }
 
-template <int TT, int K>
-inline int pick_threads(mga_plan* p, ResArgs& a, int threads, cudaStream_t st) {
-  if (threads <= 256) return launch_res<TT, K, 256>(p, a, threads, st);
-  if (threads <= 384) return launch_res<TT, K, 384>(p, a, threads, st);
-  return launch_res<TT, K, 512>(p, a, threads, st);
+template <int CH, int K>
+inline int pick_threads(mga_plan* p, ResArgs& a, const ResGeom& geo, cudaStream_t st) {
+  if (geo.threads <= 512) return launch_res<CH, K, 512>(p, a, geo, st);
+  return launch_res<CH, K, 1024>(p, a, geo, st);
 }
-
 
 }  // namespace mga
