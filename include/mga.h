@@ -203,6 +203,12 @@ int mga_admm_solve_host(mga_plan* plan, const mga_params* prm, const void* y_hos
 int mga_knn_build(int32_t n_nodes, int64_t n_edges, const int64_t* edges, const double* dists,
                   int32_t k, int32_t* out_nodes, float* out_dists);
 
+/* ---- host-only self-check of the resident kernel's plan-time schedule (no GPU needed): verifies
+ * that the internal node order, the per-row visit order and the per-warp in-list ELL are a pure
+ * re-ordering of `desc`.  stats (4 doubles, may be NULL): average shared-memory wavefronts per
+ * quarter-warp gather phase {forward table before, after, in-list before, after} scheduling. */
+int mga_schedule_selfcheck(const mga_graph_desc* desc, double* stats);
+
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */
 int64_t mga_launch_count(void);
 const char* mga_last_error(void);

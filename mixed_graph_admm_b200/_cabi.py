@@ -29,7 +29,7 @@ ERR_INVALID, ERR_INDEX, ERR_CUDA, ERR_UNSUPPORTED, ERR_NONFINITE = -1, -2, -3, -
 EXPORTS = [
     "mga_plan_create", "mga_plan_destroy", "mga_plan_resident_eligible", "mga_plan_info", "mga_apply",
     "mga_cg_solve", "mga_initial_guess", "mga_rhs_x", "mga_dual_ascent", "mga_prox_phi_dual", "mga_phi_direct",
-    "mga_admm_solve", "mga_admm_solve_host", "mga_knn_build", "mga_launch_count", "mga_last_error", "mga_version",
+    "mga_admm_solve", "mga_admm_solve_host", "mga_knn_build", "mga_schedule_selfcheck", "mga_launch_count", "mga_last_error", "mga_version",
 ]
 
 
@@ -94,6 +94,7 @@ def lib():
         L.mga_admm_solve_host.argtypes = [vp, C.POINTER(Params), vp, C.c_int, vp, i64, C.c_int, C.c_int, C.c_int,
                                           dbl, dbl, C.c_int, vp, vp, C.c_int, i64]
         L.mga_knn_build.argtypes = [i32, i64, vp, vp, i32, vp, vp]
+        L.mga_schedule_selfcheck.argtypes = [C.POINTER(GraphDesc), C.POINTER(dbl)]
         for name in EXPORTS:
             getattr(L, name)        # AttributeError here = header and library out of step
         _lib = L

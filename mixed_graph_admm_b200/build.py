@@ -12,7 +12,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(OUT_DIR, "libmga.so")
-SOURCES = ["mga_plan.cu", "mga_stream.cu", "mga_resident.cu", "mga_knn.cpp"]
+SOURCES = ["mga_plan.cu", "mga_stream.cu", "mga_resident.cu", "mga_knn.cpp", "mga_schedule.cpp"]
 # the resident kernel is instantiated once per (T bound, K bound), one translation unit each
 RESIDENT_VARIANTS = [(ch, k) for ch in (1, 2, 3) for k in (5, 7, 9)]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -36,7 +36,7 @@ def _stale(target, deps):
 def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) -> str:
     os.makedirs(OUT_DIR, exist_ok=True)
     nvcc = _nvcc()
-    headers = [os.path.join(CSRC, "mga_common.cuh"), os.path.join(CSRC, "mga_resident.cuh"),
+    headers = [os.path.join(CSRC, "mga_common.cuh"), os.path.join(CSRC, "mga_resident.cuh"), os.path.join(CSRC, "mga_schedule.h"),
                os.path.join(ROOT, "include", "mga.h"), __file__]
     jobs = []
     objs = []
@@ -50,7 +50,7 @@ def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) 
             cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if ptxas_info else []) + ["-c", sp, "-o", obj]
             if src.endswith(".cpp"):
                 cmd = [nvcc, "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"),
-                       "-x", "c++", "-c", sp, "-o", obj]
+                       "-I", CSRC, "-x", "c++", "-c", sp, "-o", obj]
             jobs.append(cmd)
 
     inst = os.path.join(CSRC, "mga_resident_inst.cu")

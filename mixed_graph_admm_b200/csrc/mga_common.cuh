@@ -63,9 +63,19 @@ struct mga_plan {
   size_t pinned_bytes = 0;
   cudaStream_t io_streams[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t io_events[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  // host copies for the resident-kernel set-up
+  // host copies of the tables
   std::vector<int> h_nbr_u, h_nbr_d, h_csr_ptr, h_csr_src;
   std::vector<float> h_u_w, h_d_w, h_csr_w;
+  // resident-kernel schedule (mga_schedule.cpp), device copies
+  bool has_sched = false;
+  const int* r_perm = nullptr;
+  const int* r_nbr_d = nullptr;
+  const float* r_w_d = nullptr;
+  const int* r_nbr_u = nullptr;
+  const float* r_w_u = nullptr;
+  const int* r_ell_ptr = nullptr;
+  const int* r_ell_ent = nullptr;     // int2 pairs (node, weight bits)
+  int r_ell_total = 0;
 };
 
 namespace mga {

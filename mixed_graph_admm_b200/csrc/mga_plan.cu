@@ -11,6 +11,7 @@
 #include <cstring>
 
 #include "mga_common.cuh"
+#include "mga_schedule.h"
 
 namespace mga {
 
@@ -68,15 +69,9 @@ static int collapse_time(const float* w, int nT, size_t slice, std::vector<float
 
 using namespace mga;
 
-extern "C" {
-
-int mga_version(void) { return MGA_VERSION; }
-const char* mga_last_error(void) { return t_error.c_str(); }
-int64_t mga_launch_count(void) { return g_launches.load(); }
-
-int mga_plan_create(const mga_graph_desc* d, int device, mga_plan** out) {
-  if (!d || !out) { set_error("mga_plan_create: NULL argument"); return MGA_ERR_INVALID; }
-  *out = nullptr;
+// Everything of plan construction that needs no device: index validation, narrowing, collapse of
+// time-expanded weights, the in-list.  `slot` receives, per in-list entry, its index into d_w.
+static int validate_desc(const mga_graph_desc* d) {
   const int N = d->n_nodes, T = d->T;
   if (N <= 0 || T < 2 || d->t_in < 1 || d->t_in > T || d->ku < 0 || !d->nbr_u && d->ku > 0) {
     set_error("mga_plan_create: bad shape (need N>0, T>=2, 1<=t_in<=T)");
@@ -94,47 +89,36 @@ int mga_plan_create(const mga_graph_desc* d, int device, mga_plan** out) {
     set_error("mga_plan_create: u_w must be (N,ku) or (T,N,ku)");
     return MGA_ERR_INVALID;
   }
-  int ndev = 0;
-  MGA_CUDA(cudaGetDeviceCount(&ndev));
-  if (device < 0 || device >= ndev) { set_error("mga_plan_create: no such CUDA device"); return MGA_ERR_CUDA; }
-  MGA_CUDA(cudaSetDevice(device));
+  return MGA_OK;
+}
 
-  mga_plan* p = new mga_plan();
-  p->device = device;
-  cudaDeviceProp prop;
-  cudaError_t e = cudaGetDeviceProperties(&prop, device);
-  if (e != cudaSuccess) { delete p; return cuda_fail(e, "cudaGetDeviceProperties"); }
-  p->sm_count = prop.multiProcessorCount;
-  p->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
-
+static int host_tables(const mga_graph_desc* d, mga_plan* p, std::vector<int>& slot) {
+  const int N = d->n_nodes, T = d->T;
   GraphDev& g = p->g;
   g.N = N; g.T = T; g.t_in = d->t_in; g.ku = d->ku;
   g.temporal = d->temporal; g.skip = 0;
-  int rc = MGA_OK;
-  auto fail = [&](int code) { mga_plan_destroy(p); return code; };
 
   // ---- spatial table
   p->h_nbr_u.resize((size_t)N * d->ku);
   for (size_t k = 0; k < p->h_nbr_u.size(); ++k) {
     int64_t v = d->nbr_u[k];
-    if (v < -1 || v >= N) { set_error("Index out of bounds"); return fail(MGA_ERR_INDEX); }
+    if (v < -1 || v >= N) { set_error("Index out of bounds"); return (MGA_ERR_INDEX); }
     p->h_nbr_u[k] = (int)v;
   }
   g.u_wT = d->ku > 0 ? collapse_time(d->u_w, d->u_w_T, (size_t)N * d->ku, p->h_u_w) : 1;
 
   // ---- temporal table + in-list
-  std::vector<int> slot;
   if (d->temporal == MGA_TEMPORAL_GRAPH) {
     if (d->d_w_T != 1 && d->d_w_T != T - 1) {
       set_error("mga_plan_create: d_w must be (N,kd) or (T-1,N,kd)");
-      return fail(MGA_ERR_INVALID);
+      return (MGA_ERR_INVALID);
     }
     g.kd = d->kd;
     g.q1 = 1;  // ADMM.py:220-222
     p->h_nbr_d.resize((size_t)N * g.kd);
     for (size_t k = 0; k < p->h_nbr_d.size(); ++k) {
       int64_t v = d->nbr_d[k];
-      if (v < -1 || v >= N) { set_error("Index out of bounds"); return fail(MGA_ERR_INDEX); }
+      if (v < -1 || v >= N) { set_error("Index out of bounds"); return (MGA_ERR_INDEX); }
       p->h_nbr_d[k] = (int)v;
     }
     g.d_wT = collapse_time(d->d_w, d->d_w_T, (size_t)N * g.kd, p->h_d_w);
@@ -173,7 +157,7 @@ int mga_plan_create(const mga_graph_desc* d, int device, mga_plan** out) {
         }
     } else {
       set_error("mga_plan_create: bad ldrt_mode");
-      return fail(MGA_ERR_INVALID);
+      return (MGA_ERR_INVALID);
     }
   } else if (d->temporal == MGA_TEMPORAL_LINE) {
     // first difference in time (ADMM.py:153-157, 182-186): self link with unit weight, no Q1 term
@@ -189,7 +173,7 @@ int mga_plan_create(const mga_graph_desc* d, int device, mga_plan** out) {
     p->h_csr_ptr[N] = N;
   } else {
     // banded temporal stencil (ADMM.py:41-52, 158-164, 187-194): weights (T, skip, N)
-    if (d->kd < 1 || !d->d_w) { set_error("mga_plan_create: BAND needs d_w (T,skip,N), kd=skip"); return fail(MGA_ERR_INVALID); }
+    if (d->kd < 1 || !d->d_w) { set_error("mga_plan_create: BAND needs d_w (T,skip,N), kd=skip"); return (MGA_ERR_INVALID); }
     g.kd = 0;
     g.q1 = 0;
     g.d_wT = 1;
@@ -202,6 +186,38 @@ int mga_plan_create(const mga_graph_desc* d, int device, mga_plan** out) {
   p->h_csr_w.resize(g.nnz);
   for (int k = 0; k < g.nnz; ++k) p->h_csr_w[k] = p->h_d_w[slot[k]];
 
+  return MGA_OK;
+}
+
+extern "C" {
+
+int mga_version(void) { return MGA_VERSION; }
+const char* mga_last_error(void) { return t_error.c_str(); }
+int64_t mga_launch_count(void) { return g_launches.load(); }
+
+int mga_plan_create(const mga_graph_desc* d, int device, mga_plan** out) {
+  if (!d || !out) { set_error("mga_plan_create: NULL argument"); return MGA_ERR_INVALID; }
+  *out = nullptr;
+  int rc = validate_desc(d);
+  if (rc) return rc;
+  const int N = d->n_nodes, T = d->T;
+  int ndev = 0;
+  MGA_CUDA(cudaGetDeviceCount(&ndev));
+  if (device < 0 || device >= ndev) { set_error("mga_plan_create: no such CUDA device"); return MGA_ERR_CUDA; }
+  MGA_CUDA(cudaSetDevice(device));
+
+  mga_plan* p = new mga_plan();
+  p->device = device;
+  cudaDeviceProp prop;
+  cudaError_t e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) { delete p; return cuda_fail(e, "cudaGetDeviceProperties"); }
+  p->sm_count = prop.multiProcessorCount;
+  p->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+
+  GraphDev& g = p->g;
+  auto fail = [&](int code) { mga_plan_destroy(p); return code; };
+  std::vector<int> slot;
+  if ((rc = host_tables(d, p, slot))) return fail(rc);
   if ((rc = upload(p, p->h_nbr_u, &g.nbr_u))) return fail(rc);
   if ((rc = upload(p, p->h_u_w, &g.u_w))) return fail(rc);
   if ((rc = upload(p, p->h_nbr_d, &g.nbr_d))) return fail(rc);
@@ -215,10 +231,145 @@ int mga_plan_create(const mga_graph_desc* d, int device, mga_plan** out) {
     std::vector<float> bw(d->d_w, d->d_w + (size_t)T * g.skip * N);
     if ((rc = upload(p, bw, &g.band_w))) return fail(rc);
   }
+  // resident-kernel schedule: only for time-invariant tables of a size one CTA can own
+  if (d->temporal != MGA_TEMPORAL_BAND && g.u_wT == 1 && g.d_wT == 1 && N <= 1024) {
+    ResidentSchedule sc;
+    build_resident_schedule(N, g.kd, p->h_nbr_d.data(), p->h_d_w.data(), g.ku, p->h_nbr_u.data(), p->h_u_w.data(),
+                            p->h_csr_ptr.data(), p->h_csr_src.data(), p->h_csr_w.data(), &sc);
+    std::vector<int> ent(sc.ell_node.size() * 2);
+    for (size_t k = 0; k < sc.ell_node.size(); ++k) {
+      ent[2 * k] = sc.ell_node[k];
+      std::memcpy(&ent[2 * k + 1], &sc.ell_w[k], sizeof(float));
+    }
+    p->r_ell_total = (int)sc.ell_node.size();
+    if ((rc = upload(p, sc.perm, &p->r_perm))) return fail(rc);
+    if ((rc = upload(p, sc.nbr_d, &p->r_nbr_d))) return fail(rc);
+    if ((rc = upload(p, sc.w_d, &p->r_w_d))) return fail(rc);
+    if ((rc = upload(p, sc.nbr_u, &p->r_nbr_u))) return fail(rc);
+    if ((rc = upload(p, sc.w_u, &p->r_w_u))) return fail(rc);
+    if ((rc = upload(p, sc.ell_ptr, &p->r_ell_ptr))) return fail(rc);
+    if ((rc = upload(p, ent, &p->r_ell_ent))) return fail(rc);
+    p->has_sched = true;
+  }
   p->pinned_bytes = 1 << 16;
   e = cudaMallocHost(&p->pinned, p->pinned_bytes);
   if (e != cudaSuccess) { int c = cuda_fail(e, "cudaMallocHost"); return fail(c); }
   *out = p;
+  return MGA_OK;
+}
+
+// Host-only: build the tables and the resident schedule for `d` and verify that the schedule is a
+// pure re-ordering (node permutation, per-row visit order, in-list placement) of the input.
+int mga_schedule_selfcheck(const mga_graph_desc* d, double* stats) {
+  if (!d) { set_error("mga_schedule_selfcheck: NULL argument"); return MGA_ERR_INVALID; }
+  int rc = validate_desc(d);
+  if (rc) return rc;
+  if (d->temporal == MGA_TEMPORAL_BAND) { set_error("no resident schedule for the banded stencil"); return MGA_ERR_UNSUPPORTED; }
+  mga_plan tmp;
+  std::vector<int> slot;
+  if ((rc = host_tables(d, &tmp, slot))) return rc;
+  const GraphDev& g = tmp.g;
+  if (g.u_wT != 1 || g.d_wT != 1) { set_error("no resident schedule for time-varying weights"); return MGA_ERR_UNSUPPORTED; }
+  const int N = g.N;
+  ResidentSchedule sc;
+  build_resident_schedule(N, g.kd, tmp.h_nbr_d.data(), tmp.h_d_w.data(), g.ku, tmp.h_nbr_u.data(), tmp.h_u_w.data(),
+                          tmp.h_csr_ptr.data(), tmp.h_csr_src.data(), tmp.h_csr_w.data(), &sc);
+  auto bad = [&](const char* what) { set_error(std::string("schedule self-check failed: ") + what); return MGA_ERR_INVALID; };
+  // (a) permutation
+  std::vector<char> hit(N, 0);
+  for (int p = 0; p < N; ++p) {
+    const int o = sc.perm[p];
+    if (o < 0 || o >= N || hit[o]) return bad("perm is not a permutation");
+    hit[o] = 1;
+    if (sc.inv[o] != p) return bad("inv is not the inverse of perm");
+  }
+  typedef std::pair<int, float> Ent;
+  auto same_multiset = [](std::vector<Ent> a, std::vector<Ent> b) {
+    std::sort(a.begin(), a.end());
+    std::sort(b.begin(), b.end());
+    return a == b;
+  };
+  // (b) forward rows: same (neighbour, weight) multiset, -1 slots became zero-weight zero-row slots
+  auto check_fwd = [&](int K, const std::vector<int>& nbr, const std::vector<float>& w, const std::vector<int>& s_n,
+                       const std::vector<float>& s_w) {
+    for (int p = 0; p < N; ++p) {
+      const int o = sc.perm[p];
+      std::vector<Ent> a, b;
+      for (int j = 0; j < K; ++j) {
+        const int nb = nbr[(size_t)o * K + j];
+        a.emplace_back(nb >= 0 ? nb : -1, nb >= 0 ? w[(size_t)o * K + j] : 0.f);
+        const int sn = s_n[(size_t)p * K + j];
+        if (sn < 0 || sn > N) return false;
+        b.emplace_back(sn < N ? sc.perm[sn] : -1, s_w[(size_t)p * K + j]);
+      }
+      if (!same_multiset(a, b)) return false;
+    }
+    return true;
+  };
+  if (!check_fwd(g.kd, tmp.h_nbr_d, tmp.h_d_w, sc.nbr_d, sc.w_d)) return bad("temporal table rows differ");
+  if (!check_fwd(g.ku, tmp.h_nbr_u, tmp.h_u_w, sc.nbr_u, sc.w_u)) return bad("spatial table rows differ");
+  // (c) in-list: every node's ELL column holds exactly its CSR row (+ zero-weight padding)
+  const int n_warps = (N + 31) / 32;
+  for (int p = 0; p < n_warps * 32; ++p) {
+    const int w = p / 32, l = p % 32;
+    std::vector<Ent> a, b;
+    if (p < N) {
+      const int o = sc.perm[p];
+      for (int e = tmp.h_csr_ptr[o]; e < tmp.h_csr_ptr[o + 1]; ++e) a.emplace_back(tmp.h_csr_src[e], tmp.h_csr_w[e]);
+    }
+    for (int e = sc.ell_ptr[w]; e < sc.ell_ptr[w + 1]; ++e) {
+      const int sn = sc.ell_node[(size_t)e * 32 + l];
+      const float sw = sc.ell_w[(size_t)e * 32 + l];
+      if (sn == N) { if (sw != 0.f) return bad("padding entry with weight"); continue; }
+      if (sn < 0 || sn > N) return bad("in-list node out of range");
+      b.emplace_back(sc.perm[sn], sw);
+    }
+    if (!same_multiset(a, b)) return bad("in-list differs");
+  }
+  if (stats) {
+    // average wavefronts per quarter-warp phase, before (input order) and after scheduling
+    auto phase = [&](const std::vector<int>& nodes) {
+      int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      std::vector<int> u(nodes);
+      std::sort(u.begin(), u.end());
+      u.erase(std::unique(u.begin(), u.end()), u.end());
+      int m = 1;
+      for (int n : u) if (n >= 0 && n < N) m = std::max(m, ++cnt[n & 7]);
+      return m;
+    };
+    auto fwd_cost = [&](int K, const std::vector<int>& tab) {
+      double tot = 0; int c = 0;
+      for (int q0 = 0; q0 < N; q0 += 8)
+        for (int j = 0; j < K; ++j) {
+          std::vector<int> t;
+          for (int r = q0; r < std::min(N, q0 + 8); ++r) t.push_back(tab[(size_t)r * K + j]);
+          tot += phase(t); ++c;
+        }
+      return c ? tot / c : 1.0;
+    };
+    stats[0] = fwd_cost(g.kd, tmp.h_nbr_d);
+    stats[1] = fwd_cost(g.kd, sc.nbr_d);
+    double tot = 0, tot2 = 0; int c = 0, c2 = 0;
+    for (int q0 = 0; q0 < N; q0 += 8) {
+      int m = 0;
+      for (int r = q0; r < std::min(N, q0 + 8); ++r) m = std::max(m, tmp.h_csr_ptr[r + 1] - tmp.h_csr_ptr[r]);
+      for (int e = 0; e < m; ++e) {
+        std::vector<int> t;
+        for (int r = q0; r < std::min(N, q0 + 8); ++r)
+          if (tmp.h_csr_ptr[r] + e < tmp.h_csr_ptr[r + 1]) t.push_back(tmp.h_csr_src[tmp.h_csr_ptr[r] + e]);
+        tot += phase(t); ++c;
+      }
+    }
+    for (int w = 0; w < n_warps; ++w)
+      for (int e = sc.ell_ptr[w]; e < sc.ell_ptr[w + 1]; ++e)
+        for (int q0 = 0; q0 < 32; q0 += 8) {
+          std::vector<int> t;
+          for (int l = q0; l < q0 + 8; ++l) t.push_back(sc.ell_node[(size_t)e * 32 + l]);
+          tot2 += phase(t); ++c2;
+        }
+    stats[2] = c ? tot / c : 1.0;
+    stats[3] = c2 ? tot2 / c2 : 1.0;
+  }
   return MGA_OK;
 }
 

@@ -16,7 +16,8 @@ constexpr int kResMaxK = 9;
 
 static bool geometry(const mga_plan* p, ResGeom* geo) {
   const GraphDev& g = p->g;
-  if (!res_geometry(g, res_forced_ch(), geo) && !res_geometry(g, 0, geo)) return false;
+  if (!p->has_sched) return false;
+  if (!res_geometry(g, p->r_ell_total, res_forced_ch(), geo) && !res_geometry(g, p->r_ell_total, 0, geo)) return false;
   return geo->core_bytes <= (size_t)p->max_smem_optin;
 }
 
@@ -58,8 +59,8 @@ int resident_admm(mga_plan* p, const mga_params* m, const void* y, void* x_out, 
   if (!geometry(p, &geo)) { set_error("resident: shape does not fit"); return MGA_ERR_UNSUPPORTED; }
   a.NT = geo.NT; a.S = geo.S; a.TP = geo.TP;
   a.B = B; a.kd = g.kd; a.ku = g.ku;
-  a.nbr_d = g.nbr_d; a.d_w = g.d_w; a.nbr_u = g.nbr_u; a.u_w = g.u_w;
-  a.csr_ptr = g.csr_ptr; a.csr_src = g.csr_src; a.csr_w = g.csr_w;
+  a.perm = p->r_perm; a.nbr_d = p->r_nbr_d; a.d_w = p->r_w_d; a.nbr_u = p->r_nbr_u; a.u_w = p->r_w_u;
+  a.ell_ptr = p->r_ell_ptr; a.ell_ent = reinterpret_cast<const int2*>(p->r_ell_ent); a.ell_total = p->r_ell_total;
   a.y = static_cast<const float*>(y);
   a.x_out = static_cast<float*>(x_out);
   a.out[ST_ZU] = static_cast<float*>(outs->zu);

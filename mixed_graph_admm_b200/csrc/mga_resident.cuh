@@ -18,8 +18,10 @@
 // touched off-chunk: p[k+1] and qs[k-1] across the slab edge, one scalar load each.
 //
 // The thread's rows of the ELL tables (neighbour row offsets + weights, time-invariant) sit in
-// registers; the in-list (transposed CSR) that replaces the reference's scatter_add sits in
-// shared memory as (row offset, weight) pairs.  The seven ADMM state vectors are parked between
+// registers; the in-list (the transpose that replaces the reference's scatter_add) sits in
+// shared memory as a per-warp, step-major ELL of (row offset, weight) pairs, read conflict-free.
+// Node numbering, the visit order of a row's neighbours and of its in-list are chosen at plan
+// time (mga_schedule.cpp) so that quarter-warps hit distinct bank groups.  The seven ADMM state vectors are parked between
 // solves in shared memory when they fit, else in a per-CTA L2-resident scratch.  HBM traffic
 // per window is y in, x out (+ optional iterates / diagnostics).
 //
@@ -43,8 +45,12 @@ struct ResArgs {
   int TP;      // row stride of the node-major buffers, floats (4 * odd, >= S * 4 * CH)
   int64_t B;
   int kd, ku;
-  const int* nbr_d; const float* d_w; const int* nbr_u; const float* u_w;
-  const int* csr_ptr; const int* csr_src; const float* csr_w;
+  // scheduled tables of the plan (mga_schedule.cpp): internal node order, conflict-aware slot order
+  const int* perm;            // perm[internal] = original node (global memory is in original order)
+  const int* nbr_d; const float* d_w; const int* nbr_u; const float* u_w;   // (N, kd) / (N, ku), N = zero row
+  const int* ell_ptr;         // (NT/32 + 1) first in-list step of each 32-row warp
+  const int2* ell_ent;        // (ell_total) step-major: (internal src or N, weight bits) per lane
+  int ell_total;
   const float* y; float* x_out;
   float* out[ST_COUNT];       // optional per-window outputs (index by ST_*; ST_X unused)
   float* scratch;             // gridDim.x * ST_COUNT * T * N floats when !state_in_smem
@@ -66,10 +72,10 @@ struct Ctx {
   float wd[K];
   int nu[K - 1];
   float wu[K - 1];
-  int e0, e1;
+  int steps;                 // in-list steps of this thread's warp (padded with zero-weight entries)
   float* pbuf;
   float* qbuf;
-  const int2* ent;           // (src * TP, weight bits)
+  const int2* ent;           // this lane's first in-list entry; stride 32: (src * TP + t0, weight bits)
   float* red;                // 2 x 32
   int red_sel;
 
@@ -122,14 +128,14 @@ struct Ctx {
   __device__ __forceinline__ void father_sum(const float* buf, float (&f)[TS]) const {
 #pragma unroll
     for (int k = 0; k < TS; ++k) f[k] = 0.f;
-    int e = e0;
-    for (; e + 1 < e1; e += 2) {          // two entries per trip: more loads in flight
-      const int2 a = ent[e], b = ent[e + 1];
+    int e = 0;
+    for (; e + 1 < steps; e += 2) {       // two entries per trip: more loads in flight
+      const int2 a = ent[e * 32], b = ent[(e + 1) * 32];
       gather_acc(buf, a.x + t0, __int_as_float(a.y), f);
       gather_acc(buf, b.x + t0, __int_as_float(b.y), f);
     }
-    if (e < e1) {
-      const int2 a = ent[e];
+    if (e < steps) {
+      const int2 a = ent[e * 32];
       gather_acc(buf, a.x + t0, __int_as_float(a.y), f);
     }
   }
@@ -233,7 +239,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_admm_resident(const ResArgs a) {
   float* red = qbuf + rows;                         // 64 floats
   float* dred = red + 64;                           // MGA_DIAG_COLS x 32 floats
   int2* ent = reinterpret_cast<int2*>(dred + MGA_DIAG_COLS * 32);
-  float* st_smem = reinterpret_cast<float*>(ent + ((a.nnz + 1) & ~1));
+  float* st_smem = reinterpret_cast<float*>(ent + a.ell_total);
   const int s = threadIdx.x / a.NT;
   const int i = threadIdx.x - s * a.NT;
   const bool active = i < N;
@@ -244,27 +250,34 @@ __global__ void __launch_bounds__(MAXT, 1) k_admm_resident(const ResArgs a) {
   c.has_next = (s + 1 < a.S);
   c.has_prev = (s > 0);
   c.own = (active ? i : N) * TP + t0;     // inactive lanes park on the zero row (they only ever write zeros)
-  c.pbuf = pbuf; c.qbuf = qbuf; c.ent = ent; c.red = red; c.red_sel = 0;
+  c.pbuf = pbuf; c.qbuf = qbuf; c.red = red; c.red_sel = 0;
 #pragma unroll
   for (int j = 0; j < K; ++j) {
-    int nb = -1;
+    int nb = N;
     float w = 0.f;
     if (active && j < a.kd) { nb = a.nbr_d[i * a.kd + j]; w = a.d_w[i * a.kd + j]; }
-    c.nd[j] = (nb >= 0 ? nb : N) * TP + t0;
-    c.wd[j] = nb >= 0 ? w : 0.f;
+    c.nd[j] = nb * TP + t0;
+    c.wd[j] = w;
   }
 #pragma unroll
   for (int j = 0; j < K - 1; ++j) {
-    int nb = -1;
+    int nb = N;
     float w = 0.f;
     if (active && j < a.ku) { nb = a.nbr_u[i * a.ku + j]; w = a.u_w[i * a.ku + j]; }
-    c.nu[j] = (nb >= 0 ? nb : N) * TP + t0;
-    c.wu[j] = nb >= 0 ? w : 0.f;
+    c.nu[j] = nb * TP + t0;
+    c.wu[j] = w;
   }
-  c.e0 = active ? a.csr_ptr[i] : 0;
-  c.e1 = active ? a.csr_ptr[i + 1] : 0;
-  for (int e = threadIdx.x; e < a.nnz; e += blockDim.x)
-    ent[e] = make_int2(a.csr_src[e] * TP, __float_as_int(a.csr_w[e]));
+  {
+    const int wn = i >> 5;     // warp of this node row (the same for every slab)
+    const int first = a.ell_ptr[wn];
+    c.steps = a.ell_ptr[wn + 1] - first;
+    c.ent = ent + (size_t)first * 32 + (i & 31);
+  }
+  for (int e = threadIdx.x; e < a.ell_total; e += blockDim.x) {
+    const int2 en = a.ell_ent[e];
+    ent[e] = make_int2(en.x * TP, en.y);
+  }
+  const int orig = active ? a.perm[i] : 0;   // this thread's node in the caller's numbering
   for (int k = threadIdx.x; k < 2 * rows; k += blockDim.x) pbuf[k] = 0.f;
   __syncthreads();
 
@@ -299,7 +312,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_admm_resident(const ResArgs a) {
   };
 
   for (int64_t b = blockIdx.x; b < a.B; b += gridDim.x) {
-    const float* yw = a.y + (size_t)b * t_in * N + (active ? i : 0);
+    const float* yw = a.y + (size_t)b * t_in * N + orig;
     float x[TS];
     // ---- initial_guess (ADMM.py:766-781) and initial state (ADMM.py:537-544)
     {
@@ -386,7 +399,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_admm_resident(const ResArgs a) {
             if (active && t0 + k < T) {
               const float dx = x[k] - xo[k];
               dg[MGA_DIAG_DX2] += dx * dx;
-              if (a.dx_sum) atomicAdd(a.dx_sum + ((size_t)it * T + t0 + k) * N + i, (double)dx);
+              if (a.dx_sum) atomicAdd(a.dx_sum + ((size_t)it * T + t0 + k) * N + orig, (double)dx);
             }
           }
         }
@@ -496,7 +509,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_admm_resident(const ResArgs a) {
     if (active) {
 #pragma unroll
       for (int k = 0; k < TS; ++k)
-        if (t0 + k < T) a.x_out[((size_t)b * T + t0 + k) * N + i] = x[k];
+        if (t0 + k < T) a.x_out[((size_t)b * T + t0 + k) * N + orig] = x[k];
     }
     for (int v = ST_ZU; v < ST_COUNT; ++v) {
       if (a.out[v]) {
@@ -505,7 +518,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_admm_resident(const ResArgs a) {
         if (active) {
 #pragma unroll
           for (int k = 0; k < TS; ++k)
-            if (t0 + k < T) a.out[v][((size_t)b * T + t0 + k) * N + i] = o[k];
+            if (t0 + k < T) a.out[v][((size_t)b * T + t0 + k) * N + orig] = o[k];
         }
       }
     }
@@ -528,7 +541,7 @@ inline int res_tp(int min_len) {          // smallest 4 * odd >= min_len
 // CH = chunks of 4 time steps per thread.  Default: the largest CH <= 3 (a node's table rows and
 // in-list entries are then read once per 12 time steps; measured 252k vs 210k windows/s against
 // CH = 1 at PEMS04 shape on B200); MGA_RES_CH overrides for experiments.
-inline bool res_geometry(const GraphDev& g, int force_ch, ResGeom* out) {
+inline bool res_geometry(const GraphDev& g, int ell_total, int force_ch, ResGeom* out) {
   const int NT = ((g.N + 31) / 32) * 32;
   const int chunks = (g.T + 3) / 4;
   for (int ch = std::min(3, chunks); ch >= 1; --ch) {
@@ -538,7 +551,7 @@ inline bool res_geometry(const GraphDev& g, int force_ch, ResGeom* out) {
     ResGeom r;
     r.CH = ch; r.S = S; r.NT = NT; r.threads = S * NT;
     r.TP = res_tp(S * 4 * ch);
-    r.core_bytes = (size_t)2 * (g.N + 1) * r.TP * 4 + 64 * 4 + MGA_DIAG_COLS * 32 * 4 + (size_t)((g.nnz + 1) & ~1) * 8;
+    r.core_bytes = (size_t)2 * (g.N + 1) * r.TP * 4 + 64 * 4 + MGA_DIAG_COLS * 32 * 4 + (size_t)ell_total * 8;
     r.state_bytes = (size_t)ST_COUNT * g.N * r.TP * 4;
     *out = r;
     return true;

@@ -1,0 +1,24 @@
+// Host-side schedule of the resident kernel's gathers (see mga_schedule.cpp).
+#pragma once
+#include <vector>
+
+namespace mga {
+
+struct ResidentSchedule {
+  int N = 0, kd = 0, ku = 0;
+  std::vector<int> perm;      // perm[internal] = original node
+  std::vector<int> inv;       // inv[original] = internal
+  std::vector<int> nbr_d;     // (N, kd) internal ids, N = zero row
+  std::vector<float> w_d;
+  std::vector<int> nbr_u;     // (N, ku)
+  std::vector<float> w_u;
+  std::vector<int> ell_ptr;   // (n_warps + 1) first step of each 32-row warp
+  std::vector<int> ell_node;  // (steps_total * 32) internal ids, N = padding
+  std::vector<float> ell_w;
+};
+
+void build_resident_schedule(int N, int kd, const int* nbr_d, const float* d_w, int ku, const int* nbr_u,
+                             const float* u_w, const int* csr_ptr, const int* csr_src, const float* csr_w,
+                             ResidentSchedule* out);
+
+}  // namespace mga
