@@ -12,7 +12,8 @@ import threading
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "_lib", "libmga.so")
+# MGA_LIB selects an experiment build of the same library (mixed_graph_admm_b200/build.py --tag=...)
+LIB_PATH = os.environ.get("MGA_LIB") or os.path.join(HERE, "_lib", "libmga.so")
 
 MGA_F32, MGA_F64 = 0, 1
 LDRT_SCATTER, LDRT_GATHER = 0, 1

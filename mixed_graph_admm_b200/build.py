@@ -33,9 +33,14 @@ def _stale(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) -> str:
-    os.makedirs(OUT_DIR, exist_ok=True)
+def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False, tag: str = "", defines=()) -> str:
+    """Default: _lib/libmga.so.  `tag` + `defines` build an experiment variant (e.g. tag="tab1",
+    defines=["MGA_RES_TAB_SMEM=1"]) into _lib/<tag>/libmga.so; select it with MGA_LIB=<path>."""
+    out_dir = os.path.join(OUT_DIR, tag) if tag else OUT_DIR
+    lib_path = os.path.join(out_dir, "libmga.so")
+    os.makedirs(out_dir, exist_ok=True)
     nvcc = _nvcc()
+    flags = NVCC_FLAGS + [f"-D{d}" for d in defines]
     headers = [os.path.join(CSRC, "mga_common.cuh"), os.path.join(CSRC, "mga_resident.cuh"), os.path.join(CSRC, "mga_schedule.h"),
                os.path.join(ROOT, "include", "mga.h"), __file__]
     jobs = []
@@ -44,10 +49,10 @@ def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) 
         sp = os.path.join(CSRC, src)
         if not os.path.exists(sp):
             continue
-        obj = os.path.join(OUT_DIR, os.path.splitext(src)[0] + ".o")
+        obj = os.path.join(out_dir, os.path.splitext(src)[0] + ".o")
         objs.append(obj)
         if force or _stale(obj, [sp] + headers):
-            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if ptxas_info else []) + ["-c", sp, "-o", obj]
+            cmd = [nvcc] + flags + (["-Xptxas", "-v"] if ptxas_info else []) + ["-c", sp, "-o", obj]
             if src.endswith(".cpp"):
                 cmd = [nvcc, "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"),
                        "-I", CSRC, "-x", "c++", "-c", sp, "-o", obj]
@@ -55,10 +60,10 @@ def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) 
 
     inst = os.path.join(CSRC, "mga_resident_inst.cu")
     for tt, k in RESIDENT_VARIANTS:
-        obj = os.path.join(OUT_DIR, f"mga_resident_ch{tt}_k{k}.o")
+        obj = os.path.join(out_dir, f"mga_resident_ch{tt}_k{k}.o")
         objs.append(obj)
         if force or _stale(obj, [inst] + headers):
-            jobs.append([nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if ptxas_info else []) +
+            jobs.append([nvcc] + flags + (["-Xptxas", "-v"] if ptxas_info else []) +
                         [f"-DMGA_CH={tt}", f"-DMGA_K={k}", "-c", inst, "-o", obj])
 
     def run(cmd):
@@ -75,10 +80,13 @@ def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) 
         if ptxas_info:
             for lg in logs:
                 sys.stderr.write(lg)
-    if jobs or force or _stale(LIB, objs):
-        run([nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
-    return LIB
+    if jobs or force or _stale(lib_path, objs):
+        run([nvcc, "-shared", "-o", lib_path] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
+    return lib_path
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose=True, ptxas_info="--ptxas" in sys.argv))
+    _tag = next((a.split("=", 1)[1] for a in sys.argv if a.startswith("--tag=")), "")
+    _defs = [a[2:] for a in sys.argv if a.startswith("-D")]
+    print(build(force="--force" in sys.argv, verbose="--quiet" not in sys.argv, ptxas_info="--ptxas" in sys.argv,
+                tag=_tag, defines=_defs))

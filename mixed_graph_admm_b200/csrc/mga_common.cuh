@@ -76,6 +76,10 @@ struct mga_plan {
   const int* r_ell_ptr = nullptr;
   const int* r_ell_ent = nullptr;     // int2 pairs (node, weight bits)
   int r_ell_total = 0;
+  // work counters of the resident kernel's dynamic window hand-out: a ring, one per launch in flight
+  static constexpr int kCounters = 16;
+  int* r_counters = nullptr;          // kCounters x 32 ints (128 B apart)
+  unsigned r_counter_next = 0;
 };
 
 namespace mga {

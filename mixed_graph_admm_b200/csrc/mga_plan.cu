@@ -249,6 +249,10 @@ int mga_plan_create(const mga_graph_desc* d, int device, mga_plan** out) {
     if ((rc = upload(p, sc.w_u, &p->r_w_u))) return fail(rc);
     if ((rc = upload(p, sc.ell_ptr, &p->r_ell_ptr))) return fail(rc);
     if ((rc = upload(p, ent, &p->r_ell_ent))) return fail(rc);
+    void* ctr = nullptr;
+    MGA_CUDA(cudaMalloc(&ctr, mga_plan::kCounters * 32 * sizeof(int)));
+    p->owned.push_back(ctr);
+    p->r_counters = static_cast<int*>(ctr);
     p->has_sched = true;
   }
   p->pinned_bytes = 1 << 16;

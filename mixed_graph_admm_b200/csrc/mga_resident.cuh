@@ -2,7 +2,8 @@
 //
 // Work mapping.  The T time steps of a node are cut into chunks of 4; a thread owns CH
 // consecutive chunks of ONE node (thread = (node i, slab s), slab-major so a warp is uniform in
-// s).  The four CG vectors (x, r, p, Ap) of the thread's 4*CH lattice points live in registers.
+// s).  The CG vectors (r, p, Ap and — unless parked — x) of the thread's 4*CH lattice points live
+// in registers.
 //
 // Shared-memory layout.  Only the vectors other threads gather from are staged: pbuf (p) and
 // qbuf (a shifted copy of q = L_d p), NODE-major: buf[node * TP + t], TP = 4 * odd.  A
@@ -17,22 +18,39 @@
 // L_d^T then needs qs at the thread's own k (aligned again).  Only the thread's own node is
 // touched off-chunk: p[k+1] and qs[k-1] across the slab edge, one scalar load each.
 //
-// The thread's rows of the ELL tables (neighbour row offsets + weights, time-invariant) sit in
-// registers; the in-list (the transpose that replaces the reference's scatter_add) sits in
-// shared memory as a per-warp, step-major ELL of (row offset, weight) pairs, read conflict-free.
-// Node numbering, the visit order of a row's neighbours and of its in-list are chosen at plan
-// time (mga_schedule.cpp) so that quarter-warps hit distinct bank groups.  The seven ADMM state vectors are parked between
-// solves in shared memory when they fit, else in a per-CTA L2-resident scratch.  HBM traffic
-// per window is y in, x out (+ optional iterates / diagnostics).
+// Tables.  The thread's rows of the ELL tables (neighbour row offsets + weights, time-invariant)
+// sit in registers (MGA_RES_TAB_SMEM=0) or in shared memory slot-major, one conflict-free 64-bit
+// load per neighbour (MGA_RES_TAB_SMEM=1: 26 registers fewer, which is what lets two CTAs share an
+// SM).  The in-list (the transpose that replaces the reference's scatter_add) sits in shared memory
+// as a per-warp, step-major ELL of (row offset, weight) pairs, read conflict-free.  Node numbering,
+// the visit order of a row's neighbours and of its in-list are chosen at plan time
+// (mga_schedule.cpp) so that quarter-warps hit distinct bank groups.
 //
-// A persistent grid strides over the batch; CTAs never communicate, so windows shard over
-// CTAs — and over GPUs — with no collective.
+// Registers are the scarce resource (12 lattice points per thread x {x, r, p, Ap, accumulators}):
+// the seven ADMM state vectors are parked between uses — in shared memory when that does not cost
+// residency, else in a per-CTA L2-resident scratch — and re-read where needed instead of being
+// kept live across a solve; with MGA_RES_XPARK=1 the CG iterate x is parked in a private
+// shared-memory row as well.  HBM traffic per window is y in, x out (+ optional iterates /
+// diagnostics).
+//
+// A persistent grid (CTAs/SM x SMs) takes windows from an atomic counter; CTAs never exchange
+// data, so windows shard over CTAs — and over GPUs — with no collective.
 #pragma once
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 
 #include "mga_common.cuh"
+
+#ifndef MGA_RES_TAB_SMEM
+#define MGA_RES_TAB_SMEM 0
+#endif
+#ifndef MGA_RES_XPARK
+#define MGA_RES_XPARK 0
+#endif
+#ifndef MGA_RES_MINB      // CTAs per SM the <= 320-thread instantiations are compiled for
+#define MGA_RES_MINB 1
+#endif
 
 namespace mga {
 
@@ -54,6 +72,7 @@ struct ResArgs {
   const float* y; float* x_out;
   float* out[ST_COUNT];       // optional per-window outputs (index by ST_*; ST_X unused)
   float* scratch;             // gridDim.x * ST_COUNT * T * N floats when !state_in_smem
+  int* next_window;           // zeroed per launch: windows beyond the first gridDim.x are handed out dynamically
   double* diag; double* dx_sum;
   float* alpha; float* beta;
   float rho, rho_u, rho_d, thr;
@@ -64,18 +83,26 @@ struct ResArgs {
 template <int CH, int K>
 struct Ctx {
   static constexpr int TS = 4 * CH;
-  int i, t0, T, t_in, TP;
-  bool active;
+  int t0, T, t_in;
   bool has_next, has_prev;   // another slab of this node owns t0+TS / t0-1
   int own;                   // i * TP + t0
+#if MGA_RES_TAB_SMEM
+  const int2* tabd;          // this lane's temporal-table column: K entries, stride NT: (nbr * TP + t0, weight bits)
+  const int2* tabu;          // spatial table, K-1 entries
+  int NT;
+#else
   int nd[K];                 // neighbour row offset + t0 (zero row for -1)
   float wd[K];
   int nu[K - 1];
   float wu[K - 1];
+#endif
   int steps;                 // in-list steps of this thread's warp (padded with zero-weight entries)
   float* pbuf;
   float* qbuf;
-  const int2* ent;           // this lane's first in-list entry; stride 32: (src * TP + t0, weight bits)
+#if MGA_RES_XPARK
+  float* xrow;               // private parking row of the CG iterate
+#endif
+  const int2* ent;           // this lane's first in-list entry; stride 32: (src * TP, weight bits)
   float* red;                // 2 x 32
   int red_sel;
 
@@ -94,6 +121,13 @@ struct Ctx {
     for (int c = 0; c < CH; ++c)
       *reinterpret_cast<float4*>(buf + own + 4 * c) = make_float4(v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
   }
+  __device__ __forceinline__ void get(const float* buf, float (&v)[TS]) const {
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      const float4 g = *reinterpret_cast<const float4*>(buf + own + 4 * c);
+      v[4 * c] = g.x; v[4 * c + 1] = g.y; v[4 * c + 2] = g.z; v[4 * c + 3] = g.w;
+    }
+  }
 
   // acc[k] += w * buf[off + k], k = 0..TS-1, as CH aligned 128-bit loads
   __device__ __forceinline__ void gather_acc(const float* buf, int off, float w, float (&acc)[TS]) const {
@@ -107,19 +141,40 @@ struct Ctx {
     }
   }
 
+  // acc += sum_j w_j * buf[nbr_j] over the temporal (kd slots) / spatial (ku slots) forward table
+  __device__ __forceinline__ void fwd_d(const float* buf, float (&acc)[TS]) const {
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+#if MGA_RES_TAB_SMEM
+      const int2 en = tabd[j * NT];
+      gather_acc(buf, en.x, __int_as_float(en.y), acc);
+#else
+      gather_acc(buf, nd[j], wd[j], acc);
+#endif
+    }
+  }
+  __device__ __forceinline__ void fwd_u(const float* buf, float (&acc)[TS]) const {
+#pragma unroll
+    for (int j = 0; j < K - 1; ++j) {
+#if MGA_RES_TAB_SMEM
+      const int2 en = tabu[j * NT];
+      gather_acc(buf, en.x, __int_as_float(en.y), acc);
+#else
+      gather_acc(buf, nu[j], wu[j], acc);
+#endif
+    }
+  }
+
   // qs[k] = q[t0+k+1] where q = L_d v (ADMM.py:166-177), v already in pbuf (synced).
-  // With first_row_zero the caller wants plain "v shifted by one" (used for Ldr_T of a vector).
   __device__ __forceinline__ void shifted_ldr(const float (&v)[TS], float (&qs)[TS]) const {
-    float acc[TS];
 #pragma unroll
-    for (int k = 0; k < TS; ++k) acc[k] = 0.f;
-#pragma unroll
-    for (int j = 0; j < K; ++j) gather_acc(pbuf, nd[j], wd[j], acc);
+    for (int k = 0; k < TS; ++k) qs[k] = 0.f;
+    fwd_d(pbuf, qs);
     const float vnext = has_next ? pbuf[own + TS] : 0.f;
 #pragma unroll
     for (int k = 0; k < TS; ++k) {
       const float up = (k < TS - 1) ? v[k + 1] : vnext;
-      qs[k] = (t0 + k + 1 < T) ? up - acc[k] : 0.f;
+      qs[k] = (t0 + k + 1 < T) ? up - qs[k] : 0.f;
     }
   }
 
@@ -145,17 +200,20 @@ struct Ctx {
   __device__ __forceinline__ void apply_cldr(const float (&v)[TS], float (&out)[TS], float a, float c) {
     put(pbuf, v);
     __syncthreads();
-    float qs[TS];
-    shifted_ldr(v, qs);
-    put(qbuf, qs);
+    {
+      float qs[TS];
+      shifted_ldr(v, qs);
+      put(qbuf, qs);
+    }
     __syncthreads();
-    float f[TS];
-    father_sum(qbuf, f);
+    father_sum(qbuf, out);                                   // out = f
     const float qprev = has_prev ? qbuf[own - 1] : 0.f;      // q[t0]; q[0] = 0 (ADMM.py:176)
+    float qs[TS];
+    get(qbuf, qs);     // the own row is re-read instead of kept live across the in-list gather
 #pragma unroll
     for (int k = 0; k < TS; ++k) {
       const float q = (k == 0) ? qprev : qs[k - 1];
-      const float l = q - f[k];      // row T-1: f = 0 because qs[T-1] = 0; Q1 is moot as q[0] = 0
+      const float l = q - out[k];    // row T-1: f = 0 because qs[T-1] = 0; Q1 is moot as q[0] = 0
       if (XSYS) out[k] = ((t0 + k < t_in ? v[k] : 0.f) + a * v[k]) + c * l;
       else out[k] = c * l + a * v[k];
     }
@@ -165,13 +223,11 @@ struct Ctx {
   __device__ __forceinline__ void apply_lu(const float (&v)[TS], float (&out)[TS], float a, float c) {
     put(pbuf, v);
     __syncthreads();
-    float acc[TS];
 #pragma unroll
-    for (int k = 0; k < TS; ++k) acc[k] = 0.f;
+    for (int k = 0; k < TS; ++k) out[k] = 0.f;
+    fwd_u(pbuf, out);
 #pragma unroll
-    for (int j = 0; j < K - 1; ++j) gather_acc(pbuf, nu[j], wu[j], acc);
-#pragma unroll
-    for (int k = 0; k < TS; ++k) out[k] = c * (v[k] - acc[k]) + a * v[k];
+    for (int k = 0; k < TS; ++k) out[k] = c * (v[k] - out[k]) + a * v[k];
   }
 
   template <int SYS>
@@ -182,12 +238,16 @@ struct Ctx {
   }
 
   // CG_solver, fixed iteration count (ADMM.py:329-368 with an unreachable tolerance; the
-  // arithmetic is unguarded like the reference's, quirk Q10).  r holds the right-hand side on entry.
+  // arithmetic is unguarded like the reference's, quirk Q10).  r holds the right-hand side on
+  // entry, x the warm start; x holds the solution on exit.
   template <int SYS>
   __device__ __forceinline__ void cg(float (&x)[TS], float (&r)[TS], float a, float c, int n_cg, float* alpha_out,
                                      float* beta_out, int64_t B) {
     float p[TS], ap[TS];
     apply<SYS>(x, ap, a, c);
+#if MGA_RES_XPARK
+    put(xrow - own, x);     // xrow is this thread's row; put() adds `own`
+#endif
     float loc = 0.f;
 #pragma unroll
     for (int k = 0; k < TS; ++k) {
@@ -203,9 +263,20 @@ struct Ctx {
       for (int k = 0; k < TS; ++k) loc += p[k] * ap[k];
       const float alpha = rr / bsum(loc);
       loc = 0.f;
+#if MGA_RES_XPARK
+#pragma unroll
+      for (int cc = 0; cc < CH; ++cc) {
+        float4 g = *reinterpret_cast<float4*>(xrow + 4 * cc);
+        g.x = g.x + alpha * p[4 * cc]; g.y = g.y + alpha * p[4 * cc + 1];
+        g.z = g.z + alpha * p[4 * cc + 2]; g.w = g.w + alpha * p[4 * cc + 3];
+        *reinterpret_cast<float4*>(xrow + 4 * cc) = g;
+      }
+#endif
 #pragma unroll
       for (int k = 0; k < TS; ++k) {
+#if !MGA_RES_XPARK
         x[k] = x[k] + alpha * p[k];
+#endif
         r[k] = r[k] - alpha * ap[k];
         loc += r[k] * r[k];
       }
@@ -219,6 +290,9 @@ struct Ctx {
 #pragma unroll
       for (int k = 0; k < TS; ++k) p[k] = r[k] + beta * p[k];
     }
+#if MGA_RES_XPARK
+    get(xrow - own, x);
+#endif
   }
 };
 
@@ -228,44 +302,68 @@ __device__ __forceinline__ float soft_thr(float s, float d) {
   return sg * u * (float)(u > 0.f);   // ADMM.py:407-408
 }
 
-template <int CH, int K, int MAXT>
-__global__ void __launch_bounds__(MAXT, 1) k_admm_resident(const ResArgs a) {
+template <int CH, int K, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) k_admm_resident(const ResArgs a) {
   constexpr int TS = 4 * CH;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int N = a.N, T = a.T, TP = a.TP, t_in = a.t_in;
   const int rows = (N + 1) * TP;
   float* pbuf = reinterpret_cast<float*>(smem_raw);
   float* qbuf = pbuf + rows;
-  float* red = qbuf + rows;                         // 64 floats
-  float* dred = red + 64;                           // MGA_DIAG_COLS x 32 floats
+  float* red = qbuf + rows;                         // 64 floats + the next-window slot (68 with padding)
+  float* dred = red + 68;                           // MGA_DIAG_COLS x 32 floats
   int2* ent = reinterpret_cast<int2*>(dred + MGA_DIAG_COLS * 32);
-  float* st_smem = reinterpret_cast<float*>(ent + a.ell_total);
+  float* nxt = reinterpret_cast<float*>(ent + a.ell_total);
+#if MGA_RES_TAB_SMEM
+  int2* tabd = reinterpret_cast<int2*>(nxt);        // K x (S * NT), slot-major, one column per thread
+  int2* tabu = tabd + K * a.S * a.NT;               // (K-1) x (S * NT)
+  nxt = reinterpret_cast<float*>(tabu + (K - 1) * a.S * a.NT);
+#endif
+#if MGA_RES_XPARK
+  float* xbuf = nxt;                                // (N + 1) x TP
+  nxt += rows;
+#endif
+  float* st_smem = nxt;
   const int s = threadIdx.x / a.NT;
   const int i = threadIdx.x - s * a.NT;
   const bool active = i < N;
   const int t0 = s * TS;
 
   Ctx<CH, K> c;
-  c.i = i; c.t0 = t0; c.T = T; c.t_in = t_in; c.TP = TP; c.active = active;
+  c.t0 = t0; c.T = T; c.t_in = t_in;
   c.has_next = (s + 1 < a.S);
   c.has_prev = (s > 0);
   c.own = (active ? i : N) * TP + t0;     // inactive lanes park on the zero row (they only ever write zeros)
   c.pbuf = pbuf; c.qbuf = qbuf; c.red = red; c.red_sel = 0;
+#if MGA_RES_XPARK
+  c.xrow = xbuf + c.own;
+#endif
+#if MGA_RES_TAB_SMEM
+  c.NT = a.S * a.NT; c.tabd = tabd + threadIdx.x; c.tabu = tabu + threadIdx.x;
+#endif
 #pragma unroll
   for (int j = 0; j < K; ++j) {
     int nb = N;
     float w = 0.f;
     if (active && j < a.kd) { nb = a.nbr_d[i * a.kd + j]; w = a.d_w[i * a.kd + j]; }
+#if MGA_RES_TAB_SMEM
+    tabd[j * c.NT + threadIdx.x] = make_int2(nb * TP + t0, __float_as_int(w));
+#else
     c.nd[j] = nb * TP + t0;
     c.wd[j] = w;
+#endif
   }
 #pragma unroll
   for (int j = 0; j < K - 1; ++j) {
     int nb = N;
     float w = 0.f;
     if (active && j < a.ku) { nb = a.nbr_u[i * a.ku + j]; w = a.u_w[i * a.ku + j]; }
+#if MGA_RES_TAB_SMEM
+    tabu[j * c.NT + threadIdx.x] = make_int2(nb * TP + t0, __float_as_int(w));
+#else
     c.nu[j] = nb * TP + t0;
     c.wu[j] = w;
+#endif
   }
   {
     const int wn = i >> 5;     // warp of this node row (the same for every slab)
@@ -279,6 +377,9 @@ __global__ void __launch_bounds__(MAXT, 1) k_admm_resident(const ResArgs a) {
   }
   const int orig = active ? a.perm[i] : 0;   // this thread's node in the caller's numbering
   for (int k = threadIdx.x; k < 2 * rows; k += blockDim.x) pbuf[k] = 0.f;
+#if MGA_RES_XPARK
+  for (int k = threadIdx.x; k < rows; k += blockDim.x) xbuf[k] = 0.f;
+#endif
   __syncthreads();
 
   // ---- parked ADMM state: smem [v][node*TP + t] (128-bit) or global scratch [v][t][node] (coalesced)
@@ -310,12 +411,22 @@ __global__ void __launch_bounds__(MAXT, 1) k_admm_resident(const ResArgs a) {
         if (t0 + k < T) gstate[((size_t)v * T + t0 + k) * N + i] = o[k];
     }
   };
+  // per-thread partial of one diagnostics column: reduced over the warp at once and left in
+  // dred[col][warp] until the end of the outer iteration, so no column stays live in registers
+  const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+  auto diag_put = [&](int col, float v) {
+    v = warp_sum<float>(v);
+    if (lane == 0) dred[col * 32 + wp] = v;
+  };
 
-  for (int64_t b = blockIdx.x; b < a.B; b += gridDim.x) {
+  // Windows are handed out dynamically (one atomic per window): CTAs that share an SM with fewer
+  // neighbours near the end of the batch run faster and pick up more of the tail.
+  int& s_next = *reinterpret_cast<int*>(red + 64);
+  for (int64_t b = blockIdx.x; b < a.B;) {
     const float* yw = a.y + (size_t)b * t_in * N + orig;
-    float x[TS];
     // ---- initial_guess (ADMM.py:766-781) and initial state (ADMM.py:537-544)
     {
+      float x[TS];
       float sy = 0.f, sty = 0.f;
       for (int t = 0; t < t_in; ++t) {
         const float v = active ? yw[(size_t)t * N] : 0.f;
@@ -325,210 +436,267 @@ __global__ void __launch_bounds__(MAXT, 1) k_admm_resident(const ResArgs a) {
       const float my = sy / (float)t_in, mty = sty / (float)t_in;
       const float w = (mty - a.t_mean * my) / a.t_var;
       const float cc = my - w * a.t_mean;
-      float tenth[TS];
+      {
+        float tenth[TS];
 #pragma unroll
-      for (int k = 0; k < TS; ++k) {
-        const int t = t0 + k;
-        float v = 0.f;
-        if (active && t < T) v = t < t_in ? yw[(size_t)t * N] : w * (float)t + cc;
-        x[k] = v;
-        tenth[k] = (active && t < T) ? 0.1f : 0.f;
+        for (int k = 0; k < TS; ++k) {
+          const int t = t0 + k;
+          float v = 0.f;
+          if (active && t < T) v = t < t_in ? yw[(size_t)t * N] : w * (float)t + cc;
+          x[k] = v;
+          tenth[k] = (active && t < T) ? 0.1f : 0.f;
+        }
+        st_state(ST_GU, tenth); st_state(ST_GD, tenth); st_state(ST_GAM, tenth);
       }
       st_state(ST_X, x); st_state(ST_ZU, x); st_state(ST_ZD, x);
-      st_state(ST_GU, tenth); st_state(ST_GD, tenth); st_state(ST_GAM, tenth);
       // phi = L_d x  (ADMM.py:541)
       c.put(pbuf, x);
       __syncthreads();
-      float qs[TS], q[TS];
+      float qs[TS];
       c.shifted_ldr(x, qs);
       c.put(qbuf, qs);
       __syncthreads();
       const float qprev = c.has_prev ? qbuf[c.own - 1] : 0.f;
 #pragma unroll
-      for (int k = 0; k < TS; ++k) q[k] = (k == 0) ? qprev : qs[k - 1];
-      st_state(ST_PHI, q);
+      for (int k = 0; k < TS; ++k) x[k] = (k == 0) ? qprev : qs[k - 1];
+      st_state(ST_PHI, x);
       __syncthreads();
     }
 
     for (int it = 0; it < a.n_outer; ++it) {
-      float dg[MGA_DIAG_COLS];
-#pragma unroll
-      for (int k = 0; k < MGA_DIAG_COLS; ++k) dg[k] = 0.f;
       float* al = a.alpha ? a.alpha + ((size_t)it * 3) * a.n_cg * a.B + b : nullptr;
       float* be = a.beta ? a.beta + ((size_t)it * 3) * a.n_cg * a.B + b : nullptr;
       const size_t sys_stride = (size_t)a.n_cg * a.B;
       float r[TS];
       // ---- RHS_x (ADMM.py:552-559): Ldr_T(gamma + rho phi)/2 + (rho_u zu + rho_d zd)/2 - (gu+gd)/2 + H^T y
       {
-        float v[TS], vs[TS], f[TS], tmp[TS];
-        ld_state(ST_GAM, v);
-        ld_state(ST_PHI, tmp);
+        float v[TS], f[TS];
+        {
+          float tmp[TS];
+          ld_state(ST_GAM, v);
+          ld_state(ST_PHI, tmp);
 #pragma unroll
-        for (int k = 0; k < TS; ++k) v[k] = v[k] + a.rho * tmp[k];
+          for (int k = 0; k < TS; ++k) v[k] = v[k] + a.rho * tmp[k];
+        }
         c.put(pbuf, v);
         __syncthreads();
-        const float vnext = c.has_next ? pbuf[c.own + TS] : 0.f;
+        {
+          float vs[TS];
+          const float vnext = c.has_next ? pbuf[c.own + TS] : 0.f;
 #pragma unroll
-        for (int k = 0; k < TS; ++k) vs[k] = (t0 + k + 1 < T) ? ((k < TS - 1) ? v[k + 1] : vnext) : 0.f;
-        c.put(qbuf, vs);
+          for (int k = 0; k < TS; ++k) vs[k] = (t0 + k + 1 < T) ? ((k < TS - 1) ? v[k + 1] : vnext) : 0.f;
+          c.put(qbuf, vs);
+        }
         __syncthreads();
         c.father_sum(qbuf, f);
-        float zu[TS], zd[TS], gu[TS], gd[TS];
-        ld_state(ST_ZU, zu); ld_state(ST_ZD, zd); ld_state(ST_GU, gu); ld_state(ST_GD, gd);
 #pragma unroll
         for (int k = 0; k < TS; ++k) {
           const int t = t0 + k;
           // rows of apply_op_Ldr_T: t = T-1 keeps v; t = 0 keeps the identity term only under Q1
-          const float l = (t == T - 1) ? v[k] : ((t == 0 && !a.q1) ? -f[k] : v[k] - f[k]);
+          r[k] = (t == T - 1) ? v[k] : ((t == 0 && !a.q1) ? -f[k] : v[k] - f[k]);
+        }
+        ld_state(ST_ZU, v); ld_state(ST_ZD, f);
+#pragma unroll
+        for (int k = 0; k < TS; ++k) v[k] = (a.rho_u * v[k] + a.rho_d * f[k]) / 2.f;
+#pragma unroll
+        for (int k = 0; k < TS; ++k) r[k] = r[k] / 2.f + v[k];
+        ld_state(ST_GU, v); ld_state(ST_GD, f);
+#pragma unroll
+        for (int k = 0; k < TS; ++k) {
+          const int t = t0 + k;
           float o = 0.f;
           if (active && t < T) {
             const float hty = t < t_in ? yw[(size_t)t * N] : 0.f;
-            o = l / 2.f + (a.rho_u * zu[k] + a.rho_d * zd[k]) / 2.f - (gu[k] + gd[k]) / 2.f + hty;
+            o = r[k] - (v[k] + f[k]) / 2.f + hty;
           }
           r[k] = o;
         }
       }
-      // ---- x solve (ADMM.py:571); x registers hold x_old
-      c.template cg<MGA_SYS_X>(x, r, a.ax, a.cx, a.n_cg, al, be, a.B);
+      // ---- x solve (ADMM.py:571), warm start x_old
       {
-        float xo[TS];
-        ld_state(ST_X, xo);
+        float x[TS];
+        ld_state(ST_X, x);
+        c.template cg<MGA_SYS_X>(x, r, a.ax, a.cx, a.n_cg, al, be, a.B);
         if (a.want_diag) {
+          float xo[TS];
+          ld_state(ST_X, xo);
+          float s2 = 0.f;
 #pragma unroll
           for (int k = 0; k < TS; ++k) {
             if (active && t0 + k < T) {
               const float dx = x[k] - xo[k];
-              dg[MGA_DIAG_DX2] += dx * dx;
+              s2 += dx * dx;
               if (a.dx_sum) atomicAdd(a.dx_sum + ((size_t)it * T + t0 + k) * N + orig, (double)dx);
             }
           }
+          diag_put(MGA_DIAG_DX2, s2);
         }
         st_state(ST_X, x);
+        // right-hand side of the z_u system (ADMM.py:579)
+        ld_state(ST_GU, r);
+#pragma unroll
+        for (int k = 0; k < TS; ++k) r[k] = r[k] / 2.f + a.azu * x[k];
       }
       // ---- z_u solve (ADMM.py:579-580) + its dual ascent (ADMM.py:595)
       {
-        float z[TS], zo[TS], g[TS];
+        float z[TS];
         ld_state(ST_ZU, z);
-        ld_state(ST_GU, g);
-#pragma unroll
-        for (int k = 0; k < TS; ++k) { zo[k] = z[k]; r[k] = g[k] / 2.f + a.azu * x[k]; }
         c.template cg<MGA_SYS_ZU>(z, r, a.azu, a.czu, a.n_cg, al ? al + sys_stride : nullptr,
                                   be ? be + sys_stride : nullptr, a.B);
+        float x[TS], g[TS];
+        ld_state(ST_X, x);
+        ld_state(ST_GU, g);
+        float s0 = 0.f, s1 = 0.f;
+        {
+          float zo[TS];
+          ld_state(ST_ZU, zo);
 #pragma unroll
-        for (int k = 0; k < TS; ++k) {
-          const float d0 = x[k] - z[k], d1 = z[k] - zo[k];
-          dg[MGA_DIAG_X_ZU2] += d0 * d0;
-          dg[MGA_DIAG_DZU2] += d1 * d1;
-          g[k] = g[k] + a.rho_u * d0;
+          for (int k = 0; k < TS; ++k) {
+            const float d0 = x[k] - z[k], d1 = z[k] - zo[k];
+            s0 += d0 * d0;
+            s1 += d1 * d1;
+            g[k] = g[k] + a.rho_u * d0;
+          }
         }
         st_state(ST_GU, g);
         st_state(ST_ZU, z);
+        if (a.want_diag) { diag_put(MGA_DIAG_X_ZU2, s0); diag_put(MGA_DIAG_DZU2, s1); }
+        // right-hand side of the z_d system (ADMM.py:587)
+        ld_state(ST_GD, r);
+#pragma unroll
+        for (int k = 0; k < TS; ++k) r[k] = r[k] / 2.f + a.azd * x[k];
       }
       // ---- z_d solve (ADMM.py:587-588) + its dual ascent (ADMM.py:597)
       {
-        float z[TS], zo[TS], g[TS];
+        float z[TS];
         ld_state(ST_ZD, z);
-        ld_state(ST_GD, g);
-#pragma unroll
-        for (int k = 0; k < TS; ++k) { zo[k] = z[k]; r[k] = g[k] / 2.f + a.azd * x[k]; }
         c.template cg<MGA_SYS_ZD>(z, r, a.azd, a.czd, a.n_cg, al ? al + 2 * sys_stride : nullptr,
                                   be ? be + 2 * sys_stride : nullptr, a.B);
+        float x[TS], g[TS];
+        ld_state(ST_X, x);
+        ld_state(ST_GD, g);
+        float s0 = 0.f, s1 = 0.f;
+        {
+          float zo[TS];
+          ld_state(ST_ZD, zo);
 #pragma unroll
-        for (int k = 0; k < TS; ++k) {
-          const float d0 = x[k] - z[k], d1 = z[k] - zo[k];
-          dg[MGA_DIAG_X_ZD2] += d0 * d0;
-          dg[MGA_DIAG_DZD2] += d1 * d1;
-          g[k] = g[k] + a.rho_d * d0;
+          for (int k = 0; k < TS; ++k) {
+            const float d0 = x[k] - z[k], d1 = z[k] - zo[k];
+            s0 += d0 * d0;
+            s1 += d1 * d1;
+            g[k] = g[k] + a.rho_d * d0;
+          }
         }
         st_state(ST_GD, g);
         st_state(ST_ZD, z);
+        if (a.want_diag) { diag_put(MGA_DIAG_X_ZD2, s0); diag_put(MGA_DIAG_DZD2, s1); }
       }
       // ---- phi prox + gamma ascent (ADMM.py:600-605) and the remaining diagnostics (ADMM.py:612-637)
       {
+        float x[TS], qs[TS];
+        ld_state(ST_X, x);
         c.put(pbuf, x);
         __syncthreads();
-        float qs[TS];
         c.shifted_ldr(x, qs);
         c.put(qbuf, qs);
         __syncthreads();
-        const float qprev = c.has_prev ? qbuf[c.own - 1] : 0.f;
-        float gam[TS], phi[TS], lux[TS];
-        ld_state(ST_GAM, gam);
-        ld_state(ST_PHI, phi);
-        if (a.want_diag) {
+        if (a.want_diag) {     // GLR = x . L_u x, recover = ||Hx - y||^2
+          float lux[TS];
 #pragma unroll
           for (int k = 0; k < TS; ++k) lux[k] = 0.f;
+          c.fwd_u(pbuf, lux);
+          float sg = 0.f, sr = 0.f;
 #pragma unroll
-          for (int j = 0; j < K - 1; ++j) c.gather_acc(pbuf, c.nu[j], c.wu[j], lux);
+          for (int k = 0; k < TS; ++k) {
+            const int t = t0 + k;
+            if (active && t < T) {
+              sg += x[k] * (x[k] - lux[k]);
+              if (t < t_in) {
+                const float h = x[k] - yw[(size_t)t * N];
+                sr += h * h;
+              }
+            }
+          }
+          diag_put(MGA_DIAG_GLR, sg);
+          diag_put(MGA_DIAG_RECOVER2, sr);
         }
         int bad = 0;
 #pragma unroll
+        for (int k = 0; k < TS; ++k) bad |= !isfinite(x[k]);
+        // x is dead from here: reuse its registers for (L_d x), gamma and phi
+        const float qprev = c.has_prev ? qbuf[c.own - 1] : 0.f;
+#pragma unroll
+        for (int k = TS - 1; k > 0; --k) qs[k] = qs[k - 1];        // qs[k] = (L_d x)[t0 + k]
+        qs[0] = qprev;
+        float gam[TS], phi[TS];
+        ld_state(ST_GAM, gam);
+        ld_state(ST_PHI, phi);
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
         for (int k = 0; k < TS; ++k) {
           const int t = t0 + k;
-          const float q = (k == 0) ? qprev : qs[k - 1];           // (L_d x)[t]
+          const float q = qs[k];
           const float ph = soft_thr(q - gam[k] / a.rho, a.thr);
           const float gn = gam[k] + a.rho * (ph - q);
           if (active && t < T) {
-            bad |= !isfinite(x[k]) || !isfinite(ph) || !isfinite(gn);
-            if (a.want_diag) {
-              const float e = ph - q, f = ph - phi[k];
-              dg[MGA_DIAG_PHI_LDX2] += e * e;
-              dg[MGA_DIAG_DPHI2] += f * f;
-              dg[MGA_DIAG_DGTV] += fabsf(q);
-              dg[MGA_DIAG_DGLR] += q * q;
-              if (t < t_in) {
-                const float h = x[k] - yw[(size_t)t * N];
-                dg[MGA_DIAG_RECOVER2] += h * h;
-              }
-              dg[MGA_DIAG_GLR] += x[k] * (x[k] - lux[k]);
-            }
+            bad |= !isfinite(ph) || !isfinite(gn);
+            const float e = ph - q, f = ph - phi[k];
+            s0 += e * e;
+            s1 += f * f;
+            s2 += fabsf(q);
+            s3 += q * q;
             phi[k] = ph;
             gam[k] = gn;
           }
         }
         st_state(ST_PHI, phi);
         st_state(ST_GAM, gam);
-        dg[MGA_DIAG_NONFINITE] = (float)bad;
-        // one-sync multi-column block reduction
-        const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
-#pragma unroll
-        for (int k = 0; k < MGA_DIAG_COLS; ++k) {
-          const float v = warp_sum<float>(dg[k]);
-          if (lane == 0) dred[k * 32 + wp] = v;
+        if (a.want_diag) {
+          diag_put(MGA_DIAG_PHI_LDX2, s0);
+          diag_put(MGA_DIAG_DPHI2, s1);
+          diag_put(MGA_DIAG_DGTV, s2);
+          diag_put(MGA_DIAG_DGLR, s3);
+          diag_put(MGA_DIAG_NONFINITE, (float)bad);
         }
         __syncthreads();
-        if (threadIdx.x < MGA_DIAG_COLS && a.diag) {
+        if (a.want_diag && threadIdx.x < MGA_DIAG_COLS && a.diag) {
+          const int nw = (blockDim.x + 31) >> 5;
           float tot = 0.f;
           for (int k = 0; k < nw; ++k) tot += dred[threadIdx.x * 32 + k];
           if (tot != 0.f) atomicAdd(a.diag + (size_t)it * MGA_DIAG_COLS + threadIdx.x, (double)tot);
         }
-        __syncthreads();
+        // the next writer of dred / pbuf is separated from these reads by the barriers of the next solve
       }
     }
     // ---- results
-    if (active) {
+    {
+      float o[TS];
+      ld_state(ST_X, o);
+      if (active) {
 #pragma unroll
-      for (int k = 0; k < TS; ++k)
-        if (t0 + k < T) a.x_out[((size_t)b * T + t0 + k) * N + orig] = x[k];
-    }
-    for (int v = ST_ZU; v < ST_COUNT; ++v) {
-      if (a.out[v]) {
-        float o[TS];
-        ld_state(v, o);
-        if (active) {
+        for (int k = 0; k < TS; ++k)
+          if (t0 + k < T) a.x_out[((size_t)b * T + t0 + k) * N + orig] = o[k];
+      }
+      for (int v = ST_ZU; v < ST_COUNT; ++v) {
+        if (a.out[v]) {
+          ld_state(v, o);
+          if (active) {
 #pragma unroll
-          for (int k = 0; k < TS; ++k)
-            if (t0 + k < T) a.out[v][((size_t)b * T + t0 + k) * N + orig] = o[k];
+            for (int k = 0; k < TS; ++k)
+              if (t0 + k < T) a.out[v][((size_t)b * T + t0 + k) * N + orig] = o[k];
+          }
         }
       }
     }
+    if (threadIdx.x == 0) s_next = atomicAdd(a.next_window, 1);
     __syncthreads();
+    b = (int64_t)gridDim.x + s_next;
   }
 }
 
 // ---- launch geometry --------------------------------------------------------------------------
 struct ResGeom {
-  int CH, S, NT, TP, threads;
+  int CH, S, NT, TP, threads, Kt;
   size_t core_bytes, state_bytes;
 };
 
@@ -542,6 +710,8 @@ inline int res_tp(int min_len) {          // smallest 4 * odd >= min_len
 // in-list entries are then read once per 12 time steps; measured 252k vs 210k windows/s against
 // CH = 1 at PEMS04 shape on B200); MGA_RES_CH overrides for experiments.
 inline bool res_geometry(const GraphDev& g, int ell_total, int force_ch, ResGeom* out) {
+  const int kk = std::max(g.kd, g.ku + 1);
+  const int Kt = kk <= 5 ? 5 : (kk <= 7 ? 7 : 9);     // the K of the kernel instantiation
   const int NT = ((g.N + 31) / 32) * 32;
   const int chunks = (g.T + 3) / 4;
   for (int ch = std::min(3, chunks); ch >= 1; --ch) {
@@ -551,7 +721,15 @@ inline bool res_geometry(const GraphDev& g, int ell_total, int force_ch, ResGeom
     ResGeom r;
     r.CH = ch; r.S = S; r.NT = NT; r.threads = S * NT;
     r.TP = res_tp(S * 4 * ch);
-    r.core_bytes = (size_t)2 * (g.N + 1) * r.TP * 4 + 64 * 4 + MGA_DIAG_COLS * 32 * 4 + (size_t)ell_total * 8;
+    r.Kt = Kt;
+    const size_t rows = (size_t)(g.N + 1) * r.TP;
+    r.core_bytes = 2 * rows * 4 + 68 * 4 + MGA_DIAG_COLS * 32 * 4 + (size_t)ell_total * 8;
+#if MGA_RES_TAB_SMEM
+    r.core_bytes += (size_t)(2 * Kt - 1) * r.threads * 8;
+#endif
+#if MGA_RES_XPARK
+    r.core_bytes += rows * 4;
+#endif
     r.state_bytes = (size_t)ST_COUNT * g.N * r.TP * 4;
     *out = r;
     return true;
@@ -564,10 +742,10 @@ inline int res_forced_ch() {
   return e ? std::atoi(e) : 0;
 }
 
-template <int CH, int K, int MAXT>
+template <int CH, int K, int MAXT, int MINB>
 inline int launch_res(mga_plan* p, ResArgs& a, const ResGeom& geo, cudaStream_t st) {
   const GraphDev& g = p->g;
-  auto kern = k_admm_resident<CH, K, MAXT>;
+  auto kern = k_admm_resident<CH, K, MAXT, MINB>;
   const size_t core = geo.core_bytes;
   const size_t with_state = core + geo.state_bytes;
   // State in shared memory only if it does not cost residency: compare CTAs/SM both ways.
@@ -587,6 +765,11 @@ inline int launch_res(mga_plan* p, ResArgs& a, const ResGeom& geo, cudaStream_t 
     if (rc) return rc;
     a.scratch = static_cast<float*>(p->ws.base);
   }
+  a.next_window = p->r_counters + (p->r_counter_next++ % mga_plan::kCounters) * 32;
+  MGA_CUDA(cudaMemsetAsync(a.next_window, 0, sizeof(int), st));
+  if (std::getenv("MGA_RES_VERBOSE"))
+    std::fprintf(stderr, "[mga] resident<%d,%d,%d,%d>: threads %d, smem %zu B (state %s), %d CTA/SM, grid %lld\n", CH, K,
+                 MAXT, MINB, geo.threads, smem, a.state_in_smem ? "smem" : "L2 scratch", occ, (long long)grid);
   kern<<<(unsigned)grid, geo.threads, smem, st>>>(a);
   MGA_LAUNCH_CHECK("k_admm_resident");
   return MGA_OK;
@@ -594,8 +777,10 @@ inline int launch_res(mga_plan* p, ResArgs& a, const ResGeom& geo, cudaStream_t 
 
 template <int CH, int K>
 inline int pick_threads(mga_plan* p, ResArgs& a, const ResGeom& geo, cudaStream_t st) {
-  if (geo.threads <= 512) return launch_res<CH, K, 512>(p, a, geo, st);
-  return launch_res<CH, K, 1024>(p, a, geo, st);
+  if (geo.threads <= 192) return launch_res<CH, K, 192, (MGA_RES_MINB > 1 ? 3 : 1)>(p, a, geo, st);
+  if (geo.threads <= 320) return launch_res<CH, K, 320, MGA_RES_MINB>(p, a, geo, st);
+  if (geo.threads <= 512) return launch_res<CH, K, 512, 1>(p, a, geo, st);
+  return launch_res<CH, K, 1024, 1>(p, a, geo, st);
 }
 
 }  // namespace mga
