@@ -205,8 +205,10 @@ int mga_knn_build(int32_t n_nodes, int64_t n_edges, const int64_t* edges, const 
 
 /* ---- host-only self-check of the resident kernel's plan-time schedule (no GPU needed): verifies
  * that the internal node order, the per-row visit order and the per-warp in-list ELL are a pure
- * re-ordering of `desc`.  stats (4 doubles, may be NULL): average shared-memory wavefronts per
- * quarter-warp gather phase {forward table before, after, in-list before, after} scheduling. */
+ * re-ordering of `desc` (self links of the temporal table are held apart as one weight per node).
+ * stats (6 doubles, may be NULL): average shared-memory wavefronts per quarter-warp gather phase
+ * {forward table before, after, in-list before, after} scheduling, then the in-list steps summed
+ * over the warps {before, after}. */
 int mga_schedule_selfcheck(const mga_graph_desc* desc, double* stats);
 
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */

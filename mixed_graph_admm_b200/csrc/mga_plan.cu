@@ -242,6 +242,8 @@ int mga_plan_create(const mga_graph_desc* d, int device, mga_plan** out) {
       std::memcpy(&ent[2 * k + 1], &sc.ell_w[k], sizeof(float));
     }
     p->r_ell_total = (int)sc.ell_node.size();
+    p->r_kd = sc.kd; p->r_ku = sc.ku;
+    if ((rc = upload(p, sc.w_self, &p->r_w_self))) return fail(rc);
     if ((rc = upload(p, sc.perm, &p->r_perm))) return fail(rc);
     if ((rc = upload(p, sc.nbr_d, &p->r_nbr_d))) return fail(rc);
     if ((rc = upload(p, sc.w_d, &p->r_w_d))) return fail(rc);
@@ -293,33 +295,46 @@ int mga_schedule_selfcheck(const mga_graph_desc* d, double* stats) {
     std::sort(b.begin(), b.end());
     return a == b;
   };
-  // (b) forward rows: same (neighbour, weight) multiset, -1 slots became zero-weight zero-row slots
-  auto check_fwd = [&](int K, const std::vector<int>& nbr, const std::vector<float>& w, const std::vector<int>& s_n,
-                       const std::vector<float>& s_w) {
+  // (b) forward rows: same (neighbour, weight) multiset once "-1" slots (weight 0 on the zero row in
+  // the schedule) and, for the temporal table, self links (kept as w_self) are set aside
+  auto check_fwd = [&](int K, const std::vector<int>& nbr, const std::vector<float>& w, int Ks,
+                       const std::vector<int>& s_n, const std::vector<float>& s_w, bool self_out) {
     for (int p = 0; p < N; ++p) {
       const int o = sc.perm[p];
       std::vector<Ent> a, b;
+      float wself = 0.f;
       for (int j = 0; j < K; ++j) {
         const int nb = nbr[(size_t)o * K + j];
-        a.emplace_back(nb >= 0 ? nb : -1, nb >= 0 ? w[(size_t)o * K + j] : 0.f);
-        const int sn = s_n[(size_t)p * K + j];
+        if (nb < 0) continue;
+        if (self_out && nb == o) wself += w[(size_t)o * K + j];
+        else a.emplace_back(nb, w[(size_t)o * K + j]);
+      }
+      for (int j = 0; j < Ks; ++j) {
+        const int sn = s_n[(size_t)p * Ks + j];
         if (sn < 0 || sn > N) return false;
-        b.emplace_back(sn < N ? sc.perm[sn] : -1, s_w[(size_t)p * K + j]);
+        if (sn == N) { if (s_w[(size_t)p * Ks + j] != 0.f) return false; continue; }
+        b.emplace_back(sc.perm[sn], s_w[(size_t)p * Ks + j]);
       }
       if (!same_multiset(a, b)) return false;
+      if (self_out && wself != sc.w_self[p]) return false;
     }
     return true;
   };
-  if (!check_fwd(g.kd, tmp.h_nbr_d, tmp.h_d_w, sc.nbr_d, sc.w_d)) return bad("temporal table rows differ");
-  if (!check_fwd(g.ku, tmp.h_nbr_u, tmp.h_u_w, sc.nbr_u, sc.w_u)) return bad("spatial table rows differ");
-  // (c) in-list: every node's ELL column holds exactly its CSR row (+ zero-weight padding)
+  if (!check_fwd(g.kd, tmp.h_nbr_d, tmp.h_d_w, sc.kd, sc.nbr_d, sc.w_d, true)) return bad("temporal table rows differ");
+  if (!check_fwd(g.ku, tmp.h_nbr_u, tmp.h_u_w, sc.ku, sc.nbr_u, sc.w_u, false)) return bad("spatial table rows differ");
+  // (c) in-list: every node's ELL column holds exactly its CSR row minus the self link (+ zero-weight padding)
   const int n_warps = (N + 31) / 32;
   for (int p = 0; p < n_warps * 32; ++p) {
     const int w = p / 32, l = p % 32;
     std::vector<Ent> a, b;
     if (p < N) {
       const int o = sc.perm[p];
-      for (int e = tmp.h_csr_ptr[o]; e < tmp.h_csr_ptr[o + 1]; ++e) a.emplace_back(tmp.h_csr_src[e], tmp.h_csr_w[e]);
+      float wself = 0.f;
+      for (int e = tmp.h_csr_ptr[o]; e < tmp.h_csr_ptr[o + 1]; ++e) {
+        if (tmp.h_csr_src[e] == o) wself += tmp.h_csr_w[e];
+        else a.emplace_back(tmp.h_csr_src[e], tmp.h_csr_w[e]);
+      }
+      if (wself != sc.w_self[p]) return bad("in-list self link differs from the forward one");
     }
     for (int e = sc.ell_ptr[w]; e < sc.ell_ptr[w + 1]; ++e) {
       const int sn = sc.ell_node[(size_t)e * 32 + l];
@@ -352,7 +367,7 @@ int mga_schedule_selfcheck(const mga_graph_desc* d, double* stats) {
       return c ? tot / c : 1.0;
     };
     stats[0] = fwd_cost(g.kd, tmp.h_nbr_d);
-    stats[1] = fwd_cost(g.kd, sc.nbr_d);
+    stats[1] = fwd_cost(sc.kd, sc.nbr_d);
     double tot = 0, tot2 = 0; int c = 0, c2 = 0;
     for (int q0 = 0; q0 < N; q0 += 8) {
       int m = 0;
@@ -373,6 +388,15 @@ int mga_schedule_selfcheck(const mga_graph_desc* d, double* stats) {
         }
     stats[2] = c ? tot / c : 1.0;
     stats[3] = c2 ? tot2 / c2 : 1.0;
+    // in-list steps a warp walks, summed over warps: input order with self links vs the schedule
+    int before = 0;
+    for (int w = 0; w < n_warps; ++w) {
+      int m = 0;
+      for (int r = w * 32; r < std::min(N, w * 32 + 32); ++r) m = std::max(m, tmp.h_csr_ptr[r + 1] - tmp.h_csr_ptr[r]);
+      before += m;
+    }
+    stats[4] = before;
+    stats[5] = sc.ell_ptr[n_warps];
   }
   return MGA_OK;
 }

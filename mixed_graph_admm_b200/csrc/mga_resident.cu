@@ -7,17 +7,19 @@
 namespace mga {
 
 #define MGA_DECL(CH, K) int resident_launch_##CH##_##K(mga_plan*, ResArgs&, const ResGeom&, cudaStream_t);
-MGA_DECL(1, 5) MGA_DECL(1, 7) MGA_DECL(1, 9) MGA_DECL(2, 5) MGA_DECL(2, 7) MGA_DECL(2, 9)
-MGA_DECL(3, 5) MGA_DECL(3, 7) MGA_DECL(3, 9)
+MGA_DECL(1, 4) MGA_DECL(1, 6) MGA_DECL(1, 8) MGA_DECL(1, 10) MGA_DECL(2, 4) MGA_DECL(2, 6) MGA_DECL(2, 8) MGA_DECL(2, 10)
+MGA_DECL(3, 4) MGA_DECL(3, 6) MGA_DECL(3, 8) MGA_DECL(3, 10)
 #undef MGA_DECL
 
 constexpr int kResMaxT = 24;
-constexpr int kResMaxK = 9;
+constexpr int kResMaxK = 10;    // slots per forward table after self links and pads are dropped
 
 static bool geometry(const mga_plan* p, ResGeom* geo) {
   const GraphDev& g = p->g;
   if (!p->has_sched) return false;
-  if (!res_geometry(g, p->r_ell_total, res_forced_ch(), geo) && !res_geometry(g, p->r_ell_total, 0, geo)) return false;
+  if (!res_geometry(g, p->r_kd, p->r_ku, p->r_ell_total, res_forced_ch(), geo) &&
+      !res_geometry(g, p->r_kd, p->r_ku, p->r_ell_total, 0, geo))
+    return false;
   return geo->core_bytes <= (size_t)p->max_smem_optin;
 }
 
@@ -27,7 +29,7 @@ bool resident_eligible(const mga_plan* p, int dtype) {
   if (g.temporal == MGA_TEMPORAL_BAND) return false;
   if (g.T > kResMaxT) return false;
   if (g.u_wT != 1 || g.d_wT != 1) return false;
-  if (std::max(g.kd, g.ku + 1) > kResMaxK) return false;
+  if (!p->has_sched || std::max(p->r_kd, p->r_ku) > kResMaxK) return false;
   ResGeom geo;
   return geometry(p, &geo);
 }
@@ -40,11 +42,10 @@ int resident_smem_bytes(const mga_plan* p, int* threads) {
 }
 
 static int pick(mga_plan* p, ResArgs& a, const ResGeom& geo, cudaStream_t st) {
-  const int k = std::max(p->g.kd, p->g.ku + 1);
-  const int kk = k <= 5 ? 5 : (k <= 7 ? 7 : 9);
+  const int kk = geo.Kt;
 #define MGA_CASE(C_, K_) if (geo.CH == C_ && kk == K_) return resident_launch_##C_##_##K_(p, a, geo, st);
-  MGA_CASE(1, 5) MGA_CASE(1, 7) MGA_CASE(1, 9) MGA_CASE(2, 5) MGA_CASE(2, 7) MGA_CASE(2, 9)
-  MGA_CASE(3, 5) MGA_CASE(3, 7) MGA_CASE(3, 9)
+  MGA_CASE(1, 4) MGA_CASE(1, 6) MGA_CASE(1, 8) MGA_CASE(1, 10) MGA_CASE(2, 4) MGA_CASE(2, 6) MGA_CASE(2, 8) MGA_CASE(2, 10)
+  MGA_CASE(3, 4) MGA_CASE(3, 6) MGA_CASE(3, 8) MGA_CASE(3, 10)
 #undef MGA_CASE
   set_error("resident: no instantiation for this (CH, K)");
   return MGA_ERR_UNSUPPORTED;
@@ -58,7 +59,8 @@ int resident_admm(mga_plan* p, const mga_params* m, const void* y, void* x_out, 
   ResGeom geo;
   if (!geometry(p, &geo)) { set_error("resident: shape does not fit"); return MGA_ERR_UNSUPPORTED; }
   a.NT = geo.NT; a.S = geo.S; a.TP = geo.TP;
-  a.B = B; a.kd = g.kd; a.ku = g.ku;
+  a.B = B; a.kd = p->r_kd; a.ku = p->r_ku;
+  a.w_self = p->r_w_self;
   a.perm = p->r_perm; a.nbr_d = p->r_nbr_d; a.d_w = p->r_w_d; a.nbr_u = p->r_nbr_u; a.u_w = p->r_w_u;
   a.ell_ptr = p->r_ell_ptr; a.ell_ent = reinterpret_cast<const int2*>(p->r_ell_ent); a.ell_total = p->r_ell_total;
   a.y = static_cast<const float*>(y);

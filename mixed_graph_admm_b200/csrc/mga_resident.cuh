@@ -66,6 +66,7 @@ struct ResArgs {
   // scheduled tables of the plan (mga_schedule.cpp): internal node order, conflict-aware slot order
   const int* perm;            // perm[internal] = original node (global memory is in original order)
   const int* nbr_d; const float* d_w; const int* nbr_u; const float* u_w;   // (N, kd) / (N, ku), N = zero row
+  const float* w_self;        // (N) weight of each node's own link in the temporal table (not in nbr_d / the in-list)
   const int* ell_ptr;         // (NT/32 + 1) first in-list step of each 32-row warp
   const int2* ell_ent;        // (ell_total) step-major: (internal src or N, weight bits) per lane
   int ell_total;
@@ -88,14 +89,15 @@ struct Ctx {
   int own;                   // i * TP + t0
 #if MGA_RES_TAB_SMEM
   const int2* tabd;          // this lane's temporal-table column: K entries, stride NT: (nbr * TP + t0, weight bits)
-  const int2* tabu;          // spatial table, K-1 entries
+  const int2* tabu;          // spatial table, K entries
   int NT;
 #else
-  int nd[K];                 // neighbour row offset + t0 (zero row for -1)
+  int nd[K];                 // neighbour row offset + t0 (zero row for padding)
   float wd[K];
-  int nu[K - 1];
-  float wu[K - 1];
+  int nu[K];
+  float wu[K];
 #endif
+  float wself;               // weight of the node's own link in the temporal table (left out of the tables)
   int steps;                 // in-list steps of this thread's warp (padded with zero-weight entries)
   float* pbuf;
   float* qbuf;
@@ -155,7 +157,7 @@ struct Ctx {
   }
   __device__ __forceinline__ void fwd_u(const float* buf, float (&acc)[TS]) const {
 #pragma unroll
-    for (int j = 0; j < K - 1; ++j) {
+    for (int j = 0; j < K; ++j) {
 #if MGA_RES_TAB_SMEM
       const int2 en = tabu[j * NT];
       gather_acc(buf, en.x, __int_as_float(en.y), acc);
@@ -168,7 +170,7 @@ struct Ctx {
   // qs[k] = q[t0+k+1] where q = L_d v (ADMM.py:166-177), v already in pbuf (synced).
   __device__ __forceinline__ void shifted_ldr(const float (&v)[TS], float (&qs)[TS]) const {
 #pragma unroll
-    for (int k = 0; k < TS; ++k) qs[k] = 0.f;
+    for (int k = 0; k < TS; ++k) qs[k] = wself * v[k];       // the self link: p_i is in registers
     fwd_d(pbuf, qs);
     const float vnext = has_next ? pbuf[own + TS] : 0.f;
 #pragma unroll
@@ -213,7 +215,7 @@ struct Ctx {
 #pragma unroll
     for (int k = 0; k < TS; ++k) {
       const float q = (k == 0) ? qprev : qs[k - 1];
-      const float l = q - out[k];    // row T-1: f = 0 because qs[T-1] = 0; Q1 is moot as q[0] = 0
+      const float l = q - (out[k] + wself * qs[k]);   // row T-1: f = 0 because qs[T-1] = 0; Q1 is moot as q[0] = 0
       if (XSYS) out[k] = ((t0 + k < t_in ? v[k] : 0.f) + a * v[k]) + c * l;
       else out[k] = c * l + a * v[k];
     }
@@ -316,8 +318,8 @@ __global__ void __launch_bounds__(MAXT, MINB) k_admm_resident(const ResArgs a) {
   float* nxt = reinterpret_cast<float*>(ent + a.ell_total);
 #if MGA_RES_TAB_SMEM
   int2* tabd = reinterpret_cast<int2*>(nxt);        // K x (S * NT), slot-major, one column per thread
-  int2* tabu = tabd + K * a.S * a.NT;               // (K-1) x (S * NT)
-  nxt = reinterpret_cast<float*>(tabu + (K - 1) * a.S * a.NT);
+  int2* tabu = tabd + K * a.S * a.NT;               // K x (S * NT)
+  nxt = reinterpret_cast<float*>(tabu + K * a.S * a.NT);
 #endif
 #if MGA_RES_XPARK
   float* xbuf = nxt;                                // (N + 1) x TP
@@ -354,7 +356,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_admm_resident(const ResArgs a) {
 #endif
   }
 #pragma unroll
-  for (int j = 0; j < K - 1; ++j) {
+  for (int j = 0; j < K; ++j) {
     int nb = N;
     float w = 0.f;
     if (active && j < a.ku) { nb = a.nbr_u[i * a.ku + j]; w = a.u_w[i * a.ku + j]; }
@@ -365,6 +367,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_admm_resident(const ResArgs a) {
     c.wu[j] = w;
 #endif
   }
+  c.wself = active ? a.w_self[i] : 0.f;
   {
     const int wn = i >> 5;     // warp of this node row (the same for every slab)
     const int first = a.ell_ptr[wn];
@@ -489,6 +492,12 @@ __global__ void __launch_bounds__(MAXT, MINB) k_admm_resident(const ResArgs a) {
         }
         __syncthreads();
         c.father_sum(qbuf, f);
+        {
+          float vs[TS];
+          c.get(qbuf, vs);
+#pragma unroll
+          for (int k = 0; k < TS; ++k) f[k] += c.wself * vs[k];
+        }
 #pragma unroll
         for (int k = 0; k < TS; ++k) {
           const int t = t0 + k;
@@ -709,9 +718,13 @@ inline int res_tp(int min_len) {          // smallest 4 * odd >= min_len
 // CH = chunks of 4 time steps per thread.  Default: the largest CH <= 3 (a node's table rows and
 // in-list entries are then read once per 12 time steps; measured 252k vs 210k windows/s against
 // CH = 1 at PEMS04 shape on B200); MGA_RES_CH overrides for experiments.
-inline bool res_geometry(const GraphDev& g, int ell_total, int force_ch, ResGeom* out) {
-  const int kk = std::max(g.kd, g.ku + 1);
-  const int Kt = kk <= 5 ? 5 : (kk <= 7 ? 7 : 9);     // the K of the kernel instantiation
+inline int res_kt(int kd_eff, int ku_eff) {            // the K (slots per forward table) of the kernel instantiation
+  const int kk = std::max(kd_eff, ku_eff);
+  return kk <= 4 ? 4 : (kk <= 6 ? 6 : (kk <= 8 ? 8 : 10));
+}
+
+inline bool res_geometry(const GraphDev& g, int kd_eff, int ku_eff, int ell_total, int force_ch, ResGeom* out) {
+  const int Kt = res_kt(kd_eff, ku_eff);
   const int NT = ((g.N + 31) / 32) * 32;
   const int chunks = (g.T + 3) / 4;
   for (int ch = std::min(3, chunks); ch >= 1; --ch) {
@@ -725,7 +738,7 @@ inline bool res_geometry(const GraphDev& g, int ell_total, int force_ch, ResGeom
     const size_t rows = (size_t)(g.N + 1) * r.TP;
     r.core_bytes = 2 * rows * 4 + 68 * 4 + MGA_DIAG_COLS * 32 * 4 + (size_t)ell_total * 8;
 #if MGA_RES_TAB_SMEM
-    r.core_bytes += (size_t)(2 * Kt - 1) * r.threads * 8;
+    r.core_bytes += (size_t)(2 * Kt) * r.threads * 8;
 #endif
 #if MGA_RES_XPARK
     r.core_bytes += rows * 4;

@@ -3,7 +3,7 @@
 #include "mga_resident.cuh"
 
 #ifndef MGA_CH
-#error "compile with -DMGA_CH=<1|2|3> -DMGA_K=<5|7|9>"
+#error "compile with -DMGA_CH=<1|2|3> -DMGA_K=<4|6|8|10>"
 #endif
 
 #define MGA_CAT_(a, b, c) a##b##_##c

@@ -99,29 +99,57 @@ void build_resident_schedule(int N, int kd, const int* nbr_d, const float* d_w, 
                              const float* u_w, const int* csr_ptr, const int* csr_src, const float* csr_w,
                              ResidentSchedule* out) {
   ResidentSchedule& S = *out;
-  S.N = N; S.kd = kd; S.ku = ku;
-  // ---- (a) node order
+  S.N = N;
+  // ---- self links leave the tables: the thread that owns node i holds p_i and q_i in registers, so
+  // the self term of L_d (and of L_d^T: the in-list entry (i -> i) carries the same weight) is one
+  // multiply instead of a shared-memory gather.  kNN tables always list the node itself first
+  // (utils.py:199-203), i.e. one of K forward gathers and one in-list entry per node go away.
+  S.w_self.assign(N, 0.f);
+  std::vector<std::vector<Cand>> fwd_d(N), fwd_u(N), in_l(N);     // original numbering
+  for (int i = 0; i < N; ++i) {
+    for (int j = 0; j < kd; ++j) {
+      const int nb = nbr_d[(size_t)i * kd + j];
+      if (nb < 0) continue;                                      // "-1 = no neighbour" contributes 0 (quirk Q6)
+      if (nb == i) S.w_self[i] += d_w[(size_t)i * kd + j];
+      else fwd_d[i].push_back(Cand{nb, d_w[(size_t)i * kd + j]});
+    }
+    for (int j = 0; j < ku; ++j) {
+      const int nb = nbr_u[(size_t)i * ku + j];
+      if (nb >= 0) fwd_u[i].push_back(Cand{nb, u_w[(size_t)i * ku + j]});
+    }
+    for (int e = csr_ptr[i]; e < csr_ptr[i + 1]; ++e)
+      if (csr_src[e] != i) in_l[i].push_back(Cand{csr_src[e], csr_w[e]});
+  }
+  S.kd = 0; S.ku = 0;
+  for (int i = 0; i < N; ++i) {
+    S.kd = std::max(S.kd, (int)fwd_d[i].size());
+    S.ku = std::max(S.ku, (int)fwd_u[i].size());
+  }
+  // ---- (a) node order: reverse Cuthill-McKee, then stably by in-degree (largest first) so that
+  // the 32 rows of a warp have in-lists of similar length (the per-warp ELL pads to the longest)
   std::vector<std::vector<int>> adj(N);
   auto link = [&](int a, int b) { if (a != b && a >= 0 && b >= 0) { adj[a].push_back(b); adj[b].push_back(a); } };
   for (int i = 0; i < N; ++i) {
-    for (int j = 0; j < kd; ++j) link(i, nbr_d[(size_t)i * kd + j]);
-    for (int j = 0; j < ku; ++j) link(i, nbr_u[(size_t)i * ku + j]);
-    for (int e = csr_ptr[i]; e < csr_ptr[i + 1]; ++e) link(i, csr_src[e]);
+    for (auto& c : fwd_d[i]) link(i, c.node);
+    for (auto& c : fwd_u[i]) link(i, c.node);
+    for (auto& c : in_l[i]) link(i, c.node);
   }
   for (auto& a : adj) { std::sort(a.begin(), a.end()); a.erase(std::unique(a.begin(), a.end()), a.end()); }
   S.perm = rcm_order(N, adj);
+  std::stable_sort(S.perm.begin(), S.perm.end(), [&](int a, int b) { return in_l[a].size() > in_l[b].size(); });
   S.inv.assign(N, 0);
   for (int p = 0; p < N; ++p) S.inv[S.perm[p]] = p;
-  auto internal = [&](int old) { return old >= 0 ? S.inv[old] : N; };
-  // ---- (b) forward tables
-  auto forward = [&](int K, const int* nbr, const float* w, std::vector<int>& o_n, std::vector<float>& o_w) {
-    std::vector<std::vector<Cand>> rows(N, std::vector<Cand>(K));
+  {
+    std::vector<float> ws(N);
+    for (int p = 0; p < N; ++p) ws[p] = S.w_self[S.perm[p]];
+    S.w_self.swap(ws);                                           // internal order from here on
+  }
+  // ---- (b) forward tables, padded to the longest row with zero-weight entries on the zero row
+  auto forward = [&](int K, const std::vector<std::vector<Cand>>& src, std::vector<int>& o_n, std::vector<float>& o_w) {
+    std::vector<std::vector<Cand>> rows(N, std::vector<Cand>(K, Cand{N, 0.f}));
     for (int p = 0; p < N; ++p) {
-      const int old = S.perm[p];
-      for (int j = 0; j < K; ++j) {
-        const int nb = nbr[(size_t)old * K + j];
-        rows[p][j] = Cand{internal(nb), nb >= 0 ? w[(size_t)old * K + j] : 0.f};
-      }
+      const std::vector<Cand>& r = src[S.perm[p]];
+      for (int j = 0; j < (int)r.size(); ++j) rows[p][j] = Cand{S.inv[r[j].node], r[j].w};
     }
     if (K > 0) assign_slots(N, K, rows);
     o_n.resize((size_t)N * K);
@@ -129,16 +157,14 @@ void build_resident_schedule(int N, int kd, const int* nbr_d, const float* d_w, 
     for (int p = 0; p < N; ++p)
       for (int j = 0; j < K; ++j) { o_n[(size_t)p * K + j] = rows[p][j].node; o_w[(size_t)p * K + j] = rows[p][j].w; }
   };
-  forward(kd, nbr_d, d_w, S.nbr_d, S.w_d);
-  forward(ku, nbr_u, u_w, S.nbr_u, S.w_u);
+  forward(S.kd, fwd_d, S.nbr_d, S.w_d);
+  forward(S.ku, fwd_u, S.nbr_u, S.w_u);
   // ---- (c) in-list as per-warp ELL
   const int NT = ((N + 31) / 32) * 32, n_warps = NT / 32;
   S.ell_ptr.assign(n_warps + 1, 0);
   std::vector<std::vector<Cand>> lists(NT);
-  for (int p = 0; p < N; ++p) {
-    const int old = S.perm[p];
-    for (int e = csr_ptr[old]; e < csr_ptr[old + 1]; ++e) lists[p].push_back(Cand{internal(csr_src[e]), csr_w[e]});
-  }
+  for (int p = 0; p < N; ++p)
+    for (auto& c : in_l[S.perm[p]]) lists[p].push_back(Cand{S.inv[c.node], c.w});
   for (int w = 0; w < n_warps; ++w) {
     int m = 0;
     for (int l = 0; l < 32; ++l) m = std::max(m, (int)lists[w * 32 + l].size());

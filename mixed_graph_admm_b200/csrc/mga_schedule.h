@@ -5,10 +5,12 @@
 namespace mga {
 
 struct ResidentSchedule {
-  int N = 0, kd = 0, ku = 0;
+  int N = 0;
+  int kd = 0, ku = 0;         // slots per row AFTER self links and "-1" pads were dropped
+  std::vector<float> w_self;  // (N) internal order: weight of the node's link to itself in the temporal table
   std::vector<int> perm;      // perm[internal] = original node
   std::vector<int> inv;       // inv[original] = internal
-  std::vector<int> nbr_d;     // (N, kd) internal ids, N = zero row
+  std::vector<int> nbr_d;     // (N, kd) internal ids, N = zero row (zero weight) padding
   std::vector<float> w_d;
   std::vector<int> nbr_u;     // (N, ku)
   std::vector<float> w_u;

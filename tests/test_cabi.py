@@ -121,9 +121,12 @@ def test_resident_schedule_is_a_pure_reordering(libmga, name):
                             d_w=dw.data_ptr(), d_w_T=1,
                             ldrt_mode=_cabi.LDRT_SCATTER if g.ctor.get("use_kNN") else _cabi.LDRT_GATHER,
                             temporal=_cabi.TEMPORAL_GRAPH)
-    stats = (C.c_double * 4)()
+    stats = (C.c_double * 6)()
     rc = libmga.mga_schedule_selfcheck(C.byref(d), stats)
     assert rc == 0, libmga.mga_last_error()
     if name == "pems04_f32":
         # measured benefit on the benchmark graph: fewer bank-group collisions per quarter-warp phase
         assert stats[1] < 0.75 * stats[0] and stats[3] < 0.9 * stats[2], list(stats)
+        # in-degree ordering + self links out of the in-list: the warps walk far fewer in-list steps
+        assert stats[5] < 0.75 * stats[4], list(stats)
+        print("schedule stats", list(stats))
