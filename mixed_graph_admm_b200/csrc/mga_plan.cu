@@ -311,8 +311,8 @@ int mga_schedule_selfcheck(const mga_graph_desc* d, double* stats) {
       }
       for (int j = 0; j < Ks; ++j) {
         const int sn = s_n[(size_t)p * Ks + j];
-        if (sn < 0 || sn > N) return false;
-        if (sn == N) { if (s_w[(size_t)p * Ks + j] != 0.f) return false; continue; }
+        if (sn < 0 || sn >= N + 8) return false;
+        if (sn >= N) { if (s_w[(size_t)p * Ks + j] != 0.f) return false; continue; }
         b.emplace_back(sc.perm[sn], s_w[(size_t)p * Ks + j]);
       }
       if (!same_multiset(a, b)) return false;
@@ -339,8 +339,8 @@ int mga_schedule_selfcheck(const mga_graph_desc* d, double* stats) {
     for (int e = sc.ell_ptr[w]; e < sc.ell_ptr[w + 1]; ++e) {
       const int sn = sc.ell_node[(size_t)e * 32 + l];
       const float sw = sc.ell_w[(size_t)e * 32 + l];
-      if (sn == N) { if (sw != 0.f) return bad("padding entry with weight"); continue; }
-      if (sn < 0 || sn > N) return bad("in-list node out of range");
+      if (sn < 0 || sn >= N + 8) return bad("in-list node out of range");
+      if (sn >= N) { if (sw != 0.f) return bad("padding entry with weight"); continue; }
       b.emplace_back(sc.perm[sn], sw);
     }
     if (!same_multiset(a, b)) return bad("in-list differs");
@@ -353,7 +353,7 @@ int mga_schedule_selfcheck(const mga_graph_desc* d, double* stats) {
       std::sort(u.begin(), u.end());
       u.erase(std::unique(u.begin(), u.end()), u.end());
       int m = 1;
-      for (int n : u) if (n >= 0 && n < N) m = std::max(m, ++cnt[n & 7]);
+      for (int n : u) if (n >= 0) m = std::max(m, ++cnt[n & 7]);     // zero rows (>= N) occupy a bank group too
       return m;
     };
     auto fwd_cost = [&](int K, const std::vector<int>& tab) {

@@ -10,7 +10,8 @@
 // neighbour's whole time series is then contiguous, so every gather is an aligned 128-bit load
 // (4 time steps per LDS.128), and `TP/4 odd` makes node -> 16-byte bank group a bijection mod 8,
 // which keeps the 8 lanes of a quarter-warp on distinct groups when their nodes differ mod 8.
-// Row N is a zero row that absorbs the "-1 = no neighbour" entries (quirk Q6).
+// Rows N .. N+7 are zero rows (one per bank group) that absorb the "-1 = no neighbour" entries (quirk Q6)
+// and the padding of the tables.
 //
 // The shift.  L_d reads p at t-1 and L_d^T reads q at t+1 (ADMM.py:171, 200-208), which would
 // misalign the 4-step chunks.  Instead each thread computes qs[k] = q[k+1] for the k it owns
@@ -43,13 +44,13 @@
 #include "mga_common.cuh"
 
 #ifndef MGA_RES_TAB_SMEM
-#define MGA_RES_TAB_SMEM 0
+#define MGA_RES_TAB_SMEM 1
 #endif
 #ifndef MGA_RES_XPARK
 #define MGA_RES_XPARK 0
 #endif
 #ifndef MGA_RES_MINB      // CTAs per SM the <= 320-thread instantiations are compiled for
-#define MGA_RES_MINB 1
+#define MGA_RES_MINB 2
 #endif
 
 namespace mga {
@@ -309,7 +310,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_admm_resident(const ResArgs a) {
   constexpr int TS = 4 * CH;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int N = a.N, T = a.T, TP = a.TP, t_in = a.t_in;
-  const int rows = (N + 1) * TP;
+  const int rows = (N + 8) * TP;
   float* pbuf = reinterpret_cast<float*>(smem_raw);
   float* qbuf = pbuf + rows;
   float* red = qbuf + rows;                         // 64 floats + the next-window slot (68 with padding)
@@ -735,7 +736,7 @@ inline bool res_geometry(const GraphDev& g, int kd_eff, int ku_eff, int ell_tota
     r.CH = ch; r.S = S; r.NT = NT; r.threads = S * NT;
     r.TP = res_tp(S * 4 * ch);
     r.Kt = Kt;
-    const size_t rows = (size_t)(g.N + 1) * r.TP;
+    const size_t rows = (size_t)(g.N + 8) * r.TP;
     r.core_bytes = 2 * rows * 4 + 68 * 4 + MGA_DIAG_COLS * 32 * 4 + (size_t)ell_total * 8;
 #if MGA_RES_TAB_SMEM
     r.core_bytes += (size_t)(2 * Kt) * r.threads * 8;

@@ -8,14 +8,15 @@ struct ResidentSchedule {
   int N = 0;
   int kd = 0, ku = 0;         // slots per row AFTER self links and "-1" pads were dropped
   std::vector<float> w_self;  // (N) internal order: weight of the node's link to itself in the temporal table
+  int overload = 0;           // gathers left over the conflict-free bound after bank-class balancing (0 = none)
   std::vector<int> perm;      // perm[internal] = original node
   std::vector<int> inv;       // inv[original] = internal
-  std::vector<int> nbr_d;     // (N, kd) internal ids, N = zero row (zero weight) padding
+  std::vector<int> nbr_d;     // (N, kd) internal ids; N .. N+7 = zero rows (zero-weight padding, one per bank class)
   std::vector<float> w_d;
   std::vector<int> nbr_u;     // (N, ku)
   std::vector<float> w_u;
   std::vector<int> ell_ptr;   // (n_warps + 1) first step of each 32-row warp
-  std::vector<int> ell_node;  // (steps_total * 32) internal ids, N = padding
+  std::vector<int> ell_node;  // (steps_total * 32) internal ids, N .. N+7 = padding
   std::vector<float> ell_w;
 };
 
