@@ -73,7 +73,7 @@ struct ResArgs {
   int ell_total;
   const float* y; float* x_out;
   float* out[ST_COUNT];       // optional per-window outputs (index by ST_*; ST_X unused)
-  float* scratch;             // gridDim.x * ST_COUNT * T * N floats when !state_in_smem
+  float* scratch;             // gridDim.x * ST_COUNT * N * TP floats when !state_in_smem
   int* next_window;           // zeroed per launch: windows beyond the first gridDim.x are handed out dynamically
   double* diag; double* dx_sum;
   float* alpha; float* beta;
@@ -82,6 +82,23 @@ struct ResArgs {
   float t_mean, t_var;
 };
 
+// Shared-memory loads by 32-bit shared address.  The tables hold ABSOLUTE shared addresses (base of
+// pbuf / qbuf folded in when the CTA fills them), so a gather is "LDS.128 [entry + 16 c]" with no
+// address arithmetic between the table load and the data load.
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+template <int OFF>
+__device__ __forceinline__ float4 lds128(uint32_t a) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+%5];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a), "n"(OFF) : "memory");
+  return v;
+}
+template <int OFF>
+__device__ __forceinline__ int2 lds64(uint32_t a) {
+  int2 v;
+  asm volatile("ld.shared.v2.b32 {%0, %1}, [%2+%3];" : "=r"(v.x), "=r"(v.y) : "r"(a), "n"(OFF) : "memory");
+  return v;
+}
+
 template <int CH, int K>
 struct Ctx {
   static constexpr int TS = 4 * CH;
@@ -89,13 +106,13 @@ struct Ctx {
   bool has_next, has_prev;   // another slab of this node owns t0+TS / t0-1
   int own;                   // i * TP + t0
 #if MGA_RES_TAB_SMEM
-  const int2* tabd;          // this lane's temporal-table column: K entries, stride NT: (nbr * TP + t0, weight bits)
-  const int2* tabu;          // spatial table, K entries
-  int NT;
+  uint32_t tabd;             // shared address of this thread's temporal-table column: K entries, stride NTB bytes:
+  uint32_t tabu;             //   (shared address of pbuf[nbr][t0], weight bits); tabu: spatial table
+  int NTB;
 #else
-  int nd[K];                 // neighbour row offset + t0 (zero row for padding)
+  uint32_t nd[K];            // shared address of pbuf[nbr][t0] (a zero row for padding)
   float wd[K];
-  int nu[K];
+  uint32_t nu[K];
   float wu[K];
 #endif
   float wself;               // weight of the node's own link in the temporal table (left out of the tables)
@@ -105,18 +122,30 @@ struct Ctx {
 #if MGA_RES_XPARK
   float* xrow;               // private parking row of the CG iterate
 #endif
-  const int2* ent;           // this lane's first in-list entry; stride 32: (src * TP, weight bits)
+  uint32_t ent;              // shared address of this lane's first in-list entry; stride 256 B:
+                             //   (shared address of qbuf[src][0], weight bits)
+  uint32_t t0b;              // t0 * 4
   float* red;                // 2 x 32
   int red_sel;
 
+  // Block sum, result in every thread.  Warp partials go to a 32-float row (zero beyond the warp count);
+  // after the barrier every thread reads the whole row as broadcast 128-bit loads and adds it up in one
+  // fixed tree — shorter than a second shuffle butterfly, and bit-identical in every thread.
   __device__ __forceinline__ float bsum(float v) {
     float* r = red + 32 * red_sel;
     red_sel ^= 1;
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     v = warp_sum<float>(v);
     if (lane == 0) r[w] = v;
     __syncthreads();
-    return warp_sum<float>(lane < nw ? r[lane] : 0.f);   // every warp reduces the <= 32 partials itself
+    const int nw4 = (blockDim.x + 127) >> 7;       // float4 groups that hold partials
+    float4 t = *reinterpret_cast<const float4*>(r);
+    float s = (t.x + t.y) + (t.z + t.w);
+    for (int k = 1; k < nw4; ++k) {
+      t = *reinterpret_cast<const float4*>(r + 4 * k);
+      s += (t.x + t.y) + (t.z + t.w);
+    }
+    return s;
   }
 
   __device__ __forceinline__ void put(float* buf, const float (&v)[TS]) const {
@@ -132,47 +161,56 @@ struct Ctx {
     }
   }
 
-  // acc[k] += w * buf[off + k], k = 0..TS-1, as CH aligned 128-bit loads
-  __device__ __forceinline__ void gather_acc(const float* buf, int off, float w, float (&acc)[TS]) const {
+  // acc[k] += w * row[k], k = 0..TS-1, as CH aligned 128-bit loads from the shared address `row`
+  __device__ __forceinline__ void gather_acc(uint32_t row, float w, float (&acc)[TS]) const {
+    float4 g[CH];
+    g[0] = lds128<0>(row);
+    if (CH > 1) g[CH > 1 ? 1 : 0] = lds128<16>(row);
+    if (CH > 2) g[CH > 2 ? 2 : 0] = lds128<32>(row);
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
-      const float4 g = *reinterpret_cast<const float4*>(buf + off + 4 * c);
-      acc[4 * c] += w * g.x;
-      acc[4 * c + 1] += w * g.y;
-      acc[4 * c + 2] += w * g.z;
-      acc[4 * c + 3] += w * g.w;
+      acc[4 * c] += w * g[c].x;
+      acc[4 * c + 1] += w * g[c].y;
+      acc[4 * c + 2] += w * g[c].z;
+      acc[4 * c + 3] += w * g[c].w;
     }
   }
 
-  // acc += sum_j w_j * buf[nbr_j] over the temporal (kd slots) / spatial (ku slots) forward table
-  __device__ __forceinline__ void fwd_d(const float* buf, float (&acc)[TS]) const {
+  // acc += sum_j w_j * pbuf[nbr_j] over the temporal / spatial forward table
+  __device__ __forceinline__ void fwd_d(float (&acc)[TS]) const {
+#if MGA_RES_TAB_SMEM
+    uint32_t t = tabd;
 #pragma unroll
     for (int j = 0; j < K; ++j) {
-#if MGA_RES_TAB_SMEM
-      const int2 en = tabd[j * NT];
-      gather_acc(buf, en.x, __int_as_float(en.y), acc);
-#else
-      gather_acc(buf, nd[j], wd[j], acc);
-#endif
+      const int2 en = lds64<0>(t);
+      t += NTB;
+      gather_acc((uint32_t)en.x, __int_as_float(en.y), acc);
     }
+#else
+#pragma unroll
+    for (int j = 0; j < K; ++j) gather_acc(nd[j], wd[j], acc);
+#endif
   }
-  __device__ __forceinline__ void fwd_u(const float* buf, float (&acc)[TS]) const {
+  __device__ __forceinline__ void fwd_u(float (&acc)[TS]) const {
+#if MGA_RES_TAB_SMEM
+    uint32_t t = tabu;
 #pragma unroll
     for (int j = 0; j < K; ++j) {
-#if MGA_RES_TAB_SMEM
-      const int2 en = tabu[j * NT];
-      gather_acc(buf, en.x, __int_as_float(en.y), acc);
-#else
-      gather_acc(buf, nu[j], wu[j], acc);
-#endif
+      const int2 en = lds64<0>(t);
+      t += NTB;
+      gather_acc((uint32_t)en.x, __int_as_float(en.y), acc);
     }
+#else
+#pragma unroll
+    for (int j = 0; j < K; ++j) gather_acc(nu[j], wu[j], acc);
+#endif
   }
 
   // qs[k] = q[t0+k+1] where q = L_d v (ADMM.py:166-177), v already in pbuf (synced).
   __device__ __forceinline__ void shifted_ldr(const float (&v)[TS], float (&qs)[TS]) const {
 #pragma unroll
     for (int k = 0; k < TS; ++k) qs[k] = wself * v[k];       // the self link: p_i is in registers
-    fwd_d(pbuf, qs);
+    fwd_d(qs);
     const float vnext = has_next ? pbuf[own + TS] : 0.f;
 #pragma unroll
     for (int k = 0; k < TS; ++k) {
@@ -181,21 +219,24 @@ struct Ctx {
     }
   }
 
-  // f[k] = sum over the in-list of w * buf[src][t0+k]   (ADMM.py:200-209 as a gather; buf holds the
-  // vector shifted by one time step, so this is the "father" sum at t0+k)
-  __device__ __forceinline__ void father_sum(const float* buf, float (&f)[TS]) const {
+  // f[k] = sum over the in-list of w * qbuf[src][t0+k]   (ADMM.py:200-209 as a gather; qbuf holds the
+  // vector shifted by one time step, so this is the "father" sum at t0+k).  Two entries per trip, the
+  // next two (row address, weight) pairs are fetched a trip ahead; the table has two spare steps at
+  // its end so the look-ahead never leaves it.
+  __device__ __forceinline__ void father_sum(float (&f)[TS]) const {
 #pragma unroll
     for (int k = 0; k < TS; ++k) f[k] = 0.f;
-    int e = 0;
-    for (; e + 1 < steps; e += 2) {       // two entries per trip: more loads in flight
-      const int2 a = ent[e * 32], b = ent[(e + 1) * 32];
-      gather_acc(buf, a.x + t0, __int_as_float(a.y), f);
-      gather_acc(buf, b.x + t0, __int_as_float(b.y), f);
+    uint32_t ep = ent;
+    int2 a = lds64<0>(ep), b = lds64<256>(ep);
+    int n = steps;
+    for (; n >= 2; n -= 2) {
+      const int2 a2 = lds64<512>(ep), b2 = lds64<768>(ep);
+      ep += 512;
+      gather_acc((uint32_t)a.x + t0b, __int_as_float(a.y), f);
+      gather_acc((uint32_t)b.x + t0b, __int_as_float(b.y), f);
+      a = a2; b = b2;
     }
-    if (e < steps) {
-      const int2 a = ent[e * 32];
-      gather_acc(buf, a.x + t0, __int_as_float(a.y), f);
-    }
+    if (n) gather_acc((uint32_t)a.x + t0b, __int_as_float(a.y), f);
   }
 
   // out = A v for the x / z_d systems: diag(v) + c * L_d^T L_d v  (ADMM.py:371-387, 392-394)
@@ -209,7 +250,7 @@ struct Ctx {
       put(qbuf, qs);
     }
     __syncthreads();
-    father_sum(qbuf, out);                                   // out = f
+    father_sum(out);                                         // out = f
     const float qprev = has_prev ? qbuf[own - 1] : 0.f;      // q[t0]; q[0] = 0 (ADMM.py:176)
     float qs[TS];
     get(qbuf, qs);     // the own row is re-read instead of kept live across the in-list gather
@@ -228,7 +269,7 @@ struct Ctx {
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < TS; ++k) out[k] = 0.f;
-    fwd_u(pbuf, out);
+    fwd_u(out);
 #pragma unroll
     for (int k = 0; k < TS; ++k) out[k] = c * (v[k] - out[k]) + a * v[k];
   }
@@ -316,7 +357,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_admm_resident(const ResArgs a) {
   float* red = qbuf + rows;                         // 64 floats + the next-window slot (68 with padding)
   float* dred = red + 68;                           // MGA_DIAG_COLS x 32 floats
   int2* ent = reinterpret_cast<int2*>(dred + MGA_DIAG_COLS * 32);
-  float* nxt = reinterpret_cast<float*>(ent + a.ell_total);
+  float* nxt = reinterpret_cast<float*>(ent + a.ell_total + 64);      // + 2 spare steps for the look-ahead
 #if MGA_RES_TAB_SMEM
   int2* tabd = reinterpret_cast<int2*>(nxt);        // K x (S * NT), slot-major, one column per thread
   int2* tabu = tabd + K * a.S * a.NT;               // K x (S * NT)
@@ -341,8 +382,11 @@ __global__ void __launch_bounds__(MAXT, MINB) k_admm_resident(const ResArgs a) {
 #if MGA_RES_XPARK
   c.xrow = xbuf + c.own;
 #endif
+  const uint32_t pb = smem_addr(pbuf), qb = smem_addr(qbuf);
+  c.t0b = (uint32_t)t0 * 4u;
 #if MGA_RES_TAB_SMEM
-  c.NT = a.S * a.NT; c.tabd = tabd + threadIdx.x; c.tabu = tabu + threadIdx.x;
+  const int ncol = a.S * a.NT;
+  c.NTB = ncol * 8; c.tabd = smem_addr(tabd + threadIdx.x); c.tabu = smem_addr(tabu + threadIdx.x);
 #endif
 #pragma unroll
   for (int j = 0; j < K; ++j) {
@@ -350,9 +394,9 @@ __global__ void __launch_bounds__(MAXT, MINB) k_admm_resident(const ResArgs a) {
     float w = 0.f;
     if (active && j < a.kd) { nb = a.nbr_d[i * a.kd + j]; w = a.d_w[i * a.kd + j]; }
 #if MGA_RES_TAB_SMEM
-    tabd[j * c.NT + threadIdx.x] = make_int2(nb * TP + t0, __float_as_int(w));
+    tabd[j * ncol + threadIdx.x] = make_int2((int)(pb + (uint32_t)(nb * TP + t0) * 4u), __float_as_int(w));
 #else
-    c.nd[j] = nb * TP + t0;
+    c.nd[j] = pb + (uint32_t)(nb * TP + t0) * 4u;
     c.wd[j] = w;
 #endif
   }
@@ -362,9 +406,9 @@ __global__ void __launch_bounds__(MAXT, MINB) k_admm_resident(const ResArgs a) {
     float w = 0.f;
     if (active && j < a.ku) { nb = a.nbr_u[i * a.ku + j]; w = a.u_w[i * a.ku + j]; }
 #if MGA_RES_TAB_SMEM
-    tabu[j * c.NT + threadIdx.x] = make_int2(nb * TP + t0, __float_as_int(w));
+    tabu[j * ncol + threadIdx.x] = make_int2((int)(pb + (uint32_t)(nb * TP + t0) * 4u), __float_as_int(w));
 #else
-    c.nu[j] = nb * TP + t0;
+    c.nu[j] = pb + (uint32_t)(nb * TP + t0) * 4u;
     c.wu[j] = w;
 #endif
   }
@@ -373,47 +417,40 @@ __global__ void __launch_bounds__(MAXT, MINB) k_admm_resident(const ResArgs a) {
     const int wn = i >> 5;     // warp of this node row (the same for every slab)
     const int first = a.ell_ptr[wn];
     c.steps = a.ell_ptr[wn + 1] - first;
-    c.ent = ent + (size_t)first * 32 + (i & 31);
+    c.ent = smem_addr(ent + (size_t)first * 32 + (i & 31));
   }
-  for (int e = threadIdx.x; e < a.ell_total; e += blockDim.x) {
-    const int2 en = a.ell_ent[e];
-    ent[e] = make_int2(en.x * TP, en.y);
+  for (int e = threadIdx.x; e < a.ell_total + 64; e += blockDim.x) {
+    int2 en = make_int2(N, 0);                 // spare steps: a zero row, zero weight
+    if (e < a.ell_total) en = a.ell_ent[e];
+    ent[e] = make_int2((int)(qb + (uint32_t)(en.x * TP) * 4u), en.y);
   }
   const int orig = active ? a.perm[i] : 0;   // this thread's node in the caller's numbering
   for (int k = threadIdx.x; k < 2 * rows; k += blockDim.x) pbuf[k] = 0.f;
+  for (int k = threadIdx.x; k < 64; k += blockDim.x) red[k] = 0.f;     // bsum() relies on zeros beyond the warp count
 #if MGA_RES_XPARK
   for (int k = threadIdx.x; k < rows; k += blockDim.x) xbuf[k] = 0.f;
 #endif
   __syncthreads();
 
-  // ---- parked ADMM state: smem [v][node*TP + t] (128-bit) or global scratch [v][t][node] (coalesced)
-  float* gstate = a.state_in_smem ? nullptr : a.scratch + (size_t)blockIdx.x * ST_COUNT * T * N;
+  // ---- parked ADMM state: [v][node * TP + t] as 128-bit chunks, in shared memory or in this CTA's slice
+  // of an L2-resident scratch (same layout: a warp reads 32 consecutive 48-byte rows)
+  float* st_base = a.state_in_smem ? st_smem : a.scratch + (size_t)blockIdx.x * ST_COUNT * N * TP;
+  st_base += i * TP + t0;
+  const int st_stride = N * TP;
   auto ld_state = [&](int v, float (&o)[TS]) {
-    if (a.state_in_smem) {
-      const float* base = st_smem + (size_t)v * N * TP + i * TP + t0;
+    const float4* base = reinterpret_cast<const float4*>(st_base + v * st_stride);
 #pragma unroll
-      for (int cc = 0; cc < CH; ++cc) {
-        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (active) g = *reinterpret_cast<const float4*>(base + 4 * cc);
-        o[4 * cc] = g.x; o[4 * cc + 1] = g.y; o[4 * cc + 2] = g.z; o[4 * cc + 3] = g.w;
-      }
-    } else {
-#pragma unroll
-      for (int k = 0; k < TS; ++k) o[k] = (active && t0 + k < T) ? gstate[((size_t)v * T + t0 + k) * N + i] : 0.f;
+    for (int cc = 0; cc < CH; ++cc) {
+      float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (active) g = base[cc];
+      o[4 * cc] = g.x; o[4 * cc + 1] = g.y; o[4 * cc + 2] = g.z; o[4 * cc + 3] = g.w;
     }
   };
   auto st_state = [&](int v, const float (&o)[TS]) {
     if (!active) return;
-    if (a.state_in_smem) {
-      float* base = st_smem + (size_t)v * N * TP + i * TP + t0;
+    float4* base = reinterpret_cast<float4*>(st_base + v * st_stride);
 #pragma unroll
-      for (int cc = 0; cc < CH; ++cc)
-        *reinterpret_cast<float4*>(base + 4 * cc) = make_float4(o[4 * cc], o[4 * cc + 1], o[4 * cc + 2], o[4 * cc + 3]);
-    } else {
-#pragma unroll
-      for (int k = 0; k < TS; ++k)
-        if (t0 + k < T) gstate[((size_t)v * T + t0 + k) * N + i] = o[k];
-    }
+    for (int cc = 0; cc < CH; ++cc) base[cc] = make_float4(o[4 * cc], o[4 * cc + 1], o[4 * cc + 2], o[4 * cc + 3]);
   };
   // per-thread partial of one diagnostics column: reduced over the warp at once and left in
   // dred[col][warp] until the end of the outer iteration, so no column stays live in registers
@@ -492,7 +529,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_admm_resident(const ResArgs a) {
           c.put(qbuf, vs);
         }
         __syncthreads();
-        c.father_sum(qbuf, f);
+        c.father_sum(f);
         {
           float vs[TS];
           c.get(qbuf, vs);
@@ -614,7 +651,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_admm_resident(const ResArgs a) {
           float lux[TS];
 #pragma unroll
           for (int k = 0; k < TS; ++k) lux[k] = 0.f;
-          c.fwd_u(pbuf, lux);
+          c.fwd_u(lux);
           float sg = 0.f, sr = 0.f;
 #pragma unroll
           for (int k = 0; k < TS; ++k) {
@@ -737,7 +774,7 @@ inline bool res_geometry(const GraphDev& g, int kd_eff, int ku_eff, int ell_tota
     r.TP = res_tp(S * 4 * ch);
     r.Kt = Kt;
     const size_t rows = (size_t)(g.N + 8) * r.TP;
-    r.core_bytes = 2 * rows * 4 + 68 * 4 + MGA_DIAG_COLS * 32 * 4 + (size_t)ell_total * 8;
+    r.core_bytes = 2 * rows * 4 + 68 * 4 + MGA_DIAG_COLS * 32 * 4 + (size_t)(ell_total + 64) * 8;
 #if MGA_RES_TAB_SMEM
     r.core_bytes += (size_t)(2 * Kt) * r.threads * 8;
 #endif
@@ -774,7 +811,7 @@ inline int launch_res(mga_plan* p, ResArgs& a, const ResGeom& geo, cudaStream_t 
   const size_t smem = a.state_in_smem ? with_state : core;
   int64_t grid = std::min<int64_t>(a.B, (int64_t)occ * p->sm_count);
   if (!a.state_in_smem) {
-    const size_t need = (size_t)grid * ST_COUNT * g.T * g.N * sizeof(float);
+    const size_t need = (size_t)grid * geo.state_bytes;
     int rc = ensure_workspace(p, p->ws, need);
     if (rc) return rc;
     a.scratch = static_cast<float*>(p->ws.base);
