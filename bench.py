@@ -196,6 +196,7 @@ def main():
     ap.add_argument("--mode", default="auto", choices=["auto", "resident", "streaming"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cg-batch", type=int, default=16384, help="batch of the streaming CG-iteration probe")
+    ap.add_argument("--no-cg-probe", action="store_true", help="skip the mga_cg_solve probe (launch lists of the step only)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -296,9 +297,24 @@ def main():
         alg_bytes = algorithmic_bytes_per_point() * npts * B
         achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
         hbm_io = (B * T_IN * N_NODES * 4 + B * npts * 4) / (ms_per_step * 1e-3) / 1e9
+        traffic, smem = None, None
+        cpath = os.path.join(ROOT, "profiles", "r01_resident_counters.json")
+        if kernel_mode == "resident" and os.path.exists(cpath):
+            # counters of one `ncu --set full` capture of this kernel (committed under profiles/), per launch
+            with open(cpath) as f:
+                cnt = json.load(f)
+            if cnt.get("batch") == B:
+                traffic = cnt["dram_bytes_read"] + cnt["dram_bytes_write"]
+            sm_clk = (clocks or {}).get("sm_mhz") or 1965.0
+            wf_per_window = cnt["smem_wavefronts"] / cnt["batch"]
+            smem = {"bound": "shared-memory pipe (128 B/clk/SM)", "wavefronts_per_window": wf_per_window,
+                    "achieved_TBps": wf_per_window * 128 * value / world / 1e12,
+                    "peak_TBps": 148 * 128 * sm_clk * 1e6 / 1e12,
+                    "ncu_pipe_pct_of_peak": cnt["smem_pipe_pct_of_peak"], "source": "profiles/r01_resident_counters.json"}
+            smem["frac"] = smem["achieved_TBps"] / smem["peak_TBps"]
         roof = {"bound": "hbm", "kernel": "k_admm_resident" if kernel_mode == "resident" else "streaming kernels",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "peak_source": peak_src,
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                "peak_source": peak_src, "smem": smem,
                 "note": ("algorithmic bytes = what a streaming implementation must move (DESIGN.md §5); the "
                          "resident kernel keeps them in registers/SMEM, its real HBM I/O is y in + x out = "
                          f"{hbm_io:.1f} GB/s") if kernel_mode == "resident" else "streaming mode"}
@@ -314,7 +330,7 @@ def main():
                 "gpu_launches": int(launches), "wall_s_timed_region": t_wall, "clocks": clocks, "roofline": roof}
 
     # ---- the fused CG iteration in streaming mode vs the HBM roofline (vectors larger than L2)
-    if rank == 0:
+    if rank == 0 and not args.no_cg_probe:
         try:
             Bc = args.cg_batch
             n = Bc * T_LEN * N_NODES

@@ -1,0 +1,32 @@
+"""Where the end-to-end (host buffers) step spends its time: cProfile over N calls of combined_loop."""
+import cProfile
+import os
+import pstats
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+import bench  # noqa: E402
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+dev = torch.device("cuda", 0)
+blk, y = bench.build_problem(B, seed=0, device=dev)
+yp = y.pin_memory()
+for _ in range(3):
+    blk.combined_loop(yp, print_info=False)
+torch.cuda.synchronize()
+n = 20
+t0 = time.perf_counter()
+for _ in range(n):
+    blk.combined_loop(yp, print_info=False)
+torch.cuda.synchronize()
+dt = (time.perf_counter() - t0) / n
+print(f"B={B}: {dt * 1e3:.3f} ms per call, {B / dt:.0f} windows/s")
+pr = cProfile.Profile()
+pr.enable()
+for _ in range(n):
+    blk.combined_loop(yp, print_info=False)
+pr.disable()
+pstats.Stats(pr).sort_stats("cumulative").print_stats(18)
