@@ -487,8 +487,13 @@ class ADMM_algorithm():
         with_phi = self.ablation in ['None', 'DGLR']
         with_zd = self.ablation != 'DGLR'
 
+        np_dt = np.float32 if dtype == torch.float32 else np.float64
+
         def rnd(v):      # value rounded to the signal dtype, as a python float
-            return torch.tensor(v, dtype=torch.float64).to(dtype).item()
+            return float(np_dt(v))
+
+        def scalar(v):   # 0-dim tensor in the signal dtype (quirk Q11)
+            return torch.tensor(float(v), dtype=dtype, device=device)
 
         for i in range(n_done):
             d = diag[i]
@@ -507,20 +512,20 @@ class ADMM_algorithm():
                 getattr(self, "beta_" + name).append(b)
             pri, dual = [], []
             self.x_shift_list.append(rnd(math.sqrt(d[_cabi.DIAG_DX2])))
-            mean_dx = torch.from_numpy(dx_sum[i] / B)
-            self.delta_x_per_step.append(mean_dx.pow(2).sum(1).sqrt().to(dtype).to(device))
+            mean_dx = dx_sum[i] / B
+            self.delta_x_per_step.append(torch.from_numpy(np.sqrt((mean_dx * mean_dx).sum(1)).astype(np_dt)).to(device))
             pri.append(rnd(math.sqrt(d[_cabi.DIAG_X_ZU2])))
             dual.append(rnd(math.sqrt(d[_cabi.DIAG_DZU2])))
-            self.GLR_list.append(torch.tensor(d[_cabi.DIAG_GLR] / B, dtype=torch.float64).to(dtype).to(device))
+            self.GLR_list.append(scalar(d[_cabi.DIAG_GLR] / B))
             self.recover_list.append(rnd(math.sqrt(d[_cabi.DIAG_RECOVER2])))
             if with_phi:
                 pri.append(rnd(math.sqrt(d[_cabi.DIAG_PHI_LDX2])))
                 dual.append(rnd(math.sqrt(d[_cabi.DIAG_DPHI2])))
-                self.DGTV_list.append(torch.tensor(d[_cabi.DIAG_DGTV] / B, dtype=torch.float64).to(dtype).to(device))
+                self.DGTV_list.append(scalar(d[_cabi.DIAG_DGTV] / B))
             if with_zd:
                 pri.append(rnd(math.sqrt(d[_cabi.DIAG_X_ZD2])))
                 dual.append(rnd(math.sqrt(d[_cabi.DIAG_DZD2])))
-                self.DGLR_list.append(torch.tensor(d[_cabi.DIAG_DGLR] / B, dtype=torch.float64).to(dtype).to(device))
+                self.DGLR_list.append(scalar(d[_cabi.DIAG_DGLR] / B))
             if print_info:
                 zd_it = its[2] if with_zd else None
                 print(f'ADMM iters {i}: x_CG_iters {its[0]}, zu_CG_iters {its[1]}, zd_CG_iters {zd_it}, '

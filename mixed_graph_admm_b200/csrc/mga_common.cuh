@@ -61,8 +61,10 @@ struct mga_plan {
   mga::Workspace ws_host_io;         // device staging of the *_host entry point
   void* pinned = nullptr;            // small pinned host block (flags, diag read-back)
   size_t pinned_bytes = 0;
-  cudaStream_t io_streams[3] = {nullptr, nullptr, nullptr};
-  cudaEvent_t io_events[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaStream_t io_streams[4] = {nullptr, nullptr, nullptr, nullptr};    // upload, run slot 0, run slot 1, download
+  cudaEvent_t io_events[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int res_slot = 0;                  // which half of the resident kernel's parking scratch the next launch uses
+                                     // (the host entry point runs two chunk solves concurrently)
   // host copies of the tables
   std::vector<int> h_nbr_u, h_nbr_d, h_csr_ptr, h_csr_src;
   std::vector<float> h_u_w, h_d_w, h_csr_w;

@@ -509,48 +509,56 @@ int mga_admm_solve_host(mga_plan* p, const mga_params* prm, const void* y_host, 
   char* base = static_cast<char*>(p->ws_host_io.base);
   for (auto& s : p->io_streams) if (!s) MGA_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
   for (auto& ev : p->io_events) if (!ev) MGA_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-  cudaStream_t s_up = p->io_streams[0], s_run = p->io_streams[1], s_dn = p->io_streams[2];
+  // Resident mode: two chunk solves may run concurrently (one stream per slot), so the tail of one chunk's
+  // persistent grid overlaps the head of the next.  Streaming mode shares one workspace: one run stream.
+  const bool can_res = mode != MGA_MODE_STREAMING && prm->ablation == MGA_ABL_NONE && resident_eligible(p, dtype);
+  cudaStream_t s_up = p->io_streams[0], s_dn = p->io_streams[3];
+  cudaStream_t s_run[2] = {p->io_streams[1], can_res ? p->io_streams[2] : p->io_streams[1]};
   cudaEvent_t* up_done = &p->io_events[0];    // [2] y slot filled
-  cudaEvent_t* run_done = &p->io_events[2];   // [2] x slot filled
-  cudaEvent_t* y_free = &p->io_events[4];     // [2] y slot consumed
-  cudaEvent_t* x_free = &p->io_events[6];     // [2] x slot drained
+  cudaEvent_t* run_done = &p->io_events[2];   // [2] x slot filled (= y slot consumed)
+  cudaEvent_t* x_free = &p->io_events[4];     // [2] x slot drained
+  cudaEvent_t diag_ready = p->io_events[6];
   double* d_diag = reinterpret_cast<double*>(base + off_d);
   double* d_dx = d_diag + diag_n;
   mga_admm_outputs outs{};
   if (want_diag) {
     outs.diag = d_diag;
     outs.dx_sum = d_dx;
-    MGA_CUDA(cudaMemsetAsync(d_diag, 0, (diag_n + dx_n) * sizeof(double), s_run));
+    MGA_CUDA(cudaMemsetAsync(d_diag, 0, (diag_n + dx_n) * sizeof(double), s_run[0]));
+    MGA_CUDA(cudaEventRecord(diag_ready, s_run[0]));
+    if (s_run[1] != s_run[0]) MGA_CUDA(cudaStreamWaitEvent(s_run[1], diag_ready, 0));
   }
   for (int64_t c = 0; c < nchunk; ++c) {
     const int slot = (int)(c & 1);
     const int64_t b0 = c * chunk, nb = std::min(chunk, B - b0);
     char* dy = base + off_y + (size_t)slot * chunk * y_win;
     char* dx = base + off_x + (size_t)slot * chunk * x_win;
-    if (c >= 2) MGA_CUDA(cudaStreamWaitEvent(s_up, y_free[slot], 0));
+    if (c >= 2) MGA_CUDA(cudaStreamWaitEvent(s_up, run_done[slot], 0));
     MGA_CUDA(cudaMemcpyAsync(dy, static_cast<const char*>(y_host) + (size_t)b0 * y_win, (size_t)nb * y_win,
                              cudaMemcpyHostToDevice, s_up));
     MGA_CUDA(cudaEventRecord(up_done[slot], s_up));
-    MGA_CUDA(cudaStreamWaitEvent(s_run, up_done[slot], 0));
-    if (c >= 2) MGA_CUDA(cudaStreamWaitEvent(s_run, x_free[slot], 0));
+    MGA_CUDA(cudaStreamWaitEvent(s_run[slot], up_done[slot], 0));
+    if (c >= 2) MGA_CUDA(cudaStreamWaitEvent(s_run[slot], x_free[slot], 0));
     // diagnostics accumulate across chunks (the kernels add into diag / dx_sum)
+    p->res_slot = slot;
     rc = mga_admm_solve(p, prm, dy, y_rows, nullptr, dx, nb, dtype, n_outer, max_cg, -1.0, -1.0, t_mean, t_var,
-                        want_diag | 2, &outs, mode, s_run);
+                        want_diag | 2, &outs, mode, s_run[slot]);
+    p->res_slot = 0;
     if (rc) { cudaDeviceSynchronize(); return rc; }
-    MGA_CUDA(cudaEventRecord(run_done[slot], s_run));
-    MGA_CUDA(cudaEventRecord(y_free[slot], s_run));
+    MGA_CUDA(cudaEventRecord(run_done[slot], s_run[slot]));
     MGA_CUDA(cudaStreamWaitEvent(s_dn, run_done[slot], 0));
     MGA_CUDA(cudaMemcpyAsync(static_cast<char*>(x_host) + (size_t)b0 * x_win, dx, (size_t)nb * x_win,
                              cudaMemcpyDeviceToHost, s_dn));
     MGA_CUDA(cudaEventRecord(x_free[slot], s_dn));
   }
+  cudaStream_t s_run0 = s_run[0], s_run1 = s_run[1];
+  MGA_CUDA(cudaStreamSynchronize(s_run0));
+  MGA_CUDA(cudaStreamSynchronize(s_run1));
   if (want_diag) {
-    MGA_CUDA(cudaStreamSynchronize(s_run));
     if (diag_host) MGA_CUDA(cudaMemcpy(diag_host, d_diag, diag_n * sizeof(double), cudaMemcpyDeviceToHost));
     if (dx_sum_host) MGA_CUDA(cudaMemcpy(dx_sum_host, d_dx, dx_n * sizeof(double), cudaMemcpyDeviceToHost));
   }
   MGA_CUDA(cudaStreamSynchronize(s_dn));
-  MGA_CUDA(cudaStreamSynchronize(s_run));
   return MGA_OK;
 }
 

@@ -811,10 +811,10 @@ inline int launch_res(mga_plan* p, ResArgs& a, const ResGeom& geo, cudaStream_t 
   const size_t smem = a.state_in_smem ? with_state : core;
   int64_t grid = std::min<int64_t>(a.B, (int64_t)occ * p->sm_count);
   if (!a.state_in_smem) {
-    const size_t need = (size_t)grid * geo.state_bytes;
-    int rc = ensure_workspace(p, p->ws, need);
+    const size_t per_launch = (size_t)grid * geo.state_bytes;      // two launches may be in flight (res_slot)
+    int rc = ensure_workspace(p, p->ws, 2 * (size_t)occ * p->sm_count * geo.state_bytes);
     if (rc) return rc;
-    a.scratch = static_cast<float*>(p->ws.base);
+    a.scratch = reinterpret_cast<float*>(static_cast<char*>(p->ws.base) + (size_t)(p->res_slot & 1) * per_launch);
   }
   a.next_window = p->r_counters + (p->r_counter_next++ % mga_plan::kCounters) * 32;
   MGA_CUDA(cudaMemsetAsync(a.next_window, 0, sizeof(int), st));
