@@ -275,8 +275,8 @@ def main():
 
     # ---- end to end through the public API with host buffers ("e2e")
     blk.mode = args.mode
-    for _ in range(3):
-        blk.combined_loop(y_pin, print_info=False)
+    for _ in range(3):      # keeps the previous result alive like the timed loop does (two pinned blocks get cached)
+        x_host = blk.combined_loop(y_pin, print_info=False)
     barrier()
     e2e_steps = max(10, args.steps)
     e2e_ms = []
@@ -341,36 +341,44 @@ def main():
             rhs = torch.rand(Bc, T_LEN, N_NODES, 1, generator=g).to(dev)
             xw = torch.zeros_like(rhs)
             res = {}
-            for sysname in ("x", "zu"):
-                def solve():
-                    _cabi.check(L.mga_cg_solve(plan.handle, _cabi.SYS[sysname], C.byref(prm), _cabi.ptr(rhs),
-                                               _cabi.ptr(xw), None, Bc, _cabi.MGA_F32, N_CG, -1.0, None, None, None,
-                                               stream.cuda_stream))
-                for _ in range(3):
-                    xw.zero_()
-                    solve()
-                torch.cuda.synchronize(dev)
-                reps, tot = 5, 0.0
-                for _ in range(reps):
-                    xw.zero_()
-                    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    a.record(stream)
-                    solve()
-                    b.record(stream)
+            for impl, cgmode in (("streaming", "streaming"), ("resident", "auto")):
+                _cabi.check(L.mga_plan_set_cg_mode(plan.handle, _cabi.MODE[cgmode]))
+                res[impl] = {}
+                for sysname in ("x", "zu"):
+                    def solve():
+                        _cabi.check(L.mga_cg_solve(plan.handle, _cabi.SYS[sysname], C.byref(prm), _cabi.ptr(rhs),
+                                                   _cabi.ptr(xw), None, Bc, _cabi.MGA_F32, N_CG, -1.0, None, None, None,
+                                                   stream.cuda_stream))
+                    for _ in range(3):
+                        xw.zero_()
+                        solve()
                     torch.cuda.synchronize(dev)
-                    tot += a.elapsed_time(b)
-                ms = tot / reps
-                per_it = cg_iter_bytes_per_point(sysname)
-                init_b = 32.0 if sysname == "x" else 20.0
-                gbs = (per_it * N_CG + init_b) * n / (ms * 1e-3) / 1e9
-                res[sysname] = {"ms_per_solve": ms, "ms_per_iter": ms / (N_CG + 1), "achieved": gbs,
-                                "frac": gbs / peak, "bytes_per_point_per_iter": per_it}
-            line["cg_iter_streaming"] = {"batch": Bc, "unit": "GB/s", "peak": peak, "vector_mb": n * 4 / 1e6,
-                                         "systems": res,
-                                         "note": "mga_cg_solve, 10 fixed iterations, vectors exceed L2"}
+                    reps, tot = 5, 0.0
+                    for _ in range(reps):
+                        xw.zero_()
+                        flush.fill_(1)
+                        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                        a.record(stream)
+                        solve()
+                        b.record(stream)
+                        torch.cuda.synchronize(dev)
+                        tot += a.elapsed_time(b)
+                    ms = tot / reps
+                    per_it = cg_iter_bytes_per_point(sysname)
+                    init_b = 32.0 if sysname == "x" else 20.0
+                    gbs = (per_it * N_CG + init_b) * n / (ms * 1e-3) / 1e9
+                    res[impl][sysname] = {"ms_per_solve": ms, "ms_per_iter": ms / (N_CG + 1), "achieved": gbs,
+                                          "frac": gbs / peak, "bytes_per_point_per_iter": per_it}
+            _cabi.check(L.mga_plan_set_cg_mode(plan.handle, _cabi.MODE["auto"]))
+            line["cg_iter"] = {"batch": Bc, "unit": "GB/s (algorithmic bytes / time)", "peak": peak,
+                               "vector_mb": n * 4 / 1e6, "impl": res,
+                               "note": "mga_cg_solve, 10 fixed iterations, vectors exceed L2, L2 flushed. 'streaming': one "
+                                       "fused kernel per CG phase, vectors in HBM (the path of windows too large for one "
+                                       "CTA). 'resident': one launch per solve, one window per CTA, rhs/x0 read once - its "
+                                       "real HBM traffic is 12 B/pt/solve, so the algorithmic rate exceeds the HBM peak"}
             del rhs, xw
         except Exception as e:  # the headline line must still be printed
-            line["cg_iter_streaming"] = {"error": str(e)[:200]}
+            line["cg_iter"] = {"error": str(e)[:200]}
 
     # ---- CPU baseline on the host cores (rank 0, N = 1 only; bounded sample)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -156,6 +156,12 @@ int mga_cg_solve(mga_plan* plan, int system, const mga_params* prm, const void* 
                  const void* mask_first, int64_t B, int dtype, int max_iter, double tol,
                  int32_t* iters_out, void* alpha_out, void* beta_out, void* stream);
 
+/* Which implementation mga_cg_solve uses (mga_mode; default MGA_MODE_AUTO): with a fixed iteration count
+ * (tol <= 0), no mask and a resident-eligible plan the whole solve runs in ONE launch, one window per CTA,
+ * iterates in registers / shared memory (rhs and x0 read once, x written once); otherwise one fused kernel
+ * per CG phase over vectors in HBM.  MGA_MODE_STREAMING forces the latter (benchmarks of the HBM path). */
+int mga_plan_set_cg_mode(mga_plan* plan, int mode);
+
 /* ---- initial_guess (ADMM.py:766-781): y (B,t_in,N) -> x (B,T,N).  t_mean / t_var are the
  * float32-rounded mean(t) and mean(t^2)-mean(t)^2 the reference computes on the host. */
 int mga_initial_guess(mga_plan* plan, const void* y, void* x, int64_t B, int dtype,

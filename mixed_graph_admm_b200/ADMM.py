@@ -353,6 +353,10 @@ class ADMM_algorithm():
         iters = C.c_int32(-1)
         plan, prm = self._plan(), self._params()
         with torch.cuda.device(self.device):
+            # mode 'streaming' keeps the CG vectors in HBM; otherwise a fixed-iteration solve of a window
+            # that fits one CTA runs in a single launch (include/mga.h: mga_plan_set_cg_mode)
+            _cabi.check(_cabi.lib().mga_plan_set_cg_mode(
+                plan.handle, _cabi.MODE["streaming"] if self.mode == "streaming" else _cabi.MODE["auto"]))
             _cabi.check(_cabi.lib().mga_cg_solve(plan.handle, _cabi.SYS[system], C.byref(prm), _cabi.ptr(rhs),
                                                  _cabi.ptr(x), _cabi.ptr(md), B, _cabi.dtype_id(rhs.dtype), n_it,
                                                  float(self.CG_tol), C.byref(iters), _cabi.ptr(alpha),

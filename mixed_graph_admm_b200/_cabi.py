@@ -28,7 +28,7 @@ DIAG_COLS = 12
 ERR_INVALID, ERR_INDEX, ERR_CUDA, ERR_UNSUPPORTED, ERR_NONFINITE = -1, -2, -3, -4, -5
 
 EXPORTS = [
-    "mga_plan_create", "mga_plan_destroy", "mga_plan_resident_eligible", "mga_plan_info", "mga_apply",
+    "mga_plan_create", "mga_plan_destroy", "mga_plan_resident_eligible", "mga_plan_info", "mga_plan_set_cg_mode", "mga_apply",
     "mga_cg_solve", "mga_initial_guess", "mga_rhs_x", "mga_dual_ascent", "mga_prox_phi_dual", "mga_phi_direct",
     "mga_admm_solve", "mga_admm_solve_host", "mga_knn_build", "mga_schedule_selfcheck", "mga_launch_count", "mga_last_error", "mga_version",
 ]
@@ -82,6 +82,7 @@ def lib():
         L.mga_plan_destroy.restype = None
         L.mga_plan_resident_eligible.argtypes = [vp, C.c_int]
         L.mga_plan_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+        L.mga_plan_set_cg_mode.argtypes = [vp, C.c_int]
         L.mga_apply.argtypes = [vp, C.c_int, C.POINTER(Params), vp, vp, vp, i64, C.c_int, vp]
         L.mga_cg_solve.argtypes = [vp, C.c_int, C.POINTER(Params), vp, vp, vp, i64, C.c_int, C.c_int, dbl,
                                    C.POINTER(i32), vp, vp, vp]

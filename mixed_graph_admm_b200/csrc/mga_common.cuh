@@ -63,6 +63,7 @@ struct mga_plan {
   size_t pinned_bytes = 0;
   cudaStream_t io_streams[4] = {nullptr, nullptr, nullptr, nullptr};    // upload, run slot 0, run slot 1, download
   cudaEvent_t io_events[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  int cg_mode = MGA_MODE_AUTO;       // mga_plan_set_cg_mode
   int res_slot = 0;                  // which half of the resident kernel's parking scratch the next launch uses
                                      // (the host entry point runs two chunk solves concurrently)
   // host copies of the tables
@@ -144,6 +145,8 @@ int stream_admm(mga_plan*, const mga_params*, const void* y, int y_rows, const v
 // resident mode (mga_resident.cu)
 bool resident_eligible(const mga_plan*, int dtype);
 int resident_smem_bytes(const mga_plan*, int* threads);
+int resident_cg(mga_plan*, int system, const mga_params*, const void* rhs, void* x, int64_t B, int n_cg, void* alpha,
+                void* beta, cudaStream_t st);
 int resident_admm(mga_plan*, const mga_params*, const void* y, void* x_out, int64_t B, int n_outer, int n_cg,
                   double t_mean, double t_var, int want_diag, const mga_admm_outputs* outs, cudaStream_t st);
 

@@ -456,8 +456,24 @@ int mga_cg_solve(mga_plan* p, int system, const mga_params* prm, const void* rhs
     set_error("mga_cg_solve: bad argument");
     return MGA_ERR_INVALID;
   }
+  // fixed iteration count, forecasting operator, a window that fits one CTA: the whole solve in one launch
+  const bool can_res = tol <= 0 && !mask_first && max_iter > 0 && prm->ablation == MGA_ABL_NONE && resident_eligible(p, dtype);
+  if (p->cg_mode == MGA_MODE_RESIDENT && !can_res) {
+    set_error("mga_cg_solve: resident mode needs fp32, tol <= 0, no mask, ablation None and a resident-eligible plan");
+    return MGA_ERR_UNSUPPORTED;
+  }
+  if (p->cg_mode != MGA_MODE_STREAMING && can_res) {
+    if (iters_out) *iters_out = -1;          // ran all iterations: "not converged" in the reference's terms (ADMM.py:368)
+    return resident_cg(p, system, prm, rhs, x, B, max_iter, alpha, beta, (cudaStream_t)stream);
+  }
   return stream_cg(p, system, prm, rhs, x, mask_first, B, dtype, max_iter, tol, iters_out, alpha, beta,
                    (cudaStream_t)stream);
+}
+
+int mga_plan_set_cg_mode(mga_plan* p, int mode) {
+  if (!p || mode < MGA_MODE_AUTO || mode > MGA_MODE_RESIDENT) { set_error("mga_plan_set_cg_mode: bad argument"); return MGA_ERR_INVALID; }
+  p->cg_mode = mode;
+  return MGA_OK;
 }
 
 int mga_admm_solve(mga_plan* p, const mga_params* prm, const void* y, int y_rows, const void* mask, void* x_out,

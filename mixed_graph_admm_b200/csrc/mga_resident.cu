@@ -10,6 +10,10 @@ namespace mga {
 MGA_DECL(1, 4) MGA_DECL(1, 6) MGA_DECL(1, 8) MGA_DECL(1, 10) MGA_DECL(2, 4) MGA_DECL(2, 6) MGA_DECL(2, 8) MGA_DECL(2, 10)
 MGA_DECL(3, 4) MGA_DECL(3, 6) MGA_DECL(3, 8) MGA_DECL(3, 10)
 #undef MGA_DECL
+#define MGA_DECL(CH, K) int resident_cg_launch_##CH##_##K(mga_plan*, ResArgs&, const CgArgs&, const ResGeom&, cudaStream_t);
+MGA_DECL(1, 4) MGA_DECL(1, 6) MGA_DECL(1, 8) MGA_DECL(1, 10) MGA_DECL(2, 4) MGA_DECL(2, 6) MGA_DECL(2, 8) MGA_DECL(2, 10)
+MGA_DECL(3, 4) MGA_DECL(3, 6) MGA_DECL(3, 8) MGA_DECL(3, 10)
+#undef MGA_DECL
 
 constexpr int kResMaxT = 24;
 constexpr int kResMaxK = 10;    // slots per forward table after self links and pads are dropped
@@ -51,18 +55,52 @@ static int pick(mga_plan* p, ResArgs& a, const ResGeom& geo, cudaStream_t st) {
   return MGA_ERR_UNSUPPORTED;
 }
 
+static void fill_tables(const mga_plan* p, const ResGeom& geo, ResArgs& a) {
+  const GraphDev& g = p->g;
+  a.N = g.N; a.T = g.T; a.t_in = g.t_in; a.q1 = g.q1; a.nnz = g.nnz;
+  a.NT = geo.NT; a.S = geo.S; a.TP = geo.TP;
+  a.kd = p->r_kd; a.ku = p->r_ku;
+  a.w_self = p->r_w_self;
+  a.perm = p->r_perm; a.nbr_d = p->r_nbr_d; a.d_w = p->r_w_d; a.nbr_u = p->r_nbr_u; a.u_w = p->r_w_u;
+  a.ell_ptr = p->r_ell_ptr; a.ell_ent = reinterpret_cast<const int2*>(p->r_ell_ent); a.ell_total = p->r_ell_total;
+}
+
+// CG_solver for one system, fixed iteration count, x_inout holds x0 / the solution (ADMM.py:329-368)
+int resident_cg(mga_plan* p, int system, const mga_params* m, const void* rhs, void* x, int64_t B, int n_cg,
+                void* alpha, void* beta, cudaStream_t st) {
+  ResGeom geo;
+  if (!geometry(p, &geo)) { set_error("resident: shape does not fit"); return MGA_ERR_UNSUPPORTED; }
+  ResArgs a{};
+  fill_tables(p, geo, a);
+  a.B = B; a.n_cg = n_cg;
+  CgArgs g{};
+  g.system = system; g.n_cg = n_cg;
+  g.rhs = static_cast<const float*>(rhs);
+  g.x = static_cast<float*>(x);
+  g.alpha = static_cast<float*>(alpha);
+  g.beta = static_cast<float*>(beta);
+  if (g.alpha && !g.beta) g.alpha = nullptr;
+  if (system == MGA_SYS_X) { g.a = (float)((m->rho_u + m->rho_d) / 2); g.c = (float)(m->rho / 2); }
+  else if (system == MGA_SYS_ZU) { g.a = (float)(m->rho_u / 2); g.c = (float)m->mu_u; }
+  else { g.a = (float)(m->rho_d / 2); g.c = (float)m->mu_d2; }
+  const int kk = geo.Kt;
+#define MGA_CASE(C_, K_) if (geo.CH == C_ && kk == K_) return resident_cg_launch_##C_##_##K_(p, a, g, geo, st);
+  MGA_CASE(1, 4) MGA_CASE(1, 6) MGA_CASE(1, 8) MGA_CASE(1, 10) MGA_CASE(2, 4) MGA_CASE(2, 6) MGA_CASE(2, 8) MGA_CASE(2, 10)
+  MGA_CASE(3, 4) MGA_CASE(3, 6) MGA_CASE(3, 8) MGA_CASE(3, 10)
+#undef MGA_CASE
+  set_error("resident: no instantiation for this (CH, K)");
+  return MGA_ERR_UNSUPPORTED;
+}
+
 int resident_admm(mga_plan* p, const mga_params* m, const void* y, void* x_out, int64_t B, int n_outer, int n_cg,
                   double t_mean, double t_var, int diag_flags, const mga_admm_outputs* outs, cudaStream_t st) {
   const GraphDev& g = p->g;
   ResArgs a{};
-  a.N = g.N; a.T = g.T; a.t_in = g.t_in; a.n_outer = n_outer; a.n_cg = n_cg; a.q1 = g.q1; a.nnz = g.nnz;
   ResGeom geo;
   if (!geometry(p, &geo)) { set_error("resident: shape does not fit"); return MGA_ERR_UNSUPPORTED; }
-  a.NT = geo.NT; a.S = geo.S; a.TP = geo.TP;
-  a.B = B; a.kd = p->r_kd; a.ku = p->r_ku;
-  a.w_self = p->r_w_self;
-  a.perm = p->r_perm; a.nbr_d = p->r_nbr_d; a.d_w = p->r_w_d; a.nbr_u = p->r_nbr_u; a.u_w = p->r_w_u;
-  a.ell_ptr = p->r_ell_ptr; a.ell_ent = reinterpret_cast<const int2*>(p->r_ell_ent); a.ell_total = p->r_ell_total;
+  fill_tables(p, geo, a);
+  a.n_outer = n_outer; a.n_cg = n_cg;
+  a.B = B;
   a.y = static_cast<const float*>(y);
   a.x_out = static_cast<float*>(x_out);
   a.out[ST_ZU] = static_cast<float*>(outs->zu);

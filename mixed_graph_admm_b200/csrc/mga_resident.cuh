@@ -30,8 +30,7 @@
 // Registers are the scarce resource (12 lattice points per thread x {x, r, p, Ap, accumulators}):
 // the seven ADMM state vectors are parked between uses — in shared memory when that does not cost
 // residency, else in a per-CTA L2-resident scratch — and re-read where needed instead of being
-// kept live across a solve; with MGA_RES_XPARK=1 the CG iterate x is parked in a private
-// shared-memory row as well.  HBM traffic per window is y in, x out (+ optional iterates /
+// kept live across a solve.  HBM traffic per window is y in, x out (+ optional iterates /
 // diagnostics).
 //
 // A persistent grid (CTAs/SM x SMs) takes windows from an atomic counter; CTAs never exchange
@@ -45,9 +44,6 @@
 
 #ifndef MGA_RES_TAB_SMEM
 #define MGA_RES_TAB_SMEM 1
-#endif
-#ifndef MGA_RES_XPARK
-#define MGA_RES_XPARK 0
 #endif
 #ifndef MGA_RES_MINB      // CTAs per SM the <= 320-thread instantiations are compiled for
 #define MGA_RES_MINB 2
@@ -119,9 +115,6 @@ struct Ctx {
   int steps;                 // in-list steps of this thread's warp (padded with zero-weight entries)
   float* pbuf;
   float* qbuf;
-#if MGA_RES_XPARK
-  float* xrow;               // private parking row of the CG iterate
-#endif
   uint32_t ent;              // shared address of this lane's first in-list entry; stride 256 B:
                              //   (shared address of qbuf[src][0], weight bits)
   uint32_t t0b;              // t0 * 4
@@ -289,9 +282,6 @@ struct Ctx {
                                      float* beta_out, int64_t B) {
     float p[TS], ap[TS];
     apply<SYS>(x, ap, a, c);
-#if MGA_RES_XPARK
-    put(xrow - own, x);     // xrow is this thread's row; put() adds `own`
-#endif
     float loc = 0.f;
 #pragma unroll
     for (int k = 0; k < TS; ++k) {
@@ -307,20 +297,9 @@ struct Ctx {
       for (int k = 0; k < TS; ++k) loc += p[k] * ap[k];
       const float alpha = rr / bsum(loc);
       loc = 0.f;
-#if MGA_RES_XPARK
-#pragma unroll
-      for (int cc = 0; cc < CH; ++cc) {
-        float4 g = *reinterpret_cast<float4*>(xrow + 4 * cc);
-        g.x = g.x + alpha * p[4 * cc]; g.y = g.y + alpha * p[4 * cc + 1];
-        g.z = g.z + alpha * p[4 * cc + 2]; g.w = g.w + alpha * p[4 * cc + 3];
-        *reinterpret_cast<float4*>(xrow + 4 * cc) = g;
-      }
-#endif
 #pragma unroll
       for (int k = 0; k < TS; ++k) {
-#if !MGA_RES_XPARK
         x[k] = x[k] + alpha * p[k];
-#endif
         r[k] = r[k] - alpha * ap[k];
         loc += r[k] * r[k];
       }
@@ -334,9 +313,6 @@ struct Ctx {
 #pragma unroll
       for (int k = 0; k < TS; ++k) p[k] = r[k] + beta * p[k];
     }
-#if MGA_RES_XPARK
-    get(xrow - own, x);
-#endif
   }
 };
 
@@ -346,91 +322,146 @@ __device__ __forceinline__ float soft_thr(float s, float d) {
   return sg * u * (float)(u > 0.f);   // ADMM.py:407-408
 }
 
+// Per-CTA setup shared by the kernels of this file: carve shared memory, fill the tables with absolute
+// shared addresses, clear the staging buffers.  Ends with a barrier.
+template <int CH, int K>
+struct Cta {
+  Ctx<CH, K> c;
+  int i, t0, orig;
+  bool active;
+  float* pbuf; float* qbuf; float* red; float* dred; float* st_smem;
+
+  __device__ __forceinline__ void init(const ResArgs& a, unsigned char* smem_raw) {
+    constexpr int TS = 4 * CH;
+    const int N = a.N, TP = a.TP;
+    const int rows = (N + 8) * TP;
+    pbuf = reinterpret_cast<float*>(smem_raw);
+    qbuf = pbuf + rows;
+    red = qbuf + rows;                                // 64 floats + the next-window slot (68 with padding)
+    dred = red + 68;                                  // MGA_DIAG_COLS x 32 floats
+    int2* ent = reinterpret_cast<int2*>(dred + MGA_DIAG_COLS * 32);
+    float* nxt = reinterpret_cast<float*>(ent + a.ell_total + 64);      // + 2 spare steps for the look-ahead
+#if MGA_RES_TAB_SMEM
+    int2* tabd = reinterpret_cast<int2*>(nxt);        // K x (S * NT), slot-major, one column per thread
+    int2* tabu = tabd + K * a.S * a.NT;               // K x (S * NT)
+    nxt = reinterpret_cast<float*>(tabu + K * a.S * a.NT);
+#endif
+    st_smem = nxt;
+    const int s = threadIdx.x / a.NT;
+    i = threadIdx.x - s * a.NT;
+    active = i < N;
+    t0 = s * TS;
+
+    c.t0 = t0; c.T = a.T; c.t_in = a.t_in;
+    c.has_next = (s + 1 < a.S);
+    c.has_prev = (s > 0);
+    c.own = (active ? i : N) * TP + t0;     // inactive lanes park on the zero row (they only ever write zeros)
+    c.pbuf = pbuf; c.qbuf = qbuf; c.red = red; c.red_sel = 0;
+    const uint32_t pb = smem_addr(pbuf), qb = smem_addr(qbuf);
+    c.t0b = (uint32_t)t0 * 4u;
+#if MGA_RES_TAB_SMEM
+    const int ncol = a.S * a.NT;
+    c.NTB = ncol * 8; c.tabd = smem_addr(tabd + threadIdx.x); c.tabu = smem_addr(tabu + threadIdx.x);
+#endif
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      int nb = N;
+      float w = 0.f;
+      if (active && j < a.kd) { nb = a.nbr_d[i * a.kd + j]; w = a.d_w[i * a.kd + j]; }
+#if MGA_RES_TAB_SMEM
+      tabd[j * ncol + threadIdx.x] = make_int2((int)(pb + (uint32_t)(nb * TP + t0) * 4u), __float_as_int(w));
+#else
+      c.nd[j] = pb + (uint32_t)(nb * TP + t0) * 4u;
+      c.wd[j] = w;
+#endif
+    }
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      int nb = N;
+      float w = 0.f;
+      if (active && j < a.ku) { nb = a.nbr_u[i * a.ku + j]; w = a.u_w[i * a.ku + j]; }
+#if MGA_RES_TAB_SMEM
+      tabu[j * ncol + threadIdx.x] = make_int2((int)(pb + (uint32_t)(nb * TP + t0) * 4u), __float_as_int(w));
+#else
+      c.nu[j] = pb + (uint32_t)(nb * TP + t0) * 4u;
+      c.wu[j] = w;
+#endif
+    }
+    c.wself = active ? a.w_self[i] : 0.f;
+    {
+      const int wn = i >> 5;     // warp of this node row (the same for every slab)
+      const int first = a.ell_ptr[wn];
+      c.steps = a.ell_ptr[wn + 1] - first;
+      c.ent = smem_addr(ent + (size_t)first * 32 + (i & 31));
+    }
+    for (int e = threadIdx.x; e < a.ell_total + 64; e += blockDim.x) {
+      int2 en = make_int2(N, 0);                 // spare steps: a zero row, zero weight
+      if (e < a.ell_total) en = a.ell_ent[e];
+      ent[e] = make_int2((int)(qb + (uint32_t)(en.x * TP) * 4u), en.y);
+    }
+    orig = active ? a.perm[i] : 0;   // this thread's node in the caller's numbering
+    for (int k = threadIdx.x; k < 2 * rows; k += blockDim.x) pbuf[k] = 0.f;
+    for (int k = threadIdx.x; k < 64; k += blockDim.x) red[k] = 0.f;     // bsum() relies on zeros beyond the warp count
+    __syncthreads();
+  }
+};
+
+// CG_solver (ADMM.py:329-368) on its own, fixed iteration count, one window per CTA: rhs and the warm
+// start come from HBM once, every iteration runs out of registers and shared memory, x goes back once
+// (12 B per lattice point and SOLVE instead of 48 B per point and ITERATION).
+struct CgArgs {
+  int system, n_cg;
+  const float* rhs;
+  float* x;
+  float* alpha; float* beta;   // (n_cg, B) or NULL
+  float a, c;                  // diagonal and operator coefficients of the system
+};
+
+template <int CH, int K, int MAXT, int MINB>
+__global__ void __launch_bounds__(MAXT, MINB) k_cg_resident(const ResArgs a, const CgArgs g) {
+  constexpr int TS = 4 * CH;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Cta<CH, K> cta;
+  cta.init(a, smem_raw);
+  Ctx<CH, K>& c = cta.c;
+  const int N = a.N, T = a.T, t0 = cta.t0;
+  int& s_next = *reinterpret_cast<int*>(cta.red + 64);
+  for (int64_t b = blockIdx.x; b < a.B;) {
+    float x[TS], r[TS];
+#pragma unroll
+    for (int k = 0; k < TS; ++k) {
+      const bool ok = cta.active && t0 + k < T;
+      const size_t at = ((size_t)b * T + t0 + k) * N + cta.orig;
+      x[k] = ok ? g.x[at] : 0.f;
+      r[k] = ok ? g.rhs[at] : 0.f;
+    }
+    float* al = g.alpha ? g.alpha + b : nullptr;
+    float* be = g.beta ? g.beta + b : nullptr;
+    if (g.system == MGA_SYS_X) c.template cg<MGA_SYS_X>(x, r, g.a, g.c, g.n_cg, al, be, a.B);
+    else if (g.system == MGA_SYS_ZU) c.template cg<MGA_SYS_ZU>(x, r, g.a, g.c, g.n_cg, al, be, a.B);
+    else c.template cg<MGA_SYS_ZD>(x, r, g.a, g.c, g.n_cg, al, be, a.B);
+    if (cta.active) {
+#pragma unroll
+      for (int k = 0; k < TS; ++k)
+        if (t0 + k < T) g.x[((size_t)b * T + t0 + k) * N + cta.orig] = x[k];
+    }
+    if (threadIdx.x == 0) s_next = atomicAdd(a.next_window, 1);
+    __syncthreads();
+    b = (int64_t)gridDim.x + s_next;
+  }
+}
+
 template <int CH, int K, int MAXT, int MINB>
 __global__ void __launch_bounds__(MAXT, MINB) k_admm_resident(const ResArgs a) {
   constexpr int TS = 4 * CH;
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  Cta<CH, K> cta;
+  cta.init(a, smem_raw);
+  Ctx<CH, K>& c = cta.c;
   const int N = a.N, T = a.T, TP = a.TP, t_in = a.t_in;
-  const int rows = (N + 8) * TP;
-  float* pbuf = reinterpret_cast<float*>(smem_raw);
-  float* qbuf = pbuf + rows;
-  float* red = qbuf + rows;                         // 64 floats + the next-window slot (68 with padding)
-  float* dred = red + 68;                           // MGA_DIAG_COLS x 32 floats
-  int2* ent = reinterpret_cast<int2*>(dred + MGA_DIAG_COLS * 32);
-  float* nxt = reinterpret_cast<float*>(ent + a.ell_total + 64);      // + 2 spare steps for the look-ahead
-#if MGA_RES_TAB_SMEM
-  int2* tabd = reinterpret_cast<int2*>(nxt);        // K x (S * NT), slot-major, one column per thread
-  int2* tabu = tabd + K * a.S * a.NT;               // K x (S * NT)
-  nxt = reinterpret_cast<float*>(tabu + K * a.S * a.NT);
-#endif
-#if MGA_RES_XPARK
-  float* xbuf = nxt;                                // (N + 1) x TP
-  nxt += rows;
-#endif
-  float* st_smem = nxt;
-  const int s = threadIdx.x / a.NT;
-  const int i = threadIdx.x - s * a.NT;
-  const bool active = i < N;
-  const int t0 = s * TS;
-
-  Ctx<CH, K> c;
-  c.t0 = t0; c.T = T; c.t_in = t_in;
-  c.has_next = (s + 1 < a.S);
-  c.has_prev = (s > 0);
-  c.own = (active ? i : N) * TP + t0;     // inactive lanes park on the zero row (they only ever write zeros)
-  c.pbuf = pbuf; c.qbuf = qbuf; c.red = red; c.red_sel = 0;
-#if MGA_RES_XPARK
-  c.xrow = xbuf + c.own;
-#endif
-  const uint32_t pb = smem_addr(pbuf), qb = smem_addr(qbuf);
-  c.t0b = (uint32_t)t0 * 4u;
-#if MGA_RES_TAB_SMEM
-  const int ncol = a.S * a.NT;
-  c.NTB = ncol * 8; c.tabd = smem_addr(tabd + threadIdx.x); c.tabu = smem_addr(tabu + threadIdx.x);
-#endif
-#pragma unroll
-  for (int j = 0; j < K; ++j) {
-    int nb = N;
-    float w = 0.f;
-    if (active && j < a.kd) { nb = a.nbr_d[i * a.kd + j]; w = a.d_w[i * a.kd + j]; }
-#if MGA_RES_TAB_SMEM
-    tabd[j * ncol + threadIdx.x] = make_int2((int)(pb + (uint32_t)(nb * TP + t0) * 4u), __float_as_int(w));
-#else
-    c.nd[j] = pb + (uint32_t)(nb * TP + t0) * 4u;
-    c.wd[j] = w;
-#endif
-  }
-#pragma unroll
-  for (int j = 0; j < K; ++j) {
-    int nb = N;
-    float w = 0.f;
-    if (active && j < a.ku) { nb = a.nbr_u[i * a.ku + j]; w = a.u_w[i * a.ku + j]; }
-#if MGA_RES_TAB_SMEM
-    tabu[j * ncol + threadIdx.x] = make_int2((int)(pb + (uint32_t)(nb * TP + t0) * 4u), __float_as_int(w));
-#else
-    c.nu[j] = pb + (uint32_t)(nb * TP + t0) * 4u;
-    c.wu[j] = w;
-#endif
-  }
-  c.wself = active ? a.w_self[i] : 0.f;
-  {
-    const int wn = i >> 5;     // warp of this node row (the same for every slab)
-    const int first = a.ell_ptr[wn];
-    c.steps = a.ell_ptr[wn + 1] - first;
-    c.ent = smem_addr(ent + (size_t)first * 32 + (i & 31));
-  }
-  for (int e = threadIdx.x; e < a.ell_total + 64; e += blockDim.x) {
-    int2 en = make_int2(N, 0);                 // spare steps: a zero row, zero weight
-    if (e < a.ell_total) en = a.ell_ent[e];
-    ent[e] = make_int2((int)(qb + (uint32_t)(en.x * TP) * 4u), en.y);
-  }
-  const int orig = active ? a.perm[i] : 0;   // this thread's node in the caller's numbering
-  for (int k = threadIdx.x; k < 2 * rows; k += blockDim.x) pbuf[k] = 0.f;
-  for (int k = threadIdx.x; k < 64; k += blockDim.x) red[k] = 0.f;     // bsum() relies on zeros beyond the warp count
-#if MGA_RES_XPARK
-  for (int k = threadIdx.x; k < rows; k += blockDim.x) xbuf[k] = 0.f;
-#endif
-  __syncthreads();
+  const int i = cta.i, t0 = cta.t0, orig = cta.orig;
+  const bool active = cta.active;
+  float* pbuf = cta.pbuf; float* qbuf = cta.qbuf; float* red = cta.red; float* dred = cta.dred; float* st_smem = cta.st_smem;
 
   // ---- parked ADMM state: [v][node * TP + t] as 128-bit chunks, in shared memory or in this CTA's slice
   // of an L2-resident scratch (same layout: a warp reads 32 consecutive 48-byte rows)
@@ -778,9 +809,6 @@ inline bool res_geometry(const GraphDev& g, int kd_eff, int ku_eff, int ell_tota
 #if MGA_RES_TAB_SMEM
     r.core_bytes += (size_t)(2 * Kt) * r.threads * 8;
 #endif
-#if MGA_RES_XPARK
-    r.core_bytes += rows * 4;
-#endif
     r.state_bytes = (size_t)ST_COUNT * g.N * r.TP * 4;
     *out = r;
     return true;
@@ -824,6 +852,30 @@ inline int launch_res(mga_plan* p, ResArgs& a, const ResGeom& geo, cudaStream_t 
   kern<<<(unsigned)grid, geo.threads, smem, st>>>(a);
   MGA_LAUNCH_CHECK("k_admm_resident");
   return MGA_OK;
+}
+
+template <int CH, int K, int MAXT, int MINB>
+inline int launch_res_cg(mga_plan* p, ResArgs& a, const CgArgs& g, const ResGeom& geo, cudaStream_t st) {
+  auto kern = k_cg_resident<CH, K, MAXT, MINB>;
+  int occ = 0;
+  MGA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, p->max_smem_optin));
+  MGA_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, geo.threads, geo.core_bytes));
+  if (occ < 1) { set_error("resident CG kernel does not fit on an SM"); return MGA_ERR_UNSUPPORTED; }
+  const int64_t grid = std::min<int64_t>(a.B, (int64_t)occ * p->sm_count);
+  a.state_in_smem = 1;
+  a.next_window = p->r_counters + (p->r_counter_next++ % mga_plan::kCounters) * 32;
+  MGA_CUDA(cudaMemsetAsync(a.next_window, 0, sizeof(int), st));
+  kern<<<(unsigned)grid, geo.threads, geo.core_bytes, st>>>(a, g);
+  MGA_LAUNCH_CHECK("k_cg_resident");
+  return MGA_OK;
+}
+
+template <int CH, int K>
+inline int pick_threads_cg(mga_plan* p, ResArgs& a, const CgArgs& g, const ResGeom& geo, cudaStream_t st) {
+  if (geo.threads <= 192) return launch_res_cg<CH, K, 192, (MGA_RES_MINB > 1 ? 3 : 1)>(p, a, g, geo, st);
+  if (geo.threads <= 320) return launch_res_cg<CH, K, 320, MGA_RES_MINB>(p, a, g, geo, st);
+  if (geo.threads <= 512) return launch_res_cg<CH, K, 512, 1>(p, a, g, geo, st);
+  return launch_res_cg<CH, K, 1024, 1>(p, a, g, geo, st);
 }
 
 template <int CH, int K>

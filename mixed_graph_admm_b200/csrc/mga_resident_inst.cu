@@ -13,4 +13,7 @@ namespace mga {
 int MGA_CAT(resident_launch_, MGA_CH, MGA_K)(mga_plan* p, ResArgs& a, const ResGeom& geo, cudaStream_t st) {
   return pick_threads<MGA_CH, MGA_K>(p, a, geo, st);
 }
+int MGA_CAT(resident_cg_launch_, MGA_CH, MGA_K)(mga_plan* p, ResArgs& a, const CgArgs& g, const ResGeom& geo, cudaStream_t st) {
+  return pick_threads_cg<MGA_CH, MGA_K>(p, a, g, geo, st);
+}
 }  // namespace mga

@@ -165,6 +165,38 @@ def test_cg_solver_api_against_oracle():
         assert al.shape == (it, 3)            # B > 1 converged: (iters, B) instead of the reference's crash (Q2)
 
 
+@pytest.mark.parametrize("name", ["pems04_f32", "pems08_f32", "tiny_f32"])
+def test_cg_solver_resident_single_launch(name):
+    """Fixed-iteration CG_solver in fp32 on a window that fits one CTA: the single-launch resident kernel
+    against the oracle's CG (same recurrence, torch CPU) and against the streaming kernels."""
+    from oracle import admm_oracle as O
+    g = Golden(name)
+    og, prm = oracle_from_golden(g)
+    gen = torch.Generator().manual_seed(7)
+    B, T, N = 5, g.ctor["T"], g.meta["n_nodes"]
+    rhs = torch.rand(B, T, N, 1, generator=gen)
+    x0 = torch.rand(B, T, N, 1, generator=gen)
+    for sysname, ofn in [("LHS_x", lambda v: O.lhs_x(og, prm, v)), ("LHS_zu", lambda v: O.lhs_zu(og, prm, v)),
+                         ("LHS_zd", lambda v: O.lhs_zd(og, prm, v))]:
+        out = {}
+        for mode in ("auto", "streaming"):
+            blk = solver_from_golden(g, mode=mode)
+            blk.max_CG_iter, blk.CG_tol = 8, -1.0
+            from mixed_graph_admm_b200 import _cabi
+            l0 = _cabi.lib().mga_launch_count()
+            x, it, al, be = blk.CG_solver(getattr(blk, sysname), rhs, x0)
+            out[mode] = (x, al, be, _cabi.lib().mga_launch_count() - l0)
+            assert it == -1 and isinstance(al, list) and len(al) == 8 and al[0].shape == (B,)
+        xo, ito, alo, beo = O.cg(ofn, rhs, x0, max_iter=8, tol=-1.0)
+        assert out["auto"][3] == 1, "the resident CG solve is one kernel launch"
+        assert out["streaming"][3] > 8
+        for mode in out:
+            assert rel_err(out[mode][0], xo) <= 1e-5, (name, sysname, mode, rel_err(out[mode][0], xo))
+            assert max_rel(out[mode][0], xo) <= 2e-5
+            np.testing.assert_allclose(torch.stack(out[mode][1])[:3].numpy(), torch.stack(alo)[:3].numpy(), rtol=1e-4)
+            np.testing.assert_allclose(torch.stack(out[mode][2])[:3].numpy(), torch.stack(beo)[:3].numpy(), rtol=1e-3)
+
+
 def test_cg_known_answer_foreign_operator():
     """CG_script.py:49-50 through CG_solver with a caller-supplied operator."""
     g = Golden("anchor5")
