@@ -71,7 +71,10 @@ typedef enum { MGA_SYS_X = 0, MGA_SYS_ZU = 1, MGA_SYS_ZD = 2 } mga_system;
 typedef enum {
   MGA_MODE_AUTO = 0,     /* resident when eligible, else streaming */
   MGA_MODE_STREAMING = 1,/* state in HBM/L2, one fused kernel per CG phase */
-  MGA_MODE_RESIDENT = 2  /* one CTA per window, CG vectors in registers, gathered vectors in SMEM */
+  MGA_MODE_RESIDENT = 2, /* one CTA per window, CG vectors in registers, gathered vectors in SMEM */
+  MGA_MODE_STREAMING_POINT = 3 /* streaming, always the general one-thread-per-lattice-point kernels (every dtype,
+                                  mask, ablation, temporal variant); MGA_MODE_STREAMING picks the chunked node-major
+                                  kernels when the call is fp32, forecasting, fixed-iteration, ablation None */
 } mga_mode;
 
 /* The graph tensors ADMM_algorithm.__init__ leaves behind (ADMM.py:25-52).  HOST pointers; the

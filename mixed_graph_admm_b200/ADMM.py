@@ -73,7 +73,7 @@ class ADMM_algorithm():
     only with 1 head (reference ADMM.py:11-14)
 
     Extra keyword-only arguments (not in the reference): ``device`` (default: current CUDA
-    device), ``mode`` ('auto' | 'streaming' | 'resident'), ``verbose`` (print the sigma lines
+    device), ``mode`` ('auto' | 'streaming' | 'streaming_point' | 'resident'), ``verbose`` (print the sigma lines
     the reference prints from graph construction).
     '''
 
@@ -356,7 +356,7 @@ class ADMM_algorithm():
             # mode 'streaming' keeps the CG vectors in HBM; otherwise a fixed-iteration solve of a window
             # that fits one CTA runs in a single launch (include/mga.h: mga_plan_set_cg_mode)
             _cabi.check(_cabi.lib().mga_plan_set_cg_mode(
-                plan.handle, _cabi.MODE["streaming"] if self.mode == "streaming" else _cabi.MODE["auto"]))
+                plan.handle, _cabi.MODE[self.mode] if self.mode.startswith("streaming") else _cabi.MODE["auto"]))
             _cabi.check(_cabi.lib().mga_cg_solve(plan.handle, _cabi.SYS[system], C.byref(prm), _cabi.ptr(rhs),
                                                  _cabi.ptr(x), _cabi.ptr(md), B, _cabi.dtype_id(rhs.dtype), n_it,
                                                  float(self.CG_tol), C.byref(iters), _cabi.ptr(alpha),

@@ -21,7 +21,7 @@ TEMPORAL_GRAPH, TEMPORAL_LINE, TEMPORAL_BAND = 0, 1, 2
 ABLATION = {"None": 0, "DGTV": 1, "DGLR": 2, "UT": 3}
 OP = {"Lu": 0, "Ldr": 1, "Ldr_T": 2, "cLdr": 3, "LHS_x": 4, "LHS_zu": 5, "LHS_zd": 6}
 SYS = {"x": 0, "zu": 1, "zd": 2}
-MODE = {"auto": 0, "streaming": 1, "resident": 2}
+MODE = {"auto": 0, "streaming": 1, "resident": 2, "streaming_point": 3}
 DIAG_COLS = 12
 (DIAG_DX2, DIAG_X_ZU2, DIAG_DZU2, DIAG_GLR, DIAG_RECOVER2, DIAG_PHI_LDX2, DIAG_DPHI2, DIAG_DGTV, DIAG_X_ZD2,
  DIAG_DZD2, DIAG_DGLR, DIAG_NONFINITE) = range(12)

@@ -44,6 +44,17 @@ struct GraphDev {
   const float* band_w;   // (T, skip, N) BAND only
 };
 
+// Device view of the tables of the chunked streaming path (mga_stream2.cu): nodes renumbered in
+// reverse-Cuthill-McKee order, time-invariant weights, vectors node-major v[b][n][4 * C4].
+struct Graph2 {
+  int N, T, t_in, C4;      // C4 = ceil(T / 4) chunks of 4 time steps per node row
+  int kd, ku, q1;
+  const int* perm;         // perm[internal] = caller's node id
+  const int* nbr_d; const float* w_d;     // (N, kd) internal ids, -1 = no neighbour
+  const int* nbr_u; const float* w_u;     // (N, ku)
+  const int* in_ptr; const int* in_src; const float* in_w;   // in-list of L_d^T (CSR, entries in scatter order)
+};
+
 struct Workspace {
   void* base = nullptr;
   size_t bytes = 0;
@@ -63,6 +74,8 @@ struct mga_plan {
   size_t pinned_bytes = 0;
   cudaStream_t io_streams[4] = {nullptr, nullptr, nullptr, nullptr};    // upload, run slot 0, run slot 1, download
   cudaEvent_t io_events[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  bool has_s2 = false;               // tables of the chunked streaming path
+  mga::Graph2 g2{};
   int cg_mode = MGA_MODE_AUTO;       // mga_plan_set_cg_mode
   int res_slot = 0;                  // which half of the resident kernel's parking scratch the next launch uses
                                      // (the host entry point runs two chunk solves concurrently)
@@ -142,6 +155,12 @@ int stream_cg(mga_plan*, int system, const mga_params*, const void* rhs, void* x
 int stream_admm(mga_plan*, const mga_params*, const void* y, int y_rows, const void* mask, void* x_out, int64_t B,
                 int dtype, int n_outer, int max_cg, double cg_tol, double admm_tol, double t_mean, double t_var,
                 int want_diag, const mga_admm_outputs* outs, cudaStream_t st);
+// chunked streaming path (mga_stream2.cu): fp32, forecasting mode, fixed iteration counts, ablation None
+bool stream2_eligible(const mga_plan*, int dtype);
+int stream2_cg(mga_plan*, int system, const mga_params*, const void* rhs, void* x, int64_t B, int n_cg, void* alpha,
+               void* beta, cudaStream_t st);
+int stream2_admm(mga_plan*, const mga_params*, const void* y, void* x_out, int64_t B, int n_outer, int max_cg, double t_mean,
+                 double t_var, int want_diag, const mga_admm_outputs* outs, cudaStream_t st);
 // resident mode (mga_resident.cu)
 bool resident_eligible(const mga_plan*, int dtype);
 int resident_smem_bytes(const mga_plan*, int* threads);

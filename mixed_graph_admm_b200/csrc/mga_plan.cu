@@ -257,6 +257,42 @@ int mga_plan_create(const mga_graph_desc* d, int device, mga_plan** out) {
     p->r_counters = static_cast<int*>(ctr);
     p->has_sched = true;
   }
+  // chunked streaming path: time-invariant tables in reverse-Cuthill-McKee node order
+  if (d->temporal != MGA_TEMPORAL_BAND && g.u_wT == 1 && g.d_wT == 1) {
+    std::vector<int> perm = graph_rcm_order(N, g.kd, p->h_nbr_d.data(), g.ku, p->h_nbr_u.data());
+    std::vector<int> inv(N);
+    for (int k = 0; k < N; ++k) inv[perm[k]] = k;
+    auto remap = [&](const std::vector<int>& nbr, const std::vector<float>& w, int K, std::vector<int>& o_n, std::vector<float>& o_w) {
+      o_n.resize((size_t)N * K);
+      o_w.resize((size_t)N * K);
+      for (int k = 0; k < N; ++k)
+        for (int j = 0; j < K; ++j) {
+          const int nb = nbr[(size_t)perm[k] * K + j];
+          o_n[(size_t)k * K + j] = nb >= 0 ? inv[nb] : -1;
+          o_w[(size_t)k * K + j] = w[(size_t)perm[k] * K + j];
+        }
+    };
+    std::vector<int> nd, nu, ip(N + 1, 0), is;
+    std::vector<float> wd, wu, iw;
+    remap(p->h_nbr_d, p->h_d_w, g.kd, nd, wd);
+    remap(p->h_nbr_u, p->h_u_w, g.ku, nu, wu);
+    for (int k = 0; k < N; ++k) {
+      const int o = perm[k];
+      for (int e = p->h_csr_ptr[o]; e < p->h_csr_ptr[o + 1]; ++e) { is.push_back(inv[p->h_csr_src[e]]); iw.push_back(p->h_csr_w[e]); }
+      ip[k + 1] = (int)is.size();
+    }
+    Graph2& g2 = p->g2;
+    g2.N = N; g2.T = T; g2.t_in = d->t_in; g2.C4 = (T + 3) / 4; g2.kd = g.kd; g2.ku = g.ku; g2.q1 = g.q1;
+    if ((rc = upload(p, perm, &g2.perm))) return fail(rc);
+    if ((rc = upload(p, nd, &g2.nbr_d))) return fail(rc);
+    if ((rc = upload(p, wd, &g2.w_d))) return fail(rc);
+    if ((rc = upload(p, nu, &g2.nbr_u))) return fail(rc);
+    if ((rc = upload(p, wu, &g2.w_u))) return fail(rc);
+    if ((rc = upload(p, ip, &g2.in_ptr))) return fail(rc);
+    if ((rc = upload(p, is, &g2.in_src))) return fail(rc);
+    if ((rc = upload(p, iw, &g2.in_w))) return fail(rc);
+    p->has_s2 = true;
+  }
   p->pinned_bytes = 1 << 16;
   e = cudaMallocHost(&p->pinned, p->pinned_bytes);
   if (e != cudaSuccess) { int c = cuda_fail(e, "cudaMallocHost"); return fail(c); }
@@ -462,16 +498,21 @@ int mga_cg_solve(mga_plan* p, int system, const mga_params* prm, const void* rhs
     set_error("mga_cg_solve: resident mode needs fp32, tol <= 0, no mask, ablation None and a resident-eligible plan");
     return MGA_ERR_UNSUPPORTED;
   }
-  if (p->cg_mode != MGA_MODE_STREAMING && can_res) {
+  if (p->cg_mode != MGA_MODE_STREAMING && p->cg_mode != MGA_MODE_STREAMING_POINT && can_res) {
     if (iters_out) *iters_out = -1;          // ran all iterations: "not converged" in the reference's terms (ADMM.py:368)
     return resident_cg(p, system, prm, rhs, x, B, max_iter, alpha, beta, (cudaStream_t)stream);
+  }
+  if (p->cg_mode != MGA_MODE_STREAMING_POINT && tol <= 0 && !mask_first && max_iter > 0 && prm->ablation == MGA_ABL_NONE &&
+      stream2_eligible(p, dtype)) {
+    if (iters_out) *iters_out = -1;
+    return stream2_cg(p, system, prm, rhs, x, B, max_iter, alpha, beta, (cudaStream_t)stream);
   }
   return stream_cg(p, system, prm, rhs, x, mask_first, B, dtype, max_iter, tol, iters_out, alpha, beta,
                    (cudaStream_t)stream);
 }
 
 int mga_plan_set_cg_mode(mga_plan* p, int mode) {
-  if (!p || mode < MGA_MODE_AUTO || mode > MGA_MODE_RESIDENT) { set_error("mga_plan_set_cg_mode: bad argument"); return MGA_ERR_INVALID; }
+  if (!p || mode < MGA_MODE_AUTO || mode > MGA_MODE_STREAMING_POINT) { set_error("mga_plan_set_cg_mode: bad argument"); return MGA_ERR_INVALID; }
   p->cg_mode = mode;
   return MGA_OK;
 }
@@ -494,8 +535,10 @@ int mga_admm_solve(mga_plan* p, const mga_params* prm, const void* y, int y_rows
               "weights, N <= 512, T <= 24, kd <= 9");
     return MGA_ERR_UNSUPPORTED;
   }
-  if (mode != MGA_MODE_STREAMING && can_res)
+  if (mode != MGA_MODE_STREAMING && mode != MGA_MODE_STREAMING_POINT && can_res)
     return resident_admm(p, prm, y, x_out, B, n_outer, max_cg, t_mean, t_var, want_diag, outs, (cudaStream_t)stream);
+  if (mode != MGA_MODE_STREAMING_POINT && forecast && fixed && prm->ablation == MGA_ABL_NONE && stream2_eligible(p, dtype))
+    return stream2_admm(p, prm, y, x_out, B, n_outer, max_cg, t_mean, t_var, want_diag, outs, (cudaStream_t)stream);
   return stream_admm(p, prm, y, y_rows, mask, x_out, B, dtype, n_outer, max_cg, cg_tol, admm_tol, t_mean, t_var,
                      want_diag, outs, (cudaStream_t)stream);
 }
@@ -527,7 +570,8 @@ int mga_admm_solve_host(mga_plan* p, const mga_params* prm, const void* y_host, 
   for (auto& ev : p->io_events) if (!ev) MGA_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   // Resident mode: two chunk solves may run concurrently (one stream per slot), so the tail of one chunk's
   // persistent grid overlaps the head of the next.  Streaming mode shares one workspace: one run stream.
-  const bool can_res = mode != MGA_MODE_STREAMING && prm->ablation == MGA_ABL_NONE && resident_eligible(p, dtype);
+  const bool can_res = mode != MGA_MODE_STREAMING && mode != MGA_MODE_STREAMING_POINT && prm->ablation == MGA_ABL_NONE &&
+                       resident_eligible(p, dtype);
   cudaStream_t s_up = p->io_streams[0], s_dn = p->io_streams[3];
   cudaStream_t s_run[2] = {p->io_streams[1], can_res ? p->io_streams[2] : p->io_streams[1]};
   cudaEvent_t* up_done = &p->io_events[0];    // [2] y slot filled

@@ -63,6 +63,18 @@ static std::vector<int> rcm_order(int N, const std::vector<std::vector<int>>& ad
   return order;   // order[new] = old
 }
 
+// node order for the streaming path: reverse Cuthill-McKee on the symmetrised union of both tables
+std::vector<int> graph_rcm_order(int N, int kd, const int* nbr_d, int ku, const int* nbr_u) {
+  std::vector<std::vector<int>> adj(N);
+  auto link = [&](int a, int b) { if (a != b && a >= 0 && b >= 0) { adj[a].push_back(b); adj[b].push_back(a); } };
+  for (int i = 0; i < N; ++i) {
+    for (int j = 0; j < kd; ++j) link(i, nbr_d[(size_t)i * kd + j]);
+    for (int j = 0; j < ku; ++j) link(i, nbr_u[(size_t)i * ku + j]);
+  }
+  for (auto& a : adj) { std::sort(a.begin(), a.end()); a.erase(std::unique(a.begin(), a.end()), a.end()); }
+  return rcm_order(N, adj);
+}
+
 namespace {
 struct Cand {
   int node;     // node id (original numbering before placement, internal after), or N for the zero row

@@ -20,6 +20,9 @@ struct ResidentSchedule {
   std::vector<float> ell_w;
 };
 
+// order[new] = old: reverse Cuthill-McKee on the symmetrised union of the two neighbour tables (-1 = none)
+std::vector<int> graph_rcm_order(int N, int kd, const int* nbr_d, int ku, const int* nbr_u);
+
 void build_resident_schedule(int N, int kd, const int* nbr_d, const float* d_w, int ku, const int* nbr_u,
                              const float* u_w, const int* csr_ptr, const int* csr_src, const float* csr_w,
                              ResidentSchedule* out);

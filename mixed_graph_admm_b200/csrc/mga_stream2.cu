@@ -1,0 +1,635 @@
+// Streaming mode, fast path ("v2"): for windows too large for one CTA (T = 288, 20 000 nodes) in the
+// unrolled (fixed iteration count) forecasting mode.  mga_stream.cu stays the general path (fp64, masks,
+// ablations, banded line graph, time-varying weights, tolerance mode).
+//
+// What differs from mga_stream.cu
+//  * Layout.  All vectors the solver owns are NODE-major per window, v[b][n][TP4] (TP4 = T rounded up to
+//    4, pads kept at zero), nodes in reverse-Cuthill-McKee order.  One thread owns one 16-byte chunk =
+//    4 consecutive time steps of one node; consecutive threads own consecutive chunks, so every own
+//    access is a coalesced 128-bit load/store, and a gather of "neighbour n', same 4 time steps" is a
+//    128-bit load whose 32-byte sector is fully used by the lanes next to it (they want the next chunks
+//    of the same neighbour row).  The reference's (B, T, N) layout is converted once on the way in
+//    (k2_init / k2_import) and once on the way out (k2_export).
+//  * The shift (as in the resident kernel).  L_d reads p[t-1] and L_d^T reads q[t+1] (ADMM.py:171,
+//    200-208); q is stored shifted, qs[t] = q[t+1], so both gathers are chunk-aligned; only the thread's
+//    own row is touched off-chunk (one scalar each).
+//  * No recomputation at the gather: p' = r + beta p gets its own elementwise kernel (12 B/pt), because
+//    gathering r AND p at every neighbour doubles the L2 traffic, which is what bounds these kernels.
+//
+// Per CG iteration of the x / z_d systems: k2_pupdate (12 B/pt), k2_ldr_shift (p' -> qs, 8 B/pt),
+// k2_ldrt_lhs (p', qs -> Ap, <p',Ap>, 12 B/pt), k2_xr (24 B/pt) = 56 B/pt of HBM traffic against the
+// 48 B/pt the algorithm needs; z_u: 12 + 8 + 24 = 44 against 40.  Gathers are served by L1/L2: a window
+// (<= 1.9 MB per vector) is far smaller than the 126 MB L2.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+
+#include "mga_common.cuh"
+
+namespace mga {
+
+constexpr int kB2 = 256;
+
+__device__ __forceinline__ float4 ld4(const float* v, size_t chunk) { return reinterpret_cast<const float4*>(v)[chunk]; }
+__device__ __forceinline__ void st4(float* v, size_t chunk, float4 a) { reinterpret_cast<float4*>(v)[chunk] = a; }
+
+struct Chunk {
+  int64_t b;       // window
+  int n, c;        // node (internal), chunk of 4 time steps
+  size_t g;        // global chunk index
+  bool ok;
+};
+
+__device__ __forceinline__ Chunk locate2(const Graph2& g, int tiles) {
+  Chunk k;
+  const int Q = g.N * g.C4;
+  k.b = blockIdx.x / tiles;
+  const int q = (blockIdx.x % tiles) * kB2 + threadIdx.x;
+  k.ok = q < Q;
+  const int qq = k.ok ? q : 0;
+  k.n = qq / g.C4;
+  k.c = qq - k.n * g.C4;
+  k.g = (size_t)k.b * Q + qq;
+  return k;
+}
+
+template <typename Tv>
+__device__ __forceinline__ void block_add(Tv v, double* slot) {
+  __shared__ Tv red[32];
+  const Tv tot = block_sum<Tv>(v, red);
+  if (threadIdx.x == 0) atomicAdd(slot, (double)tot);
+}
+
+// ---- layout conversion ----------------------------------------------------------------------------
+// (B, T, N) caller order -> node-major internal
+__global__ void __launch_bounds__(kB2) k2_import(Graph2 g, int tiles, const float* __restrict__ src, float* __restrict__ dst) {
+  const Chunk k = locate2(g, tiles);
+  if (!k.ok) return;
+  const int o = g.perm[k.n];
+  float v[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int t = 4 * k.c + j;
+    v[j] = t < g.T ? src[((size_t)k.b * g.T + t) * g.N + o] : 0.f;
+  }
+  st4(dst, k.g, make_float4(v[0], v[1], v[2], v[3]));
+}
+
+// node-major internal -> (B, T, N) caller order
+__global__ void __launch_bounds__(kB2) k2_export(Graph2 g, int tiles, const float* __restrict__ src, float* __restrict__ dst) {
+  const Chunk k = locate2(g, tiles);
+  if (!k.ok) return;
+  const int o = g.perm[k.n];
+  const float4 a = ld4(src, k.g);
+  const float v[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int t = 4 * k.c + j;
+    if (t < g.T) dst[((size_t)k.b * g.T + t) * g.N + o] = v[j];
+  }
+}
+
+// initial_guess (ADMM.py:766-781) + initial state (ADMM.py:537-544); one thread per (window, node)
+__global__ void __launch_bounds__(kB2) k2_init(Graph2 g, int64_t B, const float* __restrict__ y, float* __restrict__ x,
+                                               float* __restrict__ zu, float* __restrict__ zd, float* __restrict__ gu,
+                                               float* __restrict__ gd, float* __restrict__ gam, float t_mean, float t_var) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * g.N) return;
+  const int64_t b = idx / g.N;
+  const int n = (int)(idx - b * g.N);
+  const float* yw = y + b * (int64_t)g.t_in * g.N + g.perm[n];
+  float sy = 0.f, sty = 0.f;
+  for (int t = 0; t < g.t_in; ++t) {
+    const float v = yw[(size_t)t * g.N];
+    sy += v;
+    sty += (float)t * v;
+  }
+  const float my = sy / (float)g.t_in, mty = sty / (float)g.t_in;
+  const float w = (mty - t_mean * my) / t_var;
+  const float c = my - w * t_mean;
+  const size_t row = (size_t)idx * g.C4;
+  for (int cc = 0; cc < g.C4; ++cc) {
+    float v[4], tenth[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int t = 4 * cc + j;
+      v[j] = t < g.T ? (t < g.t_in ? yw[(size_t)t * g.N] : w * (float)t + c) : 0.f;
+      tenth[j] = t < g.T ? 0.1f : 0.f;
+    }
+    const float4 a = make_float4(v[0], v[1], v[2], v[3]), d = make_float4(tenth[0], tenth[1], tenth[2], tenth[3]);
+    st4(x, row + cc, a); st4(zu, row + cc, a); st4(zd, row + cc, a);
+    st4(gu, row + cc, d); st4(gd, row + cc, d); st4(gam, row + cc, d);
+  }
+}
+
+// ---- operator pieces ------------------------------------------------------------------------------
+// sum_j w_j v[nbr_j][chunk c] over a forward ELL table (rows of `stride` slots, -1 = no neighbour)
+__device__ __forceinline__ float4 fwd_gather(const int* __restrict__ nbr, const float* __restrict__ w, int slots,
+                                             const float* __restrict__ v, size_t win_chunk0, int n, int c, int C4) {
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int* nb = nbr + (size_t)n * slots;
+  const float* ww = w + (size_t)n * slots;
+  for (int j = 0; j < slots; ++j) {
+    const int m = nb[j];
+    if (m < 0) continue;
+    const float wj = ww[j];
+    const float4 a = ld4(v, win_chunk0 + (size_t)m * C4 + c);
+    acc.x += wj * a.x; acc.y += wj * a.y; acc.z += wj * a.z; acc.w += wj * a.w;
+  }
+  return acc;
+}
+
+// qs = shifted L_d v:  qs[t] = q[t+1] = v[t+1] - sum_j w_j v_nbr[t]  (0 for t+1 >= T)   ADMM.py:166-177
+__global__ void __launch_bounds__(kB2) k2_ldr_shift(Graph2 g, int tiles, const float* __restrict__ v, float* __restrict__ qs) {
+  const Chunk k = locate2(g, tiles);
+  if (!k.ok) return;
+  const size_t w0 = (size_t)k.b * g.N * g.C4;
+  const float4 own = ld4(v, k.g);
+  const float nxt = (k.c + 1 < g.C4) ? v[(k.g + 1) * 4] : 0.f;
+  const float4 acc = fwd_gather(g.nbr_d, g.w_d, g.kd, v, w0, k.n, k.c, g.C4);
+  const int t = 4 * k.c;
+  float4 o;
+  o.x = (t + 1 < g.T) ? own.y - acc.x : 0.f;
+  o.y = (t + 2 < g.T) ? own.z - acc.y : 0.f;
+  o.z = (t + 3 < g.T) ? own.w - acc.z : 0.f;
+  o.w = (t + 4 < g.T) ? nxt - acc.w : 0.f;
+  st4(qs, k.g, o);
+}
+
+// father sum over the in-list: f[t] = sum w qs_src[t]  (ADMM.py:200-209 as a gather, scatter order kept)
+__device__ __forceinline__ float4 inlist_gather(const Graph2& g, const float* __restrict__ qs, size_t win_chunk0, int n, int c) {
+  float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int e0 = g.in_ptr[n], e1 = g.in_ptr[n + 1];
+  for (int e = e0; e < e1; ++e) {
+    const float w = g.in_w[e];
+    const float4 a = ld4(qs, win_chunk0 + (size_t)g.in_src[e] * g.C4 + c);
+    f.x += w * a.x; f.y += w * a.y; f.z += w * a.z; f.w += w * a.w;
+  }
+  return f;
+}
+
+// MODE 0: ap = A v, dot <v, ap> -> slot      (CG iteration, phase 1)
+// MODE 1: r = rhs - A v, dot <r, r> -> slot  (initial residual)
+// A = diag + c L_d^T L_d with qs = shifted L_d v already computed.  xsys: H^T H term + LHS_x's evaluation order.
+template <int MODE>
+__global__ void __launch_bounds__(kB2) k2_ldrt_lhs(Graph2 g, int tiles, const float* __restrict__ v, const float* __restrict__ qs,
+                                                   const float* __restrict__ rhs, float* __restrict__ out, double* __restrict__ slot,
+                                                   float a, float cc, int xsys) {
+  const Chunk k = locate2(g, tiles);
+  float dot = 0.f;
+  if (k.ok) {
+    const size_t w0 = (size_t)k.b * g.N * g.C4;
+    const float4 pv = ld4(v, k.g);
+    const float4 q1 = ld4(qs, k.g);
+    const float qprev = k.c > 0 ? qs[k.g * 4 - 1] : 0.f;        // q[4c] = qs[4c-1]; q[0] = 0 (ADMM.py:176)
+    const float4 f = inlist_gather(g, qs, w0, k.n, k.c);
+    const float p[4] = {pv.x, pv.y, pv.z, pv.w};
+    const float q[4] = {qprev, q1.x, q1.y, q1.z};
+    const float ff[4] = {f.x, f.y, f.z, f.w};
+    float o[4];
+    const int t0 = 4 * k.c;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int t = t0 + j;
+      const float l = q[j] - ff[j];      // row T-1: f = 0 because qs[T-1] = 0; Q1 is moot as q[0] = 0
+      float val;
+      if (xsys) val = ((t < g.t_in ? p[j] : 0.f) + a * p[j]) + cc * l;      // ADMM.py:372-379
+      else val = cc * l + a * p[j];                                          // ADMM.py:394
+      o[j] = t < g.T ? val : 0.f;
+    }
+    if (MODE == 0) {
+      st4(out, k.g, make_float4(o[0], o[1], o[2], o[3]));
+      dot = (p[0] * o[0] + p[1] * o[1]) + (p[2] * o[2] + p[3] * o[3]);
+    } else {
+      const float4 rh = ld4(rhs, k.g);
+      const float r0 = rh.x - o[0], r1 = rh.y - o[1], r2 = rh.z - o[2], r3 = rh.w - o[3];
+      st4(out, k.g, make_float4(r0, r1, r2, r3));
+      dot = (r0 * r0 + r1 * r1) + (r2 * r2 + r3 * r3);
+    }
+  }
+  block_add<float>(dot, slot + k.b);
+}
+
+// z_u system: A = c L_u + a I  (ADMM.py:389-390), same two modes
+template <int MODE>
+__global__ void __launch_bounds__(kB2) k2_lu_lhs(Graph2 g, int tiles, const float* __restrict__ v, const float* __restrict__ rhs,
+                                                 float* __restrict__ out, double* __restrict__ slot, float a, float cc) {
+  const Chunk k = locate2(g, tiles);
+  float dot = 0.f;
+  if (k.ok) {
+    const size_t w0 = (size_t)k.b * g.N * g.C4;
+    const float4 pv = ld4(v, k.g);
+    const float4 acc = fwd_gather(g.nbr_u, g.w_u, g.ku, v, w0, k.n, k.c, g.C4);
+    float4 o;
+    o.x = cc * (pv.x - acc.x) + a * pv.x;
+    o.y = cc * (pv.y - acc.y) + a * pv.y;
+    o.z = cc * (pv.z - acc.z) + a * pv.z;
+    o.w = cc * (pv.w - acc.w) + a * pv.w;    // pads: v = 0 and every gathered pad is 0
+    if (MODE == 0) {
+      st4(out, k.g, o);
+      dot = (pv.x * o.x + pv.y * o.y) + (pv.z * o.z + pv.w * o.w);
+    } else {
+      const float4 rh = ld4(rhs, k.g);
+      const float4 r = make_float4(rh.x - o.x, rh.y - o.y, rh.z - o.z, rh.w - o.w);
+      st4(out, k.g, r);
+      dot = (r.x * r.x + r.y * r.y) + (r.z * r.z + r.w * r.w);
+    }
+  }
+  block_add<float>(dot, slot + k.b);
+}
+
+// p' = r + beta p   (first iteration: p' = r).  dots: RR(k) = dots[2k], PAP(k) = dots[2k+1], each (B)
+__global__ void __launch_bounds__(kB2) k2_pupdate(Graph2 g, int tiles, int64_t B, int it, const float* __restrict__ r,
+                                                  float* __restrict__ p, const double* __restrict__ dots) {
+  const Chunk k = locate2(g, tiles);
+  if (!k.ok) return;
+  const float4 rv = ld4(r, k.g);
+  if (it == 0) { st4(p, k.g, rv); return; }
+  const float beta = (float)dots[(size_t)(2 * it) * B + k.b] / (float)dots[(size_t)(2 * it - 2) * B + k.b];   // ADMM.py:356
+  const float4 pv = ld4(p, k.g);
+  st4(p, k.g, make_float4(rv.x + beta * pv.x, rv.y + beta * pv.y, rv.z + beta * pv.z, rv.w + beta * pv.w));
+}
+
+// x += alpha p ; r -= alpha Ap ; RR(k+1) += r.r   (ADMM.py:350-355)
+__global__ void __launch_bounds__(kB2) k2_xr(Graph2 g, int tiles, int64_t B, int it, float* __restrict__ x, float* __restrict__ r,
+                                             const float* __restrict__ p, const float* __restrict__ ap, double* __restrict__ dots) {
+  const Chunk k = locate2(g, tiles);
+  float dot = 0.f;
+  if (k.ok) {
+    const float alpha = (float)dots[(size_t)(2 * it) * B + k.b] / (float)dots[(size_t)(2 * it + 1) * B + k.b];
+    const float4 xv = ld4(x, k.g), pv = ld4(p, k.g), rv = ld4(r, k.g), av = ld4(ap, k.g);
+    st4(x, k.g, make_float4(xv.x + alpha * pv.x, xv.y + alpha * pv.y, xv.z + alpha * pv.z, xv.w + alpha * pv.w));
+    const float4 rn = make_float4(rv.x - alpha * av.x, rv.y - alpha * av.y, rv.z - alpha * av.z, rv.w - alpha * av.w);
+    st4(r, k.g, rn);
+    dot = (rn.x * rn.x + rn.y * rn.y) + (rn.z * rn.z + rn.w * rn.w);
+  }
+  block_add<float>(dot, dots + (size_t)(2 * it + 2) * B + k.b);
+}
+
+__global__ void k2_coeffs(int64_t B, int iters, const double* __restrict__ dots, float* __restrict__ alpha, float* __restrict__ beta) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * iters) return;
+  const int k = (int)(idx / B);
+  const int64_t b = idx - (int64_t)k * B;
+  const float rr = (float)dots[(size_t)(2 * k) * B + b], pap = (float)dots[(size_t)(2 * k + 1) * B + b];
+  const float rrn = (float)dots[(size_t)(2 * k + 2) * B + b];
+  if (alpha) alpha[idx] = rr / pap;
+  if (beta) beta[idx] = rrn / rr;
+}
+
+// ---- elementwise steps of combined_loop ---------------------------------------------------------------
+// (L_d v)[t] for the 4 time steps of chunk (n, c): unaligned in time, scalar gathers (once per outer iteration)
+__device__ __forceinline__ void ldr_chunk(const Graph2& g, const float* __restrict__ v, size_t w0, int n, int c, const float4 own,
+                                          float (&out)[4]) {
+  const float o[4] = {own.x, own.y, own.z, own.w};
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const int* nb = g.nbr_d + (size_t)n * g.kd;
+  const float* ww = g.w_d + (size_t)n * g.kd;
+  const int t0 = 4 * c;
+  for (int j = 0; j < g.kd; ++j) {
+    const int m = nb[j];
+    if (m < 0) continue;
+    const float wj = ww[j];
+    const float* row = v + (w0 + (size_t)m * g.C4) * 4;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int t = t0 + q;
+      if (t >= 1 && t < g.T) acc[q] += wj * row[t - 1];
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int t = t0 + q;
+    out[q] = (t >= 1 && t < g.T) ? o[q] - acc[q] : 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(kB2) k2_ldr(Graph2 g, int tiles, const float* __restrict__ v, float* __restrict__ out) {
+  const Chunk k = locate2(g, tiles);
+  if (!k.ok) return;
+  float o[4];
+  ldr_chunk(g, v, (size_t)k.b * g.N * g.C4, k.n, k.c, ld4(v, k.g), o);
+  st4(out, k.g, make_float4(o[0], o[1], o[2], o[3]));
+}
+
+// RHS_x (ADMM.py:552-559): Ldr_T(gamma + rho phi)/2 + (rho_u zu + rho_d zd)/2 - (gu + gd)/2 + H^T y
+__global__ void __launch_bounds__(kB2) k2_rhs_x(Graph2 g, int tiles, const float* __restrict__ gam, const float* __restrict__ phi,
+                                                const float* __restrict__ zu, const float* __restrict__ zd,
+                                                const float* __restrict__ gu, const float* __restrict__ gd,
+                                                const float* __restrict__ y, float* __restrict__ rhs, float rho, float rho_u,
+                                                float rho_d) {
+  const Chunk k = locate2(g, tiles);
+  if (!k.ok) return;
+  const size_t w0 = (size_t)k.b * g.N * g.C4;
+  const float4 ga = ld4(gam, k.g), ph = ld4(phi, k.g);
+  const float v[4] = {ga.x + rho * ph.x, ga.y + rho * ph.y, ga.z + rho * ph.z, ga.w + rho * ph.w};
+  float f[4] = {0.f, 0.f, 0.f, 0.f};
+  const int t0 = 4 * k.c;
+  for (int e = g.in_ptr[k.n]; e < g.in_ptr[k.n + 1]; ++e) {
+    const float w = g.in_w[e];
+    const size_t row = (w0 + (size_t)g.in_src[e] * g.C4) * 4;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int t = t0 + q;
+      if (t + 1 < g.T) f[q] += w * (gam[row + t + 1] + rho * phi[row + t + 1]);
+    }
+  }
+  const float4 a = ld4(zu, k.g), b = ld4(zd, k.g), c = ld4(gu, k.g), d = ld4(gd, k.g);
+  const float zuv[4] = {a.x, a.y, a.z, a.w}, zdv[4] = {b.x, b.y, b.z, b.w};
+  const float guv[4] = {c.x, c.y, c.z, c.w}, gdv[4] = {d.x, d.y, d.z, d.w};
+  const int o = g.perm[k.n];
+  float out[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int t = t0 + q;
+    // rows of apply_op_Ldr_T: t = T-1 keeps v; t = 0 keeps the identity term only under Q1 (ADMM.py:217-223)
+    const float l = (t == g.T - 1) ? v[q] : ((t == 0 && !g.q1) ? -f[q] : v[q] - f[q]);
+    const float hty = t < g.t_in ? y[((size_t)k.b * g.t_in + t) * g.N + o] : 0.f;
+    out[q] = t < g.T ? l / 2.f + (rho_u * zuv[q] + rho_d * zdv[q]) / 2.f - (guv[q] + gdv[q]) / 2.f + hty : 0.f;
+  }
+  st4(rhs, k.g, make_float4(out[0], out[1], out[2], out[3]));
+}
+
+// RHS_zu / RHS_zd (ADMM.py:579, 587)
+__global__ void __launch_bounds__(kB2) k2_rhs_z(size_t chunks, const float* __restrict__ gz, const float* __restrict__ x,
+                                                float* __restrict__ rhs, float half_rho) {
+  const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= chunks) return;
+  const float4 g = ld4(gz, k), xv = ld4(x, k);
+  st4(rhs, k, make_float4(g.x / 2.f + half_rho * xv.x, g.y / 2.f + half_rho * xv.y, g.z / 2.f + half_rho * xv.z,
+                          g.w / 2.f + half_rho * xv.w));
+}
+
+__device__ __forceinline__ float soft2(float s, float d) {
+  const float u = fabsf(s) - d;
+  const float sg = (float)((s > 0.f) - (s < 0.f));
+  return sg * u * (float)(u > 0.f);   // ADMM.py:407-408
+}
+
+// The tail of one outer iteration in a single pass (ADMM.py:595-637): both dual ascents, phi prox, gamma
+// ascent and all diagnostics.
+__global__ void __launch_bounds__(kB2) k2_tail(Graph2 g, int tiles, int want_diag, const float* __restrict__ x,
+                                               const float* __restrict__ x_old, const float* __restrict__ zu,
+                                               const float* __restrict__ zu_old, const float* __restrict__ zd,
+                                               const float* __restrict__ zd_old, float* __restrict__ gu, float* __restrict__ gd,
+                                               float* __restrict__ gam, float* __restrict__ phi, const float* __restrict__ y,
+                                               float rho, float rho_u, float rho_d, float thr, double* __restrict__ diag,
+                                               double* __restrict__ dx_sum) {
+  const Chunk k = locate2(g, tiles);
+  float d[MGA_DIAG_COLS];
+#pragma unroll
+  for (int c = 0; c < MGA_DIAG_COLS; ++c) d[c] = 0.f;
+  if (k.ok) {
+    const size_t w0 = (size_t)k.b * g.N * g.C4;
+    const float4 xv4 = ld4(x, k.g), zu4 = ld4(zu, k.g), zd4 = ld4(zd, k.g), gu4 = ld4(gu, k.g), gd4 = ld4(gd, k.g);
+    const float4 ga4 = ld4(gam, k.g), ph4 = ld4(phi, k.g);
+    const float xv[4] = {xv4.x, xv4.y, xv4.z, xv4.w}, zuv[4] = {zu4.x, zu4.y, zu4.z, zu4.w};
+    const float zdv[4] = {zd4.x, zd4.y, zd4.z, zd4.w};
+    float guv[4] = {gu4.x, gu4.y, gu4.z, gu4.w}, gdv[4] = {gd4.x, gd4.y, gd4.z, gd4.w};
+    float gav[4] = {ga4.x, ga4.y, ga4.z, ga4.w}, phv[4] = {ph4.x, ph4.y, ph4.z, ph4.w};
+    float ldx[4];
+    ldr_chunk(g, x, w0, k.n, k.c, xv4, ldx);
+    float lux[4] = {0.f, 0.f, 0.f, 0.f}, xo[4] = {0.f, 0.f, 0.f, 0.f}, zuo[4] = {0.f, 0.f, 0.f, 0.f}, zdo[4] = {0.f, 0.f, 0.f, 0.f};
+    if (want_diag) {
+      const float4 acc = fwd_gather(g.nbr_u, g.w_u, g.ku, x, w0, k.n, k.c, g.C4);
+      lux[0] = xv[0] - acc.x; lux[1] = xv[1] - acc.y; lux[2] = xv[2] - acc.z; lux[3] = xv[3] - acc.w;
+      const float4 a = ld4(x_old, k.g), b = ld4(zu_old, k.g), c = ld4(zd_old, k.g);
+      xo[0] = a.x; xo[1] = a.y; xo[2] = a.z; xo[3] = a.w;
+      zuo[0] = b.x; zuo[1] = b.y; zuo[2] = b.z; zuo[3] = b.w;
+      zdo[0] = c.x; zdo[1] = c.y; zdo[2] = c.z; zdo[3] = c.w;
+    }
+    const int o = g.perm[k.n];
+    const int t0 = 4 * k.c;
+    int bad = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int t = t0 + q;
+      if (t >= g.T) continue;
+      guv[q] = guv[q] + rho_u * (xv[q] - zuv[q]);
+      gdv[q] = gdv[q] + rho_d * (xv[q] - zdv[q]);
+      const float ph = soft2(ldx[q] - gav[q] / rho, thr);
+      const float gn = gav[q] + rho * (ph - ldx[q]);
+      bad |= !isfinite(xv[q]) || !isfinite(zuv[q]) || !isfinite(zdv[q]) || !isfinite(ph) || !isfinite(gn);
+      if (want_diag) {
+        const float dx = xv[q] - xo[q];
+        d[MGA_DIAG_DX2] += dx * dx;
+        if (dx_sum) atomicAdd(dx_sum + (size_t)t * g.N + o, (double)dx);
+        const float a = xv[q] - zuv[q], bz = zuv[q] - zuo[q];
+        d[MGA_DIAG_X_ZU2] += a * a;
+        d[MGA_DIAG_DZU2] += bz * bz;
+        d[MGA_DIAG_GLR] += xv[q] * lux[q];
+        if (t < g.t_in) {
+          const float h = xv[q] - y[((size_t)k.b * g.t_in + t) * g.N + o];
+          d[MGA_DIAG_RECOVER2] += h * h;
+        }
+        const float e = ph - ldx[q], f = ph - phv[q];
+        d[MGA_DIAG_PHI_LDX2] += e * e;
+        d[MGA_DIAG_DPHI2] += f * f;
+        d[MGA_DIAG_DGTV] += fabsf(ldx[q]);
+        const float e2 = xv[q] - zdv[q], f2 = zdv[q] - zdo[q];
+        d[MGA_DIAG_X_ZD2] += e2 * e2;
+        d[MGA_DIAG_DZD2] += f2 * f2;
+        d[MGA_DIAG_DGLR] += ldx[q] * ldx[q];
+      }
+      phv[q] = ph;
+      gav[q] = gn;
+    }
+    d[MGA_DIAG_NONFINITE] = (float)bad;
+    st4(gu, k.g, make_float4(guv[0], guv[1], guv[2], guv[3]));
+    st4(gd, k.g, make_float4(gdv[0], gdv[1], gdv[2], gdv[3]));
+    st4(gam, k.g, make_float4(gav[0], gav[1], gav[2], gav[3]));
+    st4(phi, k.g, make_float4(phv[0], phv[1], phv[2], phv[3]));
+  }
+  __shared__ float red[MGA_DIAG_COLS][kB2 / 32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int c = 0; c < MGA_DIAG_COLS; ++c) {
+    const float v = warp_sum<float>(d[c]);
+    if (lane == 0) red[c][w] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < MGA_DIAG_COLS) {
+    float t = 0.f;
+    for (int q = 0; q < kB2 / 32; ++q) t += red[threadIdx.x][q];
+    if (t != 0.f) atomicAdd(diag + threadIdx.x, (double)t);
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------------------
+bool stream2_eligible(const mga_plan* p, int dtype) {
+  return p->has_s2 && dtype == MGA_F32;
+}
+
+struct Bufs2 {
+  float *r, *p, *ap, *qs;
+  double* dots;
+};
+
+static size_t vec_bytes2(const Graph2& g, int64_t B) { return (((size_t)B * g.N * g.C4 * 16) + 255) & ~(size_t)255; }
+static size_t dots_bytes2(int64_t B, int max_iter) { return (((size_t)(2 * max_iter + 1) * B * sizeof(double)) + 255) & ~(size_t)255; }
+
+// CG_solver (ADMM.py:329-368) with a fixed iteration count on internal-layout vectors; x holds x0 / the solution.
+static int cg2(mga_plan* p, int system, const mga_params* m, const float* rhs, float* x, int64_t B, int n_cg, float* alpha,
+               float* beta, const Bufs2& w, cudaStream_t st) {
+  const Graph2& g = p->g2;
+  const int tiles = (g.N * g.C4 + kB2 - 1) / kB2;
+  const unsigned grid = (unsigned)(B * tiles);
+  float a, c;
+  if (system == MGA_SYS_X) { a = (float)((m->rho_u + m->rho_d) / 2); c = (float)(m->rho / 2); }
+  else if (system == MGA_SYS_ZU) { a = (float)(m->rho_u / 2); c = (float)m->mu_u; }
+  else { a = (float)(m->rho_d / 2); c = (float)m->mu_d2; }
+  const int xsys = system == MGA_SYS_X;
+  MGA_CUDA(cudaMemsetAsync(w.dots, 0, (size_t)(2 * n_cg + 1) * B * sizeof(double), st));
+  // r = rhs - A x0 ; RR(0)
+  if (system == MGA_SYS_ZU) {
+    k2_lu_lhs<1><<<grid, kB2, 0, st>>>(g, tiles, x, rhs, w.r, w.dots, a, c);
+    MGA_LAUNCH_CHECK("k2_lu_lhs");
+  } else {
+    k2_ldr_shift<<<grid, kB2, 0, st>>>(g, tiles, x, w.qs);
+    MGA_LAUNCH_CHECK("k2_ldr_shift");
+    k2_ldrt_lhs<1><<<grid, kB2, 0, st>>>(g, tiles, x, w.qs, rhs, w.r, w.dots, a, c, xsys);
+    MGA_LAUNCH_CHECK("k2_ldrt_lhs");
+  }
+  for (int it = 0; it < n_cg; ++it) {
+    k2_pupdate<<<grid, kB2, 0, st>>>(g, tiles, B, it, w.r, w.p, w.dots);
+    MGA_LAUNCH_CHECK("k2_pupdate");
+    double* pap = w.dots + (size_t)(2 * it + 1) * B;
+    if (system == MGA_SYS_ZU) {
+      k2_lu_lhs<0><<<grid, kB2, 0, st>>>(g, tiles, w.p, nullptr, w.ap, pap, a, c);
+      MGA_LAUNCH_CHECK("k2_lu_lhs");
+    } else {
+      k2_ldr_shift<<<grid, kB2, 0, st>>>(g, tiles, w.p, w.qs);
+      MGA_LAUNCH_CHECK("k2_ldr_shift");
+      k2_ldrt_lhs<0><<<grid, kB2, 0, st>>>(g, tiles, w.p, w.qs, nullptr, w.ap, pap, a, c, xsys);
+      MGA_LAUNCH_CHECK("k2_ldrt_lhs");
+    }
+    k2_xr<<<grid, kB2, 0, st>>>(g, tiles, B, it, x, w.r, w.p, w.ap, w.dots);
+    MGA_LAUNCH_CHECK("k2_xr");
+  }
+  if ((alpha || beta) && n_cg > 0) {
+    const int64_t tot = B * n_cg;
+    k2_coeffs<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(B, n_cg, w.dots, alpha, beta);
+    MGA_LAUNCH_CHECK("k2_coeffs");
+  }
+  return MGA_OK;
+}
+
+static Bufs2 carve2(char* base, const Graph2& g, int64_t B, int max_iter) {
+  const size_t vec = vec_bytes2(g, B);
+  Bufs2 w;
+  w.r = reinterpret_cast<float*>(base);
+  w.p = reinterpret_cast<float*>(base + vec);
+  w.ap = reinterpret_cast<float*>(base + 2 * vec);
+  w.qs = reinterpret_cast<float*>(base + 3 * vec);
+  w.dots = reinterpret_cast<double*>(base + 4 * vec);
+  (void)max_iter;
+  return w;
+}
+
+// mga_cg_solve, fixed iteration count, caller-layout rhs / x
+int stream2_cg(mga_plan* p, int system, const mga_params* m, const void* rhs, void* x, int64_t B, int n_cg, void* alpha,
+               void* beta, cudaStream_t st) {
+  const Graph2& g = p->g2;
+  const size_t vec = vec_bytes2(g, B);
+  int rc = ensure_workspace(p, p->ws, 6 * vec + dots_bytes2(B, n_cg) + 256);
+  if (rc) return rc;
+  char* base = static_cast<char*>(p->ws.base);
+  float* rhs_i = reinterpret_cast<float*>(base);
+  float* x_i = reinterpret_cast<float*>(base + vec);
+  Bufs2 w = carve2(base + 2 * vec, g, B, n_cg);
+  const int tiles = (g.N * g.C4 + kB2 - 1) / kB2;
+  const unsigned grid = (unsigned)(B * tiles);
+  k2_import<<<grid, kB2, 0, st>>>(g, tiles, static_cast<const float*>(rhs), rhs_i);
+  MGA_LAUNCH_CHECK("k2_import");
+  k2_import<<<grid, kB2, 0, st>>>(g, tiles, static_cast<const float*>(x), x_i);
+  MGA_LAUNCH_CHECK("k2_import");
+  rc = cg2(p, system, m, rhs_i, x_i, B, n_cg, static_cast<float*>(alpha), static_cast<float*>(beta), w, st);
+  if (rc) return rc;
+  k2_export<<<grid, kB2, 0, st>>>(g, tiles, x_i, static_cast<float*>(x));
+  MGA_LAUNCH_CHECK("k2_export");
+  return MGA_OK;
+}
+
+// combined_loop (ADMM.py:528-648), forecasting mode, ablation None, fixed iteration counts
+int stream2_admm(mga_plan* p, const mga_params* prm, const void* y_, void* x_out, int64_t B, int n_outer, int max_cg,
+                 double t_mean, double t_var, int diag_flags, const mga_admm_outputs* outs, cudaStream_t st) {
+  const Graph2& g = p->g2;
+  const float* y = static_cast<const float*>(y_);
+  const bool want_diag = (diag_flags & 1) != 0, accumulate = (diag_flags & 2) != 0;
+  const size_t vec = vec_bytes2(g, B);
+  const int n_state = 12;   // x0, x1, zu0, zu1, zd0, zd1, gu, gd, gam, phi, rhs, spare
+  const size_t need = n_state * vec + 4 * vec + dots_bytes2(B, max_cg) + 512 +
+                      (size_t)std::max(n_outer, 1) * MGA_DIAG_COLS * sizeof(double);
+  int rc = ensure_workspace(p, p->ws, need);
+  if (rc) return rc;
+  char* base = static_cast<char*>(p->ws.base);
+  auto V = [&](int k) { return reinterpret_cast<float*>(base + (size_t)k * vec); };
+  float *x_cur = V(0), *x_nxt = V(1), *zu_cur = V(2), *zu_nxt = V(3), *zd_cur = V(4), *zd_nxt = V(5);
+  float *gu = V(6), *gd = V(7), *gam = V(8), *phi = V(9), *rhs = V(10);
+  Bufs2 w = carve2(base + n_state * vec, g, B, max_cg);
+  double* own_diag = reinterpret_cast<double*>(base + n_state * vec + 4 * vec + dots_bytes2(B, max_cg) + 256);
+  double* diag = outs->diag ? outs->diag : own_diag;
+  double* dx_sum = want_diag ? outs->dx_sum : nullptr;
+  if (want_diag && !accumulate) {
+    MGA_CUDA(cudaMemsetAsync(diag, 0, (size_t)n_outer * MGA_DIAG_COLS * sizeof(double), st));
+    if (dx_sum) MGA_CUDA(cudaMemsetAsync(dx_sum, 0, (size_t)n_outer * g.T * g.N * sizeof(double), st));
+  }
+  double* nf_row = own_diag;     // non-finite flag row when diagnostics are off
+  if (!want_diag) MGA_CUDA(cudaMemsetAsync(nf_row, 0, MGA_DIAG_COLS * sizeof(double), st));
+
+  const int tiles = (g.N * g.C4 + kB2 - 1) / kB2;
+  const unsigned grid = (unsigned)(B * tiles);
+  const size_t chunks = (size_t)B * g.N * g.C4;
+  const unsigned grid_c = (unsigned)((chunks + kB2 - 1) / kB2);
+  const unsigned grid_bn = (unsigned)((B * g.N + kB2 - 1) / kB2);
+  k2_init<<<grid_bn, kB2, 0, st>>>(g, B, y, x_cur, zu_cur, zd_cur, gu, gd, gam, (float)t_mean, (float)t_var);
+  MGA_LAUNCH_CHECK("k2_init");
+  k2_ldr<<<grid, kB2, 0, st>>>(g, tiles, x_cur, phi);      // phi = L_d x (ADMM.py:541)
+  MGA_LAUNCH_CHECK("k2_ldr");
+  const float rho = (float)prm->rho, rho_u = (float)prm->rho_u, rho_d = (float)prm->rho_d;
+  const float thr = (float)(prm->mu_d1 / prm->rho);
+  const size_t coef_stride = (size_t)max_cg * B;
+  const size_t vbytes = chunks * 16;
+  for (int it = 0; it < n_outer; ++it) {
+    auto coef = [&](void* basep, int s) -> float* {
+      return basep ? static_cast<float*>(basep) + ((size_t)it * 3 + s) * coef_stride : nullptr;
+    };
+    k2_rhs_x<<<grid, kB2, 0, st>>>(g, tiles, gam, phi, zu_cur, zd_cur, gu, gd, y, rhs, rho, rho_u, rho_d);
+    MGA_LAUNCH_CHECK("k2_rhs_x");
+    MGA_CUDA(cudaMemcpyAsync(x_nxt, x_cur, vbytes, cudaMemcpyDeviceToDevice, st));       // warm start (ADMM.py:571)
+    if ((rc = cg2(p, MGA_SYS_X, prm, rhs, x_nxt, B, max_cg, coef(outs->alpha, 0), coef(outs->beta, 0), w, st))) return rc;
+    k2_rhs_z<<<grid_c, kB2, 0, st>>>(chunks, gu, x_nxt, rhs, (float)(prm->rho_u / 2));
+    MGA_LAUNCH_CHECK("k2_rhs_z");
+    MGA_CUDA(cudaMemcpyAsync(zu_nxt, zu_cur, vbytes, cudaMemcpyDeviceToDevice, st));
+    if ((rc = cg2(p, MGA_SYS_ZU, prm, rhs, zu_nxt, B, max_cg, coef(outs->alpha, 1), coef(outs->beta, 1), w, st))) return rc;
+    k2_rhs_z<<<grid_c, kB2, 0, st>>>(chunks, gd, x_nxt, rhs, (float)(prm->rho_d / 2));
+    MGA_LAUNCH_CHECK("k2_rhs_z");
+    MGA_CUDA(cudaMemcpyAsync(zd_nxt, zd_cur, vbytes, cudaMemcpyDeviceToDevice, st));
+    if ((rc = cg2(p, MGA_SYS_ZD, prm, rhs, zd_nxt, B, max_cg, coef(outs->alpha, 2), coef(outs->beta, 2), w, st))) return rc;
+    double* drow = want_diag ? diag + (size_t)it * MGA_DIAG_COLS : nf_row;
+    k2_tail<<<grid, kB2, 0, st>>>(g, tiles, want_diag ? 1 : 0, x_nxt, x_cur, zu_nxt, zu_cur, zd_nxt, zd_cur, gu, gd, gam, phi,
+                                 y, rho, rho_u, rho_d, thr, drow, dx_sum ? dx_sum + (size_t)it * g.T * g.N : nullptr);
+    MGA_LAUNCH_CHECK("k2_tail");
+    std::swap(x_cur, x_nxt);
+    std::swap(zu_cur, zu_nxt);
+    std::swap(zd_cur, zd_nxt);
+    if (outs->cg_iters) { outs->cg_iters[it * 3 + 0] = -1; outs->cg_iters[it * 3 + 1] = -1; outs->cg_iters[it * 3 + 2] = -1; }
+  }
+  auto give = [&](void* dst, const float* src) -> int {
+    if (!dst) return MGA_OK;
+    k2_export<<<grid, kB2, 0, st>>>(g, tiles, src, static_cast<float*>(dst));
+    MGA_LAUNCH_CHECK("k2_export");
+    return MGA_OK;
+  };
+  if ((rc = give(x_out, x_cur))) return rc;
+  if ((rc = give(outs->zu, zu_cur))) return rc;
+  if ((rc = give(outs->zd, zd_cur))) return rc;
+  if ((rc = give(outs->gamma_u, gu))) return rc;
+  if ((rc = give(outs->gamma_d, gd))) return rc;
+  if ((rc = give(outs->phi, phi))) return rc;
+  if ((rc = give(outs->gamma, gam))) return rc;
+  if (outs->outer_done) *outs->outer_done = n_outer;
+  return MGA_OK;
+}
+
+}  // namespace mga

@@ -93,10 +93,13 @@ def test_ldr_t_quirk_q1_row0():
     np.testing.assert_allclose(lt[2], [1, 1.1, 1.2, 1.3, 1.4], atol=1e-6)
 
 
+@pytest.mark.parametrize("mode", ["streaming", "streaming_point"])
 @pytest.mark.parametrize("name", FIXED_CASES)
-def test_combined_loop_streaming_matches_reference(name):
+def test_combined_loop_streaming_matches_reference(name, mode):
+    """'streaming' = the chunked node-major kernels where the call is eligible (fp32, forecasting, fixed counts,
+    ablation None, time-invariant weights), the general kernels otherwise; 'streaming_point' = always the general ones."""
     g = Golden(name)
-    blk = solver_from_golden(g, mode="streaming")
+    blk = solver_from_golden(g, mode=mode)
     blk.keep_iterates = True
     x = blk.combined_loop(g.y.cuda(), mask=None if g.mask is None else g.mask.cuda(), print_info=False)
     assert x.is_cuda
