@@ -48,6 +48,8 @@ struct GraphDev {
 // reverse-Cuthill-McKee order, time-invariant weights, vectors node-major v[b][n][4 * C4].
 struct Graph2 {
   int N, T, t_in, C4;      // C4 = ceil(T / 4) chunks of 4 time steps per node row
+  int CB, NB, tilesN, tilesC;   // CTA tile = NB nodes x CB chunks; tiles per window = tilesN * tilesC
+  int NBt;                      // thread rows of a tile CTA: block = (CB, NBt), NBt >= NB, CB * NBt a multiple of 32
   int kd, ku, q1;
   const int* perm;         // perm[internal] = caller's node id
   const int* nbr_d; const float* w_d;     // (N, kd) internal ids, -1 = no neighbour
@@ -157,6 +159,7 @@ int stream_admm(mga_plan*, const mga_params*, const void* y, int y_rows, const v
                 int want_diag, const mga_admm_outputs* outs, cudaStream_t st);
 // chunked streaming path (mga_stream2.cu): fp32, forecasting mode, fixed iteration counts, ablation None
 bool stream2_eligible(const mga_plan*, int dtype);
+void stream2_tiling(Graph2* g);     // fills CB / NB / tilesN / tilesC for the kernels' block size
 int stream2_cg(mga_plan*, int system, const mga_params*, const void* rhs, void* x, int64_t B, int n_cg, void* alpha,
                void* beta, cudaStream_t st);
 int stream2_admm(mga_plan*, const mga_params*, const void* y, void* x_out, int64_t B, int n_outer, int max_cg, double t_mean,

@@ -283,6 +283,7 @@ int mga_plan_create(const mga_graph_desc* d, int device, mga_plan** out) {
     }
     Graph2& g2 = p->g2;
     g2.N = N; g2.T = T; g2.t_in = d->t_in; g2.C4 = (T + 3) / 4; g2.kd = g.kd; g2.ku = g.ku; g2.q1 = g.q1;
+    stream2_tiling(&g2);
     if ((rc = upload(p, perm, &g2.perm))) return fail(rc);
     if ((rc = upload(p, nd, &g2.nbr_d))) return fail(rc);
     if ((rc = upload(p, wd, &g2.w_d))) return fail(rc);

@@ -28,42 +28,74 @@
 
 namespace mga {
 
-constexpr int kB2 = 256;
+#ifndef MGA_S2_BLOCK
+#define MGA_S2_BLOCK 256
+#endif
+constexpr int kB2 = MGA_S2_BLOCK;
 
 __device__ __forceinline__ float4 ld4(const float* v, size_t chunk) { return reinterpret_cast<const float4*>(v)[chunk]; }
 __device__ __forceinline__ void st4(float* v, size_t chunk, float4 a) { reinterpret_cast<float4*>(v)[chunk] = a; }
 
 struct Chunk {
-  int64_t b;       // window
+  int b;           // window
   int n, c;        // node (internal), chunk of 4 time steps
+  int q;           // chunk index inside the window: n * C4 + c
   size_t g;        // global chunk index
   bool ok;
 };
 
-__device__ __forceinline__ Chunk locate2(const Graph2& g, int tiles) {
+// A CTA owns a 2-D tile of one window: NB consecutive nodes x CB consecutive chunks; block = (CB, NB),
+// grid = (B, tilesN, tilesC), so no thread ever divides.  Lanes run along the chunks (a quarter-warp reads
+// >= 96 contiguous bytes of one row); RCM-consecutive nodes share most of their neighbours, so the rows a
+// tile gathers are re-used from L1.
+__device__ __forceinline__ Chunk locate2(const Graph2& g) {
+  Chunk k;
+  k.b = blockIdx.x;
+  k.n = blockIdx.y * g.NB + threadIdx.y;
+  k.c = blockIdx.z * g.CB + threadIdx.x;
+  k.ok = threadIdx.y < g.NB && k.n < g.N && k.c < g.C4;
+  if (!k.ok) { k.n = 0; k.c = 0; }
+  k.q = k.n * g.C4 + k.c;
+  k.g = (size_t)k.b * (size_t)(g.N * g.C4) + k.q;
+  return k;
+}
+__device__ __forceinline__ const float4* win4(const float* v, const Graph2& g, int b) {
+  return reinterpret_cast<const float4*>(v) + (size_t)b * (size_t)(g.N * g.C4);
+}
+__device__ __forceinline__ int tid2() { return threadIdx.y * blockDim.x + threadIdx.x; }
+
+// elementwise kernels: consecutive threads own consecutive chunks of one window; grid = (B, ceil(Q / kFlat))
+constexpr int kFlat = 256;
+__device__ __forceinline__ Chunk locate_flat(const Graph2& g) {
   Chunk k;
   const int Q = g.N * g.C4;
-  k.b = blockIdx.x / tiles;
-  const int q = (blockIdx.x % tiles) * kB2 + threadIdx.x;
-  k.ok = q < Q;
-  const int qq = k.ok ? q : 0;
-  k.n = qq / g.C4;
-  k.c = qq - k.n * g.C4;
-  k.g = (size_t)k.b * Q + qq;
+  k.b = blockIdx.x;
+  k.q = blockIdx.y * kFlat + threadIdx.x;
+  k.ok = k.q < Q;
+  if (!k.ok) k.q = 0;
+  k.n = 0; k.c = 0;
+  k.g = (size_t)k.b * (size_t)Q + k.q;
   return k;
 }
 
-template <typename Tv>
-__device__ __forceinline__ void block_add(Tv v, double* slot) {
-  __shared__ Tv red[32];
-  const Tv tot = block_sum<Tv>(v, red);
-  if (threadIdx.x == 0) atomicAdd(slot, (double)tot);
+// block sum -> one double atomicAdd per CTA; only warp 0 adds up the warp partials
+__device__ __forceinline__ void block_add(float v, double* slot, int tid, int nthreads) {
+  __shared__ float red[32];
+  const int lane = tid & 31, w = tid >> 5, nw = (nthreads + 31) >> 5;
+  v = warp_sum<float>(v);
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    float t = lane < nw ? red[lane] : 0.f;
+    t = warp_sum<float>(t);
+    if (lane == 0) atomicAdd(slot, (double)t);
+  }
 }
 
 // ---- layout conversion ----------------------------------------------------------------------------
 // (B, T, N) caller order -> node-major internal
-__global__ void __launch_bounds__(kB2) k2_import(Graph2 g, int tiles, const float* __restrict__ src, float* __restrict__ dst) {
-  const Chunk k = locate2(g, tiles);
+__global__ void __launch_bounds__(kB2) k2_import(Graph2 g, const float* __restrict__ src, float* __restrict__ dst) {
+  const Chunk k = locate2(g);
   if (!k.ok) return;
   const int o = g.perm[k.n];
   float v[4];
@@ -76,8 +108,8 @@ __global__ void __launch_bounds__(kB2) k2_import(Graph2 g, int tiles, const floa
 }
 
 // node-major internal -> (B, T, N) caller order
-__global__ void __launch_bounds__(kB2) k2_export(Graph2 g, int tiles, const float* __restrict__ src, float* __restrict__ dst) {
-  const Chunk k = locate2(g, tiles);
+__global__ void __launch_bounds__(kB2) k2_export(Graph2 g, const float* __restrict__ src, float* __restrict__ dst) {
+  const Chunk k = locate2(g);
   if (!k.ok) return;
   const int o = g.perm[k.n];
   const float4 a = ld4(src, k.g);
@@ -90,7 +122,7 @@ __global__ void __launch_bounds__(kB2) k2_export(Graph2 g, int tiles, const floa
 }
 
 // initial_guess (ADMM.py:766-781) + initial state (ADMM.py:537-544); one thread per (window, node)
-__global__ void __launch_bounds__(kB2) k2_init(Graph2 g, int64_t B, const float* __restrict__ y, float* __restrict__ x,
+__global__ void __launch_bounds__(256) k2_init(Graph2 g, int64_t B, const float* __restrict__ y, float* __restrict__ x,
                                                float* __restrict__ zu, float* __restrict__ zd, float* __restrict__ gu,
                                                float* __restrict__ gd, float* __restrict__ gam, float t_mean, float t_var) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -124,29 +156,46 @@ __global__ void __launch_bounds__(kB2) k2_init(Graph2 g, int64_t B, const float*
 
 // ---- operator pieces ------------------------------------------------------------------------------
 // sum_j w_j v[nbr_j][chunk c] over a forward ELL table (rows of `stride` slots, -1 = no neighbour)
+// Gathers index the window with 32-bit arithmetic (vw = the vector's window base as float4*); four table
+// entries per trip, their indices / weights first, then the four 128-bit loads, then the FMAs.
 __device__ __forceinline__ float4 fwd_gather(const int* __restrict__ nbr, const float* __restrict__ w, int slots,
-                                             const float* __restrict__ v, size_t win_chunk0, int n, int c, int C4) {
+                                             const float4* __restrict__ vw, int n, int c, int C4) {
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  const int* nb = nbr + (size_t)n * slots;
-  const float* ww = w + (size_t)n * slots;
-  for (int j = 0; j < slots; ++j) {
+  const int* nb = nbr + n * slots;
+  const float* ww = w + n * slots;
+  int j = 0;
+  for (; j + 4 <= slots; j += 4) {
+    int m[4];
+    float wj[4];
+    float4 a[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { m[q] = nb[j + q]; wj[q] = ww[j + q]; }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) a[q] = vw[max(m[q], 0) * C4 + c];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      if (m[q] < 0) continue;       // "-1 = no neighbour" contributes nothing (quirk Q6)
+      acc.x += wj[q] * a[q].x; acc.y += wj[q] * a[q].y; acc.z += wj[q] * a[q].z; acc.w += wj[q] * a[q].w;
+    }
+  }
+  for (; j < slots; ++j) {
     const int m = nb[j];
     if (m < 0) continue;
     const float wj = ww[j];
-    const float4 a = ld4(v, win_chunk0 + (size_t)m * C4 + c);
+    const float4 a = vw[m * C4 + c];
     acc.x += wj * a.x; acc.y += wj * a.y; acc.z += wj * a.z; acc.w += wj * a.w;
   }
   return acc;
 }
 
 // qs = shifted L_d v:  qs[t] = q[t+1] = v[t+1] - sum_j w_j v_nbr[t]  (0 for t+1 >= T)   ADMM.py:166-177
-__global__ void __launch_bounds__(kB2) k2_ldr_shift(Graph2 g, int tiles, const float* __restrict__ v, float* __restrict__ qs) {
-  const Chunk k = locate2(g, tiles);
+__global__ void __launch_bounds__(kB2) k2_ldr_shift(Graph2 g, const float* __restrict__ v, float* __restrict__ qs) {
+  const Chunk k = locate2(g);
   if (!k.ok) return;
-  const size_t w0 = (size_t)k.b * g.N * g.C4;
-  const float4 own = ld4(v, k.g);
-  const float nxt = (k.c + 1 < g.C4) ? v[(k.g + 1) * 4] : 0.f;
-  const float4 acc = fwd_gather(g.nbr_d, g.w_d, g.kd, v, w0, k.n, k.c, g.C4);
+  const float4* vw = win4(v, g, k.b);
+  const float4 own = vw[k.q];
+  const float nxt = (k.c + 1 < g.C4) ? reinterpret_cast<const float*>(vw + k.q + 1)[0] : 0.f;
+  const float4 acc = fwd_gather(g.nbr_d, g.w_d, g.kd, vw, k.n, k.c, g.C4);
   const int t = 4 * k.c;
   float4 o;
   o.x = (t + 1 < g.T) ? own.y - acc.x : 0.f;
@@ -157,12 +206,24 @@ __global__ void __launch_bounds__(kB2) k2_ldr_shift(Graph2 g, int tiles, const f
 }
 
 // father sum over the in-list: f[t] = sum w qs_src[t]  (ADMM.py:200-209 as a gather, scatter order kept)
-__device__ __forceinline__ float4 inlist_gather(const Graph2& g, const float* __restrict__ qs, size_t win_chunk0, int n, int c) {
+__device__ __forceinline__ float4 inlist_gather(const Graph2& g, const float4* __restrict__ qw, int n, int c) {
   float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
-  const int e0 = g.in_ptr[n], e1 = g.in_ptr[n + 1];
-  for (int e = e0; e < e1; ++e) {
+  int e = g.in_ptr[n];
+  const int e1 = g.in_ptr[n + 1];
+  for (; e + 4 <= e1; e += 4) {
+    int m[4];
+    float w[4];
+    float4 a[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { m[q] = g.in_src[e + q]; w[q] = g.in_w[e + q]; }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) a[q] = qw[m[q] * g.C4 + c];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { f.x += w[q] * a[q].x; f.y += w[q] * a[q].y; f.z += w[q] * a[q].z; f.w += w[q] * a[q].w; }
+  }
+  for (; e < e1; ++e) {
     const float w = g.in_w[e];
-    const float4 a = ld4(qs, win_chunk0 + (size_t)g.in_src[e] * g.C4 + c);
+    const float4 a = qw[g.in_src[e] * g.C4 + c];
     f.x += w * a.x; f.y += w * a.y; f.z += w * a.z; f.w += w * a.w;
   }
   return f;
@@ -172,17 +233,17 @@ __device__ __forceinline__ float4 inlist_gather(const Graph2& g, const float* __
 // MODE 1: r = rhs - A v, dot <r, r> -> slot  (initial residual)
 // A = diag + c L_d^T L_d with qs = shifted L_d v already computed.  xsys: H^T H term + LHS_x's evaluation order.
 template <int MODE>
-__global__ void __launch_bounds__(kB2) k2_ldrt_lhs(Graph2 g, int tiles, const float* __restrict__ v, const float* __restrict__ qs,
+__global__ void __launch_bounds__(kB2) k2_ldrt_lhs(Graph2 g, const float* __restrict__ v, const float* __restrict__ qs,
                                                    const float* __restrict__ rhs, float* __restrict__ out, double* __restrict__ slot,
                                                    float a, float cc, int xsys) {
-  const Chunk k = locate2(g, tiles);
+  const Chunk k = locate2(g);
   float dot = 0.f;
   if (k.ok) {
-    const size_t w0 = (size_t)k.b * g.N * g.C4;
+    const float4* qw = win4(qs, g, k.b);
     const float4 pv = ld4(v, k.g);
-    const float4 q1 = ld4(qs, k.g);
-    const float qprev = k.c > 0 ? qs[k.g * 4 - 1] : 0.f;        // q[4c] = qs[4c-1]; q[0] = 0 (ADMM.py:176)
-    const float4 f = inlist_gather(g, qs, w0, k.n, k.c);
+    const float4 q1 = qw[k.q];
+    const float qprev = k.c > 0 ? reinterpret_cast<const float*>(qw + k.q)[-1] : 0.f;   // q[4c] = qs[4c-1]; q[0] = 0 (ADMM.py:176)
+    const float4 f = inlist_gather(g, qw, k.n, k.c);
     const float p[4] = {pv.x, pv.y, pv.z, pv.w};
     const float q[4] = {qprev, q1.x, q1.y, q1.z};
     const float ff[4] = {f.x, f.y, f.z, f.w};
@@ -207,19 +268,19 @@ __global__ void __launch_bounds__(kB2) k2_ldrt_lhs(Graph2 g, int tiles, const fl
       dot = (r0 * r0 + r1 * r1) + (r2 * r2 + r3 * r3);
     }
   }
-  block_add<float>(dot, slot + k.b);
+  block_add(dot, slot + k.b, tid2(), blockDim.x * blockDim.y);
 }
 
 // z_u system: A = c L_u + a I  (ADMM.py:389-390), same two modes
 template <int MODE>
-__global__ void __launch_bounds__(kB2) k2_lu_lhs(Graph2 g, int tiles, const float* __restrict__ v, const float* __restrict__ rhs,
+__global__ void __launch_bounds__(kB2) k2_lu_lhs(Graph2 g, const float* __restrict__ v, const float* __restrict__ rhs,
                                                  float* __restrict__ out, double* __restrict__ slot, float a, float cc) {
-  const Chunk k = locate2(g, tiles);
+  const Chunk k = locate2(g);
   float dot = 0.f;
   if (k.ok) {
-    const size_t w0 = (size_t)k.b * g.N * g.C4;
-    const float4 pv = ld4(v, k.g);
-    const float4 acc = fwd_gather(g.nbr_u, g.w_u, g.ku, v, w0, k.n, k.c, g.C4);
+    const float4* vw = win4(v, g, k.b);
+    const float4 pv = vw[k.q];
+    const float4 acc = fwd_gather(g.nbr_u, g.w_u, g.ku, vw, k.n, k.c, g.C4);
     float4 o;
     o.x = cc * (pv.x - acc.x) + a * pv.x;
     o.y = cc * (pv.y - acc.y) + a * pv.y;
@@ -235,13 +296,13 @@ __global__ void __launch_bounds__(kB2) k2_lu_lhs(Graph2 g, int tiles, const floa
       dot = (r.x * r.x + r.y * r.y) + (r.z * r.z + r.w * r.w);
     }
   }
-  block_add<float>(dot, slot + k.b);
+  block_add(dot, slot + k.b, tid2(), blockDim.x * blockDim.y);
 }
 
 // p' = r + beta p   (first iteration: p' = r).  dots: RR(k) = dots[2k], PAP(k) = dots[2k+1], each (B)
-__global__ void __launch_bounds__(kB2) k2_pupdate(Graph2 g, int tiles, int64_t B, int it, const float* __restrict__ r,
-                                                  float* __restrict__ p, const double* __restrict__ dots) {
-  const Chunk k = locate2(g, tiles);
+__global__ void __launch_bounds__(kFlat) k2_pupdate(Graph2 g, int64_t B, int it, const float* __restrict__ r,
+                                                   float* __restrict__ p, const double* __restrict__ dots) {
+  const Chunk k = locate_flat(g);
   if (!k.ok) return;
   const float4 rv = ld4(r, k.g);
   if (it == 0) { st4(p, k.g, rv); return; }
@@ -251,9 +312,9 @@ __global__ void __launch_bounds__(kB2) k2_pupdate(Graph2 g, int tiles, int64_t B
 }
 
 // x += alpha p ; r -= alpha Ap ; RR(k+1) += r.r   (ADMM.py:350-355)
-__global__ void __launch_bounds__(kB2) k2_xr(Graph2 g, int tiles, int64_t B, int it, float* __restrict__ x, float* __restrict__ r,
-                                             const float* __restrict__ p, const float* __restrict__ ap, double* __restrict__ dots) {
-  const Chunk k = locate2(g, tiles);
+__global__ void __launch_bounds__(kFlat) k2_xr(Graph2 g, int64_t B, int it, float* __restrict__ x, float* __restrict__ r,
+                                              const float* __restrict__ p, const float* __restrict__ ap, double* __restrict__ dots) {
+  const Chunk k = locate_flat(g);
   float dot = 0.f;
   if (k.ok) {
     const float alpha = (float)dots[(size_t)(2 * it) * B + k.b] / (float)dots[(size_t)(2 * it + 1) * B + k.b];
@@ -263,7 +324,7 @@ __global__ void __launch_bounds__(kB2) k2_xr(Graph2 g, int tiles, int64_t B, int
     st4(r, k.g, rn);
     dot = (rn.x * rn.x + rn.y * rn.y) + (rn.z * rn.z + rn.w * rn.w);
   }
-  block_add<float>(dot, dots + (size_t)(2 * it + 2) * B + k.b);
+  block_add(dot, dots + (size_t)(2 * it + 2) * B + k.b, threadIdx.x, kFlat);
 }
 
 __global__ void k2_coeffs(int64_t B, int iters, const double* __restrict__ dots, float* __restrict__ alpha, float* __restrict__ beta) {
@@ -304,8 +365,8 @@ __device__ __forceinline__ void ldr_chunk(const Graph2& g, const float* __restri
   }
 }
 
-__global__ void __launch_bounds__(kB2) k2_ldr(Graph2 g, int tiles, const float* __restrict__ v, float* __restrict__ out) {
-  const Chunk k = locate2(g, tiles);
+__global__ void __launch_bounds__(kB2) k2_ldr(Graph2 g, const float* __restrict__ v, float* __restrict__ out) {
+  const Chunk k = locate2(g);
   if (!k.ok) return;
   float o[4];
   ldr_chunk(g, v, (size_t)k.b * g.N * g.C4, k.n, k.c, ld4(v, k.g), o);
@@ -313,12 +374,12 @@ __global__ void __launch_bounds__(kB2) k2_ldr(Graph2 g, int tiles, const float* 
 }
 
 // RHS_x (ADMM.py:552-559): Ldr_T(gamma + rho phi)/2 + (rho_u zu + rho_d zd)/2 - (gu + gd)/2 + H^T y
-__global__ void __launch_bounds__(kB2) k2_rhs_x(Graph2 g, int tiles, const float* __restrict__ gam, const float* __restrict__ phi,
+__global__ void __launch_bounds__(kB2) k2_rhs_x(Graph2 g, const float* __restrict__ gam, const float* __restrict__ phi,
                                                 const float* __restrict__ zu, const float* __restrict__ zd,
                                                 const float* __restrict__ gu, const float* __restrict__ gd,
                                                 const float* __restrict__ y, float* __restrict__ rhs, float rho, float rho_u,
                                                 float rho_d) {
-  const Chunk k = locate2(g, tiles);
+  const Chunk k = locate2(g);
   if (!k.ok) return;
   const size_t w0 = (size_t)k.b * g.N * g.C4;
   const float4 ga = ld4(gam, k.g), ph = ld4(phi, k.g);
@@ -351,7 +412,7 @@ __global__ void __launch_bounds__(kB2) k2_rhs_x(Graph2 g, int tiles, const float
 }
 
 // RHS_zu / RHS_zd (ADMM.py:579, 587)
-__global__ void __launch_bounds__(kB2) k2_rhs_z(size_t chunks, const float* __restrict__ gz, const float* __restrict__ x,
+__global__ void __launch_bounds__(kFlat) k2_rhs_z(size_t chunks, const float* __restrict__ gz, const float* __restrict__ x,
                                                 float* __restrict__ rhs, float half_rho) {
   const size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= chunks) return;
@@ -368,14 +429,14 @@ __device__ __forceinline__ float soft2(float s, float d) {
 
 // The tail of one outer iteration in a single pass (ADMM.py:595-637): both dual ascents, phi prox, gamma
 // ascent and all diagnostics.
-__global__ void __launch_bounds__(kB2) k2_tail(Graph2 g, int tiles, int want_diag, const float* __restrict__ x,
+__global__ void __launch_bounds__(kB2) k2_tail(Graph2 g, int want_diag, const float* __restrict__ x,
                                                const float* __restrict__ x_old, const float* __restrict__ zu,
                                                const float* __restrict__ zu_old, const float* __restrict__ zd,
                                                const float* __restrict__ zd_old, float* __restrict__ gu, float* __restrict__ gd,
                                                float* __restrict__ gam, float* __restrict__ phi, const float* __restrict__ y,
                                                float rho, float rho_u, float rho_d, float thr, double* __restrict__ diag,
                                                double* __restrict__ dx_sum) {
-  const Chunk k = locate2(g, tiles);
+  const Chunk k = locate2(g);
   float d[MGA_DIAG_COLS];
 #pragma unroll
   for (int c = 0; c < MGA_DIAG_COLS; ++c) d[c] = 0.f;
@@ -391,7 +452,7 @@ __global__ void __launch_bounds__(kB2) k2_tail(Graph2 g, int tiles, int want_dia
     ldr_chunk(g, x, w0, k.n, k.c, xv4, ldx);
     float lux[4] = {0.f, 0.f, 0.f, 0.f}, xo[4] = {0.f, 0.f, 0.f, 0.f}, zuo[4] = {0.f, 0.f, 0.f, 0.f}, zdo[4] = {0.f, 0.f, 0.f, 0.f};
     if (want_diag) {
-      const float4 acc = fwd_gather(g.nbr_u, g.w_u, g.ku, x, w0, k.n, k.c, g.C4);
+      const float4 acc = fwd_gather(g.nbr_u, g.w_u, g.ku, win4(x, g, k.b), k.n, k.c, g.C4);
       lux[0] = xv[0] - acc.x; lux[1] = xv[1] - acc.y; lux[2] = xv[2] - acc.z; lux[3] = xv[3] - acc.w;
       const float4 a = ld4(x_old, k.g), b = ld4(zu_old, k.g), c = ld4(zd_old, k.g);
       xo[0] = a.x; xo[1] = a.y; xo[2] = a.z; xo[3] = a.w;
@@ -441,21 +502,32 @@ __global__ void __launch_bounds__(kB2) k2_tail(Graph2 g, int tiles, int want_dia
     st4(phi, k.g, make_float4(phv[0], phv[1], phv[2], phv[3]));
   }
   __shared__ float red[MGA_DIAG_COLS][kB2 / 32];
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int tid = tid2(), lane = tid & 31, w = tid >> 5;
 #pragma unroll
   for (int c = 0; c < MGA_DIAG_COLS; ++c) {
     const float v = warp_sum<float>(d[c]);
     if (lane == 0) red[c][w] = v;
   }
   __syncthreads();
-  if (threadIdx.x < MGA_DIAG_COLS) {
+  if (tid < MGA_DIAG_COLS) {
     float t = 0.f;
-    for (int q = 0; q < kB2 / 32; ++q) t += red[threadIdx.x][q];
-    if (t != 0.f) atomicAdd(diag + threadIdx.x, (double)t);
+    const int nw = (blockDim.x * blockDim.y + 31) >> 5;
+    for (int q = 0; q < nw; ++q) t += red[tid][q];
+    if (t != 0.f) atomicAdd(diag + tid, (double)t);
   }
 }
 
 // ---- host side -----------------------------------------------------------------------------------------
+void stream2_tiling(Graph2* g) {
+  g->CB = std::min(g->C4, 8);
+  int step = 32;                                        // NBt must make CB * NBt whole warps
+  for (int d = 2; d <= g->CB; d *= 2) if (g->CB % d == 0) step = 32 / d;
+  g->NBt = std::max(step, (kB2 / g->CB) / step * step); // thread rows per CTA, CB * NBt <= kB2
+  g->tilesN = (g->N + g->NBt - 1) / g->NBt;
+  g->NB = (g->N + g->tilesN - 1) / g->tilesN;           // balanced node tiles, NB <= NBt (extra rows are masked off)
+  g->tilesC = (g->C4 + g->CB - 1) / g->CB;
+}
+
 bool stream2_eligible(const mga_plan* p, int dtype) {
   return p->has_s2 && dtype == MGA_F32;
 }
@@ -472,8 +544,8 @@ static size_t dots_bytes2(int64_t B, int max_iter) { return (((size_t)(2 * max_i
 static int cg2(mga_plan* p, int system, const mga_params* m, const float* rhs, float* x, int64_t B, int n_cg, float* alpha,
                float* beta, const Bufs2& w, cudaStream_t st) {
   const Graph2& g = p->g2;
-  const int tiles = (g.N * g.C4 + kB2 - 1) / kB2;
-  const unsigned grid = (unsigned)(B * tiles);
+  const dim3 grid((unsigned)B, g.tilesN, g.tilesC), blk(g.CB, g.NBt);
+  const dim3 fgrid((unsigned)B, (g.N * g.C4 + kFlat - 1) / kFlat);
   float a, c;
   if (system == MGA_SYS_X) { a = (float)((m->rho_u + m->rho_d) / 2); c = (float)(m->rho / 2); }
   else if (system == MGA_SYS_ZU) { a = (float)(m->rho_u / 2); c = (float)m->mu_u; }
@@ -482,28 +554,28 @@ static int cg2(mga_plan* p, int system, const mga_params* m, const float* rhs, f
   MGA_CUDA(cudaMemsetAsync(w.dots, 0, (size_t)(2 * n_cg + 1) * B * sizeof(double), st));
   // r = rhs - A x0 ; RR(0)
   if (system == MGA_SYS_ZU) {
-    k2_lu_lhs<1><<<grid, kB2, 0, st>>>(g, tiles, x, rhs, w.r, w.dots, a, c);
+    k2_lu_lhs<1><<<grid, blk, 0, st>>>(g, x, rhs, w.r, w.dots, a, c);
     MGA_LAUNCH_CHECK("k2_lu_lhs");
   } else {
-    k2_ldr_shift<<<grid, kB2, 0, st>>>(g, tiles, x, w.qs);
+    k2_ldr_shift<<<grid, blk, 0, st>>>(g, x, w.qs);
     MGA_LAUNCH_CHECK("k2_ldr_shift");
-    k2_ldrt_lhs<1><<<grid, kB2, 0, st>>>(g, tiles, x, w.qs, rhs, w.r, w.dots, a, c, xsys);
+    k2_ldrt_lhs<1><<<grid, blk, 0, st>>>(g, x, w.qs, rhs, w.r, w.dots, a, c, xsys);
     MGA_LAUNCH_CHECK("k2_ldrt_lhs");
   }
   for (int it = 0; it < n_cg; ++it) {
-    k2_pupdate<<<grid, kB2, 0, st>>>(g, tiles, B, it, w.r, w.p, w.dots);
+    k2_pupdate<<<fgrid, kFlat, 0, st>>>(g, B, it, w.r, w.p, w.dots);
     MGA_LAUNCH_CHECK("k2_pupdate");
     double* pap = w.dots + (size_t)(2 * it + 1) * B;
     if (system == MGA_SYS_ZU) {
-      k2_lu_lhs<0><<<grid, kB2, 0, st>>>(g, tiles, w.p, nullptr, w.ap, pap, a, c);
+      k2_lu_lhs<0><<<grid, blk, 0, st>>>(g, w.p, nullptr, w.ap, pap, a, c);
       MGA_LAUNCH_CHECK("k2_lu_lhs");
     } else {
-      k2_ldr_shift<<<grid, kB2, 0, st>>>(g, tiles, w.p, w.qs);
+      k2_ldr_shift<<<grid, blk, 0, st>>>(g, w.p, w.qs);
       MGA_LAUNCH_CHECK("k2_ldr_shift");
-      k2_ldrt_lhs<0><<<grid, kB2, 0, st>>>(g, tiles, w.p, w.qs, nullptr, w.ap, pap, a, c, xsys);
+      k2_ldrt_lhs<0><<<grid, blk, 0, st>>>(g, w.p, w.qs, nullptr, w.ap, pap, a, c, xsys);
       MGA_LAUNCH_CHECK("k2_ldrt_lhs");
     }
-    k2_xr<<<grid, kB2, 0, st>>>(g, tiles, B, it, x, w.r, w.p, w.ap, w.dots);
+    k2_xr<<<fgrid, kFlat, 0, st>>>(g, B, it, x, w.r, w.p, w.ap, w.dots);
     MGA_LAUNCH_CHECK("k2_xr");
   }
   if ((alpha || beta) && n_cg > 0) {
@@ -537,15 +609,14 @@ int stream2_cg(mga_plan* p, int system, const mga_params* m, const void* rhs, vo
   float* rhs_i = reinterpret_cast<float*>(base);
   float* x_i = reinterpret_cast<float*>(base + vec);
   Bufs2 w = carve2(base + 2 * vec, g, B, n_cg);
-  const int tiles = (g.N * g.C4 + kB2 - 1) / kB2;
-  const unsigned grid = (unsigned)(B * tiles);
-  k2_import<<<grid, kB2, 0, st>>>(g, tiles, static_cast<const float*>(rhs), rhs_i);
+  const dim3 grid((unsigned)B, g.tilesN, g.tilesC), blk(g.CB, g.NBt);
+  k2_import<<<grid, blk, 0, st>>>(g, static_cast<const float*>(rhs), rhs_i);
   MGA_LAUNCH_CHECK("k2_import");
-  k2_import<<<grid, kB2, 0, st>>>(g, tiles, static_cast<const float*>(x), x_i);
+  k2_import<<<grid, blk, 0, st>>>(g, static_cast<const float*>(x), x_i);
   MGA_LAUNCH_CHECK("k2_import");
   rc = cg2(p, system, m, rhs_i, x_i, B, n_cg, static_cast<float*>(alpha), static_cast<float*>(beta), w, st);
   if (rc) return rc;
-  k2_export<<<grid, kB2, 0, st>>>(g, tiles, x_i, static_cast<float*>(x));
+  k2_export<<<grid, blk, 0, st>>>(g, x_i, static_cast<float*>(x));
   MGA_LAUNCH_CHECK("k2_export");
   return MGA_OK;
 }
@@ -577,14 +648,13 @@ int stream2_admm(mga_plan* p, const mga_params* prm, const void* y_, void* x_out
   double* nf_row = own_diag;     // non-finite flag row when diagnostics are off
   if (!want_diag) MGA_CUDA(cudaMemsetAsync(nf_row, 0, MGA_DIAG_COLS * sizeof(double), st));
 
-  const int tiles = (g.N * g.C4 + kB2 - 1) / kB2;
-  const unsigned grid = (unsigned)(B * tiles);
+  const dim3 grid((unsigned)B, g.tilesN, g.tilesC), blk(g.CB, g.NBt);
   const size_t chunks = (size_t)B * g.N * g.C4;
-  const unsigned grid_c = (unsigned)((chunks + kB2 - 1) / kB2);
-  const unsigned grid_bn = (unsigned)((B * g.N + kB2 - 1) / kB2);
-  k2_init<<<grid_bn, kB2, 0, st>>>(g, B, y, x_cur, zu_cur, zd_cur, gu, gd, gam, (float)t_mean, (float)t_var);
+  const unsigned grid_c = (unsigned)((chunks + kFlat - 1) / kFlat);
+  const unsigned grid_bn = (unsigned)((B * g.N + 255) / 256);
+  k2_init<<<grid_bn, 256, 0, st>>>(g, B, y, x_cur, zu_cur, zd_cur, gu, gd, gam, (float)t_mean, (float)t_var);
   MGA_LAUNCH_CHECK("k2_init");
-  k2_ldr<<<grid, kB2, 0, st>>>(g, tiles, x_cur, phi);      // phi = L_d x (ADMM.py:541)
+  k2_ldr<<<grid, blk, 0, st>>>(g, x_cur, phi);      // phi = L_d x (ADMM.py:541)
   MGA_LAUNCH_CHECK("k2_ldr");
   const float rho = (float)prm->rho, rho_u = (float)prm->rho_u, rho_d = (float)prm->rho_d;
   const float thr = (float)(prm->mu_d1 / prm->rho);
@@ -594,20 +664,20 @@ int stream2_admm(mga_plan* p, const mga_params* prm, const void* y_, void* x_out
     auto coef = [&](void* basep, int s) -> float* {
       return basep ? static_cast<float*>(basep) + ((size_t)it * 3 + s) * coef_stride : nullptr;
     };
-    k2_rhs_x<<<grid, kB2, 0, st>>>(g, tiles, gam, phi, zu_cur, zd_cur, gu, gd, y, rhs, rho, rho_u, rho_d);
+    k2_rhs_x<<<grid, blk, 0, st>>>(g, gam, phi, zu_cur, zd_cur, gu, gd, y, rhs, rho, rho_u, rho_d);
     MGA_LAUNCH_CHECK("k2_rhs_x");
     MGA_CUDA(cudaMemcpyAsync(x_nxt, x_cur, vbytes, cudaMemcpyDeviceToDevice, st));       // warm start (ADMM.py:571)
     if ((rc = cg2(p, MGA_SYS_X, prm, rhs, x_nxt, B, max_cg, coef(outs->alpha, 0), coef(outs->beta, 0), w, st))) return rc;
-    k2_rhs_z<<<grid_c, kB2, 0, st>>>(chunks, gu, x_nxt, rhs, (float)(prm->rho_u / 2));
+    k2_rhs_z<<<grid_c, kFlat, 0, st>>>(chunks, gu, x_nxt, rhs, (float)(prm->rho_u / 2));
     MGA_LAUNCH_CHECK("k2_rhs_z");
     MGA_CUDA(cudaMemcpyAsync(zu_nxt, zu_cur, vbytes, cudaMemcpyDeviceToDevice, st));
     if ((rc = cg2(p, MGA_SYS_ZU, prm, rhs, zu_nxt, B, max_cg, coef(outs->alpha, 1), coef(outs->beta, 1), w, st))) return rc;
-    k2_rhs_z<<<grid_c, kB2, 0, st>>>(chunks, gd, x_nxt, rhs, (float)(prm->rho_d / 2));
+    k2_rhs_z<<<grid_c, kFlat, 0, st>>>(chunks, gd, x_nxt, rhs, (float)(prm->rho_d / 2));
     MGA_LAUNCH_CHECK("k2_rhs_z");
     MGA_CUDA(cudaMemcpyAsync(zd_nxt, zd_cur, vbytes, cudaMemcpyDeviceToDevice, st));
     if ((rc = cg2(p, MGA_SYS_ZD, prm, rhs, zd_nxt, B, max_cg, coef(outs->alpha, 2), coef(outs->beta, 2), w, st))) return rc;
     double* drow = want_diag ? diag + (size_t)it * MGA_DIAG_COLS : nf_row;
-    k2_tail<<<grid, kB2, 0, st>>>(g, tiles, want_diag ? 1 : 0, x_nxt, x_cur, zu_nxt, zu_cur, zd_nxt, zd_cur, gu, gd, gam, phi,
+    k2_tail<<<grid, blk, 0, st>>>(g, want_diag ? 1 : 0, x_nxt, x_cur, zu_nxt, zu_cur, zd_nxt, zd_cur, gu, gd, gam, phi,
                                  y, rho, rho_u, rho_d, thr, drow, dx_sum ? dx_sum + (size_t)it * g.T * g.N : nullptr);
     MGA_LAUNCH_CHECK("k2_tail");
     std::swap(x_cur, x_nxt);
@@ -617,7 +687,7 @@ int stream2_admm(mga_plan* p, const mga_params* prm, const void* y_, void* x_out
   }
   auto give = [&](void* dst, const float* src) -> int {
     if (!dst) return MGA_OK;
-    k2_export<<<grid, kB2, 0, st>>>(g, tiles, src, static_cast<float*>(dst));
+    k2_export<<<grid, blk, 0, st>>>(g, src, static_cast<float*>(dst));
     MGA_LAUNCH_CHECK("k2_export");
     return MGA_OK;
   };
