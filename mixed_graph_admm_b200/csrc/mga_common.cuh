@@ -68,6 +68,7 @@ struct mga_plan {
   int device = 0;
   int sm_count = 0;
   int max_smem_optin = 0;
+  size_t l2_bytes = 0;
   mga::GraphDev g{};
   std::vector<void*> owned;          // device allocations of the tables
   mga::Workspace ws;                 // grown on demand, reused between calls

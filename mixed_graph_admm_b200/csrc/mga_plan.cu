@@ -213,6 +213,7 @@ int mga_plan_create(const mga_graph_desc* d, int device, mga_plan** out) {
   if (e != cudaSuccess) { delete p; return cuda_fail(e, "cudaGetDeviceProperties"); }
   p->sm_count = prop.multiProcessorCount;
   p->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+  p->l2_bytes = (size_t)prop.l2CacheSize;
 
   GraphDev& g = p->g;
   auto fail = [&](int code) { mga_plan_destroy(p); return code; };

@@ -23,6 +23,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 
 #include "mga_common.cuh"
 
@@ -327,11 +328,14 @@ __global__ void __launch_bounds__(kFlat) k2_xr(Graph2 g, int64_t B, int it, floa
   block_add(dot, dots + (size_t)(2 * it + 2) * B + k.b, threadIdx.x, kFlat);
 }
 
-__global__ void k2_coeffs(int64_t B, int iters, const double* __restrict__ dots, float* __restrict__ alpha, float* __restrict__ beta) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+// alpha / beta live in arrays of B_out windows per iteration (this call's B windows are a slice of them)
+__global__ void k2_coeffs(int64_t B, int64_t B_out, int iters, const double* __restrict__ dots, float* __restrict__ alpha,
+                          float* __restrict__ beta) {
+  int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= B * iters) return;
   const int k = (int)(idx / B);
   const int64_t b = idx - (int64_t)k * B;
+  idx = (int64_t)k * B_out + b;
   const float rr = (float)dots[(size_t)(2 * k) * B + b], pap = (float)dots[(size_t)(2 * k + 1) * B + b];
   const float rrn = (float)dots[(size_t)(2 * k + 2) * B + b];
   if (alpha) alpha[idx] = rr / pap;
@@ -541,8 +545,8 @@ static size_t vec_bytes2(const Graph2& g, int64_t B) { return (((size_t)B * g.N 
 static size_t dots_bytes2(int64_t B, int max_iter) { return (((size_t)(2 * max_iter + 1) * B * sizeof(double)) + 255) & ~(size_t)255; }
 
 // CG_solver (ADMM.py:329-368) with a fixed iteration count on internal-layout vectors; x holds x0 / the solution.
-static int cg2(mga_plan* p, int system, const mga_params* m, const float* rhs, float* x, int64_t B, int n_cg, float* alpha,
-               float* beta, const Bufs2& w, cudaStream_t st) {
+static int cg2(mga_plan* p, int system, const mga_params* m, const float* rhs, float* x, int64_t B, int64_t B_out, int n_cg,
+               float* alpha, float* beta, const Bufs2& w, cudaStream_t st) {
   const Graph2& g = p->g2;
   const dim3 grid((unsigned)B, g.tilesN, g.tilesC), blk(g.CB, g.NBt);
   const dim3 fgrid((unsigned)B, (g.N * g.C4 + kFlat - 1) / kFlat);
@@ -580,7 +584,7 @@ static int cg2(mga_plan* p, int system, const mga_params* m, const float* rhs, f
   }
   if ((alpha || beta) && n_cg > 0) {
     const int64_t tot = B * n_cg;
-    k2_coeffs<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(B, n_cg, w.dots, alpha, beta);
+    k2_coeffs<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(B, B_out, n_cg, w.dots, alpha, beta);
     MGA_LAUNCH_CHECK("k2_coeffs");
   }
   return MGA_OK;
@@ -598,9 +602,38 @@ static Bufs2 carve2(char* base, const Graph2& g, int64_t B, int max_iter) {
   return w;
 }
 
+// Windows per group.  Windows are independent, so a batch can be walked in groups; measured on B200, keeping
+// a group's CG vectors L2-resident buys nothing (the gather kernels are bound by L1 wavefronts, not by where
+// the rows come from: T=288 5.57k windows/s with groups of 64 or with all 256 at once), while small groups
+// become launch-bound.  Groups therefore only cap the workspace (16 vectors per window) at 32 GB.
+static int64_t group_windows(const mga_plan* p, int64_t B) {
+  if (const char* e = std::getenv("MGA_S2_GROUP")) { const long v = std::atol(e); if (v > 0) return std::min<int64_t>(B, v); }
+  const Graph2& g = p->g2;
+  const double per_window = 16.0 * (double)g.N * g.C4 * 16.0;
+  const int64_t G = (int64_t)(32e9 / per_window);
+  return std::max<int64_t>(1, std::min<int64_t>(B, G));
+}
+
+static int stream2_cg_group(mga_plan* p, int system, const mga_params* m, const void* rhs, void* x, int64_t B, int64_t B_out,
+                            int n_cg, void* alpha, void* beta, cudaStream_t st);
+
 // mga_cg_solve, fixed iteration count, caller-layout rhs / x
 int stream2_cg(mga_plan* p, int system, const mga_params* m, const void* rhs, void* x, int64_t B, int n_cg, void* alpha,
                void* beta, cudaStream_t st) {
+  const int64_t G = group_windows(p, B);
+  const size_t win = (size_t)p->g2.T * p->g2.N;
+  for (int64_t b0 = 0; b0 < B; b0 += G) {
+    const int64_t nb = std::min(G, B - b0);
+    int rc = stream2_cg_group(p, system, m, static_cast<const float*>(rhs) + b0 * win, static_cast<float*>(x) + b0 * win, nb, B,
+                              n_cg, alpha ? static_cast<float*>(alpha) + b0 : nullptr,
+                              beta ? static_cast<float*>(beta) + b0 : nullptr, st);
+    if (rc) return rc;
+  }
+  return MGA_OK;
+}
+
+static int stream2_cg_group(mga_plan* p, int system, const mga_params* m, const void* rhs, void* x, int64_t B, int64_t B_out,
+                            int n_cg, void* alpha, void* beta, cudaStream_t st) {
   const Graph2& g = p->g2;
   const size_t vec = vec_bytes2(g, B);
   int rc = ensure_workspace(p, p->ws, 6 * vec + dots_bytes2(B, n_cg) + 256);
@@ -614,16 +647,42 @@ int stream2_cg(mga_plan* p, int system, const mga_params* m, const void* rhs, vo
   MGA_LAUNCH_CHECK("k2_import");
   k2_import<<<grid, blk, 0, st>>>(g, static_cast<const float*>(x), x_i);
   MGA_LAUNCH_CHECK("k2_import");
-  rc = cg2(p, system, m, rhs_i, x_i, B, n_cg, static_cast<float*>(alpha), static_cast<float*>(beta), w, st);
+  rc = cg2(p, system, m, rhs_i, x_i, B, B_out, n_cg, static_cast<float*>(alpha), static_cast<float*>(beta), w, st);
   if (rc) return rc;
   k2_export<<<grid, blk, 0, st>>>(g, x_i, static_cast<float*>(x));
   MGA_LAUNCH_CHECK("k2_export");
   return MGA_OK;
 }
 
-// combined_loop (ADMM.py:528-648), forecasting mode, ablation None, fixed iteration counts
+static int stream2_admm_group(mga_plan* p, const mga_params* prm, const void* y_, void* x_out, int64_t B, int64_t B_out,
+                              int n_outer, int max_cg, double t_mean, double t_var, int diag_flags,
+                              const mga_admm_outputs* outs, cudaStream_t st);
+
+// combined_loop (ADMM.py:528-648), forecasting mode, ablation None, fixed iteration counts.  Windows are
+// independent, so the batch is walked in L2-sized groups (group_windows); diagnostics accumulate over groups.
 int stream2_admm(mga_plan* p, const mga_params* prm, const void* y_, void* x_out, int64_t B, int n_outer, int max_cg,
                  double t_mean, double t_var, int diag_flags, const mga_admm_outputs* outs, cudaStream_t st) {
+  const Graph2& g = p->g2;
+  const int64_t G = group_windows(p, B);
+  const size_t win = (size_t)g.T * g.N, ywin = (size_t)g.t_in * g.N;
+  for (int64_t b0 = 0; b0 < B; b0 += G) {
+    const int64_t nb = std::min(G, B - b0);
+    mga_admm_outputs o = *outs;
+    auto off = [&](void* ptr, size_t n) -> void* { return ptr ? static_cast<float*>(ptr) + n : nullptr; };
+    o.zu = off(outs->zu, b0 * win); o.zd = off(outs->zd, b0 * win); o.phi = off(outs->phi, b0 * win);
+    o.gamma = off(outs->gamma, b0 * win); o.gamma_u = off(outs->gamma_u, b0 * win); o.gamma_d = off(outs->gamma_d, b0 * win);
+    o.alpha = off(outs->alpha, b0); o.beta = off(outs->beta, b0);
+    const int flags = b0 == 0 ? diag_flags : (diag_flags | 2);       // later groups add to the first one's sums
+    int rc = stream2_admm_group(p, prm, static_cast<const float*>(y_) + b0 * ywin, static_cast<float*>(x_out) + b0 * win, nb, B,
+                                n_outer, max_cg, t_mean, t_var, flags, &o, st);
+    if (rc) return rc;
+  }
+  return MGA_OK;
+}
+
+static int stream2_admm_group(mga_plan* p, const mga_params* prm, const void* y_, void* x_out, int64_t B, int64_t B_out,
+                              int n_outer, int max_cg, double t_mean, double t_var, int diag_flags,
+                              const mga_admm_outputs* outs, cudaStream_t st) {
   const Graph2& g = p->g2;
   const float* y = static_cast<const float*>(y_);
   const bool want_diag = (diag_flags & 1) != 0, accumulate = (diag_flags & 2) != 0;
@@ -658,7 +717,7 @@ int stream2_admm(mga_plan* p, const mga_params* prm, const void* y_, void* x_out
   MGA_LAUNCH_CHECK("k2_ldr");
   const float rho = (float)prm->rho, rho_u = (float)prm->rho_u, rho_d = (float)prm->rho_d;
   const float thr = (float)(prm->mu_d1 / prm->rho);
-  const size_t coef_stride = (size_t)max_cg * B;
+  const size_t coef_stride = (size_t)max_cg * B_out;
   const size_t vbytes = chunks * 16;
   for (int it = 0; it < n_outer; ++it) {
     auto coef = [&](void* basep, int s) -> float* {
@@ -667,15 +726,15 @@ int stream2_admm(mga_plan* p, const mga_params* prm, const void* y_, void* x_out
     k2_rhs_x<<<grid, blk, 0, st>>>(g, gam, phi, zu_cur, zd_cur, gu, gd, y, rhs, rho, rho_u, rho_d);
     MGA_LAUNCH_CHECK("k2_rhs_x");
     MGA_CUDA(cudaMemcpyAsync(x_nxt, x_cur, vbytes, cudaMemcpyDeviceToDevice, st));       // warm start (ADMM.py:571)
-    if ((rc = cg2(p, MGA_SYS_X, prm, rhs, x_nxt, B, max_cg, coef(outs->alpha, 0), coef(outs->beta, 0), w, st))) return rc;
+    if ((rc = cg2(p, MGA_SYS_X, prm, rhs, x_nxt, B, B_out, max_cg, coef(outs->alpha, 0), coef(outs->beta, 0), w, st))) return rc;
     k2_rhs_z<<<grid_c, kFlat, 0, st>>>(chunks, gu, x_nxt, rhs, (float)(prm->rho_u / 2));
     MGA_LAUNCH_CHECK("k2_rhs_z");
     MGA_CUDA(cudaMemcpyAsync(zu_nxt, zu_cur, vbytes, cudaMemcpyDeviceToDevice, st));
-    if ((rc = cg2(p, MGA_SYS_ZU, prm, rhs, zu_nxt, B, max_cg, coef(outs->alpha, 1), coef(outs->beta, 1), w, st))) return rc;
+    if ((rc = cg2(p, MGA_SYS_ZU, prm, rhs, zu_nxt, B, B_out, max_cg, coef(outs->alpha, 1), coef(outs->beta, 1), w, st))) return rc;
     k2_rhs_z<<<grid_c, kFlat, 0, st>>>(chunks, gd, x_nxt, rhs, (float)(prm->rho_d / 2));
     MGA_LAUNCH_CHECK("k2_rhs_z");
     MGA_CUDA(cudaMemcpyAsync(zd_nxt, zd_cur, vbytes, cudaMemcpyDeviceToDevice, st));
-    if ((rc = cg2(p, MGA_SYS_ZD, prm, rhs, zd_nxt, B, max_cg, coef(outs->alpha, 2), coef(outs->beta, 2), w, st))) return rc;
+    if ((rc = cg2(p, MGA_SYS_ZD, prm, rhs, zd_nxt, B, B_out, max_cg, coef(outs->alpha, 2), coef(outs->beta, 2), w, st))) return rc;
     double* drow = want_diag ? diag + (size_t)it * MGA_DIAG_COLS : nf_row;
     k2_tail<<<grid, blk, 0, st>>>(g, want_diag ? 1 : 0, x_nxt, x_cur, zu_nxt, zu_cur, zd_nxt, zd_cur, gu, gd, gam, phi,
                                  y, rho, rho_u, rho_d, thr, drow, dx_sum ? dx_sum + (size_t)it * g.T * g.N : nullptr);
