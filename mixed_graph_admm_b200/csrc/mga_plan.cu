@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "mga_common.cuh"
@@ -556,7 +557,11 @@ int mga_admm_solve_host(mga_plan* p, const mga_params* prm, const void* y_host, 
   if (y_rows != p->g.t_in) { set_error("mga_admm_solve_host: y must have t_in rows"); return MGA_ERR_INVALID; }
   const GraphDev& g = p->g;
   const size_t es = dtype == MGA_F32 ? 4 : 8;
-  if (chunk <= 0) chunk = std::max<int64_t>(1, std::min<int64_t>(B, (B + 3) / 4));
+  if (chunk <= 0) {
+    int parts = 4;
+    if (const char* e = std::getenv("MGA_HOST_CHUNKS")) parts = std::max(1, std::atoi(e));
+    chunk = std::max<int64_t>(1, std::min<int64_t>(B, (B + parts - 1) / parts));
+  }
   chunk = std::min(chunk, B);
   const int64_t nchunk = (B + chunk - 1) / chunk;
   const size_t y_win = (size_t)y_rows * g.N * es, x_win = (size_t)g.T * g.N * es;

@@ -875,6 +875,7 @@ inline int pick_threads_cg(mga_plan* p, ResArgs& a, const CgArgs& g, const ResGe
   if (geo.threads <= 192) return launch_res_cg<CH, K, 192, (MGA_RES_MINB > 1 ? 3 : 1)>(p, a, g, geo, st);
   if (geo.threads <= 320) return launch_res_cg<CH, K, 320, MGA_RES_MINB>(p, a, g, geo, st);
   if (geo.threads <= 512) return launch_res_cg<CH, K, 512, 1>(p, a, g, geo, st);
+  if (geo.threads <= 640) return launch_res_cg<CH, K, 640, 1>(p, a, g, geo, st);      // 2 slabs x 320: 96 registers, no spills
   return launch_res_cg<CH, K, 1024, 1>(p, a, g, geo, st);
 }
 
@@ -883,6 +884,7 @@ inline int pick_threads(mga_plan* p, ResArgs& a, const ResGeom& geo, cudaStream_
   if (geo.threads <= 192) return launch_res<CH, K, 192, (MGA_RES_MINB > 1 ? 3 : 1)>(p, a, geo, st);
   if (geo.threads <= 320) return launch_res<CH, K, 320, MGA_RES_MINB>(p, a, geo, st);
   if (geo.threads <= 512) return launch_res<CH, K, 512, 1>(p, a, geo, st);
+  if (geo.threads <= 640) return launch_res<CH, K, 640, 1>(p, a, geo, st);         // 2 slabs x 320: 96 registers, no spills
   return launch_res<CH, K, 1024, 1>(p, a, geo, st);
 }
 
