@@ -145,8 +145,6 @@ def run_reference(args, rank, world):
     the Python reference cannot travel to the GPU box) on the host cores; rank 0 only."""
     if rank != 0:
         return
-    from mixed_graph_admm_b200 import synth
-    from mixed_graph_admm_b200.ADMM import ADMM_algorithm  # noqa: F401  (graph construction only)
     sample = 32
     blk, y = build_problem_cpu(sample)
     for _ in range(min(args.warmup, 1)):
