@@ -339,3 +339,43 @@ def test_t24_resident_reference_default_shape():
     prm = O.OracleParams(**synth.admm_info(N), t_in=t_in, T=T)
     tr = O.admm_combined(og, prm, y, max_admm_iter=3, max_cg_iter=10, cg_tol=-1.0, admm_tol=-1.0)
     assert rel_err(x, tr.x) <= 1e-5
+
+
+@pytest.mark.parametrize("N,k,T,B,iso", [
+    (200, 8, 12, 5, False),     # K = 8 instantiation (8 neighbours after the self link is dropped)
+    (150, 9, 8, 4, True),       # K = 10 instantiation, two chunks, '-1' padding from an isolated pair
+    (100, 4, 24, 3, False),     # the reference's default k and T: two slabs per node
+    (64, 2, 4, 7, False),       # one chunk per thread, K = 4 instantiation with spare slots
+    (33, 5, 12, 9, False),      # N just over a warp
+    (307, 6, 20, 2, False),     # T not a multiple of 12: partial last slab (640-thread launch bucket)
+    (512, 6, 12, 2, False),     # the widest window the 12-step instantiation takes
+])
+@pytest.mark.parametrize("mode", ["resident", "streaming"])
+def test_shapes_and_instantiations_against_oracle(N, k, T, B, iso, mode):
+    """Every (CH, K, thread-bucket) instantiation of the resident kernels and the chunk tilings of the
+    streaming kernels, iterates included, against the oracle on graphs generated here."""
+    from mixed_graph_admm_b200 import _cabi, synth
+    from mixed_graph_admm_b200.ADMM import ADMM_algorithm
+    from oracle import admm_oracle as O
+    t_in = T // 2
+    gi = synth.road_graph(N, 1.4, seed=N + k, isolate_pair=iso)
+    blk = ADMM_algorithm(gi, synth.admm_info(N), use_kNN=True, k=k, u_sigma=50, d_sigma=50, t_in=t_in, T=T, mode=mode)
+    blk.max_ADMM_iter, blk.max_CG_iter, blk.CG_tol, blk.ADMM_tol = 3, 8, -1.0, -1.0
+    blk.keep_iterates = True
+    if mode == "resident":
+        assert _cabi.lib().mga_plan_resident_eligible(blk._plan().handle, 0) == 1
+    y = synth.signals(B, t_in, N, seed=T)
+    x = blk.combined_loop(y.cuda(), print_info=False).cpu()
+    og = O.OracleGraph(nbr=blk.connect_list, u_w=blk.u_ew, d_w=blk.d_ew)
+    prm = O.OracleParams(**synth.admm_info(N), t_in=t_in, T=T)
+    tr = O.admm_combined(og, prm, y, max_admm_iter=3, max_cg_iter=8, cg_tol=-1.0, admm_tol=-1.0)
+    assert rel_err(x, tr.x) <= 1e-5 and max_rel(x, tr.x) <= 2e-5
+    its = {k2: v.cpu() for k2, v in blk.last_iterates.items()}
+    assert rel_err(its["zu"], tr.zu) <= 1e-5 and rel_err(its["zd"], tr.zd) <= 1e-5
+    ldx = O.op_ldr(og, tr.x).double().norm().item()
+    assert (its["phi"].double() - tr.phi.double()).norm().item() <= 1e-5 * max(tr.phi.double().norm().item(), ldx)
+    for name, ref in (("gamma", tr.gamma), ("gamma_u", tr.gamma_u), ("gamma_d", tr.gamma_d)):
+        assert rel_err(its[name], ref) <= 1e-4
+    # residual lists of the last outer iteration
+    np.testing.assert_allclose(blk.x_shift_list[-1], tr.x_shift[-1], rtol=2e-5)
+    np.testing.assert_allclose(blk.p_res_list[-1], tr.p_res[-1], rtol=2e-5, atol=1e-7)
