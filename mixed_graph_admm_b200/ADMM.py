@@ -13,6 +13,7 @@ results come back on the device of the input.
 from __future__ import annotations
 
 import ctypes as C
+import functools
 import math
 
 import numpy as np
@@ -34,6 +35,7 @@ def _device_of(arg):
     return torch.device("cuda", torch.cuda.current_device())
 
 
+@functools.lru_cache(maxsize=None)
 def _regression_consts(t_in):
     """mean(t) and var(t) exactly as the reference forms them: float32 (ADMM.py:772-774)."""
     t = torch.arange(0, t_in, 1).to(torch.float)
@@ -414,8 +416,11 @@ class ADMM_algorithm():
         if differential:
             assert mask is None, 'differential mode does not support mask'
             # the reference computes a differential first guess here and then discards it (ADMM.py:521-529)
-        assert not torch.isnan(self.d_ew).any(), 'Directed graph weights d_ew has NaN value'
-        assert not torch.isnan(self.u_ew).any(), 'Undirected graph weights u_ew has NaN value'
+        wkey = (self.d_ew.data_ptr(), self.d_ew._version, self.u_ew.data_ptr(), self.u_ew._version)
+        if wkey != getattr(self, "_weights_checked", None):     # the reference re-checks every call (ADMM.py:517-518)
+            assert not torch.isnan(self.d_ew).any(), 'Directed graph weights d_ew has NaN value'
+            assert not torch.isnan(self.u_ew).any(), 'Undirected graph weights u_ew has NaN value'
+            self._weights_checked = wkey
         out_device = y.device
         B = y.size(0)
         T, N = self.T, self.n_nodes
@@ -496,8 +501,11 @@ class ADMM_algorithm():
         def rnd(v):      # value rounded to the signal dtype, as a python float
             return float(np_dt(v))
 
-        def scalar(v):   # 0-dim tensor in the signal dtype (quirk Q11)
-            return torch.tensor(float(v), dtype=dtype, device=device)
+        # the tensor-valued entries (quirk Q11) of all iterations at once: 0-dim / (T,) views of four tensors
+        nd = max(n_done, 1)
+        means = torch.from_numpy((diag[:nd][:, [_cabi.DIAG_GLR, _cabi.DIAG_DGTV, _cabi.DIAG_DGLR]] / B).astype(np_dt)).to(device)
+        mean_dx = dx_sum[:nd] / B
+        dxs = torch.from_numpy(np.sqrt((mean_dx * mean_dx).sum(2)).astype(np_dt)).to(device)
 
         for i in range(n_done):
             d = diag[i]
@@ -516,20 +524,19 @@ class ADMM_algorithm():
                 getattr(self, "beta_" + name).append(b)
             pri, dual = [], []
             self.x_shift_list.append(rnd(math.sqrt(d[_cabi.DIAG_DX2])))
-            mean_dx = dx_sum[i] / B
-            self.delta_x_per_step.append(torch.from_numpy(np.sqrt((mean_dx * mean_dx).sum(1)).astype(np_dt)).to(device))
+            self.delta_x_per_step.append(dxs[i])
             pri.append(rnd(math.sqrt(d[_cabi.DIAG_X_ZU2])))
             dual.append(rnd(math.sqrt(d[_cabi.DIAG_DZU2])))
-            self.GLR_list.append(scalar(d[_cabi.DIAG_GLR] / B))
+            self.GLR_list.append(means[i, 0])
             self.recover_list.append(rnd(math.sqrt(d[_cabi.DIAG_RECOVER2])))
             if with_phi:
                 pri.append(rnd(math.sqrt(d[_cabi.DIAG_PHI_LDX2])))
                 dual.append(rnd(math.sqrt(d[_cabi.DIAG_DPHI2])))
-                self.DGTV_list.append(scalar(d[_cabi.DIAG_DGTV] / B))
+                self.DGTV_list.append(means[i, 1])
             if with_zd:
                 pri.append(rnd(math.sqrt(d[_cabi.DIAG_X_ZD2])))
                 dual.append(rnd(math.sqrt(d[_cabi.DIAG_DZD2])))
-                self.DGLR_list.append(scalar(d[_cabi.DIAG_DGLR] / B))
+                self.DGLR_list.append(means[i, 2])
             if print_info:
                 zd_it = its[2] if with_zd else None
                 print(f'ADMM iters {i}: x_CG_iters {its[0]}, zu_CG_iters {its[1]}, zd_CG_iters {zd_it}, '
