@@ -170,7 +170,7 @@ bool resident_eligible(const mga_plan*, int dtype);
 int resident_smem_bytes(const mga_plan*, int* threads);
 int resident_cg(mga_plan*, int system, const mga_params*, const void* rhs, void* x, int64_t B, int n_cg, void* alpha,
                 void* beta, cudaStream_t st);
-int resident_admm(mga_plan*, const mga_params*, const void* y, void* x_out, int64_t B, int n_outer, int n_cg,
+int resident_admm(mga_plan*, const mga_params*, const void* y, const void* mask, void* x_out, int64_t B, int n_outer, int n_cg,
                   double t_mean, double t_var, int want_diag, const mga_admm_outputs* outs, cudaStream_t st);
 
 }  // namespace mga

@@ -532,14 +532,14 @@ int mga_admm_solve(mga_plan* p, const mga_params* prm, const void* y, int y_rows
   mga_admm_outputs none{};
   if (!outs) outs = &none;
   const bool fixed = cg_tol <= 0 && admm_tol <= 0;
-  const bool can_res = forecast && fixed && prm->ablation == MGA_ABL_NONE && resident_eligible(p, dtype);
+  const bool can_res = fixed && prm->ablation == MGA_ABL_NONE && resident_eligible(p, dtype);     // forecast or mask mode
   if (mode == MGA_MODE_RESIDENT && !can_res) {
     set_error("mga_admm_solve: resident mode needs fp32, fixed iteration counts, ablation None, time-invariant "
               "weights, N <= 512, T <= 24, kd <= 9");
     return MGA_ERR_UNSUPPORTED;
   }
   if (mode != MGA_MODE_STREAMING && mode != MGA_MODE_STREAMING_POINT && can_res)
-    return resident_admm(p, prm, y, x_out, B, n_outer, max_cg, t_mean, t_var, want_diag, outs, (cudaStream_t)stream);
+    return resident_admm(p, prm, y, mask, x_out, B, n_outer, max_cg, t_mean, t_var, want_diag, outs, (cudaStream_t)stream);
   if (mode != MGA_MODE_STREAMING_POINT && forecast && fixed && prm->ablation == MGA_ABL_NONE && stream2_eligible(p, dtype))
     return stream2_admm(p, prm, y, x_out, B, n_outer, max_cg, t_mean, t_var, want_diag, outs, (cudaStream_t)stream);
   return stream_admm(p, prm, y, y_rows, mask, x_out, B, dtype, n_outer, max_cg, cg_tol, admm_tol, t_mean, t_var,

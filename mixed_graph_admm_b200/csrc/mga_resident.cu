@@ -92,7 +92,7 @@ int resident_cg(mga_plan* p, int system, const mga_params* m, const void* rhs, v
   return MGA_ERR_UNSUPPORTED;
 }
 
-int resident_admm(mga_plan* p, const mga_params* m, const void* y, void* x_out, int64_t B, int n_outer, int n_cg,
+int resident_admm(mga_plan* p, const mga_params* m, const void* y, const void* mask, void* x_out, int64_t B, int n_outer, int n_cg,
                   double t_mean, double t_var, int diag_flags, const mga_admm_outputs* outs, cudaStream_t st) {
   const GraphDev& g = p->g;
   ResArgs a{};
@@ -102,6 +102,7 @@ int resident_admm(mga_plan* p, const mga_params* m, const void* y, void* x_out, 
   a.n_outer = n_outer; a.n_cg = n_cg;
   a.B = B;
   a.y = static_cast<const float*>(y);
+  a.mask = static_cast<const float*>(mask);
   a.x_out = static_cast<float*>(x_out);
   a.out[ST_ZU] = static_cast<float*>(outs->zu);
   a.out[ST_ZD] = static_cast<float*>(outs->zd);

@@ -68,6 +68,7 @@ struct ResArgs {
   const int2* ell_ent;        // (ell_total) step-major: (internal src or N, weight bits) per lane
   int ell_total;
   const float* y; float* x_out;
+  const float* mask;          // mask / interpolation mode (ADMM.py:373-376, 783-811): (B, T, N), y then has T rows
   float* out[ST_COUNT];       // optional per-window outputs (index by ST_*; ST_X unused)
   float* scratch;             // gridDim.x * ST_COUNT * N * TP floats when !state_in_smem
   int* next_window;           // zeroed per launch: windows beyond the first gridDim.x are handed out dynamically
@@ -233,8 +234,9 @@ struct Ctx {
   }
 
   // out = A v for the x / z_d systems: diag(v) + c * L_d^T L_d v  (ADMM.py:371-387, 392-394)
-  template <bool XSYS>
-  __device__ __forceinline__ void apply_cldr(const float (&v)[TS], float (&out)[TS], float a, float c) {
+  // MASKED: H = the caller's elementwise mask m (LHS_x(x, mask), ADMM.py:375-376) instead of "rows t < t_in"
+  template <bool XSYS, bool MASKED>
+  __device__ __forceinline__ void apply_cldr(const float (&v)[TS], float (&out)[TS], float a, float c, const float (&m)[TS]) {
     put(pbuf, v);
     __syncthreads();
     {
@@ -251,7 +253,7 @@ struct Ctx {
     for (int k = 0; k < TS; ++k) {
       const float q = (k == 0) ? qprev : qs[k - 1];
       const float l = q - (out[k] + wself * qs[k]);   // row T-1: f = 0 because qs[T-1] = 0; Q1 is moot as q[0] = 0
-      if (XSYS) out[k] = ((t0 + k < t_in ? v[k] : 0.f) + a * v[k]) + c * l;
+      if (XSYS) out[k] = ((MASKED ? v[k] * m[k] : (t0 + k < t_in ? v[k] : 0.f)) + a * v[k]) + c * l;
       else out[k] = c * l + a * v[k];
     }
   }
@@ -267,21 +269,22 @@ struct Ctx {
     for (int k = 0; k < TS; ++k) out[k] = c * (v[k] - out[k]) + a * v[k];
   }
 
-  template <int SYS>
-  __device__ __forceinline__ void apply(const float (&v)[TS], float (&out)[TS], float a, float c) {
+  template <int SYS, bool MASKED>
+  __device__ __forceinline__ void apply(const float (&v)[TS], float (&out)[TS], float a, float c, const float (&m)[TS]) {
     if (SYS == MGA_SYS_ZU) apply_lu(v, out, a, c);
-    else if (SYS == MGA_SYS_X) apply_cldr<true>(v, out, a, c);
-    else apply_cldr<false>(v, out, a, c);
+    else if (SYS == MGA_SYS_X) apply_cldr<true, MASKED>(v, out, a, c, m);
+    else apply_cldr<false, false>(v, out, a, c, m);
   }
 
   // CG_solver, fixed iteration count (ADMM.py:329-368 with an unreachable tolerance; the
   // arithmetic is unguarded like the reference's, quirk Q10).  r holds the right-hand side on
   // entry, x the warm start; x holds the solution on exit.
-  template <int SYS>
+  // MASK0: the mask goes to the initial residual only, the iterations use H = "rows t < t_in" (quirk Q4, ADMM.py:344-349)
+  template <int SYS, bool MASK0>
   __device__ __forceinline__ void cg(float (&x)[TS], float (&r)[TS], float a, float c, int n_cg, float* alpha_out,
-                                     float* beta_out, int64_t B) {
+                                     float* beta_out, int64_t B, const float (&m0)[TS]) {
     float p[TS], ap[TS];
-    apply<SYS>(x, ap, a, c);
+    apply<SYS, MASK0>(x, ap, a, c, m0);
     float loc = 0.f;
 #pragma unroll
     for (int k = 0; k < TS; ++k) {
@@ -291,7 +294,7 @@ struct Ctx {
     }
     float rr = bsum(loc);
     for (int it = 0; it < n_cg; ++it) {
-      apply<SYS>(p, ap, a, c);
+      apply<SYS, false>(p, ap, a, c, m0);
       loc = 0.f;
 #pragma unroll
       for (int k = 0; k < TS; ++k) loc += p[k] * ap[k];
@@ -437,9 +440,9 @@ __global__ void __launch_bounds__(MAXT, MINB) k_cg_resident(const ResArgs a, con
     }
     float* al = g.alpha ? g.alpha + b : nullptr;
     float* be = g.beta ? g.beta + b : nullptr;
-    if (g.system == MGA_SYS_X) c.template cg<MGA_SYS_X>(x, r, g.a, g.c, g.n_cg, al, be, a.B);
-    else if (g.system == MGA_SYS_ZU) c.template cg<MGA_SYS_ZU>(x, r, g.a, g.c, g.n_cg, al, be, a.B);
-    else c.template cg<MGA_SYS_ZD>(x, r, g.a, g.c, g.n_cg, al, be, a.B);
+    if (g.system == MGA_SYS_X) c.template cg<MGA_SYS_X, false>(x, r, g.a, g.c, g.n_cg, al, be, a.B, r);
+    else if (g.system == MGA_SYS_ZU) c.template cg<MGA_SYS_ZU, false>(x, r, g.a, g.c, g.n_cg, al, be, a.B, r);
+    else c.template cg<MGA_SYS_ZD, false>(x, r, g.a, g.c, g.n_cg, al, be, a.B, r);
     if (cta.active) {
 #pragma unroll
       for (int k = 0; k < TS; ++k)
@@ -451,7 +454,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_cg_resident(const ResArgs a, con
   }
 }
 
-template <int CH, int K, int MAXT, int MINB>
+template <int CH, int K, int MAXT, int MINB, bool MASKM>
 __global__ void __launch_bounds__(MAXT, MINB) k_admm_resident(const ResArgs a) {
   constexpr int TS = 4 * CH;
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -495,26 +498,43 @@ __global__ void __launch_bounds__(MAXT, MINB) k_admm_resident(const ResArgs a) {
   // neighbours near the end of the batch run faster and pick up more of the tail.
   int& s_next = *reinterpret_cast<int*>(red + 64);
   for (int64_t b = blockIdx.x; b < a.B;) {
-    const float* yw = a.y + (size_t)b * t_in * N + orig;
-    // ---- initial_guess (ADMM.py:766-781) and initial state (ADMM.py:537-544)
+    const int y_rows = MASKM ? T : t_in;
+    const float* yw = a.y + (size_t)b * y_rows * N + orig;
+    const float* mw = MASKM ? a.mask + (size_t)b * T * N + orig : nullptr;
+    // ---- initial_guess (ADMM.py:766-781) / initial_interpolation (ADMM.py:783-811) and initial state (ADMM.py:537-544)
     {
       float x[TS];
-      float sy = 0.f, sty = 0.f;
-      for (int t = 0; t < t_in; ++t) {
-        const float v = active ? yw[(size_t)t * N] : 0.f;
-        sy += v;
-        sty += (float)t * v;
+      float w, cc;
+      if (MASKM) {
+        float cnt = 0.f, st = 0.f, sy = 0.f, sty = 0.f, st2 = 0.f;
+        for (int t = 0; t < T; ++t) {
+          const float m = active ? mw[(size_t)t * N] : 1.f, v = active ? yw[(size_t)t * N] : 0.f, tt = (float)t;
+          cnt += m; st += tt * m; sy += v * m; sty += tt * v * m; st2 += tt * tt * m;
+        }
+        const float tm = st / cnt, ym = sy / cnt, tym = sty / cnt, t2m = st2 / cnt;
+        w = (tym - tm * ym) / (t2m - tm * tm);
+        cc = ym - w * tm;
+      } else {
+        float sy = 0.f, sty = 0.f;
+        for (int t = 0; t < t_in; ++t) {
+          const float v = active ? yw[(size_t)t * N] : 0.f;
+          sy += v;
+          sty += (float)t * v;
+        }
+        const float my = sy / (float)t_in, mty = sty / (float)t_in;
+        w = (mty - a.t_mean * my) / a.t_var;
+        cc = my - w * a.t_mean;
       }
-      const float my = sy / (float)t_in, mty = sty / (float)t_in;
-      const float w = (mty - a.t_mean * my) / a.t_var;
-      const float cc = my - w * a.t_mean;
       {
         float tenth[TS];
 #pragma unroll
         for (int k = 0; k < TS; ++k) {
           const int t = t0 + k;
           float v = 0.f;
-          if (active && t < T) v = t < t_in ? yw[(size_t)t * N] : w * (float)t + cc;
+          if (active && t < T) {
+            if (MASKM) v = (w * (float)t + cc) * (1.f - mw[(size_t)t * N]) + yw[(size_t)t * N];
+            else v = t < t_in ? yw[(size_t)t * N] : w * (float)t + cc;
+          }
           x[k] = v;
           tenth[k] = (active && t < T) ? 0.1f : 0.f;
         }
@@ -584,7 +604,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_admm_resident(const ResArgs a) {
           const int t = t0 + k;
           float o = 0.f;
           if (active && t < T) {
-            const float hty = t < t_in ? yw[(size_t)t * N] : 0.f;
+            const float hty = t < y_rows ? yw[(size_t)t * N] : 0.f;
             o = r[k] - (v[k] + f[k]) / 2.f + hty;
           }
           r[k] = o;
@@ -594,7 +614,14 @@ __global__ void __launch_bounds__(MAXT, MINB) k_admm_resident(const ResArgs a) {
       {
         float x[TS];
         ld_state(ST_X, x);
-        c.template cg<MGA_SYS_X>(x, r, a.ax, a.cx, a.n_cg, al, be, a.B);
+        if (MASKM) {
+          float m0[TS];
+#pragma unroll
+          for (int k = 0; k < TS; ++k) m0[k] = (active && t0 + k < T) ? mw[(size_t)(t0 + k) * N] : 0.f;
+          c.template cg<MGA_SYS_X, true>(x, r, a.ax, a.cx, a.n_cg, al, be, a.B, m0);
+        } else {
+          c.template cg<MGA_SYS_X, false>(x, r, a.ax, a.cx, a.n_cg, al, be, a.B, r);
+        }
         if (a.want_diag) {
           float xo[TS];
           ld_state(ST_X, xo);
@@ -619,8 +646,8 @@ __global__ void __launch_bounds__(MAXT, MINB) k_admm_resident(const ResArgs a) {
       {
         float z[TS];
         ld_state(ST_ZU, z);
-        c.template cg<MGA_SYS_ZU>(z, r, a.azu, a.czu, a.n_cg, al ? al + sys_stride : nullptr,
-                                  be ? be + sys_stride : nullptr, a.B);
+        c.template cg<MGA_SYS_ZU, false>(z, r, a.azu, a.czu, a.n_cg, al ? al + sys_stride : nullptr,
+                                         be ? be + sys_stride : nullptr, a.B, r);
         float x[TS], g[TS];
         ld_state(ST_X, x);
         ld_state(ST_GU, g);
@@ -648,8 +675,8 @@ __global__ void __launch_bounds__(MAXT, MINB) k_admm_resident(const ResArgs a) {
       {
         float z[TS];
         ld_state(ST_ZD, z);
-        c.template cg<MGA_SYS_ZD>(z, r, a.azd, a.czd, a.n_cg, al ? al + 2 * sys_stride : nullptr,
-                                  be ? be + 2 * sys_stride : nullptr, a.B);
+        c.template cg<MGA_SYS_ZD, false>(z, r, a.azd, a.czd, a.n_cg, al ? al + 2 * sys_stride : nullptr,
+                                         be ? be + 2 * sys_stride : nullptr, a.B, r);
         float x[TS], g[TS];
         ld_state(ST_X, x);
         ld_state(ST_GD, g);
@@ -689,7 +716,10 @@ __global__ void __launch_bounds__(MAXT, MINB) k_admm_resident(const ResArgs a) {
             const int t = t0 + k;
             if (active && t < T) {
               sg += x[k] * (x[k] - lux[k]);
-              if (t < t_in) {
+              if (MASKM) {             // ||x * mask - y|| (ADMM.py:620-621)
+                const float h = x[k] * mw[(size_t)t * N] - yw[(size_t)t * N];
+                sr += h * h;
+              } else if (t < t_in) {
                 const float h = x[k] - yw[(size_t)t * N];
                 sr += h * h;
               }
@@ -821,10 +851,9 @@ inline int res_forced_ch() {
   return e ? std::atoi(e) : 0;
 }
 
-template <int CH, int K, int MAXT, int MINB>
+template <int CH, int K, int MAXT, int MINB, bool MASKM>
 inline int launch_res(mga_plan* p, ResArgs& a, const ResGeom& geo, cudaStream_t st) {
-  const GraphDev& g = p->g;
-  auto kern = k_admm_resident<CH, K, MAXT, MINB>;
+  auto kern = k_admm_resident<CH, K, MAXT, MINB, MASKM>;
   const size_t core = geo.core_bytes;
   const size_t with_state = core + geo.state_bytes;
   // State in shared memory only if it does not cost residency: compare CTAs/SM both ways.
@@ -879,13 +908,18 @@ inline int pick_threads_cg(mga_plan* p, ResArgs& a, const CgArgs& g, const ResGe
   return launch_res_cg<CH, K, 1024, 1>(p, a, g, geo, st);
 }
 
+template <int CH, int K, bool MASKM>
+inline int pick_threads_m(mga_plan* p, ResArgs& a, const ResGeom& geo, cudaStream_t st) {
+  if (geo.threads <= 192) return launch_res<CH, K, 192, (MGA_RES_MINB > 1 ? 3 : 1), MASKM>(p, a, geo, st);
+  if (geo.threads <= 320) return launch_res<CH, K, 320, MGA_RES_MINB, MASKM>(p, a, geo, st);
+  if (geo.threads <= 512) return launch_res<CH, K, 512, 1, MASKM>(p, a, geo, st);
+  if (geo.threads <= 640) return launch_res<CH, K, 640, 1, MASKM>(p, a, geo, st);      // 2 slabs x 320: 96 registers, no spills
+  return launch_res<CH, K, 1024, 1, MASKM>(p, a, geo, st);
+}
+
 template <int CH, int K>
 inline int pick_threads(mga_plan* p, ResArgs& a, const ResGeom& geo, cudaStream_t st) {
-  if (geo.threads <= 192) return launch_res<CH, K, 192, (MGA_RES_MINB > 1 ? 3 : 1)>(p, a, geo, st);
-  if (geo.threads <= 320) return launch_res<CH, K, 320, MGA_RES_MINB>(p, a, geo, st);
-  if (geo.threads <= 512) return launch_res<CH, K, 512, 1>(p, a, geo, st);
-  if (geo.threads <= 640) return launch_res<CH, K, 640, 1>(p, a, geo, st);         // 2 slabs x 320: 96 registers, no spills
-  return launch_res<CH, K, 1024, 1>(p, a, geo, st);
+  return a.mask ? pick_threads_m<CH, K, true>(p, a, geo, st) : pick_threads_m<CH, K, false>(p, a, geo, st);
 }
 
 }  // namespace mga

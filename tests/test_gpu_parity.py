@@ -21,7 +21,7 @@ OP_TOL = {torch.float32: 1e-6, torch.float64: 1e-14}
 
 
 def _resident_ok(g):
-    return (g.dtype == torch.float32 and g.mask is None and g.ctor.get("ablation", "None") == "None"
+    return (g.dtype == torch.float32 and g.ctor.get("ablation", "None") == "None"
             and int(g.ctor.get("skip_connection", 1)) == 1)
 
 
@@ -120,7 +120,7 @@ def test_combined_loop_resident_matches_reference(name):
     g = Golden(name)
     blk = solver_from_golden(g, mode="resident")
     blk.keep_iterates = True
-    x = blk.combined_loop(g.y, print_info=False)          # CPU in -> CPU out, like the reference's callers
+    x = blk.combined_loop(g.y, mask=g.mask, print_info=False)          # CPU in -> CPU out, like the reference's callers
     assert not x.is_cuda
     _check_iterates(blk, x, g, TOL[g.dtype])
     _check_lists(blk, g, 2e-5)
