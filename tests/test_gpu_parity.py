@@ -379,3 +379,29 @@ def test_shapes_and_instantiations_against_oracle(N, k, T, B, iso, mode):
     # residual lists of the last outer iteration
     np.testing.assert_allclose(blk.x_shift_list[-1], tr.x_shift[-1], rtol=2e-5)
     np.testing.assert_allclose(blk.p_res_list[-1], tr.p_res[-1], rtol=2e-5, atol=1e-7)
+
+
+def test_time_varying_edge_weights_match_oracle():
+    """callers may replace u_ew / d_ew by per-time-step tables (T,N,k) / (T-1,N,K) (the
+    'unrolling' follow-up learns them).  The plan must notice that the slices differ, leave the resident and
+    chunked paths (both assume time-invariant tables) and still match the reference arithmetic."""
+    from mixed_graph_admm_b200 import _cabi
+    from oracle import admm_oracle as O
+    g = Golden("pems08_f32")
+    blk = solver_from_golden(g, mode="auto")
+    gen = torch.Generator().manual_seed(11)
+    blk.u_ew = blk.u_ew * (0.8 + 0.4 * torch.rand(blk.u_ew.shape, generator=gen))
+    blk.d_ew = blk.d_ew * (0.8 + 0.4 * torch.rand(blk.d_ew.shape, generator=gen))
+    assert blk.u_ew.dim() == 3 and not torch.equal(blk.u_ew[0], blk.u_ew[1])
+    assert _cabi.lib().mga_plan_resident_eligible(blk._plan().handle, 0) == 0
+    blk.max_ADMM_iter, blk.max_CG_iter, blk.CG_tol, blk.ADMM_tol = 3, 8, -1.0, -1.0
+    y = g.y
+    x = blk.combined_loop(y.cuda(), print_info=False).cpu()
+    og = O.OracleGraph(nbr=blk.connect_list, u_w=blk.u_ew, d_w=blk.d_ew)
+    prm = O.OracleParams(**g.admm_info, t_in=g.ctor["t_in"], T=g.ctor["T"])
+    tr = O.admm_combined(og, prm, y, max_admm_iter=3, max_cg_iter=8, cg_tol=-1.0, admm_tol=-1.0)
+    assert rel_err(x, tr.x) <= 1e-5 and max_rel(x, tr.x) <= 2e-5
+    xo = torch.rand(2, g.ctor["T"], g.meta["n_nodes"], 1, generator=gen)
+    for fn, ofn in ((blk.apply_op_Lu, O.op_lu), (blk.apply_op_Ldr, O.op_ldr), (blk.apply_op_Ldr_T, O.op_ldr_t),
+                    (blk.apply_op_cLdr, O.op_cldr)):
+        assert rel_err(fn(xo), ofn(og, xo)) <= 1e-6
