@@ -232,9 +232,18 @@ int mga_plan_create(const mga_graph_desc* d, int device, mga_plan** out) {
   if (d->temporal == MGA_TEMPORAL_BAND) {
     std::vector<float> bw(d->d_w, d->d_w + (size_t)T * g.skip * N);
     if ((rc = upload(p, bw, &g.band_w))) return fail(rc);
+    // the reference builds these weights identical for every node (ADMM.py:44-50): keep one (T, skip) copy then
+    bool uniform = true;
+    std::vector<float> bu((size_t)T * g.skip);
+    for (size_t k = 0; k < bu.size() && uniform; ++k) {
+      bu[k] = bw[k * N];
+      for (int i = 1; i < N && uniform; ++i) uniform = bw[k * N + i] == bu[k];
+    }
+    p->band_uniform = nullptr;
+    if (uniform && (rc = upload(p, bu, &p->band_uniform))) return fail(rc);
   }
   // resident-kernel schedule: only for time-invariant tables of a size one CTA can own
-  if (d->temporal != MGA_TEMPORAL_BAND && g.u_wT == 1 && g.d_wT == 1 && N <= 1024) {
+  if (g.u_wT == 1 && g.d_wT == 1 && N <= 1024) {      // (banded line graph: empty temporal tables, the stencil is per node)
     ResidentSchedule sc;
     build_resident_schedule(N, g.kd, p->h_nbr_d.data(), p->h_d_w.data(), g.ku, p->h_nbr_u.data(), p->h_u_w.data(),
                             p->h_csr_ptr.data(), p->h_csr_src.data(), p->h_csr_w.data(), &sc);
@@ -496,7 +505,8 @@ int mga_cg_solve(mga_plan* p, int system, const mga_params* prm, const void* rhs
     return MGA_ERR_INVALID;
   }
   // fixed iteration count, forecasting operator, a window that fits one CTA: the whole solve in one launch
-  const bool can_res = tol <= 0 && !mask_first && max_iter > 0 && prm->ablation == MGA_ABL_NONE && resident_eligible(p, dtype);
+  const bool can_res = tol <= 0 && !mask_first && max_iter > 0 && prm->ablation == MGA_ABL_NONE && resident_eligible(p, dtype) &&
+                       p->g.temporal != MGA_TEMPORAL_BAND;
   if (p->cg_mode == MGA_MODE_RESIDENT && !can_res) {
     set_error("mga_cg_solve: resident mode needs fp32, tol <= 0, no mask, ablation None and a resident-eligible plan");
     return MGA_ERR_UNSUPPORTED;
@@ -532,7 +542,8 @@ int mga_admm_solve(mga_plan* p, const mga_params* prm, const void* y, int y_rows
   mga_admm_outputs none{};
   if (!outs) outs = &none;
   const bool fixed = cg_tol <= 0 && admm_tol <= 0;
-  const bool can_res = fixed && prm->ablation == MGA_ABL_NONE && resident_eligible(p, dtype);     // forecast or mask mode
+  const bool can_res = fixed && prm->ablation == MGA_ABL_NONE && resident_eligible(p, dtype) &&     // forecast or mask mode
+                       !(mask && p->g.temporal == MGA_TEMPORAL_BAND);
   if (mode == MGA_MODE_RESIDENT && !can_res) {
     set_error("mga_admm_solve: resident mode needs fp32, fixed iteration counts, ablation None, time-invariant "
               "weights, N <= 512, T <= 24, kd <= 9");

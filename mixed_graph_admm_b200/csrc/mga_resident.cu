@@ -30,7 +30,6 @@ static bool geometry(const mga_plan* p, ResGeom* geo) {
 bool resident_eligible(const mga_plan* p, int dtype) {
   const GraphDev& g = p->g;
   if (dtype != MGA_F32) return false;
-  if (g.temporal == MGA_TEMPORAL_BAND) return false;
   if (g.T > kResMaxT) return false;
   if (g.u_wT != 1 || g.d_wT != 1) return false;
   if (!p->has_sched || std::max(p->r_kd, p->r_ku) > kResMaxK) return false;
@@ -103,6 +102,11 @@ int resident_admm(mga_plan* p, const mga_params* m, const void* y, const void* m
   a.B = B;
   a.y = static_cast<const float*>(y);
   a.mask = static_cast<const float*>(mask);
+  a.band_w = g.temporal == MGA_TEMPORAL_BAND ? g.band_w : nullptr;
+  a.band_uniform = g.temporal == MGA_TEMPORAL_BAND ? p->band_uniform : nullptr;
+  a.skip = g.skip;
+  a.band_floats = g.temporal == MGA_TEMPORAL_BAND ? (g.T * g.skip + 3) / 4 * 4 : 0;
+  if (a.band_w && a.mask) { set_error("resident: mask mode on the banded line graph is not built"); return MGA_ERR_UNSUPPORTED; }
   a.x_out = static_cast<float*>(x_out);
   a.out[ST_ZU] = static_cast<float*>(outs->zu);
   a.out[ST_ZD] = static_cast<float*>(outs->zd);

@@ -68,6 +68,9 @@ struct ResArgs {
   const int2* ell_ent;        // (ell_total) step-major: (internal src or N, weight bits) per lane
   int ell_total;
   const float* y; float* x_out;
+  const float* band_w;        // banded line graph: (T, skip, N) weights (caller's node order), else NULL
+  const float* band_uniform;  // (T, skip) when the weights do not depend on the node (as the reference builds them)
+  int skip, band_floats;      // band_floats: shared-memory floats reserved for the staged (T, skip) table (multiple of 4)
   const float* mask;          // mask / interpolation mode (ADMM.py:373-376, 783-811): (B, T, N), y then has T rows
   float* out[ST_COUNT];       // optional per-window outputs (index by ST_*; ST_X unused)
   float* scratch;             // gridDim.x * ST_COUNT * N * TP floats when !state_in_smem
@@ -121,6 +124,10 @@ struct Ctx {
   uint32_t t0b;              // t0 * 4
   float* red;                // 2 x 32
   int red_sel;
+  // banded line graph (use_line_graph with skip_connection > 1, ADMM.py:41-52): L_d couples a node only with
+  // its own past, weights (T, skip, N); no neighbour gathers, the stencil reads the thread's own staged row
+  const float* bw;           // band weights + this thread's node in the caller's numbering
+  int skip, bN;              // stencil length; stride between consecutive (t, s) weights
 
   // Block sum, result in every thread.  Warp partials go to a 32-float row (zero beyond the warp count);
   // after the barrier every thread reads the whole row as broadcast 128-bit loads and adds it up in one
@@ -213,6 +220,52 @@ struct Ctx {
     }
   }
 
+  // q[k] = (L_d v)[t0 + k] for the banded graph (ADMM.py:158-164): q[t] = v[t] - sum_s w[t][s] v[t-1-s].
+  // v is in registers AND staged in `buf` (own row: the columns before t0 belong to this node's earlier slabs).
+  // A register window slides one step into the past per stencil tap, so each tap costs one scalar load.
+  __device__ __forceinline__ void band_ldr(const float (&v)[TS], const float* buf, float (&q)[TS]) const {
+    float win[TS], acc[TS];
+#pragma unroll
+    for (int k = 0; k < TS; ++k) { win[k] = k > 0 ? v[k - 1] : (t0 > 0 ? buf[own - 1] : 0.f); acc[k] = 0.f; }
+    for (int s = 0; s < skip; ++s) {
+#pragma unroll
+      for (int k = 0; k < TS; ++k) {
+        const int t = t0 + k;
+        if (t < T && t - 1 - s >= 0) acc[k] += bw[(t * skip + s) * bN] * win[k];
+      }
+#pragma unroll
+      for (int k = TS - 1; k > 0; --k) win[k] = win[k - 1];
+      win[0] = (t0 - 2 - s >= 0) ? buf[own - 2 - s] : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < TS; ++k) {
+      const int t = t0 + k;
+      q[k] = (t >= 1 && t < T) ? v[k] - acc[k] : 0.f;
+    }
+  }
+  // l[k] = (L_d^T v)[t0 + k] with the row rules of ADMM.py:187-194 (row T-1 keeps v, row 0 has no identity
+  // term): l[t] = v[t] - sum_s w[t+1+s][s] v[t+1+s]; the window slides into the future
+  __device__ __forceinline__ void band_ldrt(const float (&v)[TS], const float* buf, float (&l)[TS]) const {
+    float win[TS], f[TS];
+#pragma unroll
+    for (int k = 0; k < TS; ++k) { win[k] = k < TS - 1 ? v[k + 1] : (t0 + TS < T ? buf[own + TS] : 0.f); f[k] = 0.f; }
+    for (int s = 0; s < skip; ++s) {
+#pragma unroll
+      for (int k = 0; k < TS; ++k) {
+        const int ts = t0 + k + 1 + s;
+        if (ts < T) f[k] += bw[(ts * skip + s) * bN] * win[k];
+      }
+#pragma unroll
+      for (int k = 0; k < TS - 1; ++k) win[k] = win[k + 1];
+      win[TS - 1] = (t0 + TS + 1 + s < T) ? buf[own + TS + 1 + s] : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < TS; ++k) {
+      const int t = t0 + k;
+      l[k] = t >= T ? 0.f : (t == T - 1 ? v[k] : (t == 0 ? -f[k] : v[k] - f[k]));
+    }
+  }
+
   // f[k] = sum over the in-list of w * qbuf[src][t0+k]   (ADMM.py:200-209 as a gather; qbuf holds the
   // vector shifted by one time step, so this is the "father" sum at t0+k).  Two entries per trip, the
   // next two (row address, weight) pairs are fetched a trip ahead; the table has two spare steps at
@@ -258,6 +311,23 @@ struct Ctx {
     }
   }
 
+  // the same system matrices on the banded line graph
+  template <bool XSYS, bool MASKED>
+  __device__ __forceinline__ void apply_cldr_band(const float (&v)[TS], float (&out)[TS], float a, float c, const float (&m)[TS]) {
+    put(pbuf, v);
+    __syncthreads();
+    float q[TS];
+    band_ldr(v, pbuf, q);
+    put(qbuf, q);
+    __syncthreads();
+    band_ldrt(q, qbuf, out);
+#pragma unroll
+    for (int k = 0; k < TS; ++k) {
+      if (XSYS) out[k] = ((MASKED ? v[k] * m[k] : (t0 + k < t_in ? v[k] : 0.f)) + a * v[k]) + c * out[k];
+      else out[k] = c * out[k] + a * v[k];
+    }
+  }
+
   // out = mu_u L_u v + (rho_u/2) v  (ADMM.py:389-390)
   __device__ __forceinline__ void apply_lu(const float (&v)[TS], float (&out)[TS], float a, float c) {
     put(pbuf, v);
@@ -269,9 +339,11 @@ struct Ctx {
     for (int k = 0; k < TS; ++k) out[k] = c * (v[k] - out[k]) + a * v[k];
   }
 
-  template <int SYS, bool MASKED>
+  template <int SYS, bool MASKED, bool BAND>
   __device__ __forceinline__ void apply(const float (&v)[TS], float (&out)[TS], float a, float c, const float (&m)[TS]) {
     if (SYS == MGA_SYS_ZU) apply_lu(v, out, a, c);
+    else if (BAND && SYS == MGA_SYS_X) apply_cldr_band<true, MASKED>(v, out, a, c, m);
+    else if (BAND) apply_cldr_band<false, false>(v, out, a, c, m);
     else if (SYS == MGA_SYS_X) apply_cldr<true, MASKED>(v, out, a, c, m);
     else apply_cldr<false, false>(v, out, a, c, m);
   }
@@ -280,11 +352,11 @@ struct Ctx {
   // arithmetic is unguarded like the reference's, quirk Q10).  r holds the right-hand side on
   // entry, x the warm start; x holds the solution on exit.
   // MASK0: the mask goes to the initial residual only, the iterations use H = "rows t < t_in" (quirk Q4, ADMM.py:344-349)
-  template <int SYS, bool MASK0>
+  template <int SYS, bool MASK0, bool BAND = false>
   __device__ __forceinline__ void cg(float (&x)[TS], float (&r)[TS], float a, float c, int n_cg, float* alpha_out,
                                      float* beta_out, int64_t B, const float (&m0)[TS]) {
     float p[TS], ap[TS];
-    apply<SYS, MASK0>(x, ap, a, c, m0);
+    apply<SYS, MASK0, BAND>(x, ap, a, c, m0);
     float loc = 0.f;
 #pragma unroll
     for (int k = 0; k < TS; ++k) {
@@ -294,7 +366,7 @@ struct Ctx {
     }
     float rr = bsum(loc);
     for (int it = 0; it < n_cg; ++it) {
-      apply<SYS, false>(p, ap, a, c, m0);
+      apply<SYS, false, BAND>(p, ap, a, c, m0);
       loc = 0.f;
 #pragma unroll
       for (int k = 0; k < TS; ++k) loc += p[k] * ap[k];
@@ -333,6 +405,7 @@ struct Cta {
   int i, t0, orig;
   bool active;
   float* pbuf; float* qbuf; float* red; float* dred; float* st_smem;
+  float* band_s;             // (T, skip) band weights staged in shared memory (banded line graph with node-invariant weights)
 
   __device__ __forceinline__ void init(const ResArgs& a, unsigned char* smem_raw) {
     constexpr int TS = 4 * CH;
@@ -349,6 +422,8 @@ struct Cta {
     int2* tabu = tabd + K * a.S * a.NT;               // K x (S * NT)
     nxt = reinterpret_cast<float*>(tabu + K * a.S * a.NT);
 #endif
+    band_s = nxt;
+    nxt += a.band_floats;
     st_smem = nxt;
     const int s = threadIdx.x / a.NT;
     i = threadIdx.x - s * a.NT;
@@ -405,6 +480,7 @@ struct Cta {
     orig = active ? a.perm[i] : 0;   // this thread's node in the caller's numbering
     for (int k = threadIdx.x; k < 2 * rows; k += blockDim.x) pbuf[k] = 0.f;
     for (int k = threadIdx.x; k < 64; k += blockDim.x) red[k] = 0.f;     // bsum() relies on zeros beyond the warp count
+    if (a.band_uniform) for (int k = threadIdx.x; k < a.T * a.skip; k += blockDim.x) band_s[k] = a.band_uniform[k];
     __syncthreads();
   }
 };
@@ -454,9 +530,11 @@ __global__ void __launch_bounds__(MAXT, MINB) k_cg_resident(const ResArgs a, con
   }
 }
 
-template <int CH, int K, int MAXT, int MINB, bool MASKM>
+// VAR: 0 = forecasting on the kNN / physical / first-difference temporal graph, 1 = mask mode, 2 = banded line graph
+template <int CH, int K, int MAXT, int MINB, int VAR>
 __global__ void __launch_bounds__(MAXT, MINB) k_admm_resident(const ResArgs a) {
   constexpr int TS = 4 * CH;
+  constexpr bool MASKM = VAR == 1, BANDM = VAR == 2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Cta<CH, K> cta;
   cta.init(a, smem_raw);
@@ -464,6 +542,8 @@ __global__ void __launch_bounds__(MAXT, MINB) k_admm_resident(const ResArgs a) {
   const int N = a.N, T = a.T, TP = a.TP, t_in = a.t_in;
   const int i = cta.i, t0 = cta.t0, orig = cta.orig;
   const bool active = cta.active;
+  c.bw = BANDM ? (a.band_uniform ? cta.band_s : a.band_w + orig) : nullptr;
+  c.skip = a.skip; c.bN = a.band_uniform ? 1 : N;
   float* pbuf = cta.pbuf; float* qbuf = cta.qbuf; float* red = cta.red; float* dred = cta.dred; float* st_smem = cta.st_smem;
 
   // ---- parked ADMM state: [v][node * TP + t] as 128-bit chunks, in shared memory or in this CTA's slice
@@ -544,13 +624,20 @@ __global__ void __launch_bounds__(MAXT, MINB) k_admm_resident(const ResArgs a) {
       // phi = L_d x  (ADMM.py:541)
       c.put(pbuf, x);
       __syncthreads();
-      float qs[TS];
-      c.shifted_ldr(x, qs);
-      c.put(qbuf, qs);
-      __syncthreads();
-      const float qprev = c.has_prev ? qbuf[c.own - 1] : 0.f;
+      if (BANDM) {
+        float q[TS];
+        c.band_ldr(x, pbuf, q);
 #pragma unroll
-      for (int k = 0; k < TS; ++k) x[k] = (k == 0) ? qprev : qs[k - 1];
+        for (int k = 0; k < TS; ++k) x[k] = q[k];
+      } else {
+        float qs[TS];
+        c.shifted_ldr(x, qs);
+        c.put(qbuf, qs);
+        __syncthreads();
+        const float qprev = c.has_prev ? qbuf[c.own - 1] : 0.f;
+#pragma unroll
+        for (int k = 0; k < TS; ++k) x[k] = (k == 0) ? qprev : qs[k - 1];
+      }
       st_state(ST_PHI, x);
       __syncthreads();
     }
@@ -572,26 +659,30 @@ __global__ void __launch_bounds__(MAXT, MINB) k_admm_resident(const ResArgs a) {
         }
         c.put(pbuf, v);
         __syncthreads();
-        {
-          float vs[TS];
-          const float vnext = c.has_next ? pbuf[c.own + TS] : 0.f;
+        if (BANDM) {
+          c.band_ldrt(v, pbuf, r);
+        } else {
+          {
+            float vs[TS];
+            const float vnext = c.has_next ? pbuf[c.own + TS] : 0.f;
 #pragma unroll
-          for (int k = 0; k < TS; ++k) vs[k] = (t0 + k + 1 < T) ? ((k < TS - 1) ? v[k + 1] : vnext) : 0.f;
-          c.put(qbuf, vs);
-        }
-        __syncthreads();
-        c.father_sum(f);
-        {
-          float vs[TS];
-          c.get(qbuf, vs);
+            for (int k = 0; k < TS; ++k) vs[k] = (t0 + k + 1 < T) ? ((k < TS - 1) ? v[k + 1] : vnext) : 0.f;
+            c.put(qbuf, vs);
+          }
+          __syncthreads();
+          c.father_sum(f);
+          {
+            float vs[TS];
+            c.get(qbuf, vs);
 #pragma unroll
-          for (int k = 0; k < TS; ++k) f[k] += c.wself * vs[k];
-        }
+            for (int k = 0; k < TS; ++k) f[k] += c.wself * vs[k];
+          }
 #pragma unroll
-        for (int k = 0; k < TS; ++k) {
-          const int t = t0 + k;
-          // rows of apply_op_Ldr_T: t = T-1 keeps v; t = 0 keeps the identity term only under Q1
-          r[k] = (t == T - 1) ? v[k] : ((t == 0 && !a.q1) ? -f[k] : v[k] - f[k]);
+          for (int k = 0; k < TS; ++k) {
+            const int t = t0 + k;
+            // rows of apply_op_Ldr_T: t = T-1 keeps v; t = 0 keeps the identity term only under Q1
+            r[k] = (t == T - 1) ? v[k] : ((t == 0 && !a.q1) ? -f[k] : v[k] - f[k]);
+          }
         }
         ld_state(ST_ZU, v); ld_state(ST_ZD, f);
 #pragma unroll
@@ -618,9 +709,9 @@ __global__ void __launch_bounds__(MAXT, MINB) k_admm_resident(const ResArgs a) {
           float m0[TS];
 #pragma unroll
           for (int k = 0; k < TS; ++k) m0[k] = (active && t0 + k < T) ? mw[(size_t)(t0 + k) * N] : 0.f;
-          c.template cg<MGA_SYS_X, true>(x, r, a.ax, a.cx, a.n_cg, al, be, a.B, m0);
+          c.template cg<MGA_SYS_X, true, false>(x, r, a.ax, a.cx, a.n_cg, al, be, a.B, m0);
         } else {
-          c.template cg<MGA_SYS_X, false>(x, r, a.ax, a.cx, a.n_cg, al, be, a.B, r);
+          c.template cg<MGA_SYS_X, false, BANDM>(x, r, a.ax, a.cx, a.n_cg, al, be, a.B, r);
         }
         if (a.want_diag) {
           float xo[TS];
@@ -675,7 +766,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_admm_resident(const ResArgs a) {
       {
         float z[TS];
         ld_state(ST_ZD, z);
-        c.template cg<MGA_SYS_ZD, false>(z, r, a.azd, a.czd, a.n_cg, al ? al + 2 * sys_stride : nullptr,
+        c.template cg<MGA_SYS_ZD, false, BANDM>(z, r, a.azd, a.czd, a.n_cg, al ? al + 2 * sys_stride : nullptr,
                                          be ? be + 2 * sys_stride : nullptr, a.B, r);
         float x[TS], g[TS];
         ld_state(ST_X, x);
@@ -702,9 +793,13 @@ __global__ void __launch_bounds__(MAXT, MINB) k_admm_resident(const ResArgs a) {
         ld_state(ST_X, x);
         c.put(pbuf, x);
         __syncthreads();
-        c.shifted_ldr(x, qs);
-        c.put(qbuf, qs);
-        __syncthreads();
+        if (BANDM) {
+          c.band_ldr(x, pbuf, qs);
+        } else {
+          c.shifted_ldr(x, qs);
+          c.put(qbuf, qs);
+          __syncthreads();
+        }
         if (a.want_diag) {     // GLR = x . L_u x, recover = ||Hx - y||^2
           float lux[TS];
 #pragma unroll
@@ -732,10 +827,12 @@ __global__ void __launch_bounds__(MAXT, MINB) k_admm_resident(const ResArgs a) {
 #pragma unroll
         for (int k = 0; k < TS; ++k) bad |= !isfinite(x[k]);
         // x is dead from here: reuse its registers for (L_d x), gamma and phi
-        const float qprev = c.has_prev ? qbuf[c.own - 1] : 0.f;
+        if (!BANDM) {
+          const float qprev = c.has_prev ? qbuf[c.own - 1] : 0.f;
 #pragma unroll
-        for (int k = TS - 1; k > 0; --k) qs[k] = qs[k - 1];        // qs[k] = (L_d x)[t0 + k]
-        qs[0] = qprev;
+          for (int k = TS - 1; k > 0; --k) qs[k] = qs[k - 1];        // qs[k] = (L_d x)[t0 + k]
+          qs[0] = qprev;
+        }
         float gam[TS], phi[TS];
         ld_state(ST_GAM, gam);
         ld_state(ST_PHI, phi);
@@ -839,6 +936,7 @@ inline bool res_geometry(const GraphDev& g, int kd_eff, int ku_eff, int ell_tota
 #if MGA_RES_TAB_SMEM
     r.core_bytes += (size_t)(2 * Kt) * r.threads * 8;
 #endif
+    if (g.temporal == MGA_TEMPORAL_BAND) r.core_bytes += (size_t)((g.T * g.skip + 3) / 4 * 4) * 4;
     r.state_bytes = (size_t)ST_COUNT * g.N * r.TP * 4;
     *out = r;
     return true;
@@ -851,9 +949,9 @@ inline int res_forced_ch() {
   return e ? std::atoi(e) : 0;
 }
 
-template <int CH, int K, int MAXT, int MINB, bool MASKM>
+template <int CH, int K, int MAXT, int MINB, int VAR>
 inline int launch_res(mga_plan* p, ResArgs& a, const ResGeom& geo, cudaStream_t st) {
-  auto kern = k_admm_resident<CH, K, MAXT, MINB, MASKM>;
+  auto kern = k_admm_resident<CH, K, MAXT, MINB, VAR>;
   const size_t core = geo.core_bytes;
   const size_t with_state = core + geo.state_bytes;
   // State in shared memory only if it does not cost residency: compare CTAs/SM both ways.
@@ -908,7 +1006,7 @@ inline int pick_threads_cg(mga_plan* p, ResArgs& a, const CgArgs& g, const ResGe
   return launch_res_cg<CH, K, 1024, 1>(p, a, g, geo, st);
 }
 
-template <int CH, int K, bool MASKM>
+template <int CH, int K, int MASKM>
 inline int pick_threads_m(mga_plan* p, ResArgs& a, const ResGeom& geo, cudaStream_t st) {
   if (geo.threads <= 192) return launch_res<CH, K, 192, (MGA_RES_MINB > 1 ? 3 : 1), MASKM>(p, a, geo, st);
   if (geo.threads <= 320) return launch_res<CH, K, 320, MGA_RES_MINB, MASKM>(p, a, geo, st);
@@ -919,7 +1017,8 @@ inline int pick_threads_m(mga_plan* p, ResArgs& a, const ResGeom& geo, cudaStrea
 
 template <int CH, int K>
 inline int pick_threads(mga_plan* p, ResArgs& a, const ResGeom& geo, cudaStream_t st) {
-  return a.mask ? pick_threads_m<CH, K, true>(p, a, geo, st) : pick_threads_m<CH, K, false>(p, a, geo, st);
+  if (a.band_w) return pick_threads_m<CH, K, 2>(p, a, geo, st);
+  return a.mask ? pick_threads_m<CH, K, 1>(p, a, geo, st) : pick_threads_m<CH, K, 0>(p, a, geo, st);
 }
 
 }  // namespace mga

@@ -48,12 +48,13 @@ for name, kw, dtype, B, b_cpu, fixed, use_mask in VARIANTS:
     for _ in range(2):
         x = blk.combined_loop(yd, mask=md, print_info=False)
     torch.cuda.synchronize()
-    reps = 3
-    t0 = time.perf_counter()
-    for _ in range(reps):
+    times = []
+    for _ in range(7):
+        t0 = time.perf_counter()
         x = blk.combined_loop(yd, mask=md, print_info=False)
-    torch.cuda.synchronize()
-    gpu_s = (time.perf_counter() - t0) / reps
+        torch.cuda.synchronize()
+        times.append(time.perf_counter() - t0)
+    gpu_s = sorted(times)[len(times) // 2]          # median: single calls occasionally hit an allocator stall
     # the CPU oracle on the first b_cpu windows
     og = O.OracleGraph(nbr=blk.connect_list, u_w=blk.u_ew, d_w=blk.d_ew, use_knn=bool(kw.get("use_kNN", False)),
                        line_graph=bool(kw.get("use_line_graph", False)), skip=int(kw.get("skip_connection", 1)),

@@ -21,8 +21,8 @@ OP_TOL = {torch.float32: 1e-6, torch.float64: 1e-14}
 
 
 def _resident_ok(g):
-    return (g.dtype == torch.float32 and g.ctor.get("ablation", "None") == "None"
-            and int(g.ctor.get("skip_connection", 1)) == 1)
+    band = bool(g.ctor.get("use_line_graph", False)) and int(g.ctor.get("skip_connection", 1)) > 1
+    return (g.dtype == torch.float32 and g.ctor.get("ablation", "None") == "None" and not (band and g.mask is not None))
 
 
 def _check_iterates(blk, x, g, tol):
@@ -405,3 +405,31 @@ def test_time_varying_edge_weights_match_oracle():
     for fn, ofn in ((blk.apply_op_Lu, O.op_lu), (blk.apply_op_Ldr, O.op_ldr), (blk.apply_op_Ldr_T, O.op_ldr_t),
                     (blk.apply_op_cLdr, O.op_cldr)):
         assert rel_err(fn(xo), ofn(og, xo)) <= 1e-6
+
+
+@pytest.mark.parametrize("N,k,T,skip,B", [(120, 5, 12, 3, 4), (200, 6, 24, 4, 3), (64, 4, 8, 2, 5)])
+@pytest.mark.parametrize("mode", ["resident", "streaming"])
+def test_skip_connection_line_graph_against_oracle(N, k, T, skip, B, mode):
+    """use_line_graph with skip_connection > 1 (banded temporal stencil, ADMM.py:41-52) on the
+    resident kernel (per-node stencil, no temporal gathers) and on the general streaming kernels."""
+    from mixed_graph_admm_b200 import _cabi, synth
+    from mixed_graph_admm_b200.ADMM import ADMM_algorithm
+    from oracle import admm_oracle as O
+    t_in = T // 2
+    gi = synth.road_graph(N, 1.4, seed=N)
+    blk = ADMM_algorithm(gi, synth.admm_info(N), use_kNN=True, k=k, u_sigma=50, t_in=t_in, T=T, use_line_graph=True,
+                         skip_connection=skip, mode=mode)
+    blk.max_ADMM_iter, blk.max_CG_iter, blk.CG_tol, blk.ADMM_tol = 3, 8, -1.0, -1.0
+    blk.keep_iterates = True
+    assert _cabi.lib().mga_plan_resident_eligible(blk._plan().handle, 0) == 1
+    y = synth.signals(B, t_in, N, seed=skip)
+    x = blk.combined_loop(y.cuda(), print_info=False).cpu()
+    og = O.OracleGraph(nbr=blk.connect_list, u_w=blk.u_ew, d_w=blk.d_ew, line_graph=True, skip=skip, time_list=blk.time_list)
+    prm = O.OracleParams(**synth.admm_info(N), t_in=t_in, T=T)
+    tr = O.admm_combined(og, prm, y, max_admm_iter=3, max_cg_iter=8, cg_tol=-1.0, admm_tol=-1.0)
+    assert rel_err(x, tr.x) <= 1e-5 and max_rel(x, tr.x) <= 2e-5
+    its = {k2: v.cpu() for k2, v in blk.last_iterates.items()}
+    assert rel_err(its["zu"], tr.zu) <= 1e-5 and rel_err(its["zd"], tr.zd) <= 1e-5
+    ldx = O.op_ldr(og, tr.x).double().norm().item()
+    assert (its["phi"].double() - tr.phi.double()).norm().item() <= 1e-5 * max(tr.phi.double().norm().item(), ldx)
+    np.testing.assert_allclose(blk.p_res_list[-1], tr.p_res[-1], rtol=2e-5, atol=1e-7)
