@@ -69,7 +69,8 @@ typedef enum { MGA_SYS_X = 0, MGA_SYS_ZU = 1, MGA_SYS_ZD = 2 } mga_system;
 
 /* which implementation mga_admm_solve uses */
 typedef enum {
-  MGA_MODE_AUTO = 0,     /* resident when eligible, else streaming */
+  MGA_MODE_AUTO = 0,     /* resident when eligible (fp32, fixed iteration counts, ablation None, time-invariant weights,
+                            window fits one CTA; forecasting, mask mode and every temporal-graph variant), else streaming */
   MGA_MODE_STREAMING = 1,/* state in HBM/L2, one fused kernel per CG phase */
   MGA_MODE_RESIDENT = 2, /* one CTA per window, CG vectors in registers, gathered vectors in SMEM */
   MGA_MODE_STREAMING_POINT = 3 /* streaming, always the general one-thread-per-lattice-point kernels (every dtype,

@@ -545,8 +545,9 @@ int mga_admm_solve(mga_plan* p, const mga_params* prm, const void* y, int y_rows
   const bool can_res = fixed && prm->ablation == MGA_ABL_NONE && resident_eligible(p, dtype) &&     // forecast or mask mode
                        !(mask && p->g.temporal == MGA_TEMPORAL_BAND);
   if (mode == MGA_MODE_RESIDENT && !can_res) {
-    set_error("mga_admm_solve: resident mode needs fp32, fixed iteration counts, ablation None, time-invariant "
-              "weights, N <= 512, T <= 24, kd <= 9");
+    set_error("mga_admm_solve: resident mode needs fp32, fixed iteration counts (cg_tol, admm_tol <= 0), ablation None, "
+              "time-invariant weights, a window of at most 1024 (node, 12-step slab) threads with T <= 24, at most 10 "
+              "neighbours per row after self links are dropped, and no mask on the banded line graph");
     return MGA_ERR_UNSUPPORTED;
   }
   if (mode != MGA_MODE_STREAMING && mode != MGA_MODE_STREAMING_POINT && can_res)
