@@ -433,3 +433,25 @@ def test_skip_connection_line_graph_against_oracle(N, k, T, skip, B, mode):
     ldx = O.op_ldr(og, tr.x).double().norm().item()
     assert (its["phi"].double() - tr.phi.double()).norm().item() <= 1e-5 * max(tr.phi.double().norm().item(), ldx)
     np.testing.assert_allclose(blk.p_res_list[-1], tr.p_res[-1], rtol=2e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("N,k,T,B", [(100, 4, 50, 3), (307, 6, 100, 2), (400, 6, 37, 2), (64, 3, 26, 5)])
+def test_long_windows_odd_lengths_against_oracle(N, k, T, B):
+    """T > 24 (beyond the resident kernel) with lengths that are not multiples of 4 or 12: the chunked streaming
+    kernels' padded last chunk and the general kernels, both against the oracle."""
+    from mixed_graph_admm_b200 import synth
+    from mixed_graph_admm_b200.ADMM import ADMM_algorithm
+    from oracle import admm_oracle as O
+    t_in = T // 2
+    gi = synth.road_graph(N, 1.3, seed=T)
+    y = synth.signals(B, t_in, N, seed=N)
+    xs = {}
+    for mode in ("streaming", "streaming_point"):
+        blk = ADMM_algorithm(gi, synth.admm_info(N), use_kNN=True, k=k, u_sigma=50, d_sigma=50, t_in=t_in, T=T, mode=mode)
+        blk.max_ADMM_iter, blk.max_CG_iter, blk.CG_tol, blk.ADMM_tol = 2, 8, -1.0, -1.0
+        xs[mode] = blk.combined_loop(y.cuda(), print_info=False).cpu()
+    og = O.OracleGraph(nbr=blk.connect_list, u_w=blk.u_ew, d_w=blk.d_ew)
+    prm = O.OracleParams(**synth.admm_info(N), t_in=t_in, T=T)
+    tr = O.admm_combined(og, prm, y, max_admm_iter=2, max_cg_iter=8, cg_tol=-1.0, admm_tol=-1.0)
+    for mode, x in xs.items():
+        assert rel_err(x, tr.x) <= 1e-5 and max_rel(x, tr.x) <= 2e-5, (mode, rel_err(x, tr.x))
