@@ -270,9 +270,13 @@ struct Ctx {
   // vector shifted by one time step, so this is the "father" sum at t0+k).  Two entries per trip, the
   // next two (row address, weight) pairs are fetched a trip ahead; the table has two spare steps at
   // its end so the look-ahead never leaves it.
+  // ZERO = false: accumulate on top of what f already holds
+  template <bool ZERO = true>
   __device__ __forceinline__ void father_sum(float (&f)[TS]) const {
+    if (ZERO) {
 #pragma unroll
-    for (int k = 0; k < TS; ++k) f[k] = 0.f;
+      for (int k = 0; k < TS; ++k) f[k] = 0.f;
+    }
     uint32_t ep = ent;
     int2 a = lds64<0>(ep), b = lds64<256>(ep);
     int n = steps;
@@ -293,19 +297,21 @@ struct Ctx {
     put(pbuf, v);
     __syncthreads();
     {
+      // The thread's own q terms enter the accumulator while qs is still in registers: with q[k] = qs[k-1],
+      // (L_d^T q)[k] = q[k] - wself qs[k] - f[k]; out starts as wself qs[k] - qs[k-1] and the in-list gather adds
+      // f on top, so nothing of qs has to survive (or be re-read after) the gather.
       float qs[TS];
       shifted_ldr(v, qs);
       put(qbuf, qs);
+#pragma unroll
+      for (int k = 0; k < TS; ++k) out[k] = wself * qs[k] - (k > 0 ? qs[k - 1] : 0.f);
     }
     __syncthreads();
-    father_sum(out);                                         // out = f
-    const float qprev = has_prev ? qbuf[own - 1] : 0.f;      // q[t0]; q[0] = 0 (ADMM.py:176)
-    float qs[TS];
-    get(qbuf, qs);     // the own row is re-read instead of kept live across the in-list gather
+    if (has_prev) out[0] -= qbuf[own - 1];                   // q[t0] of a later slab; q[0] = 0 (ADMM.py:176)
+    father_sum<false>(out);                                  // out = -(L_d^T L_d v); row T-1: f = 0 because qs[T-1] = 0
 #pragma unroll
     for (int k = 0; k < TS; ++k) {
-      const float q = (k == 0) ? qprev : qs[k - 1];
-      const float l = q - (out[k] + wself * qs[k]);   // row T-1: f = 0 because qs[T-1] = 0; Q1 is moot as q[0] = 0
+      const float l = -out[k];                               // Q1 is moot here as q[0] = 0
       if (XSYS) out[k] = ((MASKED ? v[k] * m[k] : (t0 + k < t_in ? v[k] : 0.f)) + a * v[k]) + c * l;
       else out[k] = c * l + a * v[k];
     }
