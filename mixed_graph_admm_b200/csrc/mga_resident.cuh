@@ -1,9 +1,11 @@
 // Resident mode: the whole of combined_loop (ADMM.py:528-648) for one window inside one CTA.
 //
+// Kernels of this file: k_admm_resident (the whole loop; instantiations for forecasting, mask /
+// interpolation mode and the banded skip-connection line graph) and k_cg_resident (CG_solver alone).
+//
 // Work mapping.  The T time steps of a node are cut into chunks of 4; a thread owns CH
 // consecutive chunks of ONE node (thread = (node i, slab s), slab-major so a warp is uniform in
-// s).  The CG vectors (r, p, Ap and — unless parked — x) of the thread's 4*CH lattice points live
-// in registers.
+// s).  The CG vectors (x, r, p, Ap) of the thread's 4*CH lattice points live in registers.
 //
 // Shared-memory layout.  Only the vectors other threads gather from are staged: pbuf (p) and
 // qbuf (a shifted copy of q = L_d p), NODE-major: buf[node * TP + t], TP = 4 * odd.  A
@@ -19,13 +21,16 @@
 // L_d^T then needs qs at the thread's own k (aligned again).  Only the thread's own node is
 // touched off-chunk: p[k+1] and qs[k-1] across the slab edge, one scalar load each.
 //
-// Tables.  The thread's rows of the ELL tables (neighbour row offsets + weights, time-invariant)
-// sit in registers (MGA_RES_TAB_SMEM=0) or in shared memory slot-major, one conflict-free 64-bit
-// load per neighbour (MGA_RES_TAB_SMEM=1: 26 registers fewer, which is what lets two CTAs share an
-// SM).  The in-list (the transpose that replaces the reference's scatter_add) sits in shared memory
-// as a per-warp, step-major ELL of (row offset, weight) pairs, read conflict-free.  Node numbering,
-// the visit order of a row's neighbours and of its in-list are chosen at plan time
-// (mga_schedule.cpp) so that quarter-warps hit distinct bank groups.
+// Tables.  The thread's rows of the ELL tables (time-invariant) sit in shared memory slot-major, one
+// conflict-free 64-bit load per neighbour, each entry = (ABSOLUTE shared address of the neighbour's
+// pbuf row at this thread's slab, weight) — so a gather is LDS.64 -> 3 x LDS.128 with immediate
+// offsets and no integer arithmetic (MGA_RES_TAB_SMEM=0 keeps them in registers instead: 26 more
+// registers, one CTA per SM, measured slower).  The node's own link is not in the tables: its weight
+// multiplies the thread's own registers.  The in-list (the transpose that replaces the reference's
+// scatter_add) sits in shared memory as a per-warp, step-major ELL of (row address, weight) pairs.
+// Node numbering, the visit order of a row's neighbours and of its in-list are chosen at plan time
+// (mga_schedule.cpp) so that warps have in-lists of similar length and quarter-warps hit distinct
+// bank groups.
 //
 // Registers are the scarce resource (12 lattice points per thread x {x, r, p, Ap, accumulators}):
 // the seven ADMM state vectors are parked between uses — in shared memory when that does not cost

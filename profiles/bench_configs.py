@@ -29,11 +29,13 @@ ap.add_argument("configs", nargs="*", default=["t288", "large20k"])
 ap.add_argument("--mode", default="auto")
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--diag", type=int, default=1)
+ap.add_argument("--batch", type=int, default=0, help="override the config's batch")
 a = ap.parse_args()
 dev = torch.device("cuda", 0)
 L = _cabi.lib()
 for name in a.configs:
     N, k, T, B, ratio, gseed = CONFIGS[name]
+    B = a.batch or B
     t_in = T // 2
     gi = synth.road_graph(N, ratio, seed=gseed)
     blk = ADMM_algorithm(gi, synth.admm_info(N), use_kNN=True, k=k, u_sigma=50, d_sigma=50, t_in=t_in, T=T,
