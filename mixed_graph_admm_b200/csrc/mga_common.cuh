@@ -96,6 +96,7 @@ struct mga_plan {
   const int* r_ell_ent = nullptr;     // int2 pairs (node, weight bits)
   int r_ell_total = 0;
   const float* band_uniform = nullptr;   // (T, skip) band weights when they are the same for every node
+  bool ldrt_gather = false;           // MGA_LDRT_GATHER: "L_d^T" is not the transpose of L_d (use_kNN=False, ADMM.py:211-215)
   int r_kd = 0, r_ku = 0;             // slots per row of the scheduled tables (self links and pads dropped)
   const float* r_w_self = nullptr;    // (N) self-link weights, internal order
   // work counters of the resident kernel's dynamic window hand-out: a ring, one per launch in flight

@@ -220,6 +220,7 @@ int mga_plan_create(const mga_graph_desc* d, int device, mga_plan** out) {
   auto fail = [&](int code) { mga_plan_destroy(p); return code; };
   std::vector<int> slot;
   if ((rc = host_tables(d, p, slot))) return fail(rc);
+  p->ldrt_gather = d->temporal == MGA_TEMPORAL_GRAPH && d->ldrt_mode == MGA_LDRT_GATHER;
   if ((rc = upload(p, p->h_nbr_u, &g.nbr_u))) return fail(rc);
   if ((rc = upload(p, p->h_u_w, &g.u_w))) return fail(rc);
   if ((rc = upload(p, p->h_nbr_d, &g.nbr_d))) return fail(rc);

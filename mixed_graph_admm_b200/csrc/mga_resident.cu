@@ -59,6 +59,7 @@ static void fill_tables(const mga_plan* p, const ResGeom& geo, ResArgs& a) {
   a.N = g.N; a.T = g.T; a.t_in = g.t_in; a.q1 = g.q1; a.nnz = g.nnz;
   a.NT = geo.NT; a.S = geo.S; a.TP = geo.TP;
   a.kd = p->r_kd; a.ku = p->r_ku;
+  a.transpose_exact = p->ldrt_gather ? 0 : 1;
   a.w_self = p->r_w_self;
   a.perm = p->r_perm; a.nbr_d = p->r_nbr_d; a.d_w = p->r_w_d; a.nbr_u = p->r_nbr_u; a.u_w = p->r_w_u;
   a.ell_ptr = p->r_ell_ptr; a.ell_ent = reinterpret_cast<const int2*>(p->r_ell_ent); a.ell_total = p->r_ell_total;

@@ -75,6 +75,7 @@ struct ResArgs {
   const float* y; float* x_out;
   const float* band_w;        // banded line graph: (T, skip, N) weights (caller's node order), else NULL
   const float* band_uniform;  // (T, skip) when the weights do not depend on the node (as the reference builds them)
+  int transpose_exact;        // 1: the in-list is the transpose of the forward temporal table (kNN scatter mode, line graph)
   int skip, band_floats;      // band_floats: shared-memory floats reserved for the staged (T, skip) table (multiple of 4)
   const float* mask;          // mask / interpolation mode (ADMM.py:373-376, 783-811): (B, T, N), y then has T rows
   float* out[ST_COUNT];       // optional per-window outputs (index by ST_*; ST_X unused)
@@ -121,6 +122,7 @@ struct Ctx {
   float wu[K];
 #endif
   float wself;               // weight of the node's own link in the temporal table (left out of the tables)
+  bool qdot;                 // the in-list is the exact transpose of the forward table: <v, L_d^T L_d v> = ||L_d v||^2
   int steps;                 // in-list steps of this thread's warp (padded with zero-weight entries)
   float* pbuf;
   float* qbuf;
@@ -145,6 +147,25 @@ struct Ctx {
     if (lane == 0) r[w] = v;
     __syncthreads();
     const int nw4 = (blockDim.x + 127) >> 7;       // float4 groups that hold partials
+    float4 t = *reinterpret_cast<const float4*>(r);
+    float s = (t.x + t.y) + (t.z + t.w);
+    for (int k = 1; k < nw4; ++k) {
+      t = *reinterpret_cast<const float4*>(r + 4 * k);
+      s += (t.x + t.y) + (t.z + t.w);
+    }
+    return s;
+  }
+
+  // The same reduction in two halves around a barrier the caller has anyway: bsum_post() before it, bsum_read() after.
+  __device__ __forceinline__ const float* bsum_post(float v) {
+    float* r = red + 32 * red_sel;
+    red_sel ^= 1;
+    v = warp_sum<float>(v);
+    if ((threadIdx.x & 31) == 0) r[threadIdx.x >> 5] = v;
+    return r;
+  }
+  __device__ __forceinline__ float bsum_read(const float* r) const {
+    const int nw4 = (blockDim.x + 127) >> 7;
     float4 t = *reinterpret_cast<const float4*>(r);
     float s = (t.x + t.y) + (t.z + t.w);
     for (int k = 1; k < nw4; ++k) {
@@ -297,10 +318,16 @@ struct Ctx {
 
   // out = A v for the x / z_d systems: diag(v) + c * L_d^T L_d v  (ADMM.py:371-387, 392-394)
   // MASKED: H = the caller's elementwise mask m (LHS_x(x, mask), ADMM.py:375-376) instead of "rows t < t_in"
-  template <bool XSYS, bool MASKED>
-  __device__ __forceinline__ void apply_cldr(const float (&v)[TS], float (&out)[TS], float a, float c, const float (&m)[TS]) {
+  // DOT: also return <v, A v>.  A = D + c L_d^T L_d, so <v, A v> = sum D v^2 + c ||L_d v||^2: every term is known
+  // once q = L_d v is (before the in-list gather), the partial sums ride on the barrier that publishes qs, and the
+  // reduction's latency hides behind the gather — one barrier fewer per CG iteration than reducing <p, Ap> afterwards.
+  // (Same value up to rounding; a sum of non-negative terms instead of one with cancellation.)
+  template <bool XSYS, bool MASKED, bool DOT>
+  __device__ __forceinline__ void apply_cldr(const float (&v)[TS], float (&out)[TS], float a, float c, const float (&m)[TS],
+                                             float& dot) {
     put(pbuf, v);
     __syncthreads();
+    const float* part = nullptr;
     {
       // The thread's own q terms enter the accumulator while qs is still in registers: with q[k] = qs[k-1],
       // (L_d^T q)[k] = q[k] - wself qs[k] - f[k]; out starts as wself qs[k] - qs[k-1] and the in-list gather adds
@@ -310,6 +337,15 @@ struct Ctx {
       put(qbuf, qs);
 #pragma unroll
       for (int k = 0; k < TS; ++k) out[k] = wself * qs[k] - (k > 0 ? qs[k - 1] : 0.f);
+      if (DOT && qdot) {
+        float dv = 0.f, dq = 0.f;
+#pragma unroll
+        for (int k = 0; k < TS; ++k) {
+          dv += ((XSYS && t0 + k < t_in) ? v[k] * v[k] : 0.f) + a * (v[k] * v[k]);
+          dq += qs[k] * qs[k];                               // the qs of all threads are exactly the q[t >= 1]; q[0] = 0
+        }
+        part = bsum_post(dv + c * dq);
+      }
     }
     __syncthreads();
     if (has_prev) out[0] -= qbuf[own - 1];                   // q[t0] of a later slab; q[0] = 0 (ADMM.py:176)
@@ -319,6 +355,16 @@ struct Ctx {
       const float l = -out[k];                               // Q1 is moot here as q[0] = 0
       if (XSYS) out[k] = ((MASKED ? v[k] * m[k] : (t0 + k < t_in ? v[k] : 0.f)) + a * v[k]) + c * l;
       else out[k] = c * l + a * v[k];
+    }
+    if (DOT) {
+      if (qdot) {
+        dot = bsum_read(part);
+      } else {                      // use_kNN=False: "L_d^T" is a gather with the forward table (ADMM.py:211-215), not a transpose
+        float loc = 0.f;
+#pragma unroll
+        for (int k = 0; k < TS; ++k) loc += v[k] * out[k];
+        dot = bsum(loc);
+      }
     }
   }
 
@@ -350,13 +396,23 @@ struct Ctx {
     for (int k = 0; k < TS; ++k) out[k] = c * (v[k] - out[k]) + a * v[k];
   }
 
-  template <int SYS, bool MASKED, bool BAND>
-  __device__ __forceinline__ void apply(const float (&v)[TS], float (&out)[TS], float a, float c, const float (&m)[TS]) {
+  // out = A v; DOT: dot = <v, A v> as well
+  template <int SYS, bool MASKED, bool BAND, bool DOT>
+  __device__ __forceinline__ void apply(const float (&v)[TS], float (&out)[TS], float a, float c, const float (&m)[TS], float& dot) {
+    if (SYS != MGA_SYS_ZU && !BAND) {
+      if (SYS == MGA_SYS_X) apply_cldr<true, MASKED, DOT>(v, out, a, c, m, dot);
+      else apply_cldr<false, false, DOT>(v, out, a, c, m, dot);
+      return;
+    }
     if (SYS == MGA_SYS_ZU) apply_lu(v, out, a, c);
-    else if (BAND && SYS == MGA_SYS_X) apply_cldr_band<true, MASKED>(v, out, a, c, m);
-    else if (BAND) apply_cldr_band<false, false>(v, out, a, c, m);
-    else if (SYS == MGA_SYS_X) apply_cldr<true, MASKED>(v, out, a, c, m);
-    else apply_cldr<false, false>(v, out, a, c, m);
+    else if (SYS == MGA_SYS_X) apply_cldr_band<true, MASKED>(v, out, a, c, m);
+    else apply_cldr_band<false, false>(v, out, a, c, m);
+    if (DOT) {                      // L_u is not symmetric (quirk Q5) and the banded stencil keeps the plain form: <v, A v> as is
+      float loc = 0.f;
+#pragma unroll
+      for (int k = 0; k < TS; ++k) loc += v[k] * out[k];
+      dot = bsum(loc);
+    }
   }
 
   // CG_solver, fixed iteration count (ADMM.py:329-368 with an unreachable tolerance; the
@@ -367,7 +423,8 @@ struct Ctx {
   __device__ __forceinline__ void cg(float (&x)[TS], float (&r)[TS], float a, float c, int n_cg, float* alpha_out,
                                      float* beta_out, int64_t B, const float (&m0)[TS]) {
     float p[TS], ap[TS];
-    apply<SYS, MASK0, BAND>(x, ap, a, c, m0);
+    float pap = 0.f;
+    apply<SYS, MASK0, BAND, false>(x, ap, a, c, m0, pap);
     float loc = 0.f;
 #pragma unroll
     for (int k = 0; k < TS; ++k) {
@@ -377,11 +434,8 @@ struct Ctx {
     }
     float rr = bsum(loc);
     for (int it = 0; it < n_cg; ++it) {
-      apply<SYS, false, BAND>(p, ap, a, c, m0);
-      loc = 0.f;
-#pragma unroll
-      for (int k = 0; k < TS; ++k) loc += p[k] * ap[k];
-      const float alpha = rr / bsum(loc);
+      apply<SYS, false, BAND, true>(p, ap, a, c, m0, pap);
+      const float alpha = rr / pap;
       loc = 0.f;
 #pragma unroll
       for (int k = 0; k < TS; ++k) {
@@ -477,6 +531,7 @@ struct Cta {
 #endif
     }
     c.wself = active ? a.w_self[i] : 0.f;
+    c.qdot = a.transpose_exact != 0;
     {
       const int wn = i >> 5;     // warp of this node row (the same for every slab)
       const int first = a.ell_ptr[wn];
