@@ -143,6 +143,7 @@ class ADMM_algorithm():
         self.last_mode = None
         self._plan_key = None
         self._plan_obj = None
+        self._plan_cache = {}
 
     @property
     def device(self):
@@ -193,17 +194,35 @@ class ADMM_algorithm():
         self._reset_lists(all_lists=False)
 
     # ------------------------------------------------------------------ plan / params
-    def _plan(self):
+    def _plan(self, Cn=1):
+        """The device plan for signals with ``Cn`` channels.  The operators act on every channel with the same
+        weights (``u_ew.unsqueeze(-1)``, ADMM.py:147,171) while dot products and norms run over (T, N, C)
+        (ADMM.py:347-356), so a (T, N, C) window on the N-node graph IS a (T, N*C) window on the graph with
+        node (i, c) -> i*C + c linked to (neighbour_j(i), c): the tables are expanded on the host and the
+        kernels see one channel."""
         cl, uw, dw = self.connect_list, self.u_ew, self.d_ew
         key = (cl.data_ptr(), cl._version, tuple(cl.shape), uw.data_ptr(), uw._version, tuple(uw.shape),
                dw.data_ptr(), dw._version, tuple(dw.shape), self.t_in, self.T, self.use_line_graph,
-               self.skip_connection, self.use_kNN, str(self.device))
+               self.skip_connection, self.use_kNN, str(self.device), int(Cn))
         if key == self._plan_key:
+            return self._plan_obj
+        if key in self._plan_cache:                   # callers that alternate channel counts keep both plans
+            self._plan_key, self._plan_obj = key, self._plan_cache[key]
             return self._plan_obj
         N, T = self.n_nodes, self.T
         cl64 = cl.detach().to('cpu', torch.int64)
         uw32 = uw.detach().to('cpu', torch.float32)
         dw32 = dw.detach().to('cpu', torch.float32)
+        if tuple(cl64.shape[:1]) != (N,):
+            raise ValueError(f"connect_list has {cl64.shape[0]} rows, graph has {N} nodes")
+        if Cn > 1 and uw32.dim() >= 2 and dw32.dim() >= 2:
+            ch = torch.arange(Cn, dtype=torch.int64).view(1, Cn, 1)
+            cl64 = torch.where(cl64.unsqueeze(1) >= 0, cl64.unsqueeze(1) * Cn + ch,
+                               cl64.unsqueeze(1).expand(N, Cn, cl64.shape[1])).reshape(N * Cn, -1)
+            uw32 = uw32.repeat_interleave(Cn, dim=-2)
+            # graph weights (N,K) / (T-1,N,K): node axis is -2; banded line-graph weights (T,skip,N): node axis is -1
+            dw32 = dw32.repeat_interleave(Cn, dim=-1 if (self.use_line_graph and self.skip_connection > 1) else -2)
+            N = N * Cn
         nbr_u = cl64[:, 1:].contiguous()
         if uw32.dim() == 2:
             u_T = 1
@@ -235,6 +254,9 @@ class ADMM_algorithm():
         desc = {k: (0 if v is None else v) for k, v in desc.items()}
         self._plan_obj = _Plan(desc, self.device)
         self._plan_key = key
+        if len(self._plan_cache) >= 4:
+            self._plan_cache.clear()
+        self._plan_cache[key] = self._plan_obj
         return self._plan_obj
 
     def _params(self):
@@ -245,11 +267,11 @@ class ADMM_algorithm():
         return p
 
     def _in(self, x):
-        """(B,T,N,1) signal -> contiguous tensor on the plan's device."""
+        """(B,T,N,C) signal -> contiguous tensor on the plan's device."""
         if x.dim() != 4:
             raise ValueError(f"signals are (B, T, N, C); got {tuple(x.shape)}")
-        if x.size(-1) != 1:
-            raise NotImplementedError("the B200 path is single-channel (C = 1), like every use in the reference")
+        if x.size(-1) < 1:
+            raise ValueError("signals need at least one channel")
         if x.size(2) != self.n_nodes:
             raise ValueError(f"signal has {x.size(2)} nodes, graph has {self.n_nodes}")
         _cabi.dtype_id(x.dtype)
@@ -261,7 +283,7 @@ class ADMM_algorithm():
         xd = self._in(x)
         md = self._in(mask.to(x.dtype)) if mask is not None else None
         y = torch.empty_like(xd)
-        plan, prm = self._plan(), self._params()
+        plan, prm = self._plan(xd.size(-1)), self._params()
         with torch.cuda.device(self.device):
             _cabi.check(_cabi.lib().mga_apply(plan.handle, _cabi.OP[op], C.byref(prm), _cabi.ptr(xd), _cabi.ptr(y),
                                               _cabi.ptr(md), xd.size(0), _cabi.dtype_id(xd.dtype),
@@ -314,7 +336,7 @@ class ADMM_algorithm():
         '''phi = soft_(mu_d1 / rho) (L^d_r x - gamma / rho)   (ADMM.py:401-408)'''
         xd, gd = self._in(x), self._in(gamma)
         out = torch.empty_like(xd)
-        plan, prm = self._plan(), self._params()
+        plan, prm = self._plan(xd.size(-1)), self._params()
         with torch.cuda.device(self.device):
             _cabi.check(_cabi.lib().mga_phi_direct(plan.handle, C.byref(prm), _cabi.ptr(xd), _cabi.ptr(gd),
                                                    _cabi.ptr(out), xd.size(0), _cabi.dtype_id(xd.dtype),
@@ -353,7 +375,7 @@ class ADMM_algorithm():
         alpha = torch.empty((max(n_it, 1), B), dtype=rhs.dtype, device=self.device)
         beta = torch.empty_like(alpha)
         iters = C.c_int32(-1)
-        plan, prm = self._plan(), self._params()
+        plan, prm = self._plan(rhs.size(-1)), self._params()
         with torch.cuda.device(self.device):
             # mode 'streaming' keeps the CG vectors in HBM; otherwise a fixed-iteration solve of a window
             # that fits one CTA runs in a single launch (include/mga.h: mga_plan_set_cg_mode)
@@ -422,7 +444,9 @@ class ADMM_algorithm():
             assert not torch.isnan(self.u_ew).any(), 'Undirected graph weights u_ew has NaN value'
             self._weights_checked = wkey
         out_device = y.device
-        B = y.size(0)
+        if y.dim() != 4:
+            raise ValueError(f"signals are (B, T, N, C); got {tuple(y.shape)}")
+        B, Cn = y.size(0), y.size(-1)
         T, N = self.T, self.n_nodes
         y_rows = y.size(1)
         if mask is None and y_rows != self.t_in:
@@ -433,7 +457,7 @@ class ADMM_algorithm():
         n_outer, n_cg = int(self.max_ADMM_iter), int(self.max_CG_iter)
         cg_tol, admm_tol = float(self.CG_tol), float(self.ADMM_tol)
         fixed = cg_tol <= 0 and admm_tol <= 0
-        plan, prm = self._plan(), self._params()
+        plan, prm = self._plan(Cn), self._params()
         L = _cabi.lib()
         t_mean, t_var = _regression_consts(self.t_in)
         want_iter = bool(self.keep_iterates)
@@ -442,7 +466,7 @@ class ADMM_algorithm():
         host_path = (y.device.type == 'cpu' and mask is None and fixed and not want_iter
                      and self.ablation == 'None')
         diag_h = np.zeros((n_outer, _cabi.DIAG_COLS), dtype=np.float64)
-        dx_h = np.zeros((n_outer, T, N), dtype=np.float64)
+        dx_h = np.zeros((n_outer, T, N * Cn), dtype=np.float64)
         cg_iters = np.full((max(n_outer, 1), 3), -1, dtype=np.int32)
         outer_done = C.c_int32(n_outer)
         alpha = beta = None
@@ -450,7 +474,7 @@ class ADMM_algorithm():
             if host_path:
                 # end-to-end call with host buffers: chunked copies overlap the solve
                 yc = y.detach().contiguous()
-                x = torch.empty((B, T, N, 1), dtype=y.dtype, pin_memory=yc.is_pinned())
+                x = torch.empty((B, T, N, Cn), dtype=y.dtype, pin_memory=yc.is_pinned())
                 _cabi.check(L.mga_admm_solve_host(plan.handle, C.byref(prm), _cabi.ptr(yc), y_rows, _cabi.ptr(x), B,
                                                   dt, n_outer, n_cg, t_mean, t_var, 1,
                                                   diag_h.ctypes.data_as(C.c_void_p),
@@ -460,7 +484,7 @@ class ADMM_algorithm():
             else:
                 yd = self._in(y)
                 md = self._in(mask.to(y.dtype)) if mask is not None else None
-                x = torch.empty((B, T, N, 1), dtype=y.dtype, device=dev)
+                x = torch.empty((B, T, N, Cn), dtype=y.dtype, device=dev)
                 outs = _cabi.AdmmOutputs()
                 its = {}
                 if want_iter:
@@ -468,7 +492,7 @@ class ADMM_algorithm():
                         its[name] = torch.zeros_like(x)
                         setattr(outs, name, its[name].data_ptr())
                 diag_d = torch.zeros((max(n_outer, 1), _cabi.DIAG_COLS), dtype=torch.float64, device=dev)
-                dx_d = torch.zeros((max(n_outer, 1), T, N), dtype=torch.float64, device=dev)
+                dx_d = torch.zeros((max(n_outer, 1), T, N * Cn), dtype=torch.float64, device=dev)
                 alpha = torch.zeros((max(n_outer, 1), 3, max(n_cg, 1), B), dtype=y.dtype, device=dev)
                 beta = torch.zeros_like(alpha)
                 outs.diag, outs.dx_sum = diag_d.data_ptr(), dx_d.data_ptr()
@@ -560,16 +584,15 @@ def initial_guess(y, t_in, T):
     '''
     if y.size(1) != t_in:
         raise ValueError("y must have t_in time steps")
-    if y.size(-1) != 1:
-        raise NotImplementedError("single-channel only")
     dev = y.device if y.is_cuda else _device_of(None)
-    B, N = y.size(0), y.size(2)
+    B, Cn = y.size(0), y.size(3)
+    N = y.size(2) * Cn          # the line is fitted per (window, node, channel): channels are extra nodes
     # a graph-free plan: initial_guess only needs the shape
     desc = dict(n_nodes=N, T=T, t_in=t_in, ku=0, nbr_u=0, u_w=0, u_w_T=1, kd=1, nbr_d=0, d_w=0, d_w_T=1,
                 ldrt_mode=0, temporal=_cabi.TEMPORAL_LINE)
     plan = _Plan(desc, dev)
     yd = y.detach().to(dev).contiguous()
-    x = torch.empty((B, T, N, 1), dtype=y.dtype, device=dev)
+    x = torch.empty((B, T, y.size(2), Cn), dtype=y.dtype, device=dev)
     t_mean, t_var = _regression_consts(t_in)
     with torch.cuda.device(dev):
         _cabi.check(_cabi.lib().mga_initial_guess(plan.handle, _cabi.ptr(yd), _cabi.ptr(x), B,

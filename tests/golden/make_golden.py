@@ -46,13 +46,18 @@ def _stack_coeffs(lst):
     return out.numpy()
 
 
+ONLY = set()     # fixture names given on the command line: regenerate just those
+
+
 def make_case(name, graph_info, admm_info, y, ctor, limits, mask=None, init=None, probe_seed=123):
+    if ONLY and name not in ONLY:
+        return
     ref = run_reference(graph_info, admm_info, y, ctor, limits, mask=mask, init=init)
     blk = ref["blk"]
     T = blk.T
     g = torch.Generator().manual_seed(probe_seed)
-    xp = torch.randn(2, T, blk.n_nodes, 1, generator=g, dtype=y.dtype)
-    gp = torch.randn(2, T, blk.n_nodes, 1, generator=g, dtype=y.dtype)
+    xp = torch.randn(2, T, blk.n_nodes, y.size(-1), generator=g, dtype=y.dtype)
+    gp = torch.randn(2, T, blk.n_nodes, y.size(-1), generator=g, dtype=y.dtype)
     d = {
         "meta": json.dumps({"ctor": ctor, "limits": limits, "admm_info": admm_info, "init": init,
                             "dtype": str(y.dtype).replace("torch.", ""), "n_nodes": graph_info["n_nodes"]}),
@@ -143,6 +148,19 @@ def main():
     mask[:, 0] = 1
     mask[:, -1] = 1
     make_case("tiny_mask", gi, ai, ym * mask, ctor, fixed(2, 4), mask=mask)
+    # 9b. multi-channel signals (row N4): C = 2 on the kNN graph, C = 3 on the banded line graph and on the
+    # physical adjacency; same weights on every channel, dot products over (T, N, C)
+    yc = lambda C, seed, dt=torch.float32: torch.rand(B, t_in, N, C, generator=torch.Generator().manual_seed(seed),  # noqa: E731
+                                                         dtype=dt)
+    make_case("tiny_c2", gi, ai_prox, yc(2, 20), ctor, fixed(3, 5))
+    make_case("tiny_c2_f64", gi, ai, yc(2, 21, torch.float64), ctor, fixed(2, 4))
+    make_case("tiny_c3_line2", gi, ai, yc(3, 22),
+              dict(use_kNN=True, k=k, u_sigma=50, d_sigma=50, t_in=t_in, T=T, use_line_graph=True,
+                   skip_connection=2), fixed(2, 4))
+    make_case("tiny_c3_physical", gi, ai, yc(3, 23),
+              dict(use_kNN=False, u_sigma=50, d_sigma=50, t_in=t_in, T=T), fixed(2, 4))
+    make_case("tiny_c2_tol", gi, ai, synth.signals(1, t_in, N, seed=2, smooth=True).repeat(1, 1, 1, 2)
+              * torch.tensor([1.0, 0.5]), ctor, {"max_ADMM_iter": 4})
     # 10. PEMS08-shaped (BASELINE.json configs[0]); 4 of the 32 windows are kept
     N, k, T, t_in = 170, 6, 12, 6
     gi = synth.road_graph(N, 1.7, seed=8, isolate_pair=True)
@@ -159,5 +177,6 @@ def main():
 
 
 if __name__ == "__main__":
+    ONLY.update(sys.argv[1:])
     with contextlib.redirect_stderr(io.StringIO()):
         main()

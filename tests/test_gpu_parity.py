@@ -216,8 +216,32 @@ def test_initial_guess_kernel():
     from mixed_graph_admm_b200.ADMM import initial_guess
     from oracle import admm_oracle as O
     for dt, tol in [(torch.float32, 1e-6), (torch.float64, 1e-14)]:
-        y = torch.rand(5, 6, 33, 1, generator=torch.Generator().manual_seed(1), dtype=dt)
-        assert rel_err(initial_guess(y, 6, 12), O.first_guess(y, 6, 12)) <= tol
+        for ch in (1, 3):
+            y = torch.rand(5, 6, 33, ch, generator=torch.Generator().manual_seed(1), dtype=dt)
+            got = initial_guess(y, 6, 12)
+            assert got.shape == (5, 12, 33, ch)
+            assert rel_err(got, O.first_guess(y, 6, 12)) <= tol
+
+
+def test_multi_channel_is_the_channel_expanded_graph():
+    """C > 1: one plan per channel count, cached; a C = 2 window whose channels are two windows
+    of a C = 1 run reproduces them when the dot products are per channel, i.e. for operators (no CG coupling),
+    and the resident kernel serves it (48 expanded nodes)."""
+    from mixed_graph_admm_b200 import _cabi
+    g = Golden("tiny_c2")
+    blk = solver_from_golden(g)
+    xp = g.t("probe_x")
+    both = blk.apply_op_cLdr(xp)
+    p2 = blk._plan(2)
+    for c in range(2):
+        one = blk.apply_op_cLdr(xp[..., c:c + 1].contiguous())
+        assert torch.equal(one[..., 0], both[..., c])
+    assert blk._plan(2) is p2                                            # switching back re-uses the cached plan
+    assert _cabi.lib().mga_plan_resident_eligible(p2.handle, 0) == 1
+    blk.max_ADMM_iter, blk.max_CG_iter, blk.CG_tol, blk.ADMM_tol = 3, 5, -1.0, -1.0
+    x = blk.combined_loop(g.y, print_info=False)
+    assert blk.last_mode in ("device", "host") and x.shape == g.t("x").shape
+    assert rel_err(x, g.t("x")) <= 1e-5
 
 
 def test_index_out_of_bounds_raises_value_error():
