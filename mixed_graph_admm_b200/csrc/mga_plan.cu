@@ -296,6 +296,46 @@ int mga_plan_create(const mga_graph_desc* d, int device, mga_plan** out) {
     Graph2& g2 = p->g2;
     g2.N = N; g2.T = T; g2.t_in = d->t_in; g2.C4 = (T + 3) / 4; g2.kd = g.kd; g2.ku = g.ku; g2.q1 = g.q1;
     stream2_tiling(&g2);
+    // packed (neighbour, weight bits) tables of the time-tiled kernels: one 8-byte load per entry and no "-1"
+    // branch - a missing neighbour points at the own row with weight 0; the self link of the temporal table
+    // leaves it (the owner already holds that value), its weight goes to tab_wself
+    auto pack = [&](const std::vector<int>& nb, const std::vector<float>& w, int K, bool drop_self, std::vector<int>& tab,
+                    std::vector<float>& wself) {
+      std::vector<std::vector<std::pair<int, float>>> rows(N);
+      int kmax = 0;
+      wself.assign(N, 0.f);
+      for (int k = 0; k < N; ++k) {
+        for (int j = 0; j < K; ++j) {
+          const int m = nb[(size_t)k * K + j];
+          if (m < 0) continue;
+          if (drop_self && m == k) { wself[k] += w[(size_t)k * K + j]; continue; }
+          rows[k].push_back({m, w[(size_t)k * K + j]});
+        }
+        kmax = std::max(kmax, (int)rows[k].size());
+      }
+      tab.assign((size_t)N * kmax * 2, 0);
+      for (int k = 0; k < N; ++k)
+        for (int j = 0; j < kmax; ++j) {
+          const bool has = j < (int)rows[k].size();
+          const float wj = has ? rows[k][j].second : 0.f;
+          tab[((size_t)k * kmax + j) * 2] = has ? rows[k][j].first : k;
+          std::memcpy(&tab[((size_t)k * kmax + j) * 2 + 1], &wj, sizeof(float));
+        }
+      return kmax;
+    };
+    std::vector<int> td, tu, ti(is.size() * 2);
+    std::vector<float> wsd, wsu;
+    g2.kd3 = pack(nd, wd, g.kd, true, td, wsd);
+    g2.ku3 = pack(nu, wu, g.ku, false, tu, wsu);
+    for (size_t e = 0; e < is.size(); ++e) { ti[2 * e] = is[e]; std::memcpy(&ti[2 * e + 1], &iw[e], sizeof(float)); }
+    const int* dev_tab = nullptr;
+    if ((rc = upload(p, td, &dev_tab))) return fail(rc);
+    g2.tab_d = reinterpret_cast<const int2*>(dev_tab);
+    if ((rc = upload(p, tu, &dev_tab))) return fail(rc);
+    g2.tab_u = reinterpret_cast<const int2*>(dev_tab);
+    if ((rc = upload(p, ti, &dev_tab))) return fail(rc);
+    g2.tab_in = reinterpret_cast<const int2*>(dev_tab);
+    if ((rc = upload(p, wsd, &g2.wself_d))) return fail(rc);
     if ((rc = upload(p, perm, &g2.perm))) return fail(rc);
     if ((rc = upload(p, nd, &g2.nbr_d))) return fail(rc);
     if ((rc = upload(p, wd, &g2.w_d))) return fail(rc);

@@ -36,6 +36,32 @@ constexpr int kB2 = MGA_S2_BLOCK;
 
 __device__ __forceinline__ float4 ld4(const float* v, size_t chunk) { return reinterpret_cast<const float4*>(v)[chunk]; }
 __device__ __forceinline__ void st4(float* v, size_t chunk, float4 a) { reinterpret_cast<float4*>(v)[chunk] = a; }
+// streamed (evict-first) accesses of the time-tiled kernels: the vectors pass through once, the L1 lines are kept
+// for the graph tables (ncu: with plain loads every table read of phase 2 was an L2 round trip - long_scoreboard)
+#ifndef MGA_S3_STREAM_HINTS
+#define MGA_S3_STREAM_HINTS 1
+#endif
+__device__ __forceinline__ float4 ld4s(const float* v, size_t chunk) {
+#if MGA_S3_STREAM_HINTS
+  return __ldcs(reinterpret_cast<const float4*>(v) + chunk);
+#else
+  return reinterpret_cast<const float4*>(v)[chunk];
+#endif
+}
+__device__ __forceinline__ float ld1s(const float* v, size_t k) {
+#if MGA_S3_STREAM_HINTS
+  return __ldcs(v + k);
+#else
+  return v[k];
+#endif
+}
+__device__ __forceinline__ void st4s(float* v, size_t chunk, float4 a) {
+#if MGA_S3_STREAM_HINTS
+  __stcs(reinterpret_cast<float4*>(v) + chunk, a);
+#else
+  reinterpret_cast<float4*>(v)[chunk] = a;
+#endif
+}
 
 struct Chunk {
   int b;           // window
@@ -328,6 +354,219 @@ __global__ void __launch_bounds__(kFlat) k2_xr(Graph2 g, int64_t B, int it, floa
   block_add(dot, dots + (size_t)(2 * it + 2) * B + k.b, threadIdx.x, kFlat);
 }
 
+// ---- time-tiled kernels: the gathered vector staged in shared memory ---------------------------------------
+// For graphs whose node set fits one CTA's shared memory (N * CB3 * 16 B <= 48 KB: the PEMS graphs at any T)
+// a CTA owns ALL nodes of one window over a tile of CB3 chunks (4 * CB3 time steps).  Phase 1 streams the tile
+// in with coalesced 128-bit loads (and applies the p update on the way: p' = r + beta p is written once to HBM
+// and once to shared memory), phase 2 gathers the neighbours' chunks from shared memory - the gathers that
+// bound k2_ldr_shift / k2_ldrt_lhs / k2_lu_lhs (L1 wavefronts + L2 traffic at ~2 TB/s of DRAM traffic) no longer
+// leave the SM.  Because the gathers are chunk-aligned (shifted q) a tile needs no halo columns, only one halo
+// SCALAR per node (p'[first step of the next tile] / qs[last step of the previous tile]).  The p update moves
+// into the operator kernel, so per CG iteration: x / z_d systems (r,p -> p',qs : 16) + (p',qs -> Ap : 12) +
+// k2_xr 24 = 52 B/pt in 3 launches (k2: 56 in 4); z_u (r,p -> p',Ap : 16) + 24 = 40 B/pt = the algorithmic
+// minimum, in 2 launches (k2: 44 in 3).  p is ping-ponged (a tile's halo reads the next tile's OLD p).
+constexpr int kU3 = 4;   // node rows whose loads are issued together in phase 1
+
+// SRC 0: v = r + beta p   SRC 1: v = r (first iteration)   SRC 2: v = vin (initial residual: v = x0)
+template <int SRC>
+__device__ __forceinline__ void tile_fill(const Graph2& g, int64_t B, int it, const float* __restrict__ r,
+                                          const float* __restrict__ p_old, float* __restrict__ p_new,
+                                          const double* __restrict__ dots, float4* tile, float* halo, bool want_halo) {
+  const int CB = blockDim.x, NBt = blockDim.y, tx = threadIdx.x;
+  const int b = blockIdx.x, c0 = blockIdx.y * CB, c = c0 + tx, cn = c0 + CB;
+  const bool cok = c < g.C4, last = want_halo && tx == CB - 1, hok = cn < g.C4;
+  const size_t w0 = (size_t)b * (size_t)(g.N * g.C4);
+  float beta = 0.f;
+  if (SRC == 0) beta = (float)dots[(size_t)(2 * it) * B + b] / (float)dots[(size_t)(2 * it - 2) * B + b];   // ADMM.py:356
+  for (int n0 = threadIdx.y; n0 < g.N; n0 += kU3 * NBt) {
+    float4 a[kU3], q[kU3];
+    float ha[kU3], hq[kU3];
+#pragma unroll
+    for (int u = 0; u < kU3; ++u) {
+      const int n = n0 + u * NBt;
+      const bool ok = n < g.N && cok;
+      const size_t k = ok ? w0 + (size_t)(n * g.C4 + c) : w0;
+      a[u] = ld4s(r, k);
+      if (SRC == 0) q[u] = ld4s(p_old, k);
+      if (last) {
+        const size_t hk = (n < g.N && hok) ? (w0 + (size_t)(n * g.C4 + cn)) * 4 : w0 * 4;
+        ha[u] = ld1s(r, hk);
+        if (SRC == 0) hq[u] = ld1s(p_old, hk);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < kU3; ++u) {
+      const int n = n0 + u * NBt;
+      if (n >= g.N) continue;
+      float4 v = a[u];
+      if (SRC == 0) v = make_float4(a[u].x + beta * q[u].x, a[u].y + beta * q[u].y, a[u].z + beta * q[u].z, a[u].w + beta * q[u].w);
+      if (!cok) v = make_float4(0.f, 0.f, 0.f, 0.f);
+      tile[n * CB + tx] = v;
+      if (SRC != 2 && cok) st4s(p_new, w0 + (size_t)(n * g.C4 + c), v);
+      if (last) halo[n] = hok ? (SRC == 0 ? ha[u] + beta * hq[u] : ha[u]) : 0.f;
+    }
+  }
+}
+
+// acc += sum_j w_j tile[nbr_j][tx] over a packed forward table (rows of `slots` (neighbour, weight) entries; a missing
+// neighbour is (own row, 0)), neighbours read from the shared-memory tile
+__device__ __forceinline__ float4 fwd_gather_s(const int2* __restrict__ tab, int slots, const float4* tile, int n, int tx,
+                                               int CB, float4 acc) {
+  const int2* row = tab + n * slots;
+#pragma unroll 2
+  for (int j = 0; j < slots; ++j) {
+    const int2 e = row[j];
+    const float wj = __int_as_float(e.y);
+    const float4 a = tile[e.x * CB + tx];
+    acc.x += wj * a.x; acc.y += wj * a.y; acc.z += wj * a.z; acc.w += wj * a.w;
+  }
+  return acc;
+}
+
+// (r, p) -> p', qs = shifted L_d p'   [SRC 2: x0 -> qs]
+template <int SRC>
+__global__ void __launch_bounds__(256, 4) k3_p_ldr(Graph2 g, int64_t B, int it, const float* __restrict__ r,
+                                                   const float* __restrict__ p_old, float* __restrict__ p_new,
+                                                   float* __restrict__ qs, const double* __restrict__ dots) {
+  extern __shared__ float4 s3[];
+  const int CB = blockDim.x, NBt = blockDim.y, tx = threadIdx.x;
+  float4* tile = s3;
+  float* halo = reinterpret_cast<float*>(s3 + g.N * CB);
+  tile_fill<SRC>(g, B, it, r, p_old, p_new, dots, tile, halo, true);
+  __syncthreads();
+  const int c = blockIdx.y * CB + tx;
+  if (c >= g.C4) return;
+  const size_t w0 = (size_t)blockIdx.x * (size_t)(g.N * g.C4);
+  const int t = 4 * c;
+  for (int n = threadIdx.y; n < g.N; n += NBt) {
+    const float4 own = tile[n * CB + tx];
+    const float nxt = (tx + 1 < CB) ? reinterpret_cast<const float*>(tile + n * CB + tx + 1)[0] : halo[n];
+    const float ws = g.wself_d[n];
+    const float4 acc = fwd_gather_s(g.tab_d, g.kd3, tile, n, tx, CB, make_float4(ws * own.x, ws * own.y, ws * own.z, ws * own.w));
+    float4 o;
+    o.x = (t + 1 < g.T) ? own.y - acc.x : 0.f;
+    o.y = (t + 2 < g.T) ? own.z - acc.y : 0.f;
+    o.z = (t + 3 < g.T) ? own.w - acc.z : 0.f;
+    o.w = (t + 4 < g.T) ? nxt - acc.w : 0.f;
+    st4s(qs, w0 + (size_t)(n * g.C4 + c), o);
+  }
+}
+
+// (v, qs) -> Ap, <v, Ap>  [MODE 1: r = rhs - A v, <r, r>];  A = diag + c L_d^T L_d; qs tile in shared memory
+template <int MODE>
+__global__ void __launch_bounds__(256, 4) k3_ldrt_lhs(Graph2 g, const float* __restrict__ v, const float* __restrict__ qs,
+                                                      const float* __restrict__ rhs, float* __restrict__ out,
+                                                      double* __restrict__ slot, float a, float cc, int xsys) {
+  extern __shared__ float4 s3[];
+  const int CB = blockDim.x, NBt = blockDim.y, tx = threadIdx.x;
+  float4* tile = s3;
+  float* halo = reinterpret_cast<float*>(s3 + g.N * CB);
+  const int b = blockIdx.x, c0 = blockIdx.y * CB, c = c0 + tx;
+  const bool cok = c < g.C4;
+  const size_t w0 = (size_t)b * (size_t)(g.N * g.C4);
+  for (int n0 = threadIdx.y; n0 < g.N; n0 += kU3 * NBt) {
+    float4 q[kU3];
+    float h[kU3];
+#pragma unroll
+    for (int u = 0; u < kU3; ++u) {
+      const int n = n0 + u * NBt;
+      const bool ok = n < g.N && cok;
+      q[u] = ld4s(qs, ok ? w0 + (size_t)(n * g.C4 + c) : w0);
+      if (tx == 0) h[u] = (n < g.N && c0 > 0) ? ld1s(qs, (w0 + (size_t)(n * g.C4 + c0)) * 4 - 1) : 0.f;   // q[4 c0] = qs[4 c0 - 1]; q[0] = 0
+    }
+#pragma unroll
+    for (int u = 0; u < kU3; ++u) {
+      const int n = n0 + u * NBt;
+      if (n >= g.N) continue;
+      tile[n * CB + tx] = cok ? q[u] : make_float4(0.f, 0.f, 0.f, 0.f);
+      if (tx == 0) halo[n] = h[u];
+    }
+  }
+  __syncthreads();
+  float dot = 0.f;
+  if (cok) {
+    const int t0 = 4 * c;
+    for (int n = threadIdx.y; n < g.N; n += NBt) {
+      const size_t k = w0 + (size_t)(n * g.C4 + c);
+      const float4 pv = ld4s(v, k);
+      float4 rh;
+      if (MODE == 1) rh = ld4s(rhs, k);
+      const float4 q1 = tile[n * CB + tx];
+      const float qprev = tx > 0 ? reinterpret_cast<const float*>(tile + n * CB + tx)[-1] : halo[n];
+      float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int e1 = g.in_ptr[n + 1];
+#pragma unroll 2
+      for (int e = g.in_ptr[n]; e < e1; ++e) {
+        const int2 en = g.tab_in[e];
+        const float w = __int_as_float(en.y);
+        const float4 s = tile[en.x * CB + tx];
+        f.x += w * s.x; f.y += w * s.y; f.z += w * s.z; f.w += w * s.w;
+      }
+      const float pp[4] = {pv.x, pv.y, pv.z, pv.w};
+      const float q[4] = {qprev, q1.x, q1.y, q1.z};
+      const float ff[4] = {f.x, f.y, f.z, f.w};
+      float o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int t = t0 + j;
+        const float l = q[j] - ff[j];
+        float val;
+        if (xsys) val = ((t < g.t_in ? pp[j] : 0.f) + a * pp[j]) + cc * l;      // ADMM.py:372-379
+        else val = cc * l + a * pp[j];                                          // ADMM.py:394
+        o[j] = t < g.T ? val : 0.f;
+      }
+      if (MODE == 0) {
+        st4s(out, k, make_float4(o[0], o[1], o[2], o[3]));
+        dot += (pp[0] * o[0] + pp[1] * o[1]) + (pp[2] * o[2] + pp[3] * o[3]);
+      } else {
+        const float r0 = rh.x - o[0], r1 = rh.y - o[1], r2 = rh.z - o[2], r3 = rh.w - o[3];
+        st4s(out, k, make_float4(r0, r1, r2, r3));
+        dot += (r0 * r0 + r1 * r1) + (r2 * r2 + r3 * r3);
+      }
+    }
+  }
+  block_add(dot, slot + b, tid2(), blockDim.x * blockDim.y);
+}
+
+// z_u system: (r, p) -> p', Ap = (c L_u + a I) p', <p', Ap>   [SRC 2 / MODE 1: r = rhs - A x0, <r, r>]
+template <int SRC, int MODE>
+__global__ void __launch_bounds__(256, 4) k3_lu(Graph2 g, int64_t B, int it, const float* __restrict__ r,
+                                                const float* __restrict__ p_old, float* __restrict__ p_new,
+                                                const float* __restrict__ rhs, float* __restrict__ out,
+                                                const double* __restrict__ dots, double* __restrict__ slot, float a, float cc) {
+  extern __shared__ float4 s3[];
+  const int CB = blockDim.x, NBt = blockDim.y, tx = threadIdx.x;
+  float4* tile = s3;
+  tile_fill<SRC>(g, B, it, r, p_old, p_new, dots, tile, nullptr, false);
+  __syncthreads();
+  const int b = blockIdx.x, c = blockIdx.y * CB + tx;
+  const size_t w0 = (size_t)b * (size_t)(g.N * g.C4);
+  float dot = 0.f;
+  if (c < g.C4) {
+    for (int n = threadIdx.y; n < g.N; n += NBt) {
+      const size_t k = w0 + (size_t)(n * g.C4 + c);
+      float4 rh;
+      if (MODE == 1) rh = ld4s(rhs, k);
+      const float4 pv = tile[n * CB + tx];
+      const float4 acc = fwd_gather_s(g.tab_u, g.ku3, tile, n, tx, CB, make_float4(0.f, 0.f, 0.f, 0.f));
+      float4 o;
+      o.x = cc * (pv.x - acc.x) + a * pv.x;
+      o.y = cc * (pv.y - acc.y) + a * pv.y;
+      o.z = cc * (pv.z - acc.z) + a * pv.z;
+      o.w = cc * (pv.w - acc.w) + a * pv.w;    // pads: v = 0 and every gathered pad is 0
+      if (MODE == 0) {
+        st4s(out, k, o);
+        dot += (pv.x * o.x + pv.y * o.y) + (pv.z * o.z + pv.w * o.w);
+      } else {
+        const float4 rr = make_float4(rh.x - o.x, rh.y - o.y, rh.z - o.z, rh.w - o.w);
+        st4s(out, k, rr);
+        dot += (rr.x * rr.x + rr.y * rr.y) + (rr.z * rr.z + rr.w * rr.w);
+      }
+    }
+  }
+  block_add(dot, slot + b, tid2(), blockDim.x * blockDim.y);
+}
+
 // alpha / beta live in arrays of B_out windows per iteration (this call's B windows are a slice of them)
 __global__ void k2_coeffs(int64_t B, int64_t B_out, int iters, const double* __restrict__ dots, float* __restrict__ alpha,
                           float* __restrict__ beta) {
@@ -530,6 +769,21 @@ void stream2_tiling(Graph2* g) {
   g->tilesN = (g->N + g->NBt - 1) / g->NBt;
   g->NB = (g->N + g->tilesN - 1) / g->tilesN;           // balanced node tiles, NB <= NBt (extra rows are masked off)
   g->tilesC = (g->C4 + g->CB - 1) / g->CB;
+  // time-tiled shared-memory kernels (k3_*): all nodes x CB3 chunks (+ one halo float per node) per CTA, <= 48 KB
+  g->CB3 = 0;
+  int force = 0;
+  if (const char* e = std::getenv("MGA_S3_CB")) force = std::atoi(e);     // 0 = automatic, < 0 = off, > 0 = chunks per tile
+  if (force >= 0) {
+    int cands[5] = {force > 0 ? std::min(force, g->C4) : std::min(g->C4, 8), 4, 2, 1, 0};
+    for (int k = 0; cands[k] > 0 && g->CB3 == 0; ++k)
+      if (cands[k] <= g->C4 && (size_t)g->N * ((size_t)cands[k] * 16 + 4) <= 48 * 1024) g->CB3 = cands[k];
+  }
+  if (g->CB3 > 0) {
+    const int cb = g->CB3;
+    g->NB3t = (cb & (cb - 1)) == 0 ? 256 / cb : 32 * std::max(1, 8 / cb);     // cb * NB3t whole warps, <= 256 threads
+    g->tiles3 = (g->C4 + cb - 1) / cb;
+    g->smem3 = (int)((size_t)g->N * ((size_t)cb * 16 + 4));
+  }
 }
 
 bool stream2_eligible(const mga_plan* p, int dtype) {
@@ -537,9 +791,10 @@ bool stream2_eligible(const mga_plan* p, int dtype) {
 }
 
 struct Bufs2 {
-  float *r, *p, *ap, *qs;
+  float *r, *p, *ap, *qs, *p2;     // p2: second p buffer of the time-tiled kernels (p is ping-ponged)
   double* dots;
 };
+constexpr int kCgVecs = 5;
 
 static size_t vec_bytes2(const Graph2& g, int64_t B) { return (((size_t)B * g.N * g.C4 * 16) + 255) & ~(size_t)255; }
 static size_t dots_bytes2(int64_t B, int max_iter) { return (((size_t)(2 * max_iter + 1) * B * sizeof(double)) + 255) & ~(size_t)255; }
@@ -556,6 +811,38 @@ static int cg2(mga_plan* p, int system, const mga_params* m, const float* rhs, f
   else { a = (float)(m->rho_d / 2); c = (float)m->mu_d2; }
   const int xsys = system == MGA_SYS_X;
   MGA_CUDA(cudaMemsetAsync(w.dots, 0, (size_t)(2 * n_cg + 1) * B * sizeof(double), st));
+  if (g.CB3 > 0) {
+    // time-tiled shared-memory kernels: p update fused into the operator kernel, p ping-ponged
+    const dim3 grid3((unsigned)B, g.tiles3), blk3(g.CB3, g.NB3t);
+    const size_t sm = (size_t)g.smem3;
+    float *p_old = w.p, *p_new = w.p2;
+    if (system == MGA_SYS_ZU) {
+      k3_lu<2, 1><<<grid3, blk3, sm, st>>>(g, B, 0, x, nullptr, nullptr, rhs, w.r, w.dots, w.dots, a, c);
+      MGA_LAUNCH_CHECK("k3_lu");
+    } else {
+      k3_p_ldr<2><<<grid3, blk3, sm, st>>>(g, B, 0, x, nullptr, nullptr, w.qs, w.dots);
+      MGA_LAUNCH_CHECK("k3_p_ldr");
+      k3_ldrt_lhs<1><<<grid3, blk3, sm, st>>>(g, x, w.qs, rhs, w.r, w.dots, a, c, xsys);
+      MGA_LAUNCH_CHECK("k3_ldrt_lhs");
+    }
+    for (int it = 0; it < n_cg; ++it) {
+      double* pap = w.dots + (size_t)(2 * it + 1) * B;
+      if (system == MGA_SYS_ZU) {
+        if (it == 0) k3_lu<1, 0><<<grid3, blk3, sm, st>>>(g, B, it, w.r, p_old, p_new, nullptr, w.ap, w.dots, pap, a, c);
+        else k3_lu<0, 0><<<grid3, blk3, sm, st>>>(g, B, it, w.r, p_old, p_new, nullptr, w.ap, w.dots, pap, a, c);
+        MGA_LAUNCH_CHECK("k3_lu");
+      } else {
+        if (it == 0) k3_p_ldr<1><<<grid3, blk3, sm, st>>>(g, B, it, w.r, p_old, p_new, w.qs, w.dots);
+        else k3_p_ldr<0><<<grid3, blk3, sm, st>>>(g, B, it, w.r, p_old, p_new, w.qs, w.dots);
+        MGA_LAUNCH_CHECK("k3_p_ldr");
+        k3_ldrt_lhs<0><<<grid3, blk3, sm, st>>>(g, p_new, w.qs, nullptr, w.ap, pap, a, c, xsys);
+        MGA_LAUNCH_CHECK("k3_ldrt_lhs");
+      }
+      k2_xr<<<fgrid, kFlat, 0, st>>>(g, B, it, x, w.r, p_new, w.ap, w.dots);
+      MGA_LAUNCH_CHECK("k2_xr");
+      std::swap(p_old, p_new);
+    }
+  } else {
   // r = rhs - A x0 ; RR(0)
   if (system == MGA_SYS_ZU) {
     k2_lu_lhs<1><<<grid, blk, 0, st>>>(g, x, rhs, w.r, w.dots, a, c);
@@ -582,6 +869,7 @@ static int cg2(mga_plan* p, int system, const mga_params* m, const float* rhs, f
     k2_xr<<<fgrid, kFlat, 0, st>>>(g, B, it, x, w.r, w.p, w.ap, w.dots);
     MGA_LAUNCH_CHECK("k2_xr");
   }
+  }
   if ((alpha || beta) && n_cg > 0) {
     const int64_t tot = B * n_cg;
     k2_coeffs<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(B, B_out, n_cg, w.dots, alpha, beta);
@@ -597,7 +885,8 @@ static Bufs2 carve2(char* base, const Graph2& g, int64_t B, int max_iter) {
   w.p = reinterpret_cast<float*>(base + vec);
   w.ap = reinterpret_cast<float*>(base + 2 * vec);
   w.qs = reinterpret_cast<float*>(base + 3 * vec);
-  w.dots = reinterpret_cast<double*>(base + 4 * vec);
+  w.p2 = reinterpret_cast<float*>(base + 4 * vec);
+  w.dots = reinterpret_cast<double*>(base + kCgVecs * vec);
   (void)max_iter;
   return w;
 }
@@ -609,7 +898,7 @@ static Bufs2 carve2(char* base, const Graph2& g, int64_t B, int max_iter) {
 static int64_t group_windows(const mga_plan* p, int64_t B) {
   if (const char* e = std::getenv("MGA_S2_GROUP")) { const long v = std::atol(e); if (v > 0) return std::min<int64_t>(B, v); }
   const Graph2& g = p->g2;
-  const double per_window = 16.0 * (double)g.N * g.C4 * 16.0;
+  const double per_window = (12.0 + kCgVecs) * (double)g.N * g.C4 * 16.0;
   const int64_t G = (int64_t)(32e9 / per_window);
   return std::max<int64_t>(1, std::min<int64_t>(B, G));
 }
@@ -636,7 +925,7 @@ static int stream2_cg_group(mga_plan* p, int system, const mga_params* m, const 
                             int n_cg, void* alpha, void* beta, cudaStream_t st) {
   const Graph2& g = p->g2;
   const size_t vec = vec_bytes2(g, B);
-  int rc = ensure_workspace(p, p->ws, 6 * vec + dots_bytes2(B, n_cg) + 256);
+  int rc = ensure_workspace(p, p->ws, (2 + kCgVecs) * vec + dots_bytes2(B, n_cg) + 256);
   if (rc) return rc;
   char* base = static_cast<char*>(p->ws.base);
   float* rhs_i = reinterpret_cast<float*>(base);
@@ -688,7 +977,7 @@ static int stream2_admm_group(mga_plan* p, const mga_params* prm, const void* y_
   const bool want_diag = (diag_flags & 1) != 0, accumulate = (diag_flags & 2) != 0;
   const size_t vec = vec_bytes2(g, B);
   const int n_state = 12;   // x0, x1, zu0, zu1, zd0, zd1, gu, gd, gam, phi, rhs, spare
-  const size_t need = n_state * vec + 4 * vec + dots_bytes2(B, max_cg) + 512 +
+  const size_t need = n_state * vec + kCgVecs * vec + dots_bytes2(B, max_cg) + 512 +
                       (size_t)std::max(n_outer, 1) * MGA_DIAG_COLS * sizeof(double);
   int rc = ensure_workspace(p, p->ws, need);
   if (rc) return rc;
@@ -697,7 +986,7 @@ static int stream2_admm_group(mga_plan* p, const mga_params* prm, const void* y_
   float *x_cur = V(0), *x_nxt = V(1), *zu_cur = V(2), *zu_nxt = V(3), *zd_cur = V(4), *zd_nxt = V(5);
   float *gu = V(6), *gd = V(7), *gam = V(8), *phi = V(9), *rhs = V(10);
   Bufs2 w = carve2(base + n_state * vec, g, B, max_cg);
-  double* own_diag = reinterpret_cast<double*>(base + n_state * vec + 4 * vec + dots_bytes2(B, max_cg) + 256);
+  double* own_diag = reinterpret_cast<double*>(base + n_state * vec + kCgVecs * vec + dots_bytes2(B, max_cg) + 256);
   double* diag = outs->diag ? outs->diag : own_diag;
   double* dx_sum = want_diag ? outs->dx_sum : nullptr;
   if (want_diag && !accumulate) {
