@@ -50,16 +50,19 @@ struct Graph2 {
   int N, T, t_in, C4;      // C4 = ceil(T / 4) chunks of 4 time steps per node row
   int CB, NB, tilesN, tilesC;   // CTA tile = NB nodes x CB chunks; tiles per window = tilesN * tilesC
   int NBt;                      // thread rows of a tile CTA: block = (CB, NBt), NBt >= NB, CB * NBt a multiple of 32
-  int CB3, NB3t, tiles3, smem3; // time-tiled shared-memory kernels (k3_*): CB3 chunks x all nodes per CTA, block = (CB3, NB3t); CB3 = 0: off
+  int CB3, NB3t, tiles3;        // time-tiled shared-memory kernels (k3_*): CB3 chunks x all nodes per CTA, block = (CB3, NB3t); CB3 = 0: off
   int kd, ku, q1;
   const int* perm;         // perm[internal] = caller's node id
   const int* nbr_d; const float* w_d;     // (N, kd) internal ids, -1 = no neighbour
   const int* nbr_u; const float* w_u;     // (N, ku)
   const int* in_ptr; const int* in_src; const float* in_w;   // in-list of L_d^T (CSR, entries in scatter order)
-  // time-tiled kernels: packed (neighbour, weight bits) entries; temporal table without the self link
-  int kd3, ku3;
-  const int2* tab_d; const int2* tab_u; const int2* tab_in;
-  const float* wself_d;    // (N) weight of the self link of the temporal table
+  // time-tiled kernels: (row byte offset in the tile, weight bits) entries; the self link of the temporal graph is
+  // in wself_d instead of the forward table / the in-list (in_self3 = 0: the in-list kept its self entries)
+  int kd3, ku3, in_self3, in_ptr3_total;
+  int smem3_d, smem3_u, smem3_in;
+  const int2* tab_d; const int2* tab_u; const int2* tab_in3;
+  const int* in_ptr3;
+  const float* wself_d;    // (N)
 };
 
 struct Workspace {

@@ -296,46 +296,87 @@ int mga_plan_create(const mga_graph_desc* d, int device, mga_plan** out) {
     Graph2& g2 = p->g2;
     g2.N = N; g2.T = T; g2.t_in = d->t_in; g2.C4 = (T + 3) / 4; g2.kd = g.kd; g2.ku = g.ku; g2.q1 = g.q1;
     stream2_tiling(&g2);
-    // packed (neighbour, weight bits) tables of the time-tiled kernels: one 8-byte load per entry and no "-1"
-    // branch - a missing neighbour points at the own row with weight 0; the self link of the temporal table
-    // leaves it (the owner already holds that value), its weight goes to tab_wself
-    auto pack = [&](const std::vector<int>& nb, const std::vector<float>& w, int K, bool drop_self, std::vector<int>& tab,
-                    std::vector<float>& wself) {
-      std::vector<std::vector<std::pair<int, float>>> rows(N);
-      int kmax = 0;
-      wself.assign(N, 0.f);
+    // tables of the time-tiled kernels (staged in shared memory by every CTA): entries (byte offset of the
+    // neighbour's row inside the tile, weight bits), so a gather is LDS.64 -> LDS.128 with no integer math and
+    // no "-1" branch - a missing neighbour points at the own row with weight 0.  The self link of the temporal
+    // graph leaves both the forward table and the in-list (the owner already holds that value): tab_wself.
+    if (g2.CB3 > 0) {
+      const int row_bytes = g2.CB3 * 16;
+      std::vector<float> wsd(N, 0.f);
+      auto pack = [&](const std::vector<int>& nb, const std::vector<float>& w, int K, bool drop_self, std::vector<int>& tab) {
+        std::vector<std::vector<std::pair<int, float>>> rows(N);
+        int kmax = 0;
+        for (int k = 0; k < N; ++k) {
+          for (int j = 0; j < K; ++j) {
+            const int m = nb[(size_t)k * K + j];
+            if (m < 0) continue;
+            if (drop_self && m == k) { wsd[k] += w[(size_t)k * K + j]; continue; }
+            rows[k].push_back({m, w[(size_t)k * K + j]});
+          }
+          kmax = std::max(kmax, (int)rows[k].size());
+        }
+        tab.assign((size_t)N * kmax * 2, 0);
+        for (int k = 0; k < N; ++k)
+          for (int j = 0; j < kmax; ++j) {
+            const bool has = j < (int)rows[k].size();
+            const float wj = has ? rows[k][j].second : 0.f;
+            tab[((size_t)k * kmax + j) * 2] = (has ? rows[k][j].first : k) * row_bytes;
+            std::memcpy(&tab[((size_t)k * kmax + j) * 2 + 1], &wj, sizeof(float));
+          }
+        return kmax;
+      };
+      std::vector<int> td, tu, ti, ip3(N + 1, 0);
+      g2.kd3 = pack(nd, wd, g.kd, true, td);
+      g2.ku3 = pack(nu, wu, g.ku, false, tu);
+      // in-list without the self entries.  The forward table's self weight is also the in-list's only when the
+      // in-list is the transpose of the forward table (not for MGA_LDRT_GATHER): check entry by entry
+      bool self_ok = true;
       for (int k = 0; k < N; ++k) {
-        for (int j = 0; j < K; ++j) {
-          const int m = nb[(size_t)k * K + j];
-          if (m < 0) continue;
-          if (drop_self && m == k) { wself[k] += w[(size_t)k * K + j]; continue; }
-          rows[k].push_back({m, w[(size_t)k * K + j]});
+        float ws_in = 0.f;
+        for (int e = ip[k]; e < ip[k + 1]; ++e) {
+          if (is[e] == k) { ws_in += iw[e]; continue; }
+          int wbits;
+          std::memcpy(&wbits, &iw[e], sizeof(float));
+          ti.push_back(is[e] * row_bytes);
+          ti.push_back(wbits);
         }
-        kmax = std::max(kmax, (int)rows[k].size());
+        if (ws_in != wsd[k]) self_ok = false;
+        ip3[k + 1] = (int)ti.size() / 2;
       }
-      tab.assign((size_t)N * kmax * 2, 0);
-      for (int k = 0; k < N; ++k)
-        for (int j = 0; j < kmax; ++j) {
-          const bool has = j < (int)rows[k].size();
-          const float wj = has ? rows[k][j].second : 0.f;
-          tab[((size_t)k * kmax + j) * 2] = has ? rows[k][j].first : k;
-          std::memcpy(&tab[((size_t)k * kmax + j) * 2 + 1], &wj, sizeof(float));
+      if (!self_ok) {          // keep every in-list entry, self included (its weight differs from the forward one)
+        ti.clear();
+        for (int k = 0; k < N; ++k) {
+          for (int e = ip[k]; e < ip[k + 1]; ++e) {
+            int wbits;
+            std::memcpy(&wbits, &iw[e], sizeof(float));
+            ti.push_back(is[e] * row_bytes);
+            ti.push_back(wbits);
+          }
+          ip3[k + 1] = (int)ti.size() / 2;
         }
-      return kmax;
-    };
-    std::vector<int> td, tu, ti(is.size() * 2);
-    std::vector<float> wsd, wsu;
-    g2.kd3 = pack(nd, wd, g.kd, true, td, wsd);
-    g2.ku3 = pack(nu, wu, g.ku, false, tu, wsu);
-    for (size_t e = 0; e < is.size(); ++e) { ti[2 * e] = is[e]; std::memcpy(&ti[2 * e + 1], &iw[e], sizeof(float)); }
-    const int* dev_tab = nullptr;
-    if ((rc = upload(p, td, &dev_tab))) return fail(rc);
-    g2.tab_d = reinterpret_cast<const int2*>(dev_tab);
-    if ((rc = upload(p, tu, &dev_tab))) return fail(rc);
-    g2.tab_u = reinterpret_cast<const int2*>(dev_tab);
-    if ((rc = upload(p, ti, &dev_tab))) return fail(rc);
-    g2.tab_in = reinterpret_cast<const int2*>(dev_tab);
-    if ((rc = upload(p, wsd, &g2.wself_d))) return fail(rc);
+      }
+      g2.in_self3 = self_ok ? 1 : 0;
+      g2.in_ptr3_total = (int)ti.size() / 2;
+      const int* dev_tab = nullptr;
+      if ((rc = upload(p, td, &dev_tab))) return fail(rc);
+      g2.tab_d = reinterpret_cast<const int2*>(dev_tab);
+      if ((rc = upload(p, tu, &dev_tab))) return fail(rc);
+      g2.tab_u = reinterpret_cast<const int2*>(dev_tab);
+      if ((rc = upload(p, ti, &dev_tab))) return fail(rc);
+      g2.tab_in3 = reinterpret_cast<const int2*>(dev_tab);
+      if ((rc = upload(p, ip3, &g2.in_ptr3))) return fail(rc);
+      if ((rc = upload(p, wsd, &g2.wself_d))) return fail(rc);
+      // dynamic shared memory of the three kernels: tile + halo + wself (+ in-list offsets) + table
+      const size_t tile_b = (size_t)N * ((size_t)row_bytes + 8);
+      g2.smem3_d = (int)(tile_b + (size_t)N * g2.kd3 * 8);
+      g2.smem3_u = (int)(tile_b + (size_t)N * g2.ku3 * 8);
+      g2.smem3_in = (int)(tile_b + (size_t)((N + 2) & ~1) * 4 + (size_t)g2.in_ptr3_total * 8);
+      if (std::max(g2.smem3_d, std::max(g2.smem3_u, g2.smem3_in)) > p->max_smem_optin - 1024) g2.CB3 = 0;
+      if (std::getenv("MGA_S3_VERBOSE"))
+        std::fprintf(stderr, "[mga] time-tiled kernels: N=%d C4=%d CB3=%d NB3t=%d tiles3=%d kd3=%d ku3=%d in=%d self=%d smem d/u/in=%d/%d/%d\n",
+                     N, g2.C4, g2.CB3, g2.NB3t, g2.tiles3, g2.kd3, g2.ku3, g2.in_ptr3_total, g2.in_self3, g2.smem3_d, g2.smem3_u,
+                     g2.smem3_in);
+    }
     if ((rc = upload(p, perm, &g2.perm))) return fail(rc);
     if ((rc = upload(p, nd, &g2.nbr_d))) return fail(rc);
     if ((rc = upload(p, wd, &g2.w_d))) return fail(rc);

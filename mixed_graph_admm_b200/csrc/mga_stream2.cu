@@ -24,6 +24,9 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <map>
+#include <mutex>
+#include <tuple>
 
 #include "mga_common.cuh"
 
@@ -354,217 +357,327 @@ __global__ void __launch_bounds__(kFlat) k2_xr(Graph2 g, int64_t B, int it, floa
   block_add(dot, dots + (size_t)(2 * it + 2) * B + k.b, threadIdx.x, kFlat);
 }
 
-// ---- time-tiled kernels: the gathered vector staged in shared memory ---------------------------------------
-// For graphs whose node set fits one CTA's shared memory (N * CB3 * 16 B <= 48 KB: the PEMS graphs at any T)
-// a CTA owns ALL nodes of one window over a tile of CB3 chunks (4 * CB3 time steps).  Phase 1 streams the tile
-// in with coalesced 128-bit loads (and applies the p update on the way: p' = r + beta p is written once to HBM
-// and once to shared memory), phase 2 gathers the neighbours' chunks from shared memory - the gathers that
-// bound k2_ldr_shift / k2_ldrt_lhs / k2_lu_lhs (L1 wavefronts + L2 traffic at ~2 TB/s of DRAM traffic) no longer
-// leave the SM.  Because the gathers are chunk-aligned (shifted q) a tile needs no halo columns, only one halo
-// SCALAR per node (p'[first step of the next tile] / qs[last step of the previous tile]).  The p update moves
-// into the operator kernel, so per CG iteration: x / z_d systems (r,p -> p',qs : 16) + (p',qs -> Ap : 12) +
-// k2_xr 24 = 52 B/pt in 3 launches (k2: 56 in 4); z_u (r,p -> p',Ap : 16) + 24 = 40 B/pt = the algorithmic
-// minimum, in 2 launches (k2: 44 in 3).  p is ping-ponged (a tile's halo reads the next tile's OLD p).
+// ---- time-tiled kernels: the gathered vector AND the graph table staged in shared memory -------------------
+// For graphs whose node set fits one CTA's shared memory (the PEMS graphs at any T) a CTA owns ALL nodes of one
+// window over a tile of CB3 chunks (4 * CB3 time steps).  Phase 1 streams the tile in with coalesced 128-bit
+// loads (and applies the p update on the way: p' = r + beta p is written once to HBM and once to shared memory),
+// phase 2 gathers the neighbours' chunks from shared memory - the gathers that bound k2_ldr_shift / k2_ldrt_lhs /
+// k2_lu_lhs no longer leave the SM.  Because the gathers are chunk-aligned (shifted q) a tile needs no halo
+// columns, only one halo SCALAR per node (p'[first step of the next tile] / qs[last step of the previous tile]).
+// The p update moves into the operator kernel, so per CG iteration: x / z_d systems (r,p -> p',qs : 16) +
+// (p',qs -> Ap : 12) + k2_xr 24 = 52 B/pt in 3 launches (k2: 56 in 4); z_u (r,p -> p',Ap : 16) + 24 = 40 B/pt = the
+// algorithmic minimum, in 2 launches (k2: 44 in 3).  p is ping-ponged (a tile's halo reads the next tile's OLD p).
+// First version (tables read through L1, one CTA per tile): no faster than k2 - ncu showed 231 warp instructions per
+// 32 chunks and every table read of phase 2 a long-scoreboard stall.  Hence: CTAs are persistent (grid = resident
+// CTAs, tiles handed out round-robin), the table is staged ONCE per CTA in shared memory as (byte offset of the
+// neighbour's row in the tile, weight) - entry -> LDS.64, gather -> LDS.128 at [thread base + offset], no integer
+// math in between -, the self link leaves the tables (the owner holds the value), rows are unrolled over the
+// table width, and all per-thread predicates / pointers are hoisted out of the row loop.
 constexpr int kU3 = 4;   // node rows whose loads are issued together in phase 1
 
-// SRC 0: v = r + beta p   SRC 1: v = r (first iteration)   SRC 2: v = vin (initial residual: v = x0)
+struct Smem3 {
+  float4* tile;    // (N, CB) chunks
+  float* halo;     // (N)
+  float* wself;    // (N)
+  int* ptr;        // (N + 1) in-list offsets (k3_ldrt_lhs only)
+  int2* tab;       // entries
+};
+__device__ __forceinline__ Smem3 carve3(const Graph2& g, float4* base, int CB, bool with_ptr) {
+  Smem3 s;
+  s.tile = base;
+  s.halo = reinterpret_cast<float*>(base + g.N * CB);
+  s.wself = s.halo + g.N;
+  s.ptr = reinterpret_cast<int*>(s.wself + g.N);
+  const int np = with_ptr ? ((g.N + 2) & ~1) : 0;      // keeps the entries 8-byte aligned
+  s.tab = reinterpret_cast<int2*>(s.ptr + np);
+  return s;
+}
+
+// While a tile is being gathered, the lines of the CTA's NEXT tile are pulled into L2 (prefetch.global.L2 needs no
+// registers): the two-phase structure leaves no loads in flight during phase 2 otherwise.
+#ifndef MGA_S3_PREFETCH
+#define MGA_S3_PREFETCH 1
+#endif
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+#if MGA_S3_PREFETCH
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#endif
+}
+// one prefetch per 16-byte chunk of the thread's column of tile `tl` in up to three vectors
+__device__ __forceinline__ void tile_prefetch(const Graph2& g, int tl, int total, const float* v0, const float* v1, const float* v2) {
+#if MGA_S3_PREFETCH
+  if (tl >= total) return;
+  const int CB = blockDim.x, NBt = blockDim.y;
+  const int b = tl / g.tiles3, c = (tl - b * g.tiles3) * CB + threadIdx.x;
+  if (c >= g.C4) return;
+  const size_t w0 = (size_t)b * (size_t)(g.N * g.C4) + c;
+  for (int n = threadIdx.y; n < g.N; n += NBt) {
+    const size_t k = w0 + (size_t)(n * g.C4);
+    if (v0) prefetch_l2(reinterpret_cast<const float4*>(v0) + k);
+    if (v1) prefetch_l2(reinterpret_cast<const float4*>(v1) + k);
+    if (v2) prefetch_l2(reinterpret_cast<const float4*>(v2) + k);
+  }
+#endif
+}
+
+// SRC 0: v = r + beta p   SRC 1: v = r (first iteration)   SRC 2: v = r (no store: r is x0 of the initial residual)
 template <int SRC>
-__device__ __forceinline__ void tile_fill(const Graph2& g, int64_t B, int it, const float* __restrict__ r,
+__device__ __forceinline__ void tile_fill(const Graph2& g, int64_t B, int it, int b, int c0, const float* __restrict__ r,
                                           const float* __restrict__ p_old, float* __restrict__ p_new,
                                           const double* __restrict__ dots, float4* tile, float* halo, bool want_halo) {
   const int CB = blockDim.x, NBt = blockDim.y, tx = threadIdx.x;
-  const int b = blockIdx.x, c0 = blockIdx.y * CB, c = c0 + tx, cn = c0 + CB;
+  const int c = c0 + tx, cn = c0 + CB;
   const bool cok = c < g.C4, last = want_halo && tx == CB - 1, hok = cn < g.C4;
   const size_t w0 = (size_t)b * (size_t)(g.N * g.C4);
+  const float4* rw = reinterpret_cast<const float4*>(r) + w0;
+  const float4* pw = reinterpret_cast<const float4*>(p_old) + w0;
+  float4* ow = reinterpret_cast<float4*>(p_new) + w0;
   float beta = 0.f;
   if (SRC == 0) beta = (float)dots[(size_t)(2 * it) * B + b] / (float)dots[(size_t)(2 * it - 2) * B + b];   // ADMM.py:356
-  for (int n0 = threadIdx.y; n0 < g.N; n0 += kU3 * NBt) {
+  const int step = NBt * g.C4;
+  int i0 = threadIdx.y * g.C4 + (cok ? c : 0);
+  for (int n0 = threadIdx.y; n0 < g.N; n0 += kU3 * NBt, i0 += kU3 * step) {
     float4 a[kU3], q[kU3];
     float ha[kU3], hq[kU3];
 #pragma unroll
     for (int u = 0; u < kU3; ++u) {
-      const int n = n0 + u * NBt;
-      const bool ok = n < g.N && cok;
-      const size_t k = ok ? w0 + (size_t)(n * g.C4 + c) : w0;
-      a[u] = ld4s(r, k);
-      if (SRC == 0) q[u] = ld4s(p_old, k);
+      const bool in = n0 + u * NBt < g.N;
+      const int i = in ? i0 + u * step : 0;
+      a[u] = __ldcs(rw + i);
+      if (SRC == 0) q[u] = __ldcs(pw + i);
       if (last) {
-        const size_t hk = (n < g.N && hok) ? (w0 + (size_t)(n * g.C4 + cn)) * 4 : w0 * 4;
-        ha[u] = ld1s(r, hk);
-        if (SRC == 0) hq[u] = ld1s(p_old, hk);
+        const int hi = (in && hok) ? (i + 1) * 4 : 0;      // first element of the next tile's first chunk
+        ha[u] = __ldcs(reinterpret_cast<const float*>(rw) + hi);
+        if (SRC == 0) hq[u] = __ldcs(reinterpret_cast<const float*>(pw) + hi);
       }
     }
 #pragma unroll
     for (int u = 0; u < kU3; ++u) {
       const int n = n0 + u * NBt;
-      if (n >= g.N) continue;
+      if (n >= g.N) break;
       float4 v = a[u];
       if (SRC == 0) v = make_float4(a[u].x + beta * q[u].x, a[u].y + beta * q[u].y, a[u].z + beta * q[u].z, a[u].w + beta * q[u].w);
       if (!cok) v = make_float4(0.f, 0.f, 0.f, 0.f);
       tile[n * CB + tx] = v;
-      if (SRC != 2 && cok) st4s(p_new, w0 + (size_t)(n * g.C4 + c), v);
+      if (SRC != 2 && cok) __stcs(ow + i0 + u * step, v);
       if (last) halo[n] = hok ? (SRC == 0 ? ha[u] + beta * hq[u] : ha[u]) : 0.f;
     }
   }
 }
 
-// acc += sum_j w_j tile[nbr_j][tx] over a packed forward table (rows of `slots` (neighbour, weight) entries; a missing
-// neighbour is (own row, 0)), neighbours read from the shared-memory tile
-__device__ __forceinline__ float4 fwd_gather_s(const int2* __restrict__ tab, int slots, const float4* tile, int n, int tx,
-                                               int CB, float4 acc) {
-  const int2* row = tab + n * slots;
+// acc += sum_j w_j tile[nbr_j][tx]: entries (byte offset of the neighbour's row in the tile, weight), `mine` = the
+// thread's chunk column in the tile; K > 0: compile-time table width
+template <int K>
+__device__ __forceinline__ float4 gather3(const int2* row, int slots, const char* mine, float4 acc) {
+#ifdef MGA_S3_NOGATHER      // timing experiment only: what the tile traffic alone costs
+  return acc;
+#endif
+  if (K > 0) {
+    int2 e[K > 0 ? K : 1];
+#pragma unroll
+    for (int j = 0; j < K; ++j) e[j] = row[j];
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      const float wj = __int_as_float(e[j].y);
+      const float4 a = *reinterpret_cast<const float4*>(mine + e[j].x);
+      acc.x += wj * a.x; acc.y += wj * a.y; acc.z += wj * a.z; acc.w += wj * a.w;
+    }
+  } else {
 #pragma unroll 2
-  for (int j = 0; j < slots; ++j) {
-    const int2 e = row[j];
-    const float wj = __int_as_float(e.y);
-    const float4 a = tile[e.x * CB + tx];
-    acc.x += wj * a.x; acc.y += wj * a.y; acc.z += wj * a.z; acc.w += wj * a.w;
+    for (int j = 0; j < slots; ++j) {
+      const int2 e = row[j];
+      const float wj = __int_as_float(e.y);
+      const float4 a = *reinterpret_cast<const float4*>(mine + e.x);
+      acc.x += wj * a.x; acc.y += wj * a.y; acc.z += wj * a.z; acc.w += wj * a.w;
+    }
   }
   return acc;
 }
 
+__device__ __forceinline__ void stage_table(const int2* __restrict__ src, int n_ent, int2* dst) {
+  const int tid = tid2(), nt = blockDim.x * blockDim.y;
+  for (int k = tid; k < n_ent; k += nt) dst[k] = src[k];
+}
+
 // (r, p) -> p', qs = shifted L_d p'   [SRC 2: x0 -> qs]
-template <int SRC>
+template <int SRC, int K>
 __global__ void __launch_bounds__(256, 4) k3_p_ldr(Graph2 g, int64_t B, int it, const float* __restrict__ r,
                                                    const float* __restrict__ p_old, float* __restrict__ p_new,
                                                    float* __restrict__ qs, const double* __restrict__ dots) {
   extern __shared__ float4 s3[];
   const int CB = blockDim.x, NBt = blockDim.y, tx = threadIdx.x;
-  float4* tile = s3;
-  float* halo = reinterpret_cast<float*>(s3 + g.N * CB);
-  tile_fill<SRC>(g, B, it, r, p_old, p_new, dots, tile, halo, true);
-  __syncthreads();
-  const int c = blockIdx.y * CB + tx;
-  if (c >= g.C4) return;
-  const size_t w0 = (size_t)blockIdx.x * (size_t)(g.N * g.C4);
-  const int t = 4 * c;
-  for (int n = threadIdx.y; n < g.N; n += NBt) {
-    const float4 own = tile[n * CB + tx];
-    const float nxt = (tx + 1 < CB) ? reinterpret_cast<const float*>(tile + n * CB + tx + 1)[0] : halo[n];
-    const float ws = g.wself_d[n];
-    const float4 acc = fwd_gather_s(g.tab_d, g.kd3, tile, n, tx, CB, make_float4(ws * own.x, ws * own.y, ws * own.z, ws * own.w));
-    float4 o;
-    o.x = (t + 1 < g.T) ? own.y - acc.x : 0.f;
-    o.y = (t + 2 < g.T) ? own.z - acc.y : 0.f;
-    o.z = (t + 3 < g.T) ? own.w - acc.z : 0.f;
-    o.w = (t + 4 < g.T) ? nxt - acc.w : 0.f;
-    st4s(qs, w0 + (size_t)(n * g.C4 + c), o);
+  const Smem3 s = carve3(g, s3, CB, false);
+  stage_table(g.tab_d, g.N * g.kd3, s.tab);
+  for (int k = tid2(); k < g.N; k += CB * NBt) s.wself[k] = g.wself_d[k];
+  const int total = (int)B * g.tiles3;
+  const char* mine = reinterpret_cast<const char*>(s.tile + tx);
+  // the element after the thread's chunk: next chunk of the row, or the halo scalar for the tile's last chunk
+  const float* nxt_p = tx + 1 < CB ? reinterpret_cast<const float*>(s.tile + tx + 1) : s.halo;
+  const int nxt_stride = tx + 1 < CB ? CB * 4 : 1;
+  for (int tl = blockIdx.x; tl < total; tl += gridDim.x) {
+    const int b = tl / g.tiles3, c0 = (tl - b * g.tiles3) * CB, c = c0 + tx;
+    if (tl != (int)blockIdx.x) __syncthreads();          // the previous tile's gathers are done
+    tile_fill<SRC>(g, B, it, b, c0, r, p_old, p_new, dots, s.tile, s.halo, true);
+    __syncthreads();
+    tile_prefetch(g, tl + gridDim.x, total, r, SRC == 0 ? p_old : nullptr, nullptr);
+    if (c >= g.C4) continue;
+    float4* qw = reinterpret_cast<float4*>(qs) + (size_t)b * (size_t)(g.N * g.C4) + c;
+    const int t = 4 * c;
+    const bool v1 = t + 1 < g.T, v2 = t + 2 < g.T, v3 = t + 3 < g.T, v4 = t + 4 < g.T;
+    for (int n = threadIdx.y; n < g.N; n += NBt) {
+      const float4 own = s.tile[n * CB + tx];
+      const float nxt = nxt_p[n * nxt_stride];
+      const float ws = s.wself[n];
+      const float4 acc = gather3<K>(s.tab + n * g.kd3, g.kd3, mine,
+                                    make_float4(ws * own.x, ws * own.y, ws * own.z, ws * own.w));
+      float4 o;
+      o.x = v1 ? own.y - acc.x : 0.f;
+      o.y = v2 ? own.z - acc.y : 0.f;
+      o.z = v3 ? own.w - acc.z : 0.f;
+      o.w = v4 ? nxt - acc.w : 0.f;
+      __stcs(qw + n * g.C4, o);
+    }
   }
 }
 
 // (v, qs) -> Ap, <v, Ap>  [MODE 1: r = rhs - A v, <r, r>];  A = diag + c L_d^T L_d; qs tile in shared memory
 template <int MODE>
-__global__ void __launch_bounds__(256, 4) k3_ldrt_lhs(Graph2 g, const float* __restrict__ v, const float* __restrict__ qs,
-                                                      const float* __restrict__ rhs, float* __restrict__ out,
-                                                      double* __restrict__ slot, float a, float cc, int xsys) {
+__global__ void __launch_bounds__(256, 4) k3_ldrt_lhs(Graph2 g, int64_t B, const float* __restrict__ v,
+                                                      const float* __restrict__ qs, const float* __restrict__ rhs,
+                                                      float* __restrict__ out, double* __restrict__ slot, float a, float cc,
+                                                      int xsys) {
   extern __shared__ float4 s3[];
   const int CB = blockDim.x, NBt = blockDim.y, tx = threadIdx.x;
-  float4* tile = s3;
-  float* halo = reinterpret_cast<float*>(s3 + g.N * CB);
-  const int b = blockIdx.x, c0 = blockIdx.y * CB, c = c0 + tx;
-  const bool cok = c < g.C4;
-  const size_t w0 = (size_t)b * (size_t)(g.N * g.C4);
-  for (int n0 = threadIdx.y; n0 < g.N; n0 += kU3 * NBt) {
-    float4 q[kU3];
-    float h[kU3];
+  const Smem3 s = carve3(g, s3, CB, true);
+  stage_table(g.tab_in3, g.in_ptr3_total, s.tab);
+  for (int k = tid2(); k < g.N; k += CB * NBt) s.wself[k] = g.wself_d[k];
+  for (int k = tid2(); k <= g.N; k += CB * NBt) s.ptr[k] = g.in_ptr3[k];
+  const int total = (int)B * g.tiles3;
+  const char* mine = reinterpret_cast<const char*>(s.tile + tx);
+  // the element before the thread's chunk: q[4c] = qs[4c - 1]
+  const float* prv_p = tx > 0 ? reinterpret_cast<const float*>(s.tile + tx) - 1 : s.halo;
+  const int prv_stride = tx > 0 ? CB * 4 : 1;
+  const int step = NBt * g.C4;
+  const bool self_in = g.in_self3 != 0;
+  for (int tl = blockIdx.x; tl < total; tl += gridDim.x) {
+    const int b = tl / g.tiles3, c0 = (tl - b * g.tiles3) * CB, c = c0 + tx;
+    const bool cok = c < g.C4;
+    const size_t w0 = (size_t)b * (size_t)(g.N * g.C4);
+    const float4* qw = reinterpret_cast<const float4*>(qs) + w0;
+    if (tl != (int)blockIdx.x) __syncthreads();
+    int i0 = threadIdx.y * g.C4 + (cok ? c : 0);
+    for (int n0 = threadIdx.y; n0 < g.N; n0 += kU3 * NBt, i0 += kU3 * step) {
+      float4 q[kU3];
+      float h[kU3];
 #pragma unroll
-    for (int u = 0; u < kU3; ++u) {
-      const int n = n0 + u * NBt;
-      const bool ok = n < g.N && cok;
-      q[u] = ld4s(qs, ok ? w0 + (size_t)(n * g.C4 + c) : w0);
-      if (tx == 0) h[u] = (n < g.N && c0 > 0) ? ld1s(qs, (w0 + (size_t)(n * g.C4 + c0)) * 4 - 1) : 0.f;   // q[4 c0] = qs[4 c0 - 1]; q[0] = 0
-    }
+      for (int u = 0; u < kU3; ++u) {
+        const bool in = n0 + u * NBt < g.N;
+        const int i = in ? i0 + u * step : 0;
+        q[u] = __ldcs(qw + i);
+        if (tx == 0) h[u] = (in && c0 > 0) ? __ldcs(reinterpret_cast<const float*>(qw) + i * 4 - 1) : 0.f;   // q[0] = 0 (ADMM.py:176)
+      }
 #pragma unroll
-    for (int u = 0; u < kU3; ++u) {
-      const int n = n0 + u * NBt;
-      if (n >= g.N) continue;
-      tile[n * CB + tx] = cok ? q[u] : make_float4(0.f, 0.f, 0.f, 0.f);
-      if (tx == 0) halo[n] = h[u];
+      for (int u = 0; u < kU3; ++u) {
+        const int n = n0 + u * NBt;
+        if (n >= g.N) break;
+        s.tile[n * CB + tx] = cok ? q[u] : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (tx == 0) s.halo[n] = h[u];
+      }
     }
+    __syncthreads();
+    tile_prefetch(g, tl + gridDim.x, total, qs, nullptr, nullptr);
+    float dot = 0.f;
+    if (cok) {
+      const int t0 = 4 * c;
+      const float4* vw = reinterpret_cast<const float4*>(v) + w0 + c;
+      const float4* rw = reinterpret_cast<const float4*>(rhs) + w0 + c;
+      float4* ow = reinterpret_cast<float4*>(out) + w0 + c;
+      float hx[4], tv[4];      // H^T H keeps rows t < t_in (ADMM.py:372-374); pads (t >= T) stay 0
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { hx[j] = (xsys && t0 + j < g.t_in) ? 1.f : 0.f; tv[j] = t0 + j < g.T ? 1.f : 0.f; }
+      for (int n = threadIdx.y; n < g.N; n += NBt) {
+        const float4 pv = __ldcs(vw + n * g.C4);
+        float4 rh;
+        if (MODE == 1) rh = __ldcs(rw + n * g.C4);
+        const float4 q1 = s.tile[n * CB + tx];
+        const float qprev = prv_p[n * prv_stride];
+        const float ws = self_in ? s.wself[n] : 0.f;
+        float4 f = make_float4(ws * q1.x, ws * q1.y, ws * q1.z, ws * q1.w);     // self link: w_self qs_own
+        int e = s.ptr[n];
+        const int e1 = s.ptr[n + 1];
+        for (; e + 2 <= e1; e += 2) f = gather3<2>(s.tab + e, 2, mine, f);
+        if (e < e1) f = gather3<1>(s.tab + e, 1, mine, f);
+        const float pp[4] = {pv.x, pv.y, pv.z, pv.w};
+        const float q[4] = {qprev, q1.x, q1.y, q1.z};
+        const float ff[4] = {f.x, f.y, f.z, f.w};
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float l = q[j] - ff[j];
+          float val;
+          if (xsys) val = (hx[j] * pp[j] + a * pp[j]) + cc * l;      // ADMM.py:372-379
+          else val = cc * l + a * pp[j];                            // ADMM.py:394
+          o[j] = tv[j] * val;
+        }
+        if (MODE == 0) {
+          __stcs(ow + n * g.C4, make_float4(o[0], o[1], o[2], o[3]));
+          dot += (pp[0] * o[0] + pp[1] * o[1]) + (pp[2] * o[2] + pp[3] * o[3]);
+        } else {
+          const float r0 = rh.x - o[0], r1 = rh.y - o[1], r2 = rh.z - o[2], r3 = rh.w - o[3];
+          __stcs(ow + n * g.C4, make_float4(r0, r1, r2, r3));
+          dot += (r0 * r0 + r1 * r1) + (r2 * r2 + r3 * r3);
+        }
+      }
+    }
+    block_add(dot, slot + b, tid2(), blockDim.x * blockDim.y);
   }
-  __syncthreads();
-  float dot = 0.f;
-  if (cok) {
-    const int t0 = 4 * c;
-    for (int n = threadIdx.y; n < g.N; n += NBt) {
-      const size_t k = w0 + (size_t)(n * g.C4 + c);
-      const float4 pv = ld4s(v, k);
-      float4 rh;
-      if (MODE == 1) rh = ld4s(rhs, k);
-      const float4 q1 = tile[n * CB + tx];
-      const float qprev = tx > 0 ? reinterpret_cast<const float*>(tile + n * CB + tx)[-1] : halo[n];
-      float4 f = make_float4(0.f, 0.f, 0.f, 0.f);
-      const int e1 = g.in_ptr[n + 1];
-#pragma unroll 2
-      for (int e = g.in_ptr[n]; e < e1; ++e) {
-        const int2 en = g.tab_in[e];
-        const float w = __int_as_float(en.y);
-        const float4 s = tile[en.x * CB + tx];
-        f.x += w * s.x; f.y += w * s.y; f.z += w * s.z; f.w += w * s.w;
-      }
-      const float pp[4] = {pv.x, pv.y, pv.z, pv.w};
-      const float q[4] = {qprev, q1.x, q1.y, q1.z};
-      const float ff[4] = {f.x, f.y, f.z, f.w};
-      float o[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int t = t0 + j;
-        const float l = q[j] - ff[j];
-        float val;
-        if (xsys) val = ((t < g.t_in ? pp[j] : 0.f) + a * pp[j]) + cc * l;      // ADMM.py:372-379
-        else val = cc * l + a * pp[j];                                          // ADMM.py:394
-        o[j] = t < g.T ? val : 0.f;
-      }
-      if (MODE == 0) {
-        st4s(out, k, make_float4(o[0], o[1], o[2], o[3]));
-        dot += (pp[0] * o[0] + pp[1] * o[1]) + (pp[2] * o[2] + pp[3] * o[3]);
-      } else {
-        const float r0 = rh.x - o[0], r1 = rh.y - o[1], r2 = rh.z - o[2], r3 = rh.w - o[3];
-        st4s(out, k, make_float4(r0, r1, r2, r3));
-        dot += (r0 * r0 + r1 * r1) + (r2 * r2 + r3 * r3);
-      }
-    }
-  }
-  block_add(dot, slot + b, tid2(), blockDim.x * blockDim.y);
 }
 
 // z_u system: (r, p) -> p', Ap = (c L_u + a I) p', <p', Ap>   [SRC 2 / MODE 1: r = rhs - A x0, <r, r>]
-template <int SRC, int MODE>
+template <int SRC, int MODE, int K>
 __global__ void __launch_bounds__(256, 4) k3_lu(Graph2 g, int64_t B, int it, const float* __restrict__ r,
                                                 const float* __restrict__ p_old, float* __restrict__ p_new,
                                                 const float* __restrict__ rhs, float* __restrict__ out,
                                                 const double* __restrict__ dots, double* __restrict__ slot, float a, float cc) {
   extern __shared__ float4 s3[];
   const int CB = blockDim.x, NBt = blockDim.y, tx = threadIdx.x;
-  float4* tile = s3;
-  tile_fill<SRC>(g, B, it, r, p_old, p_new, dots, tile, nullptr, false);
-  __syncthreads();
-  const int b = blockIdx.x, c = blockIdx.y * CB + tx;
-  const size_t w0 = (size_t)b * (size_t)(g.N * g.C4);
-  float dot = 0.f;
-  if (c < g.C4) {
-    for (int n = threadIdx.y; n < g.N; n += NBt) {
-      const size_t k = w0 + (size_t)(n * g.C4 + c);
-      float4 rh;
-      if (MODE == 1) rh = ld4s(rhs, k);
-      const float4 pv = tile[n * CB + tx];
-      const float4 acc = fwd_gather_s(g.tab_u, g.ku3, tile, n, tx, CB, make_float4(0.f, 0.f, 0.f, 0.f));
-      float4 o;
-      o.x = cc * (pv.x - acc.x) + a * pv.x;
-      o.y = cc * (pv.y - acc.y) + a * pv.y;
-      o.z = cc * (pv.z - acc.z) + a * pv.z;
-      o.w = cc * (pv.w - acc.w) + a * pv.w;    // pads: v = 0 and every gathered pad is 0
-      if (MODE == 0) {
-        st4s(out, k, o);
-        dot += (pv.x * o.x + pv.y * o.y) + (pv.z * o.z + pv.w * o.w);
-      } else {
-        const float4 rr = make_float4(rh.x - o.x, rh.y - o.y, rh.z - o.z, rh.w - o.w);
-        st4s(out, k, rr);
-        dot += (rr.x * rr.x + rr.y * rr.y) + (rr.z * rr.z + rr.w * rr.w);
+  const Smem3 s = carve3(g, s3, CB, false);
+  stage_table(g.tab_u, g.N * g.ku3, s.tab);
+  const int total = (int)B * g.tiles3;
+  const char* mine = reinterpret_cast<const char*>(s.tile + tx);
+  for (int tl = blockIdx.x; tl < total; tl += gridDim.x) {
+    const int b = tl / g.tiles3, c0 = (tl - b * g.tiles3) * CB, c = c0 + tx;
+    if (tl != (int)blockIdx.x) __syncthreads();
+    tile_fill<SRC>(g, B, it, b, c0, r, p_old, p_new, dots, s.tile, s.halo, false);
+    __syncthreads();
+    tile_prefetch(g, tl + gridDim.x, total, r, SRC == 0 ? p_old : nullptr, MODE == 1 ? rhs : nullptr);
+    float dot = 0.f;
+    if (c < g.C4) {
+      const size_t w0 = (size_t)b * (size_t)(g.N * g.C4);
+      const float4* rw = reinterpret_cast<const float4*>(rhs) + w0 + c;
+      float4* ow = reinterpret_cast<float4*>(out) + w0 + c;
+      for (int n = threadIdx.y; n < g.N; n += NBt) {
+        float4 rh;
+        if (MODE == 1) rh = __ldcs(rw + n * g.C4);
+        const float4 pv = s.tile[n * CB + tx];
+        const float4 acc = gather3<K>(s.tab + n * g.ku3, g.ku3, mine, make_float4(0.f, 0.f, 0.f, 0.f));
+        float4 o;
+        o.x = cc * (pv.x - acc.x) + a * pv.x;
+        o.y = cc * (pv.y - acc.y) + a * pv.y;
+        o.z = cc * (pv.z - acc.z) + a * pv.z;
+        o.w = cc * (pv.w - acc.w) + a * pv.w;    // pads: v = 0 and every gathered pad is 0
+        if (MODE == 0) {
+          __stcs(ow + n * g.C4, o);
+          dot += (pv.x * o.x + pv.y * o.y) + (pv.z * o.z + pv.w * o.w);
+        } else {
+          const float4 rr = make_float4(rh.x - o.x, rh.y - o.y, rh.z - o.z, rh.w - o.w);
+          __stcs(ow + n * g.C4, rr);
+          dot += (rr.x * rr.x + rr.y * rr.y) + (rr.z * rr.z + rr.w * rr.w);
+        }
       }
     }
+    block_add(dot, slot + b, tid2(), blockDim.x * blockDim.y);
   }
-  block_add(dot, slot + b, tid2(), blockDim.x * blockDim.y);
 }
 
 // alpha / beta live in arrays of B_out windows per iteration (this call's B windows are a slice of them)
@@ -769,20 +882,23 @@ void stream2_tiling(Graph2* g) {
   g->tilesN = (g->N + g->NBt - 1) / g->NBt;
   g->NB = (g->N + g->tilesN - 1) / g->tilesN;           // balanced node tiles, NB <= NBt (extra rows are masked off)
   g->tilesC = (g->C4 + g->CB - 1) / g->CB;
-  // time-tiled shared-memory kernels (k3_*): all nodes x CB3 chunks (+ one halo float per node) per CTA, <= 48 KB
+  // time-tiled shared-memory kernels (k3_*): all nodes x CB3 chunks + halo + self weights + the graph table per CTA;
+  // the largest tile that leaves 4 CTAs per SM, else the largest that leaves 2
   g->CB3 = 0;
   int force = 0;
   if (const char* e = std::getenv("MGA_S3_CB")) force = std::atoi(e);     // 0 = automatic, < 0 = off, > 0 = chunks per tile
   if (force >= 0) {
-    int cands[5] = {force > 0 ? std::min(force, g->C4) : std::min(g->C4, 8), 4, 2, 1, 0};
-    for (int k = 0; cands[k] > 0 && g->CB3 == 0; ++k)
-      if (cands[k] <= g->C4 && (size_t)g->N * ((size_t)cands[k] * 16 + 4) <= 48 * 1024) g->CB3 = cands[k];
+    const int cands[5] = {force > 0 ? std::min(force, g->C4) : std::min(g->C4, 8), 4, 2, 1, 0};
+    const size_t table = (size_t)g->N * std::max(g->kd, g->ku) * 8 + (size_t)(g->N + 2) * 4;
+    const size_t limits[2] = {(228 * 1024) / 4 - 1024, (228 * 1024) / 2 - 1024};
+    for (int l = 0; l < 2 && g->CB3 == 0; ++l)
+      for (int k = 0; cands[k] > 0 && g->CB3 == 0; ++k)
+        if (cands[k] <= g->C4 && (size_t)g->N * ((size_t)cands[k] * 16 + 8) + table <= limits[l]) g->CB3 = cands[k];
   }
   if (g->CB3 > 0) {
     const int cb = g->CB3;
     g->NB3t = (cb & (cb - 1)) == 0 ? 256 / cb : 32 * std::max(1, 8 / cb);     // cb * NB3t whole warps, <= 256 threads
     g->tiles3 = (g->C4 + cb - 1) / cb;
-    g->smem3 = (int)((size_t)g->N * ((size_t)cb * 16 + 4));
   }
 }
 
@@ -799,6 +915,32 @@ constexpr int kCgVecs = 5;
 static size_t vec_bytes2(const Graph2& g, int64_t B) { return (((size_t)B * g.N * g.C4 * 16) + 255) & ~(size_t)255; }
 static size_t dots_bytes2(int64_t B, int max_iter) { return (((size_t)(2 * max_iter + 1) * B * sizeof(double)) + 255) & ~(size_t)255; }
 
+// Resident CTAs per SM of a time-tiled kernel at this block size / dynamic shared memory (opt-in above 48 KB);
+// asked once per (kernel, configuration, device).
+static int k3_ctas_per_sm(const void* kern, int threads, size_t smem, int* rc) {
+  static std::mutex mu;
+  static std::map<std::tuple<const void*, int, size_t, int>, int> cache;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(mu);
+  const auto key = std::make_tuple(kern, threads, smem, dev);
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second;
+  // the opt-in limit only ever grows: lowering it would break the cached larger configurations
+  static std::map<std::pair<const void*, int>, size_t> limit;
+  size_t& lim = limit.emplace(std::make_pair(kern, dev), (size_t)48 * 1024).first->second;
+  cudaError_t e = cudaSuccess;
+  if (smem > lim) {
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) lim = smem;
+  }
+  int n = 0;
+  if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kern, threads, smem);
+  if (e != cudaSuccess || n < 1) { *rc = cuda_fail(e == cudaSuccess ? cudaErrorLaunchOutOfResources : e, "time-tiled kernel occupancy"); return 0; }
+  cache[key] = n;
+  return n;
+}
+
 // CG_solver (ADMM.py:329-368) with a fixed iteration count on internal-layout vectors; x holds x0 / the solution.
 static int cg2(mga_plan* p, int system, const mga_params* m, const float* rhs, float* x, int64_t B, int64_t B_out, int n_cg,
                float* alpha, float* beta, const Bufs2& w, cudaStream_t st) {
@@ -813,30 +955,40 @@ static int cg2(mga_plan* p, int system, const mga_params* m, const float* rhs, f
   MGA_CUDA(cudaMemsetAsync(w.dots, 0, (size_t)(2 * n_cg + 1) * B * sizeof(double), st));
   if (g.CB3 > 0) {
     // time-tiled shared-memory kernels: p update fused into the operator kernel, p ping-ponged
-    const dim3 grid3((unsigned)B, g.tiles3), blk3(g.CB3, g.NB3t);
-    const size_t sm = (size_t)g.smem3;
+    const dim3 blk3(g.CB3, g.NB3t);
+    const int total = (int)B * g.tiles3;
     float *p_old = w.p, *p_new = w.p2;
+    int rc3 = MGA_OK;
+#define MGA_K3_LAUNCH(kern, smem, ...)                                                    \
+    do {                                                                                   \
+      const int ctas = k3_ctas_per_sm((const void*)kern, g.CB3 * g.NB3t, (size_t)(smem), &rc3);      \
+      if (rc3) return rc3;                                                                 \
+      kern<<<std::min(total, ctas * p->sm_count), blk3, (size_t)(smem), st>>>(__VA_ARGS__); \
+      MGA_LAUNCH_CHECK(#kern);                                                             \
+    } while (0)
+#define MGA_K3_BY_K(K, macro) \
+    do { if ((K) == 4) { macro(4); } else if ((K) == 6) { macro(6); } else if ((K) == 8) { macro(8); } else { macro(0); } } while (0)
     if (system == MGA_SYS_ZU) {
-      k3_lu<2, 1><<<grid3, blk3, sm, st>>>(g, B, 0, x, nullptr, nullptr, rhs, w.r, w.dots, w.dots, a, c);
-      MGA_LAUNCH_CHECK("k3_lu");
+#define MGA_K3_LU_INIT(K) MGA_K3_LAUNCH((k3_lu<2, 1, K>), g.smem3_u, g, B, 0, x, nullptr, nullptr, rhs, w.r, w.dots, w.dots, a, c)
+      MGA_K3_BY_K(g.ku3, MGA_K3_LU_INIT);
     } else {
-      k3_p_ldr<2><<<grid3, blk3, sm, st>>>(g, B, 0, x, nullptr, nullptr, w.qs, w.dots);
-      MGA_LAUNCH_CHECK("k3_p_ldr");
-      k3_ldrt_lhs<1><<<grid3, blk3, sm, st>>>(g, x, w.qs, rhs, w.r, w.dots, a, c, xsys);
-      MGA_LAUNCH_CHECK("k3_ldrt_lhs");
+#define MGA_K3_PLDR_INIT(K) MGA_K3_LAUNCH((k3_p_ldr<2, K>), g.smem3_d, g, B, 0, x, nullptr, nullptr, w.qs, w.dots)
+      MGA_K3_BY_K(g.kd3, MGA_K3_PLDR_INIT);
+      MGA_K3_LAUNCH((k3_ldrt_lhs<1>), g.smem3_in, g, B, x, w.qs, rhs, w.r, w.dots, a, c, xsys);
     }
     for (int it = 0; it < n_cg; ++it) {
       double* pap = w.dots + (size_t)(2 * it + 1) * B;
       if (system == MGA_SYS_ZU) {
-        if (it == 0) k3_lu<1, 0><<<grid3, blk3, sm, st>>>(g, B, it, w.r, p_old, p_new, nullptr, w.ap, w.dots, pap, a, c);
-        else k3_lu<0, 0><<<grid3, blk3, sm, st>>>(g, B, it, w.r, p_old, p_new, nullptr, w.ap, w.dots, pap, a, c);
-        MGA_LAUNCH_CHECK("k3_lu");
+#define MGA_K3_LU_FIRST(K) MGA_K3_LAUNCH((k3_lu<1, 0, K>), g.smem3_u, g, B, it, w.r, p_old, p_new, nullptr, w.ap, w.dots, pap, a, c)
+#define MGA_K3_LU_NEXT(K) MGA_K3_LAUNCH((k3_lu<0, 0, K>), g.smem3_u, g, B, it, w.r, p_old, p_new, nullptr, w.ap, w.dots, pap, a, c)
+        if (it == 0) MGA_K3_BY_K(g.ku3, MGA_K3_LU_FIRST);
+        else MGA_K3_BY_K(g.ku3, MGA_K3_LU_NEXT);
       } else {
-        if (it == 0) k3_p_ldr<1><<<grid3, blk3, sm, st>>>(g, B, it, w.r, p_old, p_new, w.qs, w.dots);
-        else k3_p_ldr<0><<<grid3, blk3, sm, st>>>(g, B, it, w.r, p_old, p_new, w.qs, w.dots);
-        MGA_LAUNCH_CHECK("k3_p_ldr");
-        k3_ldrt_lhs<0><<<grid3, blk3, sm, st>>>(g, p_new, w.qs, nullptr, w.ap, pap, a, c, xsys);
-        MGA_LAUNCH_CHECK("k3_ldrt_lhs");
+#define MGA_K3_PLDR_FIRST(K) MGA_K3_LAUNCH((k3_p_ldr<1, K>), g.smem3_d, g, B, it, w.r, p_old, p_new, w.qs, w.dots)
+#define MGA_K3_PLDR_NEXT(K) MGA_K3_LAUNCH((k3_p_ldr<0, K>), g.smem3_d, g, B, it, w.r, p_old, p_new, w.qs, w.dots)
+        if (it == 0) MGA_K3_BY_K(g.kd3, MGA_K3_PLDR_FIRST);
+        else MGA_K3_BY_K(g.kd3, MGA_K3_PLDR_NEXT);
+        MGA_K3_LAUNCH((k3_ldrt_lhs<0>), g.smem3_in, g, B, p_new, w.qs, nullptr, w.ap, pap, a, c, xsys);
       }
       k2_xr<<<fgrid, kFlat, 0, st>>>(g, B, it, x, w.r, p_new, w.ap, w.dots);
       MGA_LAUNCH_CHECK("k2_xr");
