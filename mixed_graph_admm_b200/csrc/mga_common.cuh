@@ -62,6 +62,7 @@ struct Graph2 {
   int smem3_d, smem3_u, smem3_in;
   const int2* tab_d; const int2* tab_u; const int2* tab_in3;
   const int* in_ptr3;
+  const int* ord3;         // (N) row order of k3_ldrt_lhs: descending in-list length
   const float* wself_d;    // (N)
 };
 

@@ -355,6 +355,17 @@ int mga_plan_create(const mga_graph_desc* d, int device, mga_plan** out) {
           ip3[k + 1] = (int)ti.size() / 2;
         }
       }
+      // rows of k3_ldrt_lhs in descending in-list length: the 4-16 nodes a warp walks together have similar
+      // lengths (the in-degree of a kNN graph is far from uniform: hubs), so the gather loop is not padded to
+      // the longest list of an arbitrary group
+      std::vector<int> ord(N);
+      for (int k = 0; k < N; ++k) ord[k] = k;
+      // (rows of < 64 B stay in natural order: scattering them costs more DRAM sectors than the balance saves -
+      // measured T = 12: 56.6 vs 55.6 ms per step; T = 288: 38.4 vs 39.9)
+      const char* es = std::getenv("MGA_S3_SORT");
+      if (es ? std::atoi(es) != 0 : g2.CB3 >= 4)
+        std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) { return ip3[x + 1] - ip3[x] > ip3[y + 1] - ip3[y]; });
+      if ((rc = upload(p, ord, &g2.ord3))) return fail(rc);
       g2.in_self3 = self_ok ? 1 : 0;
       g2.in_ptr3_total = (int)ti.size() / 2;
       const int* dev_tab = nullptr;
@@ -367,10 +378,10 @@ int mga_plan_create(const mga_graph_desc* d, int device, mga_plan** out) {
       if ((rc = upload(p, ip3, &g2.in_ptr3))) return fail(rc);
       if ((rc = upload(p, wsd, &g2.wself_d))) return fail(rc);
       // dynamic shared memory of the three kernels: tile + halo + wself (+ in-list offsets) + table
-      const size_t tile_b = (size_t)N * ((size_t)row_bytes + 8);
+      const size_t tile_b = (size_t)N * (2 * (size_t)row_bytes + 12) + 4;      // two tile buffers, two halos, wself
       g2.smem3_d = (int)(tile_b + (size_t)N * g2.kd3 * 8);
       g2.smem3_u = (int)(tile_b + (size_t)N * g2.ku3 * 8);
-      g2.smem3_in = (int)(tile_b + (size_t)((N + 2) & ~1) * 4 + (size_t)g2.in_ptr3_total * 8);
+      g2.smem3_in = (int)(tile_b + (size_t)((N + 2) & ~1) * 4 + (size_t)((N + 1) & ~1) * 4 + (size_t)g2.in_ptr3_total * 8);
       if (std::max(g2.smem3_d, std::max(g2.smem3_u, g2.smem3_in)) > p->max_smem_optin - 1024) g2.CB3 = 0;
       if (std::getenv("MGA_S3_VERBOSE"))
         std::fprintf(stderr, "[mga] time-tiled kernels: N=%d C4=%d CB3=%d NB3t=%d tiles3=%d kd3=%d ku3=%d in=%d self=%d smem d/u/in=%d/%d/%d\n",

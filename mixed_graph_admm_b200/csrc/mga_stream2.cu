@@ -373,24 +373,40 @@ __global__ void __launch_bounds__(kFlat) k2_xr(Graph2 g, int64_t B, int it, floa
 // neighbour's row in the tile, weight) - entry -> LDS.64, gather -> LDS.128 at [thread base + offset], no integer
 // math in between -, the self link leaves the tables (the owner holds the value), rows are unrolled over the
 // table width, and all per-thread predicates / pointers are hoisted out of the row loop.
-constexpr int kU3 = 4;   // node rows whose loads are issued together in phase 1
 
 struct Smem3 {
-  float4* tile;    // (N, CB) chunks
+  float4* tile;    // (N, CB) chunks: the gathered vector
+  float4* tile2;   // (N, CB) chunks: second operand of the tile (p of p' = r + beta p; the vector A is applied to)
   float* halo;     // (N)
+  float* halo2;    // (N)
   float* wself;    // (N)
   int* ptr;        // (N + 1) in-list offsets (k3_ldrt_lhs only)
+  int* ord;        // (N) row order (k3_ldrt_lhs only)
   int2* tab;       // entries
 };
 __device__ __forceinline__ Smem3 carve3(const Graph2& g, float4* base, int CB, bool with_ptr) {
   Smem3 s;
   s.tile = base;
-  s.halo = reinterpret_cast<float*>(base + g.N * CB);
-  s.wself = s.halo + g.N;
-  s.ptr = reinterpret_cast<int*>(s.wself + g.N);
-  const int np = with_ptr ? ((g.N + 2) & ~1) : 0;      // keeps the entries 8-byte aligned
-  s.tab = reinterpret_cast<int2*>(s.ptr + np);
+  s.tile2 = base + g.N * CB;
+  s.halo = reinterpret_cast<float*>(base + 2 * g.N * CB);
+  s.halo2 = s.halo + g.N;
+  s.wself = s.halo2 + g.N;
+  s.ptr = reinterpret_cast<int*>(s.wself + g.N + (g.N & 1));      // keeps the entries 8-byte aligned
+  const int np = with_ptr ? ((g.N + 2) & ~1) : 0;
+  s.ord = s.ptr + np;
+  s.tab = reinterpret_cast<int2*>(s.ord + (with_ptr ? ((g.N + 1) & ~1) : 0));
   return s;
+}
+
+// asynchronous global -> shared copies (LDGSTS): the whole tile is in flight at once and costs no registers
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
 }
 
 // While a tile is being gathered, the lines of the CTA's NEXT tile are pulled into L2 (prefetch.global.L2 needs no
@@ -421,47 +437,46 @@ __device__ __forceinline__ void tile_prefetch(const Graph2& g, int tl, int total
 }
 
 // SRC 0: v = r + beta p   SRC 1: v = r (first iteration)   SRC 2: v = r (no store: r is x0 of the initial residual)
+// ncu on the register-staged version: every dependent round of global loads costs the loaded HBM latency (~2 us);
+// a tile took 3 such rounds.  Here ALL chunks of the tile (and the halo scalars) are issued as cp.async before
+// anything waits: one round per tile.  Each thread then finishes its OWN chunks (p' = r + beta p in place, streamed
+// to HBM), so no barrier is needed between the copy and that pass.
 template <int SRC>
 __device__ __forceinline__ void tile_fill(const Graph2& g, int64_t B, int it, int b, int c0, const float* __restrict__ r,
                                           const float* __restrict__ p_old, float* __restrict__ p_new,
-                                          const double* __restrict__ dots, float4* tile, float* halo, bool want_halo) {
+                                          const double* __restrict__ dots, const Smem3& s, bool want_halo) {
   const int CB = blockDim.x, NBt = blockDim.y, tx = threadIdx.x;
   const int c = c0 + tx, cn = c0 + CB;
   const bool cok = c < g.C4, last = want_halo && tx == CB - 1, hok = cn < g.C4;
   const size_t w0 = (size_t)b * (size_t)(g.N * g.C4);
-  const float4* rw = reinterpret_cast<const float4*>(r) + w0;
-  const float4* pw = reinterpret_cast<const float4*>(p_old) + w0;
-  float4* ow = reinterpret_cast<float4*>(p_new) + w0;
-  float beta = 0.f;
-  if (SRC == 0) beta = (float)dots[(size_t)(2 * it) * B + b] / (float)dots[(size_t)(2 * it - 2) * B + b];   // ADMM.py:356
-  const int step = NBt * g.C4;
-  int i0 = threadIdx.y * g.C4 + (cok ? c : 0);
-  for (int n0 = threadIdx.y; n0 < g.N; n0 += kU3 * NBt, i0 += kU3 * step) {
-    float4 a[kU3], q[kU3];
-    float ha[kU3], hq[kU3];
-#pragma unroll
-    for (int u = 0; u < kU3; ++u) {
-      const bool in = n0 + u * NBt < g.N;
-      const int i = in ? i0 + u * step : 0;
-      a[u] = __ldcs(rw + i);
-      if (SRC == 0) q[u] = __ldcs(pw + i);
-      if (last) {
-        const int hi = (in && hok) ? (i + 1) * 4 : 0;      // first element of the next tile's first chunk
-        ha[u] = __ldcs(reinterpret_cast<const float*>(rw) + hi);
-        if (SRC == 0) hq[u] = __ldcs(reinterpret_cast<const float*>(pw) + hi);
+  const float4* rw = reinterpret_cast<const float4*>(r) + w0 + (cok ? c : 0);
+  const float4* pw = reinterpret_cast<const float4*>(p_old) + w0 + (cok ? c : 0);
+  float4* ow = reinterpret_cast<float4*>(p_new) + w0 + (cok ? c : 0);
+  if (cok) {
+    for (int n = threadIdx.y; n < g.N; n += NBt) {
+      cp_async16(s.tile + n * CB + tx, rw + n * g.C4);
+      if (SRC == 0) cp_async16(s.tile2 + n * CB + tx, pw + n * g.C4);
+      if (last && hok) {          // first element of the next tile's first chunk
+        cp_async4(s.halo + n, reinterpret_cast<const float*>(rw + n * g.C4 + 1));
+        if (SRC == 0) cp_async4(s.halo2 + n, reinterpret_cast<const float*>(pw + n * g.C4 + 1));
       }
     }
-#pragma unroll
-    for (int u = 0; u < kU3; ++u) {
-      const int n = n0 + u * NBt;
-      if (n >= g.N) break;
-      float4 v = a[u];
-      if (SRC == 0) v = make_float4(a[u].x + beta * q[u].x, a[u].y + beta * q[u].y, a[u].z + beta * q[u].z, a[u].w + beta * q[u].w);
-      if (!cok) v = make_float4(0.f, 0.f, 0.f, 0.f);
-      tile[n * CB + tx] = v;
-      if (SRC != 2 && cok) __stcs(ow + i0 + u * step, v);
-      if (last) halo[n] = hok ? (SRC == 0 ? ha[u] + beta * hq[u] : ha[u]) : 0.f;
+  }
+  float beta = 0.f;
+  if (SRC == 0) beta = (float)dots[(size_t)(2 * it) * B + b] / (float)dots[(size_t)(2 * it - 2) * B + b];   // ADMM.py:356
+  cp_async_wait_all();
+  for (int n = threadIdx.y; n < g.N; n += NBt) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (cok) {
+      v = s.tile[n * CB + tx];
+      if (SRC == 0) {
+        const float4 q = s.tile2[n * CB + tx];
+        v = make_float4(v.x + beta * q.x, v.y + beta * q.y, v.z + beta * q.z, v.w + beta * q.w);
+      }
+      if (SRC != 2) __stcs(ow + n * g.C4, v);
     }
+    if (SRC == 0 || !cok) s.tile[n * CB + tx] = v;
+    if (last) s.halo[n] = hok ? (SRC == 0 ? s.halo[n] + beta * s.halo2[n] : s.halo[n]) : 0.f;
   }
 }
 
@@ -501,7 +516,7 @@ __device__ __forceinline__ void stage_table(const int2* __restrict__ src, int n_
 
 // (r, p) -> p', qs = shifted L_d p'   [SRC 2: x0 -> qs]
 template <int SRC, int K>
-__global__ void __launch_bounds__(256, 4) k3_p_ldr(Graph2 g, int64_t B, int it, const float* __restrict__ r,
+__global__ void __launch_bounds__(512, 2) k3_p_ldr(Graph2 g, int64_t B, int it, const float* __restrict__ r,
                                                    const float* __restrict__ p_old, float* __restrict__ p_new,
                                                    float* __restrict__ qs, const double* __restrict__ dots) {
   extern __shared__ float4 s3[];
@@ -517,7 +532,7 @@ __global__ void __launch_bounds__(256, 4) k3_p_ldr(Graph2 g, int64_t B, int it, 
   for (int tl = blockIdx.x; tl < total; tl += gridDim.x) {
     const int b = tl / g.tiles3, c0 = (tl - b * g.tiles3) * CB, c = c0 + tx;
     if (tl != (int)blockIdx.x) __syncthreads();          // the previous tile's gathers are done
-    tile_fill<SRC>(g, B, it, b, c0, r, p_old, p_new, dots, s.tile, s.halo, true);
+    tile_fill<SRC>(g, B, it, b, c0, r, p_old, p_new, dots, s, true);
     __syncthreads();
     tile_prefetch(g, tl + gridDim.x, total, r, SRC == 0 ? p_old : nullptr, nullptr);
     if (c >= g.C4) continue;
@@ -542,7 +557,7 @@ __global__ void __launch_bounds__(256, 4) k3_p_ldr(Graph2 g, int64_t B, int it, 
 
 // (v, qs) -> Ap, <v, Ap>  [MODE 1: r = rhs - A v, <r, r>];  A = diag + c L_d^T L_d; qs tile in shared memory
 template <int MODE>
-__global__ void __launch_bounds__(256, 4) k3_ldrt_lhs(Graph2 g, int64_t B, const float* __restrict__ v,
+__global__ void __launch_bounds__(512, 2) k3_ldrt_lhs(Graph2 g, int64_t B, const float* __restrict__ v,
                                                       const float* __restrict__ qs, const float* __restrict__ rhs,
                                                       float* __restrict__ out, double* __restrict__ slot, float a, float cc,
                                                       int xsys) {
@@ -552,12 +567,12 @@ __global__ void __launch_bounds__(256, 4) k3_ldrt_lhs(Graph2 g, int64_t B, const
   stage_table(g.tab_in3, g.in_ptr3_total, s.tab);
   for (int k = tid2(); k < g.N; k += CB * NBt) s.wself[k] = g.wself_d[k];
   for (int k = tid2(); k <= g.N; k += CB * NBt) s.ptr[k] = g.in_ptr3[k];
+  for (int k = tid2(); k < g.N; k += CB * NBt) s.ord[k] = g.ord3[k];
   const int total = (int)B * g.tiles3;
   const char* mine = reinterpret_cast<const char*>(s.tile + tx);
   // the element before the thread's chunk: q[4c] = qs[4c - 1]
   const float* prv_p = tx > 0 ? reinterpret_cast<const float*>(s.tile + tx) - 1 : s.halo;
   const int prv_stride = tx > 0 ? CB * 4 : 1;
-  const int step = NBt * g.C4;
   const bool self_in = g.in_self3 != 0;
   for (int tl = blockIdx.x; tl < total; tl += gridDim.x) {
     const int b = tl / g.tiles3, c0 = (tl - b * g.tiles3) * CB, c = c0 + tx;
@@ -565,38 +580,31 @@ __global__ void __launch_bounds__(256, 4) k3_ldrt_lhs(Graph2 g, int64_t B, const
     const size_t w0 = (size_t)b * (size_t)(g.N * g.C4);
     const float4* qw = reinterpret_cast<const float4*>(qs) + w0;
     if (tl != (int)blockIdx.x) __syncthreads();
-    int i0 = threadIdx.y * g.C4 + (cok ? c : 0);
-    for (int n0 = threadIdx.y; n0 < g.N; n0 += kU3 * NBt, i0 += kU3 * step) {
-      float4 q[kU3];
-      float h[kU3];
-#pragma unroll
-      for (int u = 0; u < kU3; ++u) {
-        const bool in = n0 + u * NBt < g.N;
-        const int i = in ? i0 + u * step : 0;
-        q[u] = __ldcs(qw + i);
-        if (tx == 0) h[u] = (in && c0 > 0) ? __ldcs(reinterpret_cast<const float*>(qw) + i * 4 - 1) : 0.f;   // q[0] = 0 (ADMM.py:176)
+    const float4* vw = reinterpret_cast<const float4*>(v) + w0 + (cok ? c : 0);
+    for (int n = threadIdx.y; n < g.N; n += NBt) {
+      if (cok) {
+        cp_async16(s.tile + n * CB + tx, qw + c + n * g.C4);
+        cp_async16(s.tile2 + n * CB + tx, vw + n * g.C4);
+        if (tx == 0 && c0 > 0) cp_async4(s.halo + n, reinterpret_cast<const float*>(qw + c + n * g.C4) - 1);   // q[4 c0] = qs[4 c0 - 1]
+      } else {
+        s.tile[n * CB + tx] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
-#pragma unroll
-      for (int u = 0; u < kU3; ++u) {
-        const int n = n0 + u * NBt;
-        if (n >= g.N) break;
-        s.tile[n * CB + tx] = cok ? q[u] : make_float4(0.f, 0.f, 0.f, 0.f);
-        if (tx == 0) s.halo[n] = h[u];
-      }
+      if (tx == 0 && c0 == 0) s.halo[n] = 0.f;                                                        // q[0] = 0 (ADMM.py:176)
     }
+    cp_async_wait_all();
     __syncthreads();
-    tile_prefetch(g, tl + gridDim.x, total, qs, nullptr, nullptr);
+    tile_prefetch(g, tl + gridDim.x, total, qs, v, nullptr);
     float dot = 0.f;
     if (cok) {
       const int t0 = 4 * c;
-      const float4* vw = reinterpret_cast<const float4*>(v) + w0 + c;
       const float4* rw = reinterpret_cast<const float4*>(rhs) + w0 + c;
       float4* ow = reinterpret_cast<float4*>(out) + w0 + c;
       float hx[4], tv[4];      // H^T H keeps rows t < t_in (ADMM.py:372-374); pads (t >= T) stay 0
 #pragma unroll
       for (int j = 0; j < 4; ++j) { hx[j] = (xsys && t0 + j < g.t_in) ? 1.f : 0.f; tv[j] = t0 + j < g.T ? 1.f : 0.f; }
-      for (int n = threadIdx.y; n < g.N; n += NBt) {
-        const float4 pv = __ldcs(vw + n * g.C4);
+      for (int k = threadIdx.y; k < g.N; k += NBt) {
+        const int n = s.ord[k];
+        const float4 pv = s.tile2[n * CB + tx];
         float4 rh;
         if (MODE == 1) rh = __ldcs(rw + n * g.C4);
         const float4 q1 = s.tile[n * CB + tx];
@@ -635,7 +643,7 @@ __global__ void __launch_bounds__(256, 4) k3_ldrt_lhs(Graph2 g, int64_t B, const
 
 // z_u system: (r, p) -> p', Ap = (c L_u + a I) p', <p', Ap>   [SRC 2 / MODE 1: r = rhs - A x0, <r, r>]
 template <int SRC, int MODE, int K>
-__global__ void __launch_bounds__(256, 4) k3_lu(Graph2 g, int64_t B, int it, const float* __restrict__ r,
+__global__ void __launch_bounds__(512, 2) k3_lu(Graph2 g, int64_t B, int it, const float* __restrict__ r,
                                                 const float* __restrict__ p_old, float* __restrict__ p_new,
                                                 const float* __restrict__ rhs, float* __restrict__ out,
                                                 const double* __restrict__ dots, double* __restrict__ slot, float a, float cc) {
@@ -648,7 +656,7 @@ __global__ void __launch_bounds__(256, 4) k3_lu(Graph2 g, int64_t B, int it, con
   for (int tl = blockIdx.x; tl < total; tl += gridDim.x) {
     const int b = tl / g.tiles3, c0 = (tl - b * g.tiles3) * CB, c = c0 + tx;
     if (tl != (int)blockIdx.x) __syncthreads();
-    tile_fill<SRC>(g, B, it, b, c0, r, p_old, p_new, dots, s.tile, s.halo, false);
+    tile_fill<SRC>(g, B, it, b, c0, r, p_old, p_new, dots, s, false);
     __syncthreads();
     tile_prefetch(g, tl + gridDim.x, total, r, SRC == 0 ? p_old : nullptr, MODE == 1 ? rhs : nullptr);
     float dot = 0.f;
@@ -883,21 +891,25 @@ void stream2_tiling(Graph2* g) {
   g->NB = (g->N + g->tilesN - 1) / g->tilesN;           // balanced node tiles, NB <= NBt (extra rows are masked off)
   g->tilesC = (g->C4 + g->CB - 1) / g->CB;
   // time-tiled shared-memory kernels (k3_*): all nodes x CB3 chunks + halo + self weights + the graph table per CTA;
-  // the largest tile that leaves 4 CTAs per SM, else the largest that leaves 2
   g->CB3 = 0;
   int force = 0;
   if (const char* e = std::getenv("MGA_S3_CB")) force = std::atoi(e);     // 0 = automatic, < 0 = off, > 0 = chunks per tile
   if (force >= 0) {
-    const int cands[5] = {force > 0 ? std::min(force, g->C4) : std::min(g->C4, 8), 4, 2, 1, 0};
-    const size_t table = (size_t)g->N * std::max(g->kd, g->ku) * 8 + (size_t)(g->N + 2) * 4;
-    const size_t limits[2] = {(228 * 1024) / 4 - 1024, (228 * 1024) / 2 - 1024};
-    for (int l = 0; l < 2 && g->CB3 == 0; ++l)
-      for (int k = 0; cands[k] > 0 && g->CB3 == 0; ++k)
-        if (cands[k] <= g->C4 && (size_t)g->N * ((size_t)cands[k] * 16 + 8) + table <= limits[l]) g->CB3 = cands[k];
+    // tiles of >= 4 chunks (64-byte row segments) or the whole row, and only if 2 CTAs fit an SM: PEMS-sized graphs
+    // (N <= ~360 with 8-chunk tiles, <= ~590 with 4-chunk tiles); larger graphs stay on the k2 kernels
+    const int cands[3] = {force > 0 ? std::min(force, g->C4) : std::min(g->C4, 8), std::min(g->C4, 4), 0};
+    const size_t table = (size_t)g->N * std::max(g->kd, g->ku) * 8 + (size_t)(g->N + 2) * 8;
+    const size_t limit = (228 * 1024) / 2 - 1024;
+    for (int k = 0; cands[k] > 0 && g->CB3 == 0; ++k)
+      if ((size_t)g->N * (2 * (size_t)cands[k] * 16 + 12) + 8 + table <= limit) g->CB3 = cands[k];
   }
   if (g->CB3 > 0) {
     const int cb = g->CB3;
-    g->NB3t = (cb & (cb - 1)) == 0 ? 256 / cb : 32 * std::max(1, 8 / cb);     // cb * NB3t whole warps, <= 256 threads
+    // measured on B200 (PEMS04 graph): 512 threads (2 CTAs/SM) win for tiles of >= 4 chunks (T = 24: 52.3 vs 54.6 ms per
+    // step, T = 288: 37.9 vs 38.4), 256 threads for the 3-chunk tile of T = 12 (55.3 vs 60.3)
+    int threads = cb >= 4 ? 512 : 256;
+    if (const char* e = std::getenv("MGA_S3_THREADS")) threads = std::atoi(e) >= 512 ? 512 : 256;
+    g->NB3t = (cb & (cb - 1)) == 0 ? threads / cb : 32 * std::max(1, (threads / 32) / cb);     // cb * NB3t whole warps
     g->tiles3 = (g->C4 + cb - 1) / cb;
   }
 }
@@ -928,7 +940,8 @@ static int k3_ctas_per_sm(const void* kern, int threads, size_t smem, int* rc) {
   if (it != cache.end()) return it->second;
   // the opt-in limit only ever grows: lowering it would break the cached larger configurations
   static std::map<std::pair<const void*, int>, size_t> limit;
-  size_t& lim = limit.emplace(std::make_pair(kern, dev), (size_t)48 * 1024).first->second;
+  // (default limit: 48 KB minus the kernel's static shared memory - start below it)
+  size_t& lim = limit.emplace(std::make_pair(kern, dev), (size_t)40 * 1024).first->second;
   cudaError_t e = cudaSuccess;
   if (smem > lim) {
     e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

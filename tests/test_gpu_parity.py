@@ -459,10 +459,13 @@ def test_skip_connection_line_graph_against_oracle(N, k, T, skip, B, mode):
     np.testing.assert_allclose(blk.p_res_list[-1], tr.p_res[-1], rtol=2e-5, atol=1e-7)
 
 
-@pytest.mark.parametrize("N,k,T,B", [(100, 4, 50, 3), (307, 6, 100, 2), (400, 6, 37, 2), (64, 3, 26, 5)])
+@pytest.mark.parametrize("N,k,T,B", [(100, 4, 50, 3), (307, 6, 100, 2), (400, 6, 37, 2), (64, 3, 26, 5), (500, 6, 41, 2),
+                                     (700, 5, 30, 2)])
 def test_long_windows_odd_lengths_against_oracle(N, k, T, B):
     """T > 24 (beyond the resident kernel) with lengths that are not multiples of 4 or 12: the chunked streaming
-    kernels' padded last chunk and the general kernels, both against the oracle."""
+    kernels' padded last chunk and the general kernels, both against the oracle.  N <= 360: time-tiled shared-memory
+    kernels with 8-chunk tiles (a padded last tile at T = 37, 50, 100), N = 400 / 500: 4-chunk tiles, N = 700: the
+    graph no longer fits two CTAs per SM and the L1-gather kernels run."""
     from mixed_graph_admm_b200 import synth
     from mixed_graph_admm_b200.ADMM import ADMM_algorithm
     from oracle import admm_oracle as O
