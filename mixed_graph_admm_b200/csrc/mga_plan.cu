@@ -378,14 +378,15 @@ int mga_plan_create(const mga_graph_desc* d, int device, mga_plan** out) {
       if ((rc = upload(p, ip3, &g2.in_ptr3))) return fail(rc);
       if ((rc = upload(p, wsd, &g2.wself_d))) return fail(rc);
       // dynamic shared memory of the three kernels: tile + halo + wself (+ in-list offsets) + table
-      const size_t tile_b = (size_t)N * (2 * (size_t)row_bytes + 12) + 4;      // two tile buffers, two halos, wself
+      const int nb3 = g2.db3 ? 2 : 1;      // tile / tile2 / halo per buffer, halo2, wself
+      const size_t tile_b = (size_t)N * (2 * nb3 * (size_t)row_bytes + (nb3 + 2) * 4) + 4;
       g2.smem3_d = (int)(tile_b + (size_t)N * g2.kd3 * 8);
       g2.smem3_u = (int)(tile_b + (size_t)N * g2.ku3 * 8);
       g2.smem3_in = (int)(tile_b + (size_t)((N + 2) & ~1) * 4 + (size_t)((N + 1) & ~1) * 4 + (size_t)g2.in_ptr3_total * 8);
       if (std::max(g2.smem3_d, std::max(g2.smem3_u, g2.smem3_in)) > p->max_smem_optin - 1024) g2.CB3 = 0;
       if (std::getenv("MGA_S3_VERBOSE"))
-        std::fprintf(stderr, "[mga] time-tiled kernels: N=%d C4=%d CB3=%d NB3t=%d tiles3=%d kd3=%d ku3=%d in=%d self=%d smem d/u/in=%d/%d/%d\n",
-                     N, g2.C4, g2.CB3, g2.NB3t, g2.tiles3, g2.kd3, g2.ku3, g2.in_ptr3_total, g2.in_self3, g2.smem3_d, g2.smem3_u,
+        std::fprintf(stderr, "[mga] time-tiled kernels: N=%d C4=%d db=%d CB3=%d NB3t=%d tiles3=%d kd3=%d ku3=%d in=%d self=%d smem d/u/in=%d/%d/%d\n",
+                     N, g2.C4, g2.db3, g2.CB3, g2.NB3t, g2.tiles3, g2.kd3, g2.ku3, g2.in_ptr3_total, g2.in_self3, g2.smem3_d, g2.smem3_u,
                      g2.smem3_in);
     }
     if ((rc = upload(p, perm, &g2.perm))) return fail(rc);

@@ -375,23 +375,28 @@ __global__ void __launch_bounds__(kFlat) k2_xr(Graph2 g, int64_t B, int it, floa
 // table width, and all per-thread predicates / pointers are hoisted out of the row loop.
 
 struct Smem3 {
-  float4* tile;    // (N, CB) chunks: the gathered vector
-  float4* tile2;   // (N, CB) chunks: second operand of the tile (p of p' = r + beta p; the vector A is applied to)
-  float* halo;     // (N)
+  float4* tile;    // (nb, N, CB) chunks: the gathered vector
+  float4* tile2;   // (nb, N, CB) chunks: second operand of the tile (p of p' = r + beta p; the vector A is applied to)
+  float* halo;     // (nb, N)
   float* halo2;    // (N)
   float* wself;    // (N)
   int* ptr;        // (N + 1) in-list offsets (k3_ldrt_lhs only)
   int* ord;        // (N) row order (k3_ldrt_lhs only)
   int2* tab;       // entries
+  int stride_t;    // float4 between the two tile buffers of the double-buffered mode (0: single buffer)
+  int stride_h;
 };
 __device__ __forceinline__ Smem3 carve3(const Graph2& g, float4* base, int CB, bool with_ptr) {
   Smem3 s;
+  const int nb = g.db3 ? 2 : 1;
+  s.stride_t = g.db3 ? g.N * CB : 0;
+  s.stride_h = g.db3 ? g.N : 0;
   s.tile = base;
-  s.tile2 = base + g.N * CB;
-  s.halo = reinterpret_cast<float*>(base + 2 * g.N * CB);
-  s.halo2 = s.halo + g.N;
+  s.tile2 = base + nb * g.N * CB;
+  s.halo = reinterpret_cast<float*>(base + 2 * nb * g.N * CB);
+  s.halo2 = s.halo + nb * g.N;
   s.wself = s.halo2 + g.N;
-  s.ptr = reinterpret_cast<int*>(s.wself + g.N + (g.N & 1));      // keeps the entries 8-byte aligned
+  s.ptr = reinterpret_cast<int*>(s.wself + g.N + ((nb * g.N) & 1));      // keeps the entries 8-byte aligned
   const int np = with_ptr ? ((g.N + 2) & ~1) : 0;
   s.ord = s.ptr + np;
   s.tab = reinterpret_cast<int2*>(s.ord + (with_ptr ? ((g.N + 1) & ~1) : 0));
@@ -405,78 +410,68 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
 __device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((unsigned)__cvta_generic_to_shared(smem)), "l"(gmem));
 }
-__device__ __forceinline__ void cp_async_wait_all() {
-  asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
-}
-
-// While a tile is being gathered, the lines of the CTA's NEXT tile are pulled into L2 (prefetch.global.L2 needs no
-// registers): the two-phase structure leaves no loads in flight during phase 2 otherwise.
-#ifndef MGA_S3_PREFETCH
-#define MGA_S3_PREFETCH 1
-#endif
-__device__ __forceinline__ void prefetch_l2(const void* p) {
-#if MGA_S3_PREFETCH
-  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-#endif
-}
-// one prefetch per 16-byte chunk of the thread's column of tile `tl` in up to three vectors
-__device__ __forceinline__ void tile_prefetch(const Graph2& g, int tl, int total, const float* v0, const float* v1, const float* v2) {
-#if MGA_S3_PREFETCH
-  if (tl >= total) return;
-  const int CB = blockDim.x, NBt = blockDim.y;
-  const int b = tl / g.tiles3, c = (tl - b * g.tiles3) * CB + threadIdx.x;
-  if (c >= g.C4) return;
-  const size_t w0 = (size_t)b * (size_t)(g.N * g.C4) + c;
-  for (int n = threadIdx.y; n < g.N; n += NBt) {
-    const size_t k = w0 + (size_t)(n * g.C4);
-    if (v0) prefetch_l2(reinterpret_cast<const float4*>(v0) + k);
-    if (v1) prefetch_l2(reinterpret_cast<const float4*>(v1) + k);
-    if (v2) prefetch_l2(reinterpret_cast<const float4*>(v2) + k);
-  }
-#endif
-}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // SRC 0: v = r + beta p   SRC 1: v = r (first iteration)   SRC 2: v = r (no store: r is x0 of the initial residual)
 // ncu on the register-staged version: every dependent round of global loads costs the loaded HBM latency (~2 us);
 // a tile took 3 such rounds.  Here ALL chunks of the tile (and the halo scalars) are issued as cp.async before
 // anything waits: one round per tile.  Each thread then finishes its OWN chunks (p' = r + beta p in place, streamed
 // to HBM), so no barrier is needed between the copy and that pass.
+// Double-buffered mode (g.db3, one CTA per SM): the copies of the CTA's NEXT tile are issued before the gathers of
+// the current one, so the HBM stream never stops; single-buffered mode (two CTAs per SM): issue, wait, gather.
 template <int SRC>
-__device__ __forceinline__ void tile_fill(const Graph2& g, int64_t B, int it, int b, int c0, const float* __restrict__ r,
-                                          const float* __restrict__ p_old, float* __restrict__ p_new,
-                                          const double* __restrict__ dots, const Smem3& s, bool want_halo) {
+__device__ __forceinline__ void tile_issue(const Graph2& g, int tl, int cur, const float* __restrict__ r,
+                                           const float* __restrict__ p_old, const Smem3& s, bool want_halo) {
   const int CB = blockDim.x, NBt = blockDim.y, tx = threadIdx.x;
+  const int b = tl / g.tiles3, c0 = (tl - b * g.tiles3) * CB;
   const int c = c0 + tx, cn = c0 + CB;
-  const bool cok = c < g.C4, last = want_halo && tx == CB - 1, hok = cn < g.C4;
-  const size_t w0 = (size_t)b * (size_t)(g.N * g.C4);
-  const float4* rw = reinterpret_cast<const float4*>(r) + w0 + (cok ? c : 0);
-  const float4* pw = reinterpret_cast<const float4*>(p_old) + w0 + (cok ? c : 0);
-  float4* ow = reinterpret_cast<float4*>(p_new) + w0 + (cok ? c : 0);
-  if (cok) {
+  if (c < g.C4) {
+    const bool last = want_halo && tx == CB - 1 && cn < g.C4;
+    const size_t w0 = (size_t)b * (size_t)(g.N * g.C4) + c;
+    const float4* rw = reinterpret_cast<const float4*>(r) + w0;
+    const float4* pw = reinterpret_cast<const float4*>(p_old) + w0;
+    float4* t1 = s.tile + cur * s.stride_t + tx;
+    float4* t2 = s.tile2 + cur * s.stride_t + tx;
+    float* h1 = s.halo + cur * s.stride_h;
     for (int n = threadIdx.y; n < g.N; n += NBt) {
-      cp_async16(s.tile + n * CB + tx, rw + n * g.C4);
-      if (SRC == 0) cp_async16(s.tile2 + n * CB + tx, pw + n * g.C4);
-      if (last && hok) {          // first element of the next tile's first chunk
-        cp_async4(s.halo + n, reinterpret_cast<const float*>(rw + n * g.C4 + 1));
+      cp_async16(t1 + n * CB, rw + n * g.C4);
+      if (SRC == 0) cp_async16(t2 + n * CB, pw + n * g.C4);
+      if (last) {                 // first element of the next tile's first chunk
+        cp_async4(h1 + n, reinterpret_cast<const float*>(rw + n * g.C4 + 1));
         if (SRC == 0) cp_async4(s.halo2 + n, reinterpret_cast<const float*>(pw + n * g.C4 + 1));
       }
     }
   }
+  cp_async_commit();
+}
+
+template <int SRC>
+__device__ __forceinline__ void tile_finish(const Graph2& g, int64_t B, int it, int tl, int cur, float* __restrict__ p_new,
+                                            const double* __restrict__ dots, const Smem3& s, bool want_halo) {
+  const int CB = blockDim.x, NBt = blockDim.y, tx = threadIdx.x;
+  const int b = tl / g.tiles3, c0 = (tl - b * g.tiles3) * CB;
+  const int c = c0 + tx, cn = c0 + CB;
+  const bool cok = c < g.C4, last = want_halo && tx == CB - 1, hok = cn < g.C4;
+  float4* ow = reinterpret_cast<float4*>(p_new) + (size_t)b * (size_t)(g.N * g.C4) + (cok ? c : 0);
+  float4* t1 = s.tile + cur * s.stride_t + tx;
+  const float4* t2 = s.tile2 + cur * s.stride_t + tx;
+  float* h1 = s.halo + cur * s.stride_h;
   float beta = 0.f;
   if (SRC == 0) beta = (float)dots[(size_t)(2 * it) * B + b] / (float)dots[(size_t)(2 * it - 2) * B + b];   // ADMM.py:356
   cp_async_wait_all();
   for (int n = threadIdx.y; n < g.N; n += NBt) {
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (cok) {
-      v = s.tile[n * CB + tx];
+      v = t1[n * CB];
       if (SRC == 0) {
-        const float4 q = s.tile2[n * CB + tx];
+        const float4 q = t2[n * CB];
         v = make_float4(v.x + beta * q.x, v.y + beta * q.y, v.z + beta * q.z, v.w + beta * q.w);
       }
       if (SRC != 2) __stcs(ow + n * g.C4, v);
     }
-    if (SRC == 0 || !cok) s.tile[n * CB + tx] = v;
-    if (last) s.halo[n] = hok ? (SRC == 0 ? s.halo[n] + beta * s.halo2[n] : s.halo[n]) : 0.f;
+    if (SRC == 0 || !cok) t1[n * CB] = v;
+    if (last) h1[n] = hok ? (SRC == 0 ? h1[n] + beta * s.halo2[n] : h1[n]) : 0.f;
   }
 }
 
@@ -516,7 +511,7 @@ __device__ __forceinline__ void stage_table(const int2* __restrict__ src, int n_
 
 // (r, p) -> p', qs = shifted L_d p'   [SRC 2: x0 -> qs]
 template <int SRC, int K>
-__global__ void __launch_bounds__(512, 2) k3_p_ldr(Graph2 g, int64_t B, int it, const float* __restrict__ r,
+__global__ void __launch_bounds__(1024, 1) k3_p_ldr(Graph2 g, int64_t B, int it, const float* __restrict__ r,
                                                    const float* __restrict__ p_old, float* __restrict__ p_new,
                                                    float* __restrict__ qs, const double* __restrict__ dots) {
   extern __shared__ float4 s3[];
@@ -525,22 +520,29 @@ __global__ void __launch_bounds__(512, 2) k3_p_ldr(Graph2 g, int64_t B, int it, 
   stage_table(g.tab_d, g.N * g.kd3, s.tab);
   for (int k = tid2(); k < g.N; k += CB * NBt) s.wself[k] = g.wself_d[k];
   const int total = (int)B * g.tiles3;
-  const char* mine = reinterpret_cast<const char*>(s.tile + tx);
-  // the element after the thread's chunk: next chunk of the row, or the halo scalar for the tile's last chunk
-  const float* nxt_p = tx + 1 < CB ? reinterpret_cast<const float*>(s.tile + tx + 1) : s.halo;
-  const int nxt_stride = tx + 1 < CB ? CB * 4 : 1;
-  for (int tl = blockIdx.x; tl < total; tl += gridDim.x) {
+  const bool db = g.db3 != 0;
+  int cur = 0;
+  if (db && (int)blockIdx.x < total) tile_issue<SRC>(g, blockIdx.x, 0, r, p_old, s, true);
+  for (int tl = blockIdx.x; tl < total; tl += gridDim.x, cur ^= (db ? 1 : 0)) {
     const int b = tl / g.tiles3, c0 = (tl - b * g.tiles3) * CB, c = c0 + tx;
-    if (tl != (int)blockIdx.x) __syncthreads();          // the previous tile's gathers are done
-    tile_fill<SRC>(g, B, it, b, c0, r, p_old, p_new, dots, s, true);
+    if (!db) {
+      if (tl != (int)blockIdx.x) __syncthreads();          // the previous tile's gathers are done
+      tile_issue<SRC>(g, tl, 0, r, p_old, s, true);
+    }
+    tile_finish<SRC>(g, B, it, tl, cur, p_new, dots, s, true);
     __syncthreads();
-    tile_prefetch(g, tl + gridDim.x, total, r, SRC == 0 ? p_old : nullptr, nullptr);
+    if (db && tl + (int)gridDim.x < total) tile_issue<SRC>(g, tl + gridDim.x, cur ^ 1, r, p_old, s, true);
     if (c >= g.C4) continue;
+    const float4* tile = s.tile + cur * s.stride_t;
+    const char* mine = reinterpret_cast<const char*>(tile + tx);
+    // the element after the thread's chunk: next chunk of the row, or the halo scalar for the tile's last chunk
+    const float* nxt_p = tx + 1 < CB ? reinterpret_cast<const float*>(tile + tx + 1) : s.halo + cur * s.stride_h;
+    const int nxt_stride = tx + 1 < CB ? CB * 4 : 1;
     float4* qw = reinterpret_cast<float4*>(qs) + (size_t)b * (size_t)(g.N * g.C4) + c;
     const int t = 4 * c;
     const bool v1 = t + 1 < g.T, v2 = t + 2 < g.T, v3 = t + 3 < g.T, v4 = t + 4 < g.T;
     for (int n = threadIdx.y; n < g.N; n += NBt) {
-      const float4 own = s.tile[n * CB + tx];
+      const float4 own = tile[n * CB + tx];
       const float nxt = nxt_p[n * nxt_stride];
       const float ws = s.wself[n];
       const float4 acc = gather3<K>(s.tab + n * g.kd3, g.kd3, mine,
@@ -557,7 +559,7 @@ __global__ void __launch_bounds__(512, 2) k3_p_ldr(Graph2 g, int64_t B, int it, 
 
 // (v, qs) -> Ap, <v, Ap>  [MODE 1: r = rhs - A v, <r, r>];  A = diag + c L_d^T L_d; qs tile in shared memory
 template <int MODE>
-__global__ void __launch_bounds__(512, 2) k3_ldrt_lhs(Graph2 g, int64_t B, const float* __restrict__ v,
+__global__ void __launch_bounds__(1024, 1) k3_ldrt_lhs(Graph2 g, int64_t B, const float* __restrict__ v,
                                                       const float* __restrict__ qs, const float* __restrict__ rhs,
                                                       float* __restrict__ out, double* __restrict__ slot, float a, float cc,
                                                       int xsys) {
@@ -569,31 +571,49 @@ __global__ void __launch_bounds__(512, 2) k3_ldrt_lhs(Graph2 g, int64_t B, const
   for (int k = tid2(); k <= g.N; k += CB * NBt) s.ptr[k] = g.in_ptr3[k];
   for (int k = tid2(); k < g.N; k += CB * NBt) s.ord[k] = g.ord3[k];
   const int total = (int)B * g.tiles3;
-  const char* mine = reinterpret_cast<const char*>(s.tile + tx);
-  // the element before the thread's chunk: q[4c] = qs[4c - 1]
-  const float* prv_p = tx > 0 ? reinterpret_cast<const float*>(s.tile + tx) - 1 : s.halo;
-  const int prv_stride = tx > 0 ? CB * 4 : 1;
+  const bool db = g.db3 != 0;
   const bool self_in = g.in_self3 != 0;
-  for (int tl = blockIdx.x; tl < total; tl += gridDim.x) {
+  // all copies of tile `t` into buffer `k`: qs -> tile, v -> tile2, q[4 c0] = qs[4 c0 - 1] -> halo (q[0] = 0, ADMM.py:176)
+  auto issue = [&](int t, int k) {
+    const int bb = t / g.tiles3, cc0 = (t - bb * g.tiles3) * CB, ccx = cc0 + tx;
+    float4* t1 = s.tile + k * s.stride_t + tx;
+    float4* t2 = s.tile2 + k * s.stride_t + tx;
+    float* h1 = s.halo + k * s.stride_h;
+    if (ccx < g.C4) {
+      const size_t wq = (size_t)bb * (size_t)(g.N * g.C4) + ccx;
+      const float4* qw = reinterpret_cast<const float4*>(qs) + wq;
+      const float4* vw = reinterpret_cast<const float4*>(v) + wq;
+      for (int n = threadIdx.y; n < g.N; n += NBt) {
+        cp_async16(t1 + n * CB, qw + n * g.C4);
+        cp_async16(t2 + n * CB, vw + n * g.C4);
+        if (tx == 0 && cc0 > 0) cp_async4(h1 + n, reinterpret_cast<const float*>(qw + n * g.C4) - 1);
+      }
+    } else {
+      for (int n = threadIdx.y; n < g.N; n += NBt) t1[n * CB] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (tx == 0 && cc0 == 0)
+      for (int n = threadIdx.y; n < g.N; n += NBt) h1[n] = 0.f;
+    cp_async_commit();
+  };
+  int cur = 0;
+  if (db && (int)blockIdx.x < total) issue(blockIdx.x, 0);
+  for (int tl = blockIdx.x; tl < total; tl += gridDim.x, cur ^= (db ? 1 : 0)) {
     const int b = tl / g.tiles3, c0 = (tl - b * g.tiles3) * CB, c = c0 + tx;
     const bool cok = c < g.C4;
     const size_t w0 = (size_t)b * (size_t)(g.N * g.C4);
-    const float4* qw = reinterpret_cast<const float4*>(qs) + w0;
-    if (tl != (int)blockIdx.x) __syncthreads();
-    const float4* vw = reinterpret_cast<const float4*>(v) + w0 + (cok ? c : 0);
-    for (int n = threadIdx.y; n < g.N; n += NBt) {
-      if (cok) {
-        cp_async16(s.tile + n * CB + tx, qw + c + n * g.C4);
-        cp_async16(s.tile2 + n * CB + tx, vw + n * g.C4);
-        if (tx == 0 && c0 > 0) cp_async4(s.halo + n, reinterpret_cast<const float*>(qw + c + n * g.C4) - 1);   // q[4 c0] = qs[4 c0 - 1]
-      } else {
-        s.tile[n * CB + tx] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-      if (tx == 0 && c0 == 0) s.halo[n] = 0.f;                                                        // q[0] = 0 (ADMM.py:176)
+    if (!db) {
+      if (tl != (int)blockIdx.x) __syncthreads();
+      issue(tl, 0);
     }
     cp_async_wait_all();
     __syncthreads();
-    tile_prefetch(g, tl + gridDim.x, total, qs, v, nullptr);
+    if (db && tl + (int)gridDim.x < total) issue(tl + gridDim.x, cur ^ 1);
+    const float4* tile = s.tile + cur * s.stride_t;
+    const float4* tile2 = s.tile2 + cur * s.stride_t;
+    const char* mine = reinterpret_cast<const char*>(tile + tx);
+    // the element before the thread's chunk: q[4c] = qs[4c - 1]
+    const float* prv_p = tx > 0 ? reinterpret_cast<const float*>(tile + tx) - 1 : s.halo + cur * s.stride_h;
+    const int prv_stride = tx > 0 ? CB * 4 : 1;
     float dot = 0.f;
     if (cok) {
       const int t0 = 4 * c;
@@ -604,10 +624,10 @@ __global__ void __launch_bounds__(512, 2) k3_ldrt_lhs(Graph2 g, int64_t B, const
       for (int j = 0; j < 4; ++j) { hx[j] = (xsys && t0 + j < g.t_in) ? 1.f : 0.f; tv[j] = t0 + j < g.T ? 1.f : 0.f; }
       for (int k = threadIdx.y; k < g.N; k += NBt) {
         const int n = s.ord[k];
-        const float4 pv = s.tile2[n * CB + tx];
+        const float4 pv = tile2[n * CB + tx];
         float4 rh;
         if (MODE == 1) rh = __ldcs(rw + n * g.C4);
-        const float4 q1 = s.tile[n * CB + tx];
+        const float4 q1 = tile[n * CB + tx];
         const float qprev = prv_p[n * prv_stride];
         const float ws = self_in ? s.wself[n] : 0.f;
         float4 f = make_float4(ws * q1.x, ws * q1.y, ws * q1.z, ws * q1.w);     // self link: w_self qs_own
@@ -643,7 +663,7 @@ __global__ void __launch_bounds__(512, 2) k3_ldrt_lhs(Graph2 g, int64_t B, const
 
 // z_u system: (r, p) -> p', Ap = (c L_u + a I) p', <p', Ap>   [SRC 2 / MODE 1: r = rhs - A x0, <r, r>]
 template <int SRC, int MODE, int K>
-__global__ void __launch_bounds__(512, 2) k3_lu(Graph2 g, int64_t B, int it, const float* __restrict__ r,
+__global__ void __launch_bounds__(1024, 1) k3_lu(Graph2 g, int64_t B, int it, const float* __restrict__ r,
                                                 const float* __restrict__ p_old, float* __restrict__ p_new,
                                                 const float* __restrict__ rhs, float* __restrict__ out,
                                                 const double* __restrict__ dots, double* __restrict__ slot, float a, float cc) {
@@ -652,13 +672,20 @@ __global__ void __launch_bounds__(512, 2) k3_lu(Graph2 g, int64_t B, int it, con
   const Smem3 s = carve3(g, s3, CB, false);
   stage_table(g.tab_u, g.N * g.ku3, s.tab);
   const int total = (int)B * g.tiles3;
-  const char* mine = reinterpret_cast<const char*>(s.tile + tx);
-  for (int tl = blockIdx.x; tl < total; tl += gridDim.x) {
+  const bool db = g.db3 != 0;
+  int cur = 0;
+  if (db && (int)blockIdx.x < total) tile_issue<SRC>(g, blockIdx.x, 0, r, p_old, s, false);
+  for (int tl = blockIdx.x; tl < total; tl += gridDim.x, cur ^= (db ? 1 : 0)) {
     const int b = tl / g.tiles3, c0 = (tl - b * g.tiles3) * CB, c = c0 + tx;
-    if (tl != (int)blockIdx.x) __syncthreads();
-    tile_fill<SRC>(g, B, it, b, c0, r, p_old, p_new, dots, s, false);
+    if (!db) {
+      if (tl != (int)blockIdx.x) __syncthreads();
+      tile_issue<SRC>(g, tl, 0, r, p_old, s, false);
+    }
+    tile_finish<SRC>(g, B, it, tl, cur, p_new, dots, s, false);
     __syncthreads();
-    tile_prefetch(g, tl + gridDim.x, total, r, SRC == 0 ? p_old : nullptr, MODE == 1 ? rhs : nullptr);
+    if (db && tl + (int)gridDim.x < total) tile_issue<SRC>(g, tl + gridDim.x, cur ^ 1, r, p_old, s, false);
+    const float4* tile = s.tile + cur * s.stride_t;
+    const char* mine = reinterpret_cast<const char*>(tile + tx);
     float dot = 0.f;
     if (c < g.C4) {
       const size_t w0 = (size_t)b * (size_t)(g.N * g.C4);
@@ -667,7 +694,7 @@ __global__ void __launch_bounds__(512, 2) k3_lu(Graph2 g, int64_t B, int it, con
       for (int n = threadIdx.y; n < g.N; n += NBt) {
         float4 rh;
         if (MODE == 1) rh = __ldcs(rw + n * g.C4);
-        const float4 pv = s.tile[n * CB + tx];
+        const float4 pv = tile[n * CB + tx];
         const float4 acc = gather3<K>(s.tab + n * g.ku3, g.ku3, mine, make_float4(0.f, 0.f, 0.f, 0.f));
         float4 o;
         o.x = cc * (pv.x - acc.x) + a * pv.x;
@@ -895,20 +922,25 @@ void stream2_tiling(Graph2* g) {
   int force = 0;
   if (const char* e = std::getenv("MGA_S3_CB")) force = std::atoi(e);     // 0 = automatic, < 0 = off, > 0 = chunks per tile
   if (force >= 0) {
-    // tiles of >= 4 chunks (64-byte row segments) or the whole row, and only if 2 CTAs fit an SM: PEMS-sized graphs
-    // (N <= ~360 with 8-chunk tiles, <= ~590 with 4-chunk tiles); larger graphs stay on the k2 kernels
+    // tiles of >= 4 chunks (64-byte row segments) or the whole row.  Single-buffered (default): 2 tile buffers, two CTAs
+    // per SM (N <= ~360 with 8-chunk tiles, ~590 with 4-chunk tiles).  Double-buffered (MGA_S3_DB=1): 4 buffers, one CTA
+    // per SM, the next tile's copies in flight during the gathers - measured no faster (T = 288: 40.0 vs 39.1 ms per
+    // step, T = 24: 56.0 vs 52.9): two CTAs per SM already overlap copy and gather.  Larger graphs stay on the k2 kernels.
+    g->db3 = 0;
+    if (const char* e = std::getenv("MGA_S3_DB")) g->db3 = std::atoi(e) != 0;
+    const int nb = g->db3 ? 2 : 1;
     const int cands[3] = {force > 0 ? std::min(force, g->C4) : std::min(g->C4, 8), std::min(g->C4, 4), 0};
     const size_t table = (size_t)g->N * std::max(g->kd, g->ku) * 8 + (size_t)(g->N + 2) * 8;
-    const size_t limit = (228 * 1024) / 2 - 1024;
+    const size_t limit = g->db3 ? 226 * 1024 : (228 * 1024) / 2 - 1024;
     for (int k = 0; cands[k] > 0 && g->CB3 == 0; ++k)
-      if ((size_t)g->N * (2 * (size_t)cands[k] * 16 + 12) + 8 + table <= limit) g->CB3 = cands[k];
+      if ((size_t)g->N * (2 * nb * (size_t)cands[k] * 16 + (nb + 2) * 4) + 8 + table <= limit) g->CB3 = cands[k];
   }
   if (g->CB3 > 0) {
     const int cb = g->CB3;
     // measured on B200 (PEMS04 graph): 512 threads (2 CTAs/SM) win for tiles of >= 4 chunks (T = 24: 52.3 vs 54.6 ms per
     // step, T = 288: 37.9 vs 38.4), 256 threads for the 3-chunk tile of T = 12 (55.3 vs 60.3)
     int threads = cb >= 4 ? 512 : 256;
-    if (const char* e = std::getenv("MGA_S3_THREADS")) threads = std::atoi(e) >= 512 ? 512 : 256;
+    if (const char* e = std::getenv("MGA_S3_THREADS")) threads = std::atoi(e) >= 1024 ? 1024 : std::atoi(e) >= 512 ? 512 : 256;
     g->NB3t = (cb & (cb - 1)) == 0 ? threads / cb : 32 * std::max(1, (threads / 32) / cb);     // cb * NB3t whole warps
     g->tiles3 = (g->C4 + cb - 1) / cb;
   }
