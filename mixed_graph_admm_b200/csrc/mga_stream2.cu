@@ -738,16 +738,15 @@ __device__ __forceinline__ void ldr_chunk(const Graph2& g, const float* __restri
   const int* nb = g.nbr_d + (size_t)n * g.kd;
   const float* ww = g.w_d + (size_t)n * g.kd;
   const int t0 = 4 * c;
+  const float4* vw = reinterpret_cast<const float4*>(v) + w0 + c;
   for (int j = 0; j < g.kd; ++j) {
     const int m = nb[j];
     if (m < 0) continue;
     const float wj = ww[j];
-    const float* row = v + (w0 + (size_t)m * g.C4) * 4;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int t = t0 + q;
-      if (t >= 1 && t < g.T) acc[q] += wj * row[t - 1];
-    }
+    // the neighbour's steps t0-1 .. t0+2: its chunk c (one 128-bit load) and the last element of chunk c-1; pads are 0
+    const float4 a = vw[(size_t)m * g.C4];
+    const float prev = c > 0 ? reinterpret_cast<const float*>(vw + (size_t)m * g.C4)[-1] : 0.f;
+    acc[0] += wj * prev; acc[1] += wj * a.x; acc[2] += wj * a.y; acc[3] += wj * a.z;
   }
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
@@ -777,14 +776,20 @@ __global__ void __launch_bounds__(kB2) k2_rhs_x(Graph2 g, const float* __restric
   const float v[4] = {ga.x + rho * ph.x, ga.y + rho * ph.y, ga.z + rho * ph.z, ga.w + rho * ph.w};
   float f[4] = {0.f, 0.f, 0.f, 0.f};
   const int t0 = 4 * k.c;
+  const float4* gw = reinterpret_cast<const float4*>(gam) + w0 + k.c;
+  const float4* pw = reinterpret_cast<const float4*>(phi) + w0 + k.c;
+  const bool more = k.c + 1 < g.C4;
   for (int e = g.in_ptr[k.n]; e < g.in_ptr[k.n + 1]; ++e) {
     const float w = g.in_w[e];
-    const size_t row = (w0 + (size_t)g.in_src[e] * g.C4) * 4;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int t = t0 + q;
-      if (t + 1 < g.T) f[q] += w * (gam[row + t + 1] + rho * phi[row + t + 1]);
-    }
+    // the source's steps t0+1 .. t0+4: its chunk c and the first element of chunk c+1 (pads of both vectors are 0)
+    const size_t row = (size_t)g.in_src[e] * g.C4;
+    const float4 ga2 = gw[row], ph2 = pw[row];
+    const float gn = more ? reinterpret_cast<const float*>(gw + row + 1)[0] : 0.f;
+    const float pn = more ? reinterpret_cast<const float*>(pw + row + 1)[0] : 0.f;
+    f[0] += w * (ga2.y + rho * ph2.y);
+    f[1] += w * (ga2.z + rho * ph2.z);
+    f[2] += w * (ga2.w + rho * ph2.w);
+    f[3] += w * (gn + rho * pn);
   }
   const float4 a = ld4(zu, k.g), b = ld4(zd, k.g), c = ld4(gu, k.g), d = ld4(gd, k.g);
   const float zuv[4] = {a.x, a.y, a.z, a.w}, zdv[4] = {b.x, b.y, b.z, b.w};
