@@ -50,6 +50,7 @@ struct Graph2 {
   int N, T, t_in, C4;      // C4 = ceil(T / 4) chunks of 4 time steps per node row
   int CB, NB, tilesN, tilesC;   // CTA tile = NB nodes x CB chunks; tiles per window = tilesN * tilesC
   int NBt;                      // thread rows of a tile CTA: block = (CB, NBt), NBt >= NB, CB * NBt a multiple of 32
+  int one3;                     // time-tiled kernels: the tile only fits once per SM (one CTA of 1024 threads)
   int db3;                      // time-tiled kernels double-buffered (one CTA per SM, next tile copied while this one is gathered)
   int CB3, NB3t, tiles3;        // time-tiled shared-memory kernels (k3_*): CB3 chunks x all nodes per CTA, block = (CB3, NB3t); CB3 = 0: off
   int kd, ku, q1;

@@ -928,7 +928,7 @@ void stream2_tiling(Graph2* g) {
   if (const char* e = std::getenv("MGA_S3_CB")) force = std::atoi(e);     // 0 = automatic, < 0 = off, > 0 = chunks per tile
   if (force >= 0) {
     // tiles of >= 4 chunks (64-byte row segments) or the whole row.  Single-buffered (default): 2 tile buffers, two CTAs
-    // per SM (N <= ~360 with 8-chunk tiles, ~590 with 4-chunk tiles).  Double-buffered (MGA_S3_DB=1): 4 buffers, one CTA
+    // per SM (N <= ~360 with 8-chunk tiles, ~590 with 4-chunk tiles), or one CTA per SM (8-chunk tiles, N <= ~690).  Double-buffered (MGA_S3_DB=1): 4 buffers, one CTA
     // per SM, the next tile's copies in flight during the gathers - measured no faster (T = 288: 40.0 vs 39.1 ms per
     // step, T = 24: 56.0 vs 52.9): two CTAs per SM already overlap copy and gather.  Larger graphs stay on the k2 kernels.
     g->db3 = 0;
@@ -936,15 +936,22 @@ void stream2_tiling(Graph2* g) {
     const int nb = g->db3 ? 2 : 1;
     const int cands[3] = {force > 0 ? std::min(force, g->C4) : std::min(g->C4, 8), std::min(g->C4, 4), 0};
     const size_t table = (size_t)g->N * std::max(g->kd, g->ku) * 8 + (size_t)(g->N + 2) * 8;
-    const size_t limit = g->db3 ? 226 * 1024 : (228 * 1024) / 2 - 1024;
-    for (int k = 0; cands[k] > 0 && g->CB3 == 0; ++k)
-      if ((size_t)g->N * (2 * nb * (size_t)cands[k] * 16 + (nb + 2) * 4) + 8 + table <= limit) g->CB3 = cands[k];
+    // two CTAs per SM if a tile allows it, else one CTA of 1024 threads with the 8-chunk tile (MGA_S3_ONE=0 turns the
+    // second pass off).  Measured: N = 600, T = 96 (one CTA, 8 chunks) 52.6 vs 60.2 ms per step on the k2 kernels;
+    // N = 883, T = 288 (one CTA, 4 chunks) 50.2 vs 48.7 - so 4-chunk tiles are only used two per SM.
+    bool one = !g->db3;
+    if (const char* e = std::getenv("MGA_S3_ONE")) one = one && std::atoi(e) != 0;
+    const size_t limits[2] = {g->db3 ? (size_t)226 * 1024 : (size_t)(228 * 1024) / 2 - 1024, (size_t)226 * 1024};
+    g->one3 = 0;
+    for (int l = 0; l < (one ? 2 : 1) && g->CB3 == 0; ++l)
+      for (int k = 0; cands[k] > 0 && k <= 1 - l && g->CB3 == 0; ++k)
+        if ((size_t)g->N * (2 * nb * (size_t)cands[k] * 16 + (nb + 2) * 4) + 8 + table <= limits[l]) { g->CB3 = cands[k]; g->one3 = l; }
   }
   if (g->CB3 > 0) {
     const int cb = g->CB3;
     // measured on B200 (PEMS04 graph): 512 threads (2 CTAs/SM) win for tiles of >= 4 chunks (T = 24: 52.3 vs 54.6 ms per
     // step, T = 288: 37.9 vs 38.4), 256 threads for the 3-chunk tile of T = 12 (55.3 vs 60.3)
-    int threads = cb >= 4 ? 512 : 256;
+    int threads = g->one3 ? 1024 : cb >= 4 ? 512 : 256;
     if (const char* e = std::getenv("MGA_S3_THREADS")) threads = std::atoi(e) >= 1024 ? 1024 : std::atoi(e) >= 512 ? 512 : 256;
     g->NB3t = (cb & (cb - 1)) == 0 ? threads / cb : 32 * std::max(1, (threads / 32) / cb);     // cb * NB3t whole warps
     g->tiles3 = (g->C4 + cb - 1) / cb;

@@ -22,6 +22,8 @@ CONFIGS = {
     "pems04_t24": (307, 6, 24, 4096, 1.1, 4),
     "t288": (307, 6, 288, 256, 1.1, 4),
     "large20k": (20000, 8, 24, 64, 1.1, 9),
+    "pems07_t288": (883, 6, 288, 96, 1.1, 7),      # PEMS07-sized graph, one day at 5 min
+    "n600_t96": (600, 6, 96, 512, 1.1, 6),
 }
 
 ap = argparse.ArgumentParser()
