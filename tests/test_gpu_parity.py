@@ -460,12 +460,12 @@ def test_skip_connection_line_graph_against_oracle(N, k, T, skip, B, mode):
 
 
 @pytest.mark.parametrize("N,k,T,B", [(100, 4, 50, 3), (307, 6, 100, 2), (400, 6, 37, 2), (64, 3, 26, 5), (500, 6, 41, 2),
-                                     (700, 5, 30, 2)])
+                                     (600, 6, 33, 2), (700, 5, 30, 2)])
 def test_long_windows_odd_lengths_against_oracle(N, k, T, B):
     """T > 24 (beyond the resident kernel) with lengths that are not multiples of 4 or 12: the chunked streaming
     kernels' padded last chunk and the general kernels, both against the oracle.  N <= 360: time-tiled shared-memory
-    kernels with 8-chunk tiles (a padded last tile at T = 37, 50, 100), N = 400 / 500: 4-chunk tiles, N = 700: the
-    graph no longer fits two CTAs per SM and the L1-gather kernels run."""
+    kernels with 8-chunk tiles (a padded last tile at T = 37, 50, 100), N = 400 / 500: 4-chunk tiles, N = 600: one
+    1024-thread CTA per SM with 8-chunk tiles, N = 700: the graph no longer fits and the L1-gather kernels run."""
     from mixed_graph_admm_b200 import synth
     from mixed_graph_admm_b200.ADMM import ADMM_algorithm
     from oracle import admm_oracle as O
@@ -482,6 +482,33 @@ def test_long_windows_odd_lengths_against_oracle(N, k, T, B):
     tr = O.admm_combined(og, prm, y, max_admm_iter=2, max_cg_iter=8, cg_tol=-1.0, admm_tol=-1.0)
     for mode, x in xs.items():
         assert rel_err(x, tr.x) <= 1e-5 and max_rel(x, tr.x) <= 2e-5, (mode, rel_err(x, tr.x))
+
+
+@pytest.mark.parametrize("env", [{"MGA_S3_DB": "1"}, {"MGA_S3_DB": "1", "MGA_S3_THREADS": "1024"}, {"MGA_S3_CB": "4"},
+                                 {"MGA_S3_CB": "2", "MGA_S3_THREADS": "256"}, {"MGA_S3_CB": "-1"}, {"MGA_S3_SORT": "0"}])
+def test_time_tiled_kernel_options_against_oracle(env, monkeypatch):
+    """The knobs of the time-tiled streaming kernels that are kept in the code (double-buffered mode, tile width,
+    CTA size, natural row order, the L1-gather kernels on a small graph) all give the oracle's result; the plan
+    reads them when it is created."""
+    from mixed_graph_admm_b200 import synth
+    from mixed_graph_admm_b200.ADMM import ADMM_algorithm
+    from oracle import admm_oracle as O
+    N, k, T, B = 307, 6, 50, 3
+    t_in = T // 2
+    for key, val in env.items():
+        monkeypatch.setenv(key, val)
+    gi = synth.road_graph(N, 1.1, seed=4)
+    y = synth.signals(B, t_in, N, seed=3)
+    blk = ADMM_algorithm(gi, synth.admm_info(N), use_kNN=True, k=k, u_sigma=50, d_sigma=50, t_in=t_in, T=T, mode="streaming")
+    blk.max_ADMM_iter, blk.max_CG_iter, blk.CG_tol, blk.ADMM_tol = 2, 8, -1.0, -1.0
+    blk.keep_iterates = True
+    x = blk.combined_loop(y.cuda(), print_info=False).cpu()
+    og = O.OracleGraph(nbr=blk.connect_list, u_w=blk.u_ew, d_w=blk.d_ew)
+    prm = O.OracleParams(**synth.admm_info(N), t_in=t_in, T=T)
+    tr = O.admm_combined(og, prm, y, max_admm_iter=2, max_cg_iter=8, cg_tol=-1.0, admm_tol=-1.0)
+    assert rel_err(x, tr.x) <= 1e-5 and max_rel(x, tr.x) <= 2e-5, (env, rel_err(x, tr.x))
+    assert rel_err(blk.last_iterates["zu"].cpu(), tr.zu) <= 1e-5 and rel_err(blk.last_iterates["zd"].cpu(), tr.zd) <= 1e-5
+    np.testing.assert_allclose(blk.p_res_list[-1], tr.p_res[-1], rtol=2e-5, atol=1e-7)
 
 
 @pytest.mark.parametrize("mode", ["resident", "streaming"])
