@@ -342,13 +342,15 @@ __global__ void __launch_bounds__(kFlat) k2_pupdate(Graph2 g, int64_t B, int it,
 }
 
 // x += alpha p ; r -= alpha Ap ; RR(k+1) += r.r   (ADMM.py:350-355)
-__global__ void __launch_bounds__(kFlat) k2_xr(Graph2 g, int64_t B, int it, float* __restrict__ x, float* __restrict__ r,
+// x_in: the iterate this step starts from - the warm start x0 in the first iteration (read in place, no copy of
+// the warm start is made), x itself afterwards
+__global__ void __launch_bounds__(kFlat) k2_xr(Graph2 g, int64_t B, int it, const float* x_in, float* x, float* __restrict__ r,
                                               const float* __restrict__ p, const float* __restrict__ ap, double* __restrict__ dots) {
   const Chunk k = locate_flat(g);
   float dot = 0.f;
   if (k.ok) {
     const float alpha = (float)dots[(size_t)(2 * it) * B + k.b] / (float)dots[(size_t)(2 * it + 1) * B + k.b];
-    const float4 xv = ld4(x, k.g), pv = ld4(p, k.g), rv = ld4(r, k.g), av = ld4(ap, k.g);
+    const float4 xv = ld4(x_in, k.g), pv = ld4(p, k.g), rv = ld4(r, k.g), av = ld4(ap, k.g);
     st4(x, k.g, make_float4(xv.x + alpha * pv.x, xv.y + alpha * pv.y, xv.z + alpha * pv.z, xv.w + alpha * pv.w));
     const float4 rn = make_float4(rv.x - alpha * av.x, rv.y - alpha * av.y, rv.z - alpha * av.z, rv.w - alpha * av.w);
     st4(r, k.g, rn);
@@ -999,8 +1001,9 @@ static int k3_ctas_per_sm(const void* kern, int threads, size_t smem, int* rc) {
 }
 
 // CG_solver (ADMM.py:329-368) with a fixed iteration count on internal-layout vectors; x holds x0 / the solution.
-static int cg2(mga_plan* p, int system, const mga_params* m, const float* rhs, float* x, int64_t B, int64_t B_out, int n_cg,
-               float* alpha, float* beta, const Bufs2& w, cudaStream_t st) {
+// x0: warm start (read only); x: the solution (x0 == x: in place).  With n_cg == 0 the solution IS the warm start.
+static int cg2(mga_plan* p, int system, const mga_params* m, const float* rhs, const float* x0, float* x, int64_t B,
+               int64_t B_out, int n_cg, float* alpha, float* beta, const Bufs2& w, cudaStream_t st) {
   const Graph2& g = p->g2;
   const dim3 grid((unsigned)B, g.tilesN, g.tilesC), blk(g.CB, g.NBt);
   const dim3 fgrid((unsigned)B, (g.N * g.C4 + kFlat - 1) / kFlat);
@@ -1026,12 +1029,12 @@ static int cg2(mga_plan* p, int system, const mga_params* m, const float* rhs, f
 #define MGA_K3_BY_K(K, macro) \
     do { if ((K) == 4) { macro(4); } else if ((K) == 6) { macro(6); } else if ((K) == 8) { macro(8); } else { macro(0); } } while (0)
     if (system == MGA_SYS_ZU) {
-#define MGA_K3_LU_INIT(K) MGA_K3_LAUNCH((k3_lu<2, 1, K>), g.smem3_u, g, B, 0, x, nullptr, nullptr, rhs, w.r, w.dots, w.dots, a, c)
+#define MGA_K3_LU_INIT(K) MGA_K3_LAUNCH((k3_lu<2, 1, K>), g.smem3_u, g, B, 0, x0, nullptr, nullptr, rhs, w.r, w.dots, w.dots, a, c)
       MGA_K3_BY_K(g.ku3, MGA_K3_LU_INIT);
     } else {
-#define MGA_K3_PLDR_INIT(K) MGA_K3_LAUNCH((k3_p_ldr<2, K>), g.smem3_d, g, B, 0, x, nullptr, nullptr, w.qs, w.dots)
+#define MGA_K3_PLDR_INIT(K) MGA_K3_LAUNCH((k3_p_ldr<2, K>), g.smem3_d, g, B, 0, x0, nullptr, nullptr, w.qs, w.dots)
       MGA_K3_BY_K(g.kd3, MGA_K3_PLDR_INIT);
-      MGA_K3_LAUNCH((k3_ldrt_lhs<1>), g.smem3_in, g, B, x, w.qs, rhs, w.r, w.dots, a, c, xsys);
+      MGA_K3_LAUNCH((k3_ldrt_lhs<1>), g.smem3_in, g, B, x0, w.qs, rhs, w.r, w.dots, a, c, xsys);
     }
     for (int it = 0; it < n_cg; ++it) {
       double* pap = w.dots + (size_t)(2 * it + 1) * B;
@@ -1047,19 +1050,19 @@ static int cg2(mga_plan* p, int system, const mga_params* m, const float* rhs, f
         else MGA_K3_BY_K(g.kd3, MGA_K3_PLDR_NEXT);
         MGA_K3_LAUNCH((k3_ldrt_lhs<0>), g.smem3_in, g, B, p_new, w.qs, nullptr, w.ap, pap, a, c, xsys);
       }
-      k2_xr<<<fgrid, kFlat, 0, st>>>(g, B, it, x, w.r, p_new, w.ap, w.dots);
+      k2_xr<<<fgrid, kFlat, 0, st>>>(g, B, it, it == 0 ? x0 : x, x, w.r, p_new, w.ap, w.dots);
       MGA_LAUNCH_CHECK("k2_xr");
       std::swap(p_old, p_new);
     }
   } else {
   // r = rhs - A x0 ; RR(0)
   if (system == MGA_SYS_ZU) {
-    k2_lu_lhs<1><<<grid, blk, 0, st>>>(g, x, rhs, w.r, w.dots, a, c);
+    k2_lu_lhs<1><<<grid, blk, 0, st>>>(g, x0, rhs, w.r, w.dots, a, c);
     MGA_LAUNCH_CHECK("k2_lu_lhs");
   } else {
-    k2_ldr_shift<<<grid, blk, 0, st>>>(g, x, w.qs);
+    k2_ldr_shift<<<grid, blk, 0, st>>>(g, x0, w.qs);
     MGA_LAUNCH_CHECK("k2_ldr_shift");
-    k2_ldrt_lhs<1><<<grid, blk, 0, st>>>(g, x, w.qs, rhs, w.r, w.dots, a, c, xsys);
+    k2_ldrt_lhs<1><<<grid, blk, 0, st>>>(g, x0, w.qs, rhs, w.r, w.dots, a, c, xsys);
     MGA_LAUNCH_CHECK("k2_ldrt_lhs");
   }
   for (int it = 0; it < n_cg; ++it) {
@@ -1075,10 +1078,12 @@ static int cg2(mga_plan* p, int system, const mga_params* m, const float* rhs, f
       k2_ldrt_lhs<0><<<grid, blk, 0, st>>>(g, w.p, w.qs, nullptr, w.ap, pap, a, c, xsys);
       MGA_LAUNCH_CHECK("k2_ldrt_lhs");
     }
-    k2_xr<<<fgrid, kFlat, 0, st>>>(g, B, it, x, w.r, w.p, w.ap, w.dots);
+    k2_xr<<<fgrid, kFlat, 0, st>>>(g, B, it, it == 0 ? x0 : x, x, w.r, w.p, w.ap, w.dots);
     MGA_LAUNCH_CHECK("k2_xr");
   }
   }
+  if (n_cg == 0 && x != x0)
+    MGA_CUDA(cudaMemcpyAsync(x, x0, (size_t)B * g.N * g.C4 * 16, cudaMemcpyDeviceToDevice, st));
   if ((alpha || beta) && n_cg > 0) {
     const int64_t tot = B * n_cg;
     k2_coeffs<<<(unsigned)((tot + 255) / 256), 256, 0, st>>>(B, B_out, n_cg, w.dots, alpha, beta);
@@ -1145,7 +1150,7 @@ static int stream2_cg_group(mga_plan* p, int system, const mga_params* m, const 
   MGA_LAUNCH_CHECK("k2_import");
   k2_import<<<grid, blk, 0, st>>>(g, static_cast<const float*>(x), x_i);
   MGA_LAUNCH_CHECK("k2_import");
-  rc = cg2(p, system, m, rhs_i, x_i, B, B_out, n_cg, static_cast<float*>(alpha), static_cast<float*>(beta), w, st);
+  rc = cg2(p, system, m, rhs_i, x_i, x_i, B, B_out, n_cg, static_cast<float*>(alpha), static_cast<float*>(beta), w, st);
   if (rc) return rc;
   k2_export<<<grid, blk, 0, st>>>(g, x_i, static_cast<float*>(x));
   MGA_LAUNCH_CHECK("k2_export");
@@ -1216,23 +1221,20 @@ static int stream2_admm_group(mga_plan* p, const mga_params* prm, const void* y_
   const float rho = (float)prm->rho, rho_u = (float)prm->rho_u, rho_d = (float)prm->rho_d;
   const float thr = (float)(prm->mu_d1 / prm->rho);
   const size_t coef_stride = (size_t)max_cg * B_out;
-  const size_t vbytes = chunks * 16;
   for (int it = 0; it < n_outer; ++it) {
     auto coef = [&](void* basep, int s) -> float* {
       return basep ? static_cast<float*>(basep) + ((size_t)it * 3 + s) * coef_stride : nullptr;
     };
     k2_rhs_x<<<grid, blk, 0, st>>>(g, gam, phi, zu_cur, zd_cur, gu, gd, y, rhs, rho, rho_u, rho_d);
     MGA_LAUNCH_CHECK("k2_rhs_x");
-    MGA_CUDA(cudaMemcpyAsync(x_nxt, x_cur, vbytes, cudaMemcpyDeviceToDevice, st));       // warm start (ADMM.py:571)
-    if ((rc = cg2(p, MGA_SYS_X, prm, rhs, x_nxt, B, B_out, max_cg, coef(outs->alpha, 0), coef(outs->beta, 0), w, st))) return rc;
+    // warm starts (ADMM.py:571, 580, 588) are read in place: the first x update of a solve writes the other buffer
+    if ((rc = cg2(p, MGA_SYS_X, prm, rhs, x_cur, x_nxt, B, B_out, max_cg, coef(outs->alpha, 0), coef(outs->beta, 0), w, st))) return rc;
     k2_rhs_z<<<grid_c, kFlat, 0, st>>>(chunks, gu, x_nxt, rhs, (float)(prm->rho_u / 2));
     MGA_LAUNCH_CHECK("k2_rhs_z");
-    MGA_CUDA(cudaMemcpyAsync(zu_nxt, zu_cur, vbytes, cudaMemcpyDeviceToDevice, st));
-    if ((rc = cg2(p, MGA_SYS_ZU, prm, rhs, zu_nxt, B, B_out, max_cg, coef(outs->alpha, 1), coef(outs->beta, 1), w, st))) return rc;
+    if ((rc = cg2(p, MGA_SYS_ZU, prm, rhs, zu_cur, zu_nxt, B, B_out, max_cg, coef(outs->alpha, 1), coef(outs->beta, 1), w, st))) return rc;
     k2_rhs_z<<<grid_c, kFlat, 0, st>>>(chunks, gd, x_nxt, rhs, (float)(prm->rho_d / 2));
     MGA_LAUNCH_CHECK("k2_rhs_z");
-    MGA_CUDA(cudaMemcpyAsync(zd_nxt, zd_cur, vbytes, cudaMemcpyDeviceToDevice, st));
-    if ((rc = cg2(p, MGA_SYS_ZD, prm, rhs, zd_nxt, B, B_out, max_cg, coef(outs->alpha, 2), coef(outs->beta, 2), w, st))) return rc;
+    if ((rc = cg2(p, MGA_SYS_ZD, prm, rhs, zd_cur, zd_nxt, B, B_out, max_cg, coef(outs->alpha, 2), coef(outs->beta, 2), w, st))) return rc;
     double* drow = want_diag ? diag + (size_t)it * MGA_DIAG_COLS : nf_row;
     k2_tail<<<grid, blk, 0, st>>>(g, want_diag ? 1 : 0, x_nxt, x_cur, zu_nxt, zu_cur, zd_nxt, zd_cur, gu, gd, gam, phi,
                                  y, rho, rho_u, rho_d, thr, drow, dx_sum ? dx_sum + (size_t)it * g.T * g.N : nullptr);
