@@ -61,6 +61,10 @@ struct Graph2 {
   // time-tiled kernels: (row byte offset in the tile, weight bits) entries; the self link of the temporal graph is
   // in wself_d instead of the forward table / the in-list (in_self3 = 0: the in-list kept its self entries)
   int kd3, ku3, in_self3, in_ptr3_total;
+  // node tiles: NT3 own nodes per tile (N: one tile), R3 = most rows any tile stages (own + external), in_max3 = most
+  // in-list entries of a tile; per tile and table the external rows it references (ext*[extp*[j] .. extp*[j+1]))
+  int NT3, ntile3, R3, in_max3;
+  const int* extp_d; const int* ext_d; const int* extp_u; const int* ext_u; const int* extp_in; const int* ext_in;
   int smem3_d, smem3_u, smem3_in;
   const int2* tab_d; const int2* tab_u; const int2* tab_in3;
   const int* in_ptr3;
@@ -173,6 +177,7 @@ int stream_admm(mga_plan*, const mga_params*, const void* y, int y_rows, const v
                 int want_diag, const mga_admm_outputs* outs, cudaStream_t st);
 // chunked streaming path (mga_stream2.cu): fp32, forecasting mode, fixed iteration counts, ablation None
 bool stream2_eligible(const mga_plan*, int dtype);
+void stream2_threads3(Graph2* g);   // block shape of the time-tiled kernels after CB3 / one3 are final
 void stream2_tiling(Graph2* g);     // fills CB / NB / tilesN / tilesC for the kernels' block size
 int stream2_cg(mga_plan*, int system, const mga_params*, const void* rhs, void* x, int64_t B, int n_cg, void* alpha,
                void* beta, cudaStream_t st);

@@ -302,69 +302,117 @@ int mga_plan_create(const mga_graph_desc* d, int device, mga_plan** out) {
     // graph leaves both the forward table and the in-list (the owner already holds that value): tab_wself.
     if (g2.CB3 > 0) {
       const int row_bytes = g2.CB3 * 16;
+      // Node tiles (graphs too large for one CTA, whole rows of <= 8 chunks): a CTA owns NT3 RCM-consecutive nodes and
+      // stages, besides them, the EXTERNAL rows their table entries point to (RCM keeps those few: ~90 per 256-512
+      // nodes on the 20 000-node road graph).  Table entries hold LOCAL row offsets: own rows first, then the tile's
+      // external rows in ascending order.  Single-tile plans: NT3 = N, no external rows.
+      const int NT = g2.NT3 > 0 ? std::min(g2.NT3, N) : N;
+      const int ntile = (N + NT - 1) / NT;
+      g2.NT3 = NT;
+      g2.ntile3 = ntile;
       std::vector<float> wsd(N, 0.f);
-      auto pack = [&](const std::vector<int>& nb, const std::vector<float>& w, int K, bool drop_self, std::vector<int>& tab) {
+      // per-node reference lists -> per-tile external rows + a local index for every reference
+      struct Ext { std::vector<int> ptr, rows; };
+      auto build_ext = [&](const std::vector<std::vector<std::pair<int, float>>>& refs, Ext& ex,
+                           std::vector<std::vector<int>>& local) {
+        ex.ptr.assign(ntile + 1, 0);
+        ex.rows.clear();
+        local.assign(N, {});
+        for (int j = 0; j < ntile; ++j) {
+          const int n0 = j * NT, n1 = std::min(N, n0 + NT);
+          std::vector<int> ext;
+          for (int k = n0; k < n1; ++k)
+            for (auto& r : refs[k]) if (r.first < n0 || r.first >= n1) ext.push_back(r.first);
+          std::sort(ext.begin(), ext.end());
+          ext.erase(std::unique(ext.begin(), ext.end()), ext.end());
+          for (int k = n0; k < n1; ++k)
+            for (auto& r : refs[k]) {
+              const int m = r.first;
+              local[k].push_back((m >= n0 && m < n1) ? m - n0
+                                                     : (n1 - n0) + (int)(std::lower_bound(ext.begin(), ext.end(), m) - ext.begin()));
+            }
+          ex.rows.insert(ex.rows.end(), ext.begin(), ext.end());
+          ex.ptr[j + 1] = (int)ex.rows.size();
+        }
+      };
+      auto rows_of = [&](const std::vector<int>& nb, const std::vector<float>& w, int K, bool drop_self) {
         std::vector<std::vector<std::pair<int, float>>> rows(N);
-        int kmax = 0;
-        for (int k = 0; k < N; ++k) {
+        for (int k = 0; k < N; ++k)
           for (int j = 0; j < K; ++j) {
             const int m = nb[(size_t)k * K + j];
             if (m < 0) continue;
             if (drop_self && m == k) { wsd[k] += w[(size_t)k * K + j]; continue; }
             rows[k].push_back({m, w[(size_t)k * K + j]});
           }
-          kmax = std::max(kmax, (int)rows[k].size());
-        }
+        return rows;
+      };
+      auto pack = [&](const std::vector<std::vector<std::pair<int, float>>>& rows, const std::vector<std::vector<int>>& local,
+                      std::vector<int>& tab) {
+        int kmax = 0;
+        for (int k = 0; k < N; ++k) kmax = std::max(kmax, (int)rows[k].size());
         tab.assign((size_t)N * kmax * 2, 0);
         for (int k = 0; k < N; ++k)
           for (int j = 0; j < kmax; ++j) {
             const bool has = j < (int)rows[k].size();
             const float wj = has ? rows[k][j].second : 0.f;
-            tab[((size_t)k * kmax + j) * 2] = (has ? rows[k][j].first : k) * row_bytes;
+            tab[((size_t)k * kmax + j) * 2] = (has ? local[k][j] : k % NT) * row_bytes;      // pad: own row, weight 0
             std::memcpy(&tab[((size_t)k * kmax + j) * 2 + 1], &wj, sizeof(float));
           }
         return kmax;
       };
       std::vector<int> td, tu, ti, ip3(N + 1, 0);
-      g2.kd3 = pack(nd, wd, g.kd, true, td);
-      g2.ku3 = pack(nu, wu, g.ku, false, tu);
+      Ext ex_d, ex_u, ex_in;
+      std::vector<std::vector<int>> loc_d, loc_u, loc_in;
+      const auto rows_d = rows_of(nd, wd, g.kd, true);
+      const auto rows_u = rows_of(nu, wu, g.ku, false);
+      build_ext(rows_d, ex_d, loc_d);
+      build_ext(rows_u, ex_u, loc_u);
+      g2.kd3 = pack(rows_d, loc_d, td);
+      g2.ku3 = pack(rows_u, loc_u, tu);
       // in-list without the self entries.  The forward table's self weight is also the in-list's only when the
       // in-list is the transpose of the forward table (not for MGA_LDRT_GATHER): check entry by entry
       bool self_ok = true;
       for (int k = 0; k < N; ++k) {
         float ws_in = 0.f;
-        for (int e = ip[k]; e < ip[k + 1]; ++e) {
-          if (is[e] == k) { ws_in += iw[e]; continue; }
+        for (int e = ip[k]; e < ip[k + 1]; ++e)
+          if (is[e] == k) ws_in += iw[e];
+        if (ws_in != wsd[k]) self_ok = false;
+      }
+      std::vector<std::vector<std::pair<int, float>>> rows_in(N);
+      for (int k = 0; k < N; ++k)
+        for (int e = ip[k]; e < ip[k + 1]; ++e)
+          if (!(self_ok && is[e] == k)) rows_in[k].push_back({is[e], iw[e]});     // !self_ok: every entry stays, self included
+      build_ext(rows_in, ex_in, loc_in);
+      int in_max = 0;
+      for (int k = 0; k < N; ++k) {
+        for (size_t e = 0; e < rows_in[k].size(); ++e) {
           int wbits;
-          std::memcpy(&wbits, &iw[e], sizeof(float));
-          ti.push_back(is[e] * row_bytes);
+          std::memcpy(&wbits, &rows_in[k][e].second, sizeof(float));
+          ti.push_back(loc_in[k][e] * row_bytes);
           ti.push_back(wbits);
         }
-        if (ws_in != wsd[k]) self_ok = false;
         ip3[k + 1] = (int)ti.size() / 2;
       }
-      if (!self_ok) {          // keep every in-list entry, self included (its weight differs from the forward one)
-        ti.clear();
-        for (int k = 0; k < N; ++k) {
-          for (int e = ip[k]; e < ip[k + 1]; ++e) {
-            int wbits;
-            std::memcpy(&wbits, &iw[e], sizeof(float));
-            ti.push_back(is[e] * row_bytes);
-            ti.push_back(wbits);
-          }
-          ip3[k + 1] = (int)ti.size() / 2;
-        }
+      int rmax = 0;
+      for (int j = 0; j < ntile; ++j) {
+        const int n0 = j * NT, n1 = std::min(N, n0 + NT);
+        in_max = std::max(in_max, ip3[n1] - ip3[n0]);
+        for (const Ext* ex : {&ex_d, &ex_u, &ex_in}) rmax = std::max(rmax, (n1 - n0) + ex->ptr[j + 1] - ex->ptr[j]);
       }
-      // rows of k3_ldrt_lhs in descending in-list length: the 4-16 nodes a warp walks together have similar
-      // lengths (the in-degree of a kNN graph is far from uniform: hubs), so the gather loop is not padded to
-      // the longest list of an arbitrary group
+      g2.R3 = rmax;
+      g2.in_max3 = in_max;
+      // rows of k3_ldrt_lhs in descending in-list length (inside each node tile): the 4-16 nodes a warp walks together
+      // have similar lengths (the in-degree of a kNN graph is far from uniform: hubs), so the gather loop is not
+      // padded to the longest list of an arbitrary group
       std::vector<int> ord(N);
       for (int k = 0; k < N; ++k) ord[k] = k;
       // (rows of < 64 B stay in natural order: scattering them costs more DRAM sectors than the balance saves -
       // measured T = 12: 56.6 vs 55.6 ms per step; T = 288: 38.4 vs 39.9)
       const char* es = std::getenv("MGA_S3_SORT");
       if (es ? std::atoi(es) != 0 : g2.CB3 >= 4)
-        std::stable_sort(ord.begin(), ord.end(), [&](int x, int y) { return ip3[x + 1] - ip3[x] > ip3[y + 1] - ip3[y]; });
+        for (int j = 0; j < ntile; ++j)
+          std::stable_sort(ord.begin() + j * NT, ord.begin() + std::min(N, (j + 1) * NT),
+                           [&](int x, int y) { return ip3[x + 1] - ip3[x] > ip3[y + 1] - ip3[y]; });
       if ((rc = upload(p, ord, &g2.ord3))) return fail(rc);
       g2.in_self3 = self_ok ? 1 : 0;
       g2.in_ptr3_total = (int)ti.size() / 2;
@@ -377,16 +425,22 @@ int mga_plan_create(const mga_graph_desc* d, int device, mga_plan** out) {
       g2.tab_in3 = reinterpret_cast<const int2*>(dev_tab);
       if ((rc = upload(p, ip3, &g2.in_ptr3))) return fail(rc);
       if ((rc = upload(p, wsd, &g2.wself_d))) return fail(rc);
-      // dynamic shared memory of the three kernels: tile + halo + wself (+ in-list offsets) + table
-      const int nb3 = g2.db3 ? 2 : 1;      // tile / tile2 / halo per buffer, halo2, wself
-      const size_t tile_b = (size_t)N * (2 * nb3 * (size_t)row_bytes + (nb3 + 2) * 4) + 4;
-      g2.smem3_d = (int)(tile_b + (size_t)N * g2.kd3 * 8);
-      g2.smem3_u = (int)(tile_b + (size_t)N * g2.ku3 * 8);
-      g2.smem3_in = (int)(tile_b + (size_t)((N + 2) & ~1) * 4 + (size_t)((N + 1) & ~1) * 4 + (size_t)g2.in_ptr3_total * 8);
-      if (std::max(g2.smem3_d, std::max(g2.smem3_u, g2.smem3_in)) > p->max_smem_optin - 1024) g2.CB3 = 0;
+      if ((rc = upload(p, ex_d.ptr, &g2.extp_d)) || (rc = upload(p, ex_d.rows, &g2.ext_d))) return fail(rc);
+      if ((rc = upload(p, ex_u.ptr, &g2.extp_u)) || (rc = upload(p, ex_u.rows, &g2.ext_u))) return fail(rc);
+      if ((rc = upload(p, ex_in.ptr, &g2.extp_in)) || (rc = upload(p, ex_in.rows, &g2.ext_in))) return fail(rc);
+      // dynamic shared memory of the three kernels: R3 rows of (tile, tile2, halo) per buffer + halo2 + ext list, NT3 rows
+      // of wself (+ in-list offsets, row order) + the tile's table slice
+      const int nb3 = g2.db3 ? 2 : 1;
+      const size_t tile_b = (size_t)rmax * (2 * nb3 * (size_t)row_bytes + (nb3 + 2) * 4) + (size_t)NT * 4 + 8;
+      g2.smem3_d = (int)(tile_b + (size_t)NT * g2.kd3 * 8);
+      g2.smem3_u = (int)(tile_b + (size_t)NT * g2.ku3 * 8);
+      g2.smem3_in = (int)(tile_b + (size_t)((NT + 2) & ~1) * 4 + (size_t)((NT + 1) & ~1) * 4 + (size_t)in_max * 8);
+      const int smem_max = std::max(g2.smem3_d, std::max(g2.smem3_u, g2.smem3_in));
+      if (smem_max > p->max_smem_optin - 1024) g2.CB3 = 0;
+      else if (ntile > 1 && smem_max > (228 * 1024) / 2 - 1024) { g2.one3 = 1; stream2_threads3(&g2); }   // one CTA of 1024 threads per SM
       if (std::getenv("MGA_S3_VERBOSE"))
-        std::fprintf(stderr, "[mga] time-tiled kernels: N=%d C4=%d db=%d CB3=%d NB3t=%d tiles3=%d kd3=%d ku3=%d in=%d self=%d smem d/u/in=%d/%d/%d\n",
-                     N, g2.C4, g2.db3, g2.CB3, g2.NB3t, g2.tiles3, g2.kd3, g2.ku3, g2.in_ptr3_total, g2.in_self3, g2.smem3_d, g2.smem3_u,
+        std::fprintf(stderr, "[mga] time-tiled kernels: N=%d C4=%d db=%d CB3=%d NB3t=%d tiles3=%d NT3=%d ntile3=%d R3=%d kd3=%d ku3=%d in=%d self=%d smem d/u/in=%d/%d/%d\n",
+                     N, g2.C4, g2.db3, g2.CB3, g2.NB3t, g2.tiles3, g2.NT3, g2.ntile3, g2.R3, g2.kd3, g2.ku3, g2.in_ptr3_total, g2.in_self3, g2.smem3_d, g2.smem3_u,
                      g2.smem3_in);
     }
     if ((rc = upload(p, perm, &g2.perm))) return fail(rc);

@@ -377,33 +377,69 @@ __global__ void __launch_bounds__(kFlat) k2_xr(Graph2 g, int64_t B, int it, cons
 // table width, and all per-thread predicates / pointers are hoisted out of the row loop.
 
 struct Smem3 {
-  float4* tile;    // (nb, N, CB) chunks: the gathered vector
-  float4* tile2;   // (nb, N, CB) chunks: second operand of the tile (p of p' = r + beta p; the vector A is applied to)
-  float* halo;     // (nb, N)
-  float* halo2;    // (N)
-  float* wself;    // (N)
-  int* ptr;        // (N + 1) in-list offsets (k3_ldrt_lhs only)
-  int* ord;        // (N) row order (k3_ldrt_lhs only)
-  int2* tab;       // entries
+  float4* tile;    // (nb, R3, CB) chunks: the gathered vector
+  float4* tile2;   // (nb, R3, CB) chunks: second operand of the tile (p of p' = r + beta p; the vector A is applied to)
+  float* halo;     // (nb, R3)
+  float* halo2;    // (R3)
+  int* ext;        // (R3) global rows of the tile's external rows (node-tiled plans)
+  float* wself;    // (NT3)
+  int* ptr;        // (NT3 + 1) in-list offsets (k3_ldrt_lhs only)
+  int* ord;        // (NT3) row order (k3_ldrt_lhs only)
+  int2* tab;       // the tile's table entries
   int stride_t;    // float4 between the two tile buffers of the double-buffered mode (0: single buffer)
   int stride_h;
 };
 __device__ __forceinline__ Smem3 carve3(const Graph2& g, float4* base, int CB, bool with_ptr) {
   Smem3 s;
   const int nb = g.db3 ? 2 : 1;
-  s.stride_t = g.db3 ? g.N * CB : 0;
-  s.stride_h = g.db3 ? g.N : 0;
+  s.stride_t = g.db3 ? g.R3 * CB : 0;
+  s.stride_h = g.db3 ? g.R3 : 0;
   s.tile = base;
-  s.tile2 = base + nb * g.N * CB;
-  s.halo = reinterpret_cast<float*>(base + 2 * nb * g.N * CB);
-  s.halo2 = s.halo + nb * g.N;
-  s.wself = s.halo2 + g.N;
-  s.ptr = reinterpret_cast<int*>(s.wself + g.N + ((nb * g.N) & 1));      // keeps the entries 8-byte aligned
-  const int np = with_ptr ? ((g.N + 2) & ~1) : 0;
+  s.tile2 = base + nb * g.R3 * CB;
+  s.halo = reinterpret_cast<float*>(base + 2 * nb * g.R3 * CB);
+  s.halo2 = s.halo + nb * g.R3;
+  s.ext = reinterpret_cast<int*>(s.halo2 + g.R3);
+  s.wself = reinterpret_cast<float*>(s.ext + g.R3);
+  s.ptr = reinterpret_cast<int*>(s.wself + g.NT3 + (((nb + 2) * g.R3 + g.NT3) & 1));      // keeps the entries 8-byte aligned
+  const int np = with_ptr ? ((g.NT3 + 2) & ~1) : 0;
   s.ord = s.ptr + np;
-  s.tab = reinterpret_cast<int2*>(s.ord + (with_ptr ? ((g.N + 1) & ~1) : 0));
+  s.tab = reinterpret_cast<int2*>(s.ord + (with_ptr ? ((g.NT3 + 1) & ~1) : 0));
   return s;
 }
+
+// One unit of work: window b, time tile starting at chunk c0, node tile [n0, n0 + nt) with nh external rows.
+// Single-tile plans: id -> (window, time tile), all nodes.  Node-tiled plans (whole rows): id -> (node tile, window).
+struct Item3 {
+  int b, c0, j, n0, nt, nh;
+};
+__device__ __forceinline__ Item3 item3(const Graph2& g, int64_t B, int id, const int* __restrict__ extp) {
+  Item3 t;
+  if (g.ntile3 > 1) {
+    t.j = id / (int)B;
+    t.b = id - t.j * (int)B;
+    t.c0 = 0;
+    t.n0 = t.j * g.NT3;
+    t.nt = min(g.NT3, g.N - t.n0);
+    t.nh = extp[t.j + 1] - extp[t.j];
+  } else {
+    t.b = id / g.tiles3;
+    t.c0 = (id - t.b * g.tiles3) * (int)blockDim.x;
+    t.j = 0; t.n0 = 0; t.nt = g.N; t.nh = 0;
+  }
+  return t;
+}
+// the work of a CTA: single-tile plans walk the items round-robin (neighbouring time tiles run side by side), node-tiled
+// plans give every CTA a contiguous range, so that its node tile (and the staged table) changes at most once or twice
+__device__ __forceinline__ void range3(const Graph2& g, int total, int* first, int* last, int* stride) {
+  if (g.ntile3 > 1) {
+    const int per = (total + gridDim.x - 1) / gridDim.x;
+    *first = blockIdx.x * per; *last = min(total, *first + per); *stride = 1;
+  } else {
+    *first = blockIdx.x; *last = total; *stride = gridDim.x;
+  }
+}
+// global row of local row n of the tile
+__device__ __forceinline__ int grow3(const Item3& t, const Smem3& s, int n) { return n < t.nt ? t.n0 + n : s.ext[n - t.nt]; }
 
 // asynchronous global -> shared copies (LDGSTS): the whole tile is in flight at once and costs no registers
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
@@ -419,29 +455,29 @@ __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wai
 // ncu on the register-staged version: every dependent round of global loads costs the loaded HBM latency (~2 us);
 // a tile took 3 such rounds.  Here ALL chunks of the tile (and the halo scalars) are issued as cp.async before
 // anything waits: one round per tile.  Each thread then finishes its OWN chunks (p' = r + beta p in place, streamed
-// to HBM), so no barrier is needed between the copy and that pass.
+// to HBM for the tile's own nodes), so no barrier is needed between the copy and that pass.
 // Double-buffered mode (g.db3, one CTA per SM): the copies of the CTA's NEXT tile are issued before the gathers of
 // the current one, so the HBM stream never stops; single-buffered mode (two CTAs per SM): issue, wait, gather.
 template <int SRC>
-__device__ __forceinline__ void tile_issue(const Graph2& g, int tl, int cur, const float* __restrict__ r,
+__device__ __forceinline__ void tile_issue(const Graph2& g, const Item3& t, int cur, const float* __restrict__ r,
                                            const float* __restrict__ p_old, const Smem3& s, bool want_halo) {
   const int CB = blockDim.x, NBt = blockDim.y, tx = threadIdx.x;
-  const int b = tl / g.tiles3, c0 = (tl - b * g.tiles3) * CB;
-  const int c = c0 + tx, cn = c0 + CB;
+  const int c = t.c0 + tx, cn = t.c0 + CB;
   if (c < g.C4) {
     const bool last = want_halo && tx == CB - 1 && cn < g.C4;
-    const size_t w0 = (size_t)b * (size_t)(g.N * g.C4) + c;
+    const size_t w0 = (size_t)t.b * (size_t)(g.N * g.C4) + c;
     const float4* rw = reinterpret_cast<const float4*>(r) + w0;
     const float4* pw = reinterpret_cast<const float4*>(p_old) + w0;
     float4* t1 = s.tile + cur * s.stride_t + tx;
     float4* t2 = s.tile2 + cur * s.stride_t + tx;
     float* h1 = s.halo + cur * s.stride_h;
-    for (int n = threadIdx.y; n < g.N; n += NBt) {
-      cp_async16(t1 + n * CB, rw + n * g.C4);
-      if (SRC == 0) cp_async16(t2 + n * CB, pw + n * g.C4);
-      if (last) {                 // first element of the next tile's first chunk
-        cp_async4(h1 + n, reinterpret_cast<const float*>(rw + n * g.C4 + 1));
-        if (SRC == 0) cp_async4(s.halo2 + n, reinterpret_cast<const float*>(pw + n * g.C4 + 1));
+    for (int n = threadIdx.y; n < t.nt + t.nh; n += NBt) {
+      const int gr = grow3(t, s, n) * g.C4;
+      cp_async16(t1 + n * CB, rw + gr);
+      if (SRC == 0) cp_async16(t2 + n * CB, pw + gr);
+      if (last) {                 // first element of the next time tile's first chunk
+        cp_async4(h1 + n, reinterpret_cast<const float*>(rw + gr + 1));
+        if (SRC == 0) cp_async4(s.halo2 + n, reinterpret_cast<const float*>(pw + gr + 1));
       }
     }
   }
@@ -449,20 +485,19 @@ __device__ __forceinline__ void tile_issue(const Graph2& g, int tl, int cur, con
 }
 
 template <int SRC>
-__device__ __forceinline__ void tile_finish(const Graph2& g, int64_t B, int it, int tl, int cur, float* __restrict__ p_new,
+__device__ __forceinline__ void tile_finish(const Graph2& g, int64_t B, int it, const Item3& t, int cur, float* __restrict__ p_new,
                                             const double* __restrict__ dots, const Smem3& s, bool want_halo) {
   const int CB = blockDim.x, NBt = blockDim.y, tx = threadIdx.x;
-  const int b = tl / g.tiles3, c0 = (tl - b * g.tiles3) * CB;
-  const int c = c0 + tx, cn = c0 + CB;
+  const int c = t.c0 + tx, cn = t.c0 + CB;
   const bool cok = c < g.C4, last = want_halo && tx == CB - 1, hok = cn < g.C4;
-  float4* ow = reinterpret_cast<float4*>(p_new) + (size_t)b * (size_t)(g.N * g.C4) + (cok ? c : 0);
+  float4* ow = reinterpret_cast<float4*>(p_new) + (size_t)t.b * (size_t)(g.N * g.C4) + (cok ? c : 0);
   float4* t1 = s.tile + cur * s.stride_t + tx;
   const float4* t2 = s.tile2 + cur * s.stride_t + tx;
   float* h1 = s.halo + cur * s.stride_h;
   float beta = 0.f;
-  if (SRC == 0) beta = (float)dots[(size_t)(2 * it) * B + b] / (float)dots[(size_t)(2 * it - 2) * B + b];   // ADMM.py:356
+  if (SRC == 0) beta = (float)dots[(size_t)(2 * it) * B + t.b] / (float)dots[(size_t)(2 * it - 2) * B + t.b];   // ADMM.py:356
   cp_async_wait_all();
-  for (int n = threadIdx.y; n < g.N; n += NBt) {
+  for (int n = threadIdx.y; n < t.nt + t.nh; n += NBt) {
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (cok) {
       v = t1[n * CB];
@@ -470,7 +505,7 @@ __device__ __forceinline__ void tile_finish(const Graph2& g, int64_t B, int it, 
         const float4 q = t2[n * CB];
         v = make_float4(v.x + beta * q.x, v.y + beta * q.y, v.z + beta * q.z, v.w + beta * q.w);
       }
-      if (SRC != 2) __stcs(ow + n * g.C4, v);
+      if (SRC != 2 && n < t.nt) __stcs(ow + (t.n0 + n) * g.C4, v);      // external rows are stored by their own tile
     }
     if (SRC == 0 || !cok) t1[n * CB] = v;
     if (last) h1[n] = hok ? (SRC == 0 ? h1[n] + beta * s.halo2[n] : h1[n]) : 0.f;
@@ -506,9 +541,18 @@ __device__ __forceinline__ float4 gather3(const int2* row, int slots, const char
   return acc;
 }
 
-__device__ __forceinline__ void stage_table(const int2* __restrict__ src, int n_ent, int2* dst) {
+// the tile's slice of a forward table, its external-row list and (optionally) the self weights -> shared memory
+__device__ __forceinline__ void stage3(const Graph2& g, const Item3& t, const Smem3& s, const int2* __restrict__ tab, int K,
+                                       const int* __restrict__ extp, const int* __restrict__ ext, bool want_self) {
   const int tid = tid2(), nt = blockDim.x * blockDim.y;
-  for (int k = tid; k < n_ent; k += nt) dst[k] = src[k];
+  const int2* src = tab + (size_t)t.n0 * K;
+  for (int k = tid; k < t.nt * K; k += nt) s.tab[k] = src[k];
+  if (t.nh > 0) {
+    const int* e = ext + extp[t.j];
+    for (int k = tid; k < t.nh; k += nt) s.ext[k] = e[k];
+  }
+  if (want_self)
+    for (int k = tid; k < t.nt; k += nt) s.wself[k] = g.wself_d[t.n0 + k];
 }
 
 // (r, p) -> p', qs = shifted L_d p'   [SRC 2: x0 -> qs]
@@ -519,31 +563,43 @@ __global__ void __launch_bounds__(1024, 1) k3_p_ldr(Graph2 g, int64_t B, int it,
   extern __shared__ float4 s3[];
   const int CB = blockDim.x, NBt = blockDim.y, tx = threadIdx.x;
   const Smem3 s = carve3(g, s3, CB, false);
-  stage_table(g.tab_d, g.N * g.kd3, s.tab);
-  for (int k = tid2(); k < g.N; k += CB * NBt) s.wself[k] = g.wself_d[k];
-  const int total = (int)B * g.tiles3;
+  const int total = (int)B * g.tiles3 * g.ntile3;
   const bool db = g.db3 != 0;
-  int cur = 0;
-  if (db && (int)blockIdx.x < total) tile_issue<SRC>(g, blockIdx.x, 0, r, p_old, s, true);
-  for (int tl = blockIdx.x; tl < total; tl += gridDim.x, cur ^= (db ? 1 : 0)) {
-    const int b = tl / g.tiles3, c0 = (tl - b * g.tiles3) * CB, c = c0 + tx;
+  int first, last, stride;
+  range3(g, total, &first, &last, &stride);
+  int cur = 0, staged = -1;
+  if (first < last) {
+    const Item3 t0 = item3(g, B, first, g.extp_d);
+    stage3(g, t0, s, g.tab_d, g.kd3, g.extp_d, g.ext_d, true);
+    staged = t0.j;
+    if (t0.nh > 0) __syncthreads();                      // the external-row list is read by the copies
+    if (db) tile_issue<SRC>(g, t0, 0, r, p_old, s, true);
+  }
+  for (int tl = first; tl < last; tl += stride, cur ^= (db ? 1 : 0)) {
+    const Item3 t = item3(g, B, tl, g.extp_d);
+    const int c = t.c0 + tx;
     if (!db) {
-      if (tl != (int)blockIdx.x) __syncthreads();          // the previous tile's gathers are done
-      tile_issue<SRC>(g, tl, 0, r, p_old, s, true);
+      if (tl != first) __syncthreads();                  // the previous tile's gathers are done
+      if (t.j != staged) {
+        stage3(g, t, s, g.tab_d, g.kd3, g.extp_d, g.ext_d, true);
+        staged = t.j;
+        __syncthreads();
+      }
+      tile_issue<SRC>(g, t, 0, r, p_old, s, true);
     }
-    tile_finish<SRC>(g, B, it, tl, cur, p_new, dots, s, true);
+    tile_finish<SRC>(g, B, it, t, cur, p_new, dots, s, true);
     __syncthreads();
-    if (db && tl + (int)gridDim.x < total) tile_issue<SRC>(g, tl + gridDim.x, cur ^ 1, r, p_old, s, true);
+    if (db && tl + stride < last) tile_issue<SRC>(g, item3(g, B, tl + stride, g.extp_d), cur ^ 1, r, p_old, s, true);
     if (c >= g.C4) continue;
     const float4* tile = s.tile + cur * s.stride_t;
     const char* mine = reinterpret_cast<const char*>(tile + tx);
     // the element after the thread's chunk: next chunk of the row, or the halo scalar for the tile's last chunk
     const float* nxt_p = tx + 1 < CB ? reinterpret_cast<const float*>(tile + tx + 1) : s.halo + cur * s.stride_h;
     const int nxt_stride = tx + 1 < CB ? CB * 4 : 1;
-    float4* qw = reinterpret_cast<float4*>(qs) + (size_t)b * (size_t)(g.N * g.C4) + c;
-    const int t = 4 * c;
-    const bool v1 = t + 1 < g.T, v2 = t + 2 < g.T, v3 = t + 3 < g.T, v4 = t + 4 < g.T;
-    for (int n = threadIdx.y; n < g.N; n += NBt) {
+    float4* qw = reinterpret_cast<float4*>(qs) + (size_t)t.b * (size_t)(g.N * g.C4) + (size_t)t.n0 * g.C4 + c;
+    const int tt = 4 * c;
+    const bool v1 = tt + 1 < g.T, v2 = tt + 2 < g.T, v3 = tt + 3 < g.T, v4 = tt + 4 < g.T;
+    for (int n = threadIdx.y; n < t.nt; n += NBt) {
       const float4 own = tile[n * CB + tx];
       const float nxt = nxt_p[n * nxt_stride];
       const float ws = s.wself[n];
@@ -568,48 +624,73 @@ __global__ void __launch_bounds__(1024, 1) k3_ldrt_lhs(Graph2 g, int64_t B, cons
   extern __shared__ float4 s3[];
   const int CB = blockDim.x, NBt = blockDim.y, tx = threadIdx.x;
   const Smem3 s = carve3(g, s3, CB, true);
-  stage_table(g.tab_in3, g.in_ptr3_total, s.tab);
-  for (int k = tid2(); k < g.N; k += CB * NBt) s.wself[k] = g.wself_d[k];
-  for (int k = tid2(); k <= g.N; k += CB * NBt) s.ptr[k] = g.in_ptr3[k];
-  for (int k = tid2(); k < g.N; k += CB * NBt) s.ord[k] = g.ord3[k];
-  const int total = (int)B * g.tiles3;
+  const int total = (int)B * g.tiles3 * g.ntile3;
   const bool db = g.db3 != 0;
   const bool self_in = g.in_self3 != 0;
-  // all copies of tile `t` into buffer `k`: qs -> tile, v -> tile2, q[4 c0] = qs[4 c0 - 1] -> halo (q[0] = 0, ADMM.py:176)
-  auto issue = [&](int t, int k) {
-    const int bb = t / g.tiles3, cc0 = (t - bb * g.tiles3) * CB, ccx = cc0 + tx;
+  // the tile's in-list (offsets rebased to the tile), row order, self weights and external rows -> shared memory
+  auto stage = [&](const Item3& t) {
+    const int tid = tid2(), nthr = CB * NBt;
+    const int e0 = g.in_ptr3[t.n0];
+    for (int k = tid; k <= t.nt; k += nthr) s.ptr[k] = g.in_ptr3[t.n0 + k] - e0;
+    for (int k = tid; k < t.nt; k += nthr) { s.ord[k] = g.ord3[t.n0 + k] - t.n0; s.wself[k] = g.wself_d[t.n0 + k]; }
+    const int ne = g.in_ptr3[t.n0 + t.nt] - e0;
+    for (int k = tid; k < ne; k += nthr) s.tab[k] = g.tab_in3[e0 + k];
+    const int* ex = g.ext_in + g.extp_in[t.j];
+    for (int k = tid; k < t.nh; k += nthr) s.ext[k] = ex[k];
+  };
+  // all copies of a tile into buffer `k`: qs -> tile (own + external rows), v -> tile2 (own rows),
+  // q[4 c0] = qs[4 c0 - 1] -> halo (q[0] = 0, ADMM.py:176)
+  auto issue = [&](const Item3& t, int k) {
+    const int ccx = t.c0 + tx;
     float4* t1 = s.tile + k * s.stride_t + tx;
     float4* t2 = s.tile2 + k * s.stride_t + tx;
     float* h1 = s.halo + k * s.stride_h;
     if (ccx < g.C4) {
-      const size_t wq = (size_t)bb * (size_t)(g.N * g.C4) + ccx;
+      const size_t wq = (size_t)t.b * (size_t)(g.N * g.C4) + ccx;
       const float4* qw = reinterpret_cast<const float4*>(qs) + wq;
       const float4* vw = reinterpret_cast<const float4*>(v) + wq;
-      for (int n = threadIdx.y; n < g.N; n += NBt) {
-        cp_async16(t1 + n * CB, qw + n * g.C4);
-        cp_async16(t2 + n * CB, vw + n * g.C4);
-        if (tx == 0 && cc0 > 0) cp_async4(h1 + n, reinterpret_cast<const float*>(qw + n * g.C4) - 1);
+      for (int n = threadIdx.y; n < t.nt + t.nh; n += NBt) {
+        const int gr = grow3(t, s, n) * g.C4;
+        cp_async16(t1 + n * CB, qw + gr);
+        if (n < t.nt) {
+          cp_async16(t2 + n * CB, vw + gr);
+          if (tx == 0 && t.c0 > 0) cp_async4(h1 + n, reinterpret_cast<const float*>(qw + gr) - 1);
+        }
       }
     } else {
-      for (int n = threadIdx.y; n < g.N; n += NBt) t1[n * CB] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int n = threadIdx.y; n < t.nt + t.nh; n += NBt) t1[n * CB] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    if (tx == 0 && cc0 == 0)
-      for (int n = threadIdx.y; n < g.N; n += NBt) h1[n] = 0.f;
+    if (tx == 0 && t.c0 == 0)
+      for (int n = threadIdx.y; n < t.nt; n += NBt) h1[n] = 0.f;
     cp_async_commit();
   };
-  int cur = 0;
-  if (db && (int)blockIdx.x < total) issue(blockIdx.x, 0);
-  for (int tl = blockIdx.x; tl < total; tl += gridDim.x, cur ^= (db ? 1 : 0)) {
-    const int b = tl / g.tiles3, c0 = (tl - b * g.tiles3) * CB, c = c0 + tx;
+  int first, last, stride;
+  range3(g, total, &first, &last, &stride);
+  int cur = 0, staged = -1;
+  if (first < last) {
+    const Item3 t0 = item3(g, B, first, g.extp_in);
+    stage(t0);
+    staged = t0.j;
+    if (t0.nh > 0) __syncthreads();
+    if (db) issue(t0, 0);
+  }
+  for (int tl = first; tl < last; tl += stride, cur ^= (db ? 1 : 0)) {
+    const Item3 t = item3(g, B, tl, g.extp_in);
+    const int c = t.c0 + tx;
     const bool cok = c < g.C4;
-    const size_t w0 = (size_t)b * (size_t)(g.N * g.C4);
+    const size_t w0 = (size_t)t.b * (size_t)(g.N * g.C4) + (size_t)t.n0 * g.C4;
     if (!db) {
-      if (tl != (int)blockIdx.x) __syncthreads();
-      issue(tl, 0);
+      if (tl != first) __syncthreads();
+      if (t.j != staged) {
+        stage(t);
+        staged = t.j;
+        __syncthreads();
+      }
+      issue(t, 0);
     }
     cp_async_wait_all();
     __syncthreads();
-    if (db && tl + (int)gridDim.x < total) issue(tl + gridDim.x, cur ^ 1);
+    if (db && tl + stride < last) issue(item3(g, B, tl + stride, g.extp_in), cur ^ 1);
     const float4* tile = s.tile + cur * s.stride_t;
     const float4* tile2 = s.tile2 + cur * s.stride_t;
     const char* mine = reinterpret_cast<const char*>(tile + tx);
@@ -624,7 +705,7 @@ __global__ void __launch_bounds__(1024, 1) k3_ldrt_lhs(Graph2 g, int64_t B, cons
       float hx[4], tv[4];      // H^T H keeps rows t < t_in (ADMM.py:372-374); pads (t >= T) stay 0
 #pragma unroll
       for (int j = 0; j < 4; ++j) { hx[j] = (xsys && t0 + j < g.t_in) ? 1.f : 0.f; tv[j] = t0 + j < g.T ? 1.f : 0.f; }
-      for (int k = threadIdx.y; k < g.N; k += NBt) {
+      for (int k = threadIdx.y; k < t.nt; k += NBt) {
         const int n = s.ord[k];
         const float4 pv = tile2[n * CB + tx];
         float4 rh;
@@ -659,7 +740,7 @@ __global__ void __launch_bounds__(1024, 1) k3_ldrt_lhs(Graph2 g, int64_t B, cons
         }
       }
     }
-    block_add(dot, slot + b, tid2(), blockDim.x * blockDim.y);
+    block_add(dot, slot + t.b, tid2(), blockDim.x * blockDim.y);
   }
 }
 
@@ -672,28 +753,41 @@ __global__ void __launch_bounds__(1024, 1) k3_lu(Graph2 g, int64_t B, int it, co
   extern __shared__ float4 s3[];
   const int CB = blockDim.x, NBt = blockDim.y, tx = threadIdx.x;
   const Smem3 s = carve3(g, s3, CB, false);
-  stage_table(g.tab_u, g.N * g.ku3, s.tab);
-  const int total = (int)B * g.tiles3;
+  const int total = (int)B * g.tiles3 * g.ntile3;
   const bool db = g.db3 != 0;
-  int cur = 0;
-  if (db && (int)blockIdx.x < total) tile_issue<SRC>(g, blockIdx.x, 0, r, p_old, s, false);
-  for (int tl = blockIdx.x; tl < total; tl += gridDim.x, cur ^= (db ? 1 : 0)) {
-    const int b = tl / g.tiles3, c0 = (tl - b * g.tiles3) * CB, c = c0 + tx;
+  int first, last, stride;
+  range3(g, total, &first, &last, &stride);
+  int cur = 0, staged = -1;
+  if (first < last) {
+    const Item3 t0 = item3(g, B, first, g.extp_u);
+    stage3(g, t0, s, g.tab_u, g.ku3, g.extp_u, g.ext_u, false);
+    staged = t0.j;
+    if (t0.nh > 0) __syncthreads();
+    if (db) tile_issue<SRC>(g, t0, 0, r, p_old, s, false);
+  }
+  for (int tl = first; tl < last; tl += stride, cur ^= (db ? 1 : 0)) {
+    const Item3 t = item3(g, B, tl, g.extp_u);
+    const int c = t.c0 + tx;
     if (!db) {
-      if (tl != (int)blockIdx.x) __syncthreads();
-      tile_issue<SRC>(g, tl, 0, r, p_old, s, false);
+      if (tl != first) __syncthreads();
+      if (t.j != staged) {
+        stage3(g, t, s, g.tab_u, g.ku3, g.extp_u, g.ext_u, false);
+        staged = t.j;
+        __syncthreads();
+      }
+      tile_issue<SRC>(g, t, 0, r, p_old, s, false);
     }
-    tile_finish<SRC>(g, B, it, tl, cur, p_new, dots, s, false);
+    tile_finish<SRC>(g, B, it, t, cur, p_new, dots, s, false);
     __syncthreads();
-    if (db && tl + (int)gridDim.x < total) tile_issue<SRC>(g, tl + gridDim.x, cur ^ 1, r, p_old, s, false);
+    if (db && tl + stride < last) tile_issue<SRC>(g, item3(g, B, tl + stride, g.extp_u), cur ^ 1, r, p_old, s, false);
     const float4* tile = s.tile + cur * s.stride_t;
     const char* mine = reinterpret_cast<const char*>(tile + tx);
     float dot = 0.f;
     if (c < g.C4) {
-      const size_t w0 = (size_t)b * (size_t)(g.N * g.C4);
+      const size_t w0 = (size_t)t.b * (size_t)(g.N * g.C4) + (size_t)t.n0 * g.C4;
       const float4* rw = reinterpret_cast<const float4*>(rhs) + w0 + c;
       float4* ow = reinterpret_cast<float4*>(out) + w0 + c;
-      for (int n = threadIdx.y; n < g.N; n += NBt) {
+      for (int n = threadIdx.y; n < t.nt; n += NBt) {
         float4 rh;
         if (MODE == 1) rh = __ldcs(rw + n * g.C4);
         const float4 pv = tile[n * CB + tx];
@@ -713,7 +807,7 @@ __global__ void __launch_bounds__(1024, 1) k3_lu(Graph2 g, int64_t B, int it, co
         }
       }
     }
-    block_add(dot, slot + b, tid2(), blockDim.x * blockDim.y);
+    block_add(dot, slot + t.b, tid2(), blockDim.x * blockDim.y);
   }
 }
 
@@ -949,15 +1043,27 @@ void stream2_tiling(Graph2* g) {
       for (int k = 0; cands[k] > 0 && k <= 1 - l && g->CB3 == 0; ++k)
         if ((size_t)g->N * (2 * nb * (size_t)cands[k] * 16 + (nb + 2) * 4) + 8 + table <= limits[l]) { g->CB3 = cands[k]; g->one3 = l; }
   }
-  if (g->CB3 > 0) {
-    const int cb = g->CB3;
-    // measured on B200 (PEMS04 graph): 512 threads (2 CTAs/SM) win for tiles of >= 4 chunks (T = 24: 52.3 vs 54.6 ms per
-    // step, T = 288: 37.9 vs 38.4), 256 threads for the 3-chunk tile of T = 12 (55.3 vs 60.3)
-    int threads = g->one3 ? 1024 : cb >= 4 ? 512 : 256;
-    if (const char* e = std::getenv("MGA_S3_THREADS")) threads = std::atoi(e) >= 1024 ? 1024 : std::atoi(e) >= 512 ? 512 : 256;
-    g->NB3t = (cb & (cb - 1)) == 0 ? threads / cb : 32 * std::max(1, (threads / 32) / cb);     // cb * NB3t whole warps
-    g->tiles3 = (g->C4 + cb - 1) / cb;
+  g->NT3 = 0;          // 0: one tile holds all nodes
+  if (force >= 0 && g->CB3 == 0 && g->C4 <= 8) {
+    // node tiles for graphs beyond one CTA's shared memory (whole rows only): NT3 RCM-consecutive nodes per tile
+    // plus the external rows they reference; the plan checks that two CTAs fit an SM once the external rows are known
+    int nt = 256;
+    if (const char* e = std::getenv("MGA_S3_NT")) nt = std::atoi(e);
+    if (nt > 0) { g->CB3 = g->C4; g->NT3 = nt; g->db3 = 0; g->one3 = 0; }
   }
+  stream2_threads3(g);
+}
+
+// block shape of the time-tiled kernels for the chosen tile (CB3, one3)
+void stream2_threads3(Graph2* g) {
+  if (g->CB3 <= 0) return;
+  const int cb = g->CB3;
+  // measured on B200 (PEMS04 graph): 512 threads (2 CTAs/SM) win for tiles of >= 4 chunks (T = 24: 52.3 vs 54.6 ms per
+  // step, T = 288: 37.9 vs 38.4), 256 threads for the 3-chunk tile of T = 12 (55.3 vs 60.3)
+  int threads = g->one3 ? 1024 : cb >= 4 ? 512 : 256;
+  if (const char* e = std::getenv("MGA_S3_THREADS")) threads = std::atoi(e) >= 1024 ? 1024 : std::atoi(e) >= 512 ? 512 : 256;
+  g->NB3t = (cb & (cb - 1)) == 0 ? threads / cb : 32 * std::max(1, (threads / 32) / cb);     // cb * NB3t whole warps
+  g->tiles3 = (g->C4 + cb - 1) / cb;
 }
 
 bool stream2_eligible(const mga_plan* p, int dtype) {
@@ -1016,7 +1122,7 @@ static int cg2(mga_plan* p, int system, const mga_params* m, const float* rhs, c
   if (g.CB3 > 0) {
     // time-tiled shared-memory kernels: p update fused into the operator kernel, p ping-ponged
     const dim3 blk3(g.CB3, g.NB3t);
-    const int total = (int)B * g.tiles3;
+    const int total = (int)B * g.tiles3 * g.ntile3;
     float *p_old = w.p, *p_new = w.p2;
     int rc3 = MGA_OK;
 #define MGA_K3_LAUNCH(kern, smem, ...)                                                    \
