@@ -74,8 +74,10 @@ typedef enum {
   MGA_MODE_STREAMING = 1,/* state in HBM/L2, one fused kernel per CG phase */
   MGA_MODE_RESIDENT = 2, /* one CTA per window, CG vectors in registers, gathered vectors in SMEM */
   MGA_MODE_STREAMING_POINT = 3 /* streaming, always the general one-thread-per-lattice-point kernels (every dtype,
-                                  mask, ablation, temporal variant); MGA_MODE_STREAMING picks the chunked node-major
-                                  kernels when the call is fp32, forecasting, fixed-iteration, ablation None */
+                                  mask, ablation, temporal variant); MGA_MODE_STREAMING picks the node-major
+                                  kernels (time-tiled shared-memory CG kernels for graphs or node tiles that fit a
+                                  CTA, L1-gather kernels otherwise) when the call is fp32, forecasting,
+                                  fixed-iteration, ablation None */
 } mga_mode;
 
 /* The graph tensors ADMM_algorithm.__init__ leaves behind (ADMM.py:25-52).  HOST pointers; the
