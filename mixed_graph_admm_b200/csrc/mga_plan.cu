@@ -723,7 +723,24 @@ int mga_admm_solve_host(mga_plan* p, const mga_params* prm, const void* y_host, 
     chunk = std::max<int64_t>(1, std::min<int64_t>(B, (B + parts - 1) / parts));
   }
   chunk = std::min(chunk, B);
-  const int64_t nchunk = (B + chunk - 1) / chunk;
+  // chunk sizes: equal parts, or an explicit plan "n1,n2,..." (MGA_HOST_PLAN, must add up to B) for experiments
+  std::vector<int64_t> sizes;
+  if (const char* e = std::getenv("MGA_HOST_PLAN")) {
+    int64_t sum = 0;
+    for (const char* q = e; *q;) {
+      char* end = nullptr;
+      const long v = std::strtol(q, &end, 10);
+      if (end == q || v <= 0) { sizes.clear(); break; }
+      sizes.push_back(v);
+      sum += v;
+      q = *end == ',' ? end + 1 : end;
+    }
+    if (sum != B) sizes.clear();
+  }
+  if (sizes.empty())
+    for (int64_t b0 = 0; b0 < B; b0 += chunk) sizes.push_back(std::min(chunk, B - b0));
+  chunk = *std::max_element(sizes.begin(), sizes.end());
+  const int64_t nchunk = (int64_t)sizes.size();
   const size_t y_win = (size_t)y_rows * g.N * es, x_win = (size_t)g.T * g.N * es;
   const size_t diag_n = (size_t)n_outer * MGA_DIAG_COLS, dx_n = (size_t)n_outer * g.T * g.N;
   // device staging: 2 y-slots, 2 x-slots, diag + dx_sum accumulators
@@ -755,9 +772,11 @@ int mga_admm_solve_host(mga_plan* p, const mga_params* prm, const void* y_host, 
     MGA_CUDA(cudaEventRecord(diag_ready, s_run[0]));
     if (s_run[1] != s_run[0]) MGA_CUDA(cudaStreamWaitEvent(s_run[1], diag_ready, 0));
   }
+  int64_t b_next = 0;
   for (int64_t c = 0; c < nchunk; ++c) {
     const int slot = (int)(c & 1);
-    const int64_t b0 = c * chunk, nb = std::min(chunk, B - b0);
+    const int64_t b0 = b_next, nb = sizes[c];
+    b_next += nb;
     char* dy = base + off_y + (size_t)slot * chunk * y_win;
     char* dx = base + off_x + (size_t)slot * chunk * x_win;
     if (c >= 2) MGA_CUDA(cudaStreamWaitEvent(s_up, run_done[slot], 0));
