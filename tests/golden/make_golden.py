@@ -161,6 +161,12 @@ def main():
               dict(use_kNN=False, u_sigma=50, d_sigma=50, t_in=t_in, T=T), fixed(2, 4))
     make_case("tiny_c2_tol", gi, ai, synth.signals(1, t_in, N, seed=2, smooth=True).repeat(1, 1, 1, 2)
               * torch.tensor([1.0, 0.5]), ctor, {"max_ADMM_iter": 4})
+    # 9c. mask mode with two channels (B = 1, see 9.)
+    ymc = torch.rand(1, T, N, 2, generator=torch.Generator().manual_seed(30))
+    maskc = (torch.rand(1, T, N, 2, generator=torch.Generator().manual_seed(31)) >= 0.4).float()
+    maskc[:, 0] = 1
+    maskc[:, -1] = 1
+    make_case("tiny_c2_mask", gi, ai, ymc * maskc, ctor, fixed(2, 4), mask=maskc)
     # 10. PEMS08-shaped (BASELINE.json configs[0]); 4 of the 32 windows are kept
     N, k, T, t_in = 170, 6, 12, 6
     gi = synth.road_graph(N, 1.7, seed=8, isolate_pair=True)
