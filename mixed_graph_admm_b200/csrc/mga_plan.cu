@@ -743,8 +743,10 @@ int mga_admm_solve_host(mga_plan* p, const mga_params* prm, const void* y_host, 
   const int64_t nchunk = (int64_t)sizes.size();
   const size_t y_win = (size_t)y_rows * g.N * es, x_win = (size_t)g.T * g.N * es;
   const size_t diag_n = (size_t)n_outer * MGA_DIAG_COLS, dx_n = (size_t)n_outer * g.T * g.N;
-  // device staging: 2 y-slots, 2 x-slots, diag + dx_sum accumulators
-  size_t off_y = 0, off_x = 2 * (size_t)chunk * y_win, off_d = off_x + 2 * (size_t)chunk * x_win;
+  // device staging: kSlots y-slots, kSlots x-slots, diag + dx_sum accumulators.  Three slots: with four chunks the
+  // upload of chunk 2 no longer waits for chunk 0's solve (its y slot), so all uploads run back to back
+  constexpr int kSlots = 3;
+  size_t off_y = 0, off_x = kSlots * (size_t)chunk * y_win, off_d = off_x + kSlots * (size_t)chunk * x_win;
   off_d = (off_d + 255) & ~(size_t)255;
   size_t total = off_d + (diag_n + dx_n) * sizeof(double);
   rc = ensure_workspace(p, p->ws_host_io, total);
@@ -758,10 +760,10 @@ int mga_admm_solve_host(mga_plan* p, const mga_params* prm, const void* y_host, 
                        resident_eligible(p, dtype);
   cudaStream_t s_up = p->io_streams[0], s_dn = p->io_streams[3];
   cudaStream_t s_run[2] = {p->io_streams[1], can_res ? p->io_streams[2] : p->io_streams[1]};
-  cudaEvent_t* up_done = &p->io_events[0];    // [2] y slot filled
-  cudaEvent_t* run_done = &p->io_events[2];   // [2] x slot filled (= y slot consumed)
-  cudaEvent_t* x_free = &p->io_events[4];     // [2] x slot drained
-  cudaEvent_t diag_ready = p->io_events[6];
+  cudaEvent_t* up_done = &p->io_events[0];    // [kSlots] y slot filled
+  cudaEvent_t* run_done = &p->io_events[3];   // [kSlots] x slot filled (= y slot consumed)
+  cudaEvent_t* x_free = &p->io_events[6];     // [kSlots] x slot drained
+  cudaEvent_t diag_ready = p->io_events[9];
   double* d_diag = reinterpret_cast<double*>(base + off_d);
   double* d_dx = d_diag + diag_n;
   mga_admm_outputs outs{};
@@ -774,24 +776,24 @@ int mga_admm_solve_host(mga_plan* p, const mga_params* prm, const void* y_host, 
   }
   int64_t b_next = 0;
   for (int64_t c = 0; c < nchunk; ++c) {
-    const int slot = (int)(c & 1);
+    const int slot = (int)(c % kSlots), rs = (int)(c & 1);      // staging slot, run stream
     const int64_t b0 = b_next, nb = sizes[c];
     b_next += nb;
     char* dy = base + off_y + (size_t)slot * chunk * y_win;
     char* dx = base + off_x + (size_t)slot * chunk * x_win;
-    if (c >= 2) MGA_CUDA(cudaStreamWaitEvent(s_up, run_done[slot], 0));
+    if (c >= kSlots) MGA_CUDA(cudaStreamWaitEvent(s_up, run_done[slot], 0));
     MGA_CUDA(cudaMemcpyAsync(dy, static_cast<const char*>(y_host) + (size_t)b0 * y_win, (size_t)nb * y_win,
                              cudaMemcpyHostToDevice, s_up));
     MGA_CUDA(cudaEventRecord(up_done[slot], s_up));
-    MGA_CUDA(cudaStreamWaitEvent(s_run[slot], up_done[slot], 0));
-    if (c >= 2) MGA_CUDA(cudaStreamWaitEvent(s_run[slot], x_free[slot], 0));
+    MGA_CUDA(cudaStreamWaitEvent(s_run[rs], up_done[slot], 0));
+    if (c >= kSlots) MGA_CUDA(cudaStreamWaitEvent(s_run[rs], x_free[slot], 0));
     // diagnostics accumulate across chunks (the kernels add into diag / dx_sum)
-    p->res_slot = slot;
+    p->res_slot = rs;
     rc = mga_admm_solve(p, prm, dy, y_rows, nullptr, dx, nb, dtype, n_outer, max_cg, -1.0, -1.0, t_mean, t_var,
-                        want_diag | 2, &outs, mode, s_run[slot]);
+                        want_diag | 2, &outs, mode, s_run[rs]);
     p->res_slot = 0;
     if (rc) { cudaDeviceSynchronize(); return rc; }
-    MGA_CUDA(cudaEventRecord(run_done[slot], s_run[slot]));
+    MGA_CUDA(cudaEventRecord(run_done[slot], s_run[rs]));
     MGA_CUDA(cudaStreamWaitEvent(s_dn, run_done[slot], 0));
     MGA_CUDA(cudaMemcpyAsync(static_cast<char*>(x_host) + (size_t)b0 * x_win, dx, (size_t)nb * x_win,
                              cudaMemcpyDeviceToHost, s_dn));
