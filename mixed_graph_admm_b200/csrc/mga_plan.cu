@@ -306,8 +306,9 @@ int mga_plan_create(const mga_graph_desc* d, int device, mga_plan** out) {
       // stages, besides them, the EXTERNAL rows their table entries point to (RCM keeps those few: ~90 per 256-512
       // nodes on the 20 000-node road graph).  Table entries hold LOCAL row offsets: own rows first, then the tile's
       // external rows in ascending order.  Single-tile plans: NT3 = N, no external rows.
-      const int NT = g2.NT3 > 0 ? std::min(g2.NT3, N) : N;
+      int NT = g2.NT3 > 0 ? std::min(g2.NT3, N) : N;
       const int ntile = (N + NT - 1) / NT;
+      NT = (N + ntile - 1) / ntile;                 // balanced tiles: 883 nodes -> 4 x 221, not 3 x 256 + 115
       g2.NT3 = NT;
       g2.ntile3 = ntile;
       std::vector<float> wsd(N, 0.f);

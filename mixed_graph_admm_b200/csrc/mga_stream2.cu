@@ -408,16 +408,18 @@ __device__ __forceinline__ Smem3 carve3(const Graph2& g, float4* base, int CB, b
 }
 
 // One unit of work: window b, time tile starting at chunk c0, node tile [n0, n0 + nt) with nh external rows.
-// Single-tile plans: id -> (window, time tile), all nodes.  Node-tiled plans (whole rows): id -> (node tile, window).
+// Single-tile plans: id -> (window, time tile), all nodes.  Node-tiled plans: id -> (node tile, window, time tile).
 struct Item3 {
   int b, c0, j, n0, nt, nh;
 };
 __device__ __forceinline__ Item3 item3(const Graph2& g, int64_t B, int id, const int* __restrict__ extp) {
   Item3 t;
   if (g.ntile3 > 1) {
-    t.j = id / (int)B;
-    t.b = id - t.j * (int)B;
-    t.c0 = 0;
+    const int per = (int)B * g.tiles3;          // node-tile major: (node tile, window, time tile)
+    t.j = id / per;
+    const int rem = id - t.j * per;
+    t.b = rem / g.tiles3;
+    t.c0 = (rem - t.b * g.tiles3) * (int)blockDim.x;
     t.n0 = t.j * g.NT3;
     t.nt = min(g.NT3, g.N - t.n0);
     t.nh = extp[t.j + 1] - extp[t.j];
@@ -1044,12 +1046,13 @@ void stream2_tiling(Graph2* g) {
         if ((size_t)g->N * (2 * nb * (size_t)cands[k] * 16 + (nb + 2) * 4) + 8 + table <= limits[l]) { g->CB3 = cands[k]; g->one3 = l; }
   }
   g->NT3 = 0;          // 0: one tile holds all nodes
-  if (force >= 0 && g->CB3 == 0 && g->C4 <= 8) {
-    // node tiles for graphs beyond one CTA's shared memory (whole rows only): NT3 RCM-consecutive nodes per tile
-    // plus the external rows they reference; the plan checks that two CTAs fit an SM once the external rows are known
+  if (force >= 0 && g->CB3 == 0) {
+    // node tiles for graphs beyond one CTA's shared memory: NT3 RCM-consecutive nodes per tile plus the external rows
+    // they reference, over the whole row or 8-chunk time tiles; the plan checks that two CTAs fit an SM once the
+    // external rows are known
     int nt = 256;
     if (const char* e = std::getenv("MGA_S3_NT")) nt = std::atoi(e);
-    if (nt > 0) { g->CB3 = g->C4; g->NT3 = nt; g->db3 = 0; g->one3 = 0; }
+    if (nt > 0) { g->CB3 = std::min(g->C4, force > 0 ? force : 8); g->NT3 = nt; g->db3 = 0; g->one3 = 0; }
   }
   stream2_threads3(g);
 }

@@ -460,7 +460,7 @@ def test_skip_connection_line_graph_against_oracle(N, k, T, skip, B, mode):
 
 
 @pytest.mark.parametrize("N,k,T,B", [(100, 4, 50, 3), (307, 6, 100, 2), (400, 6, 37, 2), (64, 3, 26, 5), (500, 6, 41, 2),
-                                     (600, 6, 33, 2), (700, 5, 30, 2)])
+                                     (600, 6, 33, 2), (700, 5, 30, 2), (900, 6, 50, 2)])
 def test_long_windows_odd_lengths_against_oracle(N, k, T, B):
     """T > 24 (beyond the resident kernel) with lengths that are not multiples of 4 or 12: the chunked streaming
     kernels' padded last chunk and the general kernels, both against the oracle.  N <= 360: time-tiled shared-memory
