@@ -1041,8 +1041,14 @@ void stream2_tiling(Graph2* g) {
     if (const char* e = std::getenv("MGA_S3_ONE")) one = one && std::atoi(e) != 0;
     const size_t limits[2] = {g->db3 ? (size_t)226 * 1024 : (size_t)(228 * 1024) / 2 - 1024, (size_t)226 * 1024};
     g->one3 = 0;
-    for (int l = 0; l < (one ? 2 : 1) && g->CB3 == 0; ++l)
-      for (int k = 0; cands[k] > 0 && k <= 1 - l && g->CB3 == 0; ++k)
+    // MGA_S3_SINGLE: 0 = node tiles only, 1 (default) = one tile of all nodes only with 8-chunk (or whole-row) tiles at two
+    // CTAs per SM, 2 = also 4-chunk tiles and the one-CTA-per-SM mode.  Measured against node tiles x 8-chunk time tiles:
+    // N = 450, T = 96: 4-chunk single tile 42.5 ms per step, two node tiles of 225: 40.0; N = 600: one CTA per SM 53.0,
+    // three node tiles of 200: 52.7 - so everything beyond N ~ 360 goes to node tiles.
+    int single = 1;
+    if (const char* e = std::getenv("MGA_S3_SINGLE")) single = std::atoi(e);
+    for (int l = 0; l < (one && single == 2 ? 2 : 1) && single > 0 && g->CB3 == 0; ++l)
+      for (int k = 0; cands[k] > 0 && k <= 1 - l && k < single && g->CB3 == 0; ++k)
         if ((size_t)g->N * (2 * nb * (size_t)cands[k] * 16 + (nb + 2) * 4) + 8 + table <= limits[l]) { g->CB3 = cands[k]; g->one3 = l; }
   }
   g->NT3 = 0;          // 0: one tile holds all nodes

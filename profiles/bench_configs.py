@@ -24,6 +24,7 @@ CONFIGS = {
     "large20k": (20000, 8, 24, 64, 1.1, 9),
     "pems07_t288": (883, 6, 288, 96, 1.1, 7),      # PEMS07-sized graph, one day at 5 min
     "n600_t96": (600, 6, 96, 512, 1.1, 6),
+    "n450_t96": (450, 6, 96, 512, 1.1, 5),
 }
 
 ap = argparse.ArgumentParser()
