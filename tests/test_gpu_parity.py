@@ -511,6 +511,26 @@ def test_time_tiled_kernel_options_against_oracle(env, monkeypatch):
     np.testing.assert_allclose(blk.p_res_list[-1], tr.p_res[-1], rtol=2e-5, atol=1e-7)
 
 
+@pytest.mark.parametrize("N,T", [(600, 33), (450, 41)])
+def test_single_tile_modes_kept_behind_the_knob(N, T, monkeypatch):
+    """MGA_S3_SINGLE=2 selects the single-tile modes that node tiles replaced by default: one 1024-thread CTA per SM
+    (N = 600) and 4-chunk tiles (N = 450).  Still the oracle's result."""
+    from mixed_graph_admm_b200 import synth
+    from mixed_graph_admm_b200.ADMM import ADMM_algorithm
+    from oracle import admm_oracle as O
+    monkeypatch.setenv("MGA_S3_SINGLE", "2")
+    t_in, B, k = T // 2, 2, 6
+    gi = synth.road_graph(N, 1.2, seed=N)
+    y = synth.signals(B, t_in, N, seed=T)
+    blk = ADMM_algorithm(gi, synth.admm_info(N), use_kNN=True, k=k, u_sigma=50, d_sigma=50, t_in=t_in, T=T, mode="streaming")
+    blk.max_ADMM_iter, blk.max_CG_iter, blk.CG_tol, blk.ADMM_tol = 2, 8, -1.0, -1.0
+    x = blk.combined_loop(y.cuda(), print_info=False).cpu()
+    og = O.OracleGraph(nbr=blk.connect_list, u_w=blk.u_ew, d_w=blk.d_ew)
+    prm = O.OracleParams(**synth.admm_info(N), t_in=t_in, T=T)
+    tr = O.admm_combined(og, prm, y, max_admm_iter=2, max_cg_iter=8, cg_tol=-1.0, admm_tol=-1.0)
+    assert rel_err(x, tr.x) <= 1e-5 and max_rel(x, tr.x) <= 2e-5, rel_err(x, tr.x)
+
+
 @pytest.mark.parametrize("mode", ["resident", "streaming"])
 def test_repeated_runs_are_bitwise_identical(mode):
     """compute-sanitizer is not available on the pool, so races in the shared-memory staging would have to show
