@@ -5,20 +5,29 @@
 
 One "step" = one pass of the hot path (the whole of ``combined_loop``: 5 outer ADMM iterations x
 3 CG solves x 10 iterations, diagnostics on) over one batch of synthetic PEMS04-shaped windows
-(307 nodes, kNN k=6, T=12, t_in=6, fp32) — BASELINE.json configs[1].  Windows are independent, so
-N GPUs each take their own batch of ``--batch`` windows (weak scaling, no data-path collective).
+(307 nodes, kNN k=6, T=12, t_in=6, fp32).
+
+  N = 1   BASELINE.json configs[1]: ONE batch of 1024 windows on one B200.
+  N > 1   BASELINE.json configs[2]: ONE global batch of 65 536 windows sharded over the N ranks (65 536 / N windows per
+          GPU, `parallel.solve_sharded`): no collective on the data path, one NCCL all-reduce of the diagnostics
+          partial sums per solve (inside the timed regions).
 
 Prints ONE JSON line (rank 0):
-  value      windows/s, whole job, inputs resident in HBM, C-ABI call ``mga_admm_solve``
-  e2e        windows/s through the public API ``ADMM_algorithm.combined_loop`` with HOST (pinned)
-             buffers: host->device copy of y, solve, device->host copy of x inside the timed region
-  roofline   the dominant kernel against the measured HBM peak (algorithmic bytes: see DESIGN.md §5)
+  value      windows/s, whole job, inputs resident in HBM, C-ABI call ``mga_admm_solve`` (+ the diagnostics all-reduce)
+  e2e        windows/s through the public API with HOST (pinned) buffers: ``ADMM_algorithm.combined_loop(y_cpu)``
+             (N > 1: ``parallel.solve_sharded``) — host->device copy of y, solve, device->host copy of x, the CG
+             coefficients and the diagnostics inside the timed region
+  roofline   the dominant kernel against the roofline that bounds it (resident kernel: the shared-memory pipe)
   cpu_baseline   the oracle port of the reference's torch-CPU path on the host cores (bounded sample)
+  probes     (N = 1) the other BASELINE.json configs on the same clock: T = 288 / B = 256 and 20 000 nodes / k = 8 /
+             T = 24 / B = 64 (streaming kernels vs the HBM roofline, each with a 2-window parity sample against the
+             oracle), the 65 536-window batch on one GPU, and the fused CG iteration (``cg_iter``)
 """
 from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import subprocess
 import sys
@@ -32,8 +41,12 @@ import torch  # noqa: E402
 
 N_NODES, K_NN, T_LEN, T_IN = 307, 6, 12, 6
 N_OUTER, N_CG = 5, 10
+GLOBAL_BATCH = 65536        # BASELINE.json configs[2]
 WORKLOAD = "PEMS04-shaped synthetic: 307 nodes, kNN k=6, T=12, t_in=6, full mixed graph (GLR+DGTV+DGLR), " \
            "5 outer x 3 CG x 10 iters, fp32"
+METRIC = "ADMM windows/sec (PEMS04 shape)"
+SM_COUNT, SMEM_BYTES_PER_CLK = 148, 128
+RESIDENT_COUNTERS = os.path.join("profiles", "r02_resident_counters.json")
 
 
 def algorithmic_bytes_per_point(n_outer=N_OUTER, n_cg=N_CG, t_in=T_IN, T=T_LEN):
@@ -68,36 +81,44 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
             self.proc = None
+        return self
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def mark(self):
+        return time.perf_counter()
+
+    def stop(self, t0=None, t1=None):
+        """Median SM clock over the samples taken in [t0, t1] (all samples when the window caught none)."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.12)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit())
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        rows = [r for ts, r in self.rows if len(r) >= 9 and (t0 is None or t0 <= ts <= t1 + 0.06)]
+        if not rows:
+            rows = [r for _, r in self.rows if len(r) >= 9]
+        sm = sorted(float(r[1]) for r in rows if r[1].replace(".", "").isdigit())
+        mx = [float(r[2]) for r in rows if r[2].replace(".", "").isdigit()]
+        pw = [float(r[3]) for r in rows if r[3].replace(".", "").isdigit()]
         reasons = set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            if len(r) >= 9:
-                for nm, v in zip(names, r[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(nm)
+        for r in rows:
+            for nm, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
 def measured_peaks():
@@ -109,22 +130,22 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def build_problem(batch, seed, device=None, mode="auto"):
+def build_problem(batch, seed, device=None, mode="auto", N=N_NODES, k=K_NN, T=T_LEN, t_in=T_IN, ratio=1.1, gseed=4):
     from mixed_graph_admm_b200 import synth
     from mixed_graph_admm_b200.ADMM import ADMM_algorithm
-    gi = synth.road_graph(N_NODES, 1.1, seed=4)
-    blk = ADMM_algorithm(gi, synth.admm_info(N_NODES), use_kNN=True, k=K_NN, u_sigma=50, d_sigma=50, t_in=T_IN,
-                         T=T_LEN, device=device, mode=mode)
+    gi = synth.road_graph(N, ratio, seed=gseed)
+    blk = ADMM_algorithm(gi, synth.admm_info(N), use_kNN=True, k=k, u_sigma=50, d_sigma=50, t_in=t_in, T=T,
+                         device=device, mode=mode)
     blk.max_ADMM_iter, blk.max_CG_iter, blk.CG_tol, blk.ADMM_tol = N_OUTER, N_CG, -1.0, -1.0
-    y = synth.signals(batch, T_IN, N_NODES, seed=seed)
+    y = synth.signals(batch, t_in, N, seed=seed)
     return blk, y
 
 
-def oracle_problem(blk):
+def oracle_problem(blk, N=N_NODES, T=T_LEN, t_in=T_IN):
     from mixed_graph_admm_b200 import synth
     from oracle import admm_oracle as O
     og = O.OracleGraph(nbr=blk.connect_list, u_w=blk.u_ew, d_w=blk.d_ew)
-    prm = O.OracleParams(**synth.admm_info(N_NODES), t_in=T_IN, T=T_LEN)
+    prm = O.OracleParams(**synth.admm_info(N), t_in=t_in, T=T)
     return O, og, prm
 
 
@@ -151,9 +172,19 @@ def time_oracle(blk, y, budget_s=None):
             return done / t_all, t_all, done
 
 
+def loaded_product_libraries():
+    """Shared objects of the product mapped into this process (the reference arm must show none)."""
+    try:
+        with open("/proc/self/maps") as f:
+            return sorted({ln.split()[-1] for ln in f if "libmga" in ln})
+    except OSError:
+        return []
+
+
 def run_reference(args, rank, world):
-    """--impl reference: the reference's own CPU implementation of the path (its oracle port —
-    the Python reference cannot travel to the GPU box) on the host cores; rank 0 only."""
+    """--impl reference: the reference's own CPU implementation of the path (its oracle port — the Python reference
+    cannot travel to the GPU box) on the host cores; rank 0 only.  Nothing of the product is loaded: the kNN tables
+    come from the pure-Python search (`native=False`), the solve is the torch-CPU oracle."""
     if rank != 0:
         return
     sample = 8 * CPU_BATCH          # windows per step (~1.2 s on 16 host threads)
@@ -167,19 +198,26 @@ def run_reference(args, rank, world):
     tot = sum(times)
     val = sample * len(times) / tot
     cores = torch.get_num_threads()
-    line = {"impl": "reference", "metric": "ADMM windows/sec (PEMS04 shape)", "value": val, "unit": "windows/s",
+    batch = 1024 if world == 1 else GLOBAL_BATCH
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "windows/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch_per_step": sample},
+            "higher_is_better": True, "scaling": "weak" if world == 1 else "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "global_batch": batch,
+                       "sample": f"each step solves {sample} windows of that workload in batches of {CPU_BATCH} (the batch "
+                                 "size at which the reference's torch path is fastest per window); windows are "
+                                 "independent, so windows/s does not depend on how many of the batch are solved"},
+            "same_config": "same workload and metric; the CPU arm solves a bounded sample of the batch per step",
             "cpu_baseline": {"value": val, "unit": "windows/s", "cores": cores, "kind": "port",
                              "sample": f"{sample} windows of the workload per step in batches of {CPU_BATCH}, torch-CPU "
                                        f"oracle port (bit-identical to the reference), {cores} threads"},
-            "e2e": {"value": val, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "e2e": {"value": val, "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "product_libraries_loaded": loaded_product_libraries()}
     print(json.dumps(line), flush=True)
 
 
 def build_problem_cpu(batch):
-    """Graph tables without touching CUDA (for the reference arm)."""
+    """Graph tables without touching CUDA or libmga.so (for the reference arm)."""
     from mixed_graph_admm_b200 import synth
     from mixed_graph_admm_b200 import utils as U
 
@@ -188,11 +226,94 @@ def build_problem_cpu(batch):
 
     gi = synth.road_graph(N_NODES, 1.1, seed=4)
     t = Tables()
-    nodes, dists = U.k_nearest_neighbors(N_NODES, gi["u_edges"], gi["u_dist"], K_NN)
+    nodes, dists = U.k_nearest_neighbors(N_NODES, gi["u_edges"], gi["u_dist"], K_NN, native=False)
     t.connect_list = nodes.to(torch.int64)
     t.u_ew = U.expand_time_dimension(U.undirected_graph_from_distance(t.connect_list, dists, u_sigma=50), T_LEN)
     t.d_ew = U.expand_time_dimension(U.directed_graph_from_distance(t.connect_list, dists, d_sigma=50), T_LEN - 1)
     return t, synth.signals(batch, T_IN, N_NODES, seed=0)
+
+
+class DeviceSolve:
+    """``mga_admm_solve`` on device-resident buffers for one problem (the C-ABI call behind ``value`` and the probes)."""
+
+    def __init__(self, blk, y_dev, mode, dev):
+        import ctypes as C
+
+        from mixed_graph_admm_b200 import _cabi
+        from mixed_graph_admm_b200.ADMM import _regression_consts
+        self.C, self.cabi, self.L = C, _cabi, _cabi.lib()
+        self.blk, self.y, self.mode, self.dev = blk, y_dev, mode, dev
+        self.plan, self.prm = blk._plan(), blk._params()
+        B = y_dev.size(0)
+        self.B = B
+        self.x = torch.empty((B, blk.T, blk.n_nodes, 1), dtype=torch.float32, device=dev)
+        self.diag = torch.zeros((N_OUTER * _cabi.DIAG_COLS + N_OUTER * blk.T * blk.n_nodes,), dtype=torch.float64, device=dev)
+        self.outs = _cabi.AdmmOutputs()
+        self.outs.diag = self.diag.data_ptr()
+        self.outs.dx_sum = self.diag.data_ptr() + 8 * N_OUTER * _cabi.DIAG_COLS
+        self.tm, self.tv = _regression_consts(blk.t_in)
+        self.stream = torch.cuda.current_stream(dev)
+
+    def __call__(self):
+        C, c = self.C, self.cabi
+        c.check(self.L.mga_admm_solve(self.plan.handle, C.byref(self.prm), c.ptr(self.y), self.blk.t_in, None, c.ptr(self.x),
+                                      self.B, c.MGA_F32, N_OUTER, N_CG, -1.0, -1.0, self.tm, self.tv, 1, C.byref(self.outs),
+                                      c.MODE[self.mode], self.stream.cuda_stream))
+
+
+def timed_passes(fn, passes, flush, stream, after=None):
+    """Device time of `passes` calls of `fn`, one CUDA-event pair per call on the launching stream, L2 flushed between
+    calls (outside the event pairs).  `after` (e.g. the diagnostics all-reduce) runs inside the pair.  Returns ms list."""
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(passes)]
+    for s in range(passes):
+        flush.fill_(s & 0xff)
+        ev[s][0].record(stream)
+        fn()
+        if after is not None:
+            after()
+        ev[s][1].record(stream)
+    torch.cuda.synchronize()
+    return [a.elapsed_time(b) for a, b in ev]
+
+
+def probe_config(name, N, k, T, B, ratio, gseed, dev, flush, peak, steps=6):
+    """One of the other BASELINE.json configs, device-resident, streaming kernels: windows/s, algorithmic GB/s against the
+    HBM roofline, clocks during the run, and parity of the first 2 windows against the CPU oracle."""
+    t_in = T // 2
+    t0 = time.perf_counter()
+    blk, y_host = build_problem(B, seed=0, device=dev, mode="auto", N=N, k=k, T=T, t_in=t_in, ratio=ratio, gseed=gseed)
+    y_dev = y_host.to(dev)
+    solve = DeviceSolve(blk, y_dev, "auto", dev)
+    setup_s = time.perf_counter() - t0
+    for _ in range(3):
+        solve()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(dev.index or 0).start()
+    l0 = solve.L.mga_launch_count()
+    ta = sampler.mark()
+    ms = timed_passes(solve, steps, flush, solve.stream)
+    tb = sampler.mark()
+    launches = (solve.L.mga_launch_count() - l0) // steps
+    clocks = sampler.stop(ta, tb)
+    ms_step = sum(ms) / len(ms)
+    alg = algorithmic_bytes_per_point(t_in=t_in, T=T) * T * N * B
+    gbs = alg / (ms_step * 1e-3) / 1e9
+    # parity sample: the first 2 windows against the oracle (the reference's torch-CPU arithmetic)
+    from oracle import admm_oracle as O
+    _, og, pr = oracle_problem(blk, N=N, T=T, t_in=t_in)
+    tr = O.admm_combined(og, pr, y_host[:2].contiguous(), max_admm_iter=N_OUTER, max_cg_iter=N_CG, cg_tol=-1.0, admm_tol=-1.0)
+    xs = solve.x[:2].cpu().double()
+    err = ((xs - tr.x.double()).norm() / tr.x.double().norm()).item()
+    resident = bool(solve.L.mga_plan_resident_eligible(solve.plan.handle, 0))
+    out = {"config": name, "N": N, "k": k, "T": T, "t_in": t_in, "batch": B, "kernel_mode": "resident" if resident else "streaming",
+           "ms_per_step": ms_step, "windows_per_s": B / (ms_step * 1e-3), "steps": steps, "launches_per_step": int(launches),
+           "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s", "frac": gbs / peak,
+                        "bytes": "algorithmic bytes of the whole step (algorithmic_bytes_per_point) / step time"},
+           "parity_vs_oracle_rel_l2": err, "parity_sample": "first 2 windows, x after 5 outer iterations",
+           "clocks": clocks, "setup_s": setup_s}
+    del solve, blk, y_dev
+    torch.cuda.empty_cache()
+    return out
 
 
 def main():
@@ -201,11 +322,13 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=1024, help="windows per GPU per step")
+    ap.add_argument("--batch", type=int, default=0, help="windows per GPU per step (default: 1024 at N=1, 65536/N at N>1)")
     ap.add_argument("--mode", default="auto", choices=["auto", "resident", "streaming"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cg-batch", type=int, default=16384, help="batch of the streaming CG-iteration probe")
     ap.add_argument("--no-cg-probe", action="store_true", help="skip the mga_cg_solve probe (launch lists of the step only)")
+    ap.add_argument("--no-probes", action="store_true", help="skip the T=288 / 20k-node / 65536-window probes")
+    ap.add_argument("--min-timed-s", type=float, default=1.0, help="inner repeats make the timed region at least this long")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -218,33 +341,32 @@ def main():
     import ctypes as C
 
     import torch.distributed as dist
-    from mixed_graph_admm_b200 import _cabi
+    from mixed_graph_admm_b200 import _cabi, parallel
 
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     warm = max(args.warmup, 3)
-    B = args.batch
-    blk, y_host = build_problem(B, seed=rank, device=dev, mode=args.mode)
+    # N = 1: configs[1], one batch of 1024.  N > 1: configs[2], ONE batch of 65536 sharded over the ranks.
+    if args.batch > 0:
+        B, global_batch = args.batch, args.batch * world
+    elif world == 1:
+        B, global_batch = 1024, 1024
+    else:
+        lo, hi = parallel.shard_bounds(GLOBAL_BATCH, world)[rank]
+        B, global_batch = hi - lo, GLOBAL_BATCH
+    blk, y_host = build_problem(B, seed=rank, device=dev, mode=args.mode)     # the global batch = the ranks' shards in rank order
     L = _cabi.lib()
-    plan, prm = blk._plan(), blk._params()
     y_dev = y_host.to(dev)
     y_pin = y_host.pin_memory()
-    x_dev = torch.empty((B, T_LEN, N_NODES, 1), dtype=torch.float32, device=dev)
-    diag = torch.zeros((N_OUTER, _cabi.DIAG_COLS), dtype=torch.float64, device=dev)
-    dxs = torch.zeros((N_OUTER, T_LEN, N_NODES), dtype=torch.float64, device=dev)
-    outs = _cabi.AdmmOutputs()
-    outs.diag, outs.dx_sum = diag.data_ptr(), dxs.data_ptr()
-    from mixed_graph_admm_b200.ADMM import _regression_consts
-    t_mean, t_var = _regression_consts(T_IN)
-    stream = torch.cuda.current_stream(dev)
+    solve = DeviceSolve(blk, y_dev, args.mode, dev)
+    stream = solve.stream
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)     # > 126 MB L2
 
-    def step_device():
-        _cabi.check(L.mga_admm_solve(plan.handle, C.byref(prm), _cabi.ptr(y_dev), T_IN, None, _cabi.ptr(x_dev), B,
-                                     _cabi.MGA_F32, N_OUTER, N_CG, -1.0, -1.0, t_mean, t_var, 1, C.byref(outs),
-                                     _cabi.MODE[args.mode], stream.cuda_stream))
+    def reduce_diag():          # the one collective of the sharded solve: ~74 KB of partial sums (ADMM.py:612-637)
+        if world > 1:
+            dist.all_reduce(solve.diag, op=dist.ReduceOp.SUM)
 
     def barrier():
         torch.cuda.synchronize(dev)
@@ -253,97 +375,155 @@ def main():
         torch.cuda.synchronize(dev)
 
     # ---- device-resident throughput ("value")
+    t_probe = []
     for _ in range(warm):
-        step_device()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        solve()
+        reduce_diag()
+        b.record(stream)
+        torch.cuda.synchronize(dev)
+        t_probe.append(a.elapsed_time(b))
+    # inner repeats: every --steps unit is `reps` back-to-back passes so that the timed region is long enough for the
+    # clock sampler to see the GPU under this load (the same on every rank: taken from rank 0's estimate)
+    est = torch.tensor([min(t_probe) * 1e-3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.broadcast(est, 0)
+    reps = max(1, int(math.ceil(args.min_timed_s / (args.steps * float(est.item())))))
+    passes = args.steps * reps
     barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        time.sleep(0.1)
     l0 = L.mga_launch_count()
     barrier()
     t_wall0 = time.perf_counter()
-    for s in range(args.steps):
-        flush.fill_(s & 0xff)                 # L2 flush between timed iterations (outside the events)
-        ev[s][0].record(stream)
-        step_device()
-        ev[s][1].record(stream)
+    ms = timed_passes(solve, passes, flush, stream, after=reduce_diag)
     barrier()
-    t_wall = time.perf_counter() - t_wall0
+    t_wall1 = time.perf_counter()
     launches = L.mga_launch_count() - l0
-    dev_ms = sum(a.elapsed_time(b) for a, b in ev)
-    clocks = sampler.stop() if rank == 0 else None
+    dev_ms = sum(ms)
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
     tmax = torch.tensor([dev_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
     dev_ms = float(tmax.item())
-    ms_per_step = dev_ms / args.steps
-    value = world * B * args.steps / (dev_ms * 1e-3)
-    kernel_mode = "resident" if (args.mode != "streaming" and L.mga_plan_resident_eligible(plan.handle, 0)) \
+    ms_per_step = dev_ms / passes
+    value = global_batch * passes / (dev_ms * 1e-3)
+    kernel_mode = "resident" if (args.mode != "streaming" and L.mga_plan_resident_eligible(solve.plan.handle, 0)) \
         else "streaming"
 
     # ---- end to end through the public API with host buffers ("e2e")
     blk.mode = args.mode
-    for _ in range(3):      # keeps the previous result alive like the timed loop does (two pinned blocks get cached)
-        x_host = blk.combined_loop(y_pin, print_info=False)
+
+    def e2e_call():
+        if world > 1:
+            return parallel.solve_sharded(blk, y_pin, y_is_global=False)
+        return blk.combined_loop(y_pin, print_info=False)
+
+    t_call = []
+    for _ in range(3):      # keeps the previous result alive like the timed loop does (the pinned blocks get cached)
+        t1 = time.perf_counter()
+        x_host = e2e_call()
+        t_call.append(time.perf_counter() - t1)
+    est = torch.tensor([min(t_call)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.broadcast(est, 0)
+    e2e_steps = max(args.steps, int(math.ceil(0.6 / float(est.item()))))
     barrier()
-    e2e_steps = max(10, args.steps)
     e2e_ms = []
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         t1 = time.perf_counter()
-        x_host = blk.combined_loop(y_pin, print_info=False)
+        x_host = e2e_call()
         e2e_ms.append(round(1e3 * (time.perf_counter() - t1), 3))
     barrier()
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_val = world * B * e2e_steps / float(te.item())
+    e2e_val = global_batch * e2e_steps / float(te.item())
     assert x_host.shape == (B, T_LEN, N_NODES, 1) and not x_host.is_cuda and blk.last_mode == "host"
+    assert len(blk.alpha_x[-1]) == N_CG and blk.alpha_x[-1][0].shape == (B,)      # the lists of ADMM.py:572-591 are filled
+    coef_bytes = 2 * N_OUTER * 3 * N_CG * B * 4
 
     line = None
     if rank == 0:
         peak, peak_src = measured_peaks()
         npts = T_LEN * N_NODES
-        alg_bytes = algorithmic_bytes_per_point() * npts * B
-        achieved = alg_bytes / (ms_per_step * 1e-3) / 1e9
         hbm_io = (B * T_IN * N_NODES * 4 + B * npts * 4) / (ms_per_step * 1e-3) / 1e9
-        traffic, smem = None, None
-        cpath = os.path.join(ROOT, "profiles", "r01_resident_counters.json")
+        alg_bytes = algorithmic_bytes_per_point() * npts * B
+        hbm_equiv = alg_bytes / (ms_per_step * 1e-3) / 1e9
+        sm_clk = (clocks or {}).get("sm_mhz") or 1965.0
+        cpath = os.path.join(ROOT, RESIDENT_COUNTERS)
         if kernel_mode == "resident" and os.path.exists(cpath):
-            # counters of one `ncu --set full` capture of this kernel (committed under profiles/), per launch
+            # The resident kernel never moves the algorithmic bytes through HBM (y in, x out only): what bounds it is the
+            # shared-memory pipe, 128 B per clock and SM.  Wavefronts per window are a property of the kernel and the
+            # plan's gather schedule (data-independent); they come from ONE `ncu --set full` capture of this kernel
+            # committed under profiles/ (a static file, named here), the rate and the SM clock from this run.
             with open(cpath) as f:
                 cnt = json.load(f)
-            if cnt.get("batch") == B:
-                traffic = cnt["dram_bytes_read"] + cnt["dram_bytes_write"]
-            sm_clk = (clocks or {}).get("sm_mhz") or 1965.0
-            wf_per_window = cnt["smem_wavefronts"] / cnt["batch"]
-            smem = {"bound": "shared-memory pipe (128 B/clk/SM)", "wavefronts_per_window": wf_per_window,
-                    "achieved_TBps": wf_per_window * 128 * value / world / 1e12,
-                    "peak_TBps": 148 * 128 * sm_clk * 1e6 / 1e12,
-                    "ncu_pipe_pct_of_peak": cnt["smem_pipe_pct_of_peak"], "source": "profiles/r01_resident_counters.json"}
-            smem["frac"] = smem["achieved_TBps"] / smem["peak_TBps"]
-        roof = {"bound": "hbm", "kernel": "k_admm_resident" if kernel_mode == "resident" else "streaming kernels",
-                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "peak_source": peak_src, "smem": smem,
-                "note": ("algorithmic bytes = what a streaming implementation must move (DESIGN.md §5); the "
-                         "resident kernel keeps them in registers/SMEM, its real HBM I/O is y in + x out = "
-                         f"{hbm_io:.1f} GB/s") if kernel_mode == "resident" else "streaming mode"}
-        line = {"metric": "ADMM windows/sec (PEMS04 shape)", "value": value, "unit": "windows/s", "n_gpus": world,
+            wf = cnt["smem_wavefronts"] / cnt["batch"]
+            achieved = wf * SMEM_BYTES_PER_CLK * (value / world) / 1e9
+            smem_peak = SM_COUNT * SMEM_BYTES_PER_CLK * sm_clk * 1e6 / 1e9
+            roof = {"bound": "smem", "kernel": "k_admm_resident", "achieved": achieved, "peak": smem_peak, "unit": "GB/s",
+                    "frac": achieved / smem_peak,
+                    "traffic": (cnt["dram_bytes_read"] + cnt["dram_bytes_write"]) * B / cnt["batch"],
+                    "peak_source": f"{SM_COUNT} SMs x {SMEM_BYTES_PER_CLK} B/clk x {sm_clk:.0f} MHz (median SM clock of this run)",
+                    "wavefronts_per_window": wf, "wavefronts_source": f"{RESIDENT_COUNTERS} (static: one ncu --set full "
+                    f"capture at batch {cnt['batch']}, l1tex__data_pipe_lsu_wavefronts_mem_shared.sum)",
+                    "ncu_pipe_pct_of_peak": cnt.get("smem_pipe_pct_of_peak"),
+                    "hbm": {"io_GBps": hbm_io, "algorithmic_equivalent_GBps": hbm_equiv, "peak_GBps": peak, "peak_source": peak_src,
+                            "note": "real HBM traffic is y in + x out; 'algorithmic_equivalent' = bytes a streaming "
+                                    "implementation of the same schedule would move (DESIGN.md §5) / time - context, not a fraction"}}
+        else:
+            roof = {"bound": "hbm", "kernel": "streaming kernels", "achieved": hbm_equiv, "peak": peak, "unit": "GB/s",
+                    "frac": hbm_equiv / peak, "traffic": None, "peak_source": peak_src}
+        par = (f"ONE batch of {global_batch} windows sharded over {world} GPUs ({B} per GPU), no data-path collective, one NCCL "
+               "all-reduce of the diagnostics per solve") if world > 1 else "one GPU"
+        line = {"metric": METRIC, "value": value, "unit": "windows/s", "n_gpus": world,
                 "steps": args.steps, "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": B * world,
-                           "parallelism": f"windows sharded over {world} GPU(s), no collective",
-                           "kernel_mode": kernel_mode, "diagnostics": "on", "l2": "flushed between timed steps"},
+                "scaling": "weak" if world == 1 else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "inner_repeats": reps, "passes_timed": passes,
+                "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": global_batch, "parallelism": par,
+                           "kernel_mode": kernel_mode, "diagnostics": "on", "l2": "flushed between timed passes",
+                           "baseline_config": "configs[1]" if world == 1 else "configs[2]"},
                 "e2e": {"value": e2e_val, "unit": "windows/s", "h2d_bytes_per_step": int(y_pin.numel() * 4),
-                        "d2h_bytes_per_step": int(B * npts * 4 + N_OUTER * (_cabi.DIAG_COLS + npts) * 8),
-                        "steps": e2e_steps, "ms_per_call": e2e_ms, "api": "ADMM_algorithm.combined_loop(y_pinned_cpu) -> mga_admm_solve_host"},
-                "gpu_launches": int(launches), "wall_s_timed_region": t_wall, "clocks": clocks, "roofline": roof}
+                        "d2h_bytes_per_step": int(B * npts * 4 + coef_bytes + N_OUTER * (_cabi.DIAG_COLS + npts) * 8),
+                        "steps": e2e_steps, "ms_per_call": e2e_ms[:40], "frac_of_value": e2e_val / value,
+                        "api": ("parallel.solve_sharded(blk, y_pinned_cpu_shard) -> " if world > 1 else "") +
+                               "ADMM_algorithm.combined_loop(y_pinned_cpu) -> mga_admm_solve_host; x, alpha_*/beta_* and the "
+                               "diagnostics lists come back"},
+                "gpu_launches": int(launches), "wall_s_timed_region": t_wall1 - t_wall0, "clocks": clocks, "roofline": roof}
+
+    # ---- the other BASELINE configs on the same clock (rank 0, N = 1 only)
+    if rank == 0 and world == 1 and not args.no_probes:
+        probes = {}
+        for name, cfg in (("long_horizon_T288", (307, 6, 288, 256, 1.1, 4)), ("large_graph_20k", (20000, 8, 24, 64, 1.1, 9))):
+            try:
+                probes[name] = probe_config(name, *cfg, dev=dev, flush=flush, peak=peak)
+            except Exception as e:
+                probes[name] = {"error": repr(e)[:300]}
+        try:        # configs[2]'s batch on ONE GPU: the base of the strong-scaling run
+            yb = torch.rand(GLOBAL_BATCH, T_IN, N_NODES, 1, device=dev)
+            big = DeviceSolve(blk, yb, args.mode, dev)
+            for _ in range(2):
+                big()
+            torch.cuda.synchronize(dev)
+            msb = timed_passes(big, 5, flush, stream)
+            probes["global_batch_65536_one_gpu"] = {"batch": GLOBAL_BATCH, "ms_per_step": sum(msb) / len(msb),
+                                                    "windows_per_s": GLOBAL_BATCH / (sum(msb) / len(msb) * 1e-3)}
+            del big, yb
+            torch.cuda.empty_cache()
+        except Exception as e:
+            probes["global_batch_65536_one_gpu"] = {"error": repr(e)[:300]}
+        line["probes"] = probes
 
     # ---- the fused CG iteration in streaming mode vs the HBM roofline (vectors larger than L2)
     if rank == 0 and not args.no_cg_probe:
         try:
+            plan, prm = solve.plan, solve.prm
             Bc = args.cg_batch
             n = Bc * T_LEN * N_NODES
             g = torch.Generator(device="cpu").manual_seed(1)
@@ -354,37 +534,38 @@ def main():
                 _cabi.check(L.mga_plan_set_cg_mode(plan.handle, _cabi.MODE[cgmode]))
                 res[impl] = {}
                 for sysname in ("x", "zu"):
-                    def solve():
+                    def cg():
                         _cabi.check(L.mga_cg_solve(plan.handle, _cabi.SYS[sysname], C.byref(prm), _cabi.ptr(rhs),
                                                    _cabi.ptr(xw), None, Bc, _cabi.MGA_F32, N_CG, -1.0, None, None, None,
                                                    stream.cuda_stream))
                     for _ in range(3):
                         xw.zero_()
-                        solve()
+                        cg()
                     torch.cuda.synchronize(dev)
-                    reps, tot = 5, 0.0
-                    for _ in range(reps):
+                    reps_cg, tot = 5, 0.0
+                    for _ in range(reps_cg):
                         xw.zero_()
                         flush.fill_(1)
                         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                         a.record(stream)
-                        solve()
+                        cg()
                         b.record(stream)
                         torch.cuda.synchronize(dev)
                         tot += a.elapsed_time(b)
-                    ms = tot / reps
+                    msc = tot / reps_cg
                     per_it = cg_iter_bytes_per_point(sysname)
                     init_b = 32.0 if sysname == "x" else 20.0
-                    gbs = (per_it * N_CG + init_b) * n / (ms * 1e-3) / 1e9
-                    res[impl][sysname] = {"ms_per_solve": ms, "ms_per_iter": ms / (N_CG + 1), "achieved": gbs,
+                    gbs = (per_it * N_CG + init_b) * n / (msc * 1e-3) / 1e9
+                    res[impl][sysname] = {"ms_per_solve": msc, "ms_per_iter": msc / (N_CG + 1), "achieved": gbs,
                                           "frac": gbs / peak, "bytes_per_point_per_iter": per_it}
             _cabi.check(L.mga_plan_set_cg_mode(plan.handle, _cabi.MODE["auto"]))
             line["cg_iter"] = {"batch": Bc, "unit": "GB/s (algorithmic bytes / time)", "peak": peak,
                                "vector_mb": n * 4 / 1e6, "impl": res,
-                               "note": "mga_cg_solve, 10 fixed iterations, vectors exceed L2, L2 flushed. 'streaming': one "
-                                       "fused kernel per CG phase, vectors in HBM (the path of windows too large for one "
-                                       "CTA). 'resident': one launch per solve, one window per CTA, rhs/x0 read once - its "
-                                       "real HBM traffic is 12 B/pt/solve, so the algorithmic rate exceeds the HBM peak"}
+                               "note": "mga_cg_solve, 10 fixed iterations, vectors exceed L2, L2 flushed. 'streaming': fused "
+                                       "tile kernels per CG phase, vectors in HBM (the path of windows too large for one "
+                                       "CTA), layout conversion included. 'resident': one launch per solve, one window per "
+                                       "CTA, rhs/x0 read once - its real HBM traffic is 12 B/pt/solve, so the algorithmic "
+                                       "rate exceeds the HBM peak"}
             del rhs, xw
         except Exception as e:  # the headline line must still be printed
             line["cg_iter"] = {"error": str(e)[:200]}

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define MGA_VERSION 100 /* 0.1.0 */
+#define MGA_VERSION 110 /* 0.1.1: mga_admm_solve_host returns the CG coefficients */
 
 typedef enum {
   MGA_OK = 0,
@@ -200,14 +200,18 @@ int mga_admm_solve(mga_plan* plan, const mga_params* prm, const void* y, int y_r
                    double admm_tol, double t_mean, double t_var, int want_diag,
                    const mga_admm_outputs* outs, int mode, void* stream);
 
-/* ---- same, with HOST buffers (the end-to-end call): y_host -> device, solve, x -> x_host,
- * chunked over the batch so copies overlap compute.  diag_host (n_outer, MGA_DIAG_COLS) and
- * dx_sum_host (n_outer, T, N) doubles may be NULL.  Synchronous: returns when x_host is complete.
- * Buffers need not be pinned (pinned ones are copied asynchronously). */
+/* ---- same, with HOST buffers (the end-to-end call every caller of the reference makes: CPU tensors in, CPU tensor
+ * out).  Forecasting mode, fixed iteration counts.  When the plan runs in resident mode the whole batch is ONE
+ * persistent launch: y is uploaded chunk by chunk while the kernel already solves the first chunks, finished chunks
+ * are downloaded while it solves the rest.  Otherwise the batch is cut into chunks that are uploaded / solved /
+ * downloaded on three streams.  diag_host (n_outer, MGA_DIAG_COLS) and dx_sum_host (n_outer, T, N) doubles may be
+ * NULL.  alpha_host / beta_host: HOST (n_outer, 3, max_cg_iter, B) in the signal dtype (the lists of ADMM.py:572-591),
+ * both or neither.  Synchronous: returns when every host buffer is complete.  Buffers need not be pinned (pinned
+ * ones are copied asynchronously).  chunk <= 0: automatic. */
 int mga_admm_solve_host(mga_plan* plan, const mga_params* prm, const void* y_host, int y_rows,
                         void* x_host, int64_t B, int dtype, int n_outer, int max_cg_iter,
                         double t_mean, double t_var, int want_diag, double* diag_host,
-                        double* dx_sum_host, int mode, int64_t chunk);
+                        double* dx_sum_host, void* alpha_host, void* beta_host, int mode, int64_t chunk);
 
 /* ---- kNN tables by shortest-path distance (utils.py:183-204), host only, bit-identical to the
  * reference's networkx + heapq result.  edges (E,2) int64, dists (E,) float64.

@@ -139,6 +139,7 @@ class ADMM_algorithm():
         self.diag_reduce = None         # multi-GPU hook: (diag, dx_sum, B) -> global (diag, dx_sum, B)
         self.strict_quirks = False      # True: reproduce the B>1 converged-return ValueError (quirk Q2)
         self.keep_iterates = False      # True: combined_loop leaves z_u, z_d, phi, duals in last_iterates
+        self.keep_cg_coefficients = True    # False: the CPU-input path skips the alpha_* / beta_* read-back (lists of [])
         self.last_iterates = None
         self.last_mode = None
         self._plan_key = None
@@ -253,6 +254,9 @@ class ADMM_algorithm():
             desc.update(kd=self.skip_connection, nbr_d=None, d_w=dw32, d_w_T=1, temporal=_cabi.TEMPORAL_BAND)
         desc = {k: (0 if v is None else v) for k, v in desc.items()}
         self._plan_obj = _Plan(desc, self.device)
+        # the key holds addresses: pin the tensors it was taken from so that a reassigned attribute (a sigma sweep
+        # that builds a fresh d_ew) can never be given a recycled address that matches a cached entry
+        self._plan_obj.key_tensors = (cl, uw, dw)
         self._plan_key = key
         if len(self._plan_cache) >= 4:
             self._plan_cache.clear()
@@ -439,10 +443,10 @@ class ADMM_algorithm():
             assert mask is None, 'differential mode does not support mask'
             # the reference computes a differential first guess here and then discards it (ADMM.py:521-529)
         wkey = (self.d_ew.data_ptr(), self.d_ew._version, self.u_ew.data_ptr(), self.u_ew._version)
-        if wkey != getattr(self, "_weights_checked", None):     # the reference re-checks every call (ADMM.py:517-518)
+        if wkey != getattr(self, "_weights_checked", (None,))[0]:     # the reference re-checks every call (ADMM.py:517-518)
             assert not torch.isnan(self.d_ew).any(), 'Directed graph weights d_ew has NaN value'
             assert not torch.isnan(self.u_ew).any(), 'Undirected graph weights u_ew has NaN value'
-            self._weights_checked = wkey
+            self._weights_checked = (wkey, self.d_ew, self.u_ew)    # the tensors stay alive: their addresses cannot be recycled
         out_device = y.device
         if y.dim() != 4:
             raise ValueError(f"signals are (B, T, N, C); got {tuple(y.shape)}")
@@ -465,20 +469,26 @@ class ADMM_algorithm():
 
         host_path = (y.device.type == 'cpu' and mask is None and fixed and not want_iter
                      and self.ablation == 'None')
-        diag_h = np.zeros((n_outer, _cabi.DIAG_COLS), dtype=np.float64)
-        dx_h = np.zeros((n_outer, T, N * Cn), dtype=np.float64)
+        diag_h = np.empty((n_outer, _cabi.DIAG_COLS), dtype=np.float64)
+        dx_h = np.empty((n_outer, T, N * Cn), dtype=np.float64)
         cg_iters = np.full((max(n_outer, 1), 3), -1, dtype=np.int32)
         outer_done = C.c_int32(n_outer)
         alpha = beta = None
         with torch.cuda.device(dev):
             if host_path:
-                # end-to-end call with host buffers: chunked copies overlap the solve
+                # end-to-end call with host buffers: the copies overlap the solve (include/mga.h: mga_admm_solve_host);
+                # the CG coefficients come back too, so the alpha_* / beta_* lists are what the reference fills
                 yc = y.detach().contiguous()
-                x = torch.empty((B, T, N, Cn), dtype=y.dtype, pin_memory=yc.is_pinned())
+                pin = yc.is_pinned()
+                x = torch.empty((B, T, N, Cn), dtype=y.dtype, pin_memory=pin)
+                if self.keep_cg_coefficients and n_cg > 0 and n_outer > 0:
+                    alpha = torch.empty((n_outer, 3, n_cg, B), dtype=y.dtype, pin_memory=pin)
+                    beta = torch.empty((n_outer, 3, n_cg, B), dtype=y.dtype, pin_memory=pin)
                 _cabi.check(L.mga_admm_solve_host(plan.handle, C.byref(prm), _cabi.ptr(yc), y_rows, _cabi.ptr(x), B,
                                                   dt, n_outer, n_cg, t_mean, t_var, 1,
                                                   diag_h.ctypes.data_as(C.c_void_p),
-                                                  dx_h.ctypes.data_as(C.c_void_p), _cabi.MODE[self.mode], 0))
+                                                  dx_h.ctypes.data_as(C.c_void_p), _cabi.ptr(alpha), _cabi.ptr(beta),
+                                                  _cabi.MODE[self.mode], 0))
                 self.last_mode = 'host'
                 self.last_iterates = None
             else:
@@ -509,7 +519,7 @@ class ADMM_algorithm():
                 self.last_mode = 'device'
         if self.diag_reduce is not None:      # shards of one batch: sum the partial sums over the ranks
             diag_h, dx_h, B = self.diag_reduce(diag_h, dx_h, B)
-            alpha = beta = None               # per-window CG coefficients stay with their shard
+            # (the per-window CG coefficients stay with their shard: alpha_* / beta_* hold (B_local,) tensors)
         self._fill_lists(diag_h, dx_h, cg_iters, int(outer_done.value), alpha, beta, B, y.dtype, out_device,
                          print_info)
         return x.to(out_device)
@@ -543,7 +553,7 @@ class ADMM_algorithm():
                     n_it = its[s] if its[s] > 0 else int(self.max_CG_iter)
                     a, b = self._coef_lists(alpha[i, s], beta[i, s], its[s], n_it, device)
                 else:
-                    a, b = [], []          # host path does not bring the CG coefficients back
+                    a, b = [], []          # keep_cg_coefficients = False
                 getattr(self, "alpha_" + name).append(a)
                 getattr(self, "beta_" + name).append(b)
             pri, dual = [], []

@@ -94,7 +94,7 @@ def lib():
         L.mga_admm_solve.argtypes = [vp, C.POINTER(Params), vp, C.c_int, vp, vp, i64, C.c_int, C.c_int, C.c_int,
                                      dbl, dbl, dbl, dbl, C.c_int, C.POINTER(AdmmOutputs), C.c_int, vp]
         L.mga_admm_solve_host.argtypes = [vp, C.POINTER(Params), vp, C.c_int, vp, i64, C.c_int, C.c_int, C.c_int,
-                                          dbl, dbl, C.c_int, vp, vp, C.c_int, i64]
+                                          dbl, dbl, C.c_int, vp, vp, vp, vp, C.c_int, i64]
         L.mga_knn_build.argtypes = [i32, i64, vp, vp, i32, vp, vp]
         L.mga_schedule_selfcheck.argtypes = [C.POINTER(GraphDesc), C.POINTER(dbl)]
         for name in EXPORTS:

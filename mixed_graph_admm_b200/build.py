@@ -1,10 +1,13 @@
 """Build libmga.so in-tree with nvcc for sm_100a (no JIT cache: the .so travels with the repo)."""
 from __future__ import annotations
 
+import hashlib
+import json
 import os
 import shutil
 import subprocess
 import sys
+import time
 from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -26,47 +29,73 @@ def _nvcc():
     return exe
 
 
-def _stale(target, deps):
-    if not os.path.exists(target):
-        return True
-    t = os.path.getmtime(target)
-    return any(os.path.getmtime(d) > t for d in deps)
+def _digest(paths, extra=()):
+    """Content hash of the files a target is built from (+ the flags): staleness does not depend on mtimes, which a
+    snapshot copy to the GPU box need not preserve, and the objects need not travel with the library."""
+    h = hashlib.sha1()
+    for x in extra:
+        h.update(str(x).encode())
+        h.update(b"\0")
+    for f in paths:
+        h.update(os.path.basename(f).encode())
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
+# -lineinfo on every translation unit (ncu's source page); the embedded PTX text it brings is 2/3 of an object, so the
+# instantiations for windows of T <= 8 (CH = 1, 2: test-sized problems nobody profiles) get it only with MGA_LINEINFO_ALL=1
+def _lineinfo(ch):
+    return ch >= 3 or os.environ.get("MGA_LINEINFO_ALL") == "1"
 
 
 def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False, tag: str = "", defines=()) -> str:
     """Default: _lib/libmga.so.  `tag` + `defines` build an experiment variant (e.g. tag="tab1",
-    defines=["MGA_RES_TAB_SMEM=1"]) into _lib/<tag>/libmga.so; select it with MGA_LIB=<path>."""
+    defines=["MGA_RES_TAB_SMEM=1"]) into _lib/<tag>/libmga.so; select it with MGA_LIB=<path>.
+    _lib/build_manifest.json records the content hash every object and the library were built from (what decides
+    staleness) and _lib/build_log.json what the last call compiled."""
     out_dir = os.path.join(OUT_DIR, tag) if tag else OUT_DIR
     lib_path = os.path.join(out_dir, "libmga.so")
     os.makedirs(out_dir, exist_ok=True)
-    nvcc = _nvcc()
     flags = NVCC_FLAGS + [f"-D{d}" for d in defines]
-    headers = [os.path.join(CSRC, "mga_common.cuh"), os.path.join(CSRC, "mga_resident.cuh"), os.path.join(CSRC, "mga_schedule.h"),
-               os.path.join(ROOT, "include", "mga.h"), __file__]
-    jobs = []
-    objs = []
+    headers = [os.path.join(CSRC, h) for h in sorted(os.listdir(CSRC)) if h.endswith((".cuh", ".h"))] + \
+              [os.path.join(ROOT, "include", "mga.h")]
+    man_path = os.path.join(out_dir, "build_manifest.json")
+    try:
+        with open(man_path) as fh:
+            manifest = json.load(fh)
+    except Exception:
+        manifest = {}
+    units = []      # (object, source, extra flags, lineinfo)
     for src in SOURCES:
         sp = os.path.join(CSRC, src)
-        if not os.path.exists(sp):
-            continue
-        obj = os.path.join(out_dir, os.path.splitext(src)[0] + ".o")
-        objs.append(obj)
-        if force or _stale(obj, [sp] + headers):
-            cmd = [nvcc] + flags + (["-Xptxas", "-v"] if ptxas_info else []) + ["-c", sp, "-o", obj]
-            if src.endswith(".cpp"):
-                cmd = [nvcc, "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"),
-                       "-I", CSRC, "-x", "c++", "-c", sp, "-o", obj]
-            jobs.append(cmd)
-
+        if os.path.exists(sp):
+            units.append((os.path.join(out_dir, os.path.splitext(src)[0] + ".o"), sp, [], True))
     inst = os.path.join(CSRC, "mga_resident_inst.cu")
     for tt, k in RESIDENT_VARIANTS:
-        obj = os.path.join(out_dir, f"mga_resident_ch{tt}_k{k}.o")
-        objs.append(obj)
-        if force or _stale(obj, [inst] + headers):
-            jobs.append([nvcc] + flags + (["-Xptxas", "-v"] if ptxas_info else []) +
-                        [f"-DMGA_CH={tt}", f"-DMGA_K={k}", "-c", inst, "-o", obj])
+        units.append((os.path.join(out_dir, f"mga_resident_ch{tt}_k{k}.o"), inst, [f"-DMGA_CH={tt}", f"-DMGA_K={k}"], _lineinfo(tt)))
+    want = {os.path.basename(o): _digest([sp] + headers, flags + extra + [li]) for o, sp, extra, li in units}
+    lib_key = _digest([], sorted(want.items()))
+    log = {"when": time.strftime("%Y-%m-%dT%H:%M:%SZ", time.gmtime()), "library": lib_path, "compiled": [], "linked": False}
+    if not force and os.path.exists(lib_path) and manifest.get("libmga.so") == lib_key:
+        log["note"] = "library is up to date with the sources (content hash): nothing compiled"
+        with open(os.path.join(out_dir, "build_log.json"), "w") as fh:
+            json.dump(log, fh, indent=1)
+        return lib_path
+    nvcc = _nvcc()
+    jobs = []
+    for o, sp, extra, li in units:
+        name = os.path.basename(o)
+        if force or not os.path.exists(o) or manifest.get(name) != want[name]:
+            fl = [f for f in flags if li or f != "-lineinfo"]
+            cmd = [nvcc] + fl + extra + (["-Xptxas", "-v"] if ptxas_info else []) + ["-c", sp, "-o", o]
+            if sp.endswith(".cpp"):
+                cmd = [nvcc, "-O3", "-std=c++17", "-Xcompiler", "-fPIC", "-I", os.path.join(ROOT, "include"),
+                       "-I", CSRC, "-x", "c++", "-c", sp, "-o", o]
+            jobs.append((name, cmd))
 
-    def run(cmd):
+    def run(job):
+        name, cmd = job
         if verbose:
             print(" ".join(cmd), flush=True)
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -80,8 +109,16 @@ def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False, 
         if ptxas_info:
             for lg in logs:
                 sys.stderr.write(lg)
-    if jobs or force or _stale(lib_path, objs):
-        run([nvcc, "-shared", "-o", lib_path] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"])
+        for name, _ in jobs:
+            manifest[name] = want[name]
+            log["compiled"].append(name)
+    run(("libmga.so", [nvcc, "-shared", "-o", lib_path] + [o for o, _, _, _ in units] + ["-gencode", "arch=compute_100a,code=sm_100a"]))
+    manifest["libmga.so"] = lib_key
+    log["linked"] = True
+    with open(man_path, "w") as fh:
+        json.dump(manifest, fh, indent=1, sort_keys=True)
+    with open(os.path.join(out_dir, "build_log.json"), "w") as fh:
+        json.dump(log, fh, indent=1)
     return lib_path
 
 

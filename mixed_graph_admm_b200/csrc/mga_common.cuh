@@ -77,6 +77,17 @@ struct Workspace {
   size_t bytes = 0;
 };
 
+// Pipelined host entry point: the resident kernel waits for ready[c] == epoch before it touches chunk c of the batch and
+// reports finished chunks through host_done[c] (mapped pinned host memory).  See mga_admm_solve_host.
+struct HostPipe {
+  const int* ready;
+  int* done;
+  int* host_done;      // device alias of the mapped host array
+  int* abort_flag;
+  int chunk, epoch;
+  int64_t B_coef;      // windows per row of the alpha / beta arrays
+};
+
 }  // namespace mga
 
 struct mga_plan {
@@ -97,6 +108,12 @@ struct mga_plan {
   int cg_mode = MGA_MODE_AUTO;       // mga_plan_set_cg_mode
   int res_slot = 0;                  // which half of the resident kernel's parking scratch the next launch uses
                                      // (the host entry point runs two chunk solves concurrently)
+  const mga::HostPipe* pipe = nullptr;   // set by mga_admm_solve_host around its resident launch
+  static constexpr int kPipeChunks = 256;
+  int* pipe_dev = nullptr;           // device: ready[kPipeChunks], done[kPipeChunks], abort
+  int* pipe_host = nullptr;          // mapped pinned host: host_done[kPipeChunks], then epoch words for the ready flags
+  int* pipe_host_dev = nullptr;      // device alias of pipe_host
+  int pipe_epoch = 0;
   // host copies of the tables
   std::vector<int> h_nbr_u, h_nbr_d, h_csr_ptr, h_csr_src;
   std::vector<float> h_u_w, h_d_w, h_csr_w;

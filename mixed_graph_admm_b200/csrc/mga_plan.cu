@@ -264,7 +264,8 @@ int mga_plan_create(const mga_graph_desc* d, int device, mga_plan** out) {
     if ((rc = upload(p, sc.ell_ptr, &p->r_ell_ptr))) return fail(rc);
     if ((rc = upload(p, ent, &p->r_ell_ent))) return fail(rc);
     void* ctr = nullptr;
-    MGA_CUDA(cudaMalloc(&ctr, mga_plan::kCounters * 32 * sizeof(int)));
+    e = cudaMalloc(&ctr, mga_plan::kCounters * 32 * sizeof(int));
+    if (e != cudaSuccess) return fail(cuda_fail(e, "cudaMalloc(window counters)"));
     p->owned.push_back(ctr);
     p->r_counters = static_cast<int*>(ctr);
     p->has_sched = true;
@@ -606,6 +607,7 @@ void mga_plan_destroy(mga_plan* p) {
   if (p->ws.base) cudaFree(p->ws.base);
   if (p->ws_host_io.base) cudaFree(p->ws_host_io.base);
   if (p->pinned) cudaFreeHost(p->pinned);
+  if (p->pipe_host) cudaFreeHost(p->pipe_host);
   for (auto& s : p->io_streams) if (s) cudaStreamDestroy(s);
   for (auto& ev : p->io_events) if (ev) cudaEventDestroy(ev);
   delete p;
@@ -707,17 +709,164 @@ int mga_admm_solve(mga_plan* p, const mga_params* prm, const void* y, int y_rows
                      want_diag, outs, (cudaStream_t)stream);
 }
 
-// End-to-end entry point with host buffers: the batch is cut into chunks; chunk c+1 is uploaded
-// and chunk c-1 downloaded while chunk c computes (three streams, events for ordering).
+// ---- end-to-end entry point with host buffers ------------------------------------------------------------------
+static int host_io_setup(mga_plan* p) {
+  for (auto& s : p->io_streams) if (!s) MGA_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  for (auto& ev : p->io_events) if (!ev) MGA_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+  if (!p->pipe_dev) {
+    const size_t nb = (2 * mga_plan::kPipeChunks + 8) * sizeof(int);
+    MGA_CUDA(cudaMalloc(reinterpret_cast<void**>(&p->pipe_dev), nb));
+    p->owned.push_back(p->pipe_dev);
+    MGA_CUDA(cudaMemset(p->pipe_dev, 0, nb));
+  }
+  if (!p->pipe_host) {
+    const size_t nb = 2 * mga_plan::kPipeChunks * sizeof(int);
+    MGA_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&p->pipe_host), nb, cudaHostAllocMapped));
+    std::memset(p->pipe_host, 0, nb);
+    MGA_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&p->pipe_host_dev), p->pipe_host, 0));
+  }
+  return MGA_OK;
+}
+
+// Resident mode: ONE persistent launch over the whole batch.  The upload stream copies y chunk by chunk and, in stream
+// order behind each chunk, a 4-byte "ready" word; the kernel's CTAs wait for the word of the chunk their next window
+// lives in, so the solve starts as soon as the first chunk has landed and always runs on a full grid (chunked launches
+// each under-filled the 2-CTAs-per-SM grid and paid a tail per chunk).  The CTA that finishes the last window of a
+// chunk raises a flag in mapped host memory; this thread polls the flags and queues the chunk's x download, so copies
+// in both directions overlap the solve.  alpha / beta come back in one copy behind the kernel.
+static int solve_host_pipelined(mga_plan* p, const mga_params* prm, const char* y_host, int y_rows, char* x_host, int64_t B,
+                                int n_outer, int max_cg, double t_mean, double t_var, int want_diag, double* diag_host,
+                                double* dx_sum_host, void* alpha_host, void* beta_host, int mode, int64_t chunk) {
+  const GraphDev& g = p->g;
+  const size_t es = 4;
+  const size_t y_win = (size_t)y_rows * g.N * es, x_win = (size_t)g.T * g.N * es;
+  const size_t diag_n = (size_t)n_outer * MGA_DIAG_COLS, dx_n = (size_t)n_outer * g.T * g.N;
+  const bool want_coef = alpha_host && beta_host && max_cg > 0 && n_outer > 0;
+  const size_t coef_bytes = want_coef ? (size_t)n_outer * 3 * max_cg * (size_t)B * es : 0;
+  // windows per launch: the staging of one launch stays below a cap (default 16 GB); larger batches take several launches
+  double cap_gb = 16.0;
+  if (const char* e = std::getenv("MGA_HOST_STAGING_GB")) cap_gb = std::max(0.001, std::atof(e));
+  const int64_t Bs = std::max<int64_t>(1, std::min<int64_t>(B, (int64_t)(cap_gb * 1e9 / (double)(y_win + x_win))));
+  size_t off_x = ((size_t)Bs * y_win + 255) & ~(size_t)255;
+  size_t off_d = (off_x + (size_t)Bs * x_win + 255) & ~(size_t)255;
+  size_t off_a = (off_d + (diag_n + dx_n) * sizeof(double) + 255) & ~(size_t)255;
+  size_t off_b = (off_a + coef_bytes + 255) & ~(size_t)255;
+  int rc = ensure_workspace(p, p->ws_host_io, off_b + coef_bytes);
+  if (rc) return rc;
+  if ((rc = host_io_setup(p))) return rc;
+  char* base = static_cast<char*>(p->ws_host_io.base);
+  char* dy = base;
+  char* dx = base + off_x;
+  double* d_diag = reinterpret_cast<double*>(base + off_d);
+  double* d_dx = d_diag + diag_n;
+  cudaStream_t s_up = p->io_streams[0], s_run = p->io_streams[1], s_dn = p->io_streams[3];
+  mga_admm_outputs outs{};
+  if (want_diag) {
+    outs.diag = d_diag;
+    outs.dx_sum = d_dx;
+    MGA_CUDA(cudaMemsetAsync(d_diag, 0, (diag_n + dx_n) * sizeof(double), s_run));
+  }
+  for (int64_t s0 = 0; s0 < B; s0 += Bs) {
+    const int64_t nbs = std::min(Bs, B - s0);
+    int64_t ck = chunk > 0 ? chunk : std::max<int64_t>(64, (nbs + 63) / 64);
+    if (const char* e = std::getenv("MGA_HOST_CHUNK")) ck = std::max<long>(1, std::atol(e));
+    ck = std::min(ck, nbs);
+    if ((nbs + ck - 1) / ck > mga_plan::kPipeChunks) ck = (nbs + mga_plan::kPipeChunks - 1) / mga_plan::kPipeChunks;
+    const int nchunk = (int)((nbs + ck - 1) / ck);
+    const int epoch = (p->pipe_epoch = p->pipe_epoch >= (1 << 30) ? 1 : p->pipe_epoch + 1);
+    int* host_done = p->pipe_host;
+    int* host_word = p->pipe_host + mga_plan::kPipeChunks;      // source of the "ready" copies
+    for (int c = 0; c < nchunk; ++c) host_word[c] = epoch;
+    HostPipe pipe{};
+    pipe.ready = p->pipe_dev;
+    pipe.done = p->pipe_dev + mga_plan::kPipeChunks;
+    pipe.abort_flag = p->pipe_dev + 2 * mga_plan::kPipeChunks;
+    pipe.host_done = p->pipe_host_dev;
+    pipe.chunk = (int)ck;
+    pipe.epoch = epoch;
+    pipe.B_coef = B;
+    if (want_coef) {
+      outs.alpha = base + off_a + (size_t)s0 * es;
+      outs.beta = base + off_b + (size_t)s0 * es;
+    }
+    auto upload = [&](int c) -> int {
+      const int64_t b0 = (int64_t)c * ck, nb = std::min(ck, nbs - b0);
+      MGA_CUDA(cudaMemcpyAsync(dy + (size_t)b0 * y_win, y_host + (size_t)(s0 + b0) * y_win, (size_t)nb * y_win,
+                               cudaMemcpyHostToDevice, s_up));
+      MGA_CUDA(cudaMemcpyAsync(const_cast<int*>(pipe.ready) + c, host_word + c, sizeof(int), cudaMemcpyHostToDevice, s_up));
+      return MGA_OK;
+    };
+    MGA_CUDA(cudaMemsetAsync(pipe.done, 0, (mga_plan::kPipeChunks + 8) * sizeof(int), s_run));     // counters + abort flag
+    if ((rc = upload(0))) return rc;
+    p->pipe = &pipe;
+    rc = mga_admm_solve(p, prm, dy, y_rows, nullptr, dx, nbs, MGA_F32, n_outer, max_cg, -1.0, -1.0, t_mean, t_var,
+                        want_diag | 2, &outs, mode, s_run);
+    p->pipe = nullptr;
+    if (rc) { cudaDeviceSynchronize(); return rc; }
+    for (int c = 1; c < nchunk; ++c)
+      if ((rc = upload(c))) { cudaDeviceSynchronize(); return rc; }
+    // hand finished chunks to the download stream as the kernel reports them
+    bool kernel_over = false;
+    for (int c = 0; c < nchunk; ++c) {
+      volatile int* flag = host_done + c;
+      for (unsigned spin = 0; *flag != epoch; ++spin) {
+        if ((spin & 1023u) == 1023u && !kernel_over) {
+          const cudaError_t q = cudaStreamQuery(s_run);
+          if (q == cudaSuccess) kernel_over = true;                   // one more look at the flag, then it is an error
+          else if (q != cudaErrorNotReady) return cuda_fail(q, "resident kernel (host entry)");
+        } else if (kernel_over && (spin & 1023u) == 1023u) {
+          cudaDeviceSynchronize();
+          set_error("mga_admm_solve_host: the solve ended without finishing every chunk (an upload never arrived)");
+          return MGA_ERR_CUDA;
+        }
+#if defined(__x86_64__)
+        __builtin_ia32_pause();
+#endif
+      }
+      const int64_t b0 = (int64_t)c * ck, nb = std::min(ck, nbs - b0);
+      MGA_CUDA(cudaMemcpyAsync(x_host + (size_t)(s0 + b0) * x_win, dx + (size_t)b0 * x_win, (size_t)nb * x_win,
+                               cudaMemcpyDeviceToHost, s_dn));
+    }
+    MGA_CUDA(cudaStreamSynchronize(s_run));
+    if (s0 + nbs < B) MGA_CUDA(cudaStreamSynchronize(s_dn));          // the next launch reuses the x staging
+  }
+  if (want_coef) {
+    MGA_CUDA(cudaMemcpyAsync(alpha_host, base + off_a, coef_bytes, cudaMemcpyDeviceToHost, s_dn));
+    MGA_CUDA(cudaMemcpyAsync(beta_host, base + off_b, coef_bytes, cudaMemcpyDeviceToHost, s_dn));
+  }
+  if (want_diag) {
+    if (diag_host) MGA_CUDA(cudaMemcpyAsync(diag_host, d_diag, diag_n * sizeof(double), cudaMemcpyDeviceToHost, s_dn));
+    if (dx_sum_host) MGA_CUDA(cudaMemcpyAsync(dx_sum_host, d_dx, dx_n * sizeof(double), cudaMemcpyDeviceToHost, s_dn));
+  }
+  MGA_CUDA(cudaStreamSynchronize(s_dn));
+  return MGA_OK;
+}
+
+// Streaming modes (and MGA_HOST_PIPE=0): the batch is cut into chunks; chunk c+1 is uploaded and chunk c-1 downloaded
+// while chunk c computes (upload / run / download streams, events for ordering).
 int mga_admm_solve_host(mga_plan* p, const mga_params* prm, const void* y_host, int y_rows, void* x_host, int64_t B,
                         int dtype, int n_outer, int max_cg, double t_mean, double t_var, int want_diag,
-                        double* diag_host, double* dx_sum_host, int mode, int64_t chunk) {
+                        double* diag_host, double* dx_sum_host, void* alpha_host, void* beta_host, int mode,
+                        int64_t chunk) {
   int rc = check_common(p, prm, B, dtype, "mga_admm_solve_host");
   if (rc) return rc;
   if (!prm || !y_host || !x_host) { set_error("mga_admm_solve_host: NULL buffer"); return MGA_ERR_INVALID; }
   if (y_rows != p->g.t_in) { set_error("mga_admm_solve_host: y must have t_in rows"); return MGA_ERR_INVALID; }
+  if ((alpha_host != nullptr) != (beta_host != nullptr)) { set_error("mga_admm_solve_host: alpha_host and beta_host go together"); return MGA_ERR_INVALID; }
+  if (n_outer < 0 || max_cg < 0) { set_error("mga_admm_solve_host: bad iteration counts"); return MGA_ERR_INVALID; }
   const GraphDev& g = p->g;
   const size_t es = dtype == MGA_F32 ? 4 : 8;
+  const bool can_res = mode != MGA_MODE_STREAMING && mode != MGA_MODE_STREAMING_POINT && prm->ablation == MGA_ABL_NONE &&
+                       resident_eligible(p, dtype);
+  if (mode == MGA_MODE_RESIDENT && !can_res) {
+    set_error("mga_admm_solve_host: resident mode is not available for this plan / dtype / ablation");
+    return MGA_ERR_UNSUPPORTED;
+  }
+  bool pipelined = can_res;
+  if (const char* e = std::getenv("MGA_HOST_PIPE")) pipelined = pipelined && std::atoi(e) != 0;
+  if (pipelined)
+    return solve_host_pipelined(p, prm, static_cast<const char*>(y_host), y_rows, static_cast<char*>(x_host), B, n_outer,
+                                max_cg, t_mean, t_var, want_diag, diag_host, dx_sum_host, alpha_host, beta_host, mode, chunk);
   if (chunk <= 0) {
     int parts = 4;
     if (const char* e = std::getenv("MGA_HOST_CHUNKS")) parts = std::max(1, std::atoi(e));
@@ -744,21 +893,22 @@ int mga_admm_solve_host(mga_plan* p, const mga_params* prm, const void* y_host, 
   const int64_t nchunk = (int64_t)sizes.size();
   const size_t y_win = (size_t)y_rows * g.N * es, x_win = (size_t)g.T * g.N * es;
   const size_t diag_n = (size_t)n_outer * MGA_DIAG_COLS, dx_n = (size_t)n_outer * g.T * g.N;
-  // device staging: kSlots y-slots, kSlots x-slots, diag + dx_sum accumulators.  Three slots: with four chunks the
-  // upload of chunk 2 no longer waits for chunk 0's solve (its y slot), so all uploads run back to back
+  const bool want_coef = alpha_host && beta_host && max_cg > 0 && n_outer > 0;
+  const size_t coef_rows = (size_t)n_outer * 3 * max_cg;
+  const size_t coef_slot = want_coef ? ((coef_rows * (size_t)chunk * es + 255) & ~(size_t)255) : 0;
+  // device staging: kSlots y-slots, kSlots x-slots, (alpha, beta) per slot, diag + dx_sum accumulators.  Three slots: with
+  // four chunks the upload of chunk 2 no longer waits for chunk 0's solve (its y slot), so all uploads run back to back
   constexpr int kSlots = 3;
-  size_t off_y = 0, off_x = kSlots * (size_t)chunk * y_win, off_d = off_x + kSlots * (size_t)chunk * x_win;
-  off_d = (off_d + 255) & ~(size_t)255;
+  size_t off_y = 0, off_x = kSlots * (size_t)chunk * y_win, off_c = off_x + kSlots * (size_t)chunk * x_win;
+  off_c = (off_c + 255) & ~(size_t)255;
+  size_t off_d = off_c + 2 * kSlots * coef_slot;
   size_t total = off_d + (diag_n + dx_n) * sizeof(double);
   rc = ensure_workspace(p, p->ws_host_io, total);
   if (rc) return rc;
+  if ((rc = host_io_setup(p))) return rc;
   char* base = static_cast<char*>(p->ws_host_io.base);
-  for (auto& s : p->io_streams) if (!s) MGA_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
-  for (auto& ev : p->io_events) if (!ev) MGA_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-  // Resident mode: two chunk solves may run concurrently (one stream per slot), so the tail of one chunk's
-  // persistent grid overlaps the head of the next.  Streaming mode shares one workspace: one run stream.
-  const bool can_res = mode != MGA_MODE_STREAMING && mode != MGA_MODE_STREAMING_POINT && prm->ablation == MGA_ABL_NONE &&
-                       resident_eligible(p, dtype);
+  // Resident mode (MGA_HOST_PIPE=0): two chunk solves may run concurrently (one stream per slot), so the tail of one
+  // chunk's persistent grid overlaps the head of the next.  Streaming mode shares one workspace: one run stream.
   cudaStream_t s_up = p->io_streams[0], s_dn = p->io_streams[3];
   cudaStream_t s_run[2] = {p->io_streams[1], can_res ? p->io_streams[2] : p->io_streams[1]};
   cudaEvent_t* up_done = &p->io_events[0];    // [kSlots] y slot filled
@@ -782,13 +932,17 @@ int mga_admm_solve_host(mga_plan* p, const mga_params* prm, const void* y_host, 
     b_next += nb;
     char* dy = base + off_y + (size_t)slot * chunk * y_win;
     char* dx = base + off_x + (size_t)slot * chunk * x_win;
+    char* da = base + off_c + (size_t)(2 * slot) * coef_slot;
+    char* db = da + coef_slot;
     if (c >= kSlots) MGA_CUDA(cudaStreamWaitEvent(s_up, run_done[slot], 0));
     MGA_CUDA(cudaMemcpyAsync(dy, static_cast<const char*>(y_host) + (size_t)b0 * y_win, (size_t)nb * y_win,
                              cudaMemcpyHostToDevice, s_up));
     MGA_CUDA(cudaEventRecord(up_done[slot], s_up));
     MGA_CUDA(cudaStreamWaitEvent(s_run[rs], up_done[slot], 0));
     if (c >= kSlots) MGA_CUDA(cudaStreamWaitEvent(s_run[rs], x_free[slot], 0));
-    // diagnostics accumulate across chunks (the kernels add into diag / dx_sum)
+    // diagnostics accumulate across chunks (the kernels add into diag / dx_sum); the chunk's CG coefficients land in
+    // a (rows, nb) block of its slot and go to columns [b0, b0 + nb) of the caller's (rows, B) arrays
+    if (want_coef) { outs.alpha = da; outs.beta = db; }
     p->res_slot = rs;
     rc = mga_admm_solve(p, prm, dy, y_rows, nullptr, dx, nb, dtype, n_outer, max_cg, -1.0, -1.0, t_mean, t_var,
                         want_diag | 2, &outs, mode, s_run[rs]);
@@ -798,6 +952,12 @@ int mga_admm_solve_host(mga_plan* p, const mga_params* prm, const void* y_host, 
     MGA_CUDA(cudaStreamWaitEvent(s_dn, run_done[slot], 0));
     MGA_CUDA(cudaMemcpyAsync(static_cast<char*>(x_host) + (size_t)b0 * x_win, dx, (size_t)nb * x_win,
                              cudaMemcpyDeviceToHost, s_dn));
+    if (want_coef) {
+      MGA_CUDA(cudaMemcpy2DAsync(static_cast<char*>(alpha_host) + (size_t)b0 * es, (size_t)B * es, da, (size_t)nb * es,
+                                 (size_t)nb * es, coef_rows, cudaMemcpyDeviceToHost, s_dn));
+      MGA_CUDA(cudaMemcpy2DAsync(static_cast<char*>(beta_host) + (size_t)b0 * es, (size_t)B * es, db, (size_t)nb * es,
+                                 (size_t)nb * es, coef_rows, cudaMemcpyDeviceToHost, s_dn));
+    }
     MGA_CUDA(cudaEventRecord(x_free[slot], s_dn));
   }
   cudaStream_t s_run0 = s_run[0], s_run1 = s_run[1];

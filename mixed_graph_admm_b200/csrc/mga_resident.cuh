@@ -86,7 +86,26 @@ struct ResArgs {
   float rho, rho_u, rho_d, thr;
   float ax, cx, azu, czu, azd, czd;
   float t_mean, t_var;
+  // Host-buffer entry point (mga_admm_solve_host): ONE persistent launch consumes the batch while it is still being
+  // uploaded and hands finished chunks to the download stream.  Chunk c = windows [c * chunk, (c + 1) * chunk).
+  const int* ready;           // device: ready[c] == epoch once the chunk's y (and the flag, in stream order) has landed; NULL: y is there
+  int* done;                  // device: finished windows per chunk (left at 0 again by the CTA that completes the chunk)
+  int* host_done;             // mapped pinned host memory: host_done[c] = epoch when every x of the chunk is in device memory
+  int* abort_flag;            // device: set when a CTA gave up waiting (upload never arrived); the host reports an error
+  int chunk, epoch;
+  int64_t B_coef;             // windows per row of alpha / beta (>= B: this launch may be a slice of the caller's batch)
 };
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
 
 // Shared-memory loads by 32-bit shared address.  The tables hold ABSOLUTE shared addresses (base of
 // pbuf / qbuf folded in when the CTA fills them), so a gather is "LDS.128 [entry + 16 c]" with no
@@ -643,7 +662,25 @@ __global__ void __launch_bounds__(MAXT, MINB) k_admm_resident(const ResArgs a) {
   // Windows are handed out dynamically (one atomic per window): CTAs that share an SM with fewer
   // neighbours near the end of the batch run faster and pick up more of the tail.
   int& s_next = *reinterpret_cast<int*>(red + 64);
+  int& s_abort = *reinterpret_cast<int*>(red + 65);
+  if (threadIdx.x == 0) s_abort = 0;
   for (int64_t b = blockIdx.x; b < a.B;) {
+    if (a.ready) {
+      // the host entry point uploads the batch chunk by chunk while this kernel runs: wait for this window's chunk.
+      // y is then read with ld.global.cg (below): a 128-byte L1 line may straddle two windows of different chunks.
+      if (threadIdx.x == 0) {
+        const int* flag = a.ready + b / a.chunk;
+        if (ld_acquire_gpu(flag) != a.epoch) {
+          const unsigned long long t_start = globaltimer_ns();
+          while (ld_acquire_gpu(flag) != a.epoch) {
+            __nanosleep(256);
+            if (globaltimer_ns() - t_start > 4000000000ull) { s_abort = 1; atomicExch(a.abort_flag, 1); break; }   // 4 s: never hang the device
+          }
+        }
+      }
+      __syncthreads();
+      if (s_abort) return;
+    }
     const int y_rows = MASKM ? T : t_in;
     const float* yw = a.y + (size_t)b * y_rows * N + orig;
     const float* mw = MASKM ? a.mask + (size_t)b * T * N + orig : nullptr;
@@ -654,7 +691,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_admm_resident(const ResArgs a) {
       if (MASKM) {
         float cnt = 0.f, st = 0.f, sy = 0.f, sty = 0.f, st2 = 0.f;
         for (int t = 0; t < T; ++t) {
-          const float m = active ? mw[(size_t)t * N] : 1.f, v = active ? yw[(size_t)t * N] : 0.f, tt = (float)t;
+          const float m = active ? mw[(size_t)t * N] : 1.f, v = active ? __ldcg(yw + (size_t)t * N) : 0.f, tt = (float)t;
           cnt += m; st += tt * m; sy += v * m; sty += tt * v * m; st2 += tt * tt * m;
         }
         const float tm = st / cnt, ym = sy / cnt, tym = sty / cnt, t2m = st2 / cnt;
@@ -663,7 +700,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_admm_resident(const ResArgs a) {
       } else {
         float sy = 0.f, sty = 0.f;
         for (int t = 0; t < t_in; ++t) {
-          const float v = active ? yw[(size_t)t * N] : 0.f;
+          const float v = active ? __ldcg(yw + (size_t)t * N) : 0.f;
           sy += v;
           sty += (float)t * v;
         }
@@ -678,8 +715,8 @@ __global__ void __launch_bounds__(MAXT, MINB) k_admm_resident(const ResArgs a) {
           const int t = t0 + k;
           float v = 0.f;
           if (active && t < T) {
-            if (MASKM) v = (w * (float)t + cc) * (1.f - mw[(size_t)t * N]) + yw[(size_t)t * N];
-            else v = t < t_in ? yw[(size_t)t * N] : w * (float)t + cc;
+            if (MASKM) v = (w * (float)t + cc) * (1.f - mw[(size_t)t * N]) + __ldcg(yw + (size_t)t * N);
+            else v = t < t_in ? __ldcg(yw + (size_t)t * N) : w * (float)t + cc;
           }
           x[k] = v;
           tenth[k] = (active && t < T) ? 0.1f : 0.f;
@@ -709,9 +746,9 @@ __global__ void __launch_bounds__(MAXT, MINB) k_admm_resident(const ResArgs a) {
     }
 
     for (int it = 0; it < a.n_outer; ++it) {
-      float* al = a.alpha ? a.alpha + ((size_t)it * 3) * a.n_cg * a.B + b : nullptr;
-      float* be = a.beta ? a.beta + ((size_t)it * 3) * a.n_cg * a.B + b : nullptr;
-      const size_t sys_stride = (size_t)a.n_cg * a.B;
+      float* al = a.alpha ? a.alpha + ((size_t)it * 3) * a.n_cg * a.B_coef + b : nullptr;
+      float* be = a.beta ? a.beta + ((size_t)it * 3) * a.n_cg * a.B_coef + b : nullptr;
+      const size_t sys_stride = (size_t)a.n_cg * a.B_coef;
       float r[TS];
       // ---- RHS_x (ADMM.py:552-559): Ldr_T(gamma + rho phi)/2 + (rho_u zu + rho_d zd)/2 - (gu+gd)/2 + H^T y
       {
@@ -761,7 +798,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_admm_resident(const ResArgs a) {
           const int t = t0 + k;
           float o = 0.f;
           if (active && t < T) {
-            const float hty = t < y_rows ? yw[(size_t)t * N] : 0.f;
+            const float hty = t < y_rows ? __ldcg(yw + (size_t)t * N) : 0.f;
             o = r[k] - (v[k] + f[k]) / 2.f + hty;
           }
           r[k] = o;
@@ -775,9 +812,9 @@ __global__ void __launch_bounds__(MAXT, MINB) k_admm_resident(const ResArgs a) {
           float m0[TS];
 #pragma unroll
           for (int k = 0; k < TS; ++k) m0[k] = (active && t0 + k < T) ? mw[(size_t)(t0 + k) * N] : 0.f;
-          c.template cg<MGA_SYS_X, true, false>(x, r, a.ax, a.cx, a.n_cg, al, be, a.B, m0);
+          c.template cg<MGA_SYS_X, true, false>(x, r, a.ax, a.cx, a.n_cg, al, be, a.B_coef, m0);
         } else {
-          c.template cg<MGA_SYS_X, false, BANDM>(x, r, a.ax, a.cx, a.n_cg, al, be, a.B, r);
+          c.template cg<MGA_SYS_X, false, BANDM>(x, r, a.ax, a.cx, a.n_cg, al, be, a.B_coef, r);
         }
         if (a.want_diag) {
           float xo[TS];
@@ -804,7 +841,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_admm_resident(const ResArgs a) {
         float z[TS];
         ld_state(ST_ZU, z);
         c.template cg<MGA_SYS_ZU, false>(z, r, a.azu, a.czu, a.n_cg, al ? al + sys_stride : nullptr,
-                                         be ? be + sys_stride : nullptr, a.B, r);
+                                         be ? be + sys_stride : nullptr, a.B_coef, r);
         float x[TS], g[TS];
         ld_state(ST_X, x);
         ld_state(ST_GU, g);
@@ -833,7 +870,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_admm_resident(const ResArgs a) {
         float z[TS];
         ld_state(ST_ZD, z);
         c.template cg<MGA_SYS_ZD, false, BANDM>(z, r, a.azd, a.czd, a.n_cg, al ? al + 2 * sys_stride : nullptr,
-                                         be ? be + 2 * sys_stride : nullptr, a.B, r);
+                                         be ? be + 2 * sys_stride : nullptr, a.B_coef, r);
         float x[TS], g[TS];
         ld_state(ST_X, x);
         ld_state(ST_GD, g);
@@ -878,10 +915,10 @@ __global__ void __launch_bounds__(MAXT, MINB) k_admm_resident(const ResArgs a) {
             if (active && t < T) {
               sg += x[k] * (x[k] - lux[k]);
               if (MASKM) {             // ||x * mask - y|| (ADMM.py:620-621)
-                const float h = x[k] * mw[(size_t)t * N] - yw[(size_t)t * N];
+                const float h = x[k] * mw[(size_t)t * N] - __ldcg(yw + (size_t)t * N);
                 sr += h * h;
               } else if (t < t_in) {
-                const float h = x[k] - yw[(size_t)t * N];
+                const float h = x[k] - __ldcg(yw + (size_t)t * N);
                 sr += h * h;
               }
             }
@@ -959,6 +996,22 @@ __global__ void __launch_bounds__(MAXT, MINB) k_admm_resident(const ResArgs a) {
         }
       }
     }
+    if (a.done) {
+      // hand the finished window to the download stream: stores -> device-scope fence -> CTA barrier -> one count per window;
+      // the CTA that completes a chunk publishes it to the host (system-scope fence, then the flag in mapped host memory)
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        const int c = (int)(b / a.chunk);
+        const int64_t left = a.B - (int64_t)c * a.chunk;
+        const int nwin = (int)(left < a.chunk ? left : a.chunk);
+        if (atomicAdd(a.done + c, 1) + 1 == nwin) {
+          a.done[c] = 0;
+          __threadfence_system();
+          *reinterpret_cast<volatile int*>(a.host_done + c) = a.epoch;
+        }
+      }
+    }
     if (threadIdx.x == 0) s_next = atomicAdd(a.next_window, 1);
     __syncthreads();
     b = (int64_t)gridDim.x + s_next;
@@ -1032,10 +1085,12 @@ inline int launch_res(mga_plan* p, ResArgs& a, const ResGeom& geo, cudaStream_t 
   const size_t smem = a.state_in_smem ? with_state : core;
   int64_t grid = std::min<int64_t>(a.B, (int64_t)occ * p->sm_count);
   if (!a.state_in_smem) {
-    const size_t per_launch = (size_t)grid * geo.state_bytes;      // two launches may be in flight (res_slot)
-    int rc = ensure_workspace(p, p->ws, 2 * (size_t)occ * p->sm_count * geo.state_bytes);
+    // two launches may be in flight (res_slot): each owns a launch-independent half of the scratch, sized for a full
+    // grid - a stride that followed THIS launch's grid let a short last chunk park its state inside its predecessor's
+    const size_t per_slot = (size_t)occ * p->sm_count * geo.state_bytes;
+    int rc = ensure_workspace(p, p->ws, 2 * per_slot);
     if (rc) return rc;
-    a.scratch = reinterpret_cast<float*>(static_cast<char*>(p->ws.base) + (size_t)(p->res_slot & 1) * per_launch);
+    a.scratch = reinterpret_cast<float*>(static_cast<char*>(p->ws.base) + (size_t)(p->res_slot & 1) * per_slot);
   }
   a.next_window = p->r_counters + (p->r_counter_next++ % mga_plan::kCounters) * 32;
   MGA_CUDA(cudaMemsetAsync(a.next_window, 0, sizeof(int), st));

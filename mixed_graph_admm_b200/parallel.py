@@ -53,12 +53,22 @@ def solve_sharded(blk, y, *, mask=None, group=None, gather=False, print_info=Fal
     """Run ``blk.combined_loop`` on this rank's slice of the batch.
 
     ``y_is_global``: ``y`` holds the whole batch on every rank (the slice is taken here);
-    otherwise ``y`` is already the local shard.  The result lists of ``blk`` receive the GLOBAL
-    diagnostics (identical on every rank).  Returns the local ``x`` slice, or the full ``x`` on
-    every rank when ``gather`` (equal shard sizes required by all_gather_into_tensor).
+    otherwise ``y`` is already the local shard.  The residual / regulariser lists of ``blk`` receive
+    the GLOBAL diagnostics (identical on every rank); ``alpha_*`` / ``beta_*`` hold the local
+    windows' coefficients.  Returns the local ``x`` slice, or the full ``x`` on every rank when
+    ``gather``.
+
+    Fixed iteration counts only (``CG_tol <= 0`` and ``ADMM_tol <= 0``): "windows are independent"
+    holds for the arithmetic, but the reference's stop tests are batch-global — the CG test is a
+    max over the batch (ADMM.py:360) and the outer test uses whole-batch norms (ADMM.py:645) —
+    so a shard that tested only its own windows would run different iteration counts than the
+    unsharded call.  Tolerance mode is therefore single-device.
     """
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if world > 1 and (float(blk.CG_tol) > 0 or float(blk.ADMM_tol) > 0):
+        raise ValueError("solve_sharded needs fixed iteration counts (CG_tol <= 0 and ADMM_tol <= 0): the reference's "
+                         "stop tests are batch-global (ADMM.py:360, 645), so tolerance mode cannot be sharded")
     if y_is_global:
         lo, hi = shard_bounds(y.size(0), world)[rank]
         y = y[lo:hi]
@@ -71,7 +81,23 @@ def solve_sharded(blk, y, *, mask=None, group=None, gather=False, print_info=Fal
         blk.diag_reduce = prev
     if not gather or world == 1:
         return x
+    # optional final gather (the only data-path collective; NVLink makes 966 MB at B = 65536 a matter of ms).
+    # Shards may differ by one window: every rank pads to the largest shard, the pads are dropped afterwards.
     xd = x.to(blk.device).contiguous()
-    full = torch.empty((world * xd.size(0),) + tuple(xd.shape[1:]), dtype=xd.dtype, device=xd.device)
-    dist.all_gather_into_tensor(full, xd, group=group)
+    sizes = torch.zeros(world, dtype=torch.int64, device=xd.device if dist.get_backend(group) == "nccl" else "cpu")
+    sizes[rank] = xd.size(0)
+    dist.all_reduce(sizes, op=dist.ReduceOp.SUM, group=group)
+    sizes = sizes.tolist()
+    top = max(sizes)
+    if xd.size(0) < top:
+        xd = torch.cat([xd, xd.new_zeros((top - xd.size(0),) + tuple(xd.shape[1:]))])
+    full = torch.empty((world * top,) + tuple(xd.shape[1:]), dtype=xd.dtype, device=xd.device)
+    if dist.get_backend(group) == "nccl":
+        dist.all_gather_into_tensor(full, xd, group=group)
+    else:
+        parts = [torch.empty_like(xd) for _ in range(world)]
+        dist.all_gather(parts, xd, group=group)
+        full = torch.cat(parts)
+    if min(sizes) != top:
+        full = torch.cat([full[r * top:r * top + n] for r, n in enumerate(sizes)])
     return full.to(x.device)

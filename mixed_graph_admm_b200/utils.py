@@ -71,15 +71,21 @@ def _settle_first(succ, source, n_settle):
     return list(done.items())
 
 
-def k_nearest_neighbors(n_nodes, edges: torch.Tensor, dists: torch.Tensor, k, verbose=False):
+def k_nearest_neighbors(n_nodes, edges: torch.Tensor, dists: torch.Tensor, k, verbose=False, *, native=None):
     """kNN by shortest-path distance (reference ``utils.py:183-204``).
 
     Returns ``(nearest_nodes (N, k+1) int32, nearest_dists (N, k+1) float32)`` with the node
     itself in column 0, ``-1`` / ``inf`` where fewer than ``k+1`` nodes are reachable.
+    ``native`` (not in the reference): ``None`` uses the C++ builder of libmga when it is built,
+    ``False`` forces the pure-Python search (bench.py's reference arm: nothing of the product
+    is loaded there), ``True`` requires the C++ builder.  Both produce the same bits.
     """
-    native = _native_knn(n_nodes, edges, dists, k)
-    if native is not None:
-        return native
+    if native is None or native:
+        tables = _native_knn(n_nodes, edges, dists, k)
+        if tables is not None:
+            return tables
+        if native:
+            raise RuntimeError("k_nearest_neighbors(native=True): libmga.so is not built")
     succ = _adjacency(edges, dists)
     if verbose:
         print(f'{n_nodes} nodes, {k} neighbors')

@@ -180,6 +180,13 @@ def main():
     gi = synth.road_graph(N, 1.1, seed=4)
     make_case("pems04_f32", gi, synth.admm_info(N), synth.signals(1024, t_in, N, seed=0)[:2].contiguous(), ctor,
               fixed(5, 10))
+    # 12. PEMS04 shape in tolerance mode (B = 1, class defaults CG_tol 1e-8): the CG counts of BASELINE.md §2
+    make_case("pems04_tol", gi, synth.admm_info(N), synth.signals(1, t_in, N, seed=1, smooth=True), ctor,
+              {"max_ADMM_iter": 5})
+    # 13. the reference's own call pattern (notebooks): B = 1, float64, T = 24, tolerances
+    ctor24 = dict(use_kNN=True, k=k, u_sigma=50, d_sigma=50, t_in=12, T=24)
+    make_case("pems04_t24_tol_f64", gi, synth.admm_info(N), synth.signals(1, 12, N, seed=1, smooth=True, dtype=torch.float64),
+              ctor24, {"max_ADMM_iter": 6})
 
 
 if __name__ == "__main__":

@@ -18,6 +18,8 @@ def test_reference_arm_prints_the_contract_line():
     assert line["cpu_baseline"]["value"] == line["value"]
     assert line["e2e"] == {"value": line["value"], "unit": "windows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in line["config"] and "model" not in line["config"]
+    # the CPU arm is independent of the product: the kNN tables come from the pure-Python search, libmga.so is never mapped
+    assert line["product_libraries_loaded"] == []
 
 
 def test_reference_arm_other_ranks_exit_silently():

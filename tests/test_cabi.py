@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol(libmga):
     for name in _declared():
         assert hasattr(libmga, name), f"{name} declared in mga.h but not exported"
     assert sorted(_cabi.EXPORTS) == _declared()
-    assert libmga.mga_version() == 100
+    assert libmga.mga_version() == 110
 
 
 def test_library_is_sm100a_with_lineinfo(libmga):

@@ -180,3 +180,33 @@ def test_two_rank_sharding_reproduces_unsharded_diagnostics():
         np.testing.assert_allclose(glr, g.z["glr"], rtol=1e-12)
         np.testing.assert_allclose(dxs, g.z["delta_x_per_step"], rtol=1e-10)
         np.testing.assert_allclose(x, g.z["x"], rtol=0, atol=1e-13)
+
+
+def test_solve_sharded_refuses_tolerance_mode(monkeypatch):
+    """The reference's stop tests are batch-global (ADMM.py:360, 645): a shard cannot run them on its own windows."""
+    from mixed_graph_admm_b200 import parallel
+    g = Golden("tiny_f32")
+    blk = solver_from_golden(g)
+    blk.CG_tol, blk.ADMM_tol = 1e-8, -1.0
+    monkeypatch.setattr(parallel.dist, "is_initialized", lambda: True)
+    monkeypatch.setattr(parallel.dist, "get_world_size", lambda group=None: 2)
+    monkeypatch.setattr(parallel.dist, "get_rank", lambda group=None: 0)
+    with pytest.raises(ValueError, match="fixed iteration counts"):
+        parallel.solve_sharded(blk, g.y)
+
+
+def test_plan_cache_pins_the_tensors_behind_its_key():
+    """The plan cache is keyed by addresses: the cached entry must keep those tensors alive, or a reassigned d_ew
+    could be handed a recycled address and hit a stale plan."""
+    import inspect
+    from mixed_graph_admm_b200 import ADMM
+    src = inspect.getsource(ADMM.ADMM_algorithm._plan)
+    assert "key_tensors" in src
+
+
+def test_knn_pure_python_equals_native(libmga):
+    from mixed_graph_admm_b200 import synth, utils
+    gi = synth.road_graph(60, 1.3, seed=3, isolate_pair=True)
+    a = utils.k_nearest_neighbors(60, gi["u_edges"], gi["u_dist"], 4, native=False)
+    b = utils.k_nearest_neighbors(60, gi["u_edges"], gi["u_dist"], 4, native=True)
+    assert torch.equal(a[0].to(torch.int64), b[0].to(torch.int64)) and torch.equal(a[1], b[1])
