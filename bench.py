@@ -418,6 +418,10 @@ def main():
     blk.mode = args.mode
 
     def e2e_call():
+        # a caller that solves batch after batch clears the result lists between calls (they grow without bound otherwise,
+        # ADMM.py:66-92; here they would also keep every call's pinned alpha / beta blocks alive, and each call would pay
+        # for fresh page-locked allocations)
+        blk._reset_lists(all_lists=True)
         if world > 1:
             return parallel.solve_sharded(blk, y_pin, y_is_global=False)
         return blk.combined_loop(y_pin, print_info=False)

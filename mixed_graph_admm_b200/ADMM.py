@@ -541,6 +541,14 @@ class ADMM_algorithm():
         mean_dx = dx_sum[:nd] / B
         dxs = torch.from_numpy(np.sqrt((mean_dx * mean_dx).sum(2)).astype(np_dt)).to(device)
 
+        # fixed iteration counts (nothing converged): every entry of alpha_* / beta_* is a python list of n_cg (B,)
+        # tensors (quirk Q11) - all rows of the (n_outer, 3, n_cg, B) arrays are unbound in ONE call each
+        rows_a = rows_b = None
+        if alpha is not None and n_done > 0 and bool((cg_iters[:n_done] < 0).all()):
+            n_row = alpha.size(2)
+            rows_a = alpha.to(device).reshape(-1, alpha.size(-1)).unbind(0)
+            rows_b = beta.to(device).reshape(-1, beta.size(-1)).unbind(0)
+
         for i in range(n_done):
             d = diag[i]
             if d[_cabi.DIAG_NONFINITE] > 0:
@@ -549,7 +557,10 @@ class ADMM_algorithm():
             names = ["x", "zu"] + (["zd"] if with_zd else [])
             for s, name in enumerate(names):
                 getattr(self, "CG_iter_" + name).append(its[s])
-                if alpha is not None:
+                if rows_a is not None:
+                    r0 = (i * 3 + s) * n_row
+                    a, b = list(rows_a[r0:r0 + n_row]), list(rows_b[r0:r0 + n_row])
+                elif alpha is not None:
                     n_it = its[s] if its[s] > 0 else int(self.max_CG_iter)
                     a, b = self._coef_lists(alpha[i, s], beta[i, s], its[s], n_it, device)
                 else:

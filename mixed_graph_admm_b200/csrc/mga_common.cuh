@@ -2,11 +2,14 @@
 // Everything here is internal; the public surface is include/mga.h.
 #pragma once
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
 #include <atomic>
+#include <map>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "mga.h"
@@ -85,7 +88,6 @@ struct HostPipe {
   int* host_done;      // device alias of the mapped host array
   int* abort_flag;
   int chunk, epoch;
-  int64_t B_coef;      // windows per row of the alpha / beta arrays
 };
 
 }  // namespace mga
@@ -105,6 +107,7 @@ struct mga_plan {
   cudaEvent_t io_events[10] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   bool has_s2 = false;               // tables of the chunked streaming path
   mga::Graph2 g2{};
+  std::map<std::pair<const void*, int64_t>, CUtensorMap> tmaps;   // TMA descriptors of workspace vectors, by (base, windows)
   int cg_mode = MGA_MODE_AUTO;       // mga_plan_set_cg_mode
   int res_slot = 0;                  // which half of the resident kernel's parking scratch the next launch uses
                                      // (the host entry point runs two chunk solves concurrently)

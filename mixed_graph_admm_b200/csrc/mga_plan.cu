@@ -6,6 +6,7 @@
 // reference stores T identical copies, utils.py:294-295), and builds the in-list (transposed
 // CSR) that turns the reference's scatter_add into an atomics-free gather.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -742,11 +743,12 @@ static int solve_host_pipelined(mga_plan* p, const mga_params* prm, const char* 
   const size_t y_win = (size_t)y_rows * g.N * es, x_win = (size_t)g.T * g.N * es;
   const size_t diag_n = (size_t)n_outer * MGA_DIAG_COLS, dx_n = (size_t)n_outer * g.T * g.N;
   const bool want_coef = alpha_host && beta_host && max_cg > 0 && n_outer > 0;
-  const size_t coef_bytes = want_coef ? (size_t)n_outer * 3 * max_cg * (size_t)B * es : 0;
   // windows per launch: the staging of one launch stays below a cap (default 16 GB); larger batches take several launches
   double cap_gb = 16.0;
   if (const char* e = std::getenv("MGA_HOST_STAGING_GB")) cap_gb = std::max(0.001, std::atof(e));
   const int64_t Bs = std::max<int64_t>(1, std::min<int64_t>(B, (int64_t)(cap_gb * 1e9 / (double)(y_win + x_win))));
+  const size_t coef_rows = (size_t)n_outer * 3 * max_cg;
+  const size_t coef_bytes = want_coef ? coef_rows * (size_t)Bs * es : 0;     // (rows, windows of one launch), compact
   size_t off_x = ((size_t)Bs * y_win + 255) & ~(size_t)255;
   size_t off_d = (off_x + (size_t)Bs * x_win + 255) & ~(size_t)255;
   size_t off_a = (off_d + (diag_n + dx_n) * sizeof(double) + 255) & ~(size_t)255;
@@ -766,6 +768,10 @@ static int solve_host_pipelined(mga_plan* p, const mga_params* prm, const char* 
     outs.dx_sum = d_dx;
     MGA_CUDA(cudaMemsetAsync(d_diag, 0, (diag_n + dx_n) * sizeof(double), s_run));
   }
+  const bool trace = std::getenv("MGA_HOST_TRACE") != nullptr;
+  const auto t_begin = std::chrono::steady_clock::now();
+  auto us = [&]() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_begin).count(); };
+  double t_launch = 0, t_uploads = 0, t_first = 0, t_last = 0, t_run = 0;
   for (int64_t s0 = 0; s0 < B; s0 += Bs) {
     const int64_t nbs = std::min(Bs, B - s0);
     int64_t ck = chunk > 0 ? chunk : std::max<int64_t>(64, (nbs + 63) / 64);
@@ -784,10 +790,9 @@ static int solve_host_pipelined(mga_plan* p, const mga_params* prm, const char* 
     pipe.host_done = p->pipe_host_dev;
     pipe.chunk = (int)ck;
     pipe.epoch = epoch;
-    pipe.B_coef = B;
     if (want_coef) {
-      outs.alpha = base + off_a + (size_t)s0 * es;
-      outs.beta = base + off_b + (size_t)s0 * es;
+      outs.alpha = base + off_a;
+      outs.beta = base + off_b;
     }
     auto upload = [&](int c) -> int {
       const int64_t b0 = (int64_t)c * ck, nb = std::min(ck, nbs - b0);
@@ -803,8 +808,10 @@ static int solve_host_pipelined(mga_plan* p, const mga_params* prm, const char* 
                         want_diag | 2, &outs, mode, s_run);
     p->pipe = nullptr;
     if (rc) { cudaDeviceSynchronize(); return rc; }
+    t_launch = us();
     for (int c = 1; c < nchunk; ++c)
       if ((rc = upload(c))) { cudaDeviceSynchronize(); return rc; }
+    t_uploads = us();
     // hand finished chunks to the download stream as the kernel reports them
     bool kernel_over = false;
     for (int c = 0; c < nchunk; ++c) {
@@ -823,22 +830,30 @@ static int solve_host_pipelined(mga_plan* p, const mga_params* prm, const char* 
         __builtin_ia32_pause();
 #endif
       }
+      if (c == 0) t_first = us();
+      if (c == nchunk - 1) t_last = us();
       const int64_t b0 = (int64_t)c * ck, nb = std::min(ck, nbs - b0);
       MGA_CUDA(cudaMemcpyAsync(x_host + (size_t)(s0 + b0) * x_win, dx + (size_t)b0 * x_win, (size_t)nb * x_win,
                                cudaMemcpyDeviceToHost, s_dn));
     }
     MGA_CUDA(cudaStreamSynchronize(s_run));
-    if (s0 + nbs < B) MGA_CUDA(cudaStreamSynchronize(s_dn));          // the next launch reuses the x staging
-  }
-  if (want_coef) {
-    MGA_CUDA(cudaMemcpyAsync(alpha_host, base + off_a, coef_bytes, cudaMemcpyDeviceToHost, s_dn));
-    MGA_CUDA(cudaMemcpyAsync(beta_host, base + off_b, coef_bytes, cudaMemcpyDeviceToHost, s_dn));
+    t_run = us();
+    if (want_coef) {        // columns [s0, s0 + nbs) of the caller's (rows, B) arrays
+      MGA_CUDA(cudaMemcpy2DAsync(static_cast<char*>(alpha_host) + (size_t)s0 * es, (size_t)B * es, base + off_a, (size_t)nbs * es,
+                                 (size_t)nbs * es, coef_rows, cudaMemcpyDeviceToHost, s_dn));
+      MGA_CUDA(cudaMemcpy2DAsync(static_cast<char*>(beta_host) + (size_t)s0 * es, (size_t)B * es, base + off_b, (size_t)nbs * es,
+                                 (size_t)nbs * es, coef_rows, cudaMemcpyDeviceToHost, s_dn));
+    }
+    if (s0 + nbs < B) MGA_CUDA(cudaStreamSynchronize(s_dn));          // the next launch reuses the staging
   }
   if (want_diag) {
     if (diag_host) MGA_CUDA(cudaMemcpyAsync(diag_host, d_diag, diag_n * sizeof(double), cudaMemcpyDeviceToHost, s_dn));
     if (dx_sum_host) MGA_CUDA(cudaMemcpyAsync(dx_sum_host, d_dx, dx_n * sizeof(double), cudaMemcpyDeviceToHost, s_dn));
   }
   MGA_CUDA(cudaStreamSynchronize(s_dn));
+  if (trace)
+    std::fprintf(stderr, "[mga] host entry (us): launched %.0f, uploads queued %.0f, first chunk done %.0f, last chunk done %.0f, "
+                 "kernel over %.0f, all copies back %.0f\n", t_launch, t_uploads, t_first, t_last, t_run, us());
   return MGA_OK;
 }
 
@@ -862,7 +877,7 @@ int mga_admm_solve_host(mga_plan* p, const mga_params* prm, const void* y_host, 
     set_error("mga_admm_solve_host: resident mode is not available for this plan / dtype / ablation");
     return MGA_ERR_UNSUPPORTED;
   }
-  bool pipelined = can_res;
+  bool pipelined = can_res && p->g.temporal != MGA_TEMPORAL_BAND;      // (the banded line graph keeps chunked launches)
   if (const char* e = std::getenv("MGA_HOST_PIPE")) pipelined = pipelined && std::atoi(e) != 0;
   if (pipelined)
     return solve_host_pipelined(p, prm, static_cast<const char*>(y_host), y_rows, static_cast<char*>(x_host), B, n_outer,

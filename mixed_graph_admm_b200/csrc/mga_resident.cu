@@ -127,11 +127,9 @@ int resident_admm(mga_plan* p, const mga_params* m, const void* y, const void* m
   a.azu = (float)(m->rho_u / 2); a.czu = (float)m->mu_u;
   a.azd = (float)(m->rho_d / 2); a.czd = (float)m->mu_d2;
   a.t_mean = (float)t_mean; a.t_var = (float)t_var;
-  a.B_coef = B;
   if (p->pipe) {
     a.ready = p->pipe->ready; a.done = p->pipe->done; a.host_done = p->pipe->host_done; a.abort_flag = p->pipe->abort_flag;
     a.chunk = p->pipe->chunk; a.epoch = p->pipe->epoch;
-    if (p->pipe->B_coef > 0) a.B_coef = p->pipe->B_coef;
   }
   if (a.want_diag && !(diag_flags & 2)) {
     if (a.diag) MGA_CUDA(cudaMemsetAsync(a.diag, 0, (size_t)n_outer * MGA_DIAG_COLS * sizeof(double), st));

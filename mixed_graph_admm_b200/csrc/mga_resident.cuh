@@ -50,6 +50,9 @@
 #ifndef MGA_RES_TAB_SMEM
 #define MGA_RES_TAB_SMEM 1
 #endif
+#ifndef MGA_RES_LDCG      // 0: plain (L1-cached) loads of y (experiments; the host entry point needs ld.global.cg)
+#define MGA_RES_LDCG 1
+#endif
 #ifndef MGA_RES_MINB      // CTAs per SM the <= 320-thread instantiations are compiled for
 #define MGA_RES_MINB 2
 #endif
@@ -93,9 +96,15 @@ struct ResArgs {
   int* host_done;             // mapped pinned host memory: host_done[c] = epoch when every x of the chunk is in device memory
   int* abort_flag;            // device: set when a CTA gave up waiting (upload never arrived); the host reports an error
   int chunk, epoch;
-  int64_t B_coef;             // windows per row of alpha / beta (>= B: this launch may be a slice of the caller's batch)
 };
 
+template <bool CG>
+__device__ __forceinline__ float ldy(const float* p) {
+#if MGA_RES_LDCG
+  if (CG) return __ldcg(p);
+#endif
+  return *p;
+}
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
   int v;
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -616,7 +625,10 @@ __global__ void __launch_bounds__(MAXT, MINB) k_cg_resident(const ResArgs a, con
 }
 
 // VAR: 0 = forecasting on the kNN / physical / first-difference temporal graph, 1 = mask mode, 2 = banded line graph
-template <int CH, int K, int MAXT, int MINB, int VAR>
+// PIPE: the launch of the host entry point (mga_admm_solve_host), which waits for each chunk of y to arrive and reports
+// finished chunks.  A separate instantiation: carrying the hand-shake in the kernel of the device entry point cost it
+// 4 % (measured: 471 k vs 490 k windows/s at B = 1024) although it only runs once per window.
+template <int CH, int K, int MAXT, int MINB, int VAR, bool PIPE>
 __global__ void __launch_bounds__(MAXT, MINB) k_admm_resident(const ResArgs a) {
   constexpr int TS = 4 * CH;
   constexpr bool MASKM = VAR == 1, BANDM = VAR == 2;
@@ -663,9 +675,9 @@ __global__ void __launch_bounds__(MAXT, MINB) k_admm_resident(const ResArgs a) {
   // neighbours near the end of the batch run faster and pick up more of the tail.
   int& s_next = *reinterpret_cast<int*>(red + 64);
   int& s_abort = *reinterpret_cast<int*>(red + 65);
-  if (threadIdx.x == 0) s_abort = 0;
+  if (PIPE && threadIdx.x == 0) s_abort = 0;
   for (int64_t b = blockIdx.x; b < a.B;) {
-    if (a.ready) {
+    if (PIPE) {
       // the host entry point uploads the batch chunk by chunk while this kernel runs: wait for this window's chunk.
       // y is then read with ld.global.cg (below): a 128-byte L1 line may straddle two windows of different chunks.
       if (threadIdx.x == 0) {
@@ -691,7 +703,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_admm_resident(const ResArgs a) {
       if (MASKM) {
         float cnt = 0.f, st = 0.f, sy = 0.f, sty = 0.f, st2 = 0.f;
         for (int t = 0; t < T; ++t) {
-          const float m = active ? mw[(size_t)t * N] : 1.f, v = active ? __ldcg(yw + (size_t)t * N) : 0.f, tt = (float)t;
+          const float m = active ? mw[(size_t)t * N] : 1.f, v = active ? ldy<PIPE>(yw + (size_t)t * N) : 0.f, tt = (float)t;
           cnt += m; st += tt * m; sy += v * m; sty += tt * v * m; st2 += tt * tt * m;
         }
         const float tm = st / cnt, ym = sy / cnt, tym = sty / cnt, t2m = st2 / cnt;
@@ -700,7 +712,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_admm_resident(const ResArgs a) {
       } else {
         float sy = 0.f, sty = 0.f;
         for (int t = 0; t < t_in; ++t) {
-          const float v = active ? __ldcg(yw + (size_t)t * N) : 0.f;
+          const float v = active ? ldy<PIPE>(yw + (size_t)t * N) : 0.f;
           sy += v;
           sty += (float)t * v;
         }
@@ -715,8 +727,8 @@ __global__ void __launch_bounds__(MAXT, MINB) k_admm_resident(const ResArgs a) {
           const int t = t0 + k;
           float v = 0.f;
           if (active && t < T) {
-            if (MASKM) v = (w * (float)t + cc) * (1.f - mw[(size_t)t * N]) + __ldcg(yw + (size_t)t * N);
-            else v = t < t_in ? __ldcg(yw + (size_t)t * N) : w * (float)t + cc;
+            if (MASKM) v = (w * (float)t + cc) * (1.f - mw[(size_t)t * N]) + ldy<PIPE>(yw + (size_t)t * N);
+            else v = t < t_in ? ldy<PIPE>(yw + (size_t)t * N) : w * (float)t + cc;
           }
           x[k] = v;
           tenth[k] = (active && t < T) ? 0.1f : 0.f;
@@ -746,9 +758,9 @@ __global__ void __launch_bounds__(MAXT, MINB) k_admm_resident(const ResArgs a) {
     }
 
     for (int it = 0; it < a.n_outer; ++it) {
-      float* al = a.alpha ? a.alpha + ((size_t)it * 3) * a.n_cg * a.B_coef + b : nullptr;
-      float* be = a.beta ? a.beta + ((size_t)it * 3) * a.n_cg * a.B_coef + b : nullptr;
-      const size_t sys_stride = (size_t)a.n_cg * a.B_coef;
+      float* al = a.alpha ? a.alpha + ((size_t)it * 3) * a.n_cg * a.B + b : nullptr;
+      float* be = a.beta ? a.beta + ((size_t)it * 3) * a.n_cg * a.B + b : nullptr;
+      const size_t sys_stride = (size_t)a.n_cg * a.B;
       float r[TS];
       // ---- RHS_x (ADMM.py:552-559): Ldr_T(gamma + rho phi)/2 + (rho_u zu + rho_d zd)/2 - (gu+gd)/2 + H^T y
       {
@@ -798,7 +810,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_admm_resident(const ResArgs a) {
           const int t = t0 + k;
           float o = 0.f;
           if (active && t < T) {
-            const float hty = t < y_rows ? __ldcg(yw + (size_t)t * N) : 0.f;
+            const float hty = t < y_rows ? ldy<PIPE>(yw + (size_t)t * N) : 0.f;
             o = r[k] - (v[k] + f[k]) / 2.f + hty;
           }
           r[k] = o;
@@ -812,9 +824,9 @@ __global__ void __launch_bounds__(MAXT, MINB) k_admm_resident(const ResArgs a) {
           float m0[TS];
 #pragma unroll
           for (int k = 0; k < TS; ++k) m0[k] = (active && t0 + k < T) ? mw[(size_t)(t0 + k) * N] : 0.f;
-          c.template cg<MGA_SYS_X, true, false>(x, r, a.ax, a.cx, a.n_cg, al, be, a.B_coef, m0);
+          c.template cg<MGA_SYS_X, true, false>(x, r, a.ax, a.cx, a.n_cg, al, be, a.B, m0);
         } else {
-          c.template cg<MGA_SYS_X, false, BANDM>(x, r, a.ax, a.cx, a.n_cg, al, be, a.B_coef, r);
+          c.template cg<MGA_SYS_X, false, BANDM>(x, r, a.ax, a.cx, a.n_cg, al, be, a.B, r);
         }
         if (a.want_diag) {
           float xo[TS];
@@ -841,7 +853,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_admm_resident(const ResArgs a) {
         float z[TS];
         ld_state(ST_ZU, z);
         c.template cg<MGA_SYS_ZU, false>(z, r, a.azu, a.czu, a.n_cg, al ? al + sys_stride : nullptr,
-                                         be ? be + sys_stride : nullptr, a.B_coef, r);
+                                         be ? be + sys_stride : nullptr, a.B, r);
         float x[TS], g[TS];
         ld_state(ST_X, x);
         ld_state(ST_GU, g);
@@ -870,7 +882,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_admm_resident(const ResArgs a) {
         float z[TS];
         ld_state(ST_ZD, z);
         c.template cg<MGA_SYS_ZD, false, BANDM>(z, r, a.azd, a.czd, a.n_cg, al ? al + 2 * sys_stride : nullptr,
-                                         be ? be + 2 * sys_stride : nullptr, a.B_coef, r);
+                                         be ? be + 2 * sys_stride : nullptr, a.B, r);
         float x[TS], g[TS];
         ld_state(ST_X, x);
         ld_state(ST_GD, g);
@@ -915,10 +927,10 @@ __global__ void __launch_bounds__(MAXT, MINB) k_admm_resident(const ResArgs a) {
             if (active && t < T) {
               sg += x[k] * (x[k] - lux[k]);
               if (MASKM) {             // ||x * mask - y|| (ADMM.py:620-621)
-                const float h = x[k] * mw[(size_t)t * N] - __ldcg(yw + (size_t)t * N);
+                const float h = x[k] * mw[(size_t)t * N] - ldy<PIPE>(yw + (size_t)t * N);
                 sr += h * h;
               } else if (t < t_in) {
-                const float h = x[k] - __ldcg(yw + (size_t)t * N);
+                const float h = x[k] - ldy<PIPE>(yw + (size_t)t * N);
                 sr += h * h;
               }
             }
@@ -996,7 +1008,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_admm_resident(const ResArgs a) {
         }
       }
     }
-    if (a.done) {
+    if (PIPE) {
       // hand the finished window to the download stream: stores -> device-scope fence -> CTA barrier -> one count per window;
       // the CTA that completes a chunk publishes it to the host (system-scope fence, then the flag in mapped host memory)
       __threadfence();
@@ -1070,7 +1082,8 @@ inline int res_forced_ch() {
 
 template <int CH, int K, int MAXT, int MINB, int VAR>
 inline int launch_res(mga_plan* p, ResArgs& a, const ResGeom& geo, cudaStream_t st) {
-  auto kern = k_admm_resident<CH, K, MAXT, MINB, VAR>;
+  if (a.ready && VAR != 0) { set_error("resident: the pipelined host launch is built for the forecasting kernel only"); return MGA_ERR_UNSUPPORTED; }
+  auto kern = (a.ready && VAR == 0) ? k_admm_resident<CH, K, MAXT, MINB, VAR, VAR == 0> : k_admm_resident<CH, K, MAXT, MINB, VAR, false>;
   const size_t core = geo.core_bytes;
   const size_t with_state = core + geo.state_bytes;
   // State in shared memory only if it does not cost residency: compare CTAs/SM both ways.

@@ -557,6 +557,10 @@ __device__ __forceinline__ void stage3(const Graph2& g, const Item3& t, const Sm
     for (int k = tid; k < t.nt; k += nt) s.wself[k] = g.wself_d[t.n0 + k];
 }
 
+}  // namespace mga
+#include "mga_stream4.cuh"
+namespace mga {
+
 // (r, p) -> p', qs = shifted L_d p'   [SRC 2: x0 -> qs]
 template <int SRC, int K>
 __global__ void __launch_bounds__(1024, 1) k3_p_ldr(Graph2 g, int64_t B, int it, const float* __restrict__ r,
@@ -1115,6 +1119,138 @@ static int k3_ctas_per_sm(const void* kern, int threads, size_t smem, int* rc) {
   return n;
 }
 
+// ---- fused TMA-staged kernels (mga_stream4.cuh): eligibility, tensor maps, launch -------------------------------
+struct K4Plan {
+  bool ok;
+  int nstage, rows_box, nbox, rows_tile;
+  size_t smem[2];        // by SYS
+};
+
+static size_t k4_smem_bytes(const Graph2& g, int nstage, int rows_tile, int sys) {
+  const size_t N = g.N, kf = sys == 0 ? g.kd3 : g.ku3, n_in = sys == 0 ? g.in_ptr3_total : 0;
+  return (size_t)nstage * 2 * rows_tile * kCB4 * 16 + 4 * N * 4 + (2 * N + 2) * 4 + N * kf * 8 + n_in * 8 + 2 * (size_t)nstage * 8 + 32 * 4;
+}
+
+static K4Plan k4_plan(const mga_plan* p) {
+  const Graph2& g = p->g2;
+  K4Plan k{};
+  int want = 1;
+  if (const char* e = std::getenv("MGA_S4")) want = std::atoi(e);
+  // one all-node tile of 8-chunk rows (the PEMS-sized graphs at T >= 29); node-tiled plans keep the k3 kernels
+  if (!want || g.CB3 != kCB4 || g.ntile3 != 1 || g.db3 || g.C4 < kCB4 || g.N > kCons4) return k;
+  k.nbox = (g.N + 255) / 256;
+  k.rows_box = (g.N + k.nbox - 1) / k.nbox;
+  k.rows_tile = k.rows_box * k.nbox;
+  int stages = 2;
+  if (const char* e = std::getenv("MGA_S4_STAGES")) stages = std::max(2, std::min(4, std::atoi(e)));
+  k.nstage = stages;
+  for (int sys = 0; sys < 2; ++sys) {
+    k.smem[sys] = k4_smem_bytes(g, k.nstage, k.rows_tile, sys);
+    if (k.smem[sys] > (size_t)p->max_smem_optin) return k;
+  }
+  k.ok = true;
+  return k;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// (4 C4 floats, N rows, B windows) view of a node-major workspace vector; box = {32 floats, rows_box, 1}
+static int k4_map(mga_plan* p, const float* v, int64_t B, int rows_box, const CUtensorMap** out) {
+  static EncodeTiledFn encode = [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) fn = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(fn);
+  }();
+  if (!encode) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return MGA_ERR_CUDA; }
+  const auto key = std::make_pair(static_cast<const void*>(v), B);
+  auto it = p->tmaps.find(key);
+  if (it == p->tmaps.end()) {
+    if (p->tmaps.size() > 64) p->tmaps.clear();
+    const Graph2& g = p->g2;
+    CUtensorMap m;
+    const cuuint64_t dims[3] = {(cuuint64_t)g.C4 * 4, (cuuint64_t)g.N, (cuuint64_t)B};
+    const cuuint64_t strides[2] = {(cuuint64_t)g.C4 * 16, (cuuint64_t)g.N * g.C4 * 16};
+    const cuuint32_t box[3] = {kCB4 * 4, (cuuint32_t)rows_box, 1};
+    const cuuint32_t es[3] = {1, 1, 1};
+    const CUresult r = encode(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(v), dims, strides, box, es,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")"); return MGA_ERR_CUDA; }
+    it = p->tmaps.emplace(key, m).first;
+  }
+  *out = &it->second;
+  return MGA_OK;
+}
+
+template <int SYS, int SRC, int K>
+static int k4_launch(mga_plan* p, const K4Plan& k4, const CUtensorMap* mr, const CUtensorMap* mp, const CUtensorMap* mn,
+                     const K4Args& a, cudaStream_t st) {
+  auto kern = k4_cg<SYS, SRC, K>;
+  static std::mutex mu;
+  static std::map<int, size_t> limit;            // per device: the opt-in limit only ever grows
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    size_t& lim = limit[p->device];
+    if (k4.smem[SYS] > lim) {
+      MGA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k4.smem[SYS]));
+      lim = k4.smem[SYS];
+    }
+  }
+  kern<<<std::min(a.total, p->sm_count), kThreads4, k4.smem[SYS], st>>>(*mr, *mp, *mn, p->g2, a);
+  MGA_LAUNCH_CHECK("k4_cg");
+  return MGA_OK;
+}
+
+template <int SYS, int SRC>
+static int k4_launch_k(mga_plan* p, const K4Plan& k4, const CUtensorMap* mr, const CUtensorMap* mp, const CUtensorMap* mn,
+                       const K4Args& a, cudaStream_t st) {
+  const int K = SYS == 0 ? p->g2.kd3 : p->g2.ku3;
+  if (K == 4) return k4_launch<SYS, SRC, 4>(p, k4, mr, mp, mn, a, st);
+  if (K == 6) return k4_launch<SYS, SRC, 6>(p, k4, mr, mp, mn, a, st);
+  if (K == 8) return k4_launch<SYS, SRC, 8>(p, k4, mr, mp, mn, a, st);
+  return k4_launch<SYS, SRC, 0>(p, k4, mr, mp, mn, a, st);
+}
+
+// one CG solve with the fused kernels: per iteration k4_cg (r, p -> p', Ap, <p', Ap>) + k2_xr
+static int cg4(mga_plan* p, const K4Plan& k4, int system, const float* rhs, const float* x0, float* x, int64_t B, int n_cg,
+               float a, float c, const Bufs2& w, cudaStream_t st) {
+  const Graph2& g = p->g2;
+  const dim3 fgrid((unsigned)B, (g.N * g.C4 + kFlat - 1) / kFlat);
+  K4Args ka{};
+  ka.B = B; ka.nstage = k4.nstage; ka.rows_box = k4.rows_box; ka.nbox = k4.nbox; ka.rows_tile = k4.rows_tile;
+  ka.tiles = (g.C4 + kCB4 - 1) / kCB4;
+  ka.total = (int)B * ka.tiles;
+  ka.a = a; ka.cc = c; ka.xsys = system == MGA_SYS_X;
+  ka.dots = w.dots;
+  const CUtensorMap *m_x0, *m_r, *m_p[2];
+  int rc;
+  if ((rc = k4_map(p, x0, B, k4.rows_box, &m_x0)) || (rc = k4_map(p, w.r, B, k4.rows_box, &m_r)) ||
+      (rc = k4_map(p, w.p, B, k4.rows_box, &m_p[0])) || (rc = k4_map(p, w.p2, B, k4.rows_box, &m_p[1])))
+    return rc;
+  // r = rhs - A x0, RR(0)
+  ka.it = 0; ka.v_r = x0; ka.v_p = nullptr; ka.rhs = rhs; ka.out = w.r; ka.slot = w.dots;
+  rc = system == MGA_SYS_ZU ? k4_launch_k<1, 2>(p, k4, m_x0, m_x0, m_x0, ka, st) : k4_launch_k<0, 2>(p, k4, m_x0, m_x0, m_x0, ka, st);
+  if (rc) return rc;
+  int cur = 0;                                   // p_old = w.p (never read in the first iteration), p_new = w.p2
+  float* pbuf[2] = {w.p, w.p2};
+  for (int it = 0; it < n_cg; ++it) {
+    ka.it = it; ka.v_r = w.r; ka.v_p = pbuf[cur]; ka.rhs = nullptr; ka.out = w.ap;
+    ka.slot = w.dots + (size_t)(2 * it + 1) * B;
+    if (system == MGA_SYS_ZU)
+      rc = it == 0 ? k4_launch_k<1, 1>(p, k4, m_r, m_p[cur], m_p[cur ^ 1], ka, st) : k4_launch_k<1, 0>(p, k4, m_r, m_p[cur], m_p[cur ^ 1], ka, st);
+    else
+      rc = it == 0 ? k4_launch_k<0, 1>(p, k4, m_r, m_p[cur], m_p[cur ^ 1], ka, st) : k4_launch_k<0, 0>(p, k4, m_r, m_p[cur], m_p[cur ^ 1], ka, st);
+    if (rc) return rc;
+    k2_xr<<<fgrid, kFlat, 0, st>>>(g, B, it, it == 0 ? x0 : x, x, w.r, pbuf[cur ^ 1], w.ap, w.dots);
+    MGA_LAUNCH_CHECK("k2_xr");
+    cur ^= 1;
+  }
+  return MGA_OK;
+}
+
 // CG_solver (ADMM.py:329-368) with a fixed iteration count on internal-layout vectors; x holds x0 / the solution.
 // x0: warm start (read only); x: the solution (x0 == x: in place).  With n_cg == 0 the solution IS the warm start.
 static int cg2(mga_plan* p, int system, const mga_params* m, const float* rhs, const float* x0, float* x, int64_t B,
@@ -1128,7 +1264,11 @@ static int cg2(mga_plan* p, int system, const mga_params* m, const float* rhs, c
   else { a = (float)(m->rho_d / 2); c = (float)m->mu_d2; }
   const int xsys = system == MGA_SYS_X;
   MGA_CUDA(cudaMemsetAsync(w.dots, 0, (size_t)(2 * n_cg + 1) * B * sizeof(double), st));
-  if (g.CB3 > 0) {
+  const K4Plan k4 = k4_plan(p);
+  if (k4.ok) {
+    const int rc4 = cg4(p, k4, system, rhs, x0, x, B, n_cg, a, c, w, st);
+    if (rc4) return rc4;
+  } else if (g.CB3 > 0) {
     // time-tiled shared-memory kernels: p update fused into the operator kernel, p ping-ponged
     const dim3 blk3(g.CB3, g.NB3t);
     const int total = (int)B * g.tiles3 * g.ntile3;

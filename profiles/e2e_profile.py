@@ -20,6 +20,7 @@ torch.cuda.synchronize()
 n = 20
 t0 = time.perf_counter()
 for _ in range(n):
+    blk._reset_lists(all_lists=True)
     blk.combined_loop(yp, print_info=False)
 torch.cuda.synchronize()
 dt = (time.perf_counter() - t0) / n
@@ -27,6 +28,26 @@ print(f"B={B}: {dt * 1e3:.3f} ms per call, {B / dt:.0f} windows/s")
 pr = cProfile.Profile()
 pr.enable()
 for _ in range(n):
+    blk._reset_lists(all_lists=True)
     blk.combined_loop(yp, print_info=False)
 pr.disable()
+for knob, val in (("MGA_HOST_PIPE", "0"), ("MGA_HOST_CHUNK", "32"), ("MGA_HOST_CHUNK", "128"), ("MGA_HOST_CHUNK", "256")):
+    os.environ[knob] = val
+    for _ in range(3):
+        blk._reset_lists(all_lists=True)
+        blk.combined_loop(yp, print_info=False)
+    t0 = time.perf_counter()
+    for _ in range(n):
+        blk._reset_lists(all_lists=True)
+        blk.combined_loop(yp, print_info=False)
+    dt = (time.perf_counter() - t0) / n
+    print(f"{knob}={val}: {dt * 1e3:.3f} ms per call, {B / dt:.0f} windows/s")
+    del os.environ[knob]
+blk.keep_cg_coefficients = False
+t0 = time.perf_counter()
+for _ in range(n):
+    blk._reset_lists(all_lists=True)
+    blk.combined_loop(yp, print_info=False)
+dt = (time.perf_counter() - t0) / n
+print(f"without the CG coefficients: {dt * 1e3:.3f} ms per call, {B / dt:.0f} windows/s")
 pstats.Stats(pr).sort_stats("cumulative").print_stats(18)
