@@ -7,6 +7,7 @@
 #include <stdint.h>
 
 #include <atomic>
+#include <cstdlib>
 #include <map>
 #include <string>
 #include <utility>
@@ -72,8 +73,16 @@ struct Graph2 {
   const int2* tab_d; const int2* tab_u; const int2* tab_in3;
   const int* in_ptr3;
   const int* ord3;         // (N) row order of k3_ldrt_lhs: descending in-list length
+  const int* ord4;         // (N) row order of k4_cg's phase C: ord3 dealt to the warps of a consumer group in snake order
   const float* wself_d;    // (N)
 };
+
+// consumer threads of the fused TMA kernels (mga_stream4.cuh); MGA_S4_NC overrides
+inline void k4_env(int* cons) {
+  int nc = 768;
+  if (const char* e = std::getenv("MGA_S4_NC")) nc = std::atoi(e) >= 768 ? 768 : 512;
+  *cons = nc;
+}
 
 struct Workspace {
   void* base = nullptr;

@@ -1123,12 +1123,14 @@ static int k3_ctas_per_sm(const void* kern, int threads, size_t smem, int* rc) {
 struct K4Plan {
   bool ok;
   int nstage, rows_box, nbox, rows_tile;
+  int cons;              // consumer threads of the instantiation (512 / 768)
   size_t smem[2];        // by SYS
 };
 
 static size_t k4_smem_bytes(const Graph2& g, int nstage, int rows_tile, int sys) {
   const size_t N = g.N, kf = sys == 0 ? g.kd3 : g.ku3, n_in = sys == 0 ? g.in_ptr3_total : 0;
-  return (size_t)nstage * 2 * rows_tile * kCB4 * 16 + 4 * N * 4 + (2 * N + 2) * 4 + N * kf * 8 + n_in * 8 + 2 * (size_t)nstage * 8 + 32 * 4;
+  return (size_t)nstage * 2 * rows_tile * kCB4 * 16 + 4 * (size_t)rows_tile * 16 + 5 * N * 4 + (2 * N + 2) * 4 + N * kf * 8 +
+         n_in * 8 + (2 * (size_t)nstage + 2) * 8 + (size_t)nstage * 4 + 16;
 }
 
 static K4Plan k4_plan(const mga_plan* p) {
@@ -1136,14 +1138,14 @@ static K4Plan k4_plan(const mga_plan* p) {
   K4Plan k{};
   int want = 1;
   if (const char* e = std::getenv("MGA_S4")) want = std::atoi(e);
+  k4_env(&k.cons);
   // one all-node tile of 8-chunk rows (the PEMS-sized graphs at T >= 29); node-tiled plans keep the k3 kernels
-  if (!want || g.CB3 != kCB4 || g.ntile3 != 1 || g.db3 || g.C4 < kCB4 || g.N > kCons4) return k;
+  if (!want || g.CB3 != kCB4 || g.ntile3 != 1 || g.db3 || g.C4 < kCB4 || g.N > k.cons) return k;
   k.nbox = (g.N + 255) / 256;
-  k.rows_box = (g.N + k.nbox - 1) / k.nbox;
+  k.rows_box = ((g.N + k.nbox - 1) / k.nbox + 7) & ~7;     // whole 128-byte lines in the halo buffer (TMA destinations)
+  if (k.rows_box > 256) return k;
   k.rows_tile = k.rows_box * k.nbox;
-  int stages = 2;
-  if (const char* e = std::getenv("MGA_S4_STAGES")) stages = std::max(2, std::min(4, std::atoi(e)));
-  k.nstage = stages;
+  k.nstage = 2;
   for (int sys = 0; sys < 2; ++sys) {
     k.smem[sys] = k4_smem_bytes(g, k.nstage, k.rows_tile, sys);
     if (k.smem[sys] > (size_t)p->max_smem_optin) return k;
@@ -1156,8 +1158,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-// (4 C4 floats, N rows, B windows) view of a node-major workspace vector; box = {32 floats, rows_box, 1}
-static int k4_map(mga_plan* p, const float* v, int64_t B, int rows_box, const CUtensorMap** out) {
+// (4 C4 floats, N rows, B windows) view of a node-major workspace vector; box = {box_w floats, rows_box, 1}
+static int k4_map(mga_plan* p, const float* v, int64_t B, int box_w, int rows_box, CUtensorMap* out) {
   static EncodeTiledFn encode = [] {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult q;
@@ -1165,7 +1167,7 @@ static int k4_map(mga_plan* p, const float* v, int64_t B, int rows_box, const CU
     return reinterpret_cast<EncodeTiledFn>(fn);
   }();
   if (!encode) { set_error("cuTensorMapEncodeTiled is not available from this driver"); return MGA_ERR_CUDA; }
-  const auto key = std::make_pair(static_cast<const void*>(v), B);
+  const auto key = std::make_pair(static_cast<const void*>(v), B * 64 + box_w);
   auto it = p->tmaps.find(key);
   if (it == p->tmaps.end()) {
     if (p->tmaps.size() > 64) p->tmaps.clear();
@@ -1173,7 +1175,7 @@ static int k4_map(mga_plan* p, const float* v, int64_t B, int rows_box, const CU
     CUtensorMap m;
     const cuuint64_t dims[3] = {(cuuint64_t)g.C4 * 4, (cuuint64_t)g.N, (cuuint64_t)B};
     const cuuint64_t strides[2] = {(cuuint64_t)g.C4 * 16, (cuuint64_t)g.N * g.C4 * 16};
-    const cuuint32_t box[3] = {kCB4 * 4, (cuuint32_t)rows_box, 1};
+    const cuuint32_t box[3] = {(cuuint32_t)box_w, (cuuint32_t)rows_box, 1};
     const cuuint32_t es[3] = {1, 1, 1};
     const CUresult r = encode(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(v), dims, strides, box, es,
                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -1181,14 +1183,13 @@ static int k4_map(mga_plan* p, const float* v, int64_t B, int rows_box, const CU
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")"); return MGA_ERR_CUDA; }
     it = p->tmaps.emplace(key, m).first;
   }
-  *out = &it->second;
+  *out = it->second;
   return MGA_OK;
 }
 
-template <int SYS, int SRC, int K>
-static int k4_launch(mga_plan* p, const K4Plan& k4, const CUtensorMap* mr, const CUtensorMap* mp, const CUtensorMap* mn,
-                     const K4Args& a, cudaStream_t st) {
-  auto kern = k4_cg<SYS, SRC, K>;
+template <int SYS, int SRC, int K, int NC>
+static int k4_launch(mga_plan* p, const K4Plan& k4, const K4Maps& maps, const K4Args& a, cudaStream_t st) {
+  auto kern = k4_cg<SYS, SRC, K, NC>;
   static std::mutex mu;
   static std::map<int, size_t> limit;            // per device: the opt-in limit only ever grows
   {
@@ -1199,19 +1200,24 @@ static int k4_launch(mga_plan* p, const K4Plan& k4, const CUtensorMap* mr, const
       lim = k4.smem[SYS];
     }
   }
-  kern<<<std::min(a.total, p->sm_count), kThreads4, k4.smem[SYS], st>>>(*mr, *mp, *mn, p->g2, a);
+  kern<<<std::min(a.total, p->sm_count), NC + 32, k4.smem[SYS], st>>>(maps, p->g2, a);
   MGA_LAUNCH_CHECK("k4_cg");
   return MGA_OK;
 }
 
+template <int SYS, int SRC, int K>
+static int k4_launch_nc(mga_plan* p, const K4Plan& k4, const K4Maps& maps, const K4Args& a, cudaStream_t st) {
+  if (k4.cons == 768) return k4_launch<SYS, SRC, K, 768>(p, k4, maps, a, st);
+  return k4_launch<SYS, SRC, K, 512>(p, k4, maps, a, st);
+}
+
 template <int SYS, int SRC>
-static int k4_launch_k(mga_plan* p, const K4Plan& k4, const CUtensorMap* mr, const CUtensorMap* mp, const CUtensorMap* mn,
-                       const K4Args& a, cudaStream_t st) {
+static int k4_launch_k(mga_plan* p, const K4Plan& k4, const K4Maps& maps, const K4Args& a, cudaStream_t st) {
   const int K = SYS == 0 ? p->g2.kd3 : p->g2.ku3;
-  if (K == 4) return k4_launch<SYS, SRC, 4>(p, k4, mr, mp, mn, a, st);
-  if (K == 6) return k4_launch<SYS, SRC, 6>(p, k4, mr, mp, mn, a, st);
-  if (K == 8) return k4_launch<SYS, SRC, 8>(p, k4, mr, mp, mn, a, st);
-  return k4_launch<SYS, SRC, 0>(p, k4, mr, mp, mn, a, st);
+  if (K == 4) return k4_launch_nc<SYS, SRC, 4>(p, k4, maps, a, st);
+  if (K == 6) return k4_launch_nc<SYS, SRC, 6>(p, k4, maps, a, st);
+  if (K == 8) return k4_launch_nc<SYS, SRC, 8>(p, k4, maps, a, st);
+  return k4_launch_nc<SYS, SRC, 0>(p, k4, maps, a, st);
 }
 
 // one CG solve with the fused kernels: per iteration k4_cg (r, p -> p', Ap, <p', Ap>) + k2_xr
@@ -1225,24 +1231,33 @@ static int cg4(mga_plan* p, const K4Plan& k4, int system, const float* rhs, cons
   ka.total = (int)B * ka.tiles;
   ka.a = a; ka.cc = c; ka.xsys = system == MGA_SYS_X;
   ka.dots = w.dots;
-  const CUtensorMap *m_x0, *m_r, *m_p[2];
   int rc;
-  if ((rc = k4_map(p, x0, B, k4.rows_box, &m_x0)) || (rc = k4_map(p, w.r, B, k4.rows_box, &m_r)) ||
-      (rc = k4_map(p, w.p, B, k4.rows_box, &m_p[0])) || (rc = k4_map(p, w.p2, B, k4.rows_box, &m_p[1])))
-    return rc;
+  // tensor maps (cached per vector): tile boxes {32 floats, rows_box, 1}, halo boxes {4 floats, rows_box, 1}
+  K4Maps m_init{}, m_it[2]{};
+  const float* pbuf_c[2] = {w.p, w.p2};
+  if ((rc = k4_map(p, x0, B, kCB4 * 4, k4.rows_box, &m_init.r)) || (rc = k4_map(p, x0, B, 4, k4.rows_box, &m_init.r_halo))) return rc;
+  m_init.p = m_init.pnew = m_init.r;
+  m_init.p_halo = m_init.r_halo;
+  for (int cur = 0; cur < 2; ++cur) {            // p_old = pbuf[cur], p_new = pbuf[cur ^ 1]
+    if ((rc = k4_map(p, w.r, B, kCB4 * 4, k4.rows_box, &m_it[cur].r)) || (rc = k4_map(p, w.r, B, 4, k4.rows_box, &m_it[cur].r_halo)) ||
+        (rc = k4_map(p, pbuf_c[cur], B, kCB4 * 4, k4.rows_box, &m_it[cur].p)) ||
+        (rc = k4_map(p, pbuf_c[cur], B, 4, k4.rows_box, &m_it[cur].p_halo)) ||
+        (rc = k4_map(p, pbuf_c[cur ^ 1], B, kCB4 * 4, k4.rows_box, &m_it[cur].pnew)))
+      return rc;
+  }
   // r = rhs - A x0, RR(0)
-  ka.it = 0; ka.v_r = x0; ka.v_p = nullptr; ka.rhs = rhs; ka.out = w.r; ka.slot = w.dots;
-  rc = system == MGA_SYS_ZU ? k4_launch_k<1, 2>(p, k4, m_x0, m_x0, m_x0, ka, st) : k4_launch_k<0, 2>(p, k4, m_x0, m_x0, m_x0, ka, st);
+  ka.it = 0; ka.rhs = rhs; ka.out = w.r; ka.slot = w.dots;
+  rc = system == MGA_SYS_ZU ? k4_launch_k<1, 2>(p, k4, m_init, ka, st) : k4_launch_k<0, 2>(p, k4, m_init, ka, st);
   if (rc) return rc;
   int cur = 0;                                   // p_old = w.p (never read in the first iteration), p_new = w.p2
   float* pbuf[2] = {w.p, w.p2};
   for (int it = 0; it < n_cg; ++it) {
-    ka.it = it; ka.v_r = w.r; ka.v_p = pbuf[cur]; ka.rhs = nullptr; ka.out = w.ap;
+    ka.it = it; ka.rhs = nullptr; ka.out = w.ap;
     ka.slot = w.dots + (size_t)(2 * it + 1) * B;
     if (system == MGA_SYS_ZU)
-      rc = it == 0 ? k4_launch_k<1, 1>(p, k4, m_r, m_p[cur], m_p[cur ^ 1], ka, st) : k4_launch_k<1, 0>(p, k4, m_r, m_p[cur], m_p[cur ^ 1], ka, st);
+      rc = it == 0 ? k4_launch_k<1, 1>(p, k4, m_it[cur], ka, st) : k4_launch_k<1, 0>(p, k4, m_it[cur], ka, st);
     else
-      rc = it == 0 ? k4_launch_k<0, 1>(p, k4, m_r, m_p[cur], m_p[cur ^ 1], ka, st) : k4_launch_k<0, 0>(p, k4, m_r, m_p[cur], m_p[cur ^ 1], ka, st);
+      rc = it == 0 ? k4_launch_k<0, 1>(p, k4, m_it[cur], ka, st) : k4_launch_k<0, 0>(p, k4, m_it[cur], ka, st);
     if (rc) return rc;
     k2_xr<<<fgrid, kFlat, 0, st>>>(g, B, it, it == 0 ? x0 : x, x, w.r, pbuf[cur ^ 1], w.ap, w.dots);
     MGA_LAUNCH_CHECK("k2_xr");

@@ -6,26 +6,32 @@
 // k2_xr (24 B/pt) a CG iteration of the 2-hop systems moves 40 B/pt in 2 launches (k3: 52 in 3; algorithmic: 48).
 //
 // A persistent CTA per SM walks (window, time tile) items.  A tile is ALL nodes x 8 chunks (32 time steps) of r and p:
-//   * a producer warp (one elected lane) stages the next tile while the 16 consumer warps work on the current one:
+//   * a producer warp (one elected lane) stages the next tile while the consumer warps work on the current one:
 //     cp.async.bulk.tensor (TMA) 3-D boxes {32 floats, <= 256 node rows, 1 window} of a (T, N, B) tensor map, completion
 //     on an mbarrier (expect-tx); out-of-range rows / columns are zero-filled by the TMA unit, so partial tiles and the
-//     rounding of the node rows to whole boxes need no code.  Two stages (full / empty barrier pairs).
+//     rounding of the node rows to whole boxes need no code.  Two stages (full / empty barrier pairs).  The same lane
+//     computes beta of the tile's window (it can afford the latency of the two loads) and leaves it with the stage.
+//   * L_d^T L_d couples t-1, t, t+1, so a tile needs p' one step beyond each edge, for every node.  Those halo columns
+//     come through TMA as well: boxes {4 floats, node rows, 1} left and right of the tile into one small buffer with its
+//     own barrier pair (free again as soon as phase A has consumed it).  Fetching them with per-thread loads - 4 scalars
+//     per node and tile, whatever the mechanism: registers or 4-byte cp.async - cost 45 of 160 us per launch: 32 distinct
+//     sectors per warp instruction sit in the same LSU queue as the shared-memory gathers.
 //   * phase A: p' = r + beta p in place in the r tile; one thread then hands the tile to a TMA store (p' -> HBM),
 //   * phase B: qs = shifted L_d p' (gathers from the p' tile, table entries = (row byte offset, weight)) overwrites the
-//     dead p tile,
-//   * phase C: Ap = D p' + c (q - in-list gather of qs), streamed to HBM, <p', Ap> reduced per tile.
-//   L_d^T L_d couples t-1, t, t+1, so a tile needs p' one step beyond each edge, for every node: those two halo
-//   scalars per node are fetched by the consumer threads one tile ahead (plain loads, registers), q at the tile's
-//   first step is then one scalar gather per node.
+//     dead p tile; q at the tile's first step is one scalar gather per node from the halo column,
+//   * phase C: Ap = D p' + c (q - in-list gather of qs), streamed to HBM, <p', Ap> added per warp.
 // Thread = one 16-byte chunk (4 time steps of one node); the 8 lanes of a quarter-warp own the 8 chunks of one row, so a
-// neighbour's chunk gather is a conflict-free 128-byte shared-memory wavefront.
+// neighbour's chunk gather is a conflict-free 128-byte shared-memory wavefront, and the element next to a chunk comes
+// from the neighbouring lane by shuffle.
 #pragma once
 #include <cuda.h>
 
+#ifndef MGA_K4_X            // timing experiments only (bit mask): 1 no phase-C gather, 2 no phase-B gather, 4 no p' TMA store,
+#define MGA_K4_X 0          // 8 no Ap store, 16 no halo fetch, 32 no phase A, 64 no first-step q gather
+#endif
+
 namespace mga {
 
-constexpr int kCons4 = 512;                // consumer threads (16 warps)
-constexpr int kThreads4 = kCons4 + 32;     // + the producer warp
 constexpr int kCB4 = 8;                    // chunks per tile row
 
 struct K4Args {
@@ -33,8 +39,6 @@ struct K4Args {
   int it;
   int nstage, rows_box, nbox, rows_tile;   // rows_tile = rows_box * nbox >= N
   int tiles, total;                        // time tiles per window, B * tiles
-  const float* v_r;      // the vector behind map_r: r (SRC 0 / 1) or x0 (SRC 2) - halo scalars
-  const float* v_p;      // p_old (SRC 0)
   const float* rhs;      // SRC 2
   float* out;            // Ap (SRC 0 / 1) or r = rhs - A x0 (SRC 2)
   const double* dots;    // RR(k) = dots[2k], PAP(k) = dots[2k+1], each (B)
@@ -76,88 +80,88 @@ __device__ __forceinline__ void tma_commit() { asm volatile("cp.async.bulk.commi
 __device__ __forceinline__ void tma_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void bar_cons() { asm volatile("bar.sync 1, %0;" ::"n"(kCons4) : "memory"); }
+template <int NC>
+__device__ __forceinline__ void bar_cons() { asm volatile("bar.sync 1, %0;" ::"n"(NC) : "memory"); }
 
-// halo scalars of tile (b, c0) for node n: the element before the tile's first chunk and the one after its last
-struct Halo4 {
-  float rl, rr, pl, pr;
+struct K4Maps {          // tile boxes {32 floats, rows_box, 1} and halo boxes {4 floats, rows_box, 1} of the same vectors
+  CUtensorMap r, p, pnew, r_halo, p_halo;
 };
-template <int SRC>
-__device__ __forceinline__ Halo4 halo_fetch(const Graph2& g, const K4Args& a, int b, int c0, int n) {
-  Halo4 h{0.f, 0.f, 0.f, 0.f};
-  const size_t row = ((size_t)b * g.N + n) * (size_t)g.C4;
-  if (c0 > 0) {
-    const size_t k = (row + c0) * 4 - 1;
-    h.rl = __ldg(a.v_r + k);
-    if (SRC == 0) h.pl = __ldg(a.v_p + k);
-  }
-  if (c0 + kCB4 < g.C4) {
-    const size_t k = (row + c0 + kCB4) * 4;
-    h.rr = __ldg(a.v_r + k);
-    if (SRC == 0) h.pr = __ldg(a.v_p + k);
-  }
-  return h;
-}
 
 // SYS 0: A = diag + c L_d^T L_d (x / z_d systems), SYS 1: A = c L_u + a I (z_u system)
 // SRC 0: v = r + beta p (stored as the new p)   SRC 1: v = r (first iteration; stored as p)   SRC 2: v = x0, out = rhs - A v
 // K: compile-time width of the forward table (0: run-time)
-template <int SYS, int SRC, int K>
-__global__ void __launch_bounds__(kThreads4, 1)
-k4_cg(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ CUtensorMap map_p,
-      const __grid_constant__ CUtensorMap map_pnew, const Graph2 g, const K4Args a) {
+// NC: consumer threads (a multiple of 32 and of 8, >= N); the block has NC + 32 threads (one producer warp)
+template <int SYS, int SRC, int K, int NC>
+__global__ void __launch_bounds__(NC + 32, 1)
+k4_cg(const __grid_constant__ K4Maps maps, const Graph2 g, const K4Args a) {
   extern __shared__ __align__(128) unsigned char smem4[];
   const int N = g.N, C4 = g.C4, T = g.T;
   const int tid = threadIdx.x;
   const size_t tile_f4 = (size_t)a.rows_tile * kCB4;                 // float4 per tile buffer
   float4* tiles = reinterpret_cast<float4*>(smem4);                  // [stage][R | P][rows_tile * 8]
-  float* hl = reinterpret_cast<float*>(tiles + 2 * tile_f4 * a.nstage);
-  float* hr = hl + N;
-  float* qsl = hr + N;
-  float* wself = qsl + N;
+  float4* hbuf = tiles + 2 * tile_f4 * a.nstage;                     // [r left, r right, p left, p right][rows_tile]: halo chunks
+  float* hl = reinterpret_cast<float*>(hbuf + 4 * (size_t)a.rows_tile);   // p' one step before the tile, per node
+  float* hr = hl + N;                                                // p' one step after the tile
+  float* qsl = hr + N;                                               // q at the tile's first step
+  float* p0 = qsl + N;                                               // p' at the tile's first step
+  float* wself = p0 + N;
   int* ptr = reinterpret_cast<int*>(wself + N);                      // (N + 1) in-list offsets        [SYS 0]
   int* ord = ptr + N + 1;                                            // (N) row order of phase C         [SYS 0]
   const int kf = SYS == 0 ? g.kd3 : g.ku3;
-  int2* tab = reinterpret_cast<int2*>(ord + N + ((2 * N + 1) & 1));  // forward table (N, kf), 8-byte aligned (4 N floats + 2 N + 1 ints before it)
+  int2* tab = reinterpret_cast<int2*>(ord + N + ((N & 1) ^ 1));      // forward table (N, kf), 8-byte aligned: 7 N + 1 words precede it (odd iff N is even)
   int2* tab_in = tab + (size_t)N * kf;                               // in-list entries                  [SYS 0]
   const int n_in = SYS == 0 ? g.in_ptr3_total : 0;
   uint64_t* bars = reinterpret_cast<uint64_t*>(tab_in + n_in);       // full[nstage], empty[nstage]
-  float* red = reinterpret_cast<float*>(bars + 2 * a.nstage);
   uint64_t* full = bars;
   uint64_t* empty = bars + a.nstage;
+  uint64_t* hfull = bars + 2 * a.nstage;                             // the halo buffer: one barrier pair
+  uint64_t* hempty = hfull + 1;
+  float* beta_s = reinterpret_cast<float*>(hempty + 1);              // (nstage) beta of the window of the staged tile
 
-  // ---- one-time staging of the graph tables (all threads), barrier init
-  {
-    const int2* src = SYS == 0 ? g.tab_d : g.tab_u;
-    for (int k = tid; k < N * kf; k += kThreads4) tab[k] = src[k];
-    if (SYS == 0) {
-      for (int k = tid; k < n_in; k += kThreads4) tab_in[k] = g.tab_in3[k];
-      for (int k = tid; k <= N; k += kThreads4) ptr[k] = g.in_ptr3[k];
-      for (int k = tid; k < N; k += kThreads4) { ord[k] = g.ord3[k]; wself[k] = g.wself_d[k]; }
-    }
-    if (tid == 0) {
-      for (int s = 0; s < a.nstage; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, 1); }
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    fence_async_smem();
-    __syncthreads();
+  // ---- barrier init, then the producer starts fetching while the consumers stage the graph tables
+  if (tid == 0) {
+    for (int s = 0; s < a.nstage; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, NC / 32); }
+    mbar_init(hfull, 1);
+    mbar_init(hempty, NC / 32);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
+  fence_async_smem();
+  __syncthreads();
   const uint32_t stage_bytes = (uint32_t)(tile_f4 * 16) * (SRC == 0 ? 2u : 1u);
+  const uint32_t halo_bytes = (uint32_t)(a.rows_tile * 16) * (SRC == 0 ? 4u : 2u);
+  const bool want_halo = SYS == 0 && !(MGA_K4_X & 16);
 
-  if (tid >= kCons4) {
+  if (tid >= NC) {
     // ================= producer warp: one lane keeps the stages full =================
-    if (tid == kCons4) {
+    if (tid == NC) {
       int k = 0;
       for (int tl = blockIdx.x; tl < a.total; tl += gridDim.x, ++k) {
         const int s = k % a.nstage, ph = (k / a.nstage) & 1;
         const int b = tl / a.tiles, c0 = (tl - b * a.tiles) * kCB4;
         mbar_wait(empty + s, ph ^ 1);                                // first pass over the stages: free at once
+        // beta of the tile's window travels with the stage: this lane can afford the load latency, the consumers cannot
+        // (written before the arrive on `full`, whose release / acquire pair publishes it)
+        if (SRC == 0) beta_s[s] = (float)a.dots[(size_t)(2 * a.it) * a.B + b] / (float)a.dots[(size_t)(2 * a.it - 2) * a.B + b];   // ADMM.py:356
         mbar_expect_tx(full + s, stage_bytes);
         float4* tR = tiles + (size_t)s * 2 * tile_f4;
         float4* tP = tR + tile_f4;
         for (int j = 0; j < a.nbox; ++j) {
-          tma_load3(tR + (size_t)j * a.rows_box * kCB4, &map_r, 4 * c0, j * a.rows_box, b, full + s);
-          if (SRC == 0) tma_load3(tP + (size_t)j * a.rows_box * kCB4, &map_p, 4 * c0, j * a.rows_box, b, full + s);
+          tma_load3(tR + (size_t)j * a.rows_box * kCB4, &maps.r, 4 * c0, j * a.rows_box, b, full + s);
+          if (SRC == 0) tma_load3(tP + (size_t)j * a.rows_box * kCB4, &maps.p, 4 * c0, j * a.rows_box, b, full + s);
+        }
+        if (want_halo) {
+          // the halo buffer is free once phase A of the previous tile has read it; columns outside the window are zero-filled
+          mbar_wait(hempty, (k & 1) ^ 1);
+          mbar_expect_tx(hfull, halo_bytes);
+          for (int j = 0; j < a.nbox; ++j) {
+            const int r0 = j * a.rows_box;
+            tma_load3(hbuf + r0, &maps.r_halo, 4 * c0 - 4, r0, b, hfull);
+            tma_load3(hbuf + a.rows_tile + r0, &maps.r_halo, 4 * (c0 + kCB4), r0, b, hfull);
+            if (SRC == 0) {
+              tma_load3(hbuf + 2 * a.rows_tile + r0, &maps.p_halo, 4 * c0 - 4, r0, b, hfull);
+              tma_load3(hbuf + 3 * a.rows_tile + r0, &maps.p_halo, 4 * (c0 + kCB4), r0, b, hfull);
+            }
+          }
         }
       }
     }
@@ -165,18 +169,22 @@ k4_cg(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ CUtenso
   }
 
   // ================= consumers =================
-  const int lane = tid & 31, wp = tid >> 5;
+  {
+    const int2* src = SYS == 0 ? g.tab_d : g.tab_u;
+    for (int k = tid; k < N * kf; k += NC) tab[k] = src[k];
+    if (SYS == 0) {
+      for (int k = tid; k < n_in; k += NC) tab_in[k] = g.tab_in3[k];
+      for (int k = tid; k <= N; k += NC) ptr[k] = g.in_ptr3[k];
+      for (int k = tid; k < N; k += NC) { ord[k] = g.ord4[k]; wself[k] = g.wself_d[k]; }
+    }
+  }
+  // (published to the other consumers by the barrier that ends phase A of the first tile)
+  const int lane = tid & 31;
   const bool self_in = g.in_self3 != 0;
-  const int col = tid & 7;                   // items advance by kCons4 (a multiple of 8): a thread keeps its column
-  Halo4 hn{0.f, 0.f, 0.f, 0.f};
-  float beta_n = 0.f;
-  auto prefetch = [&](int tl) {              // halo scalars and beta of tile `tl`, one tile ahead of their use
-    if (tl >= a.total) return;
-    const int b = tl / a.tiles, c0 = (tl - b * a.tiles) * kCB4;
-    if (tid < N) hn = halo_fetch<SRC>(g, a, b, c0, tid);
-    if (SRC == 0) beta_n = (float)a.dots[(size_t)(2 * a.it) * a.B + b] / (float)a.dots[(size_t)(2 * a.it - 2) * a.B + b];   // ADMM.py:356
-  };
-  prefetch(blockIdx.x);
+  const int col = tid & 7;                   // items advance by NC (a multiple of 8): a thread keeps its column
+  // the node of this thread in the per-node steps: spread over all warps (every (NC / N)-th thread)
+  const int nstep = NC / N > 0 ? NC / N : 1;
+  const int node = (tid % nstep == 0 && tid / nstep < N) ? tid / nstep : -1;
   int k = 0;
   for (int tl = blockIdx.x; tl < a.total; tl += gridDim.x, ++k) {
     const int s = k % a.nstage, ph = (k / a.nstage) & 1;
@@ -185,28 +193,44 @@ k4_cg(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ CUtenso
     const bool cok = c < C4;
     float4* tR = tiles + (size_t)s * 2 * tile_f4;
     float4* tP = tR + tile_f4;
-    const Halo4 h = hn;
-    const float beta = beta_n;
-    prefetch(tl + gridDim.x);
     mbar_wait(full + s, ph);
+    const float beta = SRC == 0 ? beta_s[s] : 0.f;
 
     // ---- phase A: p' = r + beta p, in place
-    if (SRC == 0) {
-      for (int item = tid; item < N * kCB4; item += kCons4) {
+    if (SRC == 0 && !(MGA_K4_X & 32)) {
+      for (int item = tid; item < N * kCB4; item += NC) {
         float4 v = tR[item];
         const float4 q = tP[item];
         v.x += beta * q.x; v.y += beta * q.y; v.z += beta * q.z; v.w += beta * q.w;
         tR[item] = v;
+        if (SYS == 0 && col == 0) p0[item >> 3] = v.x;
       }
+    } else if (SYS == 0 && col == 0) {
+      for (int item = tid; item < N * kCB4; item += NC) p0[item >> 3] = tR[item].x;
     }
-    if (SYS == 0 && tid < N) {
-      hl[tid] = SRC == 0 ? h.rl + beta * h.pl : h.rl;
-      hr[tid] = SRC == 0 ? h.rr + beta * h.pr : h.rr;
+    if (want_halo) {
+      mbar_wait(hfull, k & 1);
+      if (node >= 0) {
+        const float* hb = reinterpret_cast<const float*>(hbuf);
+        const float rl = hb[node * 4 + 3], rr = hb[((size_t)a.rows_tile + node) * 4];      // last of the chunk before, first of the chunk after
+        if (SRC == 0) {
+          hl[node] = rl + beta * hb[((size_t)2 * a.rows_tile + node) * 4 + 3];
+          hr[node] = rr + beta * hb[((size_t)3 * a.rows_tile + node) * 4];
+        } else {
+          hl[node] = rl;
+          hr[node] = rr;
+        }
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(hempty);
+    } else if (SYS == 0 && node >= 0) {
+      hl[node] = 0.f;
+      hr[node] = 0.f;
     }
     fence_async_smem();                      // generic-proxy writes of p' -> visible to the TMA store
-    bar_cons();
-    if (SRC != 2 && tid == 0) {              // p' -> HBM (rows beyond N / columns beyond the row are clipped by the map)
-      for (int j = 0; j < a.nbox; ++j) tma_store3(&map_pnew, tR + (size_t)j * a.rows_box * kCB4, 4 * c0, j * a.rows_box, b);
+    bar_cons<NC>();
+    if (SRC != 2 && tid == 0 && !(MGA_K4_X & 4)) {   // p' -> HBM (rows beyond N / columns beyond the row are clipped by the map)
+      for (int j = 0; j < a.nbox; ++j) tma_store3(&maps.pnew, tR + (size_t)j * a.rows_box * kCB4, 4 * c0, j * a.rows_box, b);
       tma_commit();
     }
 
@@ -218,58 +242,67 @@ k4_cg(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ CUtenso
       {
         const char* mine = reinterpret_cast<const char*>(tR + col);
         const bool v1 = tt + 1 < T, v2 = tt + 2 < T, v3 = tt + 3 < T, v4 = tt + 4 < T;
-        for (int item = tid; item < N * kCB4; item += kCons4) {
+        for (int it0 = tid - lane; it0 < N * kCB4; it0 += NC) {              // warp-uniform trips: the shuffle needs every lane
+          const bool on = it0 + lane < N * kCB4;
+          const int item = on ? it0 + lane : N * kCB4 - 1;
           const int n = item >> 3;
           const float4 own = tR[item];
-          const float nxt = col < kCB4 - 1 ? tR[item + 1].x : hr[n];
+          const float up = __shfl_down_sync(0xffffffffu, own.x, 1);          // the next chunk of the row is the next lane's
+          const float nxt = col < kCB4 - 1 ? up : hr[n];
           const float ws = wself[n];
-          const float4 acc = gather3<K>(tab + n * kf, kf, mine, make_float4(ws * own.x, ws * own.y, ws * own.z, ws * own.w));
+          float4 acc = make_float4(ws * own.x, ws * own.y, ws * own.z, ws * own.w);
+          if (!(MGA_K4_X & 2)) acc = gather3<K>(tab + n * kf, kf, mine, acc);
           float4 o;
           o.x = v1 ? own.y - acc.x : 0.f;
           o.y = v2 ? own.z - acc.y : 0.f;
           o.z = v3 ? own.w - acc.z : 0.f;
           o.w = v4 ? nxt - acc.w : 0.f;
-          tP[item] = o;
+          if (on) tP[item] = o;
         }
         // q at the tile's first step, one scalar gather per node: q[4 c0] = p'[4 c0] - sum_j w_j p'_nbr[4 c0 - 1]; q[0] = 0 (ADMM.py:176)
-        if (tid < N) {
+        if (node >= 0) {
           float qv = 0.f;
-          if (c0 > 0 && 4 * c0 < T) {
-            float acc = wself[tid] * hl[tid];
-            const int2* row = tab + tid * kf;
+          if (c0 > 0 && 4 * c0 < T && !(MGA_K4_X & 64)) {
+            float acc = wself[node] * hl[node];
+            const int2* row = tab + node * kf;
             for (int j = 0; j < kf; ++j) {
               const int2 e = row[j];
               acc += __int_as_float(e.y) * hl[e.x >> 7];             // entry = (row * 128 bytes, weight)
             }
-            qv = tR[tid * kCB4].x - acc;
+            qv = p0[node] - acc;
           }
-          qsl[tid] = qv;
+          qsl[node] = qv;
         }
       }
-      bar_cons();
+      bar_cons<NC>();
       // ---- phase C: Ap = D p' + c (q - f), f = in-list gather of qs (ADMM.py:200-209 as a gather, scatter order kept)
-      if (cok) {
+      {
         const char* mine = reinterpret_cast<const char*>(tP + col);
         const float4* rw = reinterpret_cast<const float4*>(a.rhs) + w0 + c;
         float4* ow = reinterpret_cast<float4*>(a.out) + w0 + c;
         float hx[4], tv[4];                  // H^T H keeps rows t < t_in (ADMM.py:372-374); pads (t >= T) stay 0
 #pragma unroll
         for (int j = 0; j < 4; ++j) { hx[j] = (a.xsys && tt + j < g.t_in) ? 1.f : 0.f; tv[j] = tt + j < T ? 1.f : 0.f; }
-        for (int item = tid; item < N * kCB4; item += kCons4) {
+        for (int it0 = tid - lane; it0 < N * kCB4; it0 += NC) {
+          const bool on = cok && it0 + lane < N * kCB4;                     // (columns beyond the row: zero-filled tile, nothing to store)
+          const int item = it0 + lane < N * kCB4 ? it0 + lane : N * kCB4 - 1;
           const int n = ord[item >> 3];
           const int idx = n * kCB4 + col;
           const float4 pv = tR[idx];
-          float4 rh;
-          if (SRC == 2) rh = __ldcs(rw + (size_t)n * C4);
+          float4 rh = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (SRC == 2 && on) rh = __ldcs(rw + (size_t)n * C4);
           const float4 q1 = tP[idx];
-          const float qprev = col > 0 ? tP[idx - 1].w : qsl[n];
+          const float dn = __shfl_up_sync(0xffffffffu, q1.w, 1);
+          const float qprev = col > 0 ? dn : qsl[n];
           const float ws = self_in ? wself[n] : 0.f;
           float4 f = make_float4(ws * q1.x, ws * q1.y, ws * q1.z, ws * q1.w);
           int e = ptr[n];
           const int e1 = ptr[n + 1];
-          for (; e + 4 <= e1; e += 4) f = gather3<4>(tab_in + e, 4, mine, f);
-          if (e + 2 <= e1) { f = gather3<2>(tab_in + e, 2, mine, f); e += 2; }
-          if (e < e1) f = gather3<1>(tab_in + e, 1, mine, f);
+          if (!(MGA_K4_X & 1)) {
+            for (; e + 4 <= e1; e += 4) f = gather3<4>(tab_in + e, 4, mine, f);
+            if (e + 2 <= e1) { f = gather3<2>(tab_in + e, 2, mine, f); e += 2; }
+            if (e < e1) f = gather3<1>(tab_in + e, 1, mine, f);
+          }
           const float pp[4] = {pv.x, pv.y, pv.z, pv.w};
           const float q[4] = {qprev, q1.x, q1.y, q1.z};
           const float ff[4] = {f.x, f.y, f.z, f.w};
@@ -282,8 +315,9 @@ k4_cg(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ CUtenso
             else val = a.cc * l + a.a * pp[j];                               // ADMM.py:394
             o[j] = tv[j] * val;
           }
+          if (!on) continue;
           if (SRC != 2) {
-            __stcs(ow + (size_t)n * C4, make_float4(o[0], o[1], o[2], o[3]));
+            if (!(MGA_K4_X & 8)) __stcs(ow + (size_t)n * C4, make_float4(o[0], o[1], o[2], o[3]));
             dot += (pp[0] * o[0] + pp[1] * o[1]) + (pp[2] * o[2] + pp[3] * o[3]);
           } else {
             const float r0 = rh.x - o[0], r1 = rh.y - o[1], r2 = rh.z - o[2], r3 = rh.w - o[3];
@@ -298,7 +332,7 @@ k4_cg(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ CUtenso
         const char* mine = reinterpret_cast<const char*>(tR + col);
         const float4* rw = reinterpret_cast<const float4*>(a.rhs) + w0 + c;
         float4* ow = reinterpret_cast<float4*>(a.out) + w0 + c;
-        for (int item = tid; item < N * kCB4; item += kCons4) {
+        for (int item = tid; item < N * kCB4; item += NC) {
           const int n = item >> 3;
           float4 rh;
           if (SRC == 2) rh = __ldcs(rw + (size_t)n * C4);
@@ -320,16 +354,13 @@ k4_cg(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ CUtenso
         }
       }
     }
-    // ---- per-tile dot product and release of the stage
+    // ---- per-warp: dot product of the tile and release of the stage (no CTA-wide barrier: the next tile's phase A only
+    // touches its own stage and hl / hr / p0, which nobody reads after the barrier that ended phase B)
     dot = warp_sum<float>(dot);
-    if (lane == 0) red[wp] = dot;
     if (SRC != 2 && tid == 0) tma_wait_read();       // the p' store has read its tile
-    bar_cons();
-    if (tid == 0) {
-      float t = 0.f;
-#pragma unroll
-      for (int w = 0; w < kCons4 / 32; ++w) t += red[w];
-      atomicAdd(a.slot + b, (double)t);
+    __syncwarp();
+    if (lane == 0) {
+      atomicAdd(a.slot + b, (double)dot);
       mbar_arrive(empty + s);
     }
   }
