@@ -70,6 +70,33 @@ class _Plan:
             pass
 
 
+_RESULT_LISTS = ("alpha_x", "beta_x", "alpha_zu", "beta_zu", "alpha_zd", "beta_zd", "CG_iter_x", "CG_iter_zu", "CG_iter_zd",
+                 "p_res_list", "d_res_list", "x_shift_list", "delta_x_per_step", "DGTV_list", "DGLR_list", "GLR_list",
+                 "recover_list")
+
+
+class _ResultList:
+    """The result lists of the reference (ADMM.py:66-92) are plain python lists on the instance, and they are here too -
+    but a call with ``print_info=False`` only records what it has to append (the diagnostics sums and the CG coefficient
+    arrays, already on the host); the entries - a few hundred tensor views per call - are created when a list is first
+    read.  Reading, appending to or replacing a list behaves exactly as with eager filling."""
+
+    def __init__(self, name):
+        self.slot = "_" + name
+
+    def __get__(self, obj, cls):
+        if obj is None:
+            return self
+        if obj._pending:
+            obj._flush_pending()
+        return obj.__dict__[self.slot]
+
+    def __set__(self, obj, value):
+        if obj.__dict__.get("_pending"):
+            obj._flush_pending()
+        obj.__dict__[self.slot] = value
+
+
 class ADMM_algorithm():
     '''
     only with 1 head (reference ADMM.py:11-14)
@@ -79,9 +106,14 @@ class ADMM_algorithm():
     the reference prints from graph construction).
     '''
 
+    for _name in _RESULT_LISTS:
+        locals()[_name] = _ResultList(_name)
+    del _name
+
     def __init__(self, graph_info, ADMM_info, use_kNN=False, k=4, u_sigma=None, d_sigma=None, expand_time_dim=True,
                  ablation='None', t_in=12, T=24, use_line_graph=False, skip_connection=1, *, device=None,
                  mode='auto', verbose=False):
+        self._pending = []              # calls whose result-list entries have not been materialised yet (_ResultList)
         self.t_in = t_in
         self.T = T
         self.use_line_graph = use_line_graph
@@ -157,7 +189,16 @@ class ADMM_algorithm():
         self._device_arg, self._device = value, None
 
     # ------------------------------------------------------------------ bookkeeping
+    def _flush_pending(self):
+        pending, self._pending = self._pending, []
+        for args in pending:
+            self._fill_lists(*args)
+
     def _reset_lists(self, all_lists):
+        if all_lists:
+            self._pending = []          # every list is replaced: what was pending for them is void
+        elif self._pending:
+            self._flush_pending()       # recover_list survives init_iterations (ADMM.py:100-132)
         self.alpha_x = []
         self.beta_x = []
         self.alpha_zu = []
@@ -469,8 +510,7 @@ class ADMM_algorithm():
 
         host_path = (y.device.type == 'cpu' and mask is None and fixed and not want_iter
                      and self.ablation == 'None')
-        diag_h = np.empty((n_outer, _cabi.DIAG_COLS), dtype=np.float64)
-        dx_h = np.empty((n_outer, T, N * Cn), dtype=np.float64)
+        diag_h = dx_h = None
         cg_iters = np.full((max(n_outer, 1), 3), -1, dtype=np.int32)
         outer_done = C.c_int32(n_outer)
         alpha = beta = None
@@ -481,14 +521,21 @@ class ADMM_algorithm():
                 yc = y.detach().contiguous()
                 pin = yc.is_pinned()
                 x = torch.empty((B, T, N, Cn), dtype=y.dtype, pin_memory=pin)
-                if self.keep_cg_coefficients and n_cg > 0 and n_outer > 0:
-                    alpha = torch.empty((n_outer, 3, n_cg, B), dtype=y.dtype, pin_memory=pin)
-                    beta = torch.empty((n_outer, 3, n_cg, B), dtype=y.dtype, pin_memory=pin)
+                # alpha | beta | diag | dx_sum in ONE host block: the library then brings them back in one copy
+                want_coef = self.keep_cg_coefficients and n_cg > 0 and n_outer > 0
+                coef_b = n_outer * 3 * n_cg * B * y.element_size() if want_coef else 0
+                diag_n, dx_n = n_outer * _cabi.DIAG_COLS, n_outer * T * N * Cn
+                blob = torch.empty((2 * coef_b + 8 * (diag_n + dx_n),), dtype=torch.uint8, pin_memory=pin)   # (2 * coef_b: a multiple of 8)
+                if want_coef:
+                    alpha = blob[:coef_b].view(y.dtype).view(n_outer, 3, n_cg, B)
+                    beta = blob[coef_b:2 * coef_b].view(y.dtype).view(n_outer, 3, n_cg, B)
+                dd = blob[2 * coef_b:].view(torch.float64)
+                diag_t, dx_t = dd[:diag_n], dd[diag_n:]
                 _cabi.check(L.mga_admm_solve_host(plan.handle, C.byref(prm), _cabi.ptr(yc), y_rows, _cabi.ptr(x), B,
-                                                  dt, n_outer, n_cg, t_mean, t_var, 1,
-                                                  diag_h.ctypes.data_as(C.c_void_p),
-                                                  dx_h.ctypes.data_as(C.c_void_p), _cabi.ptr(alpha), _cabi.ptr(beta),
-                                                  _cabi.MODE[self.mode], 0))
+                                                  dt, n_outer, n_cg, t_mean, t_var, 1, _cabi.ptr(diag_t), _cabi.ptr(dx_t),
+                                                  _cabi.ptr(alpha), _cabi.ptr(beta), _cabi.MODE[self.mode], 0))
+                diag_h = diag_t.numpy().reshape(n_outer, _cabi.DIAG_COLS)
+                dx_h = dx_t.numpy().reshape(n_outer, T, N * Cn)
                 self.last_mode = 'host'
                 self.last_iterates = None
             else:
@@ -520,8 +567,17 @@ class ADMM_algorithm():
         if self.diag_reduce is not None:      # shards of one batch: sum the partial sums over the ranks
             diag_h, dx_h, B = self.diag_reduce(diag_h, dx_h, B)
             # (the per-window CG coefficients stay with their shard: alpha_* / beta_* hold (B_local,) tensors)
-        self._fill_lists(diag_h, dx_h, cg_iters, int(outer_done.value), alpha, beta, B, y.dtype, out_device,
-                         print_info)
+        n_done = int(outer_done.value)
+        if n_done > 0 and diag_h[:n_done, _cabi.DIAG_NONFINITE].any():
+            i = int(np.nonzero(diag_h[:n_done, _cabi.DIAG_NONFINITE])[0][0])
+            raise AssertionError(f'x / z / phi / gamma has NaN or inf value in loop {i}')   # ADMM.py:575-606
+        if self._pending:
+            self._flush_pending()       # keep the order of the entries (and at most one call's arrays alive)
+        args = (diag_h, dx_h, cg_iters, n_done, alpha, beta, B, y.dtype, out_device, print_info)
+        if print_info:
+            self._fill_lists(*args)     # the per-iteration lines are printed now
+        else:
+            self._pending.append(args)
         return x.to(out_device)
 
     def _fill_lists(self, diag, dx_sum, cg_iters, n_done, alpha, beta, B, dtype, device, print_info):

@@ -79,7 +79,7 @@ struct Graph2 {
 
 // consumer threads of the fused TMA kernels (mga_stream4.cuh); MGA_S4_NC overrides
 inline void k4_env(int* cons) {
-  int nc = 768;
+  int nc = 512;
   if (const char* e = std::getenv("MGA_S4_NC")) nc = std::atoi(e) >= 768 ? 768 : 512;
   *cons = nc;
 }

@@ -768,11 +768,13 @@ static int solve_host_pipelined(mga_plan* p, const mga_params* prm, const char* 
   const int64_t Bs = std::max<int64_t>(1, std::min<int64_t>(B, (int64_t)(cap_gb * 1e9 / (double)(y_win + x_win))));
   const size_t coef_rows = (size_t)n_outer * 3 * max_cg;
   const size_t coef_bytes = want_coef ? coef_rows * (size_t)Bs * es : 0;     // (rows, windows of one launch), compact
+  // staging: y | x | alpha | beta | diag | dx_sum - the last four back to back, so that a caller who keeps its four
+  // result arrays back to back as well gets them in ONE copy behind the kernel
   size_t off_x = ((size_t)Bs * y_win + 255) & ~(size_t)255;
-  size_t off_d = (off_x + (size_t)Bs * x_win + 255) & ~(size_t)255;
-  size_t off_a = (off_d + (diag_n + dx_n) * sizeof(double) + 255) & ~(size_t)255;
-  size_t off_b = (off_a + coef_bytes + 255) & ~(size_t)255;
-  int rc = ensure_workspace(p, p->ws_host_io, off_b + coef_bytes);
+  size_t off_a = (off_x + (size_t)Bs * x_win + 255) & ~(size_t)255;
+  size_t off_b = off_a + coef_bytes;
+  size_t off_d = (off_b + coef_bytes + 7) & ~(size_t)7;
+  int rc = ensure_workspace(p, p->ws_host_io, off_d + (diag_n + dx_n) * sizeof(double));
   if (rc) return rc;
   if ((rc = host_io_setup(p))) return rc;
   char* base = static_cast<char*>(p->ws_host_io.base);
@@ -791,6 +793,7 @@ static int solve_host_pipelined(mga_plan* p, const mga_params* prm, const char* 
   const auto t_begin = std::chrono::steady_clock::now();
   auto us = [&]() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_begin).count(); };
   double t_launch = 0, t_uploads = 0, t_first = 0, t_last = 0, t_run = 0;
+  bool one_copy = false;
   for (int64_t s0 = 0; s0 < B; s0 += Bs) {
     const int64_t nbs = std::min(Bs, B - s0);
     int64_t ck = chunk > 0 ? chunk : std::max<int64_t>(64, (nbs + 63) / 64);
@@ -857,7 +860,14 @@ static int solve_host_pipelined(mga_plan* p, const mga_params* prm, const char* 
     }
     MGA_CUDA(cudaStreamSynchronize(s_run));
     t_run = us();
-    if (want_coef) {        // columns [s0, s0 + nbs) of the caller's (rows, B) arrays
+    one_copy = want_diag && diag_host && dx_sum_host && nbs == B && off_d == off_b + coef_bytes &&
+               reinterpret_cast<char*>(dx_sum_host) == reinterpret_cast<char*>(diag_host) + diag_n * sizeof(double) &&
+               (!want_coef || (static_cast<char*>(beta_host) == static_cast<char*>(alpha_host) + coef_bytes &&
+                               reinterpret_cast<char*>(diag_host) == static_cast<char*>(beta_host) + coef_bytes));
+    if (one_copy) {
+      MGA_CUDA(cudaMemcpyAsync(want_coef ? alpha_host : static_cast<void*>(diag_host), base + (want_coef ? off_a : off_d),
+                               (want_coef ? 2 * coef_bytes : 0) + (diag_n + dx_n) * sizeof(double), cudaMemcpyDeviceToHost, s_dn));
+    } else if (want_coef) {        // columns [s0, s0 + nbs) of the caller's (rows, B) arrays
       MGA_CUDA(cudaMemcpy2DAsync(static_cast<char*>(alpha_host) + (size_t)s0 * es, (size_t)B * es, base + off_a, (size_t)nbs * es,
                                  (size_t)nbs * es, coef_rows, cudaMemcpyDeviceToHost, s_dn));
       MGA_CUDA(cudaMemcpy2DAsync(static_cast<char*>(beta_host) + (size_t)s0 * es, (size_t)B * es, base + off_b, (size_t)nbs * es,
@@ -865,7 +875,7 @@ static int solve_host_pipelined(mga_plan* p, const mga_params* prm, const char* 
     }
     if (s0 + nbs < B) MGA_CUDA(cudaStreamSynchronize(s_dn));          // the next launch reuses the staging
   }
-  if (want_diag) {
+  if (want_diag && !one_copy) {
     if (diag_host) MGA_CUDA(cudaMemcpyAsync(diag_host, d_diag, diag_n * sizeof(double), cudaMemcpyDeviceToHost, s_dn));
     if (dx_sum_host) MGA_CUDA(cudaMemcpyAsync(dx_sum_host, d_dx, dx_n * sizeof(double), cudaMemcpyDeviceToHost, s_dn));
   }

@@ -116,6 +116,31 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   return t;
 }
 
+// The chunk hand-shake of the pipelined host launch, called by one thread between two windows.  Kept out of line on
+// purpose: inlined, its 64-bit divisions and spin loops changed the register allocation of the whole kernel (4 % slower).
+// pipe_acquire: wait until the chunk of window b has landed; returns 1 when it gave up (an upload never arrived).
+static __device__ __noinline__ int pipe_acquire(const int* ready, int chunk, int epoch, long long b, int* abort_flag) {
+  const int* flag = ready + (int)(b / chunk);
+  if (ld_acquire_gpu(flag) == epoch) return 0;
+  const unsigned long long t_start = globaltimer_ns();
+  while (ld_acquire_gpu(flag) != epoch) {
+    __nanosleep(256);
+    if (globaltimer_ns() - t_start > 4000000000ull) { atomicExch(abort_flag, 1); return 1; }   // 4 s: never hang the device
+  }
+  return 0;
+}
+// pipe_release: count window b as finished; the thread that completes a chunk publishes it to the host
+static __device__ __noinline__ void pipe_release(int* done, int* host_done, int chunk, int epoch, long long b, long long B) {
+  const int c = (int)(b / chunk);
+  const long long left = B - (long long)c * chunk;
+  const int nwin = (int)(left < chunk ? left : chunk);
+  if (atomicAdd(done + c, 1) + 1 == nwin) {
+    done[c] = 0;
+    __threadfence_system();
+    *reinterpret_cast<volatile int*>(host_done + c) = epoch;
+  }
+}
+
 // Shared-memory loads by 32-bit shared address.  The tables hold ABSOLUTE shared addresses (base of
 // pbuf / qbuf folded in when the CTA fills them), so a gather is "LDS.128 [entry + 16 c]" with no
 // address arithmetic between the table load and the data load.
@@ -680,16 +705,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_admm_resident(const ResArgs a) {
     if (PIPE) {
       // the host entry point uploads the batch chunk by chunk while this kernel runs: wait for this window's chunk.
       // y is then read with ld.global.cg (below): a 128-byte L1 line may straddle two windows of different chunks.
-      if (threadIdx.x == 0) {
-        const int* flag = a.ready + b / a.chunk;
-        if (ld_acquire_gpu(flag) != a.epoch) {
-          const unsigned long long t_start = globaltimer_ns();
-          while (ld_acquire_gpu(flag) != a.epoch) {
-            __nanosleep(256);
-            if (globaltimer_ns() - t_start > 4000000000ull) { s_abort = 1; atomicExch(a.abort_flag, 1); break; }   // 4 s: never hang the device
-          }
-        }
-      }
+      if (threadIdx.x == 0 && pipe_acquire(a.ready, a.chunk, a.epoch, b, a.abort_flag)) s_abort = 1;
       __syncthreads();
       if (s_abort) return;
     }
@@ -1013,16 +1029,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_admm_resident(const ResArgs a) {
       // the CTA that completes a chunk publishes it to the host (system-scope fence, then the flag in mapped host memory)
       __threadfence();
       __syncthreads();
-      if (threadIdx.x == 0) {
-        const int c = (int)(b / a.chunk);
-        const int64_t left = a.B - (int64_t)c * a.chunk;
-        const int nwin = (int)(left < a.chunk ? left : a.chunk);
-        if (atomicAdd(a.done + c, 1) + 1 == nwin) {
-          a.done[c] = 0;
-          __threadfence_system();
-          *reinterpret_cast<volatile int*>(a.host_done + c) = a.epoch;
-        }
-      }
+      if (threadIdx.x == 0) pipe_release(a.done, a.host_done, a.chunk, a.epoch, b, a.B);
     }
     if (threadIdx.x == 0) s_next = atomicAdd(a.next_window, 1);
     __syncthreads();

@@ -105,9 +105,10 @@ k4_cg(const __grid_constant__ K4Maps maps, const Graph2 g, const K4Args a) {
   float* qsl = hr + N;                                               // q at the tile's first step
   float* p0 = qsl + N;                                               // p' at the tile's first step
   float* wself = p0 + N;
-  int* ptr = reinterpret_cast<int*>(wself + N);                      // (N + 1) in-list offsets        [SYS 0]
-  int* ord = ptr + N + 1;                                            // (N) row order of phase C         [SYS 0]
+  int* ptr = reinterpret_cast<int*>(wself + N);                      // (N + 1) words + (N) words: the phase-C slots  [SYS 0]
+  int* ord = ptr + N + 1;                                            //   int2 sdesc[k] = (row | list length << 16, first in-list entry), k-th row in ord4 order
   const int kf = SYS == 0 ? g.kd3 : g.ku3;
+  int2* sdesc = reinterpret_cast<int2*>(ptr + ((5 * N) & 1));        // 8-byte aligned inside the (2 N + 2)-word block
   int2* tab = reinterpret_cast<int2*>(ord + N + ((N & 1) ^ 1));      // forward table (N, kf), 8-byte aligned: 7 N + 1 words precede it (odd iff N is even)
   int2* tab_in = tab + (size_t)N * kf;                               // in-list entries                  [SYS 0]
   const int n_in = SYS == 0 ? g.in_ptr3_total : 0;
@@ -174,8 +175,11 @@ k4_cg(const __grid_constant__ K4Maps maps, const Graph2 g, const K4Args a) {
     for (int k = tid; k < N * kf; k += NC) tab[k] = src[k];
     if (SYS == 0) {
       for (int k = tid; k < n_in; k += NC) tab_in[k] = g.tab_in3[k];
-      for (int k = tid; k <= N; k += NC) ptr[k] = g.in_ptr3[k];
-      for (int k = tid; k < N; k += NC) { ord[k] = g.ord4[k]; wself[k] = g.wself_d[k]; }
+      for (int k = tid; k < N; k += NC) {
+        const int n = g.ord4[k], e0 = g.in_ptr3[n];
+        sdesc[k] = make_int2(n | ((g.in_ptr3[n + 1] - e0) << 16), e0);
+        wself[k] = g.wself_d[k];
+      }
     }
   }
   // (published to the other consumers by the barrier that ends phase A of the first tile)
@@ -286,7 +290,8 @@ k4_cg(const __grid_constant__ K4Maps maps, const Graph2 g, const K4Args a) {
         for (int it0 = tid - lane; it0 < N * kCB4; it0 += NC) {
           const bool on = cok && it0 + lane < N * kCB4;                     // (columns beyond the row: zero-filled tile, nothing to store)
           const int item = it0 + lane < N * kCB4 ? it0 + lane : N * kCB4 - 1;
-          const int n = ord[item >> 3];
+          const int2 sd = sdesc[item >> 3];
+          const int n = sd.x & 0xffff;
           const int idx = n * kCB4 + col;
           const float4 pv = tR[idx];
           float4 rh = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -296,8 +301,8 @@ k4_cg(const __grid_constant__ K4Maps maps, const Graph2 g, const K4Args a) {
           const float qprev = col > 0 ? dn : qsl[n];
           const float ws = self_in ? wself[n] : 0.f;
           float4 f = make_float4(ws * q1.x, ws * q1.y, ws * q1.z, ws * q1.w);
-          int e = ptr[n];
-          const int e1 = ptr[n + 1];
+          int e = sd.y;
+          const int e1 = e + (sd.x >> 16);
           if (!(MGA_K4_X & 1)) {
             for (; e + 4 <= e1; e += 4) f = gather3<4>(tab_in + e, 4, mine, f);
             if (e + 2 <= e1) { f = gather3<2>(tab_in + e, 2, mine, f); e += 2; }
