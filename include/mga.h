@@ -200,6 +200,17 @@ int mga_admm_solve(mga_plan* plan, const mga_params* prm, const void* y, int y_r
                    double admm_tol, double t_mean, double t_var, int want_diag,
                    const mga_admm_outputs* outs, int mode, void* stream);
 
+/* ---- the same loop in "cluster mode": one thread-block cluster per window (time slabs dealt to the CTAs, halo rows
+ * exchanged through distributed shared memory), in the signal's own precision, with the reference's stop tests
+ * (ADMM.py:360, 645) decided on the device - one launch for a whole tolerance-driven solve.  mga_admm_solve(MODE_AUTO)
+ * picks it for tolerance mode at B = 1 (the reference's own call pattern: float64, CG_tol 1e-8, ADMM_tol 1e-6,
+ * ADMM.py:76-80) and for float64 batches with fixed counts; this entry point runs it on request.  Forecasting mode,
+ * ablation None, time-invariant weights, T <= 32, N <= 1024; cg_tol / admm_tol > 0 need B = 1 (for B > 1 the
+ * reference's tests are batch-global).  Arguments as mga_admm_solve. */
+int mga_cluster_solve(mga_plan* plan, const mga_params* prm, const void* y, void* x_out, int64_t B, int dtype,
+                      int n_outer, int max_cg_iter, double cg_tol, double admm_tol, double t_mean, double t_var,
+                      int want_diag, const mga_admm_outputs* outs, void* stream);
+
 /* ---- same, with HOST buffers (the end-to-end call every caller of the reference makes: CPU tensors in, CPU tensor
  * out).  Forecasting mode, fixed iteration counts.  When the plan runs in resident mode the whole batch is ONE
  * persistent launch: y is uploaded chunk by chunk while the kernel already solves the first chunks, finished chunks

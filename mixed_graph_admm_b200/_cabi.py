@@ -30,7 +30,7 @@ ERR_INVALID, ERR_INDEX, ERR_CUDA, ERR_UNSUPPORTED, ERR_NONFINITE = -1, -2, -3, -
 EXPORTS = [
     "mga_plan_create", "mga_plan_destroy", "mga_plan_resident_eligible", "mga_plan_info", "mga_plan_set_cg_mode", "mga_apply",
     "mga_cg_solve", "mga_initial_guess", "mga_rhs_x", "mga_dual_ascent", "mga_prox_phi_dual", "mga_phi_direct",
-    "mga_admm_solve", "mga_admm_solve_host", "mga_knn_build", "mga_schedule_selfcheck", "mga_launch_count", "mga_last_error", "mga_version",
+    "mga_admm_solve", "mga_admm_solve_host", "mga_cluster_solve", "mga_knn_build", "mga_schedule_selfcheck", "mga_launch_count", "mga_last_error", "mga_version",
 ]
 
 
@@ -93,6 +93,8 @@ def lib():
         L.mga_phi_direct.argtypes = [vp, C.POINTER(Params), vp, vp, vp, i64, C.c_int, vp]
         L.mga_admm_solve.argtypes = [vp, C.POINTER(Params), vp, C.c_int, vp, vp, i64, C.c_int, C.c_int, C.c_int,
                                      dbl, dbl, dbl, dbl, C.c_int, C.POINTER(AdmmOutputs), C.c_int, vp]
+        L.mga_cluster_solve.argtypes = [vp, C.POINTER(Params), vp, vp, i64, C.c_int, C.c_int, C.c_int, dbl, dbl, dbl, dbl,
+                                        C.c_int, C.POINTER(AdmmOutputs), vp]
         L.mga_admm_solve_host.argtypes = [vp, C.POINTER(Params), vp, C.c_int, vp, i64, C.c_int, C.c_int, C.c_int,
                                           dbl, dbl, C.c_int, vp, vp, vp, vp, C.c_int, i64]
         L.mga_knn_build.argtypes = [i32, i64, vp, vp, i32, vp, vp]

@@ -15,7 +15,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(OUT_DIR, "libmga.so")
-SOURCES = ["mga_plan.cu", "mga_stream.cu", "mga_stream2.cu", "mga_resident.cu", "mga_knn.cpp", "mga_schedule.cpp"]
+SOURCES = ["mga_plan.cu", "mga_stream.cu", "mga_stream2.cu", "mga_resident.cu", "mga_cluster.cu", "mga_knn.cpp", "mga_schedule.cpp"]
 # the resident kernels are instantiated per (chunks per thread, table slots), one translation unit each
 RESIDENT_VARIANTS = [(ch, k) for ch in (1, 2, 3) for k in (4, 6, 8, 10)]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

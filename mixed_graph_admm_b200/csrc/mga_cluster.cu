@@ -1,0 +1,585 @@
+// Cluster mode: the whole of combined_loop (ADMM.py:528-648) for one window inside one thread-block CLUSTER, in the
+// signal's own precision (float64 as the reference's PEMS runs, or float32) and with the reference's stop tests decided
+// on the device - the reference's own call pattern (B = 1, float64, CG_tol = 1e-8, ADMM_tol = 1e-6, up to 150 outer
+// iterations; ADMM.py:76-80) in ONE launch with no host round trip per CG iteration.
+//
+// Why a cluster: a float64 window of PEMS size (307 nodes x 24 steps: 59 KB per vector, 12 vectors live) does not fit the
+// registers / shared memory of one SM, and with the vectors in L2 one SM executes every gather itself (measured: 28 us
+// per CG iteration).  Here the T time steps are dealt to the CTAs of a cluster as slabs of TL consecutive steps
+// (T = 24 -> 8 CTAs x 3 steps); a thread owns one node over the slab of its CTA:
+//   * CG vectors of the thread's points in registers, the seven ADMM state vectors in shared memory;
+//   * the vector other threads gather from (p, then q = L_d p) is staged per CTA as TL + 1 time rows: the slab plus ONE
+//     halo row, pushed by the neighbouring CTA through distributed shared memory (L_d reads step t-1, L_d^T step t+1;
+//     ADMM.py:171, 200-208) - 2.4 KB per exchange instead of a whole vector;
+//   * dot products: warp shuffle -> CTA -> every CTA writes its partial into a slot of EVERY CTA's shared memory ->
+//     cluster barrier -> all threads add the slots in the same order, so alpha, beta and the stop decisions are
+//     bit-identical across the cluster and the control flow stays uniform (barrier.cluster needs that);
+//   * graph tables (forward ELL, in-list CSR in scatter order) staged once per CTA.
+// Tolerance mode is per window here, so it is offered for B = 1 (for B > 1 the reference's tests are batch-global,
+// quirk Q3: the general kernels keep those); fixed iteration counts run any B, one cluster per window.
+#include <cooperative_groups.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+
+#include "mga_common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace mga {
+
+constexpr int kClMaxTL = 4;     // time steps per CTA (T <= 8 * 4)
+constexpr int kClMaxCL = 8;     // portable cluster size
+
+template <typename S>
+struct ClArgs {
+  int N, NP, T, t_in, CL, kd, ku, q1, nnz;
+  int n_outer, max_cg, want_diag;
+  int64_t B;
+  const int* nbr_d; const float* d_w; const int* nbr_u; const float* u_w;
+  const int* csr_ptr; const int* csr_src; const float* csr_w;
+  const S* y; S* x_out;
+  S* out[6];               // zu, zd, phi, gamma, gamma_u, gamma_d (optional)
+  double* diag; double* dx_sum;
+  S* alpha; S* beta;       // (n_outer, 3, max_cg, B) or NULL
+  int* cg_iters;           // (n_outer, 3) device-visible, tolerance mode; NULL otherwise
+  int* outer_done;
+  double cg_tol, admm_tol;
+  S rho, rho_u, rho_d, thr;
+  S ax, cx, azu, czu, azd, czd;
+  float t_mean, t_var;
+};
+
+enum { CS_X = 0, CS_ZU, CS_ZD, CS_GU, CS_GD, CS_GAM, CS_PHI, CS_COUNT };
+
+template <typename S>
+__device__ __forceinline__ S cl_soft(S s, S d) {
+  const S u = fabs(s) - d;
+  const S sg = (S)((s > (S)0) - (s < (S)0));
+  return sg * u * (S)(u > (S)0);   // ADMM.py:407-408
+}
+
+template <typename S, int TL>
+struct ClCtx {
+  int N, NP, T, t_in, t0, i, rank, CL, kd, ku, q1;
+  bool active;
+  const int* nbr_d; const float* w_d; const int* nbr_u; const float* w_u;
+  const int* cptr; const int* csrc; const float* cw;
+  S* pbuf;        // (TL + 1) rows x NP: row 0 = the previous CTA's last step (halo), rows 1..TL = own steps
+  S* qbuf;        // (TL + 1) rows x NP: rows 0..TL-1 = own steps, row TL = the next CTA's first step (halo)
+  S* red;         // 32 warp partials
+  S* slots;       // [2][kClMaxCL] cluster reduction slots (a full copy in every CTA), double-buffered
+  int parity;
+  cg::cluster_group cl = cg::this_cluster();
+
+  // Sum over the whole window (all CTAs of the cluster), the same bits in every thread of the cluster.
+  __device__ __forceinline__ S csum(S v) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum<S>(v);
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    if (threadIdx.x < (unsigned)CL) {
+      S t = 0;
+      for (int k = 0; k < nw; ++k) t += red[k];
+      S* remote = cl.map_shared_rank(slots, threadIdx.x);      // thread r delivers this CTA's partial to CTA r
+      remote[parity * kClMaxCL + rank] = t;
+    }
+    cl.sync();
+    S tot = 0;
+    for (int r = 0; r < CL; ++r) tot += slots[parity * kClMaxCL + r];
+    parity ^= 1;
+    return tot;
+  }
+
+  // own steps -> pbuf rows 1..TL, last own step -> halo row 0 of the next CTA; cluster barrier
+  __device__ __forceinline__ void publish_p(const S (&v)[TL]) {
+#pragma unroll
+    for (int l = 0; l < TL; ++l) pbuf[(l + 1) * NP + i] = v[l];
+    if (rank + 1 < CL) cl.map_shared_rank(pbuf, rank + 1)[i] = v[TL - 1];
+    cl.sync();
+  }
+  // own steps -> qbuf rows 0..TL-1, first own step -> halo row TL of the previous CTA; cluster barrier
+  __device__ __forceinline__ void publish_q(const S (&v)[TL]) {
+#pragma unroll
+    for (int l = 0; l < TL; ++l) qbuf[l * NP + i] = v[l];
+    if (rank > 0) cl.map_shared_rank(qbuf, rank - 1)[TL * NP + i] = v[0];
+    cl.sync();
+  }
+  // q = L_d v with v published in pbuf (ADMM.py:166-177): q[t] = v[t] - sum_j w_j v[t-1, nbr_j], q[0] = 0
+  __device__ __forceinline__ void ldr(const S (&v)[TL], S (&q)[TL]) const {
+#pragma unroll
+    for (int l = 0; l < TL; ++l) {
+      const int t = t0 + l;
+      S acc = 0;
+      if (active && t >= 1 && t < T) {
+        const S* prev = pbuf + l * NP;
+        for (int j = 0; j < kd; ++j) {
+          const int c = nbr_d[i * kd + j];
+          if (c >= 0) acc += (S)w_d[i * kd + j] * prev[c];
+        }
+        acc = v[l] - acc;
+      }
+      q[l] = acc;
+    }
+  }
+  // (L_d^T + Q1) v with v published in qbuf (ADMM.py:196-223): the "father" sum over the in-list at step t+1
+  __device__ __forceinline__ void ldrt(const S (&v)[TL], S (&out)[TL]) const {
+#pragma unroll
+    for (int l = 0; l < TL; ++l) {
+      const int t = t0 + l;
+      S o = 0;
+      if (active && t < T) {
+        if (t == T - 1) {
+          o = v[l];
+        } else {
+          const S* next = qbuf + (l + 1) * NP;
+          S f = 0;
+          for (int e = cptr[i]; e < cptr[i + 1]; ++e) f += (S)cw[e] * next[csrc[e]];
+          o = (t == 0 && !q1) ? -f : v[l] - f;
+        }
+      }
+      out[l] = o;
+    }
+  }
+  // L_u v with v published in pbuf (ADMM.py:138-148)
+  __device__ __forceinline__ void lu(const S (&v)[TL], S (&out)[TL]) const {
+#pragma unroll
+    for (int l = 0; l < TL; ++l) {
+      const int t = t0 + l;
+      S o = 0;
+      if (active && t < T) {
+        const S* row = pbuf + (l + 1) * NP;
+        S acc = 0;
+        for (int j = 0; j < ku; ++j) {
+          const int c = nbr_u[i * ku + j];
+          if (c >= 0) acc += (S)w_u[i * ku + j] * row[c];
+        }
+        o = v[l] - acc;
+      }
+      out[l] = o;
+    }
+  }
+  // out = A v for system SYS (ADMM.py:371-399), the reference's evaluation order
+  template <int SYS>
+  __device__ __forceinline__ void apply(const S (&v)[TL], S (&out)[TL], S a, S c) {
+    publish_p(v);
+    if (SYS == MGA_SYS_ZU) {
+      lu(v, out);
+#pragma unroll
+      for (int l = 0; l < TL; ++l) out[l] = c * out[l] + a * v[l];                       // ADMM.py:390
+      return;
+    }
+    S q[TL];
+    ldr(v, q);
+    publish_q(q);
+    ldrt(q, out);
+#pragma unroll
+    for (int l = 0; l < TL; ++l) {
+      if (SYS == MGA_SYS_X) {
+        const S hx = (t0 + l < t_in) ? v[l] : (S)0;                                     // H^T H (ADMM.py:372-374)
+        out[l] = (hx + a * v[l]) + c * out[l];                                          // ADMM.py:379
+      } else {
+        out[l] = c * out[l] + a * v[l];                                                 // ADMM.py:394
+      }
+    }
+  }
+
+  // CG_solver (ADMM.py:329-368): r holds the right-hand side on entry, x the warm start.  Returns the iteration count
+  // (tol > 0 and reached) or -1.  alpha_out / beta_out: this window's column of the (max_cg, B) arrays or NULL.
+  template <int SYS>
+  __device__ __forceinline__ int cg_solve(S (&x)[TL], S (&r)[TL], S a, S c, int max_cg, double tol, S* alpha_out, S* beta_out,
+                                          int64_t B) {
+    S p[TL], ap[TL];
+    apply<SYS>(x, ap, a, c);
+    S loc = 0;
+#pragma unroll
+    for (int l = 0; l < TL; ++l) {
+      r[l] = r[l] - ap[l];
+      p[l] = r[l];
+      loc += r[l] * r[l];
+    }
+    S rr = csum(loc);
+    for (int k = 0; k < max_cg; ++k) {
+      apply<SYS>(p, ap, a, c);
+      loc = 0;
+#pragma unroll
+      for (int l = 0; l < TL; ++l) loc += p[l] * ap[l];
+      const S alpha = rr / csum(loc);
+      loc = 0;
+#pragma unroll
+      for (int l = 0; l < TL; ++l) {
+        x[l] = x[l] + alpha * p[l];
+        r[l] = r[l] - alpha * ap[l];
+        loc += r[l] * r[l];
+      }
+      const S rrn = csum(loc);
+      const S beta = rrn / rr;
+      rr = rrn;
+      if (alpha_out && rank == 0 && threadIdx.x == 0) {
+        alpha_out[(size_t)k * B] = alpha;
+        beta_out[(size_t)k * B] = beta;
+      }
+      if (tol > 0 && sqrt(rr) < (S)tol) return k + 1;          // ADMM.py:360 (B = 1: the max over the batch is this window)
+#pragma unroll
+      for (int l = 0; l < TL; ++l) p[l] = r[l] + beta * p[l];
+    }
+    return -1;
+  }
+};
+
+// MAXT: launch bound (384: PEMS-sized graphs keep their registers - no spills in float64; 1024: up to 1024 nodes)
+template <typename S, int TL, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) k_admm_cluster(const ClArgs<S> a) {
+  extern __shared__ __align__(16) unsigned char smem_cl[];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int N = a.N, NP = a.NP, T = a.T, t_in = a.t_in, CL = a.CL;
+  const int rank = (int)cluster.block_rank();
+  const int64_t b = blockIdx.x / CL;
+  // ---- carve shared memory
+  S* state = reinterpret_cast<S*>(smem_cl);                        // [CS_COUNT][TL][NP]
+  S* pbuf = state + (size_t)CS_COUNT * TL * NP;
+  S* qbuf = pbuf + (size_t)(TL + 1) * NP;
+  S* red = qbuf + (size_t)(TL + 1) * NP;
+  S* slots = red + 32;
+  float* w_d = reinterpret_cast<float*>(slots + 2 * kClMaxCL);
+  float* w_u = w_d + (size_t)N * a.kd;
+  float* cw = w_u + (size_t)N * a.ku;
+  int* nbr_d = reinterpret_cast<int*>(cw + a.nnz);
+  int* nbr_u = nbr_d + (size_t)N * a.kd;
+  int* cptr = nbr_u + (size_t)N * a.ku;
+  int* csrc = cptr + N + 1;
+  float* dred = reinterpret_cast<float*>(csrc + a.nnz);            // (used as S below) 12 x 32 partials of the diagnostics
+  S* dredS = reinterpret_cast<S*>(reinterpret_cast<size_t>(dred + 1) & ~(size_t)7);
+  for (int k = threadIdx.x; k < N * a.kd; k += blockDim.x) { w_d[k] = a.d_w[k]; nbr_d[k] = a.nbr_d[k]; }
+  for (int k = threadIdx.x; k < N * a.ku; k += blockDim.x) { w_u[k] = a.u_w[k]; nbr_u[k] = a.nbr_u[k]; }
+  for (int k = threadIdx.x; k < a.nnz; k += blockDim.x) { cw[k] = a.csr_w[k]; csrc[k] = a.csr_src[k]; }
+  for (int k = threadIdx.x; k <= N; k += blockDim.x) cptr[k] = a.csr_ptr[k];
+  for (int k = threadIdx.x; k < 2 * (TL + 1) * NP; k += blockDim.x) pbuf[k] = (S)0;     // incl. the outermost halo rows
+  for (int k = threadIdx.x; k < 2 * kClMaxCL; k += blockDim.x) slots[k] = (S)0;
+
+  ClCtx<S, TL> c;
+  c.N = N; c.NP = NP; c.T = T; c.t_in = t_in; c.t0 = rank * TL; c.i = threadIdx.x; c.rank = rank; c.CL = CL;
+  c.kd = a.kd; c.ku = a.ku; c.q1 = a.q1;
+  c.active = (int)threadIdx.x < N;
+  c.nbr_d = nbr_d; c.w_d = w_d; c.nbr_u = nbr_u; c.w_u = w_u; c.cptr = cptr; c.csrc = csrc; c.cw = cw;
+  c.pbuf = pbuf; c.qbuf = qbuf; c.red = red; c.slots = slots; c.parity = 0;
+  cluster.sync();                                                    // tables and zeroed buffers of every CTA are in place
+  const int i = c.i, t0 = c.t0;
+  const bool active = c.active;
+  auto st = [&](int v, int l) -> S& { return state[((size_t)v * TL + l) * NP + i]; };
+  const S* yw = a.y + (size_t)b * t_in * N + i;
+
+  // ---- initial_guess (ADMM.py:766-781) and initial state (ADMM.py:537-544)
+  {
+    S sy = 0, sty = 0;
+    if (active)
+      for (int t = 0; t < t_in; ++t) {
+        const S v = yw[(size_t)t * N];
+        sy += v;
+        sty += (S)(float)t * v;
+      }
+    const S my = sy / (S)t_in, mty = sty / (S)t_in;
+    const S w = (mty - (S)a.t_mean * my) / (S)a.t_var;
+    const S cc = my - w * (S)a.t_mean;
+    S x[TL], q[TL];
+#pragma unroll
+    for (int l = 0; l < TL; ++l) {
+      const int t = t0 + l;
+      S v = 0;
+      if (active && t < T) v = t < t_in ? yw[(size_t)t * N] : w * (S)(float)t + cc;
+      x[l] = v;
+      const S tenth = (active && t < T) ? (S)0.1 : (S)0;
+      st(CS_X, l) = v; st(CS_ZU, l) = v; st(CS_ZD, l) = v;
+      st(CS_GU, l) = tenth; st(CS_GD, l) = tenth; st(CS_GAM, l) = tenth;
+    }
+    c.publish_p(x);
+    c.ldr(x, q);                                                     // phi = L_d x (ADMM.py:541)
+#pragma unroll
+    for (int l = 0; l < TL; ++l) st(CS_PHI, l) = q[l];
+  }
+
+  int outer_done = 0;
+  for (int it = 0; it < a.n_outer; ++it) {
+    const size_t sys_stride = (size_t)a.max_cg * a.B;
+    S* al = a.alpha ? a.alpha + ((size_t)it * 3) * sys_stride + b : nullptr;
+    S* be = a.beta ? a.beta + ((size_t)it * 3) * sys_stride + b : nullptr;
+    int iters[3] = {-1, -1, -1};
+    S d[MGA_DIAG_COLS];
+#pragma unroll
+    for (int k = 0; k < MGA_DIAG_COLS; ++k) d[k] = 0;
+    S r[TL], x[TL];
+    // ---- RHS_x (ADMM.py:552-559): Ldr_T(gamma + rho phi)/2 + (rho_u zu + rho_d zd)/2 - (gu + gd)/2 + H^T y
+    {
+      S v[TL], lt[TL];
+#pragma unroll
+      for (int l = 0; l < TL; ++l) v[l] = st(CS_GAM, l) + a.rho * st(CS_PHI, l);
+      c.publish_q(v);
+      c.ldrt(v, lt);
+#pragma unroll
+      for (int l = 0; l < TL; ++l) {
+        const int t = t0 + l;
+        S o = 0;
+        if (active && t < T) {
+          const S hty = t < t_in ? yw[(size_t)t * N] : (S)0;
+          o = lt[l] / (S)2 + (a.rho_u * st(CS_ZU, l) + a.rho_d * st(CS_ZD, l)) / (S)2 - (st(CS_GU, l) + st(CS_GD, l)) / (S)2 + hty;
+        }
+        r[l] = o;
+        x[l] = st(CS_X, l);
+      }
+    }
+    // ---- x solve (ADMM.py:571), warm start x_old
+    iters[0] = c.template cg_solve<MGA_SYS_X>(x, r, a.ax, a.cx, a.max_cg, a.cg_tol, al, be, a.B);
+#pragma unroll
+    for (int l = 0; l < TL; ++l) {
+      const int t = t0 + l;
+      if (active && t < T) {
+        const S dx = x[l] - st(CS_X, l);
+        d[MGA_DIAG_DX2] += dx * dx;
+        d[MGA_DIAG_NONFINITE] += (S)(!isfinite(x[l]));
+        if (a.want_diag && a.dx_sum) atomicAdd(a.dx_sum + ((size_t)it * T + t) * N + i, (double)dx);
+      }
+      st(CS_X, l) = x[l];
+    }
+    // ---- z_u solve (ADMM.py:579-580)
+    {
+      S z[TL];
+#pragma unroll
+      for (int l = 0; l < TL; ++l) { r[l] = st(CS_GU, l) / (S)2 + a.azu * x[l]; z[l] = st(CS_ZU, l); }
+      iters[1] = c.template cg_solve<MGA_SYS_ZU>(z, r, a.azu, a.czu, a.max_cg, a.cg_tol, al ? al + sys_stride : nullptr,
+                                                 be ? be + sys_stride : nullptr, a.B);
+#pragma unroll
+      for (int l = 0; l < TL; ++l) {
+        if (active && t0 + l < T) {
+          const S d0 = x[l] - z[l], d1 = z[l] - st(CS_ZU, l);
+          d[MGA_DIAG_X_ZU2] += d0 * d0;
+          d[MGA_DIAG_DZU2] += d1 * d1;
+          d[MGA_DIAG_NONFINITE] += (S)(!isfinite(z[l]));
+        }
+        st(CS_ZU, l) = z[l];
+      }
+    }
+    // ---- z_d solve (ADMM.py:587-588)
+    {
+      S z[TL];
+#pragma unroll
+      for (int l = 0; l < TL; ++l) { r[l] = st(CS_GD, l) / (S)2 + a.azd * x[l]; z[l] = st(CS_ZD, l); }
+      iters[2] = c.template cg_solve<MGA_SYS_ZD>(z, r, a.azd, a.czd, a.max_cg, a.cg_tol, al ? al + 2 * sys_stride : nullptr,
+                                                 be ? be + 2 * sys_stride : nullptr, a.B);
+#pragma unroll
+      for (int l = 0; l < TL; ++l) {
+        if (active && t0 + l < T) {
+          const S d0 = x[l] - z[l], d1 = z[l] - st(CS_ZD, l);
+          d[MGA_DIAG_X_ZD2] += d0 * d0;
+          d[MGA_DIAG_DZD2] += d1 * d1;
+          d[MGA_DIAG_NONFINITE] += (S)(!isfinite(z[l]));
+          // dual ascents (ADMM.py:595-597): gamma_u uses the z_u stored above
+          st(CS_GU, l) = st(CS_GU, l) + a.rho_u * (x[l] - st(CS_ZU, l));
+          st(CS_GD, l) = st(CS_GD, l) + a.rho_d * d0;
+        }
+        st(CS_ZD, l) = z[l];
+      }
+    }
+    // ---- phi prox + gamma ascent (ADMM.py:600-605) and the remaining diagnostics (ADMM.py:612-637)
+    {
+      S ldx[TL], lux[TL];
+      c.publish_p(x);
+      c.ldr(x, ldx);
+      if (a.want_diag) c.lu(x, lux);
+#pragma unroll
+      for (int l = 0; l < TL; ++l) {
+        const int t = t0 + l;
+        if (active && t < T) {
+          const S gam = st(CS_GAM, l), pho = st(CS_PHI, l), q = ldx[l];
+          const S ph = cl_soft<S>(q - gam / a.rho, a.thr);
+          const S gn = gam + a.rho * (ph - q);
+          d[MGA_DIAG_NONFINITE] += (S)(!isfinite(ph) || !isfinite(gn));
+          const S e = ph - q, f = ph - pho;
+          d[MGA_DIAG_PHI_LDX2] += e * e;
+          d[MGA_DIAG_DPHI2] += f * f;
+          d[MGA_DIAG_DGTV] += fabs(q);
+          d[MGA_DIAG_DGLR] += q * q;
+          if (a.want_diag) {
+            d[MGA_DIAG_GLR] += x[l] * lux[l];
+            if (t < t_in) {
+              const S h = x[l] - yw[(size_t)t * N];
+              d[MGA_DIAG_RECOVER2] += h * h;
+            }
+          }
+          st(CS_PHI, l) = ph;
+          st(CS_GAM, l) = gn;
+        }
+      }
+    }
+    // ---- diagnostics out (one double atomic per CTA and column) and the outer stop test (ADMM.py:645)
+    {
+      const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+      for (int k = 0; k < MGA_DIAG_COLS; ++k) {
+        const S v = warp_sum<S>(d[k]);
+        if (lane == 0) dredS[k * 32 + w] = v;
+      }
+      __syncthreads();
+      if (threadIdx.x < MGA_DIAG_COLS && a.diag && (a.want_diag || threadIdx.x == MGA_DIAG_NONFINITE)) {
+        S t = 0;
+        for (int k = 0; k < nw; ++k) t += dredS[threadIdx.x * 32 + k];
+        if (t != (S)0) atomicAdd(a.diag + (size_t)it * MGA_DIAG_COLS + threadIdx.x, (double)t);
+      }
+      __syncthreads();
+    }
+    if (a.cg_iters && rank == 0 && threadIdx.x == 0) {
+      a.cg_iters[it * 3 + 0] = iters[0]; a.cg_iters[it * 3 + 1] = iters[1]; a.cg_iters[it * 3 + 2] = iters[2];
+    }
+    outer_done = it + 1;
+    if (a.admm_tol > 0) {
+      // whole-window norms, as the reference takes them in the signal dtype (B = 1)
+      const S pzu = sqrt(c.csum(d[MGA_DIAG_X_ZU2])), dzu = sqrt(c.csum(d[MGA_DIAG_DZU2]));
+      const S pph = sqrt(c.csum(d[MGA_DIAG_PHI_LDX2])), dph = sqrt(c.csum(d[MGA_DIAG_DPHI2]));
+      const S pzd = sqrt(c.csum(d[MGA_DIAG_X_ZD2])), dzd = sqrt(c.csum(d[MGA_DIAG_DZD2]));
+      const S pri = fmax(fmax(pzu, pph), pzd), dua = fmax(fmax(dzu, dph), dzd);
+      if ((double)pri < a.admm_tol && (double)dua < a.admm_tol) break;
+    }
+  }
+  if (a.outer_done && rank == 0 && threadIdx.x == 0 && b == 0) *a.outer_done = outer_done;
+  // ---- results
+#pragma unroll
+  for (int l = 0; l < TL; ++l) {
+    const int t = t0 + l;
+    if (active && t < T) {
+      const size_t at = ((size_t)b * T + t) * N + i;
+      a.x_out[at] = st(CS_X, l);
+      if (a.out[0]) a.out[0][at] = st(CS_ZU, l);
+      if (a.out[1]) a.out[1][at] = st(CS_ZD, l);
+      if (a.out[2]) a.out[2][at] = st(CS_PHI, l);
+      if (a.out[3]) a.out[3][at] = st(CS_GAM, l);
+      if (a.out[4]) a.out[4][at] = st(CS_GU, l);
+      if (a.out[5]) a.out[5][at] = st(CS_GD, l);
+    }
+  }
+  cluster.sync();      // no CTA leaves while a neighbour may still push into its shared memory
+}
+
+// ---- host side ------------------------------------------------------------------------------------------------
+struct ClGeom {
+  int CL, TL, NP;
+  size_t smem;
+};
+
+template <typename S>
+static bool cl_geometry(const mga_plan* p, ClGeom* out) {
+  const GraphDev& g = p->g;
+  if (g.temporal == MGA_TEMPORAL_BAND || g.u_wT != 1 || g.d_wT != 1 || g.N > 1024 || g.T > kClMaxCL * kClMaxTL) return false;
+  ClGeom q;
+  q.CL = std::min(g.T, kClMaxCL);
+  q.TL = (g.T + q.CL - 1) / q.CL;
+  q.CL = (g.T + q.TL - 1) / q.TL;                 // no empty CTAs (T = 9 -> TL = 2 -> 5 CTAs)
+  q.NP = ((g.N + 31) / 32) * 32;
+  q.smem = ((size_t)CS_COUNT * q.TL + 2 * (q.TL + 1)) * q.NP * sizeof(S) + (32 + 2 * kClMaxCL) * sizeof(S) +
+           ((size_t)g.N * (g.kd + g.ku) + g.nnz) * 8 + (size_t)(g.N + 1) * 4 + 16 + (size_t)MGA_DIAG_COLS * 32 * sizeof(S);
+  if (q.smem > (size_t)p->max_smem_optin) return false;
+  *out = q;
+  return true;
+}
+
+bool cluster_eligible(const mga_plan* p, int dtype) {
+  ClGeom q;
+  return dtype == MGA_F64 ? cl_geometry<double>(p, &q) : cl_geometry<float>(p, &q);
+}
+
+template <typename S, int TL>
+static int cl_launch(mga_plan* p, const ClArgs<S>& a, const ClGeom& q, cudaStream_t st) {
+  auto kern = q.NP <= 384 ? k_admm_cluster<S, TL, 384> : k_admm_cluster<S, TL, 1024>;
+  MGA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)q.smem));
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(a.B * q.CL));
+  cfg.blockDim = dim3(q.NP);
+  cfg.dynamicSmemBytes = q.smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = q.CL;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  MGA_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
+  MGA_LAUNCH_CHECK("k_admm_cluster");
+  return MGA_OK;
+}
+
+template <typename S>
+static int cl_admm(mga_plan* p, const mga_params* m, const void* y, void* x_out, int64_t B, int n_outer, int max_cg, double cg_tol,
+                   double admm_tol, double t_mean, double t_var, int diag_flags, const mga_admm_outputs* outs, cudaStream_t st) {
+  const GraphDev& g = p->g;
+  ClGeom q;
+  if (!cl_geometry<S>(p, &q)) { set_error("cluster mode: the window does not fit"); return MGA_ERR_UNSUPPORTED; }
+  const bool tol_mode = cg_tol > 0 || admm_tol > 0;
+  if (tol_mode && B != 1) { set_error("cluster mode: the stop tests are per window, tolerance mode takes B = 1"); return MGA_ERR_UNSUPPORTED; }
+  ClArgs<S> a{};
+  a.N = g.N; a.NP = q.NP; a.T = g.T; a.t_in = g.t_in; a.CL = q.CL; a.kd = g.kd; a.ku = g.ku; a.q1 = g.q1; a.nnz = g.nnz;
+  a.n_outer = n_outer; a.max_cg = max_cg; a.want_diag = (diag_flags & 1) ? 1 : 0;
+  a.B = B;
+  a.nbr_d = g.nbr_d; a.d_w = g.d_w; a.nbr_u = g.nbr_u; a.u_w = g.u_w; a.csr_ptr = g.csr_ptr; a.csr_src = g.csr_src; a.csr_w = g.csr_w;
+  a.y = static_cast<const S*>(y); a.x_out = static_cast<S*>(x_out);
+  a.out[0] = static_cast<S*>(outs->zu); a.out[1] = static_cast<S*>(outs->zd); a.out[2] = static_cast<S*>(outs->phi);
+  a.out[3] = static_cast<S*>(outs->gamma); a.out[4] = static_cast<S*>(outs->gamma_u); a.out[5] = static_cast<S*>(outs->gamma_d);
+  a.alpha = static_cast<S*>(outs->alpha); a.beta = static_cast<S*>(outs->beta);
+  if (a.alpha && !a.beta) a.alpha = nullptr;
+  a.cg_tol = cg_tol; a.admm_tol = admm_tol;
+  a.rho = (S)m->rho; a.rho_u = (S)m->rho_u; a.rho_d = (S)m->rho_d; a.thr = (S)(m->mu_d1 / m->rho);
+  a.ax = (S)((m->rho_u + m->rho_d) / 2); a.cx = (S)(m->rho / 2);
+  a.azu = (S)(m->rho_u / 2); a.czu = (S)m->mu_u;
+  a.azd = (S)(m->rho_d / 2); a.czd = (S)m->mu_d2;
+  a.t_mean = (float)t_mean; a.t_var = (float)t_var;
+  // diagnostics: the non-finite column is needed even with diagnostics off -> a scratch row block in the workspace
+  const size_t diag_bytes = (size_t)std::max(n_outer, 1) * MGA_DIAG_COLS * sizeof(double);
+  double* diag = a.want_diag ? outs->diag : nullptr;
+  if (!diag) {
+    int rc = ensure_workspace(p, p->ws, diag_bytes);
+    if (rc) return rc;
+    diag = static_cast<double*>(p->ws.base);
+  }
+  a.diag = diag;
+  a.dx_sum = a.want_diag ? outs->dx_sum : nullptr;
+  if (!(a.want_diag && (diag_flags & 2))) {
+    MGA_CUDA(cudaMemsetAsync(diag, 0, diag_bytes, st));
+    if (a.dx_sum) MGA_CUDA(cudaMemsetAsync(a.dx_sum, 0, (size_t)n_outer * g.T * g.N * sizeof(double), st));
+  }
+  // iteration counts of tolerance mode come back through the plan's pinned block (device-visible host memory)
+  int* h_iters = reinterpret_cast<int*>(static_cast<char*>(p->pinned) + 1024);
+  if (tol_mode) {
+    if ((size_t)n_outer * 3 * sizeof(int) + 2048 > p->pinned_bytes) { set_error("cluster mode: too many outer iterations"); return MGA_ERR_UNSUPPORTED; }
+    for (int k = 0; k < n_outer * 3; ++k) h_iters[64 + k] = -1;
+    h_iters[0] = 0;
+    a.cg_iters = h_iters + 64;
+    a.outer_done = h_iters;
+  }
+  int rc;
+  switch (q.TL) {
+    case 1: rc = cl_launch<S, 1>(p, a, q, st); break;
+    case 2: rc = cl_launch<S, 2>(p, a, q, st); break;
+    case 3: rc = cl_launch<S, 3>(p, a, q, st); break;
+    default: rc = cl_launch<S, 4>(p, a, q, st); break;
+  }
+  if (rc) return rc;
+  if (tol_mode) {
+    MGA_CUDA(cudaStreamSynchronize(st));
+    const int done = h_iters[0];
+    if (outs->cg_iters) for (int k = 0; k < n_outer * 3; ++k) outs->cg_iters[k] = k < done * 3 ? h_iters[64 + k] : -1;
+    if (outs->outer_done) *outs->outer_done = done;
+  } else {
+    if (outs->cg_iters) for (int k = 0; k < n_outer * 3; ++k) outs->cg_iters[k] = -1;
+    if (outs->outer_done) *outs->outer_done = n_outer;
+  }
+  return MGA_OK;
+}
+
+int cluster_admm(mga_plan* p, const mga_params* m, const void* y, void* x_out, int64_t B, int dtype, int n_outer, int max_cg,
+                 double cg_tol, double admm_tol, double t_mean, double t_var, int diag_flags, const mga_admm_outputs* outs,
+                 cudaStream_t st) {
+  if (dtype == MGA_F64)
+    return cl_admm<double>(p, m, y, x_out, B, n_outer, max_cg, cg_tol, admm_tol, t_mean, t_var, diag_flags, outs, st);
+  return cl_admm<float>(p, m, y, x_out, B, n_outer, max_cg, cg_tol, admm_tol, t_mean, t_var, diag_flags, outs, st);
+}
+
+}  // namespace mga

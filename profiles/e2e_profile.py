@@ -17,7 +17,7 @@ yp = y.pin_memory()
 for _ in range(3):
     blk.combined_loop(yp, print_info=False)
 torch.cuda.synchronize()
-n = 20
+n = 20 if B >= 256 else 2
 t0 = time.perf_counter()
 for _ in range(n):
     blk._reset_lists(all_lists=True)
