@@ -548,10 +548,12 @@ class ADMM_algorithm():
                     for name in ("zu", "zd", "phi", "gamma", "gamma_u", "gamma_d"):
                         its[name] = torch.zeros_like(x)
                         setattr(outs, name, its[name].data_ptr())
-                diag_d = torch.zeros((max(n_outer, 1), _cabi.DIAG_COLS), dtype=torch.float64, device=dev)
-                dx_d = torch.zeros((max(n_outer, 1), T, N * Cn), dtype=torch.float64, device=dev)
-                alpha = torch.zeros((max(n_outer, 1), 3, max(n_cg, 1), B), dtype=y.dtype, device=dev)
-                beta = torch.zeros_like(alpha)
+                # (the library zeroes the diagnostics itself; alpha / beta are read up to the iteration counts only)
+                no, dn, xn = max(n_outer, 1), max(n_outer, 1) * _cabi.DIAG_COLS, max(n_outer, 1) * T * N * Cn
+                dd = torch.empty((dn + xn,), dtype=torch.float64, device=dev)
+                diag_d, dx_d = dd[:dn].view(no, _cabi.DIAG_COLS), dd[dn:].view(no, T, N * Cn)
+                alpha = torch.empty((2, no, 3, max(n_cg, 1), B), dtype=y.dtype, device=dev)
+                alpha, beta = alpha[0], alpha[1]
                 outs.diag, outs.dx_sum = diag_d.data_ptr(), dx_d.data_ptr()
                 outs.alpha, outs.beta = alpha.data_ptr(), beta.data_ptr()
                 outs.cg_iters = cg_iters.ctypes.data
@@ -559,9 +561,8 @@ class ADMM_algorithm():
                 _cabi.check(L.mga_admm_solve(plan.handle, C.byref(prm), _cabi.ptr(yd), y_rows, _cabi.ptr(md),
                                              _cabi.ptr(x), B, dt, n_outer, n_cg, cg_tol, admm_tol, t_mean, t_var, 1,
                                              C.byref(outs), _cabi.MODE[self.mode], _cabi.stream_ptr(dev)))
-                torch.cuda.current_stream(dev).synchronize()
-                diag_h = diag_d.cpu().numpy()
-                dx_h = dx_d.cpu().numpy()
+                dd_h = dd.cpu().numpy()                                   # (synchronises the stream)
+                diag_h, dx_h = dd_h[:dn].reshape(no, _cabi.DIAG_COLS), dd_h[dn:].reshape(no, T, N * Cn)
                 self.last_iterates = {k: v.to(out_device) for k, v in its.items()} if want_iter else None
                 self.last_mode = 'device'
         if self.diag_reduce is not None:      # shards of one batch: sum the partial sums over the ranks

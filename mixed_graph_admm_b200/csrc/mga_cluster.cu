@@ -6,7 +6,8 @@
 // Why a cluster: a float64 window of PEMS size (307 nodes x 24 steps: 59 KB per vector, 12 vectors live) does not fit the
 // registers / shared memory of one SM, and with the vectors in L2 one SM executes every gather itself (measured: 28 us
 // per CG iteration).  Here the T time steps are dealt to the CTAs of a cluster as slabs of TL consecutive steps
-// (T = 24 -> 8 CTAs x 3 steps); a thread owns one node over the slab of its CTA:
+// (T = 24 -> 8 CTAs x 3 steps); a thread owns one node at RPT consecutive steps of the slab (PEMS sizes: one step per
+// thread, 3 x 320 threads per CTA - with one thread per node and slab the gathers of a step ran one after the other):
 //   * CG vectors of the thread's points in registers, the seven ADMM state vectors in shared memory;
 //   * the vector other threads gather from (p, then q = L_d p) is staged per CTA as TL + 1 time rows: the slab plus ONE
 //     halo row, pushed by the neighbouring CTA through distributed shared memory (L_d reads step t-1, L_d^T step t+1;
@@ -34,11 +35,13 @@ constexpr int kClMaxCL = 8;     // portable cluster size
 
 template <typename S>
 struct ClArgs {
-  int N, NP, T, t_in, CL, kd, ku, q1, nnz;
+  int N, NP, T, t_in, CL, TL, kd, ku, q1, nnz;      // TL: time steps per CTA
+  int transpose_exact;
   int n_outer, max_cg, want_diag;
   int64_t B;
   const int* nbr_d; const float* d_w; const int* nbr_u; const float* u_w;
   const int* csr_ptr; const int* csr_src; const float* csr_w;
+  const int* perm;         // perm[internal node] = caller's node (tables in reverse-Cuthill-McKee order), or NULL
   const S* y; S* x_out;
   S* out[6];               // zu, zd, phi, gamma, gamma_u, gamma_d (optional)
   double* diag; double* dx_sum;
@@ -60,9 +63,10 @@ __device__ __forceinline__ S cl_soft(S s, S d) {
   return sg * u * (S)(u > (S)0);   // ADMM.py:407-408
 }
 
-template <typename S, int TL>
+template <typename S, int RPT>
 struct ClCtx {
   int N, NP, T, t_in, t0, i, rank, CL, kd, ku, q1;
+  int TL, l0;     // time steps per CTA; this thread's first local step (it owns l0 .. l0 + RPT - 1)
   bool active;
   const int* nbr_d; const float* w_d; const int* nbr_u; const float* w_u;
   const int* cptr; const int* csrc; const float* cw;
@@ -71,6 +75,7 @@ struct ClCtx {
   S* red;         // 32 warp partials
   S* slots;       // [2][kClMaxCL] cluster reduction slots (a full copy in every CTA), double-buffered
   int parity;
+  bool qdot;      // the in-list is the exact transpose of the forward temporal table
   cg::cluster_group cl = cg::this_cluster();
 
   // Sum over the whole window (all CTAs of the cluster), the same bits in every thread of the cluster.
@@ -92,123 +97,201 @@ struct ClCtx {
     return tot;
   }
 
-  // own steps -> pbuf rows 1..TL, last own step -> halo row 0 of the next CTA; cluster barrier
-  __device__ __forceinline__ void publish_p(const S (&v)[TL]) {
+  // the same sum in two halves around a cluster barrier the caller has anyway
+  __device__ __forceinline__ void csum_post(S v) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum<S>(v);
+    if (lane == 0) red[w] = v;
+    __syncthreads();
+    if (threadIdx.x < (unsigned)CL) {
+      S t = 0;
+      for (int k = 0; k < nw; ++k) t += red[k];
+      cl.map_shared_rank(slots, threadIdx.x)[parity * kClMaxCL + rank] = t;
+    }
+  }
+  __device__ __forceinline__ S csum_read() {
+    S tot = 0;
+    for (int r = 0; r < CL; ++r) tot += slots[parity * kClMaxCL + r];
+    parity ^= 1;
+    return tot;
+  }
+
+  // K sums at once (one CTA barrier, one cluster barrier): the outer stop test needs six norms
+  template <int K>
+  __device__ __forceinline__ void csum_vec(S (&v)[K], S* scratch /* K x 32 local */, S* vs /* K x kClMaxCL, written by every CTA */) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    S* part = scratch;                    // [K][32] warp partials
 #pragma unroll
-    for (int l = 0; l < TL; ++l) pbuf[(l + 1) * NP + i] = v[l];
-    if (rank + 1 < CL) cl.map_shared_rank(pbuf, rank + 1)[i] = v[TL - 1];
+    for (int k = 0; k < K; ++k) {
+      const S t = warp_sum<S>(v[k]);
+      if (lane == 0) part[k * 32 + w] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x < (unsigned)(CL * K)) {
+      const int r = threadIdx.x / K, k = threadIdx.x - r * K;
+      S t = 0;
+      for (int q = 0; q < nw; ++q) t += part[k * 32 + q];
+      cl.map_shared_rank(vs, r)[k * kClMaxCL + rank] = t;
+    }
+    cl.sync();
+#pragma unroll
+    for (int k = 0; k < K; ++k) {
+      S tot = 0;
+      for (int r = 0; r < CL; ++r) tot += vs[k * kClMaxCL + r];
+      v[k] = tot;
+    }
+    // (`vs` is written again an outer iteration later: dozens of cluster barriers after these reads)
+  }
+
+  // own steps -> pbuf rows 1..TL, last own step -> halo row 0 of the next CTA; cluster barrier
+  __device__ __forceinline__ void publish_p(const S (&v)[RPT]) {
+#pragma unroll
+    for (int m = 0; m < RPT; ++m) pbuf[(l0 + m + 1) * NP + i] = v[m];
+    if (rank + 1 < CL && l0 + RPT == TL) cl.map_shared_rank(pbuf, rank + 1)[i] = v[RPT - 1];
     cl.sync();
   }
   // own steps -> qbuf rows 0..TL-1, first own step -> halo row TL of the previous CTA; cluster barrier
-  __device__ __forceinline__ void publish_q(const S (&v)[TL]) {
+  __device__ __forceinline__ void publish_q(const S (&v)[RPT]) {
 #pragma unroll
-    for (int l = 0; l < TL; ++l) qbuf[l * NP + i] = v[l];
-    if (rank > 0) cl.map_shared_rank(qbuf, rank - 1)[TL * NP + i] = v[0];
+    for (int m = 0; m < RPT; ++m) qbuf[(l0 + m) * NP + i] = v[m];
+    if (rank > 0 && l0 == 0) cl.map_shared_rank(qbuf, rank - 1)[TL * NP + i] = v[0];
     cl.sync();
   }
-  // q = L_d v with v published in pbuf (ADMM.py:166-177): q[t] = v[t] - sum_j w_j v[t-1, nbr_j], q[0] = 0
-  __device__ __forceinline__ void ldr(const S (&v)[TL], S (&q)[TL]) const {
+  // q = L_d v with v published in pbuf (ADMM.py:166-177): q[t] = v[t] - sum_j w_j v[t-1, nbr_j], q[0] = 0.
+  // Neighbour-major: one table entry per neighbour serves all the thread's steps.
+  __device__ __forceinline__ void ldr(const S (&v)[RPT], S (&q)[RPT]) const {
+    S acc[RPT];
 #pragma unroll
-    for (int l = 0; l < TL; ++l) {
-      const int t = t0 + l;
-      S acc = 0;
-      if (active && t >= 1 && t < T) {
-        const S* prev = pbuf + l * NP;
-        for (int j = 0; j < kd; ++j) {
-          const int c = nbr_d[i * kd + j];
-          if (c >= 0) acc += (S)w_d[i * kd + j] * prev[c];
-        }
-        acc = v[l] - acc;
+    for (int m = 0; m < RPT; ++m) acc[m] = 0;
+    if (active) {
+      const S* prev = pbuf + l0 * NP;                  // row l0 + m holds step t - 1 of the thread's m-th step
+      for (int j = 0; j < kd; ++j) {
+        const int c = nbr_d[i * kd + j];
+        if (c < 0) continue;
+        const S w = (S)w_d[i * kd + j];
+#pragma unroll
+        for (int m = 0; m < RPT; ++m) acc[m] += w * prev[m * NP + c];
       }
-      q[l] = acc;
+    }
+#pragma unroll
+    for (int m = 0; m < RPT; ++m) {
+      const int t = t0 + l0 + m;
+      q[m] = (active && t >= 1 && t < T) ? v[m] - acc[m] : (S)0;
     }
   }
   // (L_d^T + Q1) v with v published in qbuf (ADMM.py:196-223): the "father" sum over the in-list at step t+1
-  __device__ __forceinline__ void ldrt(const S (&v)[TL], S (&out)[TL]) const {
+  __device__ __forceinline__ void ldrt(const S (&v)[RPT], S (&out)[RPT]) const {
+    S f[RPT];
 #pragma unroll
-    for (int l = 0; l < TL; ++l) {
-      const int t = t0 + l;
-      S o = 0;
-      if (active && t < T) {
-        if (t == T - 1) {
-          o = v[l];
-        } else {
-          const S* next = qbuf + (l + 1) * NP;
-          S f = 0;
-          for (int e = cptr[i]; e < cptr[i + 1]; ++e) f += (S)cw[e] * next[csrc[e]];
-          o = (t == 0 && !q1) ? -f : v[l] - f;
-        }
+    for (int m = 0; m < RPT; ++m) f[m] = 0;
+    if (active) {
+      const S* next = qbuf + (l0 + 1) * NP;
+      for (int e = cptr[i]; e < cptr[i + 1]; ++e) {
+        const int src = csrc[e];
+        const S w = (S)cw[e];
+#pragma unroll
+        for (int m = 0; m < RPT; ++m) f[m] += w * next[m * NP + src];
       }
-      out[l] = o;
+    }
+#pragma unroll
+    for (int m = 0; m < RPT; ++m) {
+      const int t = t0 + l0 + m;
+      S o = 0;
+      if (active && t < T) o = (t == T - 1) ? v[m] : ((t == 0 && !q1) ? -f[m] : v[m] - f[m]);   // rows beyond T - 1 gather zeros
+      out[m] = o;
     }
   }
   // L_u v with v published in pbuf (ADMM.py:138-148)
-  __device__ __forceinline__ void lu(const S (&v)[TL], S (&out)[TL]) const {
+  __device__ __forceinline__ void lu(const S (&v)[RPT], S (&out)[RPT]) const {
+    S acc[RPT];
 #pragma unroll
-    for (int l = 0; l < TL; ++l) {
-      const int t = t0 + l;
-      S o = 0;
-      if (active && t < T) {
-        const S* row = pbuf + (l + 1) * NP;
-        S acc = 0;
-        for (int j = 0; j < ku; ++j) {
-          const int c = nbr_u[i * ku + j];
-          if (c >= 0) acc += (S)w_u[i * ku + j] * row[c];
-        }
-        o = v[l] - acc;
+    for (int m = 0; m < RPT; ++m) acc[m] = 0;
+    if (active) {
+      const S* row = pbuf + (l0 + 1) * NP;
+      for (int j = 0; j < ku; ++j) {
+        const int c = nbr_u[i * ku + j];
+        if (c < 0) continue;
+        const S w = (S)w_u[i * ku + j];
+#pragma unroll
+        for (int m = 0; m < RPT; ++m) acc[m] += w * row[m * NP + c];
       }
-      out[l] = o;
+    }
+#pragma unroll
+    for (int m = 0; m < RPT; ++m) {
+      const int t = t0 + l0 + m;
+      out[m] = (active && t < T) ? v[m] - acc[m] : (S)0;
     }
   }
-  // out = A v for system SYS (ADMM.py:371-399), the reference's evaluation order
-  template <int SYS>
-  __device__ __forceinline__ void apply(const S (&v)[TL], S (&out)[TL], S a, S c) {
+  // out = A v for system SYS (ADMM.py:371-399), the reference's evaluation order.
+  // DOT: also dot = <v, A v>.  For the x / z_d systems with an exact transpose (kNN scatter mode, line graph)
+  // A = D + c L_d^T L_d, so <v, A v> = sum D v^2 + c ||L_d v||^2: every term is known once q = L_d v is, and the partial
+  // sums ride on the cluster barrier that publishes q - one barrier fewer per CG iteration (the same value up to
+  // rounding; the resident float32 kernel does the same).
+  template <int SYS, bool DOT>
+  __device__ __forceinline__ void apply(const S (&v)[RPT], S (&out)[RPT], S a, S c, S& dot) {
     publish_p(v);
     if (SYS == MGA_SYS_ZU) {
       lu(v, out);
+      S loc = 0;
 #pragma unroll
-      for (int l = 0; l < TL; ++l) out[l] = c * out[l] + a * v[l];                       // ADMM.py:390
+      for (int m = 0; m < RPT; ++m) {
+        out[m] = c * out[m] + a * v[m];                                                 // ADMM.py:390
+        loc += v[m] * out[m];
+      }
+      if (DOT) dot = csum(loc);
       return;
     }
-    S q[TL];
+    S q[RPT];
     ldr(v, q);
-    publish_q(q);
-    ldrt(q, out);
+    const bool fused = DOT && qdot;
+    if (fused) {
+      S loc = 0;
 #pragma unroll
-    for (int l = 0; l < TL; ++l) {
-      if (SYS == MGA_SYS_X) {
-        const S hx = (t0 + l < t_in) ? v[l] : (S)0;                                     // H^T H (ADMM.py:372-374)
-        out[l] = (hx + a * v[l]) + c * out[l];                                          // ADMM.py:379
-      } else {
-        out[l] = c * out[l] + a * v[l];                                                 // ADMM.py:394
+      for (int m = 0; m < RPT; ++m) {
+        const S hx = (SYS == MGA_SYS_X && t0 + l0 + m < t_in) ? v[m] * v[m] : (S)0;
+        loc += (hx + a * (v[m] * v[m])) + c * (q[m] * q[m]);
       }
+      csum_post(loc);                     // partial -> every CTA's slot; completed by the barrier of publish_q
     }
+    publish_q(q);
+    if (fused) dot = csum_read();
+    ldrt(q, out);
+    S loc = 0;
+#pragma unroll
+    for (int m = 0; m < RPT; ++m) {
+      if (SYS == MGA_SYS_X) {
+        const S hx = (t0 + l0 + m < t_in) ? v[m] : (S)0;                                // H^T H (ADMM.py:372-374)
+        out[m] = (hx + a * v[m]) + c * out[m];                                          // ADMM.py:379
+      } else {
+        out[m] = c * out[m] + a * v[m];                                                 // ADMM.py:394
+      }
+      loc += v[m] * out[m];
+    }
+    if (DOT && !fused) dot = csum(loc);
   }
 
   // CG_solver (ADMM.py:329-368): r holds the right-hand side on entry, x the warm start.  Returns the iteration count
   // (tol > 0 and reached) or -1.  alpha_out / beta_out: this window's column of the (max_cg, B) arrays or NULL.
   template <int SYS>
-  __device__ __forceinline__ int cg_solve(S (&x)[TL], S (&r)[TL], S a, S c, int max_cg, double tol, S* alpha_out, S* beta_out,
+  __device__ __forceinline__ int cg_solve(S (&x)[RPT], S (&r)[RPT], S a, S c, int max_cg, double tol, S* alpha_out, S* beta_out,
                                           int64_t B) {
-    S p[TL], ap[TL];
-    apply<SYS>(x, ap, a, c);
+    S p[RPT], ap[RPT];
+    S pap = 0;
+    apply<SYS, false>(x, ap, a, c, pap);
     S loc = 0;
 #pragma unroll
-    for (int l = 0; l < TL; ++l) {
+    for (int l = 0; l < RPT; ++l) {
       r[l] = r[l] - ap[l];
       p[l] = r[l];
       loc += r[l] * r[l];
     }
     S rr = csum(loc);
     for (int k = 0; k < max_cg; ++k) {
-      apply<SYS>(p, ap, a, c);
+      apply<SYS, true>(p, ap, a, c, pap);
+      const S alpha = rr / pap;
       loc = 0;
 #pragma unroll
-      for (int l = 0; l < TL; ++l) loc += p[l] * ap[l];
-      const S alpha = rr / csum(loc);
-      loc = 0;
-#pragma unroll
-      for (int l = 0; l < TL; ++l) {
+      for (int l = 0; l < RPT; ++l) {
         x[l] = x[l] + alpha * p[l];
         r[l] = r[l] - alpha * ap[l];
         loc += r[l] * r[l];
@@ -222,18 +305,18 @@ struct ClCtx {
       }
       if (tol > 0 && sqrt(rr) < (S)tol) return k + 1;          // ADMM.py:360 (B = 1: the max over the batch is this window)
 #pragma unroll
-      for (int l = 0; l < TL; ++l) p[l] = r[l] + beta * p[l];
+      for (int l = 0; l < RPT; ++l) p[l] = r[l] + beta * p[l];
     }
     return -1;
   }
 };
 
 // MAXT: launch bound (384: PEMS-sized graphs keep their registers - no spills in float64; 1024: up to 1024 nodes)
-template <typename S, int TL, int MAXT>
+template <typename S, int RPT, int MAXT>
 __global__ void __launch_bounds__(MAXT, 1) k_admm_cluster(const ClArgs<S> a) {
   extern __shared__ __align__(16) unsigned char smem_cl[];
   cg::cluster_group cluster = cg::this_cluster();
-  const int N = a.N, NP = a.NP, T = a.T, t_in = a.t_in, CL = a.CL;
+  const int N = a.N, NP = a.NP, T = a.T, t_in = a.t_in, CL = a.CL, TL = a.TL;
   const int rank = (int)cluster.block_rank();
   const int64_t b = blockIdx.x / CL;
   // ---- carve shared memory
@@ -258,17 +341,22 @@ __global__ void __launch_bounds__(MAXT, 1) k_admm_cluster(const ClArgs<S> a) {
   for (int k = threadIdx.x; k < 2 * (TL + 1) * NP; k += blockDim.x) pbuf[k] = (S)0;     // incl. the outermost halo rows
   for (int k = threadIdx.x; k < 2 * kClMaxCL; k += blockDim.x) slots[k] = (S)0;
 
-  ClCtx<S, TL> c;
-  c.N = N; c.NP = NP; c.T = T; c.t_in = t_in; c.t0 = rank * TL; c.i = threadIdx.x; c.rank = rank; c.CL = CL;
-  c.kd = a.kd; c.ku = a.ku; c.q1 = a.q1;
-  c.active = (int)threadIdx.x < N;
+  ClCtx<S, RPT> c;
+  const int lr = threadIdx.x / NP;                                   // row group of this thread: steps lr * RPT .. + RPT - 1 of the slab
+  c.N = N; c.NP = NP; c.T = T; c.t_in = t_in; c.t0 = rank * TL; c.i = threadIdx.x - lr * NP; c.rank = rank; c.CL = CL;
+  c.TL = TL; c.l0 = lr * RPT;
+  c.kd = a.kd; c.ku = a.ku; c.q1 = a.q1; c.qdot = a.transpose_exact != 0;
+  c.active = c.i < N;
   c.nbr_d = nbr_d; c.w_d = w_d; c.nbr_u = nbr_u; c.w_u = w_u; c.cptr = cptr; c.csrc = csrc; c.cw = cw;
   c.pbuf = pbuf; c.qbuf = qbuf; c.red = red; c.slots = slots; c.parity = 0;
   cluster.sync();                                                    // tables and zeroed buffers of every CTA are in place
-  const int i = c.i, t0 = c.t0;
+  const int i = c.i, t0 = c.t0 + c.l0;                               // t0: the thread's first step
   const bool active = c.active;
-  auto st = [&](int v, int l) -> S& { return state[((size_t)v * TL + l) * NP + i]; };
-  const S* yw = a.y + (size_t)b * t_in * N + i;
+  auto st = [&](int v, int m) -> S& { return state[((size_t)v * TL + c.l0 + m) * NP + i]; };
+  // the tables come in reverse-Cuthill-McKee order: the 32 nodes of a warp gather from a few neighbouring rows (fewer
+  // shared-memory bank conflicts than with the caller's numbering); global memory keeps the caller's order
+  const int orig = active ? (a.perm ? a.perm[i] : i) : 0;
+  const S* yw = a.y + (size_t)b * t_in * N + orig;
 
   // ---- initial_guess (ADMM.py:766-781) and initial state (ADMM.py:537-544)
   {
@@ -282,9 +370,9 @@ __global__ void __launch_bounds__(MAXT, 1) k_admm_cluster(const ClArgs<S> a) {
     const S my = sy / (S)t_in, mty = sty / (S)t_in;
     const S w = (mty - (S)a.t_mean * my) / (S)a.t_var;
     const S cc = my - w * (S)a.t_mean;
-    S x[TL], q[TL];
+    S x[RPT], q[RPT];
 #pragma unroll
-    for (int l = 0; l < TL; ++l) {
+    for (int l = 0; l < RPT; ++l) {
       const int t = t0 + l;
       S v = 0;
       if (active && t < T) v = t < t_in ? yw[(size_t)t * N] : w * (S)(float)t + cc;
@@ -296,7 +384,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_admm_cluster(const ClArgs<S> a) {
     c.publish_p(x);
     c.ldr(x, q);                                                     // phi = L_d x (ADMM.py:541)
 #pragma unroll
-    for (int l = 0; l < TL; ++l) st(CS_PHI, l) = q[l];
+    for (int l = 0; l < RPT; ++l) st(CS_PHI, l) = q[l];
   }
 
   int outer_done = 0;
@@ -308,16 +396,16 @@ __global__ void __launch_bounds__(MAXT, 1) k_admm_cluster(const ClArgs<S> a) {
     S d[MGA_DIAG_COLS];
 #pragma unroll
     for (int k = 0; k < MGA_DIAG_COLS; ++k) d[k] = 0;
-    S r[TL], x[TL];
+    S r[RPT], x[RPT];
     // ---- RHS_x (ADMM.py:552-559): Ldr_T(gamma + rho phi)/2 + (rho_u zu + rho_d zd)/2 - (gu + gd)/2 + H^T y
     {
-      S v[TL], lt[TL];
+      S v[RPT], lt[RPT];
 #pragma unroll
-      for (int l = 0; l < TL; ++l) v[l] = st(CS_GAM, l) + a.rho * st(CS_PHI, l);
+      for (int l = 0; l < RPT; ++l) v[l] = st(CS_GAM, l) + a.rho * st(CS_PHI, l);
       c.publish_q(v);
       c.ldrt(v, lt);
 #pragma unroll
-      for (int l = 0; l < TL; ++l) {
+      for (int l = 0; l < RPT; ++l) {
         const int t = t0 + l;
         S o = 0;
         if (active && t < T) {
@@ -331,25 +419,25 @@ __global__ void __launch_bounds__(MAXT, 1) k_admm_cluster(const ClArgs<S> a) {
     // ---- x solve (ADMM.py:571), warm start x_old
     iters[0] = c.template cg_solve<MGA_SYS_X>(x, r, a.ax, a.cx, a.max_cg, a.cg_tol, al, be, a.B);
 #pragma unroll
-    for (int l = 0; l < TL; ++l) {
+    for (int l = 0; l < RPT; ++l) {
       const int t = t0 + l;
       if (active && t < T) {
         const S dx = x[l] - st(CS_X, l);
         d[MGA_DIAG_DX2] += dx * dx;
         d[MGA_DIAG_NONFINITE] += (S)(!isfinite(x[l]));
-        if (a.want_diag && a.dx_sum) atomicAdd(a.dx_sum + ((size_t)it * T + t) * N + i, (double)dx);
+        if (a.want_diag && a.dx_sum) atomicAdd(a.dx_sum + ((size_t)it * T + t) * N + orig, (double)dx);
       }
       st(CS_X, l) = x[l];
     }
     // ---- z_u solve (ADMM.py:579-580)
     {
-      S z[TL];
+      S z[RPT];
 #pragma unroll
-      for (int l = 0; l < TL; ++l) { r[l] = st(CS_GU, l) / (S)2 + a.azu * x[l]; z[l] = st(CS_ZU, l); }
+      for (int l = 0; l < RPT; ++l) { r[l] = st(CS_GU, l) / (S)2 + a.azu * x[l]; z[l] = st(CS_ZU, l); }
       iters[1] = c.template cg_solve<MGA_SYS_ZU>(z, r, a.azu, a.czu, a.max_cg, a.cg_tol, al ? al + sys_stride : nullptr,
                                                  be ? be + sys_stride : nullptr, a.B);
 #pragma unroll
-      for (int l = 0; l < TL; ++l) {
+      for (int l = 0; l < RPT; ++l) {
         if (active && t0 + l < T) {
           const S d0 = x[l] - z[l], d1 = z[l] - st(CS_ZU, l);
           d[MGA_DIAG_X_ZU2] += d0 * d0;
@@ -361,13 +449,13 @@ __global__ void __launch_bounds__(MAXT, 1) k_admm_cluster(const ClArgs<S> a) {
     }
     // ---- z_d solve (ADMM.py:587-588)
     {
-      S z[TL];
+      S z[RPT];
 #pragma unroll
-      for (int l = 0; l < TL; ++l) { r[l] = st(CS_GD, l) / (S)2 + a.azd * x[l]; z[l] = st(CS_ZD, l); }
+      for (int l = 0; l < RPT; ++l) { r[l] = st(CS_GD, l) / (S)2 + a.azd * x[l]; z[l] = st(CS_ZD, l); }
       iters[2] = c.template cg_solve<MGA_SYS_ZD>(z, r, a.azd, a.czd, a.max_cg, a.cg_tol, al ? al + 2 * sys_stride : nullptr,
                                                  be ? be + 2 * sys_stride : nullptr, a.B);
 #pragma unroll
-      for (int l = 0; l < TL; ++l) {
+      for (int l = 0; l < RPT; ++l) {
         if (active && t0 + l < T) {
           const S d0 = x[l] - z[l], d1 = z[l] - st(CS_ZD, l);
           d[MGA_DIAG_X_ZD2] += d0 * d0;
@@ -382,12 +470,12 @@ __global__ void __launch_bounds__(MAXT, 1) k_admm_cluster(const ClArgs<S> a) {
     }
     // ---- phi prox + gamma ascent (ADMM.py:600-605) and the remaining diagnostics (ADMM.py:612-637)
     {
-      S ldx[TL], lux[TL];
+      S ldx[RPT], lux[RPT];
       c.publish_p(x);
       c.ldr(x, ldx);
       if (a.want_diag) c.lu(x, lux);
 #pragma unroll
-      for (int l = 0; l < TL; ++l) {
+      for (int l = 0; l < RPT; ++l) {
         const int t = t0 + l;
         if (active && t < T) {
           const S gam = st(CS_GAM, l), pho = st(CS_PHI, l), q = ldx[l];
@@ -433,20 +521,19 @@ __global__ void __launch_bounds__(MAXT, 1) k_admm_cluster(const ClArgs<S> a) {
     outer_done = it + 1;
     if (a.admm_tol > 0) {
       // whole-window norms, as the reference takes them in the signal dtype (B = 1)
-      const S pzu = sqrt(c.csum(d[MGA_DIAG_X_ZU2])), dzu = sqrt(c.csum(d[MGA_DIAG_DZU2]));
-      const S pph = sqrt(c.csum(d[MGA_DIAG_PHI_LDX2])), dph = sqrt(c.csum(d[MGA_DIAG_DPHI2]));
-      const S pzd = sqrt(c.csum(d[MGA_DIAG_X_ZD2])), dzd = sqrt(c.csum(d[MGA_DIAG_DZD2]));
-      const S pri = fmax(fmax(pzu, pph), pzd), dua = fmax(fmax(dzu, dph), dzd);
+      S nrm[6] = {d[MGA_DIAG_X_ZU2], d[MGA_DIAG_DZU2], d[MGA_DIAG_PHI_LDX2], d[MGA_DIAG_DPHI2], d[MGA_DIAG_X_ZD2], d[MGA_DIAG_DZD2]};
+      c.template csum_vec<6>(nrm, dredS, dredS + MGA_DIAG_COLS * 32);
+      const S pri = fmax(fmax(sqrt(nrm[0]), sqrt(nrm[2])), sqrt(nrm[4])), dua = fmax(fmax(sqrt(nrm[1]), sqrt(nrm[3])), sqrt(nrm[5]));
       if ((double)pri < a.admm_tol && (double)dua < a.admm_tol) break;
     }
   }
   if (a.outer_done && rank == 0 && threadIdx.x == 0 && b == 0) *a.outer_done = outer_done;
   // ---- results
 #pragma unroll
-  for (int l = 0; l < TL; ++l) {
+  for (int l = 0; l < RPT; ++l) {
     const int t = t0 + l;
     if (active && t < T) {
-      const size_t at = ((size_t)b * T + t) * N + i;
+      const size_t at = ((size_t)b * T + t) * N + orig;
       a.x_out[at] = st(CS_X, l);
       if (a.out[0]) a.out[0][at] = st(CS_ZU, l);
       if (a.out[1]) a.out[1][at] = st(CS_ZD, l);
@@ -461,7 +548,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_admm_cluster(const ClArgs<S> a) {
 
 // ---- host side ------------------------------------------------------------------------------------------------
 struct ClGeom {
-  int CL, TL, NP;
+  int CL, TL, TR, RPT, NP;      // cluster size, steps per CTA, row groups per CTA (threads = NP * TR), steps per thread
   size_t smem;
 };
 
@@ -470,12 +557,16 @@ static bool cl_geometry(const mga_plan* p, ClGeom* out) {
   const GraphDev& g = p->g;
   if (g.temporal == MGA_TEMPORAL_BAND || g.u_wT != 1 || g.d_wT != 1 || g.N > 1024 || g.T > kClMaxCL * kClMaxTL) return false;
   ClGeom q;
+  q.NP = ((g.N + 31) / 32) * 32;
   q.CL = std::min(g.T, kClMaxCL);
   q.TL = (g.T + q.CL - 1) / q.CL;
+  q.TR = 1;                                       // one thread per node and slab: a table entry is read once for all its steps
+  if (const char* e = std::getenv("MGA_CLUSTER_TR")) q.TR = std::max(1, std::min(std::min(q.TL, 1024 / q.NP), std::atoi(e)));
+  q.RPT = (q.TL + q.TR - 1) / q.TR;
+  q.TL = q.TR * q.RPT;
   q.CL = (g.T + q.TL - 1) / q.TL;                 // no empty CTAs (T = 9 -> TL = 2 -> 5 CTAs)
-  q.NP = ((g.N + 31) / 32) * 32;
   q.smem = ((size_t)CS_COUNT * q.TL + 2 * (q.TL + 1)) * q.NP * sizeof(S) + (32 + 2 * kClMaxCL) * sizeof(S) +
-           ((size_t)g.N * (g.kd + g.ku) + g.nnz) * 8 + (size_t)(g.N + 1) * 4 + 16 + (size_t)MGA_DIAG_COLS * 32 * sizeof(S);
+           ((size_t)g.N * (g.kd + g.ku) + g.nnz) * 8 + (size_t)(g.N + 1) * 4 + 16 + ((size_t)MGA_DIAG_COLS * 32 + 6 * kClMaxCL) * sizeof(S);
   if (q.smem > (size_t)p->max_smem_optin) return false;
   *out = q;
   return true;
@@ -486,13 +577,13 @@ bool cluster_eligible(const mga_plan* p, int dtype) {
   return dtype == MGA_F64 ? cl_geometry<double>(p, &q) : cl_geometry<float>(p, &q);
 }
 
-template <typename S, int TL>
+template <typename S, int RPT>
 static int cl_launch(mga_plan* p, const ClArgs<S>& a, const ClGeom& q, cudaStream_t st) {
-  auto kern = q.NP <= 384 ? k_admm_cluster<S, TL, 384> : k_admm_cluster<S, TL, 1024>;
+  auto kern = q.NP * q.TR <= 384 ? k_admm_cluster<S, RPT, 384> : k_admm_cluster<S, RPT, 1024>;
   MGA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)q.smem));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(a.B * q.CL));
-  cfg.blockDim = dim3(q.NP);
+  cfg.blockDim = dim3(q.NP * q.TR);
   cfg.dynamicSmemBytes = q.smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -516,10 +607,15 @@ static int cl_admm(mga_plan* p, const mga_params* m, const void* y, void* x_out,
   const bool tol_mode = cg_tol > 0 || admm_tol > 0;
   if (tol_mode && B != 1) { set_error("cluster mode: the stop tests are per window, tolerance mode takes B = 1"); return MGA_ERR_UNSUPPORTED; }
   ClArgs<S> a{};
-  a.N = g.N; a.NP = q.NP; a.T = g.T; a.t_in = g.t_in; a.CL = q.CL; a.kd = g.kd; a.ku = g.ku; a.q1 = g.q1; a.nnz = g.nnz;
+  a.N = g.N; a.NP = q.NP; a.T = g.T; a.t_in = g.t_in; a.CL = q.CL; a.TL = q.TL; a.transpose_exact = p->ldrt_gather ? 0 : 1; a.kd = g.kd; a.ku = g.ku; a.q1 = g.q1; a.nnz = g.nnz;
   a.n_outer = n_outer; a.max_cg = max_cg; a.want_diag = (diag_flags & 1) ? 1 : 0;
   a.B = B;
   a.nbr_d = g.nbr_d; a.d_w = g.d_w; a.nbr_u = g.nbr_u; a.u_w = g.u_w; a.csr_ptr = g.csr_ptr; a.csr_src = g.csr_src; a.csr_w = g.csr_w;
+  if (p->has_s2 && !std::getenv("MGA_CLUSTER_NATURAL")) {       // the streaming path's reordered tables (same entries, same order within a row)
+    const Graph2& g2 = p->g2;
+    a.nbr_d = g2.nbr_d; a.d_w = g2.w_d; a.nbr_u = g2.nbr_u; a.u_w = g2.w_u;
+    a.csr_ptr = g2.in_ptr; a.csr_src = g2.in_src; a.csr_w = g2.in_w; a.perm = g2.perm;
+  }
   a.y = static_cast<const S*>(y); a.x_out = static_cast<S*>(x_out);
   a.out[0] = static_cast<S*>(outs->zu); a.out[1] = static_cast<S*>(outs->zd); a.out[2] = static_cast<S*>(outs->phi);
   a.out[3] = static_cast<S*>(outs->gamma); a.out[4] = static_cast<S*>(outs->gamma_u); a.out[5] = static_cast<S*>(outs->gamma_d);
@@ -555,7 +651,7 @@ static int cl_admm(mga_plan* p, const mga_params* m, const void* y, void* x_out,
     a.outer_done = h_iters;
   }
   int rc;
-  switch (q.TL) {
+  switch (q.RPT) {
     case 1: rc = cl_launch<S, 1>(p, a, q, st); break;
     case 2: rc = cl_launch<S, 2>(p, a, q, st); break;
     case 3: rc = cl_launch<S, 3>(p, a, q, st); break;
