@@ -21,7 +21,8 @@ Prints ONE JSON line (rank 0):
   cpu_baseline   the oracle port of the reference's torch-CPU path on the host cores (bounded sample)
   probes     (N = 1) the other BASELINE.json configs on the same clock: T = 288 / B = 256 and 20 000 nodes / k = 8 /
              T = 24 / B = 64 (streaming kernels vs the HBM roofline, each with a 2-window parity sample against the
-             oracle), the 65 536-window batch on one GPU, and the fused CG iteration (``cg_iter``)
+             oracle), the 65 536-window batch on one GPU, the reference's own notebook call (B = 1, float64, tolerances),
+             and the fused CG iteration (``cg_iter`` at PEMS04 shape, ``cg_iter_long_horizon`` at T = 288)
 """
 from __future__ import annotations
 
@@ -316,6 +317,88 @@ def probe_config(name, N, k, T, B, ratio, gseed, dev, flush, peak, steps=6):
     return out
 
 
+def cg_iter_probe(dev, flush, peak, N, k, T, B):
+    """The fused CG iteration where the streaming kernels are the real path (windows too long for one CTA): mga_cg_solve
+    with 10 and 30 fixed iterations on a batch larger than L2; the difference / 20 is the time of one iteration
+    (operator kernel + update kernel), free of the layout conversion and the initial residual."""
+    import ctypes as C
+
+    from mixed_graph_admm_b200 import _cabi
+    blk, _ = build_problem(1, seed=0, device=dev, mode="streaming", N=N, k=k, T=T, t_in=T // 2)
+    L = _cabi.lib()
+    plan, prm = blk._plan(), blk._params()
+    _cabi.check(L.mga_plan_set_cg_mode(plan.handle, _cabi.MODE["streaming"]))
+    g = torch.Generator().manual_seed(1)
+    rhs = torch.rand(B, T, N, 1, generator=g).to(dev)
+    x = torch.zeros_like(rhs)
+    st = torch.cuda.current_stream(dev)
+    n = B * T * N
+    out = {"N": N, "T": T, "batch": B, "vector_mb": n * 4 / 1e6, "peak": peak, "unit": "GB/s (algorithmic bytes / time)"}
+    for sysname in ("x", "zu"):
+        res = {}
+        for n_cg in (10, 30):
+            def solve_cg():
+                _cabi.check(L.mga_cg_solve(plan.handle, _cabi.SYS[sysname], C.byref(prm), _cabi.ptr(rhs), _cabi.ptr(x), None, B,
+                                           _cabi.MGA_F32, n_cg, -1.0, None, None, None, st.cuda_stream))
+            for _ in range(2):
+                x.zero_()
+                solve_cg()
+            torch.cuda.synchronize(dev)
+            best = 1e9
+            for _ in range(4):
+                x.zero_()
+                flush.fill_(1)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(st)
+                solve_cg()
+                b.record(st)
+                torch.cuda.synchronize(dev)
+                best = min(best, a.elapsed_time(b))
+            res[n_cg] = best
+        us = (res[30] - res[10]) / 20 * 1e3
+        per_it = cg_iter_bytes_per_point(sysname)
+        gbs = per_it * n / (us * 1e-6) / 1e9
+        out[sysname] = {"us_per_iter": us, "achieved": gbs, "frac": gbs / peak, "bytes_per_point_per_iter": per_it,
+                        "ms_10_iters": res[10], "ms_30_iters": res[30]}
+    del rhs, x, blk
+    torch.cuda.empty_cache()
+    return out
+
+
+def notebook_probe(dev):
+    """The reference's own call pattern (ADMM.py:76-80 defaults): B = 1, float64, T = 24, tolerance mode, 30 outer
+    iterations, through the public API with a CPU tensor in and a CPU tensor out; the CPU oracle beside it."""
+    from mixed_graph_admm_b200 import synth
+    from mixed_graph_admm_b200.ADMM import ADMM_algorithm
+    from oracle import admm_oracle as O
+    N, k, T, t_in = 307, 6, 24, 12
+    gi = synth.road_graph(N, 1.1, seed=4)
+    blk = ADMM_algorithm(gi, synth.admm_info(N), use_kNN=True, k=k, u_sigma=50, d_sigma=50, t_in=t_in, T=T, device=dev)
+    blk.max_ADMM_iter = 30
+    y = synth.signals(1, t_in, N, seed=1, smooth=True, dtype=torch.float64)
+    for _ in range(3):
+        blk._reset_lists(all_lists=True)
+        x = blk.combined_loop(y, print_info=False)
+    n = 20
+    t0 = time.perf_counter()
+    for _ in range(n):
+        blk._reset_lists(all_lists=True)
+        x = blk.combined_loop(y, print_info=False)
+    dt = (time.perf_counter() - t0) / n
+    og = O.OracleGraph(nbr=blk.connect_list, u_w=blk.u_ew, d_w=blk.d_ew)
+    prm = O.OracleParams(**synth.admm_info(N), t_in=t_in, T=T)
+    torch.set_num_threads(os.cpu_count() or 1)
+    t0 = time.perf_counter()
+    tr = O.admm_combined(og, prm, y, max_admm_iter=30)
+    t_cpu = time.perf_counter() - t0
+    return {"call": "combined_loop(y_cpu) with the class defaults CG_tol 1e-8 / ADMM_tol 1e-6, B = 1, float64, N = 307, T = 24, 30 outer",
+            "ms_per_solve": 1e3 * dt, "solves_per_s": 1 / dt, "kernel": "k_admm_cluster (one launch per solve)",
+            "cg_iters_x_equal": blk.CG_iter_x == tr.cg_iter_x, "cg_iters_zu_equal": blk.CG_iter_zu == tr.cg_iter_zu,
+            "cg_iters_zd_equal": blk.CG_iter_zd == tr.cg_iter_zd, "cg_iters_x": blk.CG_iter_x[:8],
+            "rel_l2_vs_oracle": ((x.double() - tr.x.double()).norm() / tr.x.double().norm()).item(),
+            "cpu_oracle_ms_per_solve": 1e3 * t_cpu, "cpu_threads": torch.get_num_threads()}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -497,8 +580,9 @@ def main():
                         "d2h_bytes_per_step": int(B * npts * 4 + coef_bytes + N_OUTER * (_cabi.DIAG_COLS + npts) * 8),
                         "steps": e2e_steps, "ms_per_call": e2e_ms[:40], "frac_of_value": e2e_val / value,
                         "api": ("parallel.solve_sharded(blk, y_pinned_cpu_shard) -> " if world > 1 else "") +
-                               "ADMM_algorithm.combined_loop(y_pinned_cpu) -> mga_admm_solve_host; x, alpha_*/beta_* and the "
-                               "diagnostics lists come back"},
+                               "ADMM_algorithm.combined_loop(y_pinned_cpu) -> mga_admm_solve_host; x, the CG coefficient arrays "
+                               "and the diagnostics sums come back to the host inside the timed call (the python list "
+                               "entries over them are created when a list is first read)"},
                 "gpu_launches": int(launches), "wall_s_timed_region": t_wall1 - t_wall0, "clocks": clocks, "roofline": roof}
 
     # ---- the other BASELINE configs on the same clock (rank 0, N = 1 only)
@@ -522,10 +606,18 @@ def main():
             torch.cuda.empty_cache()
         except Exception as e:
             probes["global_batch_65536_one_gpu"] = {"error": repr(e)[:300]}
+        try:
+            probes["notebook_call_b1_f64_tolerance"] = notebook_probe(dev)
+        except Exception as e:
+            probes["notebook_call_b1_f64_tolerance"] = {"error": repr(e)[:300]}
         line["probes"] = probes
 
     # ---- the fused CG iteration in streaming mode vs the HBM roofline (vectors larger than L2)
     if rank == 0 and not args.no_cg_probe:
+        try:
+            line["cg_iter_long_horizon"] = cg_iter_probe(dev, flush, peak, N=307, k=6, T=288, B=256)
+        except Exception as e:
+            line["cg_iter_long_horizon"] = {"error": repr(e)[:300]}
         try:
             plan, prm = solve.plan, solve.prm
             Bc = args.cg_batch

@@ -1266,6 +1266,61 @@ static int cg4(mga_plan* p, const K4Plan& k4, int system, const float* rhs, cons
   return MGA_OK;
 }
 
+// the tail of an outer iteration with the x tile staged by TMA (k5_tail); same arguments as k2_tail
+template <int K>
+static int k5_launch(mga_plan* p, const K4Plan& k4, const K5Maps& maps, K5Args a, cudaStream_t st) {
+  constexpr int NC = 512;
+  const Graph2& g = p->g2;
+  a.nstage = 3;
+  const size_t smem = (size_t)a.nstage * ((size_t)k4.rows_tile * kCB4 * 16 + (size_t)k4.rows_tile * 16) + ((size_t)g.N + 1) * 4 +
+                      (size_t)g.N * (g.kd3 + g.ku3) * 8 + 2 * (size_t)a.nstage * 8 + (size_t)MGA_DIAG_COLS * 32 * 4 + 16;
+  if (smem > (size_t)p->max_smem_optin) { a.nstage = 2; }
+  const size_t smem2 = a.nstage == 3 ? smem : smem - ((size_t)k4.rows_tile * kCB4 * 16 + (size_t)k4.rows_tile * 16) - 16;
+  auto kern = k5_tail<K, NC>;
+  static std::mutex mu;
+  static std::map<int, size_t> limit;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    size_t& lim = limit[p->device];
+    if (smem2 > lim) {
+      MGA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
+      lim = smem2;
+    }
+  }
+  kern<<<std::min(a.total, p->sm_count), NC + 32, smem2, st>>>(maps, g, a);
+  MGA_LAUNCH_CHECK("k5_tail");
+  return MGA_OK;
+}
+
+static bool k5_ok(const mga_plan* p, const K4Plan& k4) {
+  static const bool on = [] { const char* e = std::getenv("MGA_S5"); return !e || std::atoi(e) != 0; }();
+  return on && k4.ok && p->g2.N * kCB4 <= kK5Slots * 512;
+}
+
+static int k5_tail_launch(mga_plan* p, const K4Plan& k4, int want_diag, const float* x, const float* x_old, const float* zu,
+                          const float* zu_old, const float* zd, const float* zd_old, float* gu, float* gd, float* gam, float* phi,
+                          const float* y, float rho, float rho_u, float rho_d, float thr, double* diag, double* dx_sum, int64_t B,
+                          cudaStream_t st) {
+  const Graph2& g = p->g2;
+  K5Maps maps{};
+  int rc;
+  if ((rc = k4_map(p, x, B, kCB4 * 4, k4.rows_box, &maps.x)) || (rc = k4_map(p, x, B, 4, k4.rows_box, &maps.x_halo))) return rc;
+  K5Args a{};
+  a.B = B; a.rows_box = k4.rows_box; a.nbox = k4.nbox; a.rows_tile = k4.rows_tile;
+  a.tiles = (g.C4 + kCB4 - 1) / kCB4;
+  a.total = (int)B * a.tiles;
+  a.want_diag = want_diag;
+  a.x = x; a.x_old = x_old; a.zu = zu; a.zu_old = zu_old; a.zd = zd; a.zd_old = zd_old;
+  a.gu = gu; a.gd = gd; a.gam = gam; a.phi = phi; a.y = y;
+  a.rho = rho; a.rho_u = rho_u; a.rho_d = rho_d; a.thr = thr;
+  a.diag = diag; a.dx_sum = dx_sum;
+  const int K = g.kd3 == g.ku3 ? g.kd3 : 0;
+  if (K == 4) return k5_launch<4>(p, k4, maps, a, st);
+  if (K == 6) return k5_launch<6>(p, k4, maps, a, st);
+  if (K == 8) return k5_launch<8>(p, k4, maps, a, st);
+  return k5_launch<0>(p, k4, maps, a, st);
+}
+
 // CG_solver (ADMM.py:329-368) with a fixed iteration count on internal-layout vectors; x holds x0 / the solution.
 // x0: warm start (read only); x: the solution (x0 == x: in place).  With n_cg == 0 the solution IS the warm start.
 static int cg2(mga_plan* p, int system, const mga_params* m, const float* rhs, const float* x0, float* x, int64_t B,
@@ -1491,6 +1546,7 @@ static int stream2_admm_group(mga_plan* p, const mga_params* prm, const void* y_
   const float rho = (float)prm->rho, rho_u = (float)prm->rho_u, rho_d = (float)prm->rho_d;
   const float thr = (float)(prm->mu_d1 / prm->rho);
   const size_t coef_stride = (size_t)max_cg * B_out;
+  const K4Plan k4t = k4_plan(p);
   for (int it = 0; it < n_outer; ++it) {
     auto coef = [&](void* basep, int s) -> float* {
       return basep ? static_cast<float*>(basep) + ((size_t)it * 3 + s) * coef_stride : nullptr;
@@ -1506,9 +1562,15 @@ static int stream2_admm_group(mga_plan* p, const mga_params* prm, const void* y_
     MGA_LAUNCH_CHECK("k2_rhs_z");
     if ((rc = cg2(p, MGA_SYS_ZD, prm, rhs, zd_cur, zd_nxt, B, B_out, max_cg, coef(outs->alpha, 2), coef(outs->beta, 2), w, st))) return rc;
     double* drow = want_diag ? diag + (size_t)it * MGA_DIAG_COLS : nf_row;
-    k2_tail<<<grid, blk, 0, st>>>(g, want_diag ? 1 : 0, x_nxt, x_cur, zu_nxt, zu_cur, zd_nxt, zd_cur, gu, gd, gam, phi,
-                                 y, rho, rho_u, rho_d, thr, drow, dx_sum ? dx_sum + (size_t)it * g.T * g.N : nullptr);
-    MGA_LAUNCH_CHECK("k2_tail");
+    if (k5_ok(p, k4t)) {
+      if ((rc = k5_tail_launch(p, k4t, want_diag ? 1 : 0, x_nxt, x_cur, zu_nxt, zu_cur, zd_nxt, zd_cur, gu, gd, gam, phi, y, rho, rho_u,
+                               rho_d, thr, drow, dx_sum ? dx_sum + (size_t)it * g.T * g.N : nullptr, B, st)))
+        return rc;
+    } else {
+      k2_tail<<<grid, blk, 0, st>>>(g, want_diag ? 1 : 0, x_nxt, x_cur, zu_nxt, zu_cur, zd_nxt, zd_cur, gu, gd, gam, phi,
+                                   y, rho, rho_u, rho_d, thr, drow, dx_sum ? dx_sum + (size_t)it * g.T * g.N : nullptr);
+      MGA_LAUNCH_CHECK("k2_tail");
+    }
     std::swap(x_cur, x_nxt);
     std::swap(zu_cur, zu_nxt);
     std::swap(zd_cur, zd_nxt);

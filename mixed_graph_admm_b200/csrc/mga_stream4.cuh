@@ -372,4 +372,249 @@ k4_cg(const __grid_constant__ K4Maps maps, const Graph2 g, const K4Args a) {
   if (SRC != 2 && tid == 0) tma_wait_all();          // stores complete before the grid ends
 }
 
+
+
+// ---------------------------------------------------------------------------------------------------------------------
+// k5_tail: the tail of one outer iteration (ADMM.py:595-637: both dual ascents, phi prox, gamma ascent, every
+// diagnostics sum) with the x tile staged by TMA - what k2_tail does with L1 / L2 gathers (2.4 TB/s of its 1.36 GB).
+// Only x is gathered (L_d x needs the neighbours one step back, L_u x the neighbours at the same step), so only x goes
+// through shared memory: tile {32 floats, node rows} + the chunk left of it (halo), two stages, producer warp as in
+// k4_cg.  The other nine vectors are read and the four results written straight from / to HBM by the thread that owns
+// the chunk (coalesced 128-bit accesses).  L_d is unaligned in time (x[t-1] of the neighbour): the element before a
+// chunk is the previous lane's last element of the SAME neighbour's row (the 8 lanes of a row share the table row),
+// so it comes by shuffle; only the first column reads the halo.
+// Items are dealt to the CTAs as contiguous ranges of (time tile, window) with the time tile major: a CTA stays on one
+// time tile for ~B * tiles / gridDim windows and adds up x - x_old over them in registers - one double atomic per
+// lattice point and CTA for the (T, N) batch sum instead of one per point and window.
+struct K5Maps {
+  CUtensorMap x, x_halo;
+};
+struct K5Args {
+  int64_t B;
+  int nstage, rows_box, nbox, rows_tile, tiles, total;
+  int want_diag;
+  const float *x, *x_old, *zu, *zu_old, *zd, *zd_old;
+  float *gu, *gd, *gam, *phi;
+  const float* y;
+  float rho, rho_u, rho_d, thr;
+  double* diag;
+  double* dx_sum;
+};
+
+constexpr int kK5Slots = 8;      // items per consumer thread and tile: N * 8 / NC <= 8
+
+__device__ __forceinline__ float soft5(float s, float d) {
+  const float u = fabsf(s) - d;
+  const float sg = (float)((s > 0.f) - (s < 0.f));
+  return sg * u * (float)(u > 0.f);   // ADMM.py:407-408
+}
+
+template <int K, int NC>
+__global__ void __launch_bounds__(NC + 32, 1) k5_tail(const __grid_constant__ K5Maps maps, const Graph2 g, const K5Args a) {
+  extern __shared__ __align__(128) unsigned char smem5[];
+  const int N = g.N, C4 = g.C4, T = g.T;
+  const int tid = threadIdx.x;
+  const size_t tile_f4 = (size_t)a.rows_tile * kCB4;
+  float4* tiles = reinterpret_cast<float4*>(smem5);                  // [stage][rows_tile * 8]
+  float4* hbuf = tiles + tile_f4 * a.nstage;                         // [stage][rows_tile]: the chunk left of the tile
+  float* wself = reinterpret_cast<float*>(hbuf + (size_t)a.rows_tile * a.nstage);
+  int2* tab_d = reinterpret_cast<int2*>(wself + N + (N & 1));
+  int2* tab_u = tab_d + (size_t)N * g.kd3;
+  uint64_t* full = reinterpret_cast<uint64_t*>(tab_u + (size_t)N * g.ku3);
+  uint64_t* empty = full + a.nstage;
+  float* dred = reinterpret_cast<float*>(empty + a.nstage);          // MGA_DIAG_COLS x 32
+  if (tid == 0) {
+    for (int s = 0; s < a.nstage; ++s) { mbar_init(full + s, 1); mbar_init(empty + s, NC / 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  fence_async_smem();
+  __syncthreads();
+  // contiguous range of items for this CTA; item id = time tile * B + window
+  const int per = (a.total + gridDim.x - 1) / gridDim.x;
+  const int first = blockIdx.x * per, last = min(a.total, first + per);
+  const uint32_t stage_bytes = (uint32_t)(tile_f4 * 16 + (size_t)a.rows_tile * 16);
+  if (tid >= NC) {
+    if (tid == NC) {
+      int k = 0;
+      for (int id = first; id < last; ++id, ++k) {
+        const int s = k % a.nstage, ph = (k / a.nstage) & 1;
+        const int ct = id / (int)a.B, b = id - ct * (int)a.B, c0 = ct * kCB4;
+        mbar_wait(empty + s, ph ^ 1);
+        mbar_expect_tx(full + s, stage_bytes);
+        for (int j = 0; j < a.nbox; ++j) {
+          tma_load3(tiles + (size_t)s * tile_f4 + (size_t)j * a.rows_box * kCB4, &maps.x, 4 * c0, j * a.rows_box, b, full + s);
+          tma_load3(hbuf + (size_t)s * a.rows_tile + j * a.rows_box, &maps.x_halo, 4 * c0 - 4, j * a.rows_box, b, full + s);
+        }
+      }
+    }
+    return;
+  }
+  for (int k = tid; k < N * g.kd3; k += NC) tab_d[k] = g.tab_d[k];
+  for (int k = tid; k < N * g.ku3; k += NC) tab_u[k] = g.tab_u[k];
+  for (int k = tid; k < N; k += NC) wself[k] = g.wself_d[k];
+  asm volatile("bar.sync 1, %0;" ::"n"(NC) : "memory");
+  const int lane = tid & 31, col = tid & 7;
+  float d[MGA_DIAG_COLS];
+#pragma unroll
+  for (int c = 0; c < MGA_DIAG_COLS; ++c) d[c] = 0.f;
+  float4 dxacc[kK5Slots];
+#pragma unroll
+  for (int j = 0; j < kK5Slots; ++j) dxacc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  int ct_acc = -1;
+  auto flush_dx = [&](int ct) {          // x - x_old summed over this CTA's windows of time tile ct -> the (T, N) batch sum
+    if (ct < 0 || !a.dx_sum) return;
+    const int c = ct * kCB4 + col;
+#pragma unroll
+    for (int j = 0; j < kK5Slots; ++j) {
+      const int item = tid + j * NC;
+      if (item < N * kCB4 && c < C4) {
+        const int o = g.perm[item >> 3];
+        const float v[4] = {dxacc[j].x, dxacc[j].y, dxacc[j].z, dxacc[j].w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (4 * c + q < T) atomicAdd(a.dx_sum + (size_t)(4 * c + q) * N + o, (double)v[q]);
+      }
+      dxacc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  int k = 0;
+  for (int id = first; id < last; ++id, ++k) {
+    const int s = k % a.nstage, ph = (k / a.nstage) & 1;
+    const int ct = id / (int)a.B, b = id - ct * (int)a.B, c0 = ct * kCB4;
+    if (ct != ct_acc) { flush_dx(ct_acc); ct_acc = ct; }
+    const int c = c0 + col;
+    const bool cok = c < C4;
+    const float4* tX = tiles + (size_t)s * tile_f4;
+    const float* hX = reinterpret_cast<const float*>(hbuf + (size_t)s * a.rows_tile);
+    const size_t w0 = (size_t)b * (size_t)(N * C4);
+    const int t0 = 4 * c;
+    mbar_wait(full + s, ph);
+    const char* mine = reinterpret_cast<const char*>(tX + col);
+#pragma unroll
+    for (int j = 0; j < kK5Slots; ++j) {
+      const int it0 = tid - lane + j * NC;
+      if (it0 >= N * kCB4) break;                                    // warp-uniform
+      const bool on = cok && it0 + lane < N * kCB4;
+      const int item = it0 + lane < N * kCB4 ? it0 + lane : N * kCB4 - 1;
+      const int n = item >> 3;
+      const float4 xv4 = tX[item];
+      // ---- L_d x at the chunk's four steps: x[t] - sum_j w_j x_nbr[t-1]  (ADMM.py:166-177)
+      float acc[4];
+      {
+        const float ws = wself[n];
+        const float up = __shfl_up_sync(0xffffffffu, xv4.w, 1);
+        const float prev = col > 0 ? up : hX[n * 4 + 3];
+        acc[0] = ws * prev; acc[1] = ws * xv4.x; acc[2] = ws * xv4.y; acc[3] = ws * xv4.z;
+        const int2* row = tab_d + n * g.kd3;
+        int2 e[K > 0 ? K : 1];
+        if (K > 0) {
+#pragma unroll
+          for (int q = 0; q < K; ++q) e[q] = row[q];
+#pragma unroll
+          for (int q = 0; q < K; ++q) {
+            const float wj = __int_as_float(e[q].y);
+            const float4 nb = *reinterpret_cast<const float4*>(mine + e[q].x);
+            const float nup = __shfl_up_sync(0xffffffffu, nb.w, 1);
+            const float np = col > 0 ? nup : hX[(e[q].x >> 7) * 4 + 3];
+            acc[0] += wj * np; acc[1] += wj * nb.x; acc[2] += wj * nb.y; acc[3] += wj * nb.z;
+          }
+        } else {
+          for (int q = 0; q < g.kd3; ++q) {
+            const int2 en = row[q];
+            const float wj = __int_as_float(en.y);
+            const float4 nb = *reinterpret_cast<const float4*>(mine + en.x);
+            const float nup = __shfl_up_sync(0xffffffffu, nb.w, 1);
+            const float np = col > 0 ? nup : hX[(en.x >> 7) * 4 + 3];
+            acc[0] += wj * np; acc[1] += wj * nb.x; acc[2] += wj * nb.y; acc[3] += wj * nb.z;
+          }
+        }
+      }
+      const float xv[4] = {xv4.x, xv4.y, xv4.z, xv4.w};
+      float ldx[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) ldx[q] = (t0 + q >= 1 && t0 + q < T) ? xv[q] - acc[q] : 0.f;
+      float lux[4] = {0.f, 0.f, 0.f, 0.f};
+      if (a.want_diag) {
+        const float4 au = gather3<K>(tab_u + n * g.ku3, g.ku3, mine, make_float4(0.f, 0.f, 0.f, 0.f));
+        lux[0] = xv[0] - au.x; lux[1] = xv[1] - au.y; lux[2] = xv[2] - au.z; lux[3] = xv[3] - au.w;
+      }
+      if (!on) continue;
+      // ---- the elementwise part, as k2_tail
+      const size_t gq = w0 + (size_t)n * C4 + c;
+      const float4 zu4 = ld4s(a.zu, gq), zd4 = ld4s(a.zd, gq), gu4 = ld4s(a.gu, gq), gd4 = ld4s(a.gd, gq);
+      const float4 ga4 = ld4s(a.gam, gq), ph4 = ld4s(a.phi, gq);
+      const float zuv[4] = {zu4.x, zu4.y, zu4.z, zu4.w}, zdv[4] = {zd4.x, zd4.y, zd4.z, zd4.w};
+      float guv[4] = {gu4.x, gu4.y, gu4.z, gu4.w}, gdv[4] = {gd4.x, gd4.y, gd4.z, gd4.w};
+      float gav[4] = {ga4.x, ga4.y, ga4.z, ga4.w}, phv[4] = {ph4.x, ph4.y, ph4.z, ph4.w};
+      float xo[4] = {0.f, 0.f, 0.f, 0.f}, zuo[4] = {0.f, 0.f, 0.f, 0.f}, zdo[4] = {0.f, 0.f, 0.f, 0.f};
+      if (a.want_diag) {
+        const float4 p1 = ld4s(a.x_old, gq), p2 = ld4s(a.zu_old, gq), p3 = ld4s(a.zd_old, gq);
+        xo[0] = p1.x; xo[1] = p1.y; xo[2] = p1.z; xo[3] = p1.w;
+        zuo[0] = p2.x; zuo[1] = p2.y; zuo[2] = p2.z; zuo[3] = p2.w;
+        zdo[0] = p3.x; zdo[1] = p3.y; zdo[2] = p3.z; zdo[3] = p3.w;
+      }
+      const int o = g.perm[n];
+      int bad = 0;
+      float dxv[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int t = t0 + q;
+        if (t >= T) continue;
+        guv[q] = guv[q] + a.rho_u * (xv[q] - zuv[q]);
+        gdv[q] = gdv[q] + a.rho_d * (xv[q] - zdv[q]);
+        const float ph = soft5(ldx[q] - gav[q] / a.rho, a.thr);
+        const float gn = gav[q] + a.rho * (ph - ldx[q]);
+        bad |= !isfinite(xv[q]) || !isfinite(zuv[q]) || !isfinite(zdv[q]) || !isfinite(ph) || !isfinite(gn);
+        if (a.want_diag) {
+          const float dx = xv[q] - xo[q];
+          d[MGA_DIAG_DX2] += dx * dx;
+          dxv[q] = dx;
+          const float e1 = xv[q] - zuv[q], bz = zuv[q] - zuo[q];
+          d[MGA_DIAG_X_ZU2] += e1 * e1;
+          d[MGA_DIAG_DZU2] += bz * bz;
+          d[MGA_DIAG_GLR] += xv[q] * lux[q];
+          if (t < g.t_in) {
+            const float h = xv[q] - a.y[((size_t)b * g.t_in + t) * N + o];
+            d[MGA_DIAG_RECOVER2] += h * h;
+          }
+          const float e = ph - ldx[q], f = ph - phv[q];
+          d[MGA_DIAG_PHI_LDX2] += e * e;
+          d[MGA_DIAG_DPHI2] += f * f;
+          d[MGA_DIAG_DGTV] += fabsf(ldx[q]);
+          const float e2 = xv[q] - zdv[q], f2 = zdv[q] - zdo[q];
+          d[MGA_DIAG_X_ZD2] += e2 * e2;
+          d[MGA_DIAG_DZD2] += f2 * f2;
+          d[MGA_DIAG_DGLR] += ldx[q] * ldx[q];
+        }
+        phv[q] = ph;
+        gav[q] = gn;
+      }
+      d[MGA_DIAG_NONFINITE] += (float)bad;
+      dxacc[j].x += dxv[0]; dxacc[j].y += dxv[1]; dxacc[j].z += dxv[2]; dxacc[j].w += dxv[3];
+      st4s(a.gu, gq, make_float4(guv[0], guv[1], guv[2], guv[3]));
+      st4s(a.gd, gq, make_float4(gdv[0], gdv[1], gdv[2], gdv[3]));
+      st4s(a.gam, gq, make_float4(gav[0], gav[1], gav[2], gav[3]));
+      st4s(a.phi, gq, make_float4(phv[0], phv[1], phv[2], phv[3]));
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty + s);
+  }
+  flush_dx(ct_acc);
+  // diagnostics: one double atomic per CTA and column
+  {
+    const int w = tid >> 5;
+#pragma unroll
+    for (int c = 0; c < MGA_DIAG_COLS; ++c) {
+      const float v = warp_sum<float>(d[c]);
+      if (lane == 0) dred[c * 32 + w] = v;
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(NC) : "memory");
+    if (tid < MGA_DIAG_COLS) {
+      float t = 0.f;
+      for (int q = 0; q < NC / 32; ++q) t += dred[tid * 32 + q];
+      if (t != 0.f) atomicAdd(a.diag + tid, (double)t);
+    }
+  }
+}
+
 }  // namespace mga
