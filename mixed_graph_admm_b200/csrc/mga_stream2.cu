@@ -151,26 +151,32 @@ __global__ void __launch_bounds__(kB2) k2_export(Graph2 g, const float* __restri
   }
 }
 
-// initial_guess (ADMM.py:766-781) + initial state (ADMM.py:537-544); one thread per (window, node)
+// initial_guess (ADMM.py:766-781) + initial state (ADMM.py:537-544); one WARP per (window, node): the lanes share the
+// regression sums (shuffle) and then write the node's row chunk by chunk - 512 contiguous bytes per store instruction
+// (one thread per row wrote 16 bytes every 1152: 1.6 TB/s at T = 288).  The sums run over t in the reference's order
+// per lane and are combined across lanes; float32 rounding of the regression is at the 1e-7 level either way.
 __global__ void __launch_bounds__(256) k2_init(Graph2 g, int64_t B, const float* __restrict__ y, float* __restrict__ x,
                                                float* __restrict__ zu, float* __restrict__ zd, float* __restrict__ gu,
                                                float* __restrict__ gd, float* __restrict__ gam, float t_mean, float t_var) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int64_t idx = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (idx >= B * g.N) return;
   const int64_t b = idx / g.N;
   const int n = (int)(idx - b * g.N);
   const float* yw = y + b * (int64_t)g.t_in * g.N + g.perm[n];
   float sy = 0.f, sty = 0.f;
-  for (int t = 0; t < g.t_in; ++t) {
+  for (int t = lane; t < g.t_in; t += 32) {
     const float v = yw[(size_t)t * g.N];
     sy += v;
     sty += (float)t * v;
   }
+  sy = warp_sum<float>(sy);
+  sty = warp_sum<float>(sty);
   const float my = sy / (float)g.t_in, mty = sty / (float)g.t_in;
   const float w = (mty - t_mean * my) / t_var;
   const float c = my - w * t_mean;
   const size_t row = (size_t)idx * g.C4;
-  for (int cc = 0; cc < g.C4; ++cc) {
+  for (int cc = lane; cc < g.C4; cc += 32) {
     float v[4], tenth[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -1538,7 +1544,7 @@ static int stream2_admm_group(mga_plan* p, const mga_params* prm, const void* y_
   const dim3 grid((unsigned)B, g.tilesN, g.tilesC), blk(g.CB, g.NBt);
   const size_t chunks = (size_t)B * g.N * g.C4;
   const unsigned grid_c = (unsigned)((chunks + kFlat - 1) / kFlat);
-  const unsigned grid_bn = (unsigned)((B * g.N + 255) / 256);
+  const unsigned grid_bn = (unsigned)((B * g.N * 32 + 255) / 256);      // one warp per (window, node)
   k2_init<<<grid_bn, 256, 0, st>>>(g, B, y, x_cur, zu_cur, zd_cur, gu, gd, gam, (float)t_mean, (float)t_var);
   MGA_LAUNCH_CHECK("k2_init");
   k2_ldr<<<grid, blk, 0, st>>>(g, x_cur, phi);      // phi = L_d x (ADMM.py:541)
