@@ -472,8 +472,75 @@ class ADMM_algorithm():
 
     # ------------------------------------------------------------------ the loop (ADMM.py:511-648)
     def two_loops(self, y, mask=None, differential=False):
-        raise NotImplementedError("two_loops is unfinished upstream (it returns nothing and no script calls it, "
-                                  "ADMM.py:410-508); use combined_loop")
+        '''
+        two-loops algorithm (reference ADMM.py:410-508): an outer loop over the phi / gamma update around an inner loop
+        (``max_inner_iter``) of x, z_u, z_d solves; gamma_u, gamma_d, z_u, z_d are reset at every outer iteration.
+        Input:  y in (B, t_in, N, C)   [mask mode: y and mask in (B, T, N, C)]
+        Like the reference it has no stop test, appends only the CG lists (``alpha_*``, ``beta_*``, ``CG_iter_*``) and
+        RETURNS NOTHING (upstream the method ends without a ``return``); what its locals hold at the end is left in
+        ``self.last_iterates`` (x, zu, zd, phi, gamma, gamma_u, gamma_d).  Every operator application, CG solve and prox
+        goes through the C ABI (``mga_apply``, ``mga_cg_solve``, ``mga_phi_direct``) on device tensors.
+        '''
+        if differential:
+            assert mask is None, 'differential mode does not support mask'   # (its first guess is discarded, ADMM.py:419-429)
+        assert not torch.isnan(self.d_ew).any(), 'Directed graph weights d_ew has NaN value'
+        assert not torch.isnan(self.u_ew).any(), 'Undirected graph weights u_ew has NaN value'
+        out_device = y.device
+        yd = self._in(y)
+        md = self._in(mask.to(y.dtype)) if mask is not None else None
+        x = initial_guess(yd, self.t_in, self.T) if mask is None else initial_interpolation(yd, md)
+        with_phi = self.ablation in ['None', 'DGLR']
+        with_zd = self.ablation != 'DGLR'
+        gamma = phi = None
+        if with_phi:
+            gamma = torch.ones_like(x) * 0.1
+            phi = self.apply_op_Ldr(x)
+            assert not torch.isnan(phi).any(), 'initial phi has NaN value'
+        gamma_u = gamma_d = zu = zd = None
+        for _ in range(self.max_ADMM_iter):
+            gamma_u, gamma_d = torch.ones_like(x) * 0.1, torch.ones_like(x) * 0.1
+            zu, zd = x.clone(), x.clone()
+            for i in range(self.max_inner_iter):
+                x_old, zu_old, zd_old = x, zu, zd
+                Hty = torch.zeros_like(x)
+                Hty[:, 0:yd.size(1)] = yd
+                if self.ablation == 'None':
+                    RHS_x = self.apply_op_Ldr_T(gamma + self.rho * phi) / 2 + (self.rho_u * zu + self.rho_d * zd) / 2 \
+                        - (gamma_u + gamma_d) / 2 + Hty
+                elif self.ablation == 'DGLR':
+                    RHS_x = self.apply_op_Ldr_T(gamma + self.rho * phi) / 2 + self.rho_u * zu / 2 - gamma_u / 2 + Hty
+                else:
+                    RHS_x = (self.rho_u * zu + self.rho_d * zd) / 2 - (gamma_u + gamma_d) / 2 + Hty
+                assert not torch.isnan(RHS_x).any(), f'RHS_x has NaN value in ADMM loop {i}'
+                x, CG_iter_x, alpha_x, beta_x = self.CG_solver(self.LHS_x, RHS_x, x_old, mask=md)
+                self.alpha_x.append(alpha_x)
+                self.beta_x.append(beta_x)
+                self.CG_iter_x.append(CG_iter_x)
+                assert not torch.isnan(x).any(), f'RHS_x has NaN value in loop {i}'
+                assert not torch.isinf(x).any(), f'x has inf value in loop {i}'
+                zu, CG_iter_zu, alpha_zu, beta_zu = self.CG_solver(self.LHS_zu, gamma_u / 2 + self.rho_u / 2 * x, zu_old)
+                self.alpha_zu.append(alpha_zu)
+                self.beta_zu.append(beta_zu)
+                self.CG_iter_zu.append(CG_iter_zu)
+                assert not torch.isnan(zu).any(), f'zu has NaN value in loop {i}'
+                if with_zd:
+                    zd, CG_iter_zd, alpha_zd, beta_zd = self.CG_solver(self.LHS_zd, gamma_d / 2 + self.rho_d / 2 * x, zd_old)
+                    self.alpha_zd.append(alpha_zd)
+                    self.beta_zd.append(beta_zd)
+                    self.CG_iter_zd.append(CG_iter_zd)
+                    assert not torch.isnan(zd).any(), f'zd has NaN value in loop {i}'
+                gamma_u = gamma_u + self.rho_u * (x - zu)
+                if with_zd:
+                    gamma_d = gamma_d + self.rho_d * (x - zd)
+            if with_phi:
+                phi = self.phi_direct(x, gamma)
+                assert not torch.isnan(phi).any(), "phi has NaN value"
+                gamma = gamma + self.rho * (phi - self.apply_op_Ldr(x))
+                assert not torch.isnan(gamma).any(), 'gamma has NaN'
+        its = dict(x=x, zu=zu, zd=zd, phi=phi, gamma=gamma, gamma_u=gamma_u, gamma_d=gamma_d)
+        self.last_iterates = {k: v.to(out_device) for k, v in its.items() if v is not None}
+        self.last_mode = 'two_loops'
+        return None
 
     def combined_loop(self, y, mask=None, differential=False, print_info=True):
         '''

@@ -348,3 +348,50 @@ def admm_combined(g: OracleGraph, prm: OracleParams, y, mask=None, max_admm_iter
             break
     tr.x, tr.zu, tr.zd, tr.phi, tr.gamma, tr.gamma_u, tr.gamma_d = x, zu, zd, phi, gamma, gu, gd
     return tr
+
+
+def two_loops(g: OracleGraph, prm: OracleParams, y, mask=None, max_admm_iter=150, max_inner_iter=100, max_cg_iter=100,
+              cg_tol=1e-8) -> OracleTrace:
+    """``two_loops`` (ADMM.py:410-508): an outer loop over the phi / gamma update around an inner loop of x, z_u, z_d
+    solves whose duals gamma_u, gamma_d and splits z_u, z_d are RESET at every outer iteration (ADMM.py:446-447).
+    The reference has no stop test and no residual lists here and returns nothing (the method ends without a
+    ``return``); the trace keeps what its locals hold at the end and the CG lists it appends."""
+    tr = OracleTrace()
+    x = first_guess(y, prm.t_in, prm.T) if mask is None else first_interpolation(y, mask)
+    with_phi = prm.ablation in ('None', 'DGLR')
+    with_zd = prm.ablation != 'DGLR'
+    gamma = phi = None
+    if with_phi:
+        gamma = torch.ones_like(x) * 0.1
+        phi = op_ldr(g, x)
+    gu = gd = zu = zd = None
+    for _ in range(max_admm_iter):
+        gu, gd = torch.ones_like(x) * 0.1, torch.ones_like(x) * 0.1
+        zu, zd = x.clone(), x.clone()
+        for _ in range(max_inner_iter):
+            x_old, zu_old, zd_old = x, zu, zd
+            hty = torch.zeros_like(x)
+            hty[:, 0:y.size(1)] = y
+            if prm.ablation == 'None':
+                rhs = op_ldr_t(g, gamma + prm.rho * phi) / 2 + (prm.rho_u * zu + prm.rho_d * zd) / 2 - (gu + gd) / 2 + hty
+            elif prm.ablation == 'DGLR':
+                rhs = op_ldr_t(g, gamma + prm.rho * phi) / 2 + prm.rho_u * zu / 2 - gu / 2 + hty
+            else:
+                rhs = (prm.rho_u * zu + prm.rho_d * zd) / 2 - (gu + gd) / 2 + hty
+            x, it, al, be = cg(lambda v, mask=None: lhs_x(g, prm, v, mask), rhs, x_old, max_iter=max_cg_iter, tol=cg_tol,
+                               first_kwargs={"mask": mask})
+            tr.cg_iter_x.append(it); tr.alpha_x.append(al); tr.beta_x.append(be)
+            zu, it, al, be = cg(lambda v: lhs_zu(g, prm, v), gu / 2 + prm.rho_u / 2 * x, zu_old, max_iter=max_cg_iter, tol=cg_tol)
+            tr.cg_iter_zu.append(it); tr.alpha_zu.append(al); tr.beta_zu.append(be)
+            if with_zd:
+                zd, it, al, be = cg(lambda v: lhs_zd(g, prm, v), gd / 2 + prm.rho_d / 2 * x, zd_old, max_iter=max_cg_iter,
+                                    tol=cg_tol)
+                tr.cg_iter_zd.append(it); tr.alpha_zd.append(al); tr.beta_zd.append(be)
+            gu = gu + prm.rho_u * (x - zu)
+            if with_zd:
+                gd = gd + prm.rho_d * (x - zd)
+        if with_phi:
+            phi = soft_phi(g, prm, x, gamma)
+            gamma = gamma + prm.rho * (phi - op_ldr(g, x))
+    tr.x, tr.zu, tr.zd, tr.phi, tr.gamma, tr.gamma_u, tr.gamma_d = x, zu, zd, phi, gamma, gu, gd
+    return tr

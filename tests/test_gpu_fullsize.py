@@ -276,3 +276,28 @@ def test_cluster_mode_notebook_call_is_one_launch():
     assert blk.CG_iter_x == g.z["cg_iter_x"].tolist() and blk.CG_iter_zu == g.z["cg_iter_zu"].tolist()
     assert blk.CG_iter_zd == g.z["cg_iter_zd"].tolist()
     assert rel_err(x, g.t("x")) <= 1e-11
+
+
+@pytest.mark.parametrize("name", ["two_loops_f32", "two_loops_f64"])
+def test_two_loops_matches_reference(name):
+    """``two_loops`` (ADMM.py:410-508): returns nothing like the reference, appends only the CG lists, and
+    leaves in ``last_iterates`` what the reference's locals hold at the end (fixture captured from the live reference)."""
+    from test_gpu_parity import DUAL_TOL, TOL
+    g = Golden(name)
+    blk = solver_from_golden(g)
+    assert blk.two_loops(g.y) is None
+    n_solves = g.limits["max_ADMM_iter"] * g.limits["max_inner_iter"]
+    assert blk.CG_iter_x == g.z["cg_iter_x"].tolist() and len(blk.CG_iter_zu) == n_solves and len(blk.CG_iter_zd) == n_solves
+    assert len(blk.alpha_x) == n_solves and isinstance(blk.alpha_x[0], list) and len(blk.alpha_x[0]) == g.limits["max_CG_iter"]
+    assert blk.p_res_list == [] and blk.x_shift_list == [] and blk.GLR_list == []       # no residual lists in two_loops
+    its = blk.last_iterates
+    for k in ("x", "zu", "zd"):
+        assert not its[k].is_cuda and rel_err(its[k], g.t(k)) <= TOL[g.dtype], (k, rel_err(its[k], g.t(k)))
+    for k in ("gamma", "gamma_u", "gamma_d"):
+        assert rel_err(its[k], g.t(k)) <= DUAL_TOL[g.dtype], (k, rel_err(its[k], g.t(k)))
+    og, _ = oracle_from_golden(g)
+    from oracle import admm_oracle as O
+    ldx = O.op_ldr(og, g.t("x")).double().norm().item()
+    assert (its["phi"].double() - g.t("phi").double()).norm().item() <= TOL[g.dtype] * max(g.t("phi").double().norm().item(), ldx)
+    a0 = torch.stack(list(blk.alpha_x[0])).cpu()[:2].double().numpy()
+    np.testing.assert_allclose(a0, g.z["alpha_x"][0, :2], rtol=1e-4 if g.dtype == torch.float32 else 1e-9)

@@ -130,3 +130,19 @@ def test_oracle_equals_live_reference(name):
         if k in ref:
             assert torch.equal(getattr(tr, k), ref[k]), k
     assert tr.cg_iter_x == ref["blk"].CG_iter_x
+
+
+@pytest.mark.parametrize("name", ["two_loops_f32", "two_loops_f64"])
+def test_two_loops_oracle_equals_reference_fixture(name):
+    """``two_loops`` (ADMM.py:410-508): the oracle restatement is bit-identical to what the live reference left in
+    its locals (fixture from tests/golden/make_golden_two_loops.py); the reference appends no residual lists there."""
+    from _cases import Golden, oracle_from_golden
+    from oracle import admm_oracle as O
+    g = Golden(name)
+    og, prm = oracle_from_golden(g)
+    tr = O.two_loops(og, prm, g.y, max_admm_iter=g.limits["max_ADMM_iter"], max_inner_iter=g.limits["max_inner_iter"],
+                     max_cg_iter=g.limits["max_CG_iter"], cg_tol=g.limits["CG_tol"])
+    for k in ("x", "zu", "zd", "phi", "gamma", "gamma_u", "gamma_d"):
+        assert torch.equal(getattr(tr, k), g.t(k)), k
+    assert tr.cg_iter_x == g.z["cg_iter_x"].tolist() and len(tr.cg_iter_zd) == len(tr.cg_iter_x)
+    assert g.z["n_lists"].tolist() == [0, 0, 0]
