@@ -97,6 +97,7 @@ struct HostPipe {
   int* host_done;      // device alias of the mapped host array
   int* abort_flag;
   int chunk, epoch;
+  int chunk_up;        // windows per upload chunk (a multiple of `chunk`)
 };
 
 }  // namespace mga

@@ -828,6 +828,10 @@ static int solve_host_pipelined(mga_plan* p, const mga_params* prm, const char* 
     ck = std::min(ck, nbs);
     if ((nbs + ck - 1) / ck > mga_plan::kPipeChunks) ck = (nbs + mga_plan::kPipeChunks - 1) / mga_plan::kPipeChunks;
     const int nchunk = (int)((nbs + ck - 1) / ck);
+    // uploads in fewer, larger pieces than downloads (every piece is two API calls ahead of the launch): 8 for small batches
+    int64_t ck_up = ck;
+    if (nbs <= 4096) ck_up = std::max<int64_t>(ck, (((nbs + 7) / 8 + ck - 1) / ck) * ck);
+    const int nup = (int)((nbs + ck_up - 1) / ck_up);
     const int epoch = (p->pipe_epoch = p->pipe_epoch >= (1 << 30) ? 1 : p->pipe_epoch + 1);
     int* host_done = p->pipe_host;
     int* host_word = p->pipe_host + mga_plan::kPipeChunks;      // source of the "ready" copies
@@ -838,29 +842,32 @@ static int solve_host_pipelined(mga_plan* p, const mga_params* prm, const char* 
     pipe.abort_flag = p->pipe_dev + 2 * mga_plan::kPipeChunks;
     pipe.host_done = p->pipe_host_dev;
     pipe.chunk = (int)ck;
+    pipe.chunk_up = (int)ck_up;
     pipe.epoch = epoch;
     if (want_coef) {
       outs.alpha = base + off_a;
       outs.beta = base + off_b;
     }
     auto upload = [&](int c) -> int {
-      const int64_t b0 = (int64_t)c * ck, nb = std::min(ck, nbs - b0);
+      const int64_t b0 = (int64_t)c * ck_up, nb = std::min(ck_up, nbs - b0);
       MGA_CUDA(cudaMemcpyAsync(dy + (size_t)b0 * y_win, y_host + (size_t)(s0 + b0) * y_win, (size_t)nb * y_win,
                                cudaMemcpyHostToDevice, s_up));
       MGA_CUDA(cudaMemcpyAsync(const_cast<int*>(pipe.ready) + c, host_word + c, sizeof(int), cudaMemcpyHostToDevice, s_up));
       return MGA_OK;
     };
     MGA_CUDA(cudaMemsetAsync(pipe.done, 0, (mga_plan::kPipeChunks + 8) * sizeof(int), s_run));     // counters + abort flag
-    if ((rc = upload(0))) return rc;
+    // Every upload is queued BEFORE the launch: the kernel waits for data, so nothing it waits for may depend on a host
+    // action that follows the launch call - under a profiler or CUDA_LAUNCH_BLOCKING the launch call only returns when the
+    // kernel is over (measured under ncu with the uploads queued after the launch: every CTA ran into the 4 s give-up).
+    for (int c = 0; c < nup; ++c)
+      if ((rc = upload(c))) { cudaDeviceSynchronize(); return rc; }
+    t_uploads = us();
     p->pipe = &pipe;
     rc = mga_admm_solve(p, prm, dy, y_rows, nullptr, dx, nbs, MGA_F32, n_outer, max_cg, -1.0, -1.0, t_mean, t_var,
                         want_diag | 2, &outs, mode, s_run);
     p->pipe = nullptr;
     if (rc) { cudaDeviceSynchronize(); return rc; }
     t_launch = us();
-    for (int c = 1; c < nchunk; ++c)
-      if ((rc = upload(c))) { cudaDeviceSynchronize(); return rc; }
-    t_uploads = us();
     // hand finished chunks to the download stream as the kernel reports them
     bool kernel_over = false;
     for (int c = 0; c < nchunk; ++c) {
@@ -908,8 +915,8 @@ static int solve_host_pipelined(mga_plan* p, const mga_params* prm, const char* 
   }
   MGA_CUDA(cudaStreamSynchronize(s_dn));
   if (trace)
-    std::fprintf(stderr, "[mga] host entry (us): launched %.0f, uploads queued %.0f, first chunk done %.0f, last chunk done %.0f, "
-                 "kernel over %.0f, all copies back %.0f\n", t_launch, t_uploads, t_first, t_last, t_run, us());
+    std::fprintf(stderr, "[mga] host entry (us): uploads queued %.0f, launched %.0f, first chunk done %.0f, last chunk done %.0f, "
+                 "kernel over %.0f, all copies back %.0f\n", t_uploads, t_launch, t_first, t_last, t_run, us());
   return MGA_OK;
 }
 

@@ -129,7 +129,7 @@ int resident_admm(mga_plan* p, const mga_params* m, const void* y, const void* m
   a.t_mean = (float)t_mean; a.t_var = (float)t_var;
   if (p->pipe) {
     a.ready = p->pipe->ready; a.done = p->pipe->done; a.host_done = p->pipe->host_done; a.abort_flag = p->pipe->abort_flag;
-    a.chunk = p->pipe->chunk; a.epoch = p->pipe->epoch;
+    a.chunk = p->pipe->chunk; a.chunk_up = p->pipe->chunk_up; a.epoch = p->pipe->epoch;
   }
   if (a.want_diag && !(diag_flags & 2)) {
     if (a.diag) MGA_CUDA(cudaMemsetAsync(a.diag, 0, (size_t)n_outer * MGA_DIAG_COLS * sizeof(double), st));

@@ -96,6 +96,7 @@ struct ResArgs {
   int* host_done;             // mapped pinned host memory: host_done[c] = epoch when every x of the chunk is in device memory
   int* abort_flag;            // device: set when a CTA gave up waiting (upload never arrived); the host reports an error
   int chunk, epoch;
+  int chunk_up;               // windows per UPLOAD chunk (ready flags); `chunk` is the download granularity (done counters)
 };
 
 template <bool CG>
@@ -705,7 +706,7 @@ __global__ void __launch_bounds__(MAXT, MINB) k_admm_resident(const ResArgs a) {
     if (PIPE) {
       // the host entry point uploads the batch chunk by chunk while this kernel runs: wait for this window's chunk.
       // y is then read with ld.global.cg (below): a 128-byte L1 line may straddle two windows of different chunks.
-      if (threadIdx.x == 0 && pipe_acquire(a.ready, a.chunk, a.epoch, b, a.abort_flag)) s_abort = 1;
+      if (threadIdx.x == 0 && pipe_acquire(a.ready, a.chunk_up, a.epoch, b, a.abort_flag)) s_abort = 1;
       __syncthreads();
       if (s_abort) return;
     }

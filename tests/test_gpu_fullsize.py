@@ -301,3 +301,22 @@ def test_two_loops_matches_reference(name):
     assert (its["phi"].double() - g.t("phi").double()).norm().item() <= TOL[g.dtype] * max(g.t("phi").double().norm().item(), ldx)
     a0 = torch.stack(list(blk.alpha_x[0])).cpu()[:2].double().numpy()
     np.testing.assert_allclose(a0, g.z["alpha_x"][0, :2], rtol=1e-4 if g.dtype == torch.float32 else 1e-9)
+
+
+def test_host_entry_survives_blocking_launches():
+    """The pipelined host launch waits for its uploads on the device, so every upload must be queued before the launch call:
+    with CUDA_LAUNCH_BLOCKING=1 (or under a profiler that serialises launches) the launch call only returns when the
+    kernel is over.  Run the host entry that way in a fresh process; it must finish and agree with the device entry."""
+    import subprocess
+    code = (
+        "import sys, time, torch; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "from test_gpu_parity import _pems04\n"
+        "blk, y = _pems04(600, seed=9)\n"
+        "t0 = time.time(); xh = blk.combined_loop(y.pin_memory(), print_info=False); dt = time.time() - t0\n"
+        "xd = blk.combined_loop(y.cuda(), print_info=False).cpu()\n"
+        "assert blk.last_mode == 'device' and torch.equal(xh, xd), 'host entry differs'\n"
+        "assert dt < 3.0, dt\n"
+        "print('ok', dt)\n") % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, CUDA_LAUNCH_BLOCKING="1")
+    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 0 and "ok" in out.stdout, out.stderr[-2000:]
