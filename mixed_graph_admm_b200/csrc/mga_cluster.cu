@@ -43,6 +43,7 @@ struct ClArgs {
   const int* csr_ptr; const int* csr_src; const float* csr_w;
   const int* perm;         // perm[internal node] = caller's node (tables in reverse-Cuthill-McKee order), or NULL
   const S* y; S* x_out;
+  const S* mask;           // mask / interpolation mode (ADMM.py:373-376, 783-811): (B, T, N); y then has T rows
   S* out[6];               // zu, zd, phi, gamma, gamma_u, gamma_d (optional)
   double* diag; double* dx_sum;
   S* alpha; S* beta;       // (n_outer, 3, max_cg, B) or NULL
@@ -227,8 +228,10 @@ struct ClCtx {
   // A = D + c L_d^T L_d, so <v, A v> = sum D v^2 + c ||L_d v||^2: every term is known once q = L_d v is, and the partial
   // sums ride on the cluster barrier that publishes q - one barrier fewer per CG iteration (the same value up to
   // rounding; the resident float32 kernel does the same).
+  // mk != nullptr: H = the caller's elementwise mask (values of this thread's steps) instead of "rows t < t_in" - the
+  // reference passes the mask to the FIRST residual of the x solve only (quirk Q4, ADMM.py:344-349)
   template <int SYS, bool DOT>
-  __device__ __forceinline__ void apply(const S (&v)[RPT], S (&out)[RPT], S a, S c, S& dot) {
+  __device__ __forceinline__ void apply(const S (&v)[RPT], S (&out)[RPT], S a, S c, S& dot, const S* mk = nullptr) {
     publish_p(v);
     if (SYS == MGA_SYS_ZU) {
       lu(v, out);
@@ -260,7 +263,7 @@ struct ClCtx {
 #pragma unroll
     for (int m = 0; m < RPT; ++m) {
       if (SYS == MGA_SYS_X) {
-        const S hx = (t0 + l0 + m < t_in) ? v[m] : (S)0;                                // H^T H (ADMM.py:372-374)
+        const S hx = mk ? v[m] * mk[m] : ((t0 + l0 + m < t_in) ? v[m] : (S)0);          // H^T H (ADMM.py:372-376)
         out[m] = (hx + a * v[m]) + c * out[m];                                          // ADMM.py:379
       } else {
         out[m] = c * out[m] + a * v[m];                                                 // ADMM.py:394
@@ -274,10 +277,10 @@ struct ClCtx {
   // (tol > 0 and reached) or -1.  alpha_out / beta_out: this window's column of the (max_cg, B) arrays or NULL.
   template <int SYS>
   __device__ __forceinline__ int cg_solve(S (&x)[RPT], S (&r)[RPT], S a, S c, int max_cg, double tol, S* alpha_out, S* beta_out,
-                                          int64_t B) {
+                                          int64_t B, const S* mask0 = nullptr) {
     S p[RPT], ap[RPT];
     S pap = 0;
-    apply<SYS, false>(x, ap, a, c, pap);
+    apply<SYS, false>(x, ap, a, c, pap, mask0);
     S loc = 0;
 #pragma unroll
     for (int l = 0; l < RPT; ++l) {
@@ -356,26 +359,44 @@ __global__ void __launch_bounds__(MAXT, 1) k_admm_cluster(const ClArgs<S> a) {
   // the tables come in reverse-Cuthill-McKee order: the 32 nodes of a warp gather from a few neighbouring rows (fewer
   // shared-memory bank conflicts than with the caller's numbering); global memory keeps the caller's order
   const int orig = active ? (a.perm ? a.perm[i] : i) : 0;
-  const S* yw = a.y + (size_t)b * t_in * N + orig;
+  const bool maskm = a.mask != nullptr;
+  const int y_rows = maskm ? T : t_in;
+  const S* yw = a.y + (size_t)b * y_rows * N + orig;
+  const S* mw = maskm ? a.mask + (size_t)b * T * N + orig : nullptr;
 
   // ---- initial_guess (ADMM.py:766-781) and initial state (ADMM.py:537-544)
   {
-    S sy = 0, sty = 0;
-    if (active)
-      for (int t = 0; t < t_in; ++t) {
-        const S v = yw[(size_t)t * N];
-        sy += v;
-        sty += (S)(float)t * v;
+    S w, cc;
+    if (maskm) {                                                     // initial_interpolation (ADMM.py:783-811)
+      S cnt = 0, st_ = 0, sy = 0, sty = 0, st2 = 0;
+      for (int t = 0; t < T; ++t) {
+        const S m = active ? mw[(size_t)t * N] : (S)1, v = active ? yw[(size_t)t * N] : (S)0, tt = (S)(float)t;
+        cnt += m; st_ += tt * m; sy += v * m; sty += tt * v * m; st2 += tt * tt * m;
       }
-    const S my = sy / (S)t_in, mty = sty / (S)t_in;
-    const S w = (mty - (S)a.t_mean * my) / (S)a.t_var;
-    const S cc = my - w * (S)a.t_mean;
+      const S tm = st_ / cnt, ym = sy / cnt, tym = sty / cnt, t2m = st2 / cnt;
+      w = (tym - tm * ym) / (t2m - tm * tm);
+      cc = ym - w * tm;
+    } else {
+      S sy = 0, sty = 0;
+      if (active)
+        for (int t = 0; t < t_in; ++t) {
+          const S v = yw[(size_t)t * N];
+          sy += v;
+          sty += (S)(float)t * v;
+        }
+      const S my = sy / (S)t_in, mty = sty / (S)t_in;
+      w = (mty - (S)a.t_mean * my) / (S)a.t_var;
+      cc = my - w * (S)a.t_mean;
+    }
     S x[RPT], q[RPT];
 #pragma unroll
     for (int l = 0; l < RPT; ++l) {
       const int t = t0 + l;
       S v = 0;
-      if (active && t < T) v = t < t_in ? yw[(size_t)t * N] : w * (S)(float)t + cc;
+      if (active && t < T) {
+        if (maskm) v = (w * (S)(float)t + cc) * ((S)1 - mw[(size_t)t * N]) + yw[(size_t)t * N];
+        else v = t < t_in ? yw[(size_t)t * N] : w * (S)(float)t + cc;
+      }
       x[l] = v;
       const S tenth = (active && t < T) ? (S)0.1 : (S)0;
       st(CS_X, l) = v; st(CS_ZU, l) = v; st(CS_ZD, l) = v;
@@ -409,7 +430,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_admm_cluster(const ClArgs<S> a) {
         const int t = t0 + l;
         S o = 0;
         if (active && t < T) {
-          const S hty = t < t_in ? yw[(size_t)t * N] : (S)0;
+          const S hty = t < y_rows ? yw[(size_t)t * N] : (S)0;
           o = lt[l] / (S)2 + (a.rho_u * st(CS_ZU, l) + a.rho_d * st(CS_ZD, l)) / (S)2 - (st(CS_GU, l) + st(CS_GD, l)) / (S)2 + hty;
         }
         r[l] = o;
@@ -417,7 +438,12 @@ __global__ void __launch_bounds__(MAXT, 1) k_admm_cluster(const ClArgs<S> a) {
       }
     }
     // ---- x solve (ADMM.py:571), warm start x_old
-    iters[0] = c.template cg_solve<MGA_SYS_X>(x, r, a.ax, a.cx, a.max_cg, a.cg_tol, al, be, a.B);
+    {
+      S m0[RPT];
+#pragma unroll
+      for (int l = 0; l < RPT; ++l) m0[l] = (maskm && active && t0 + l < T) ? mw[(size_t)(t0 + l) * N] : (S)0;
+      iters[0] = c.template cg_solve<MGA_SYS_X>(x, r, a.ax, a.cx, a.max_cg, a.cg_tol, al, be, a.B, maskm ? m0 : nullptr);
+    }
 #pragma unroll
     for (int l = 0; l < RPT; ++l) {
       const int t = t0 + l;
@@ -489,7 +515,10 @@ __global__ void __launch_bounds__(MAXT, 1) k_admm_cluster(const ClArgs<S> a) {
           d[MGA_DIAG_DGLR] += q * q;
           if (a.want_diag) {
             d[MGA_DIAG_GLR] += x[l] * lux[l];
-            if (t < t_in) {
+            if (maskm) {                                           // ||x * mask - y|| (ADMM.py:620-621)
+              const S h = x[l] * mw[(size_t)t * N] - yw[(size_t)t * N];
+              d[MGA_DIAG_RECOVER2] += h * h;
+            } else if (t < t_in) {
               const S h = x[l] - yw[(size_t)t * N];
               d[MGA_DIAG_RECOVER2] += h * h;
             }
@@ -599,7 +628,7 @@ static int cl_launch(mga_plan* p, const ClArgs<S>& a, const ClGeom& q, cudaStrea
 }
 
 template <typename S>
-static int cl_admm(mga_plan* p, const mga_params* m, const void* y, void* x_out, int64_t B, int n_outer, int max_cg, double cg_tol,
+static int cl_admm(mga_plan* p, const mga_params* m, const void* y, const void* mask, void* x_out, int64_t B, int n_outer, int max_cg, double cg_tol,
                    double admm_tol, double t_mean, double t_var, int diag_flags, const mga_admm_outputs* outs, cudaStream_t st) {
   const GraphDev& g = p->g;
   ClGeom q;
@@ -617,6 +646,7 @@ static int cl_admm(mga_plan* p, const mga_params* m, const void* y, void* x_out,
     a.csr_ptr = g2.in_ptr; a.csr_src = g2.in_src; a.csr_w = g2.in_w; a.perm = g2.perm;
   }
   a.y = static_cast<const S*>(y); a.x_out = static_cast<S*>(x_out);
+  a.mask = static_cast<const S*>(mask);
   a.out[0] = static_cast<S*>(outs->zu); a.out[1] = static_cast<S*>(outs->zd); a.out[2] = static_cast<S*>(outs->phi);
   a.out[3] = static_cast<S*>(outs->gamma); a.out[4] = static_cast<S*>(outs->gamma_u); a.out[5] = static_cast<S*>(outs->gamma_d);
   a.alpha = static_cast<S*>(outs->alpha); a.beta = static_cast<S*>(outs->beta);
@@ -670,12 +700,12 @@ static int cl_admm(mga_plan* p, const mga_params* m, const void* y, void* x_out,
   return MGA_OK;
 }
 
-int cluster_admm(mga_plan* p, const mga_params* m, const void* y, void* x_out, int64_t B, int dtype, int n_outer, int max_cg,
+int cluster_admm(mga_plan* p, const mga_params* m, const void* y, const void* mask, void* x_out, int64_t B, int dtype, int n_outer, int max_cg,
                  double cg_tol, double admm_tol, double t_mean, double t_var, int diag_flags, const mga_admm_outputs* outs,
                  cudaStream_t st) {
   if (dtype == MGA_F64)
-    return cl_admm<double>(p, m, y, x_out, B, n_outer, max_cg, cg_tol, admm_tol, t_mean, t_var, diag_flags, outs, st);
-  return cl_admm<float>(p, m, y, x_out, B, n_outer, max_cg, cg_tol, admm_tol, t_mean, t_var, diag_flags, outs, st);
+    return cl_admm<double>(p, m, y, mask, x_out, B, n_outer, max_cg, cg_tol, admm_tol, t_mean, t_var, diag_flags, outs, st);
+  return cl_admm<float>(p, m, y, mask, x_out, B, n_outer, max_cg, cg_tol, admm_tol, t_mean, t_var, diag_flags, outs, st);
 }
 
 }  // namespace mga

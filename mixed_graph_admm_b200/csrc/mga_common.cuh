@@ -215,7 +215,7 @@ int stream2_admm(mga_plan*, const mga_params*, const void* y, void* x_out, int64
                  double t_var, int want_diag, const mga_admm_outputs* outs, cudaStream_t st);
 // cluster mode (mga_cluster.cu): one thread-block cluster per window, any dtype, stop tests on the device (B = 1)
 bool cluster_eligible(const mga_plan*, int dtype);
-int cluster_admm(mga_plan*, const mga_params*, const void* y, void* x_out, int64_t B, int dtype, int n_outer, int max_cg,
+int cluster_admm(mga_plan*, const mga_params*, const void* y, const void* mask, void* x_out, int64_t B, int dtype, int n_outer, int max_cg,
                  double cg_tol, double admm_tol, double t_mean, double t_var, int want_diag, const mga_admm_outputs* outs,
                  cudaStream_t st);
 // resident mode (mga_resident.cu)

@@ -727,9 +727,9 @@ int mga_admm_solve(mga_plan* p, const mga_params* prm, const void* y, int y_rows
   // thread-block cluster per window, the stop tests decided on the device (MGA_CLUSTER=0: the general kernels instead)
   {
     static const bool cluster_on = [] { const char* e = std::getenv("MGA_CLUSTER"); return !e || std::atoi(e) != 0; }();
-    if (cluster_on && mode != MGA_MODE_STREAMING && mode != MGA_MODE_STREAMING_POINT && forecast && prm->ablation == MGA_ABL_NONE &&
+    if (cluster_on && mode != MGA_MODE_STREAMING && mode != MGA_MODE_STREAMING_POINT && prm->ablation == MGA_ABL_NONE &&
         (fixed ? dtype == MGA_F64 : B == 1) && cluster_eligible(p, dtype))
-      return cluster_admm(p, prm, y, x_out, B, dtype, n_outer, max_cg, cg_tol, admm_tol, t_mean, t_var, want_diag, outs,
+      return cluster_admm(p, prm, y, mask, x_out, B, dtype, n_outer, max_cg, cg_tol, admm_tol, t_mean, t_var, want_diag, outs,
                           (cudaStream_t)stream);
   }
   if (mode != MGA_MODE_STREAMING_POINT && forecast && fixed && prm->ablation == MGA_ABL_NONE && stream2_eligible(p, dtype))
@@ -752,7 +752,7 @@ int mga_cluster_solve(mga_plan* p, const mga_params* prm, const void* y, void* x
   }
   mga_admm_outputs none{};
   if (!outs) outs = &none;
-  return cluster_admm(p, prm, y, x_out, B, dtype, n_outer, max_cg, cg_tol, admm_tol, t_mean, t_var, want_diag, outs,
+  return cluster_admm(p, prm, y, nullptr, x_out, B, dtype, n_outer, max_cg, cg_tol, admm_tol, t_mean, t_var, want_diag, outs,
                       (cudaStream_t)stream);
 }
 

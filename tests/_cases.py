@@ -12,9 +12,9 @@ import torch
 GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 FIXED_CASES = ["anchor5", "tiny_f32", "tiny_f64", "tiny_prox", "tiny_noexpand", "tiny_physical", "tiny_line1", "tiny_line2",
-               "tiny_reinit", "tiny_abl_dgtv", "tiny_mask", "tiny_c2", "tiny_c2_f64", "tiny_c3_line2", "tiny_c3_physical", "tiny_c2_mask",
+               "tiny_reinit", "tiny_abl_dgtv", "tiny_mask", "tiny_mask_f64", "tiny_c2", "tiny_c2_f64", "tiny_c3_line2", "tiny_c3_physical", "tiny_c2_mask",
                "pems08_f32", "pems04_f32"]
-TOL_CASES = ["tiny_tol", "tiny_tol_f64", "tiny_c2_tol", "pems08_tol", "pems04_tol", "pems04_t24_tol_f64"]
+TOL_CASES = ["tiny_tol", "tiny_tol_f64", "tiny_c2_tol", "pems08_tol", "pems04_tol", "pems04_t24_tol_f64", "tiny_mask_tol_f64"]
 ALL_CASES = FIXED_CASES + TOL_CASES
 ITERATES = ("x", "zu", "zd", "phi", "gamma", "gamma_u", "gamma_d")
 

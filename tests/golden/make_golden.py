@@ -148,6 +148,10 @@ def main():
     mask[:, 0] = 1
     mask[:, -1] = 1
     make_case("tiny_mask", gi, ai, ym * mask, ctor, fixed(2, 4), mask=mask)
+    # 9a. the notebooks' interpolation call: float64, tolerance mode (B = 1), and float64 with fixed counts
+    ym64 = synth.signals(1, T, N, seed=9, dtype=torch.float64, smooth=True)
+    make_case("tiny_mask_tol_f64", gi, ai, ym64 * mask.double(), ctor, {"max_ADMM_iter": 5}, mask=mask.double())
+    make_case("tiny_mask_f64", gi, ai, ym64 * mask.double(), ctor, fixed(3, 5), mask=mask.double())
     # 9b. multi-channel signals (row N4): C = 2 on the kNN graph, C = 3 on the banded line graph and on the
     # physical adjacency; same weights on every channel, dot products over (T, N, C)
     yc = lambda C, seed, dt=torch.float32: torch.rand(B, t_in, N, C, generator=torch.Generator().manual_seed(seed),  # noqa: E731

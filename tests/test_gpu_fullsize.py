@@ -226,7 +226,7 @@ def test_nccl_two_rank_sharded_solve_equals_unsharded():
 
 
 # ---- cluster mode: one thread-block cluster per window, the signal's own precision, stop tests on the device
-@pytest.mark.parametrize("name", ["tiny_f64", "tiny_c2_f64", "tiny_f32", "tiny_prox", "tiny_physical", "tiny_line1", "pems08_f32"])
+@pytest.mark.parametrize("name", ["tiny_f64", "tiny_c2_f64", "tiny_mask_f64", "tiny_f32", "tiny_prox", "tiny_physical", "tiny_line1", "pems08_f32"])
 def test_cluster_mode_fixed_iterations_match_reference(name):
     """Fixed iteration counts through the cluster kernel (float64 takes it by default; float32 goldens are sent there by
     asking for tolerance -1 with a batch the kernel also serves): every iterate and list against the golden."""
@@ -239,7 +239,7 @@ def test_cluster_mode_fixed_iterations_match_reference(name):
     y = g.y.cuda()
     if g.dtype == torch.float64:
         l0 = L.mga_launch_count()
-        x = blk.combined_loop(y, print_info=False).cpu()
+        x = blk.combined_loop(y, mask=None if g.mask is None else g.mask.cuda(), print_info=False).cpu()
         assert L.mga_launch_count() - l0 == 1, "float64 with fixed counts is one cluster launch"
     else:
         # float32 + fixed counts belongs to the resident kernel; reach the cluster kernel through the C ABI

@@ -133,7 +133,7 @@ def test_tolerance_mode_cg_counts_equal(name):
     g = Golden(name)
     blk = solver_from_golden(g)
     blk.keep_iterates = True
-    x = blk.combined_loop(g.y, print_info=False)
+    x = blk.combined_loop(g.y, mask=g.mask, print_info=False)
     assert blk.CG_iter_x == g.z["cg_iter_x"].tolist()
     assert blk.CG_iter_zu == g.z["cg_iter_zu"].tolist()
     assert blk.CG_iter_zd == g.z["cg_iter_zd"].tolist()
