@@ -204,9 +204,10 @@ int mga_admm_solve(mga_plan* plan, const mga_params* prm, const void* y, int y_r
  * exchanged through distributed shared memory), in the signal's own precision, with the reference's stop tests
  * (ADMM.py:360, 645) decided on the device - one launch for a whole tolerance-driven solve.  mga_admm_solve(MODE_AUTO)
  * picks it for tolerance mode at B = 1 (the reference's own call pattern: float64, CG_tol 1e-8, ADMM_tol 1e-6,
- * ADMM.py:76-80) and for float64 batches with fixed counts; this entry point runs it on request.  Forecasting mode,
- * ablation None, time-invariant weights, T <= 32, N <= 1024; cg_tol / admm_tol > 0 need B = 1 (for B > 1 the
- * reference's tests are batch-global).  Arguments as mga_admm_solve. */
+ * ADMM.py:76-80), for float64 batches with fixed counts and for plans with per-time-step weight tables (T,N,k) /
+ * (T-1,N,K); this entry point runs it on request.  Forecasting or mask mode (pass the mask through mga_admm_solve),
+ * ablation None, T <= 32, N <= 1024; cg_tol / admm_tol > 0 need B = 1 (for B > 1 the reference's tests are
+ * batch-global).  Arguments as mga_admm_solve. */
 int mga_cluster_solve(mga_plan* plan, const mga_params* prm, const void* y, void* x_out, int64_t B, int dtype,
                       int n_outer, int max_cg_iter, double cg_tol, double admm_tol, double t_mean, double t_var,
                       int want_diag, const mga_admm_outputs* outs, void* stream);

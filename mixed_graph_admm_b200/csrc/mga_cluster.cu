@@ -37,6 +37,8 @@ template <typename S>
 struct ClArgs {
   int N, NP, T, t_in, CL, TL, kd, ku, q1, nnz;      // TL: time steps per CTA
   int transpose_exact;
+  int u_wT, d_wT;          // 1: time-invariant weights; T / T-1: one slice per time step (the caller's learned / time-varying tables)
+  const int* csr_slot;     // (nnz) index of every in-list entry into a d_w slice (time-varying weights)
   int n_outer, max_cg, want_diag;
   int64_t B;
   const int* nbr_d; const float* d_w; const int* nbr_u; const float* u_w;
@@ -77,6 +79,7 @@ struct ClCtx {
   S* slots;       // [2][kClMaxCL] cluster reduction slots (a full copy in every CTA), double-buffered
   int parity;
   bool qdot;      // the in-list is the exact transpose of the forward temporal table
+  int sd_stride, su_stride, sc_stride;   // floats between the weight slices of consecutive local steps (0: time-invariant)
   cg::cluster_group cl = cg::this_cluster();
 
   // Sum over the whole window (all CTAs of the cluster), the same bits in every thread of the cluster.
@@ -169,9 +172,8 @@ struct ClCtx {
       for (int j = 0; j < kd; ++j) {
         const int c = nbr_d[i * kd + j];
         if (c < 0) continue;
-        const S w = (S)w_d[i * kd + j];
 #pragma unroll
-        for (int m = 0; m < RPT; ++m) acc[m] += w * prev[m * NP + c];
+        for (int m = 0; m < RPT; ++m) acc[m] += (S)w_d[(l0 + m) * sd_stride + i * kd + j] * prev[m * NP + c];
       }
     }
 #pragma unroll
@@ -189,9 +191,8 @@ struct ClCtx {
       const S* next = qbuf + (l0 + 1) * NP;
       for (int e = cptr[i]; e < cptr[i + 1]; ++e) {
         const int src = csrc[e];
-        const S w = (S)cw[e];
 #pragma unroll
-        for (int m = 0; m < RPT; ++m) f[m] += w * next[m * NP + src];
+        for (int m = 0; m < RPT; ++m) f[m] += (S)cw[(l0 + m) * sc_stride + e] * next[m * NP + src];
       }
     }
 #pragma unroll
@@ -212,9 +213,8 @@ struct ClCtx {
       for (int j = 0; j < ku; ++j) {
         const int c = nbr_u[i * ku + j];
         if (c < 0) continue;
-        const S w = (S)w_u[i * ku + j];
 #pragma unroll
-        for (int m = 0; m < RPT; ++m) acc[m] += w * row[m * NP + c];
+        for (int m = 0; m < RPT; ++m) acc[m] += (S)w_u[(l0 + m) * su_stride + i * ku + j] * row[m * NP + c];
       }
     }
 #pragma unroll
@@ -328,18 +328,32 @@ __global__ void __launch_bounds__(MAXT, 1) k_admm_cluster(const ClArgs<S> a) {
   S* qbuf = pbuf + (size_t)(TL + 1) * NP;
   S* red = qbuf + (size_t)(TL + 1) * NP;
   S* slots = red + 32;
-  float* w_d = reinterpret_cast<float*>(slots + 2 * kClMaxCL);
-  float* w_u = w_d + (size_t)N * a.kd;
-  float* cw = w_u + (size_t)N * a.ku;
-  int* nbr_d = reinterpret_cast<int*>(cw + a.nnz);
+  // weight slices: one per local time step when the caller's tables vary in time, else one
+  const int nsd = a.d_wT > 1 ? TL : 1, nsu = a.u_wT > 1 ? TL : 1;
+  float* w_d = reinterpret_cast<float*>(slots + 2 * kClMaxCL);      // [nsd][N * kd]: slice l = weights of L_d at step t0 + l (d_w[t - 1])
+  float* w_u = w_d + (size_t)nsd * N * a.kd;                         // [nsu][N * ku]: u_w[t]
+  float* cw = w_u + (size_t)nsu * N * a.ku;                          // [nsd][nnz]: in-list weights of L_d^T at step t (d_w[t][slot])
+  int* nbr_d = reinterpret_cast<int*>(cw + (size_t)nsd * a.nnz);
   int* nbr_u = nbr_d + (size_t)N * a.kd;
   int* cptr = nbr_u + (size_t)N * a.ku;
   int* csrc = cptr + N + 1;
   float* dred = reinterpret_cast<float*>(csrc + a.nnz);            // (used as S below) 12 x 32 partials of the diagnostics
   S* dredS = reinterpret_cast<S*>(reinterpret_cast<size_t>(dred + 1) & ~(size_t)7);
-  for (int k = threadIdx.x; k < N * a.kd; k += blockDim.x) { w_d[k] = a.d_w[k]; nbr_d[k] = a.nbr_d[k]; }
-  for (int k = threadIdx.x; k < N * a.ku; k += blockDim.x) { w_u[k] = a.u_w[k]; nbr_u[k] = a.nbr_u[k]; }
-  for (int k = threadIdx.x; k < a.nnz; k += blockDim.x) { cw[k] = a.csr_w[k]; csrc[k] = a.csr_src[k]; }
+  for (int k = threadIdx.x; k < N * a.kd; k += blockDim.x) nbr_d[k] = a.nbr_d[k];
+  for (int k = threadIdx.x; k < N * a.ku; k += blockDim.x) nbr_u[k] = a.nbr_u[k];
+  for (int k = threadIdx.x; k < a.nnz; k += blockDim.x) csrc[k] = a.csr_src[k];
+  for (int l = 0; l < nsd; ++l) {
+    const int t = rank * TL + l;
+    const int sd = a.d_wT > 1 ? min(max(t - 1, 0), a.d_wT - 1) : 0;        // L_d at step t uses d_w[t - 1] (ADMM.py:171)
+    const int st = a.d_wT > 1 ? min(t, a.d_wT - 1) : 0;                    // L_d^T at step t uses d_w[t] (ADMM.py:200-208)
+    for (int k = threadIdx.x; k < N * a.kd; k += blockDim.x) w_d[(size_t)l * N * a.kd + k] = a.d_w[(size_t)sd * N * a.kd + k];
+    for (int k = threadIdx.x; k < a.nnz; k += blockDim.x)
+      cw[(size_t)l * a.nnz + k] = a.d_wT > 1 ? a.d_w[(size_t)st * N * a.kd + a.csr_slot[k]] : a.csr_w[k];
+  }
+  for (int l = 0; l < nsu; ++l) {
+    const int su = a.u_wT > 1 ? min(rank * TL + l, a.u_wT - 1) : 0;
+    for (int k = threadIdx.x; k < N * a.ku; k += blockDim.x) w_u[(size_t)l * N * a.ku + k] = a.u_w[(size_t)su * N * a.ku + k];
+  }
   for (int k = threadIdx.x; k <= N; k += blockDim.x) cptr[k] = a.csr_ptr[k];
   for (int k = threadIdx.x; k < 2 * (TL + 1) * NP; k += blockDim.x) pbuf[k] = (S)0;     // incl. the outermost halo rows
   for (int k = threadIdx.x; k < 2 * kClMaxCL; k += blockDim.x) slots[k] = (S)0;
@@ -349,6 +363,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_admm_cluster(const ClArgs<S> a) {
   c.N = N; c.NP = NP; c.T = T; c.t_in = t_in; c.t0 = rank * TL; c.i = threadIdx.x - lr * NP; c.rank = rank; c.CL = CL;
   c.TL = TL; c.l0 = lr * RPT;
   c.kd = a.kd; c.ku = a.ku; c.q1 = a.q1; c.qdot = a.transpose_exact != 0;
+  c.sd_stride = a.d_wT > 1 ? N * a.kd : 0; c.su_stride = a.u_wT > 1 ? N * a.ku : 0; c.sc_stride = a.d_wT > 1 ? a.nnz : 0;
   c.active = c.i < N;
   c.nbr_d = nbr_d; c.w_d = w_d; c.nbr_u = nbr_u; c.w_u = w_u; c.cptr = cptr; c.csrc = csrc; c.cw = cw;
   c.pbuf = pbuf; c.qbuf = qbuf; c.red = red; c.slots = slots; c.parity = 0;
@@ -584,7 +599,7 @@ struct ClGeom {
 template <typename S>
 static bool cl_geometry(const mga_plan* p, ClGeom* out) {
   const GraphDev& g = p->g;
-  if (g.temporal == MGA_TEMPORAL_BAND || g.u_wT != 1 || g.d_wT != 1 || g.N > 1024 || g.T > kClMaxCL * kClMaxTL) return false;
+  if (g.temporal == MGA_TEMPORAL_BAND || g.N > 1024 || g.T > kClMaxCL * kClMaxTL) return false;
   ClGeom q;
   q.NP = ((g.N + 31) / 32) * 32;
   q.CL = std::min(g.T, kClMaxCL);
@@ -595,7 +610,8 @@ static bool cl_geometry(const mga_plan* p, ClGeom* out) {
   q.TL = q.TR * q.RPT;
   q.CL = (g.T + q.TL - 1) / q.TL;                 // no empty CTAs (T = 9 -> TL = 2 -> 5 CTAs)
   q.smem = ((size_t)CS_COUNT * q.TL + 2 * (q.TL + 1)) * q.NP * sizeof(S) + (32 + 2 * kClMaxCL) * sizeof(S) +
-           ((size_t)g.N * (g.kd + g.ku) + g.nnz) * 8 + (size_t)(g.N + 1) * 4 + 16 + ((size_t)MGA_DIAG_COLS * 32 + 6 * kClMaxCL) * sizeof(S);
+           ((size_t)g.N * (g.kd + g.ku) + g.nnz) * 4 + (size_t)(g.N + 1) * 4 + 16 +
+           ((size_t)(g.d_wT > 1 ? q.TL : 1) * ((size_t)g.N * g.kd + g.nnz) + (size_t)(g.u_wT > 1 ? q.TL : 1) * g.N * g.ku) * 4 + ((size_t)MGA_DIAG_COLS * 32 + 6 * kClMaxCL) * sizeof(S);
   if (q.smem > (size_t)p->max_smem_optin) return false;
   *out = q;
   return true;
@@ -636,7 +652,7 @@ static int cl_admm(mga_plan* p, const mga_params* m, const void* y, const void* 
   const bool tol_mode = cg_tol > 0 || admm_tol > 0;
   if (tol_mode && B != 1) { set_error("cluster mode: the stop tests are per window, tolerance mode takes B = 1"); return MGA_ERR_UNSUPPORTED; }
   ClArgs<S> a{};
-  a.N = g.N; a.NP = q.NP; a.T = g.T; a.t_in = g.t_in; a.CL = q.CL; a.TL = q.TL; a.transpose_exact = p->ldrt_gather ? 0 : 1; a.kd = g.kd; a.ku = g.ku; a.q1 = g.q1; a.nnz = g.nnz;
+  a.N = g.N; a.NP = q.NP; a.T = g.T; a.t_in = g.t_in; a.CL = q.CL; a.TL = q.TL; a.transpose_exact = p->ldrt_gather ? 0 : 1; a.u_wT = g.u_wT; a.d_wT = g.d_wT; a.csr_slot = g.csr_slot; a.kd = g.kd; a.ku = g.ku; a.q1 = g.q1; a.nnz = g.nnz;
   a.n_outer = n_outer; a.max_cg = max_cg; a.want_diag = (diag_flags & 1) ? 1 : 0;
   a.B = B;
   a.nbr_d = g.nbr_d; a.d_w = g.d_w; a.nbr_u = g.nbr_u; a.u_w = g.u_w; a.csr_ptr = g.csr_ptr; a.csr_src = g.csr_src; a.csr_w = g.csr_w;

@@ -723,12 +723,13 @@ int mga_admm_solve(mga_plan* p, const mga_params* prm, const void* y, int y_rows
   }
   if (mode != MGA_MODE_STREAMING && mode != MGA_MODE_STREAMING_POINT && can_res)
     return resident_admm(p, prm, y, mask, x_out, B, n_outer, max_cg, t_mean, t_var, want_diag, outs, (cudaStream_t)stream);
-  // The reference's own call pattern - one window, tolerances, float64 (ADMM.py:76-80) - and float64 batches: one
-  // thread-block cluster per window, the stop tests decided on the device (MGA_CLUSTER=0: the general kernels instead)
+  // The reference's own call pattern - one window, tolerances, float64 (ADMM.py:76-80) -, float64 batches and plans with
+  // time-varying weight tables (T, N, k): one thread-block cluster per window, the stop tests decided on the device
+  // (MGA_CLUSTER=0: the general kernels instead)
   {
     static const bool cluster_on = [] { const char* e = std::getenv("MGA_CLUSTER"); return !e || std::atoi(e) != 0; }();
     if (cluster_on && mode != MGA_MODE_STREAMING && mode != MGA_MODE_STREAMING_POINT && prm->ablation == MGA_ABL_NONE &&
-        (fixed ? dtype == MGA_F64 : B == 1) && cluster_eligible(p, dtype))
+        (fixed ? (dtype == MGA_F64 || p->g.u_wT > 1 || p->g.d_wT > 1) : B == 1) && cluster_eligible(p, dtype))
       return cluster_admm(p, prm, y, mask, x_out, B, dtype, n_outer, max_cg, cg_tol, admm_tol, t_mean, t_var, want_diag, outs,
                           (cudaStream_t)stream);
   }
@@ -747,7 +748,7 @@ int mga_cluster_solve(mga_plan* p, const mga_params* prm, const void* y, void* x
   if (rc) return rc;
   if (!prm || !y || !x_out || n_outer < 0 || max_cg < 0) { set_error("mga_cluster_solve: bad argument"); return MGA_ERR_INVALID; }
   if (prm->ablation != MGA_ABL_NONE || !cluster_eligible(p, dtype)) {
-    set_error("mga_cluster_solve: needs ablation None, time-invariant weights, no banded line graph, T <= 32 and N <= 1024");
+    set_error("mga_cluster_solve: needs ablation None, no banded line graph, T <= 32 and N <= 1024");
     return MGA_ERR_UNSUPPORTED;
   }
   mga_admm_outputs none{};

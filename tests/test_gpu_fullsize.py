@@ -278,6 +278,29 @@ def test_cluster_mode_notebook_call_is_one_launch():
     assert rel_err(x, g.t("x")) <= 1e-11
 
 
+def test_cluster_mode_time_varying_weights_tolerance_call():
+    """Per-time-step weight tables (T,N,k) / (T-1,N,K) with the notebooks' call pattern (B = 1, float64,
+    tolerances): one cluster launch, the oracle's CG counts and iterates."""
+    from mixed_graph_admm_b200 import _cabi
+    from oracle import admm_oracle as O
+    g = Golden("pems04_t24_tol_f64")
+    blk = solver_from_golden(g)
+    gen = torch.Generator().manual_seed(5)
+    blk.u_ew = blk.u_ew * (0.7 + 0.6 * torch.rand(blk.u_ew.shape, generator=gen, dtype=blk.u_ew.dtype))
+    blk.d_ew = blk.d_ew * (0.7 + 0.6 * torch.rand(blk.d_ew.shape, generator=gen, dtype=blk.d_ew.dtype))
+    assert blk.u_ew.dim() == 3 and blk.d_ew.dim() == 3
+    l0 = _cabi.lib().mga_launch_count()
+    x = blk.combined_loop(g.y, print_info=False)
+    assert _cabi.lib().mga_launch_count() - l0 == 1
+    og = O.OracleGraph(nbr=blk.connect_list, u_w=blk.u_ew, d_w=blk.d_ew)
+    prm = O.OracleParams(**g.admm_info, t_in=g.ctor["t_in"], T=g.ctor["T"])
+    tr = O.admm_combined(og, prm, g.y, max_admm_iter=blk.max_ADMM_iter, max_cg_iter=blk.max_CG_iter, cg_tol=blk.CG_tol,
+                         admm_tol=blk.ADMM_tol)
+    assert blk.CG_tol > 0 and blk.ADMM_tol > 0
+    assert blk.CG_iter_x == list(tr.cg_iter_x) and blk.CG_iter_zu == list(tr.cg_iter_zu) and blk.CG_iter_zd == list(tr.cg_iter_zd)
+    assert rel_err(x, tr.x) <= 1e-11
+
+
 @pytest.mark.parametrize("name", ["two_loops_f32", "two_loops_f64"])
 def test_two_loops_matches_reference(name):
     """``two_loops`` (ADMM.py:410-508): returns nothing like the reference, appends only the CG lists, and

@@ -420,7 +420,13 @@ def test_time_varying_edge_weights_match_oracle():
     assert _cabi.lib().mga_plan_resident_eligible(blk._plan().handle, 0) == 0
     blk.max_ADMM_iter, blk.max_CG_iter, blk.CG_tol, blk.ADMM_tol = 3, 8, -1.0, -1.0
     y = g.y
+    l0 = _cabi.lib().mga_launch_count()
     x = blk.combined_loop(y.cuda(), print_info=False).cpu()
+    assert _cabi.lib().mga_launch_count() - l0 == 1      # cluster mode: per-step weight slices staged per CTA, one launch
+    xs = solver_from_golden(g, mode="streaming_point")
+    xs.u_ew, xs.d_ew = blk.u_ew, blk.d_ew
+    xs.max_ADMM_iter, xs.max_CG_iter, xs.CG_tol, xs.ADMM_tol = 3, 8, -1.0, -1.0
+    assert rel_err(xs.combined_loop(y.cuda(), print_info=False).cpu(), x) <= 2e-6      # the general kernels agree
     og = O.OracleGraph(nbr=blk.connect_list, u_w=blk.u_ew, d_w=blk.d_ew)
     prm = O.OracleParams(**g.admm_info, t_in=g.ctor["t_in"], T=g.ctor["T"])
     tr = O.admm_combined(og, prm, y, max_admm_iter=3, max_cg_iter=8, cg_tol=-1.0, admm_tol=-1.0)
