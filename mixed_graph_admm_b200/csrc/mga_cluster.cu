@@ -30,8 +30,9 @@ namespace cg = cooperative_groups;
 
 namespace mga {
 
-constexpr int kClMaxTL = 4;     // time steps per CTA (T <= 8 * 4)
-constexpr int kClMaxCL = 8;     // portable cluster size
+constexpr int kClMaxTL = 4;     // time steps per CTA (T <= 8 * 4 with portable clusters)
+constexpr int kClMaxCL = 16;    // largest cluster (8 is the portable size; 9..16 need the non-portable opt-in)
+constexpr int kClPortable = 8;
 
 template <typename S>
 struct ClArgs {
@@ -148,10 +149,13 @@ struct ClCtx {
   }
 
   // own steps -> pbuf rows 1..TL, last own step -> halo row 0 of the next CTA; cluster barrier
-  __device__ __forceinline__ void publish_p(const S (&v)[RPT]) {
+  __device__ __forceinline__ void put_p(const S (&v)[RPT]) {
 #pragma unroll
     for (int m = 0; m < RPT; ++m) pbuf[(l0 + m + 1) * NP + i] = v[m];
     if (rank + 1 < CL && l0 + RPT == TL) cl.map_shared_rank(pbuf, rank + 1)[i] = v[RPT - 1];
+  }
+  __device__ __forceinline__ void publish_p(const S (&v)[RPT]) {
+    put_p(v);
     cl.sync();
   }
   // own steps -> qbuf rows 0..TL-1, first own step -> halo row TL of the previous CTA; cluster barrier
@@ -231,7 +235,7 @@ struct ClCtx {
   // mk != nullptr: H = the caller's elementwise mask (values of this thread's steps) instead of "rows t < t_in" - the
   // reference passes the mask to the FIRST residual of the x solve only (quirk Q4, ADMM.py:344-349)
   template <int SYS, bool DOT>
-  __device__ __forceinline__ void apply(const S (&v)[RPT], S (&out)[RPT], S a, S c, S& dot, const S* mk = nullptr) {
+  __device__ __forceinline__ void apply(const S (&v)[RPT], S (&out)[RPT], S a, S c, S& dot, S (&q)[RPT], const S* mk = nullptr) {
     publish_p(v);
     if (SYS == MGA_SYS_ZU) {
       lu(v, out);
@@ -244,18 +248,9 @@ struct ClCtx {
       if (DOT) dot = csum(loc);
       return;
     }
-    S q[RPT];
     ldr(v, q);
     const bool fused = DOT && qdot;
-    if (fused) {
-      S loc = 0;
-#pragma unroll
-      for (int m = 0; m < RPT; ++m) {
-        const S hx = (SYS == MGA_SYS_X && t0 + l0 + m < t_in) ? v[m] * v[m] : (S)0;
-        loc += (hx + a * (v[m] * v[m])) + c * (q[m] * q[m]);
-      }
-      csum_post(loc);                     // partial -> every CTA's slot; completed by the barrier of publish_q
-    }
+    if (fused) csum_post(quad<SYS>(v, q, a, c));      // partial -> every CTA's slot; completed by the barrier of publish_q
     publish_q(q);
     if (fused) dot = csum_read();
     ldrt(q, out);
@@ -272,15 +267,33 @@ struct ClCtx {
     }
     if (DOT && !fused) dot = csum(loc);
   }
+  // this thread's part of <v, A v> = sum D v^2 + c ||L_d v||^2 with q = L_d v
+  template <int SYS>
+  __device__ __forceinline__ S quad(const S (&v)[RPT], const S (&q)[RPT], S a, S c) const {
+    S loc = 0;
+#pragma unroll
+    for (int m = 0; m < RPT; ++m) {
+      const S hx = (SYS == MGA_SYS_X && t0 + l0 + m < t_in) ? v[m] * v[m] : (S)0;
+      loc += (hx + a * (v[m] * v[m])) + c * (q[m] * q[m]);
+    }
+    return loc;
+  }
 
   // CG_solver (ADMM.py:329-368): r holds the right-hand side on entry, x the warm start.  Returns the iteration count
   // (tol > 0 and reached) or -1.  alpha_out / beta_out: this window's column of the (max_cg, B) arrays or NULL.
+  //
+  // Two cluster barriers per iteration instead of three.  The reference's iteration needs p' = r' + beta p before it can
+  // gather A p', and beta needs <r', r'> - a barrier of its own.  A is linear: A p' = A r' + beta A p (and L_d p' =
+  // L_d r' + beta L_d p), so the kernel publishes r' TOGETHER with the partial sums of <r', r'> (barrier A), gathers on
+  // r', and rebuilds A p' / L_d p' from the previous ones it still holds; <p', A p'> rides on the barrier that publishes
+  // L_d r' (barrier B; z_u: its own reduction).  Same iterates up to rounding; alpha, beta, the stop test on
+  // sqrt(<r', r'>) (ADMM.py:360) and the iteration counts are those of the reference's recurrence.
   template <int SYS>
   __device__ __forceinline__ int cg_solve(S (&x)[RPT], S (&r)[RPT], S a, S c, int max_cg, double tol, S* alpha_out, S* beta_out,
                                           int64_t B, const S* mask0 = nullptr) {
-    S p[RPT], ap[RPT];
+    S p[RPT], ap[RPT], qp[RPT], t[RPT];
     S pap = 0;
-    apply<SYS, false>(x, ap, a, c, pap, mask0);
+    apply<SYS, false>(x, ap, a, c, pap, qp, mask0);
     S loc = 0;
 #pragma unroll
     for (int l = 0; l < RPT; ++l) {
@@ -289,8 +302,9 @@ struct ClCtx {
       loc += r[l] * r[l];
     }
     S rr = csum(loc);
+    if (max_cg <= 0) return -1;
+    apply<SYS, true>(p, ap, a, c, pap, qp);                    // A p_0, L_d p_0, <p_0, A p_0>
     for (int k = 0; k < max_cg; ++k) {
-      apply<SYS, true>(p, ap, a, c, pap);
       const S alpha = rr / pap;
       loc = 0;
 #pragma unroll
@@ -299,7 +313,11 @@ struct ClCtx {
         r[l] = r[l] - alpha * ap[l];
         loc += r[l] * r[l];
       }
-      const S rrn = csum(loc);
+      const bool more = k + 1 < max_cg;
+      if (more) put_p(r);                                      // barrier A: r' and the partial sums of <r', r'>
+      csum_post(loc);
+      cl.sync();
+      const S rrn = csum_read();
       const S beta = rrn / rr;
       rr = rrn;
       if (alpha_out && rank == 0 && threadIdx.x == 0) {
@@ -307,8 +325,38 @@ struct ClCtx {
         beta_out[(size_t)k * B] = beta;
       }
       if (tol > 0 && sqrt(rr) < (S)tol) return k + 1;          // ADMM.py:360 (B = 1: the max over the batch is this window)
+      if (!more) break;
 #pragma unroll
       for (int l = 0; l < RPT; ++l) p[l] = r[l] + beta * p[l];
+      if (SYS == MGA_SYS_ZU) {
+        lu(r, t);
+        loc = 0;
+#pragma unroll
+        for (int l = 0; l < RPT; ++l) {
+          ap[l] = (c * t[l] + a * r[l]) + beta * ap[l];
+          loc += p[l] * ap[l];
+        }
+        pap = csum(loc);                                       // barrier B
+        continue;
+      }
+      S qr[RPT];
+      ldr(r, qr);
+#pragma unroll
+      for (int l = 0; l < RPT; ++l) qp[l] = qr[l] + beta * qp[l];
+      if (qdot) csum_post(quad<SYS>(p, qp, a, c));
+      publish_q(qr);                                           // barrier B: L_d r' and the partial sums of <p', A p'>
+      if (qdot) pap = csum_read();
+      ldrt(qr, t);
+      loc = 0;
+#pragma unroll
+      for (int l = 0; l < RPT; ++l) {
+        S ar;
+        if (SYS == MGA_SYS_X) ar = (((t0 + l0 + l < t_in) ? r[l] : (S)0) + a * r[l]) + c * t[l];
+        else ar = c * t[l] + a * r[l];
+        ap[l] = ar + beta * ap[l];
+        loc += p[l] * ap[l];
+      }
+      if (!qdot) pap = csum(loc);                              // use_kNN=False: the "transpose" is a gather with the forward table
     }
     return -1;
   }
@@ -597,12 +645,12 @@ struct ClGeom {
 };
 
 template <typename S>
-static bool cl_geometry(const mga_plan* p, ClGeom* out) {
+static bool cl_geometry(const mga_plan* p, ClGeom* out, int maxcl = kClPortable) {
   const GraphDev& g = p->g;
-  if (g.temporal == MGA_TEMPORAL_BAND || g.N > 1024 || g.T > kClMaxCL * kClMaxTL) return false;
+  if (g.temporal == MGA_TEMPORAL_BAND || g.N > 1024 || g.T > maxcl * kClMaxTL) return false;
   ClGeom q;
   q.NP = ((g.N + 31) / 32) * 32;
-  q.CL = std::min(g.T, kClMaxCL);
+  q.CL = std::min(g.T, maxcl);
   q.TL = (g.T + q.CL - 1) / q.CL;
   q.TR = 1;                                       // one thread per node and slab: a table entry is read once for all its steps
   if (const char* e = std::getenv("MGA_CLUSTER_TR")) q.TR = std::max(1, std::min(std::min(q.TL, 1024 / q.NP), std::atoi(e)));
@@ -626,6 +674,7 @@ template <typename S, int RPT>
 static int cl_launch(mga_plan* p, const ClArgs<S>& a, const ClGeom& q, cudaStream_t st) {
   auto kern = q.NP * q.TR <= 384 ? k_admm_cluster<S, RPT, 384> : k_admm_cluster<S, RPT, 1024>;
   MGA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)q.smem));
+  if (q.CL > kClPortable) MGA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(a.B * q.CL));
   cfg.blockDim = dim3(q.NP * q.TR);
@@ -638,6 +687,10 @@ static int cl_launch(mga_plan* p, const ClArgs<S>& a, const ClGeom& q, cudaStrea
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (q.CL > kClPortable) {            // a GPC must have room for the whole cluster; MGA_ERR_UNSUPPORTED sends the caller back to 8
+    int nc = 0;
+    if (cudaOccupancyMaxActiveClusters(&nc, kern, &cfg) != cudaSuccess || nc < 1) { cudaGetLastError(); return MGA_ERR_UNSUPPORTED; }
+  }
   MGA_CUDA(cudaLaunchKernelEx(&cfg, kern, a));
   MGA_LAUNCH_CHECK("k_admm_cluster");
   return MGA_OK;
@@ -645,10 +698,16 @@ static int cl_launch(mga_plan* p, const ClArgs<S>& a, const ClGeom& q, cudaStrea
 
 template <typename S>
 static int cl_admm(mga_plan* p, const mga_params* m, const void* y, const void* mask, void* x_out, int64_t B, int n_outer, int max_cg, double cg_tol,
-                   double admm_tol, double t_mean, double t_var, int diag_flags, const mga_admm_outputs* outs, cudaStream_t st) {
+                   double admm_tol, double t_mean, double t_var, int diag_flags, const mga_admm_outputs* outs, cudaStream_t st,
+                   int force_cl = 0) {
   const GraphDev& g = p->g;
+  // Few windows: the largest cluster a GPC takes (T = 24: 12 CTAs of 2 steps instead of 8 of 3 - the slab's gathers are bound by
+  // ONE SM's shared-memory pipe); batches: portable clusters, two of which fit a GPC.  MGA_CLUSTER_CL overrides.
+  int maxcl = B <= 8 ? kClMaxCL : kClPortable;
+  if (const char* e = std::getenv("MGA_CLUSTER_CL")) maxcl = std::max(1, std::min(kClMaxCL, std::atoi(e)));
+  if (force_cl > 0) maxcl = force_cl;
   ClGeom q;
-  if (!cl_geometry<S>(p, &q)) { set_error("cluster mode: the window does not fit"); return MGA_ERR_UNSUPPORTED; }
+  if (!cl_geometry<S>(p, &q, maxcl) && !cl_geometry<S>(p, &q)) { set_error("cluster mode: the window does not fit"); return MGA_ERR_UNSUPPORTED; }
   const bool tol_mode = cg_tol > 0 || admm_tol > 0;
   if (tol_mode && B != 1) { set_error("cluster mode: the stop tests are per window, tolerance mode takes B = 1"); return MGA_ERR_UNSUPPORTED; }
   ClArgs<S> a{};
@@ -703,6 +762,8 @@ static int cl_admm(mga_plan* p, const mga_params* m, const void* y, const void* 
     case 3: rc = cl_launch<S, 3>(p, a, q, st); break;
     default: rc = cl_launch<S, 4>(p, a, q, st); break;
   }
+  if (rc == MGA_ERR_UNSUPPORTED && q.CL > kClPortable)      // no GPC takes this cluster: portable size
+    return cl_admm<S>(p, m, y, mask, x_out, B, n_outer, max_cg, cg_tol, admm_tol, t_mean, t_var, diag_flags, outs, st, kClPortable);
   if (rc) return rc;
   if (tol_mode) {
     MGA_CUDA(cudaStreamSynchronize(st));

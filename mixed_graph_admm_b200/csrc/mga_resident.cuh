@@ -488,7 +488,12 @@ struct Ctx {
     }
     float rr = bsum(loc);
     for (int it = 0; it < n_cg; ++it) {
+#if defined(MGA_RES_X) && (MGA_RES_X & 2)      // timing experiment: no <p, Ap> reduction
+      apply<SYS, false, BAND, false>(p, ap, a, c, m0, pap);
+      pap = rr * 2.f + ap[0] * 1e-30f;
+#else
       apply<SYS, false, BAND, true>(p, ap, a, c, m0, pap);
+#endif
       const float alpha = rr / pap;
       loc = 0.f;
 #pragma unroll
@@ -497,7 +502,11 @@ struct Ctx {
         r[k] = r[k] - alpha * ap[k];
         loc += r[k] * r[k];
       }
+#if defined(MGA_RES_X) && (MGA_RES_X & 1)      // timing experiment: no <r, r> reduction (and its barrier)
+      const float rrn = rr * 0.5f + loc * 1e-30f;
+#else
       const float rrn = bsum(loc);
+#endif
       const float beta = rrn / rr;
       rr = rrn;
       if (alpha_out && threadIdx.x == 0) {
