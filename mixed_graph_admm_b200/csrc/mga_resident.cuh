@@ -599,6 +599,9 @@ struct Cta {
       const int wn = i >> 5;     // warp of this node row (the same for every slab)
       const int first = a.ell_ptr[wn];
       c.steps = a.ell_ptr[wn + 1] - first;
+#if defined(MGA_RES_X) && (MGA_RES_X & 12)      // timing experiment: every warp's in-list cut to 7 steps (4) / set to 6 steps (8)
+      c.steps = (MGA_RES_X & 8) ? 6 : min(c.steps, 7);
+#endif
       c.ent = smem_addr(ent + (size_t)first * 32 + (i & 31));
     }
     for (int e = threadIdx.x; e < a.ell_total + 64; e += blockDim.x) {
