@@ -405,6 +405,25 @@ def test_shapes_and_instantiations_against_oracle(N, k, T, B, iso, mode):
     np.testing.assert_allclose(blk.p_res_list[-1], tr.p_res[-1], rtol=2e-5, atol=1e-7)
 
 
+def test_empty_batch_raises_runtime_error_like_the_reference():
+    """B = 0: the reference dies in its first reshape with a RuntimeError (torch: 'cannot reshape tensor of 0 elements',
+    checked on the oracle here); the library refuses the call with a RuntimeError too - on both entry points."""
+    from oracle import admm_oracle as O
+    g = Golden("tiny_f32")
+    og = O.OracleGraph(nbr=g.t("connect_list"), u_w=g.t("u_ew"), d_w=g.t("d_ew"))
+    prm = O.OracleParams(**g.admm_info, t_in=g.ctor["t_in"], T=g.ctor["T"])
+    with pytest.raises(RuntimeError):
+        O.admm_combined(og, prm, g.y[:0], max_admm_iter=2, max_cg_iter=3, cg_tol=-1.0, admm_tol=-1.0)
+    blk = solver_from_golden(g)
+    blk.max_ADMM_iter, blk.max_CG_iter, blk.CG_tol, blk.ADMM_tol = 2, 3, -1.0, -1.0
+    with pytest.raises(RuntimeError):
+        blk.combined_loop(g.y[:0].cuda(), print_info=False)
+    with pytest.raises(RuntimeError):
+        blk.combined_loop(g.y[:0], print_info=False)          # host entry
+    x = blk.combined_loop(g.y[:1], print_info=False)           # the solver is still usable afterwards
+    assert x.shape[0] == 1 and torch.isfinite(x).all()
+
+
 def test_time_varying_edge_weights_match_oracle():
     """callers may replace u_ew / d_ew by per-time-step tables (T,N,k) / (T-1,N,K) (the
     'unrolling' follow-up learns them).  The plan must notice that the slices differ, leave the resident and
