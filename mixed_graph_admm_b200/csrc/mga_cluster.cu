@@ -67,13 +67,17 @@ __device__ __forceinline__ S cl_soft(S s, S d) {
   return sg * u * (S)(u > (S)0);   // ADMM.py:407-408
 }
 
-template <typename S, int RPT>
+// CMP (the two-CTAs-per-SM instantiation): compact tables - 16-bit neighbour / source indices, and the in-list reads its
+// weights from the forward table's slices through a 16-bit slot index instead of keeping a permuted copy
+template <typename S, int RPT, bool CMP = false>
 struct ClCtx {
+  using I = typename std::conditional<CMP, short, int>::type;
   int N, NP, T, t_in, t0, i, rank, CL, kd, ku, q1;
   int TL, l0;     // time steps per CTA; this thread's first local step (it owns l0 .. l0 + RPT - 1)
   bool active;
-  const int* nbr_d; const float* w_d; const int* nbr_u; const float* w_u;
-  const int* cptr; const int* csrc; const float* cw;
+  const I* nbr_d; const float* w_d; const I* nbr_u; const float* w_u;
+  const int* cptr; const I* csrc; const float* cw;
+  const unsigned short* slot;     // CMP: position of every in-list entry in a d_w slice
   S* pbuf;        // (TL + 1) rows x NP: row 0 = the previous CTA's last step (halo), rows 1..TL = own steps
   S* qbuf;        // (TL + 1) rows x NP: rows 0..TL-1 = own steps, row TL = the next CTA's first step (halo)
   S* red;         // 32 warp partials
@@ -196,7 +200,11 @@ struct ClCtx {
       for (int e = cptr[i]; e < cptr[i + 1]; ++e) {
         const int src = csrc[e];
 #pragma unroll
-        for (int m = 0; m < RPT; ++m) f[m] += (S)cw[(l0 + m) * sc_stride + e] * next[m * NP + src];
+        for (int m = 0; m < RPT; ++m) {
+          // step t reads d_w[t]: one slice after the one L_d uses at the same step (CMP: slices t0 - 1 .. t0 + TL - 1 are staged)
+          const float w = CMP ? w_d[(l0 + m + 1) * sd_stride + slot[e]] : cw[(l0 + m) * sc_stride + e];
+          f[m] += (S)w * next[m * NP + src];
+        }
       }
     }
 #pragma unroll
@@ -363,8 +371,9 @@ struct ClCtx {
 };
 
 // MAXT: launch bound (384: PEMS-sized graphs keep their registers - no spills in float64; 1024: up to 1024 nodes)
-template <typename S, int RPT, int MAXT>
-__global__ void __launch_bounds__(MAXT, 1) k_admm_cluster(const ClArgs<S> a) {
+// MINB = 2 (batches): two CTAs per SM, i.e. two clusters share a group of SMs - a cluster alone leaves its SMs waiting on barriers
+template <typename S, int RPT, int MAXT, int MINB = 1>
+__global__ void __launch_bounds__(MAXT, MINB) k_admm_cluster(const ClArgs<S> a) {
   extern __shared__ __align__(16) unsigned char smem_cl[];
   cg::cluster_group cluster = cg::this_cluster();
   const int N = a.N, NP = a.NP, T = a.T, t_in = a.t_in, CL = a.CL, TL = a.TL;
@@ -377,26 +386,32 @@ __global__ void __launch_bounds__(MAXT, 1) k_admm_cluster(const ClArgs<S> a) {
   S* red = qbuf + (size_t)(TL + 1) * NP;
   S* slots = red + 32;
   // weight slices: one per local time step when the caller's tables vary in time, else one
-  const int nsd = a.d_wT > 1 ? TL : 1, nsu = a.u_wT > 1 ? TL : 1;
+  constexpr bool CMP = MINB == 2;
+  using I = typename ClCtx<S, RPT, CMP>::I;
+  const int nsd = a.d_wT > 1 ? (CMP ? TL + 1 : TL) : 1, nsu = a.u_wT > 1 ? TL : 1;
   float* w_d = reinterpret_cast<float*>(slots + 2 * kClMaxCL);      // [nsd][N * kd]: slice l = weights of L_d at step t0 + l (d_w[t - 1])
   float* w_u = w_d + (size_t)nsd * N * a.kd;                         // [nsu][N * ku]: u_w[t]
-  float* cw = w_u + (size_t)nsu * N * a.ku;                          // [nsd][nnz]: in-list weights of L_d^T at step t (d_w[t][slot])
-  int* nbr_d = reinterpret_cast<int*>(cw + (size_t)nsd * a.nnz);
-  int* nbr_u = nbr_d + (size_t)N * a.kd;
-  int* cptr = nbr_u + (size_t)N * a.ku;
-  int* csrc = cptr + N + 1;
-  float* dred = reinterpret_cast<float*>(csrc + a.nnz);            // (used as S below) 12 x 32 partials of the diagnostics
-  S* dredS = reinterpret_cast<S*>(reinterpret_cast<size_t>(dred + 1) & ~(size_t)7);
-  for (int k = threadIdx.x; k < N * a.kd; k += blockDim.x) nbr_d[k] = a.nbr_d[k];
-  for (int k = threadIdx.x; k < N * a.ku; k += blockDim.x) nbr_u[k] = a.nbr_u[k];
-  for (int k = threadIdx.x; k < a.nnz; k += blockDim.x) csrc[k] = a.csr_src[k];
+  float* cw = w_u + (size_t)nsu * N * a.ku;                          // [nsd][nnz]: in-list weights of L_d^T at step t (d_w[t][slot]); not CMP
+  int* cptr = reinterpret_cast<int*>(cw + (CMP ? 0 : (size_t)nsd * a.nnz));
+  I* nbr_d = reinterpret_cast<I*>(cptr + N + 1);
+  I* nbr_u = nbr_d + (size_t)N * a.kd;
+  I* csrc = nbr_u + (size_t)N * a.ku;
+  unsigned short* slot = reinterpret_cast<unsigned short*>(csrc + a.nnz);     // CMP only
+  unsigned char* tail = reinterpret_cast<unsigned char*>(CMP ? (void*)(slot + a.nnz) : (void*)(csrc + a.nnz));
+  S* dredS = reinterpret_cast<S*>((reinterpret_cast<size_t>(tail) + 15) & ~(size_t)15);      // 12 x 32 partials of the diagnostics
+  for (int k = threadIdx.x; k < N * a.kd; k += blockDim.x) nbr_d[k] = (I)a.nbr_d[k];
+  for (int k = threadIdx.x; k < N * a.ku; k += blockDim.x) nbr_u[k] = (I)a.nbr_u[k];
+  for (int k = threadIdx.x; k < a.nnz; k += blockDim.x) csrc[k] = (I)a.csr_src[k];
+  if (CMP)
+    for (int k = threadIdx.x; k < a.nnz; k += blockDim.x) slot[k] = (unsigned short)a.csr_slot[k];
   for (int l = 0; l < nsd; ++l) {
     const int t = rank * TL + l;
     const int sd = a.d_wT > 1 ? min(max(t - 1, 0), a.d_wT - 1) : 0;        // L_d at step t uses d_w[t - 1] (ADMM.py:171)
     const int st = a.d_wT > 1 ? min(t, a.d_wT - 1) : 0;                    // L_d^T at step t uses d_w[t] (ADMM.py:200-208)
     for (int k = threadIdx.x; k < N * a.kd; k += blockDim.x) w_d[(size_t)l * N * a.kd + k] = a.d_w[(size_t)sd * N * a.kd + k];
-    for (int k = threadIdx.x; k < a.nnz; k += blockDim.x)
-      cw[(size_t)l * a.nnz + k] = a.d_wT > 1 ? a.d_w[(size_t)st * N * a.kd + a.csr_slot[k]] : a.csr_w[k];
+    if (!CMP)
+      for (int k = threadIdx.x; k < a.nnz; k += blockDim.x)
+        cw[(size_t)l * a.nnz + k] = a.d_wT > 1 ? a.d_w[(size_t)st * N * a.kd + a.csr_slot[k]] : a.csr_w[k];
   }
   for (int l = 0; l < nsu; ++l) {
     const int su = a.u_wT > 1 ? min(rank * TL + l, a.u_wT - 1) : 0;
@@ -406,14 +421,14 @@ __global__ void __launch_bounds__(MAXT, 1) k_admm_cluster(const ClArgs<S> a) {
   for (int k = threadIdx.x; k < 2 * (TL + 1) * NP; k += blockDim.x) pbuf[k] = (S)0;     // incl. the outermost halo rows
   for (int k = threadIdx.x; k < 2 * kClMaxCL; k += blockDim.x) slots[k] = (S)0;
 
-  ClCtx<S, RPT> c;
+  ClCtx<S, RPT, CMP> c;
   const int lr = threadIdx.x / NP;                                   // row group of this thread: steps lr * RPT .. + RPT - 1 of the slab
   c.N = N; c.NP = NP; c.T = T; c.t_in = t_in; c.t0 = rank * TL; c.i = threadIdx.x - lr * NP; c.rank = rank; c.CL = CL;
   c.TL = TL; c.l0 = lr * RPT;
   c.kd = a.kd; c.ku = a.ku; c.q1 = a.q1; c.qdot = a.transpose_exact != 0;
   c.sd_stride = a.d_wT > 1 ? N * a.kd : 0; c.su_stride = a.u_wT > 1 ? N * a.ku : 0; c.sc_stride = a.d_wT > 1 ? a.nnz : 0;
   c.active = c.i < N;
-  c.nbr_d = nbr_d; c.w_d = w_d; c.nbr_u = nbr_u; c.w_u = w_u; c.cptr = cptr; c.csrc = csrc; c.cw = cw;
+  c.nbr_d = nbr_d; c.w_d = w_d; c.nbr_u = nbr_u; c.w_u = w_u; c.cptr = cptr; c.csrc = csrc; c.cw = cw; c.slot = slot;
   c.pbuf = pbuf; c.qbuf = qbuf; c.red = red; c.slots = slots; c.parity = 0;
   cluster.sync();                                                    // tables and zeroed buffers of every CTA are in place
   const int i = c.i, t0 = c.t0 + c.l0;                               // t0: the thread's first step
@@ -642,6 +657,7 @@ __global__ void __launch_bounds__(MAXT, 1) k_admm_cluster(const ClArgs<S> a) {
 struct ClGeom {
   int CL, TL, TR, RPT, NP;      // cluster size, steps per CTA, row groups per CTA (threads = NP * TR), steps per thread
   size_t smem;
+  size_t smem2;                 // with compact tables (the two-CTAs-per-SM instantiation)
 };
 
 template <typename S>
@@ -657,9 +673,11 @@ static bool cl_geometry(const mga_plan* p, ClGeom* out, int maxcl = kClPortable)
   q.RPT = (q.TL + q.TR - 1) / q.TR;
   q.TL = q.TR * q.RPT;
   q.CL = (g.T + q.TL - 1) / q.TL;                 // no empty CTAs (T = 9 -> TL = 2 -> 5 CTAs)
-  q.smem = ((size_t)CS_COUNT * q.TL + 2 * (q.TL + 1)) * q.NP * sizeof(S) + (32 + 2 * kClMaxCL) * sizeof(S) +
-           ((size_t)g.N * (g.kd + g.ku) + g.nnz) * 4 + (size_t)(g.N + 1) * 4 + 16 +
-           ((size_t)(g.d_wT > 1 ? q.TL : 1) * ((size_t)g.N * g.kd + g.nnz) + (size_t)(g.u_wT > 1 ? q.TL : 1) * g.N * g.ku) * 4 + ((size_t)MGA_DIAG_COLS * 32 + 6 * kClMaxCL) * sizeof(S);
+  const size_t vec = ((size_t)CS_COUNT * q.TL + 2 * (q.TL + 1)) * q.NP * sizeof(S) + (32 + 2 * kClMaxCL) * sizeof(S) +
+                     ((size_t)MGA_DIAG_COLS * 32 + 6 * kClMaxCL) * sizeof(S) + 32 + (size_t)(g.N + 1) * 4;
+  const size_t nd = (size_t)g.N * g.kd, nu = (size_t)g.N * g.ku, sl_u = g.u_wT > 1 ? q.TL : 1;
+  q.smem = vec + (nd + nu + g.nnz) * 4 + ((size_t)(g.d_wT > 1 ? q.TL : 1) * (nd + g.nnz) + sl_u * nu) * 4;
+  q.smem2 = vec + (nd + nu + 2 * (size_t)g.nnz) * 2 + 8 + ((size_t)(g.d_wT > 1 ? q.TL + 1 : 1) * nd + sl_u * nu) * 4;
   if (q.smem > (size_t)p->max_smem_optin) return false;
   *out = q;
   return true;
@@ -672,13 +690,21 @@ bool cluster_eligible(const mga_plan* p, int dtype) {
 
 template <typename S, int RPT>
 static int cl_launch(mga_plan* p, const ClArgs<S>& a, const ClGeom& q, cudaStream_t st) {
-  auto kern = q.NP * q.TR <= 384 ? k_admm_cluster<S, RPT, 384> : k_admm_cluster<S, RPT, 1024>;
-  MGA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)q.smem));
+  // batches that oversubscribe the GPU with one cluster per SM group: two CTAs per SM when shared memory and registers allow
+  const bool two = a.B * q.CL > p->sm_count && q.NP * q.TR <= 384 && 2 * (q.smem2 + 1024) <= (size_t)p->max_smem_sm &&
+                   (size_t)a.N * a.kd < 65536 && !std::getenv("MGA_CLUSTER_ONE");
+  const size_t smem = two ? q.smem2 : q.smem;
+  const int nthr = q.NP * q.TR;
+  auto kern = nthr > 384 ? k_admm_cluster<S, RPT, 1024, 1>
+              : !two     ? k_admm_cluster<S, RPT, 384, 1>
+              : nthr <= 320 ? k_admm_cluster<S, RPT, 320, 2>      // PEMS04-sized graphs: 96 instead of 80 registers
+                            : k_admm_cluster<S, RPT, 384, 2>;
+  MGA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   if (q.CL > kClPortable) MGA_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(a.B * q.CL));
   cfg.blockDim = dim3(q.NP * q.TR);
-  cfg.dynamicSmemBytes = q.smem;
+  cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -718,7 +744,7 @@ static int cl_admm(mga_plan* p, const mga_params* m, const void* y, const void* 
   if (p->has_s2 && !std::getenv("MGA_CLUSTER_NATURAL")) {       // the streaming path's reordered tables (same entries, same order within a row)
     const Graph2& g2 = p->g2;
     a.nbr_d = g2.nbr_d; a.d_w = g2.w_d; a.nbr_u = g2.nbr_u; a.u_w = g2.w_u;
-    a.csr_ptr = g2.in_ptr; a.csr_src = g2.in_src; a.csr_w = g2.in_w; a.perm = g2.perm;
+    a.csr_ptr = g2.in_ptr; a.csr_src = g2.in_src; a.csr_w = g2.in_w; a.csr_slot = g2.in_slot; a.perm = g2.perm;
   }
   a.y = static_cast<const S*>(y); a.x_out = static_cast<S*>(x_out);
   a.mask = static_cast<const S*>(mask);

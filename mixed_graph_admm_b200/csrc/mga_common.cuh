@@ -62,6 +62,7 @@ struct Graph2 {
   const int* nbr_d; const float* w_d;     // (N, kd) internal ids, -1 = no neighbour
   const int* nbr_u; const float* w_u;     // (N, ku)
   const int* in_ptr; const int* in_src; const float* in_w;   // in-list of L_d^T (CSR, entries in scatter order)
+  const int* in_slot;                                        // in_w[e] == w_d[in_slot[e]]
   // time-tiled kernels: (row byte offset in the tile, weight bits) entries; the self link of the temporal graph is
   // in wself_d instead of the forward table / the in-list (in_self3 = 0: the in-list kept its self entries)
   int kd3, ku3, in_self3, in_ptr3_total;
@@ -106,6 +107,7 @@ struct mga_plan {
   int device = 0;
   int sm_count = 0;
   int max_smem_optin = 0;
+  int max_smem_sm = 0;         // shared memory of one SM (all resident CTAs together)
   size_t l2_bytes = 0;
   mga::GraphDev g{};
   std::vector<void*> owned;          // device allocations of the tables

@@ -215,6 +215,7 @@ int mga_plan_create(const mga_graph_desc* d, int device, mga_plan** out) {
   if (e != cudaSuccess) { delete p; return cuda_fail(e, "cudaGetDeviceProperties"); }
   p->sm_count = prop.multiProcessorCount;
   p->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+  p->max_smem_sm = (int)prop.sharedMemPerMultiprocessor;
   p->l2_bytes = (size_t)prop.l2CacheSize;
 
   GraphDev& g = p->g;
@@ -286,13 +287,17 @@ int mga_plan_create(const mga_graph_desc* d, int device, mga_plan** out) {
           o_w[(size_t)k * K + j] = w[(size_t)perm[k] * K + j];
         }
     };
-    std::vector<int> nd, nu, ip(N + 1, 0), is;
+    std::vector<int> nd, nu, ip(N + 1, 0), is, isl;
     std::vector<float> wd, wu, iw;
     remap(p->h_nbr_d, p->h_d_w, g.kd, nd, wd);
     remap(p->h_nbr_u, p->h_u_w, g.ku, nu, wu);
     for (int k = 0; k < N; ++k) {
       const int o = perm[k];
-      for (int e = p->h_csr_ptr[o]; e < p->h_csr_ptr[o + 1]; ++e) { is.push_back(inv[p->h_csr_src[e]]); iw.push_back(p->h_csr_w[e]); }
+      for (int e = p->h_csr_ptr[o]; e < p->h_csr_ptr[o + 1]; ++e) {
+        is.push_back(inv[p->h_csr_src[e]]);
+        iw.push_back(p->h_csr_w[e]);
+        isl.push_back(inv[slot[e] / g.kd] * g.kd + slot[e] % g.kd);      // the entry's place in the reordered forward table
+      }
       ip[k + 1] = (int)is.size();
     }
     Graph2& g2 = p->g2;
@@ -473,6 +478,7 @@ int mga_plan_create(const mga_graph_desc* d, int device, mga_plan** out) {
     if ((rc = upload(p, ip, &g2.in_ptr))) return fail(rc);
     if ((rc = upload(p, is, &g2.in_src))) return fail(rc);
     if ((rc = upload(p, iw, &g2.in_w))) return fail(rc);
+    if ((rc = upload(p, isl, &g2.in_slot))) return fail(rc);
     p->has_s2 = true;
   }
   p->pinned_bytes = 1 << 16;

@@ -3,6 +3,7 @@ adjacency, fp64, tolerance mode), timed through the public Python API on device 
 oracle (= the reference's torch path, bit-identical) on a bounded sample of the same windows.
 
     python profiles/bench_variants.py            # one JSON line per variant
+    python profiles/bench_variants.py knn_T24_fp64 time_varying_weights     # only these
 """
 import json
 import os
@@ -26,15 +27,23 @@ VARIANTS = [
     ("mask_interpolation", dict(use_kNN=True, k=K, u_sigma=50, d_sigma=50), torch.float32, 1024, 4, (5, 10), True),
     ("two_channels_C2", dict(use_kNN=True, k=K, u_sigma=50, d_sigma=50), torch.float32, 1024, 8, (5, 10), False, 2),
     ("knn_T24_fp64", dict(use_kNN=True, k=K, u_sigma=50, d_sigma=50), torch.float64, 1024, 16, (5, 10), False),
+    ("time_varying_weights", dict(use_kNN=True, k=K, u_sigma=50, d_sigma=50), torch.float32, 1024, 8, (5, 10), False, 1, True),
     ("notebook_B1_fp64_tolerance", dict(use_kNN=True, k=4, u_sigma=50, d_sigma=50), torch.float64, 1, 1, None, False),
 ]
 
 dev = torch.device("cuda", 0)
 gi = synth.road_graph(N, 1.1, seed=4)
 torch.set_num_threads(os.cpu_count() or 1)
+only = set(sys.argv[1:])
 for name, kw, dtype, B, b_cpu, fixed, use_mask, *rest in VARIANTS:
+    if only and name not in only:
+        continue
     Cn = rest[0] if rest else 1
     blk = ADMM_algorithm(gi, synth.admm_info(N), t_in=T_IN, T=T, device=dev, **kw)
+    if len(rest) > 1 and rest[1]:       # per-time-step weight tables (T,N,k) / (T-1,N,K): what the unrolling follow-up learns
+        gw = torch.Generator().manual_seed(11)
+        blk.u_ew = blk.u_ew * (0.8 + 0.4 * torch.rand(blk.u_ew.shape, generator=gw))
+        blk.d_ew = blk.d_ew * (0.8 + 0.4 * torch.rand(blk.d_ew.shape, generator=gw))
     if fixed:
         blk.max_ADMM_iter, blk.max_CG_iter, blk.CG_tol, blk.ADMM_tol = fixed[0], fixed[1], -1.0, -1.0
     else:

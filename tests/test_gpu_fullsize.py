@@ -278,6 +278,33 @@ def test_cluster_mode_notebook_call_is_one_launch():
     assert rel_err(x, g.t("x")) <= 1e-11
 
 
+def test_cluster_mode_batches_two_ctas_per_sm(monkeypatch):
+    """float64 batch that oversubscribes the GPU with clusters: the two-CTAs-per-SM instantiation (when shared memory allows)
+    against the one-per-SM one (MGA_CLUSTER_ONE=1; different register allocation, same arithmetic up to fma contraction)
+    and against the oracle on the first windows."""
+    from mixed_graph_admm_b200 import synth
+    from mixed_graph_admm_b200.ADMM import ADMM_algorithm
+    from oracle import admm_oracle as O
+    N, k, T, B = 170, 6, 12, 48
+    gi = synth.road_graph(N, 1.7, seed=8)
+    y = synth.signals(B, T // 2, N, seed=3, dtype=torch.float64)
+    xs = {}
+    for one in ("1", None):
+        if one:
+            monkeypatch.setenv("MGA_CLUSTER_ONE", one)
+        else:
+            monkeypatch.delenv("MGA_CLUSTER_ONE", raising=False)
+        blk = ADMM_algorithm(gi, synth.admm_info(N), use_kNN=True, k=k, u_sigma=50, d_sigma=50, t_in=T // 2, T=T)
+        blk.max_ADMM_iter, blk.max_CG_iter, blk.CG_tol, blk.ADMM_tol = 4, 8, -1.0, -1.0
+        xs[one] = blk.combined_loop(y.cuda(), print_info=False).cpu()
+        assert blk.last_mode == "device"
+    assert rel_err(xs[None], xs["1"]) <= 1e-14
+    og = O.OracleGraph(nbr=blk.connect_list, u_w=blk.u_ew, d_w=blk.d_ew)
+    prm = O.OracleParams(**synth.admm_info(N), t_in=T // 2, T=T)
+    tr = O.admm_combined(og, prm, y[:3], max_admm_iter=4, max_cg_iter=8, cg_tol=-1.0, admm_tol=-1.0)
+    assert rel_err(xs[None][:3], tr.x) <= 1e-12
+
+
 def test_cluster_mode_time_varying_weights_tolerance_call():
     """Per-time-step weight tables (T,N,k) / (T-1,N,K) with the notebooks' call pattern (B = 1, float64,
     tolerances): one cluster launch, the oracle's CG counts and iterates."""
