@@ -19,12 +19,20 @@ python profiles/notebook_call.py > $out/${tag}_notebook.json 2>/dev/null
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:k_admm_resident --launch-skip 1 -c 1 \
   -o $out/${tag}_resident -f python profiles/profile_step.py --mode resident --batch 1024 --steps 2 > $out/${tag}_resident_ncu.log 2>&1 && \
 python profiles/refresh_counters.py $out/${tag}_resident.ncu-rep 1024 $out/${tag}_resident_counters.json > /dev/null 2>&1
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:"k4_cg<0, 0" --launch-skip 8 -c 1 \
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:k4_cg --launch-skip 8 -c 1 \
   -o $out/${tag}_k4_t288 -f python profiles/bench_configs.py t288 --mode streaming --steps 1 > $out/${tag}_k4_ncu.log 2>&1
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:"k5_tail" --launch-skip 2 -c 1 \
   -o $out/${tag}_k5_t288 -f python profiles/bench_configs.py t288 --mode streaming --steps 1 > $out/${tag}_k5_ncu.log 2>&1
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:"k_admm_cluster" --launch-skip 2 -c 1 \
   -o $out/${tag}_cluster -f python profiles/notebook_call.py > $out/${tag}_cluster_ncu.log 2>&1
+# ---- summaries on the box (the reports together exceed what a call may bring back): keep the text, drop the big reports
+for k in resident k4_t288 k5_t288 cluster; do
+  rep=$out/${tag}_$k.ncu-rep
+  [ -f $rep ] || continue
+  { python profiles/ncu_summary.py $rep; echo; echo "---- stall samples by source line (ncu source page, -lineinfo)"; python profiles/ncu_lines.py $rep; } \
+    > $out/${tag}_${k}_ncu_summary.txt 2> $out/${tag}_${k}_ncu_summary.err
+  [ $k = resident ] || rm -f $rep
+done
 # ---- launch lists (time + DRAM bytes per launch)
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file $out/${tag}_launches_step.csv \
   python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-cg-probe --no-probes --min-timed-s 0 > $out/${tag}_launches_stdout.log 2>&1
