@@ -136,8 +136,8 @@ struct ClCtx {
       if (lane == 0) part[k * 32 + w] = t;
     }
     __syncthreads();
-    if (threadIdx.x < (unsigned)(CL * K)) {
-      const int r = threadIdx.x / K, k = threadIdx.x - r * K;
+    for (int e = threadIdx.x; e < CL * K; e += blockDim.x) {      // (a 32-thread CTA in a 16-CTA cluster has fewer threads than CL * K)
+      const int r = e / K, k = e - r * K;
       S t = 0;
       for (int q = 0; q < nw; ++q) t += part[k * 32 + q];
       cl.map_shared_rank(vs, r)[k * kClMaxCL + rank] = t;

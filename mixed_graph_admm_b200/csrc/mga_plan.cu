@@ -434,7 +434,9 @@ int mga_plan_create(const mga_graph_desc* d, int device, mga_plan** out) {
           const int ngrp = (N + 3) / 4;
           for (int pass = 0; pass * nw < ngrp; ++pass) {
             const int g0 = pass * nw, cnt = std::min(nw, ngrp - g0);
-            if (!(pass & 1) || cnt < nw) continue;             // (a partial last pass stays in order: its short group is the tail)
+            // (a partial last pass stays in order: its short group is the tail; so does a full last pass whose last group
+            // holds fewer than 4 rows, N % 4 != 0 - mirroring it would index past the N rows)
+            if (!(pass & 1) || cnt < nw || (g0 + cnt) * 4 > N) continue;
             for (int w = 0; w < cnt; ++w)
               for (int r = 0; r < 4; ++r) ord4[(g0 + w) * 4 + r] = ord[(g0 + cnt - 1 - w) * 4 + r];
           }

@@ -1,0 +1,93 @@
+"""Seeded random configurations of the whole path against the oracle: graph size, k, window length, t_in, batch, dtype, temporal
+graph variant (kNN scatter / physical adjacency / line graph / banded line graph), mask mode, channels, per-step weight
+tables, kernel mode, fixed counts or (B = 1) tolerances.  Every case runs `combined_loop` on the GPU and the oracle on the
+CPU on the same inputs (sizes the oracle finishes in a fraction of a second)."""
+import os
+import random
+
+import pytest
+import torch
+
+from _cases import max_rel, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _draw(seed):
+    r = random.Random(1000 + seed)
+    c = {"seed": seed}
+    c["N"] = r.choice([5, 9, 17, 31, 32, 33, 64, 95, 129, 170, 200, 257, 307, 320, 321, 400])
+    c["k"] = r.choice([2, 3, 4, 6, 8])
+    c["T"] = r.choice([4, 5, 8, 11, 12, 13, 16, 24, 25, 29, 31, 32, 33, 40])
+    c["t_in"] = r.choice([2, max(2, c["T"] // 2), max(2, c["T"] - 1)])
+    c["B"] = r.choice([1, 1, 2, 3, 5])
+    c["dtype"] = r.choice([torch.float32, torch.float32, torch.float64])
+    c["variant"] = r.choice(["knn", "knn", "knn", "physical", "line", "band"])
+    c["skip"] = r.choice([2, 3]) if c["variant"] == "band" else 1
+    c["mask"] = r.random() < 0.2
+    c["channels"] = r.choice([1, 1, 1, 2, 3])
+    c["varying"] = c["variant"] == "knn" and r.random() < 0.25
+    c["mode"] = r.choice(["auto", "auto", "streaming", "streaming_point"])
+    c["tol"] = c["B"] == 1 and c["channels"] == 1 and r.random() < 0.4
+    c["outer"], c["cg"] = r.choice([1, 2, 3]), r.choice([1, 3, 6, 8])
+    c["ratio"] = r.choice([1.1, 1.4, 1.7])
+    if c["mask"]:
+        c["B"] = 1                      # the reference's initial_interpolation only broadcasts for one window (ADMM.py:783-811)
+    return c
+
+
+# MGA_FUZZ_CASES=1000: a longer search; MGA_FUZZ_FIRST: first seed (a search split over processes, so that a device
+# fault in one case does not fail the cases after it)
+_FIRST = int(os.environ.get("MGA_FUZZ_FIRST", "0"))
+
+
+# seeds that found something (kept in every run): 39 - a 64-thread CTA in a 16-CTA cluster skipped reduction slots of the outer
+# stop test; 112 - N % 4 != 0 with a full last pass of k4_cg's row order wrote past the table (host heap)
+_FOUND = [39, 112]
+_SEEDS = list(range(_FIRST, _FIRST + int(os.environ.get("MGA_FUZZ_CASES", "32"))))
+
+
+@pytest.mark.parametrize("seed", _SEEDS + [s for s in _FOUND if s not in _SEEDS])
+def test_random_configuration_against_oracle(seed):
+    from mixed_graph_admm_b200 import synth
+    from mixed_graph_admm_b200.ADMM import ADMM_algorithm
+    from oracle import admm_oracle as O
+    c = _draw(seed)
+    N, k, T, t_in, B, dt = c["N"], min(c["k"], c["N"] - 1), c["T"], c["t_in"], c["B"], c["dtype"]
+    gi = synth.road_graph(N, c["ratio"], seed=seed, isolate_pair=N >= 9 and seed % 3 == 0)
+    kw = dict(t_in=t_in, T=T, mode=c["mode"])
+    if c["variant"] == "knn":
+        kw.update(use_kNN=True, k=k, u_sigma=50, d_sigma=50)
+    elif c["variant"] == "physical":
+        kw.update(use_kNN=False)
+    else:
+        kw.update(use_kNN=True, k=k, u_sigma=50, use_line_graph=True, skip_connection=c["skip"])
+    blk = ADMM_algorithm(gi, synth.admm_info(N), **kw)
+    gen = torch.Generator().manual_seed(seed)
+    if c["varying"]:
+        blk.u_ew = blk.u_ew * (0.8 + 0.4 * torch.rand(blk.u_ew.shape, generator=gen))
+        blk.d_ew = blk.d_ew * (0.8 + 0.4 * torch.rand(blk.d_ew.shape, generator=gen))
+    Cn = c["channels"]
+    rows = T if c["mask"] else t_in
+    y = torch.cat([synth.signals(B, rows, N, seed=seed + 7 * ch, dtype=dt, smooth=c["tol"]) for ch in range(Cn)], dim=-1).contiguous()
+    mask = None
+    if c["mask"]:
+        mask = (torch.rand(B, T, N, Cn, generator=gen) < 0.6).to(dt)
+        mask[:, :2] = 1                                   # every node keeps two observed steps: the interpolation slope is defined
+        y = y * mask
+    if c["tol"]:
+        blk.max_ADMM_iter, blk.max_CG_iter = 4, 60
+        blk.CG_tol, blk.ADMM_tol = (1e-8, 1e-6) if dt == torch.float64 else (1e-4, 1e-3)
+    else:
+        blk.max_ADMM_iter, blk.max_CG_iter, blk.CG_tol, blk.ADMM_tol = c["outer"], c["cg"], -1.0, -1.0
+    x = blk.combined_loop(y.cuda(), mask=None if mask is None else mask.cuda(), print_info=False).cpu()
+    og = O.OracleGraph(nbr=blk.connect_list, u_w=blk.u_ew, d_w=blk.d_ew, use_knn=c["variant"] != "physical",
+                       line_graph=c["variant"] in ("line", "band"), skip=c["skip"], time_list=getattr(blk, "time_list", None))
+    prm = O.OracleParams(**synth.admm_info(N), t_in=t_in, T=T)
+    tr = O.admm_combined(og, prm, y, mask=mask, max_admm_iter=int(blk.max_ADMM_iter), max_cg_iter=int(blk.max_CG_iter),
+                         cg_tol=float(blk.CG_tol), admm_tol=float(blk.ADMM_tol))
+    tol = 1e-5 if dt == torch.float32 else 1e-11
+    assert x.shape == tr.x.shape and x.dtype == dt, c
+    assert rel_err(x, tr.x) <= tol and max_rel(x, tr.x) <= 4 * tol, (c, rel_err(x, tr.x), max_rel(x, tr.x))
+    if c["tol"] and dt == torch.float64:
+        assert blk.CG_iter_x == list(tr.cg_iter_x) and blk.CG_iter_zu == list(tr.cg_iter_zu) and blk.CG_iter_zd == list(tr.cg_iter_zd), c
