@@ -44,15 +44,53 @@ _FIRST = int(os.environ.get("MGA_FUZZ_FIRST", "0"))
 # seeds that found something (kept in every run): 39 - a 64-thread CTA in a 16-CTA cluster skipped reduction slots of the outer
 # stop test; 112 - N % 4 != 0 with a full last pass of k4_cg's row order wrote past the table (host heap)
 _FOUND = [39, 112]
-_SEEDS = list(range(_FIRST, _FIRST + int(os.environ.get("MGA_FUZZ_CASES", "32"))))
+_SEEDS = list(range(_FIRST, _FIRST + int(os.environ.get("MGA_FUZZ_CASES", "24"))))
+
+
+def _draw_long(seed):
+    """Long windows and larger graphs: the time-tiled streaming kernels (k4_cg / k5_tail, k3 node tiles), graphs beyond one
+    CTA, the host-buffer entry (``y`` on the CPU), odd window lengths."""
+    r = random.Random(77000 + seed)
+    c = {"seed": seed, "long": True}
+    c["N"] = r.choice([30, 63, 127, 128, 255, 256, 307, 362, 450, 510, 600, 883, 1025, 1500])
+    c["k"] = r.choice([2, 4, 6, 8])
+    c["T"] = r.choice([41, 48, 64, 96, 100, 127, 144, 200, 288, 289])
+    c["t_in"] = r.choice([2, 12, c["T"] // 2, c["T"] - 1])
+    c["B"] = r.choice([1, 2, 3])
+    c["dtype"] = r.choice([torch.float32, torch.float32, torch.float32, torch.float64])
+    c["variant"] = r.choice(["knn", "knn", "knn", "physical", "line", "band"])
+    c["skip"] = r.choice([2, 3]) if c["variant"] == "band" else 1
+    c["mask"] = r.random() < 0.1
+    c["channels"] = r.choice([1, 1, 1, 1, 2])
+    c["varying"] = False
+    c["mode"] = r.choice(["auto", "auto", "streaming", "streaming_point"])
+    c["tol"] = False
+    c["outer"], c["cg"] = r.choice([1, 2]), r.choice([1, 2, 4])
+    c["ratio"] = r.choice([1.1, 1.4, 1.7])
+    c["host"] = r.random() < 0.3
+    if c["mask"]:
+        c["B"] = 1
+    return c
 
 
 @pytest.mark.parametrize("seed", _SEEDS + [s for s in _FOUND if s not in _SEEDS])
 def test_random_configuration_against_oracle(seed):
+    _run_case(_draw(seed))
+
+
+_LONG = list(range(_FIRST, _FIRST + int(os.environ.get("MGA_FUZZ_LONG_CASES", "6"))))
+
+
+@pytest.mark.parametrize("seed", _LONG)
+def test_random_long_window_against_oracle(seed):
+    _run_case(_draw_long(seed))
+
+
+def _run_case(c):
+    seed = c["seed"]
     from mixed_graph_admm_b200 import synth
     from mixed_graph_admm_b200.ADMM import ADMM_algorithm
     from oracle import admm_oracle as O
-    c = _draw(seed)
     N, k, T, t_in, B, dt = c["N"], min(c["k"], c["N"] - 1), c["T"], c["t_in"], c["B"], c["dtype"]
     gi = synth.road_graph(N, c["ratio"], seed=seed, isolate_pair=N >= 9 and seed % 3 == 0)
     kw = dict(t_in=t_in, T=T, mode=c["mode"])
@@ -80,7 +118,10 @@ def test_random_configuration_against_oracle(seed):
         blk.CG_tol, blk.ADMM_tol = (1e-8, 1e-6) if dt == torch.float64 else (1e-4, 1e-3)
     else:
         blk.max_ADMM_iter, blk.max_CG_iter, blk.CG_tol, blk.ADMM_tol = c["outer"], c["cg"], -1.0, -1.0
-    x = blk.combined_loop(y.cuda(), mask=None if mask is None else mask.cuda(), print_info=False).cpu()
+    if c.get("host"):                                   # the host-buffer entry point: y (and the mask) stay on the CPU
+        x = blk.combined_loop(y, mask=mask, print_info=False).cpu()
+    else:
+        x = blk.combined_loop(y.cuda(), mask=None if mask is None else mask.cuda(), print_info=False).cpu()
     og = O.OracleGraph(nbr=blk.connect_list, u_w=blk.u_ew, d_w=blk.d_ew, use_knn=c["variant"] != "physical",
                        line_graph=c["variant"] in ("line", "band"), skip=c["skip"], time_list=getattr(blk, "time_list", None))
     prm = O.OracleParams(**synth.admm_info(N), t_in=t_in, T=T)
