@@ -378,15 +378,20 @@ def two_loops(g: OracleGraph, prm: OracleParams, y, mask=None, max_admm_iter=150
                 rhs = op_ldr_t(g, gamma + prm.rho * phi) / 2 + prm.rho_u * zu / 2 - gu / 2 + hty
             else:
                 rhs = (prm.rho_u * zu + prm.rho_d * zd) / 2 - (gu + gd) / 2 + hty
+            assert not torch.isnan(rhs).any(), 'RHS_x has NaN value in ADMM loop'                    # ADMM.py:466
             x, it, al, be = cg(lambda v, mask=None: lhs_x(g, prm, v, mask), rhs, x_old, max_iter=max_cg_iter, tol=cg_tol,
                                first_kwargs={"mask": mask})
             tr.cg_iter_x.append(it); tr.alpha_x.append(al); tr.beta_x.append(be)
+            assert not torch.isnan(x).any(), 'RHS_x has NaN value in loop'                           # ADMM.py:473 (its wording)
+            assert not torch.isinf(x).any(), 'x has inf value in loop'                               # ADMM.py:474
             zu, it, al, be = cg(lambda v: lhs_zu(g, prm, v), gu / 2 + prm.rho_u / 2 * x, zu_old, max_iter=max_cg_iter, tol=cg_tol)
             tr.cg_iter_zu.append(it); tr.alpha_zu.append(al); tr.beta_zu.append(be)
+            assert not torch.isnan(zu).any(), 'zu has NaN value in loop'                             # ADMM.py:482
             if with_zd:
                 zd, it, al, be = cg(lambda v: lhs_zd(g, prm, v), gd / 2 + prm.rho_d / 2 * x, zd_old, max_iter=max_cg_iter,
                                     tol=cg_tol)
                 tr.cg_iter_zd.append(it); tr.alpha_zd.append(al); tr.beta_zd.append(be)
+                assert not torch.isnan(zd).any(), 'zd has NaN value in loop'                         # ADMM.py:490
             gu = gu + prm.rho_u * (x - zu)
             if with_zd:
                 gd = gd + prm.rho_d * (x - zd)

@@ -86,8 +86,35 @@ def test_random_long_window_against_oracle(seed):
     _run_case(_draw_long(seed))
 
 
+def _draw_api(seed):
+    """The other settings of the same entry points: the three ablations of ``combined_loop`` (ADMM.py:559-569, 371-399) and
+    ``two_loops`` (ADMM.py:410-508), small shapes, every temporal-graph variant but the banded one."""
+    r = random.Random(424200 + seed)
+    c = _draw(seed + 5000)
+    c["seed"] = seed
+    c["ablation"] = r.choice(["DGTV", "DGLR", "UT", "None"])
+    c["loop"] = r.choice(["combined", "combined", "two_loops"])
+    if c["variant"] == "band":
+        c["variant"], c["skip"] = "line", 1
+    c["tol"] = c["tol"] and c["loop"] == "combined"
+    c["varying"] = False
+    c["inner"] = r.choice([1, 2])
+    if c["loop"] == "two_loops":
+        c["mask"] = False
+    return c
+
+
+_API = list(range(_FIRST, _FIRST + int(os.environ.get("MGA_FUZZ_API_CASES", "12"))))
+
+
+@pytest.mark.parametrize("seed", _API)
+def test_random_ablation_and_two_loops_against_oracle(seed):
+    _run_case(_draw_api(seed))
+
+
 def _run_case(c):
     seed = c["seed"]
+    abl = c.get("ablation", "None")
     from mixed_graph_admm_b200 import synth
     from mixed_graph_admm_b200.ADMM import ADMM_algorithm
     from oracle import admm_oracle as O
@@ -100,7 +127,7 @@ def _run_case(c):
         kw.update(use_kNN=False)
     else:
         kw.update(use_kNN=True, k=k, u_sigma=50, use_line_graph=True, skip_connection=c["skip"])
-    blk = ADMM_algorithm(gi, synth.admm_info(N), **kw)
+    blk = ADMM_algorithm(gi, synth.admm_info(N), ablation=abl, **kw)
     gen = torch.Generator().manual_seed(seed)
     if c["varying"]:
         blk.u_ew = blk.u_ew * (0.8 + 0.4 * torch.rand(blk.u_ew.shape, generator=gen))
@@ -118,16 +145,42 @@ def _run_case(c):
         blk.CG_tol, blk.ADMM_tol = (1e-8, 1e-6) if dt == torch.float64 else (1e-4, 1e-3)
     else:
         blk.max_ADMM_iter, blk.max_CG_iter, blk.CG_tol, blk.ADMM_tol = c["outer"], c["cg"], -1.0, -1.0
+    og = O.OracleGraph(nbr=blk.connect_list, u_w=blk.u_ew, d_w=blk.d_ew, use_knn=c["variant"] != "physical",
+                       line_graph=c["variant"] in ("line", "band"), skip=c["skip"], time_list=getattr(blk, "time_list", None))
+    prm = O.OracleParams(**synth.admm_info(N), t_in=t_in, T=T, ablation=abl)
+    tol = 1e-5 if dt == torch.float32 else 1e-11
+    # The oracle first.  Without the DGLR term the x-system is diagonal: CG has solved it after two iterations and a fixed
+    # count keeps iterating on a residual that underflows to 0 -> alpha = 0 / 0, and the reference's NaN asserts fire
+    # (ADMM.py:575-606).  The product must then fail the same way (AssertionError), not return numbers.
+    two = c.get("loop") == "two_loops"
+    try:
+        if two:
+            tr = O.two_loops(og, prm, y, max_admm_iter=int(blk.max_ADMM_iter), max_inner_iter=c["inner"],
+                             max_cg_iter=int(blk.max_CG_iter), cg_tol=float(blk.CG_tol))
+        else:
+            tr = O.admm_combined(og, prm, y, mask=mask, max_admm_iter=int(blk.max_ADMM_iter), max_cg_iter=int(blk.max_CG_iter),
+                                 cg_tol=float(blk.CG_tol), admm_tol=float(blk.ADMM_tol))
+        if not torch.isfinite(tr.x).all():
+            raise AssertionError("oracle: non-finite x")
+    except AssertionError:
+        with pytest.raises(AssertionError):
+            if two:
+                blk.max_inner_iter = c["inner"]
+                blk.two_loops(y.cuda())
+            else:
+                blk.combined_loop(y.cuda(), mask=None if mask is None else mask.cuda(), print_info=False)
+        return
+    if two:
+        blk.max_inner_iter = c["inner"]
+        assert blk.two_loops(y.cuda()) is None
+        x = blk.last_iterates["x"].cpu()
+        assert rel_err(x, tr.x) <= tol and max_rel(x, tr.x) <= 4 * tol, (c, rel_err(x, tr.x), max_rel(x, tr.x))
+        assert rel_err(blk.last_iterates["zu"].cpu(), tr.zu) <= tol, c
+        return
     if c.get("host"):                                   # the host-buffer entry point: y (and the mask) stay on the CPU
         x = blk.combined_loop(y, mask=mask, print_info=False).cpu()
     else:
         x = blk.combined_loop(y.cuda(), mask=None if mask is None else mask.cuda(), print_info=False).cpu()
-    og = O.OracleGraph(nbr=blk.connect_list, u_w=blk.u_ew, d_w=blk.d_ew, use_knn=c["variant"] != "physical",
-                       line_graph=c["variant"] in ("line", "band"), skip=c["skip"], time_list=getattr(blk, "time_list", None))
-    prm = O.OracleParams(**synth.admm_info(N), t_in=t_in, T=T)
-    tr = O.admm_combined(og, prm, y, mask=mask, max_admm_iter=int(blk.max_ADMM_iter), max_cg_iter=int(blk.max_CG_iter),
-                         cg_tol=float(blk.CG_tol), admm_tol=float(blk.ADMM_tol))
-    tol = 1e-5 if dt == torch.float32 else 1e-11
     assert x.shape == tr.x.shape and x.dtype == dt, c
     assert rel_err(x, tr.x) <= tol and max_rel(x, tr.x) <= 4 * tol, (c, rel_err(x, tr.x), max_rel(x, tr.x))
     if c["tol"] and dt == torch.float64:
