@@ -350,14 +350,20 @@ __global__ void __launch_bounds__(kFlat) k2_pupdate(Graph2 g, int64_t B, int it,
 // x += alpha p ; r -= alpha Ap ; RR(k+1) += r.r   (ADMM.py:350-355)
 // x_in: the iterate this step starts from - the warm start x0 in the first iteration (read in place, no copy of
 // the warm start is made), x itself afterwards
+// XUP = false: r only - the x update of this iteration is applied by the NEXT iteration's k4_cg, which stages p anyway
+// (K4Args::xd_in / xd_out): 12 instead of 24 B/pt here, 8 B/pt more in a kernel that is not bound by HBM
+template <bool XUP = true>
 __global__ void __launch_bounds__(kFlat) k2_xr(Graph2 g, int64_t B, int it, const float* x_in, float* x, float* __restrict__ r,
                                               const float* __restrict__ p, const float* __restrict__ ap, double* __restrict__ dots) {
   const Chunk k = locate_flat(g);
   float dot = 0.f;
   if (k.ok) {
     const float alpha = (float)dots[(size_t)(2 * it) * B + k.b] / (float)dots[(size_t)(2 * it + 1) * B + k.b];
-    const float4 xv = ld4(x_in, k.g), pv = ld4(p, k.g), rv = ld4(r, k.g), av = ld4(ap, k.g);
-    st4(x, k.g, make_float4(xv.x + alpha * pv.x, xv.y + alpha * pv.y, xv.z + alpha * pv.z, xv.w + alpha * pv.w));
+    const float4 rv = ld4(r, k.g), av = ld4(ap, k.g);
+    if (XUP) {
+      const float4 xv = ld4(x_in, k.g), pv = ld4(p, k.g);
+      st4(x, k.g, make_float4(xv.x + alpha * pv.x, xv.y + alpha * pv.y, xv.z + alpha * pv.z, xv.w + alpha * pv.w));
+    }
     const float4 rn = make_float4(rv.x - alpha * av.x, rv.y - alpha * av.y, rv.z - alpha * av.z, rv.w - alpha * av.w);
     st4(r, k.g, rn);
     dot = (rn.x * rn.x + rn.y * rn.y) + (rn.z * rn.z + rn.w * rn.w);
@@ -1136,7 +1142,7 @@ struct K4Plan {
 static size_t k4_smem_bytes(const Graph2& g, int nstage, int rows_tile, int sys) {
   const size_t N = g.N, kf = sys == 0 ? g.kd3 : g.ku3, n_in = sys == 0 ? g.in_ptr3_total : 0;
   return (size_t)nstage * 2 * rows_tile * kCB4 * 16 + 4 * (size_t)rows_tile * 16 + 5 * N * 4 + (2 * N + 2) * 4 + N * kf * 8 +
-         n_in * 8 + (2 * (size_t)nstage + 2) * 8 + (size_t)nstage * 4 + 16;
+         n_in * 8 + (2 * (size_t)nstage + 2) * 8 + 2 * (size_t)nstage * 4 + 16;
 }
 
 static K4Plan k4_plan(const mga_plan* p) {
@@ -1257,15 +1263,23 @@ static int cg4(mga_plan* p, const K4Plan& k4, int system, const float* rhs, cons
   if (rc) return rc;
   int cur = 0;                                   // p_old = w.p (never read in the first iteration), p_new = w.p2
   float* pbuf[2] = {w.p, w.p2};
+  // measured at T = 288, B = 256 (profiles/r02_defer_x.txt): x / z_d iteration 202.7 -> 197.2 us, z_u 152.6 -> 156.1 us (its k4_cg has
+  // no second gather phase to hide the extra loads behind): on for the two-hop systems only.  MGA_S4_DEFER_X = 0 off, 2 all systems
+  static const int defer_mode = [] { const char* e = std::getenv("MGA_S4_DEFER_X"); return e ? std::atoi(e) : 1; }();
+  const bool defer_x = defer_mode == 2 || (defer_mode == 1 && system != MGA_SYS_ZU);
   for (int it = 0; it < n_cg; ++it) {
     ka.it = it; ka.rhs = nullptr; ka.out = w.ap;
     ka.slot = w.dots + (size_t)(2 * it + 1) * B;
+    // x += alpha p of iteration it - 1 rides on this launch (it reads that p as its p_old); the last iteration's is k2_xr's
+    ka.xd_in = (defer_x && it > 0) ? (it == 1 ? x0 : x) : nullptr;
+    ka.xd_out = (defer_x && it > 0) ? x : nullptr;
     if (system == MGA_SYS_ZU)
       rc = it == 0 ? k4_launch_k<1, 1>(p, k4, m_it[cur], ka, st) : k4_launch_k<1, 0>(p, k4, m_it[cur], ka, st);
     else
       rc = it == 0 ? k4_launch_k<0, 1>(p, k4, m_it[cur], ka, st) : k4_launch_k<0, 0>(p, k4, m_it[cur], ka, st);
     if (rc) return rc;
-    k2_xr<<<fgrid, kFlat, 0, st>>>(g, B, it, it == 0 ? x0 : x, x, w.r, pbuf[cur ^ 1], w.ap, w.dots);
+    if (defer_x && it + 1 < n_cg) k2_xr<false><<<fgrid, kFlat, 0, st>>>(g, B, it, nullptr, nullptr, w.r, nullptr, w.ap, w.dots);
+    else k2_xr<true><<<fgrid, kFlat, 0, st>>>(g, B, it, (it == 0 || (defer_x && n_cg == 1)) ? x0 : x, x, w.r, pbuf[cur ^ 1], w.ap, w.dots);
     MGA_LAUNCH_CHECK("k2_xr");
     cur ^= 1;
   }
@@ -1381,7 +1395,7 @@ static int cg2(mga_plan* p, int system, const mga_params* m, const float* rhs, c
         else MGA_K3_BY_K(g.kd3, MGA_K3_PLDR_NEXT);
         MGA_K3_LAUNCH((k3_ldrt_lhs<0>), g.smem3_in, g, B, p_new, w.qs, nullptr, w.ap, pap, a, c, xsys);
       }
-      k2_xr<<<fgrid, kFlat, 0, st>>>(g, B, it, it == 0 ? x0 : x, x, w.r, p_new, w.ap, w.dots);
+      k2_xr<true><<<fgrid, kFlat, 0, st>>>(g, B, it, it == 0 ? x0 : x, x, w.r, p_new, w.ap, w.dots);
       MGA_LAUNCH_CHECK("k2_xr");
       std::swap(p_old, p_new);
     }
@@ -1409,7 +1423,7 @@ static int cg2(mga_plan* p, int system, const mga_params* m, const float* rhs, c
       k2_ldrt_lhs<0><<<grid, blk, 0, st>>>(g, w.p, w.qs, nullptr, w.ap, pap, a, c, xsys);
       MGA_LAUNCH_CHECK("k2_ldrt_lhs");
     }
-    k2_xr<<<fgrid, kFlat, 0, st>>>(g, B, it, it == 0 ? x0 : x, x, w.r, w.p, w.ap, w.dots);
+    k2_xr<true><<<fgrid, kFlat, 0, st>>>(g, B, it, it == 0 ? x0 : x, x, w.r, w.p, w.ap, w.dots);
     MGA_LAUNCH_CHECK("k2_xr");
   }
   }

@@ -45,6 +45,10 @@ struct K4Args {
   double* slot;          // (B): where this launch's dot product goes
   float a, cc;
   int xsys;
+  // deferred x update of the PREVIOUS iteration (SRC 0): x_out = x_in + alpha(it-1) p_old, with the p_old tile this launch
+  // stages anyway - k2_xr then only updates r (12 instead of 24 B/pt).  NULL: off.
+  const float* xd_in;
+  float* xd_out;
 };
 
 __device__ __forceinline__ uint32_t s2u(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -117,7 +121,7 @@ k4_cg(const __grid_constant__ K4Maps maps, const Graph2 g, const K4Args a) {
   uint64_t* empty = bars + a.nstage;
   uint64_t* hfull = bars + 2 * a.nstage;                             // the halo buffer: one barrier pair
   uint64_t* hempty = hfull + 1;
-  float* beta_s = reinterpret_cast<float*>(hempty + 1);              // (nstage) beta of the window of the staged tile
+  float* beta_s = reinterpret_cast<float*>(hempty + 1);              // (nstage) beta of the window of the staged tile, then (nstage) alpha of the previous iteration
 
   // ---- barrier init, then the producer starts fetching while the consumers stage the graph tables
   if (tid == 0) {
@@ -142,7 +146,11 @@ k4_cg(const __grid_constant__ K4Maps maps, const Graph2 g, const K4Args a) {
         mbar_wait(empty + s, ph ^ 1);                                // first pass over the stages: free at once
         // beta of the tile's window travels with the stage: this lane can afford the load latency, the consumers cannot
         // (written before the arrive on `full`, whose release / acquire pair publishes it)
-        if (SRC == 0) beta_s[s] = (float)a.dots[(size_t)(2 * a.it) * a.B + b] / (float)a.dots[(size_t)(2 * a.it - 2) * a.B + b];   // ADMM.py:356
+        if (SRC == 0) {
+          beta_s[s] = (float)a.dots[(size_t)(2 * a.it) * a.B + b] / (float)a.dots[(size_t)(2 * a.it - 2) * a.B + b];   // ADMM.py:356
+          if (a.xd_out)      // alpha of the previous iteration, formed as k2_xr forms it (ADMM.py:351)
+            beta_s[a.nstage + s] = (float)a.dots[(size_t)(2 * a.it - 2) * a.B + b] / (float)a.dots[(size_t)(2 * a.it - 1) * a.B + b];
+        }
         mbar_expect_tx(full + s, stage_bytes);
         float4* tR = tiles + (size_t)s * 2 * tile_f4;
         float4* tP = tR + tile_f4;
@@ -197,17 +205,51 @@ k4_cg(const __grid_constant__ K4Maps maps, const Graph2 g, const K4Args a) {
     const bool cok = c < C4;
     float4* tR = tiles + (size_t)s * 2 * tile_f4;
     float4* tP = tR + tile_f4;
+    // deferred x update: this thread's chunks of x are requested before the wait for the tile (N <= NC: at most 8 items)
+    constexpr int kXI = 8;
+    float4 xv[kXI];
+    const bool xdef = SRC == 0 && a.xd_out != nullptr;
+    const size_t xw0 = (size_t)b * (size_t)(N * C4) + c;
+    if (xdef && cok) {
+      const float4* xi = reinterpret_cast<const float4*>(a.xd_in) + xw0;
+#pragma unroll
+      for (int j = 0; j < kXI; ++j) {
+        const int item = tid + j * NC;
+        if (item < N * kCB4) xv[j] = __ldcs(xi + (size_t)(item >> 3) * C4);
+      }
+    }
     mbar_wait(full + s, ph);
     const float beta = SRC == 0 ? beta_s[s] : 0.f;
 
-    // ---- phase A: p' = r + beta p, in place
+    // ---- phase A: p' = r + beta p, in place (and x += alpha_prev p with the old p, before phase B overwrites its tile)
     if (SRC == 0 && !(MGA_K4_X & 32)) {
-      for (int item = tid; item < N * kCB4; item += NC) {
-        float4 v = tR[item];
-        const float4 q = tP[item];
-        v.x += beta * q.x; v.y += beta * q.y; v.z += beta * q.z; v.w += beta * q.w;
-        tR[item] = v;
-        if (SYS == 0 && col == 0) p0[item >> 3] = v.x;
+      if (xdef) {
+        const float al = beta_s[a.nstage + s];
+        float4* xo = reinterpret_cast<float4*>(a.xd_out) + xw0;
+#pragma unroll
+        for (int j = 0; j < kXI; ++j) {
+          const int item = tid + j * NC;
+          if (item < N * kCB4) {
+            float4 v = tR[item];
+            const float4 q = tP[item];
+            v.x += beta * q.x; v.y += beta * q.y; v.z += beta * q.z; v.w += beta * q.w;
+            tR[item] = v;
+            if (SYS == 0 && col == 0) p0[item >> 3] = v.x;
+            if (cok) {
+              float4 u = xv[j];
+              u.x += al * q.x; u.y += al * q.y; u.z += al * q.z; u.w += al * q.w;
+              __stcs(xo + (size_t)(item >> 3) * C4, u);
+            }
+          }
+        }
+      } else {
+        for (int item = tid; item < N * kCB4; item += NC) {
+          float4 v = tR[item];
+          const float4 q = tP[item];
+          v.x += beta * q.x; v.y += beta * q.y; v.z += beta * q.z; v.w += beta * q.w;
+          tR[item] = v;
+          if (SYS == 0 && col == 0) p0[item >> 3] = v.x;
+        }
       }
     } else if (SYS == 0 && col == 0) {
       for (int item = tid; item < N * kCB4; item += NC) p0[item >> 3] = tR[item].x;
