@@ -498,10 +498,25 @@ __device__ __forceinline__ void tile_issue(const Graph2& g, const Item3& t, int 
   cp_async_commit();
 }
 
+// xd_in / xd_out (SRC 0): the deferred x update of the previous iteration, x_out = x_in + alpha(it - 1) p_old for the tile's OWN
+// rows - p_old is staged here anyway, and k2_xr then only updates r (see k4_cg, mga_stream4.cuh).  The thread's chunks of x are
+// requested before the wait for the tile's copies, so both round trips overlap; at most kXR3 own rows per thread (host check).
+constexpr int kXR3 = 8;
 template <int SRC>
 __device__ __forceinline__ void tile_finish(const Graph2& g, int64_t B, int it, const Item3& t, int cur, float* __restrict__ p_new,
-                                            const double* __restrict__ dots, const Smem3& s, bool want_halo) {
+                                            const double* __restrict__ dots, const Smem3& s, bool want_halo,
+                                            const float* xd_in = nullptr, float* xd_out = nullptr) {
   const int CB = blockDim.x, NBt = blockDim.y, tx = threadIdx.x;
+  float4 xv[kXR3];
+  const bool xdef = SRC == 0 && xd_out != nullptr && t.c0 + tx < g.C4;
+  if (xdef) {
+    const float4* xi = reinterpret_cast<const float4*>(xd_in) + (size_t)t.b * (size_t)(g.N * g.C4) + (size_t)t.n0 * g.C4 + t.c0 + tx;
+#pragma unroll
+    for (int j = 0; j < kXR3; ++j) {
+      const int n = threadIdx.y + j * NBt;
+      if (n < t.nt) xv[j] = __ldcs(xi + (size_t)n * g.C4);
+    }
+  }
   const int c = t.c0 + tx, cn = t.c0 + CB;
   const bool cok = c < g.C4, last = want_halo && tx == CB - 1, hok = cn < g.C4;
   float4* ow = reinterpret_cast<float4*>(p_new) + (size_t)t.b * (size_t)(g.N * g.C4) + (cok ? c : 0);
@@ -523,6 +538,20 @@ __device__ __forceinline__ void tile_finish(const Graph2& g, int64_t B, int it, 
     }
     if (SRC == 0 || !cok) t1[n * CB] = v;
     if (last) h1[n] = hok ? (SRC == 0 ? h1[n] + beta * s.halo2[n] : h1[n]) : 0.f;
+  }
+  if (xdef) {
+    const float al = (float)dots[(size_t)(2 * it - 2) * B + t.b] / (float)dots[(size_t)(2 * it - 1) * B + t.b];   // as k2_xr forms it (ADMM.py:351)
+    float4* xo = reinterpret_cast<float4*>(xd_out) + (size_t)t.b * (size_t)(g.N * g.C4) + (size_t)t.n0 * g.C4 + c;
+#pragma unroll
+    for (int j = 0; j < kXR3; ++j) {
+      const int n = threadIdx.y + j * NBt;
+      if (n < t.nt) {
+        const float4 q = t2[n * CB];
+        float4 u = xv[j];
+        u.x += al * q.x; u.y += al * q.y; u.z += al * q.z; u.w += al * q.w;
+        __stcs(xo + (size_t)n * g.C4, u);
+      }
+    }
   }
 }
 
@@ -577,7 +606,8 @@ namespace mga {
 template <int SRC, int K>
 __global__ void __launch_bounds__(1024, 1) k3_p_ldr(Graph2 g, int64_t B, int it, const float* __restrict__ r,
                                                    const float* __restrict__ p_old, float* __restrict__ p_new,
-                                                   float* __restrict__ qs, const double* __restrict__ dots) {
+                                                   float* __restrict__ qs, const double* __restrict__ dots,
+                                                   const float* xd_in, float* xd_out) {
   extern __shared__ float4 s3[];
   const int CB = blockDim.x, NBt = blockDim.y, tx = threadIdx.x;
   const Smem3 s = carve3(g, s3, CB, false);
@@ -605,7 +635,7 @@ __global__ void __launch_bounds__(1024, 1) k3_p_ldr(Graph2 g, int64_t B, int it,
       }
       tile_issue<SRC>(g, t, 0, r, p_old, s, true);
     }
-    tile_finish<SRC>(g, B, it, t, cur, p_new, dots, s, true);
+    tile_finish<SRC>(g, B, it, t, cur, p_new, dots, s, true, xd_in, xd_out);
     __syncthreads();
     if (db && tl + stride < last) tile_issue<SRC>(g, item3(g, B, tl + stride, g.extp_d), cur ^ 1, r, p_old, s, true);
     if (c >= g.C4) continue;
@@ -767,7 +797,8 @@ template <int SRC, int MODE, int K>
 __global__ void __launch_bounds__(1024, 1) k3_lu(Graph2 g, int64_t B, int it, const float* __restrict__ r,
                                                 const float* __restrict__ p_old, float* __restrict__ p_new,
                                                 const float* __restrict__ rhs, float* __restrict__ out,
-                                                const double* __restrict__ dots, double* __restrict__ slot, float a, float cc) {
+                                                const double* __restrict__ dots, double* __restrict__ slot, float a, float cc,
+                                                const float* xd_in, float* xd_out) {
   extern __shared__ float4 s3[];
   const int CB = blockDim.x, NBt = blockDim.y, tx = threadIdx.x;
   const Smem3 s = carve3(g, s3, CB, false);
@@ -795,7 +826,7 @@ __global__ void __launch_bounds__(1024, 1) k3_lu(Graph2 g, int64_t B, int it, co
       }
       tile_issue<SRC>(g, t, 0, r, p_old, s, false);
     }
-    tile_finish<SRC>(g, B, it, t, cur, p_new, dots, s, false);
+    tile_finish<SRC>(g, B, it, t, cur, p_new, dots, s, false, xd_in, xd_out);
     __syncthreads();
     if (db && tl + stride < last) tile_issue<SRC>(g, item3(g, B, tl + stride, g.extp_u), cur ^ 1, r, p_old, s, false);
     const float4* tile = s.tile + cur * s.stride_t;
@@ -1263,9 +1294,9 @@ static int cg4(mga_plan* p, const K4Plan& k4, int system, const float* rhs, cons
   if (rc) return rc;
   int cur = 0;                                   // p_old = w.p (never read in the first iteration), p_new = w.p2
   float* pbuf[2] = {w.p, w.p2};
-  // measured at T = 288, B = 256 (profiles/r02_defer_x.txt): x / z_d iteration 202.7 -> 197.2 us, z_u 152.6 -> 156.1 us (its k4_cg has
-  // no second gather phase to hide the extra loads behind): on for the two-hop systems only.  MGA_S4_DEFER_X = 0 off, 2 all systems
-  static const int defer_mode = [] { const char* e = std::getenv("MGA_S4_DEFER_X"); return e ? std::atoi(e) : 1; }();
+  // measured at T = 288, B = 256 (profiles/r02_defer_x.txt, same box): x / z_d iteration 214.4 -> 194.2 us, z_u 151.6 -> 147.4 us,
+  // step 34.04 -> 32.04 ms.  MGA_S4_DEFER_X = 0 off, 1 two-hop systems only, 2 (default) all systems
+  static const int defer_mode = [] { const char* e = std::getenv("MGA_S4_DEFER_X"); return e ? std::atoi(e) : 2; }();
   const bool defer_x = defer_mode == 2 || (defer_mode == 1 && system != MGA_SYS_ZU);
   for (int it = 0; it < n_cg; ++it) {
     ka.it = it; ka.rhs = nullptr; ka.out = w.ap;
@@ -1374,28 +1405,36 @@ static int cg2(mga_plan* p, int system, const mga_params* m, const float* rhs, c
 #define MGA_K3_BY_K(K, macro) \
     do { if ((K) == 4) { macro(4); } else if ((K) == 6) { macro(6); } else if ((K) == 8) { macro(8); } else { macro(0); } } while (0)
     if (system == MGA_SYS_ZU) {
-#define MGA_K3_LU_INIT(K) MGA_K3_LAUNCH((k3_lu<2, 1, K>), g.smem3_u, g, B, 0, x0, nullptr, nullptr, rhs, w.r, w.dots, w.dots, a, c)
+#define MGA_K3_LU_INIT(K) MGA_K3_LAUNCH((k3_lu<2, 1, K>), g.smem3_u, g, B, 0, x0, nullptr, nullptr, rhs, w.r, w.dots, w.dots, a, c, nullptr, nullptr)
       MGA_K3_BY_K(g.ku3, MGA_K3_LU_INIT);
     } else {
-#define MGA_K3_PLDR_INIT(K) MGA_K3_LAUNCH((k3_p_ldr<2, K>), g.smem3_d, g, B, 0, x0, nullptr, nullptr, w.qs, w.dots)
+#define MGA_K3_PLDR_INIT(K) MGA_K3_LAUNCH((k3_p_ldr<2, K>), g.smem3_d, g, B, 0, x0, nullptr, nullptr, w.qs, w.dots, nullptr, nullptr)
       MGA_K3_BY_K(g.kd3, MGA_K3_PLDR_INIT);
       MGA_K3_LAUNCH((k3_ldrt_lhs<1>), g.smem3_in, g, B, x0, w.qs, rhs, w.r, w.dots, a, c, xsys);
     }
+    // deferred x update as in cg4: iteration it - 1's x += alpha p rides on this iteration's tile kernel (its p_old), k2_xr<false>
+    // updates r only; own rows per thread must fit the kernel's register array.  MGA_S3_DEFER_X=0: off
+    static const bool defer_env = [] { const char* e = std::getenv("MGA_S3_DEFER_X"); return !e || std::atoi(e) != 0; }();
+    const int own_rows = g.ntile3 > 1 ? g.NT3 : g.N;
+    const bool defer_x = defer_env && !g.db3 && (own_rows + g.NB3t - 1) / g.NB3t <= kXR3;
     for (int it = 0; it < n_cg; ++it) {
       double* pap = w.dots + (size_t)(2 * it + 1) * B;
+      const float* xd_in = (defer_x && it > 0) ? (it == 1 ? x0 : x) : nullptr;
+      float* xd_out = (defer_x && it > 0) ? x : nullptr;
       if (system == MGA_SYS_ZU) {
-#define MGA_K3_LU_FIRST(K) MGA_K3_LAUNCH((k3_lu<1, 0, K>), g.smem3_u, g, B, it, w.r, p_old, p_new, nullptr, w.ap, w.dots, pap, a, c)
-#define MGA_K3_LU_NEXT(K) MGA_K3_LAUNCH((k3_lu<0, 0, K>), g.smem3_u, g, B, it, w.r, p_old, p_new, nullptr, w.ap, w.dots, pap, a, c)
+#define MGA_K3_LU_FIRST(K) MGA_K3_LAUNCH((k3_lu<1, 0, K>), g.smem3_u, g, B, it, w.r, p_old, p_new, nullptr, w.ap, w.dots, pap, a, c, nullptr, nullptr)
+#define MGA_K3_LU_NEXT(K) MGA_K3_LAUNCH((k3_lu<0, 0, K>), g.smem3_u, g, B, it, w.r, p_old, p_new, nullptr, w.ap, w.dots, pap, a, c, xd_in, xd_out)
         if (it == 0) MGA_K3_BY_K(g.ku3, MGA_K3_LU_FIRST);
         else MGA_K3_BY_K(g.ku3, MGA_K3_LU_NEXT);
       } else {
-#define MGA_K3_PLDR_FIRST(K) MGA_K3_LAUNCH((k3_p_ldr<1, K>), g.smem3_d, g, B, it, w.r, p_old, p_new, w.qs, w.dots)
-#define MGA_K3_PLDR_NEXT(K) MGA_K3_LAUNCH((k3_p_ldr<0, K>), g.smem3_d, g, B, it, w.r, p_old, p_new, w.qs, w.dots)
+#define MGA_K3_PLDR_FIRST(K) MGA_K3_LAUNCH((k3_p_ldr<1, K>), g.smem3_d, g, B, it, w.r, p_old, p_new, w.qs, w.dots, nullptr, nullptr)
+#define MGA_K3_PLDR_NEXT(K) MGA_K3_LAUNCH((k3_p_ldr<0, K>), g.smem3_d, g, B, it, w.r, p_old, p_new, w.qs, w.dots, xd_in, xd_out)
         if (it == 0) MGA_K3_BY_K(g.kd3, MGA_K3_PLDR_FIRST);
         else MGA_K3_BY_K(g.kd3, MGA_K3_PLDR_NEXT);
         MGA_K3_LAUNCH((k3_ldrt_lhs<0>), g.smem3_in, g, B, p_new, w.qs, nullptr, w.ap, pap, a, c, xsys);
       }
-      k2_xr<true><<<fgrid, kFlat, 0, st>>>(g, B, it, it == 0 ? x0 : x, x, w.r, p_new, w.ap, w.dots);
+      if (defer_x && it + 1 < n_cg) k2_xr<false><<<fgrid, kFlat, 0, st>>>(g, B, it, nullptr, nullptr, w.r, nullptr, w.ap, w.dots);
+      else k2_xr<true><<<fgrid, kFlat, 0, st>>>(g, B, it, it == 0 ? x0 : x, x, w.r, p_new, w.ap, w.dots);
       MGA_LAUNCH_CHECK("k2_xr");
       std::swap(p_old, p_new);
     }

@@ -218,6 +218,19 @@ k4_cg(const __grid_constant__ K4Maps maps, const Graph2 g, const K4Args a) {
         if (item < N * kCB4) xv[j] = __ldcs(xi + (size_t)(item >> 3) * C4);
       }
     }
+    // ... and the chunks of the CTA's NEXT tile are pulled into L2 now: the loads above are consumed right behind the wait
+    // (the tile itself is staged a whole item ahead), so an HBM round trip per tile would be exposed - measured +34 us per launch
+    if (xdef && tl + (int)gridDim.x < a.total) {
+      const int tn = tl + (int)gridDim.x, bn = tn / a.tiles, cn = (tn - bn * a.tiles) * kCB4 + col;
+      if (cn < C4) {
+        const float4* xn = reinterpret_cast<const float4*>(a.xd_in) + (size_t)bn * (size_t)(N * C4) + cn;
+#pragma unroll
+        for (int j = 0; j < kXI; ++j) {
+          const int item = tid + j * NC;
+          if (item < N * kCB4) asm volatile("prefetch.global.L2 [%0];" ::"l"(xn + (size_t)(item >> 3) * C4));
+        }
+      }
+    }
     mbar_wait(full + s, ph);
     const float beta = SRC == 0 ? beta_s[s] : 0.f;
 
