@@ -1,4 +1,5 @@
 #!/bin/bash
+# (needs the experiment builds --tag=ldcg0 -DMGA_RES_LDCG=0 / --tag=nofence and the MGA_HOST_COEF_CHUNK patch; none is in the shipped library - DESIGN 4.6)
 # what the PIPE instantiation of the resident kernel pays for (timing only; the variants are not correct builds):
 # ldcg0 = y through L1 (plain loads), nofence = hand-over without fence + barrier
 for v in main ldcg0 nofence; do
