@@ -40,8 +40,11 @@ def _fake_plan_init(self, desc, device):
 
 A._Plan.__init__ = _fake_plan_init
 A._device_of = lambda a: torch.device("cpu")
-for fam, draw, cnt in (("s", fz._draw, n_short), ("l", fz._draw_long, n_long)):
-    for seed in range(cnt):
+total = 0
+for fam, draw, seeds in (("s", fz._draw, list(range(n_short)) + [f for f in fz._FOUND if f >= n_short]),   # (+ the seeds that found bugs)
+                         ("l", fz._draw_long, list(range(n_long)))):
+    for seed in seeds:
+        total += 1
         c = draw(seed)
         N, k = c["N"], min(c["k"], c["N"] - 1)
         gi = synth.road_graph(N, c["ratio"], seed=seed, isolate_pair=N >= 9 and seed % 3 == 0)
@@ -62,4 +65,4 @@ for fam, draw, cnt in (("s", fz._draw, n_short), ("l", fz._draw_long, n_long)):
             blk._plan(c["channels"])
         except _Dumped:
             pass
-print("dumped", n_short + n_long, "descriptors to", out_dir)
+print("dumped", total, "descriptors to", out_dir)
